@@ -1,0 +1,145 @@
+/*
+ * spimcuda.h -- C ABI of libspimcuda.so, the B200 (sm_100a) replacement for the
+ * device side of spimagine's volume renderer.
+ *
+ * Every entry point below stands in for one group of gputools / pyopencl calls
+ * that the reference's spimagine/volumerender/volumerender.py makes (file:line
+ * cited per function, relative to the reference tree).  Plain pointers and
+ * sizes only; all functions return 0 on success or a negative SPV_E* /
+ * positive cudaError_t code, never throw, never exit.  A context is not
+ * thread-safe; distinct contexts are independent.
+ */
+#ifndef SPIMCUDA_H_
+#define SPIMCUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPV_VERSION 100
+
+#if defined(__GNUC__)
+#define SPV_API __attribute__((visibility("default")))
+#else
+#define SPV_API
+#endif
+
+typedef struct spv_ctx spv_ctx;
+
+/* volume texel types: VolumeRenderer.dtypes, volumerender.py:67 */
+enum { SPV_F32 = 0, SPV_U16 = 1, SPV_U8 = 2 };
+
+/* result buffers: VolumeRenderer.buf / buf_alpha / buf_depth / buf_normals /
+ * buf_occlusion, volumerender.py:185-193.  SPV_BUF_RAW is new: the un-windowed
+ * ray maximum that the sort-last composite reduces across GPUs. */
+enum { SPV_BUF_OUT = 0, SPV_BUF_ALPHA = 1, SPV_BUF_DEPTH = 2, SPV_BUF_NORMALS = 3, SPV_BUF_OCC = 4, SPV_BUF_RAW = 5 };
+
+/* sampler implementations */
+enum {
+  SPV_SAMPLER_TMU = 0,   /* hardware-filtered tex3D (9-bit weights), fma sample positions, brick skipping */
+  SPV_SAMPLER_EXACT = 1  /* fp32 software trilinear from 8 point fetches, positions accumulated like the
+                            reference loop: bit-comparable with the reference kernel text built for the host */
+};
+
+enum {
+  SPV_EINVAL = -22,   /* bad argument */
+  SPV_ENODATA = -61,  /* render before set_volume */
+  SPV_ENOMEM = -12
+};
+
+/* ---- lifetime: VolumeRenderer.__init__/resize/reset_buffer, volumerender.py:72-134, 181-197 ---- */
+SPV_API int spv_create(int device, int width, int height, spv_ctx **out);
+SPV_API int spv_destroy(spv_ctx *ctx);
+SPV_API int spv_resize(spv_ctx *ctx, int width, int height);
+/* run on a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the context's own stream */
+SPV_API int spv_set_stream(spv_ctx *ctx, void *cuda_stream);
+SPV_API int spv_sync(spv_ctx *ctx);
+
+/* ---- volume: set_shape / update_data, volumerender.py:260-294 (OCLImage.empty + write_array) ----
+ * host: C-order (z,y,x) array of nz*ny*nx texels of `dtype`.  Allocates the 3-D array, uploads,
+ * builds the min/max brick grid and the global min/max in the same pass. */
+SPV_API int spv_set_volume(spv_ctx *ctx, const void *host, int dtype, int nx, int ny, int nz);
+/* same shape and dtype as the current volume: re-upload only (the timelapse path, glwidget.py:372-374) */
+SPV_API int spv_update_volume(spv_ctx *ctx, const void *host);
+/* as above from a DEVICE pointer (C-order linear); used by frame sources that keep timepoints in HBM */
+SPV_API int spv_set_volume_device(spv_ctx *ctx, const void *dev, int dtype, int nx, int ny, int nz);
+/* One z-slab of a larger volume for sort-last rendering (new).  The host/dev pointer
+ * holds slices [z_lo, z_hi) of a global volume of gnz slices, where z_lo = max(z0-1,0) and
+ * z_hi = min(z1+1,gnz) (one halo slice either side); the context then renders only the ray samples
+ * whose trilinear footprint starts in slices [z0, z1) (the last slab also owns everything beyond). */
+SPV_API int spv_set_volume_slab(spv_ctx *ctx, const void *host, int on_device, int dtype, int nx, int ny, int gnz, int z0,
+                        int z1);
+/* global min/max of the resident volume (replaces GLWidget._get_min_max, gui/glwidget.py:328-344) */
+SPV_API int spv_volume_minmax(spv_ctx *ctx, float *vmin, float *vmax);
+
+/* -D SAMPLER_FILTER=..., volumerender.py:69-70, 146-147: 1 = linear, 0 = nearest */
+SPV_API int spv_set_interp(spv_ctx *ctx, int linear);
+SPV_API int spv_set_sampler(spv_ctx *ctx, int sampler);
+/* what read_imageui + a LINEAR sampler means for integer volumes (undefined by OpenCL):
+ * 1 = interpolate like a float image (default), 0 = nearest */
+SPV_API int spv_set_int_filter(spv_ctx *ctx, int linear);
+/* empty-brick skipping for the TMU max projection (default on; results are identical either way) */
+SPV_API int spv_set_skipping(spv_ctx *ctx, int on);
+
+/* invPBuf / invMBuf.write_array, volumerender.py:310-316: row-major float[16] each */
+SPV_API int spv_set_matrices(spv_ctx *ctx, const float *invP, const float *invM);
+
+/* ---- max projection: _render_max_project, volumerender.py:327-386 -> max_project_float/short ---- */
+typedef struct {
+  float box[6];      /* boxMin_x, boxMax_x, boxMin_y, boxMax_y, boxMin_z, boxMax_z */
+  float min_val, max_val, gamma, alpha_pow;
+  int num_parts, current_part;
+  int max_steps;     /* -D maxSteps (config.__DEFAULTMAXSTEPS__ = 200) */
+  int flags;         /* SPV_MIP_* */
+} spv_mip_params;
+enum {
+  SPV_MIP_RAW_ONLY = 1  /* write only SPV_BUF_RAW (+ alpha): the per-slab partial of a sort-last render;
+                           needs alpha_pow == 0 and num_parts == 1 */
+};
+SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p);
+/* window + gamma of SPV_BUF_RAW into SPV_BUF_OUT after the cross-GPU max composite */
+SPV_API int spv_mip_finish(spv_ctx *ctx, const spv_mip_params *p);
+
+/* ---- iso surface: _render_isosurface, volumerender.py:446-506
+ *      iso_surface -> conv_vec_x/y(7) -> occlusion -> conv_x/y(5) -> shading ---- */
+typedef struct {
+  float box[6];
+  float iso_val;     /* maxVal / 2, volumerender.py:463 */
+  float gamma;
+  int max_steps;
+  float occ_strength;
+  int occ_radius, occ_n_points;
+  int flags;         /* SPV_ISO_* */
+} spv_iso_params;
+enum {
+  SPV_ISO_RAW_ONLY = 1  /* the iso_surface kernel alone, no blur / occlusion / shading passes */
+};
+SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p);
+
+/* ---- results: buf.get(), volumerender.py:388-390, 499-506 ---- */
+/* copies n floats (n = w*h, or 3*w*h for normals) to host memory; synchronises */
+SPV_API int spv_read(spv_ctx *ctx, int which, float *host_dst, size_t n);
+/* all MIP results (out, alpha) or iso results in ONE device->host transfer into pinned staging, then
+ * scattered to the given host pointers (any may be NULL) */
+SPV_API int spv_read_many(spv_ctx *ctx, float *out, float *alpha, float *depth, float *normals, float *occ);
+/* zero-copy variant: one device->host transfer of the first `planes` planes of [out | alpha | depth | occ |
+ * normals(3)] into the context's pinned staging buffer; *host points at it (valid until the next read/resize) */
+SPV_API int spv_read_pinned(spv_ctx *ctx, int planes, float **host);
+SPV_API int spv_device_ptr(spv_ctx *ctx, int which, void **dev_ptr);
+
+/* ---- diagnostics ---- */
+SPV_API int spv_last_timing_ms(spv_ctx *ctx, float *ms);            /* device time of the last render call */
+SPV_API int spv_last_stats(spv_ctx *ctx, unsigned long long *v, int n); /* [hit rays, texture samples issued] of the
+                                                                last render when stats were enabled */
+SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
+SPV_API const char *spv_last_error(spv_ctx *ctx);                   /* ctx may be NULL: last create error */
+SPV_API int spv_version(void);
+SPV_API int spv_launch_count(spv_ctx *ctx, unsigned long long *n);  /* kernels launched by this context so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPIMCUDA_H_ */

@@ -4,7 +4,7 @@
 // TEST INFRASTRUCTURE ONLY (see oracle/spim_oracle.c header).  Nothing here is
 // derived from the reference: it supplies what the OpenCL *implementation*
 // would supply (vector types, built-ins, the image sampler of OpenCL 1.2 spec
-// section 8.2, work-item ids).  oracle/build_ref.py streams the reference .cl
+// section 8.2, work-item ids).  oracle/build.py streams the reference .cl
 // files from /root/reference through a one-line syntax rewrite
 // ("(float4)(" -> "float4(") into g++ together with this header and
 // ref_driver.inc; only the resulting oracle/_ref/libspim_ref.so is kept.

@@ -68,6 +68,8 @@ def load(kind="port"):
     lib.so_shading.argtypes = [_FP, C.c_int, C.c_int, _FP, _FP, C.c_float, _FP, _FP, _FP]
     lib.so_render_isosurface.argtypes = [VP, C.c_int, C.c_int, _FP, _FP, _FP, C.c_float, C.c_float, C.c_int,
                                          C.c_float, C.c_int, C.c_int, _FP, _FP, _FP, _FP, _FP, _FP, _FP]
+    if kind == "port":
+        lib.so_max_project_raw.argtypes = [VP, C.c_int, C.c_int, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, _FP]
     lib.so_count_hit_rays.argtypes = [C.c_int, C.c_int, _FP, _FP, _FP]
     lib.so_count_hit_rays.restype = C.c_long
     lib.so_random.argtypes = [C.c_uint32, C.c_uint32]
@@ -202,6 +204,17 @@ class OracleRenderer(object):
             raise ValueError(method)
         if rc != 0:
             raise RuntimeError("oracle returned %d" % rc)
+
+    def render_raw(self, z0=0, z1=None):
+        """Sort-last partial: raw ray maximum over the samples owned by slices [z0, z1) (port only)."""
+        invP, invM = self.matrices()
+        box = np.ascontiguousarray(self.boxBounds, np.float32)
+        raw = np.zeros((self.height, self.width), np.float32)
+        rc = self.lib.so_max_project_raw(C.byref(self.vol), self.width, self.height, _fp(invP), _fp(invM), _fp(box),
+                                         self.max_steps, int(z0), int(self.vol.nz if z1 is None else z1), _fp(raw))
+        if rc != 0:
+            raise RuntimeError("oracle returned %d" % rc)
+        return raw
 
     def count_hit_rays(self):
         invP, invM = self.matrices()

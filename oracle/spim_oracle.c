@@ -31,7 +31,7 @@
  *
  * PARITY PIN: the reference ships no golden vectors for this path and cannot
  * run here (no pyopencl / OpenCL device).  The restatement is pinned instead
- * against oracle/_ref/libspim_ref.so, which oracle/build_ref.py compiles from
+ * against oracle/_ref/libspim_ref.so, which oracle/build.py compiles from
  * the reference's own kernel TEXT (the .cl files where they lie under
  * /root/reference, through a small OpenCL-C-on-g++ shim).  tests/ asserts that
  * both agree bit for bit, and tests/golden/ holds outputs of that build.
@@ -139,10 +139,7 @@ static inline float quant_weight(float a, int bits) {
   float s = (float)(1 << bits);
   return floorf(a * s + 0.5f) / s;
 }
-static inline float sample(const so_volume *V, v4 pos) {
-  float u = pos.x * (float)V->nx;
-  float v = pos.y * (float)V->ny;
-  float w = pos.z * (float)V->nz;
+static inline float sample_uvw(const so_volume *V, float u, float v, float w) {
   int linear = V->filter && (V->dtype == 0 || V->int_linear);
   if (!linear) {
     int i = clampi_cl(floor_to_int(u, V->nx), 0, V->nx - 1);
@@ -171,6 +168,9 @@ static inline float sample(const so_volume *V, v4 pos) {
   T = T + a1 * b * c * texel(V, i0, j1, k1);
   T = T + a * b * c * texel(V, i1, j1, k1);
   return T;
+}
+static inline float sample(const so_volume *V, v4 pos) {
+  return sample_uvw(V, pos.x * (float)V->nx, pos.y * (float)V->ny, pos.z * (float)V->nz);
 }
 
 /* ------------------------------------------------------------------ */
@@ -212,7 +212,9 @@ static inline ray_t make_ray(unsigned x, unsigned y, unsigned Nx, unsigned Ny,
 /* ------------------------------------------------------------------ */
 /* pos_mode: 0 = accumulate pos += delta exactly like the reference loop;
  *           1 = pos_k = fma(k, delta, pos0)  (the form a kernel that skips or
- *               re-orders samples must use; differs by fp32 rounding drift) */
+ *               re-orders samples must use; differs by fp32 rounding drift)
+ *           2 = as 1 but in unnormalised texel coordinates, u_k = fma(k, delta*N, pos0*N):
+ *               the form libspimcuda's TMU kernel uses (alpha_pow == 0 branch only) */
 SO_EXPORT int so_max_project(const so_volume *V, int width, int height,
                              const float *invP, const float *invM, const float *box,
                              float minVal, float maxVal, float gamma, float alpha_pow,
@@ -247,7 +249,12 @@ SO_EXPORT int so_max_project(const so_volume *V, int width, int height,
       if (alpha_pow == 0) {
         for (int i = 0; i <= reducedSteps / LOOPUNROLL; ++i) {
           for (int j = 0; j < LOOPUNROLL; ++j) {
-            newVal = sample(V, pos);
+            if (pos_mode == 2)
+              newVal = sample_uvw(V, fmaf((float)k, delta_pos.x * (float)V->nx, pos0.x * (float)V->nx),
+                                  fmaf((float)k, delta_pos.y * (float)V->ny, pos0.y * (float)V->ny),
+                                  fmaf((float)k, delta_pos.z * (float)V->nz, pos0.z * (float)V->nz));
+            else
+              newVal = sample(V, pos);
             colVal = fmaxf(colVal, newVal);
             ++k;
             if (pos_mode == 0) pos = add4(pos, delta_pos);
@@ -287,9 +294,40 @@ SO_EXPORT int so_max_project(const so_volume *V, int width, int height,
   return 0;
 }
 
-/* Raw (un-windowed) maximum, and number of hit rays: used by the sort-last
- * brick tests (max over bricks must equal this bitwise) and by bench.py to
- * count algorithmic samples.  Same marching as so_max_project, pos_mode 1. */
+/* Sort-last partial render (NOT in the reference; restates SURVEY.md 8e): the raw, un-windowed maximum over
+ * the samples of each ray whose trilinear footprint STARTS in slices [z0, z1) of the volume (clamped slice
+ * index), -1 for rays that miss the box, 0 for hit rays that own no sample.  Positions as pos_mode 2.  The
+ * element-wise maximum over a partition of [0, nz) equals the z0=0, z1=nz render bit for bit. */
+SO_EXPORT int so_max_project_raw(const so_volume *V, int width, int height, const float *invP, const float *invM,
+                                 const float *box, int maxSteps, int z0, int z1, float *raw) {
+  const unsigned Nx = (unsigned)width, Ny = (unsigned)height;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int yy = 0; yy < height; ++yy) {
+    for (int xx = 0; xx < width; ++xx) {
+      unsigned x = (unsigned)xx, y = (unsigned)yy;
+      ray_t r = make_ray(x, y, Nx, Ny, invP, invM, box);
+      if (!r.hit) { raw[x + Nx * y] = -1.f; continue; }
+      float tnear = r.tnear < 0.0f ? 0.0f : r.tnear;
+      const int S = (maxSteps / 16 + 1) * 16;
+      const float dt = fabsf(r.tfar - tnear) / (float)((maxSteps / 16) * 16);
+      v4 delta_pos = scl4(.5f * dt, r.direc);
+      v4 pos0 = scl4(0.5f, add4(sadd4(1.f, r.orig), scl4(tnear, r.direc)));
+      const float u0 = pos0.x * (float)V->nx, v0 = pos0.y * (float)V->ny, w0 = pos0.z * (float)V->nz;
+      const float du = delta_pos.x * (float)V->nx, dv = delta_pos.y * (float)V->ny, dw = delta_pos.z * (float)V->nz;
+      float colVal = 0.f;
+      for (int k = 0; k < S; ++k) {
+        float w = fmaf((float)k, dw, w0);
+        float kf = fminf(fmaxf(floorf(w - 0.5f), 0.f), (float)(V->nz - 1));
+        if (kf >= (float)z0 && kf < (float)z1)
+          colVal = fmaxf(colVal, sample_uvw(V, fmaf((float)k, du, u0), fmaf((float)k, dv, v0), w));
+      }
+      raw[x + Nx * y] = colVal;
+    }
+  }
+  return 0;
+}
+
+/* Number of rays that hit the box: bench.py counts algorithmic samples with it. */
 SO_EXPORT long so_count_hit_rays(int width, int height, const float *invP, const float *invM,
                                  const float *box) {
   long n = 0;

@@ -1,0 +1,103 @@
+"""ctypes binding of libspimcuda.so (include/spimcuda.h).
+
+There is no CPU implementation behind this module: if the shared library is missing or no CUDA
+device is usable, loading / context creation raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libspimcuda.so")
+
+SPV_F32, SPV_U16, SPV_U8 = 0, 1, 2
+BUF_OUT, BUF_ALPHA, BUF_DEPTH, BUF_NORMALS, BUF_OCC, BUF_RAW = range(6)
+SAMPLER_TMU, SAMPLER_EXACT = 0, 1
+MIP_RAW_ONLY = 1
+ISO_RAW_ONLY = 1
+
+DTYPE_CODES = {np.dtype(np.float32): SPV_F32, np.dtype(np.uint16): SPV_U16, np.dtype(np.uint8): SPV_U8}
+
+
+class MipParams(C.Structure):
+    _fields_ = [("box", C.c_float * 6), ("min_val", C.c_float), ("max_val", C.c_float), ("gamma", C.c_float),
+                ("alpha_pow", C.c_float), ("num_parts", C.c_int), ("current_part", C.c_int),
+                ("max_steps", C.c_int), ("flags", C.c_int)]
+
+
+class IsoParams(C.Structure):
+    _fields_ = [("box", C.c_float * 6), ("iso_val", C.c_float), ("gamma", C.c_float), ("max_steps", C.c_int),
+                ("occ_strength", C.c_float), ("occ_radius", C.c_int), ("occ_n_points", C.c_int),
+                ("flags", C.c_int)]
+
+
+_FP = C.POINTER(C.c_float)
+_CTX = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/spimcuda.h declares
+SIGNATURES = {
+    "spv_version": (C.c_int, []),
+    "spv_last_error": (C.c_char_p, [_CTX]),
+    "spv_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_CTX)]),
+    "spv_destroy": (C.c_int, [_CTX]),
+    "spv_resize": (C.c_int, [_CTX, C.c_int, C.c_int]),
+    "spv_set_stream": (C.c_int, [_CTX, C.c_void_p]),
+    "spv_sync": (C.c_int, [_CTX]),
+    "spv_set_volume": (C.c_int, [_CTX, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "spv_update_volume": (C.c_int, [_CTX, C.c_void_p]),
+    "spv_set_volume_device": (C.c_int, [_CTX, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "spv_set_volume_slab": (C.c_int, [_CTX, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int]),
+    "spv_volume_minmax": (C.c_int, [_CTX, _FP, _FP]),
+    "spv_set_interp": (C.c_int, [_CTX, C.c_int]),
+    "spv_set_sampler": (C.c_int, [_CTX, C.c_int]),
+    "spv_set_int_filter": (C.c_int, [_CTX, C.c_int]),
+    "spv_set_skipping": (C.c_int, [_CTX, C.c_int]),
+    "spv_set_matrices": (C.c_int, [_CTX, _FP, _FP]),
+    "spv_render_mip": (C.c_int, [_CTX, C.POINTER(MipParams)]),
+    "spv_mip_finish": (C.c_int, [_CTX, C.POINTER(MipParams)]),
+    "spv_render_iso": (C.c_int, [_CTX, C.POINTER(IsoParams)]),
+    "spv_read": (C.c_int, [_CTX, C.c_int, _FP, C.c_size_t]),
+    "spv_read_many": (C.c_int, [_CTX, _FP, _FP, _FP, _FP, _FP]),
+    "spv_read_pinned": (C.c_int, [_CTX, C.c_int, C.POINTER(_FP)]),
+    "spv_device_ptr": (C.c_int, [_CTX, C.c_int, C.POINTER(C.c_void_p)]),
+    "spv_last_timing_ms": (C.c_int, [_CTX, _FP]),
+    "spv_last_stats": (C.c_int, [_CTX, C.POINTER(C.c_ulonglong), C.c_int]),
+    "spv_enable_stats": (C.c_int, [_CTX, C.c_int]),
+    "spv_launch_count": (C.c_int, [_CTX, C.POINTER(C.c_ulonglong)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libspimcuda.so (once).  Raises ImportError with a build hint if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s not found: build it with `python -m spimagine_b200.build` "
+                          "(needs nvcc; there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def fp(a):
+    assert a.dtype == np.float32 and a.flags.c_contiguous
+    return a.ctypes.data_as(_FP)
+
+
+class SpvError(RuntimeError):
+    pass
+
+
+def check(rc, ctx=None):
+    if rc != 0:
+        msg = load().spv_last_error(ctx)
+        raise SpvError("libspimcuda: %s" % (msg.decode() if msg else "error %d" % rc))

@@ -1,0 +1,519 @@
+// spv_api.cu -- the C ABI of libspimcuda.so (include/spimcuda.h): context, volume residency, render dispatch,
+// result read-back.  Device side of spimagine/volumerender/volumerender.py; see the header for the reference
+// call each entry point replaces.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "spv_kernels.h"
+
+using namespace spv;
+
+struct spv_ctx {
+  int device = 0;
+  int width = 0, height = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  // volume
+  cudaArray_t arr = nullptr;
+  cudaTextureObject_t tex_lin = 0, tex_near = 0, tex_pt = 0;
+  int dtype = -1, nx = 0, ny = 0, gnz = 0, local_nz = 0, z_lo = 0, z0 = 0, z1 = 0;
+  bool slab = false;
+  float2 *bricks = nullptr, *coarse = nullptr;
+  int gx = 0, gy = 0, gz = 0, cgx = 0, cgy = 0, cgz = 0;
+  float *d_minmax = nullptr;
+  float h_minmax[2] = {0.f, 0.f};
+  bool minmax_valid = false;
+  // settings
+  int linear = 1, sampler = SPV_SAMPLER_TMU, int_filter = 1, skipping = 1, stats_on = 0;
+  Camera cam;
+  // result buffers: one allocation  [out | alpha | depth | occ | normals(3) | raw | tmp | tmp_vec(3)]
+  float *dbuf = nullptr;
+  float *hpin = nullptr;  // pinned staging for [out | alpha | depth | occ | normals(3)]
+  int last_method = 0;    // 0 = mip, 1 = iso
+  unsigned long long *d_stats = nullptr;
+  unsigned long long h_stats[2] = {0, 0};
+  unsigned long long launches = 0;
+  std::string err;
+
+  size_t n() const { return (size_t)width * height; }
+  float *out() const { return dbuf; }
+  float *alpha() const { return dbuf + n(); }
+  float *depth() const { return dbuf + 2 * n(); }
+  float *occ() const { return dbuf + 3 * n(); }
+  float *normals() const { return dbuf + 4 * n(); }
+  float *raw() const { return dbuf + 7 * n(); }
+  float *tmp() const { return dbuf + 8 * n(); }
+  float *tmp_vec() const { return dbuf + 9 * n(); }
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(spv_ctx *c, int code, const char *what) {
+  char b[512];
+  snprintf(b, sizeof b, "%s (code %d)", what, code);
+  if (c) c->err = b; else g_create_err = b;
+  return code;
+}
+static int cufail(spv_ctx *c, cudaError_t e, const char *where) {
+  char b[512];
+  snprintf(b, sizeof b, "%s: %s", where, cudaGetErrorString(e));
+  if (c) c->err = b; else g_create_err = b;
+  return (int)e;
+}
+#define CU(call)                                              \
+  do {                                                        \
+    cudaError_t e_ = (call);                                  \
+    if (e_ != cudaSuccess) return cufail(ctx, e_, #call);     \
+  } while (0)
+#define BIND()                                                \
+  do {                                                        \
+    if (!ctx) return fail(nullptr, SPV_EINVAL, "null ctx");   \
+    CU(cudaSetDevice(ctx->device));                           \
+  } while (0)
+
+static void free_buffers(spv_ctx *c) {
+  if (c->dbuf) cudaFree(c->dbuf);
+  if (c->hpin) cudaFreeHost(c->hpin);
+  c->dbuf = nullptr;
+  c->hpin = nullptr;
+}
+static void free_volume(spv_ctx *c) {
+  if (c->tex_lin) cudaDestroyTextureObject(c->tex_lin);
+  if (c->tex_near) cudaDestroyTextureObject(c->tex_near);
+  if (c->tex_pt) cudaDestroyTextureObject(c->tex_pt);
+  if (c->arr) cudaFreeArray(c->arr);
+  if (c->bricks) cudaFree(c->bricks);
+  if (c->coarse) cudaFree(c->coarse);
+  c->tex_lin = c->tex_near = c->tex_pt = 0;
+  c->arr = nullptr;
+  c->bricks = c->coarse = nullptr;
+  c->dtype = -1;
+}
+
+static int alloc_buffers(spv_ctx *ctx, int w, int h) {
+  if (w <= 0 || h <= 0) return fail(ctx, SPV_EINVAL, "spv_resize: width and height must be positive");
+  free_buffers(ctx);
+  ctx->width = w;
+  ctx->height = h;
+  const size_t n = ctx->n();
+  CU(cudaMalloc(&ctx->dbuf, 12 * n * sizeof(float)));
+  CU(cudaMemsetAsync(ctx->dbuf, 0, 12 * n * sizeof(float), ctx->stream));
+  CU(cudaMallocHost(&ctx->hpin, 7 * n * sizeof(float)));
+  memset(ctx->hpin, 0, 7 * n * sizeof(float));
+  return 0;
+}
+
+extern "C" {
+
+SPV_API int spv_version(void) { return SPV_VERSION; }
+
+SPV_API const char *spv_last_error(spv_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+SPV_API int spv_create(int device, int width, int height, spv_ctx **out) {
+  if (!out) return fail(nullptr, SPV_EINVAL, "spv_create: null out");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess) return cufail(nullptr, e, "spv_create: cudaGetDeviceCount (no CUDA device: this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(nullptr, SPV_EINVAL, "spv_create: no such CUDA device");
+  spv_ctx *ctx = new spv_ctx();
+  ctx->device = device;
+  for (int i = 0; i < 16; ++i) ctx->cam.invP[i] = ctx->cam.invM[i] = (i % 5 == 0) ? 1.f : 0.f;
+#define CC(call)                                   \
+  do {                                             \
+    cudaError_t e_ = (call);                       \
+    if (e_ != cudaSuccess) {                       \
+      cufail(nullptr, e_, #call);                  \
+      spv_destroy(ctx);                            \
+      return (int)e_;                              \
+    }                                              \
+  } while (0)
+  CC(cudaSetDevice(device));
+  CC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  CC(cudaEventCreate(&ctx->ev0));
+  CC(cudaEventCreate(&ctx->ev1));
+  CC(cudaMalloc(&ctx->d_minmax, 2 * sizeof(float)));
+  CC(cudaMalloc(&ctx->d_stats, 2 * sizeof(unsigned long long)));
+#undef CC
+  int rc = alloc_buffers(ctx, width, height);
+  if (rc) {
+    g_create_err = ctx->err;
+    spv_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return 0;
+}
+
+SPV_API int spv_destroy(spv_ctx *ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  free_volume(ctx);
+  free_buffers(ctx);
+  if (ctx->d_minmax) cudaFree(ctx->d_minmax);
+  if (ctx->d_stats) cudaFree(ctx->d_stats);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return 0;
+}
+
+SPV_API int spv_resize(spv_ctx *ctx, int width, int height) {
+  BIND();
+  CU(cudaStreamSynchronize(ctx->stream));
+  return alloc_buffers(ctx, width, height);
+}
+
+SPV_API int spv_set_stream(spv_ctx *ctx, void *cuda_stream) {
+  BIND();
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return 0;
+}
+
+SPV_API int spv_sync(spv_ctx *ctx) {
+  BIND();
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static size_t elem_size(int dtype) { return dtype == SPV_F32 ? 4 : (dtype == SPV_U16 ? 2 : 1); }
+
+static int make_textures(spv_ctx *ctx) {
+  cudaResourceDesc rd;
+  memset(&rd, 0, sizeof rd);
+  rd.resType = cudaResourceTypeArray;
+  rd.res.array.array = ctx->arr;
+  cudaTextureDesc td;
+  memset(&td, 0, sizeof td);
+  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+  td.normalizedCoords = 0;
+  // filtered: integer texels can only be filtered when read as normalised floats
+  td.readMode = ctx->dtype == SPV_F32 ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+  td.filterMode = cudaFilterModeLinear;
+  CU(cudaCreateTextureObject(&ctx->tex_lin, &rd, &td, nullptr));
+  td.filterMode = cudaFilterModePoint;
+  CU(cudaCreateTextureObject(&ctx->tex_near, &rd, &td, nullptr));
+  td.readMode = cudaReadModeElementType;
+  CU(cudaCreateTextureObject(&ctx->tex_pt, &rd, &td, nullptr));
+  return 0;
+}
+
+static Volume volume_of(const spv_ctx *c) {
+  Volume V;
+  const bool lin = c->linear && (c->dtype == SPV_F32 || c->int_filter);
+  V.filt = lin ? c->tex_lin : c->tex_near;
+  V.pt = c->tex_pt;
+  V.nx = c->nx; V.ny = c->ny; V.nz = c->gnz;
+  V.fnx = (float)c->nx; V.fny = (float)c->ny; V.fnz = (float)c->gnz;
+  V.scale = c->dtype == SPV_F32 ? 1.f : (c->dtype == SPV_U16 ? 65535.f : 255.f);
+  V.z_lo = c->z_lo; V.z0 = c->z0; V.z1 = c->z1;
+  V.bricks = c->bricks;
+  V.gx = c->gx; V.gy = c->gy; V.gz = c->gz;
+  return V;
+}
+
+static int upload(spv_ctx *ctx, const void *src, bool on_device) {
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof p);
+  p.srcPtr = make_cudaPitchedPtr(const_cast<void *>(src), (size_t)ctx->nx * elem_size(ctx->dtype), ctx->nx, ctx->ny);
+  p.dstArray = ctx->arr;
+  p.extent = make_cudaExtent(ctx->nx, ctx->ny, ctx->local_nz);
+  p.kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CU(cudaMemcpy3DAsync(&p, ctx->stream));
+  Volume V = volume_of(ctx);
+  CU(launch_build_bricks(V, ctx->dtype, ctx->local_nz, ctx->bricks, ctx->coarse, ctx->cgx, ctx->cgy, ctx->cgz,
+                         ctx->d_minmax, ctx->stream));
+  ctx->launches += 3;
+  ctx->minmax_valid = false;
+  if (!on_device) CU(cudaStreamSynchronize(ctx->stream));  // the host pointer is only borrowed for this call
+  return 0;
+}
+
+static int set_volume_impl(spv_ctx *ctx, const void *src, bool on_device, int dtype, int nx, int ny, int gnz, int z0,
+                           int z1, bool slab) {
+  BIND();
+  if (!src) return fail(ctx, SPV_EINVAL, "spv_set_volume: null data");
+  if (dtype < 0 || dtype > 2) return fail(ctx, SPV_EINVAL, "spv_set_volume: dtype must be 0 (f32), 1 (u16) or 2 (u8)");
+  if (nx <= 0 || ny <= 0 || gnz <= 0 || z0 < 0 || z1 > gnz || z0 >= z1)
+    return fail(ctx, SPV_EINVAL, "spv_set_volume: bad extent");
+  const int z_lo = slab ? (z0 > 0 ? z0 - 1 : 0) : 0;
+  const int z_hi = slab ? (z1 < gnz ? z1 + 1 : gnz) : gnz;
+  const int local_nz = z_hi - z_lo;
+  CU(cudaStreamSynchronize(ctx->stream));
+  const bool same = ctx->arr && ctx->dtype == dtype && ctx->nx == nx && ctx->ny == ny && ctx->local_nz == local_nz;
+  if (!same) {
+    free_volume(ctx);
+    ctx->dtype = dtype;
+    ctx->nx = nx; ctx->ny = ny; ctx->local_nz = local_nz;
+    cudaChannelFormatDesc cd = dtype == SPV_F32 ? cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat)
+                             : dtype == SPV_U16 ? cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned)
+                                                : cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
+    CU(cudaMalloc3DArray(&ctx->arr, &cd, make_cudaExtent(nx, ny, local_nz), 0));
+    int rc = make_textures(ctx);
+    if (rc) return rc;
+    ctx->gx = (nx + BRICK - 1) / BRICK; ctx->gy = (ny + BRICK - 1) / BRICK; ctx->gz = (local_nz + BRICK - 1) / BRICK;
+    ctx->cgx = (ctx->gx + 3) / 4; ctx->cgy = (ctx->gy + 3) / 4; ctx->cgz = (ctx->gz + 3) / 4;
+    CU(cudaMalloc(&ctx->bricks, (size_t)ctx->gx * ctx->gy * ctx->gz * sizeof(float2)));
+    CU(cudaMalloc(&ctx->coarse, (size_t)ctx->cgx * ctx->cgy * ctx->cgz * sizeof(float2)));
+  }
+  ctx->gnz = gnz; ctx->z_lo = z_lo; ctx->z0 = z0; ctx->z1 = z1; ctx->slab = slab;
+  return upload(ctx, src, on_device);
+}
+
+SPV_API int spv_set_volume(spv_ctx *ctx, const void *host, int dtype, int nx, int ny, int nz) {
+  return set_volume_impl(ctx, host, false, dtype, nx, ny, nz, 0, nz, false);
+}
+SPV_API int spv_set_volume_device(spv_ctx *ctx, const void *dev, int dtype, int nx, int ny, int nz) {
+  return set_volume_impl(ctx, dev, true, dtype, nx, ny, nz, 0, nz, false);
+}
+SPV_API int spv_set_volume_slab(spv_ctx *ctx, const void *src, int on_device, int dtype, int nx, int ny, int gnz, int z0,
+                        int z1) {
+  return set_volume_impl(ctx, src, on_device != 0, dtype, nx, ny, gnz, z0, z1, true);
+}
+SPV_API int spv_update_volume(spv_ctx *ctx, const void *host) {
+  BIND();
+  if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_update_volume: no volume set");
+  if (!host) return fail(ctx, SPV_EINVAL, "spv_update_volume: null data");
+  return upload(ctx, host, false);
+}
+
+SPV_API int spv_volume_minmax(spv_ctx *ctx, float *vmin, float *vmax) {
+  BIND();
+  if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_volume_minmax: no volume set");
+  if (!ctx->minmax_valid) {
+    CU(cudaMemcpyAsync(ctx->h_minmax, ctx->d_minmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->minmax_valid = true;
+  }
+  if (vmin) *vmin = ctx->h_minmax[0];
+  if (vmax) *vmax = ctx->h_minmax[1];
+  return 0;
+}
+
+SPV_API int spv_set_interp(spv_ctx *ctx, int linear) {
+  if (!ctx) return SPV_EINVAL;
+  ctx->linear = linear != 0;
+  return 0;
+}
+SPV_API int spv_set_sampler(spv_ctx *ctx, int sampler) {
+  if (!ctx) return SPV_EINVAL;
+  if (sampler != SPV_SAMPLER_TMU && sampler != SPV_SAMPLER_EXACT) return fail(ctx, SPV_EINVAL, "spv_set_sampler: unknown sampler");
+  ctx->sampler = sampler;
+  return 0;
+}
+SPV_API int spv_set_int_filter(spv_ctx *ctx, int linear) {
+  if (!ctx) return SPV_EINVAL;
+  ctx->int_filter = linear != 0;
+  return 0;
+}
+SPV_API int spv_set_skipping(spv_ctx *ctx, int on) {
+  if (!ctx) return SPV_EINVAL;
+  ctx->skipping = on != 0;
+  return 0;
+}
+SPV_API int spv_enable_stats(spv_ctx *ctx, int on) {
+  if (!ctx) return SPV_EINVAL;
+  ctx->stats_on = on != 0;
+  return 0;
+}
+
+SPV_API int spv_set_matrices(spv_ctx *ctx, const float *invP, const float *invM) {
+  if (!ctx || !invP || !invM) return fail(ctx, SPV_EINVAL, "spv_set_matrices: null argument");
+  memcpy(ctx->cam.invP, invP, 16 * sizeof(float));
+  memcpy(ctx->cam.invM, invM, 16 * sizeof(float));
+  return 0;
+}
+
+static int begin_render(spv_ctx *ctx) {
+  if (ctx->stats_on) CU(cudaMemsetAsync(ctx->d_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  return 0;
+}
+static int end_render(spv_ctx *ctx) {
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  if (ctx->stats_on)
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+static bool bad_float(float f) { return !(f == f); }
+
+SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p) {
+  BIND();
+  if (!p) return fail(ctx, SPV_EINVAL, "spv_render_mip: null params");
+  if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_render_mip: no volume set");
+  if (p->num_parts < 1 || p->current_part < 0 || p->max_steps / p->num_parts < 16)
+    return fail(ctx, SPV_EINVAL, "spv_render_mip: need num_parts >= 1 and max_steps/num_parts >= 16");
+  if (bad_float(p->alpha_pow) || bad_float(p->gamma)) return fail(ctx, SPV_EINVAL, "spv_render_mip: NaN parameter");
+  const bool raw_only = (p->flags & SPV_MIP_RAW_ONLY) != 0;
+  const bool exact = ctx->sampler == SPV_SAMPLER_EXACT;
+  const bool fast = !exact && p->alpha_pow == 0.f;
+  if ((raw_only || ctx->slab) && !fast)
+    return fail(ctx, SPV_EINVAL, "spv_render_mip: slab / raw renders need the TMU sampler and alpha_pow == 0");
+  if (raw_only && p->num_parts != 1) return fail(ctx, SPV_EINVAL, "spv_render_mip: raw renders need num_parts == 1");
+  MipArgs a;
+  a.cam = ctx->cam;
+  a.vol = volume_of(ctx);
+  a.coarse = ctx->coarse;
+  a.cgx = ctx->cgx; a.cgy = ctx->cgy; a.cgz = ctx->cgz;
+  memcpy(a.box, p->box, sizeof a.box);
+  a.min_val = p->min_val; a.max_val = p->max_val; a.gamma = p->gamma; a.alpha_pow = p->alpha_pow;
+  a.num_parts = p->num_parts; a.current_part = p->current_part; a.max_steps = p->max_steps; a.flags = p->flags;
+  a.width = ctx->width; a.height = ctx->height;
+  a.out = ctx->out(); a.alpha = ctx->alpha(); a.raw = ctx->raw();
+  a.stats = ctx->stats_on ? ctx->d_stats : nullptr;
+  const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
+  int rc = begin_render(ctx);
+  if (rc) return rc;
+  CU(launch_mip(a, ctx->dtype, linear, fast, exact, ctx->skipping != 0, ctx->slab, ctx->stats_on != 0, ctx->stream));
+  ctx->launches += 1;
+  ctx->last_method = 0;
+  return end_render(ctx);
+}
+
+SPV_API int spv_mip_finish(spv_ctx *ctx, const spv_mip_params *p) {
+  BIND();
+  if (!p) return fail(ctx, SPV_EINVAL, "spv_mip_finish: null params");
+  CU(launch_mip_finish(ctx->raw(), ctx->out(), (int)ctx->n(), p->min_val, p->max_val, p->gamma, ctx->stream));
+  ctx->launches += 1;
+  ctx->last_method = 0;
+  return 0;
+}
+
+static ConvWeights conv_weights(int Nh, float coef) {
+  ConvWeights w;
+  memset(&w, 0, sizeof w);
+  w.nh = Nh;
+  for (int ht = 0; ht < Nh; ++ht)  // convolve_2d.cl:23 / :86, evaluated left to right in fp32
+    w.w[ht] = expf((float)(coef * ((float)ht - (float)Nh / 2.f) * ((float)ht - (float)Nh / 2.f) / (float)Nh / (float)Nh));
+  return w;
+}
+
+SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p) {
+  BIND();
+  if (!p) return fail(ctx, SPV_EINVAL, "spv_render_iso: null params");
+  if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_render_iso: no volume set");
+  if (ctx->slab) return fail(ctx, SPV_EINVAL, "spv_render_iso: not available on a slab context");
+  if (p->max_steps < 2) return fail(ctx, SPV_EINVAL, "spv_render_iso: max_steps must be >= 2");
+  if (p->occ_n_points < 0 || p->occ_radius < 0) return fail(ctx, SPV_EINVAL, "spv_render_iso: negative occlusion parameter");
+  IsoArgs a;
+  a.cam = ctx->cam;
+  a.vol = volume_of(ctx);
+  a.coarse = ctx->coarse;
+  a.cgx = ctx->cgx; a.cgy = ctx->cgy; a.cgz = ctx->cgz;
+  memcpy(a.box, p->box, sizeof a.box);
+  a.iso_val = p->iso_val; a.gamma = p->gamma; a.max_steps = p->max_steps;
+  a.width = ctx->width; a.height = ctx->height;
+  a.out = ctx->out(); a.alpha = ctx->alpha(); a.depth = ctx->depth(); a.normals = ctx->normals();
+  a.stats = ctx->stats_on ? ctx->d_stats : nullptr;
+  const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
+  int rc = begin_render(ctx);
+  if (rc) return rc;
+  CU(launch_iso(a, ctx->dtype, linear, ctx->sampler == SPV_SAMPLER_EXACT, ctx->stats_on != 0, ctx->stream));
+  ctx->launches += 1;
+  if (!(p->flags & SPV_ISO_RAW_ONLY)) {
+    // volumerender.py:470-497
+    CU(launch_conv(ctx->normals(), ctx->tmp_vec(), ctx->width, ctx->height, 3, conv_weights(7, -5.f), ctx->stream));
+    CU(launch_occlusion(ctx->occ(), ctx->width, ctx->height, p->occ_radius, p->occ_n_points, ctx->depth(), ctx->stream));
+    CU(launch_conv(ctx->occ(), ctx->tmp(), ctx->width, ctx->height, 1, conv_weights(5, -10.f), ctx->stream));
+    CU(launch_shading(ctx->out(), ctx->width, ctx->height, ctx->cam, p->occ_strength, ctx->normals(), ctx->depth(),
+                      ctx->occ(), ctx->stream));
+    ctx->launches += 6;
+  }
+  ctx->last_method = 1;
+  return end_render(ctx);
+}
+
+static float *buf_of(spv_ctx *c, int which, size_t *count) {
+  const size_t n = c->n();
+  *count = n;
+  switch (which) {
+    case SPV_BUF_OUT: return c->out();
+    case SPV_BUF_ALPHA: return c->alpha();
+    case SPV_BUF_DEPTH: return c->depth();
+    case SPV_BUF_OCC: return c->occ();
+    case SPV_BUF_RAW: return c->raw();
+    case SPV_BUF_NORMALS: *count = 3 * n; return c->normals();
+    default: return nullptr;
+  }
+}
+
+SPV_API int spv_read(spv_ctx *ctx, int which, float *host_dst, size_t n) {
+  BIND();
+  size_t count = 0;
+  float *src = buf_of(ctx, which, &count);
+  if (!src || !host_dst) return fail(ctx, SPV_EINVAL, "spv_read: bad buffer id or null destination");
+  if (n != count) return fail(ctx, SPV_EINVAL, "spv_read: element count does not match the buffer");
+  CU(cudaMemcpyAsync(host_dst, src, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+SPV_API int spv_read_many(spv_ctx *ctx, float *out, float *alpha, float *depth, float *normals, float *occ) {
+  BIND();
+  const size_t n = ctx->n();
+  // [out | alpha | depth | occ | normals]: MIP wrote the first two planes, iso all seven
+  const size_t planes = (depth || normals || occ) ? 7 : 2;
+  CU(cudaMemcpyAsync(ctx->hpin, ctx->dbuf, planes * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (out) memcpy(out, ctx->hpin, n * sizeof(float));
+  if (alpha) memcpy(alpha, ctx->hpin + n, n * sizeof(float));
+  if (depth) memcpy(depth, ctx->hpin + 2 * n, n * sizeof(float));
+  if (occ) memcpy(occ, ctx->hpin + 3 * n, n * sizeof(float));
+  if (normals) memcpy(normals, ctx->hpin + 4 * n, 3 * n * sizeof(float));
+  return 0;
+}
+
+SPV_API int spv_read_pinned(spv_ctx *ctx, int planes, float **host) {
+  BIND();
+  if (planes < 1 || planes > 7 || !host) return fail(ctx, SPV_EINVAL, "spv_read_pinned: planes must be 1..7");
+  CU(cudaMemcpyAsync(ctx->hpin, ctx->dbuf, (size_t)planes * ctx->n() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *host = ctx->hpin;
+  return 0;
+}
+
+SPV_API int spv_device_ptr(spv_ctx *ctx, int which, void **dev_ptr) {
+  if (!ctx || !dev_ptr) return fail(ctx, SPV_EINVAL, "spv_device_ptr: null argument");
+  size_t count = 0;
+  float *src = buf_of(ctx, which, &count);
+  if (!src) return fail(ctx, SPV_EINVAL, "spv_device_ptr: bad buffer id");
+  *dev_ptr = src;
+  return 0;
+}
+
+SPV_API int spv_last_timing_ms(spv_ctx *ctx, float *ms) {
+  BIND();
+  if (!ms) return fail(ctx, SPV_EINVAL, "spv_last_timing_ms: null argument");
+  if (!ctx->timed) return fail(ctx, SPV_ENODATA, "spv_last_timing_ms: nothing rendered yet");
+  CU(cudaEventSynchronize(ctx->ev1));
+  CU(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return 0;
+}
+
+SPV_API int spv_last_stats(spv_ctx *ctx, unsigned long long *v, int n) {
+  BIND();
+  if (!v || n < 2) return fail(ctx, SPV_EINVAL, "spv_last_stats: need room for 2 counters");
+  if (!ctx->stats_on) return fail(ctx, SPV_ENODATA, "spv_last_stats: statistics are not enabled");
+  CU(cudaStreamSynchronize(ctx->stream));
+  v[0] = ctx->h_stats[0];
+  v[1] = ctx->h_stats[1];
+  return 0;
+}
+
+SPV_API int spv_launch_count(spv_ctx *ctx, unsigned long long *n) {
+  if (!ctx || !n) return SPV_EINVAL;
+  *n = ctx->launches;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,253 @@
+// spv_iso.cu -- iso-surface ray march and its screen-space post passes.  Replaces
+//   iso_surface            spimagine/volumerender/kernels/iso_kernel.cl:17-225
+//   conv_x/y, conv_vec_x/y spimagine/volumerender/kernels/convolve_2d.cl:6-137
+//   occlusion              spimagine/volumerender/kernels/occlusion.cl:41-82  (+ utils.cl:10-38)
+//   shading                spimagine/volumerender/kernels/iso_kernel.cl:505-588
+// in the launch order of VolumeRenderer._render_isosurface (volumerender.py:446-506).
+#include "spv_kernels.h"
+
+namespace spv {
+
+// -------------------------------------------------------------------------------------------------------------
+// iso_surface.  One warp = one 8x4 pixel tile (same lane order as the MIP kernel).  The coarse search keeps the
+// reference's sample positions (pos += delta accumulation) and its first-crossing rule; the bracket refinement
+// and the 12-tap gradient follow iso_kernel.cl:140-200 operation by operation.
+template <int DT, bool LINEAR, bool EXACT, bool STATS>
+__global__ void __launch_bounds__(128) iso_kernel(const IsoArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
+  const int ly = ((lane >> 1) & 1) | ((lane >> 2) & 2);
+  const unsigned x = blockIdx.x * 16 + (warp & 1) * 8 + lx, y = blockIdx.y * 8 + (warp >> 1) * 4 + ly;
+  const unsigned Nx = a.width, Ny = a.height;
+  if (x >= Nx || y >= Ny) return;
+  const size_t p = x + (size_t)Nx * y;
+  const Volume &V = a.vol;
+  const float INF = __int_as_float(0x7f800000);
+  unsigned long long nfetch = 0;
+
+  Ray r = make_ray(x, y, Nx, Ny, a.cam, a.box);
+  bool hitIso = false;
+  float tnear = r.tnear, t_hit = INF;
+  v4 normal = mk4(0.f, 0.f, 0.f, 0.f);
+  float colVal = 0.f;
+  if (r.hit) {
+    const v4 orig = r.orig, direc = r.direc;
+    if (tnear < 0.0f) tnear = 0.0f;
+    const float isoVal = a.iso_val;
+    const int maxSteps = a.max_steps;
+    const float dt = 1.f * (r.tfar - tnear) / ((float)maxSteps - 1.f);
+    const v4 delta_pos = scl4(.5f * dt, direc);
+    const v4 pos0 = scl4(0.5f, add4(sadd4(1.f, orig), scl4(tnear, direc)));
+    v4 pos = pos0;
+    // :106 reads the first sample with read_imagef whatever the image type; taken as a proper read
+    float newVal = sample<DT, LINEAR, EXACT>(V, pos.x, pos.y, pos.z);
+    const bool isGreater = newVal > isoVal;
+    int i = 1;
+    for (i = 1; i < maxSteps; i++) {
+      pos = add4(pos, delta_pos);
+      t_hit = tnear + (float)i * dt;
+      newVal = sample<DT, LINEAR, EXACT>(V, pos.x, pos.y, pos.z);
+      if ((newVal > isoVal) != isGreater) {
+        hitIso = true;
+        break;
+      }
+    }
+    if (STATS) nfetch += (unsigned long long)min(i, maxSteps - 1) + 1ull;
+    if (hitIso) {
+      const int maxBisect = 10;
+      const v4 delta_pos2 = mk4(delta_pos.x / (float)maxBisect, delta_pos.y / (float)maxBisect,
+                                delta_pos.z / (float)maxBisect, delta_pos.w / (float)maxBisect);
+      const float dt2 = dt / (float)maxBisect;
+      pos = add4(pos0, scl4((float)(i - 1), delta_pos));
+      for (int j = 1; j <= maxBisect; j++) {
+        newVal = sample<DT, LINEAR, EXACT>(V, pos.x, pos.y, pos.z);
+        pos = add4(pos, delta_pos2);
+        t_hit += dt2;
+        if (STATS) ++nfetch;
+        if ((newVal > isoVal) != isGreater) break;
+      }
+      v4 light = mk4(2.f, -1.f, -2.f, 0.f);
+      const float c_ambient = .3f, c_diffuse = .4f, c_specular = .3f;
+      light = mult(a.cam.invM, light);
+      light = normalize4(light);
+      float h = dt;
+      h *= (a.gamma * a.gamma);  // pow(gamma, 2.f)
+      const float h2 = 2.f * h;
+#define SPV_S(dx, dy, dz) sample<DT, LINEAR, EXACT>(V, pos.x + (dx), pos.y + (dy), pos.z + (dz))
+      normal.x = 2.f * SPV_S(h, 0.f, 0.f) - 2.f * SPV_S(-h, 0.f, 0.f) + SPV_S(h2, 0.f, 0.f) - SPV_S(-h2, 0.f, 0.f);
+      normal.y = 2.f * SPV_S(0.f, h, 0.f) - 2.f * SPV_S(0.f, -h, 0.f) + SPV_S(0.f, h2, 0.f) - SPV_S(0.f, -h2, 0.f);
+      normal.z = SPV_S(0.f, 0.f, h) - SPV_S(0.f, 0.f, -h) + SPV_S(0.f, 0.f, h2) - SPV_S(0.f, 0.f, -h2);
+#undef SPV_S
+      if (STATS) nfetch += 12;
+      normal.w = 0.f;
+      normal = scl4(1.f - (float)(2 * (int)isGreater), normalize4(normal));
+      const v4 reflect = sub4(scl4(2.f * dot4(light, normal), normal), light);
+      const float diffuse = fmaxf(0.f, dot4(light, normal));
+      const float specular = powf(fmaxf(0.f, dot4(normalize4(reflect), normalize4(direc))), 10.f);
+      colVal = c_ambient + c_diffuse * diffuse + (diffuse > 0.f ? 1.f : 0.f) * c_specular * specular;
+    }
+  }
+  if (hitIso) {
+    a.out[p] = colVal;
+    a.alpha[p] = tnear;
+    a.depth[p] = t_hit;
+    a.normals[3 * p + 0] = normal.x;
+    a.normals[3 * p + 1] = normal.y;
+    a.normals[3 * p + 2] = normal.z;
+  } else {
+    a.out[p] = 0.f;
+    a.alpha[p] = 0.f;
+    a.depth[p] = INF;
+    a.normals[3 * p + 0] = 0.f;
+    a.normals[3 * p + 1] = 0.f;
+    a.normals[3 * p + 2] = 0.f;
+  }
+  if (STATS && a.stats) {
+    atomicAdd(a.stats + 0, r.hit ? 1ull : 0ull);
+    atomicAdd(a.stats + 1, nfetch);
+  }
+}
+
+template <int DT>
+static cudaError_t launch_iso_dt(const IsoArgs &a, bool linear, bool exact, bool stats, cudaStream_t st) {
+  dim3 grid((a.width + 15) / 16, (a.height + 7) / 8), block(128);
+#define SPV_ISO(L, E, S) iso_kernel<DT, L, E, S><<<grid, block, 0, st>>>(a)
+  if (stats) {
+    if (linear) { if (exact) SPV_ISO(true, true, true); else SPV_ISO(true, false, true); }
+    else { if (exact) SPV_ISO(false, true, true); else SPV_ISO(false, false, true); }
+  } else {
+    if (linear) { if (exact) SPV_ISO(true, true, false); else SPV_ISO(true, false, false); }
+    else { if (exact) SPV_ISO(false, true, false); else SPV_ISO(false, false, false); }
+  }
+#undef SPV_ISO
+  return cudaGetLastError();
+}
+
+cudaError_t launch_iso(const IsoArgs &a, int dtype, bool linear, bool exact, bool stats, cudaStream_t st) {
+  switch (dtype) {
+    case 0: return launch_iso_dt<0>(a, linear, exact, stats, st);
+    case 1: return launch_iso_dt<1>(a, linear, exact, stats, st);
+    default: return launch_iso_dt<2>(a, linear, exact, stats, st);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// separable blur, one output pixel per thread.  Taps ht in [h_start, h_end) at offset ht - Nh/2 (integer
+// division): the weight table is centred at Nh/2.f but the taps at Nh/2, as in the reference.
+template <int NCOMP, bool ALONG_Y>
+__global__ void conv_kernel(const float *__restrict__ input, float *__restrict__ output, int Nx, int Ny,
+                            const ConvWeights cw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= Nx || j >= Ny) return;
+  const int Nh = cw.nh;
+  const int c = ALONG_Y ? j : i, N = ALONG_Y ? Ny : Nx;
+  const int start = c - Nh / 2;
+  const int h_start = ((c - Nh / 2) < 0) ? Nh / 2 - c : 0;
+  const int h_end = ((c + Nh / 2) >= N) ? Nh - (c + Nh / 2 - N + 1) : Nh;
+  float res[NCOMP];
+#pragma unroll
+  for (int k = 0; k < NCOMP; ++k) res[k] = 0.f;
+  float sum_val = 0.f;
+  for (int ht = h_start; ht < h_end; ++ht) {
+    const float val = cw.w[ht];
+    sum_val += val;
+    const size_t q = ALONG_Y ? ((size_t)i + (size_t)(start + ht) * Nx) : ((size_t)(start + ht) + (size_t)j * Nx);
+#pragma unroll
+    for (int k = 0; k < NCOMP; ++k) res[k] += val * input[NCOMP * q + k];
+  }
+  const size_t o = (size_t)i + (size_t)j * Nx;
+#pragma unroll
+  for (int k = 0; k < NCOMP; ++k) output[NCOMP * o + k] = res[k] / sum_val;
+}
+
+cudaError_t launch_conv(float *buf, float *tmp, int width, int height, int ncomp, const ConvWeights &w,
+                        cudaStream_t st) {
+  dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
+  if (ncomp == 1) {
+    conv_kernel<1, false><<<grid, block, 0, st>>>(buf, tmp, width, height, w);
+    conv_kernel<1, true><<<grid, block, 0, st>>>(tmp, buf, width, height, w);
+  } else {
+    conv_kernel<3, false><<<grid, block, 0, st>>>(buf, tmp, width, height, w);
+    conv_kernel<3, true><<<grid, block, 0, st>>>(tmp, buf, width, height, w);
+  }
+  return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// utils.cl:10-38, uint32 wrap-around arithmetic
+__device__ __forceinline__ uint32_t lcg_hash(uint32_t x, uint32_t y) {
+  uint32_t a = 4421u + (1u + x) * (1u + y) + x + y;
+#pragma unroll
+  for (int i = 0; i < 10; i++) a = (1664525u * a + 1013904223u) % 79197919u;
+  return a;
+}
+__device__ __forceinline__ float random_cl(uint32_t x, uint32_t y) {
+  return ((float)lcg_hash(x, y) * 1.0f) / (float)(79197919);
+}
+__device__ __forceinline__ float rand_int_cl(uint32_t x, uint32_t y, int start, int end) {
+  return (float)(int)((float)start + random_cl(x, y) * (float)(end - start));
+}
+
+__global__ void occlusion_kernel(float *__restrict__ d_output, int Nx, int Ny, int radius, int number_points,
+                                 const float *__restrict__ input_depth) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= Nx || y >= Ny) return;
+  const float MPI_2 = 6.2831853071795f;
+  const float depth0 = input_depth[x + (size_t)y * Nx];
+  float occ = 0.f;
+  for (unsigned i = 0; i < (unsigned)number_points; ++i) {
+    const float r = (float)(unsigned)radius * random_cl((uint32_t)((float)x + rand_int_cl(i, i * i, 0, 1000)),
+                                                        (uint32_t)((float)y + rand_int_cl(i * i, i, 294, 97701)));
+    const float phi = MPI_2 * random_cl((uint32_t)((float)x + rand_int_cl(i * i, i, 0, 1997)),
+                                        (uint32_t)((float)y + rand_int_cl(i, i * i, 569, 17633)));
+    const int x2 = clampi((int)((float)x + r * cosf(phi)), 0, Nx - 1);
+    const int y2 = clampi((int)((float)y + r * sinf(phi)), 0, Ny - 1);
+    const float depth = input_depth[x2 + (size_t)y2 * Nx];
+    occ += (depth < depth0 ? 1.f : 0.f);
+  }
+  d_output[x + (size_t)Nx * y] = occ / (float)(unsigned)number_points;
+}
+
+cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int n_points, const float *depth,
+                             cudaStream_t st) {
+  dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
+  occlusion_kernel<<<grid, block, 0, st>>>(occ, width, height, radius, n_points, depth);
+  return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------------------------
+__global__ void shading_kernel(float *__restrict__ d_output, int Nx, int Ny, const Camera cam, float occ_strength,
+                               const float *__restrict__ input_normals, const float *__restrict__ input_depth,
+                               const float *__restrict__ input_occlusion) {
+  const unsigned x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= (unsigned)Nx || y >= (unsigned)Ny) return;
+  v4 orig, direc;
+  eye_ray(x, y, Nx, Ny, cam, orig, direc);
+  v4 light = mk4(2.f, -1.f, -2.f, 0.f);
+  const float c_ambient = .5f, c_diffuse = .3f, c_specular = .2f;
+  light = mult(cam.invM, light);
+  light = normalize4(light);
+  const size_t p = x + (size_t)Nx * y;
+  v4 normal = mk4(input_normals[3 * p], input_normals[1 + 3 * p], input_normals[2 + 3 * p], 0.f);
+  const float occ = input_occlusion[p];
+  const float depth = input_depth[p];
+  normal = normalize4(normal);
+  const v4 reflect = sub4(scl4(2.f * dot4(light, normal), normal), light);
+  const float diffuse = fmaxf(0.f, dot4(light, normal));
+  const float specular = powf(fmaxf(0.f, dot4(normalize4(reflect), normalize4(direc))), 10.f);
+  float colVal = c_ambient + c_diffuse * diffuse + (diffuse > 0.f ? 1.f : 0.f) * c_specular * specular;
+  colVal = (1.f - occ_strength) * colVal + occ_strength * colVal * (1.f - occ);
+  // iso_kernel.cl:580 has a double literal: the sum is formed in double and rounded once
+  colVal = (float)((double)((1.f - occ_strength) * colVal) + 1.0 * (double)occ_strength * (double)colVal);
+  colVal *= ((depth < __int_as_float(0x7f800000)) ? 1.f : 0.f);
+  d_output[p] = colVal;
+}
+
+cudaError_t launch_shading(float *out, int width, int height, const Camera &cam, float occ_strength,
+                           const float *normals, const float *depth, const float *occ, cudaStream_t st) {
+  dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
+  shading_kernel<<<grid, block, 0, st>>>(out, width, height, cam, occ_strength, normals, depth, occ);
+  return cudaGetLastError();
+}
+
+}  // namespace spv

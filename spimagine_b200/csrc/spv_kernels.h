@@ -1,0 +1,57 @@
+// spv_kernels.h -- argument blocks and host-side launchers shared by the kernel files and the C ABI.
+#pragma once
+#include "../../include/spimcuda.h"
+#include "spv_common.cuh"
+
+namespace spv {
+
+struct MipArgs {
+  Camera cam;
+  Volume vol;
+  const float2 *coarse;  // coarse min/max grid: one cell = 4^3 bricks
+  int cgx, cgy, cgz;
+  float box[6];
+  float min_val, max_val, gamma, alpha_pow;
+  int num_parts, current_part, max_steps, flags;
+  int width, height;
+  float *out, *alpha, *raw;
+  unsigned long long *stats;  // [hit rays, texture samples issued] or nullptr
+};
+
+struct IsoArgs {
+  Camera cam;
+  Volume vol;
+  const float2 *coarse;
+  int cgx, cgy, cgz;
+  float box[6];
+  float iso_val, gamma;
+  int max_steps;
+  int width, height;
+  float *out, *alpha, *depth, *normals;
+  unsigned long long *stats;
+};
+
+struct ConvWeights {
+  float w[32];  // exp(coef*(ht - Nh/2)^2/Nh^2), ht = 0..Nh-1, evaluated on the host
+  int nh;
+};
+
+cudaError_t launch_mip(const MipArgs &a, int dtype, bool linear, bool fast, bool exact, bool skip, bool slab,
+                       bool stats, cudaStream_t st);
+cudaError_t launch_mip_finish(const float *raw, float *out, int n, float minVal, float maxVal, float gamma,
+                              cudaStream_t st);
+
+cudaError_t launch_iso(const IsoArgs &a, int dtype, bool linear, bool exact, bool stats, cudaStream_t st);
+// buf -> tmp (x pass), tmp -> buf (y pass); ncomp = 1 (conv_x/conv_y) or 3 (conv_vec_x/conv_vec_y)
+cudaError_t launch_conv(float *buf, float *tmp, int width, int height, int ncomp, const ConvWeights &w,
+                        cudaStream_t st);
+cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int n_points, const float *depth,
+                             cudaStream_t st);
+cudaError_t launch_shading(float *out, int width, int height, const Camera &cam, float occ_strength,
+                           const float *normals, const float *depth, const float *occ, cudaStream_t st);
+
+// min/max brick grids of the resident volume (built from the point texture)
+cudaError_t launch_build_bricks(const Volume &vol, int dtype, int local_nz, float2 *bricks, float2 *coarse, int cgx,
+                                int cgy, int cgz, float *minmax /* [2] device */, cudaStream_t st);
+
+}  // namespace spv

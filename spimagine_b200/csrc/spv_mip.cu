@@ -1,0 +1,342 @@
+// spv_mip.cu -- maximum-intensity projection kernels (replace max_project_float / max_project_short,
+// spimagine/volumerender/kernels/volume_kernel.cl:20-345).
+//
+//   mip_ref_kernel   the reference's loop structure verbatim (16-unrolled blocks, positions accumulated with
+//                    pos += delta, both attenuation laws, the inner-loop-only break): used for the EXACT
+//                    sampler and whenever alpha_pow != 0.
+//   mip_fast_kernel  alpha_pow == 0 only.  One warp = one 8x4 pixel tile (2x2 quads on consecutive lanes so a
+//                    texture quad is spatially compact), sample positions pos0 + k*delta by fma (so samples can
+//                    be visited in any order), hardware-filtered tex3D, optional empty-space skipping on the
+//                    two-level min/max brick grid, optional slab ownership test for sort-last rendering, results
+//                    staged through shared memory and written with 128-bit stores.
+#include "spv_kernels.h"
+
+namespace spv {
+
+__device__ __forceinline__ float window_value(float col, float minVal, float maxVal, float gamma) {
+  col = (maxVal == 0.f) ? col : (col - minVal) / (maxVal - minVal);
+  if (gamma != 1.f) col = powf(col, gamma);
+  return clampf_cl(col, 0.f, 1.f);
+}
+
+// -------------------------------------------------------------------------------------------------------------
+template <int DT, bool LINEAR, bool EXACT>
+__global__ void __launch_bounds__(128) mip_ref_kernel(const MipArgs a) {
+  const unsigned x = blockIdx.x * 16 + (threadIdx.x & 15);
+  const unsigned y = blockIdx.y * 8 + (threadIdx.x >> 4);
+  const unsigned Nx = a.width, Ny = a.height;
+  if (x >= Nx || y >= Ny) return;
+  const bool isShort = DT != 0;
+  const size_t p = x + (size_t)Nx * y;
+  Ray r = make_ray(x, y, Nx, Ny, a.cam, a.box);
+  if (!r.hit) {
+    a.out[p] = 0.f;
+    a.alpha[p] = isShort ? 0.f : -1.f;  // volume_kernel.cl:88 vs :261
+    return;
+  }
+  float tnear = r.tnear, tfar = r.tfar;
+  v4 orig = r.orig, direc = r.direc;
+  if (tnear < 0.0f) tnear = 0.0f;
+  float colVal = 0.f;
+  const int reducedSteps = a.max_steps / a.num_parts;
+  const int LOOPUNROLL = 16;
+  const float dt = fabsf(tfar - tnear) / (float)((reducedSteps / LOOPUNROLL) * LOOPUNROLL);
+  orig = add4(orig, scl4((float)a.current_part * dt, direc));
+  const v4 delta_pos = scl4(.5f * dt, direc);
+  v4 pos = scl4(0.5f, add4(sadd4(1.f, orig), scl4(tnear, direc)));
+  float newVal;
+  const float minVal = a.min_val, maxVal = a.max_val, alpha_pow = a.alpha_pow;
+  if (alpha_pow == 0.f) {
+    for (int i = 0; i <= reducedSteps / LOOPUNROLL; ++i) {
+#pragma unroll 4
+      for (int j = 0; j < LOOPUNROLL; ++j) {
+        newVal = sample<DT, LINEAR, EXACT>(a.vol, pos.x, pos.y, pos.z);
+        colVal = fmaxf(colVal, newVal);
+        pos = add4(pos, delta_pos);
+      }
+    }
+    colVal = (maxVal == 0.f) ? colVal : (colVal - minVal) / (maxVal - minVal);
+  } else {
+    float cumsum = 1.f;
+    for (int i = 0; i <= reducedSteps / LOOPUNROLL; ++i) {
+      for (int j = 0; j < LOOPUNROLL; ++j) {
+        newVal = sample<DT, LINEAR, EXACT>(a.vol, pos.x, pos.y, pos.z);
+        newVal = (maxVal == 0.f) ? newVal : (newVal - minVal) / (maxVal - minVal);
+        colVal = fmaxf(colVal, cumsum * newVal);
+        if (isShort) cumsum *= (1.f - .1f * alpha_pow * alpha_pow * newVal);         // :312
+        else cumsum *= (1.f - alpha_pow * alpha_pow * clampf_cl(newVal, 0.f, 1.f));  // :146
+        pos = add4(pos, delta_pos);
+        if (cumsum <= 0.01f) break;  // leaves the inner loop only, as in the reference
+      }
+    }
+  }
+  if (a.gamma != 1.f) colVal = powf(colVal, a.gamma);
+  colVal = clampf_cl(colVal, 0.f, 1.f);
+  const float alphaVal = isShort ? tnear : 1.f;  // :329 vs :168
+  if (a.current_part == 0) {
+    a.out[p] = colVal;
+    a.alpha[p] = alphaVal;
+  } else {
+    a.out[p] = fmaxf(colVal, a.out[p]);
+    a.alpha[p] = fmaxf(alphaVal, a.alpha[p]);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Fast path.
+struct Marcher {
+  float u0, v0, w0, du, dv, dw;  // unnormalised texel coordinates of sample k: u0 + k*du
+};
+
+template <int DT, bool LINEAR, bool SLAB>
+__device__ __forceinline__ float fetch_k(const Volume &V, const Marcher &m, float k) {
+  return sample_tmu_uvw<DT, LINEAR>(V, fmaf(k, m.du, m.u0), fmaf(k, m.dv, m.v0), fmaf(k, m.dw, m.w0));
+}
+
+// does sample k belong to this slab?  (its footprint starts in global slices [z0, z1))
+__device__ __forceinline__ bool owns_k(const Volume &V, const Marcher &m, float k) {
+  float wb = fmaf(k, m.dw, m.w0) - 0.5f;
+  float kf = fminf(fmaxf(floorf(wb), 0.f), (float)(V.nz - 1));
+  return kf >= (float)V.z0 && kf < (float)V.z1;
+}
+
+// clamped brick coordinate of a texel-centre coordinate c = u - 0.5
+__device__ __forceinline__ int brick_coord(float c, int g, int shift) {
+  // floor, then arithmetic shift; clamp handles everything outside (incl. huge/NaN -> 0)
+  float f = fminf(fmaxf(floorf(c), -1.f), 2147483000.f);
+  int i = (int)f >> shift;
+  return min(max(i, 0), g - 1);
+}
+
+template <int DT, bool LINEAR, bool SKIP, bool SLAB, bool STATS>
+__global__ void __launch_bounds__(128) mip_fast_kernel(const MipArgs a) {
+  __shared__ __align__(16) float s_out[4][32];
+  __shared__ __align__(16) float s_alpha[4][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
+  const int ly = ((lane >> 1) & 1) | ((lane >> 2) & 2);
+  const unsigned tx0 = blockIdx.x * 16 + (warp & 1) * 8, ty0 = blockIdx.y * 8 + (warp >> 1) * 4;
+  const unsigned x = tx0 + lx, y = ty0 + ly;
+  const unsigned Nx = a.width, Ny = a.height;
+  const bool inb = x < Nx && y < Ny;
+  const bool isShort = DT != 0;
+  const Volume &V = a.vol;
+
+  Ray r = make_ray(x, y, Nx, Ny, a.cam, a.box);
+  const bool hit = inb && r.hit;
+  float tnear = r.tnear;
+  if (tnear < 0.0f) tnear = 0.0f;
+  float cur = 0.f;
+  unsigned long long nfetch = 0;
+
+  if (hit) {
+    const int reducedSteps = a.max_steps / a.num_parts;
+    const int S = (reducedSteps / 16 + 1) * 16;
+    const float dt = fabsf(r.tfar - tnear) / (float)((reducedSteps / 16) * 16);
+    v4 orig = add4(r.orig, scl4((float)a.current_part * dt, r.direc));
+    const v4 delta_pos = scl4(.5f * dt, r.direc);
+    const v4 pos0 = scl4(0.5f, add4(sadd4(1.f, orig), scl4(tnear, r.direc)));
+    Marcher m;
+    m.u0 = pos0.x * V.fnx; m.v0 = pos0.y * V.fny; m.w0 = pos0.z * V.fnz;
+    m.du = delta_pos.x * V.fnx; m.dv = delta_pos.y * V.fny; m.dw = delta_pos.z * V.fnz;
+
+    if (!SKIP) {
+      if (!SLAB) {
+        for (int k = 0; k < S; k += 16) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = fetch_k<DT, LINEAR, SLAB>(V, m, (float)(k + j));
+#pragma unroll
+          for (int j = 0; j < 16; ++j) cur = fmaxf(cur, v[j]);
+        }
+        if (STATS) nfetch += S;
+      } else {
+        for (int k = 0; k < S; ++k) {
+          if (owns_k(V, m, (float)k)) {
+            cur = fmaxf(cur, fetch_k<DT, LINEAR, SLAB>(V, m, (float)k));
+            if (STATS) ++nfetch;
+          }
+        }
+      }
+    } else {
+      // ---- pre-pass: every PRE-th sample gives a true lower bound of the ray maximum cheaply ----
+      constexpr int PRE = 8;
+      for (int k = 0; k < S; k += PRE * 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float kk = (float)(k + j * PRE);
+          const bool ok = (k + j * PRE < S) && (!SLAB || owns_k(V, m, kk));
+          v[j] = ok ? fetch_k<DT, LINEAR, SLAB>(V, m, kk) : 0.f;
+          if (STATS) nfetch += ok;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur = fmaxf(cur, v[j]);
+      }
+      // ---- coarse DDA over cells of CBRICK texels; descend to per-sample brick tests where needed ----
+      constexpr int CSHIFT = BRICK_SHIFT + 2;
+      constexpr float CB = (float)(1 << CSHIFT);
+      // texel-centre coordinates c(k) = (u0 - .5) + k*du ; local z for the brick grid
+      const float cx0 = m.u0 - 0.5f, cy0 = m.v0 - 0.5f, cz0 = m.w0 - 0.5f - (float)V.z_lo;
+      int ix = (int)floorf(cx0 / CB), iy = (int)floorf(cy0 / CB), iz = (int)floorf(cz0 / CB);
+      const float inf = __int_as_float(0x7f800000);
+      const int sx = m.du > 0.f ? 1 : -1, sy = m.dv > 0.f ? 1 : -1, sz = m.dw > 0.f ? 1 : -1;
+      const float tdx = m.du != 0.f ? CB / fabsf(m.du) : inf;
+      const float tdy = m.dv != 0.f ? CB / fabsf(m.dv) : inf;
+      const float tdz = m.dw != 0.f ? CB / fabsf(m.dw) : inf;
+      float tmx = m.du != 0.f ? ((float)(ix + (sx > 0)) * CB - cx0) / m.du : inf;
+      float tmy = m.dv != 0.f ? ((float)(iy + (sy > 0)) * CB - cy0) / m.dv : inf;
+      float tmz = m.dw != 0.f ? ((float)(iz + (sz > 0)) * CB - cz0) / m.dw : inf;
+      int k0 = 0;
+      const int max_iter = 3 * S + a.cgx + a.cgy + a.cgz + 16;  // NaN/degenerate rays cannot spin here
+      for (int it = 0; it < max_iter && k0 < S; ++it) {
+        const float tout = fminf(fminf(tmx, tmy), tmz);
+        // samples k < tout lie in this coarse cell (to within the dilation slack)
+        int k1 = tout >= (float)S ? S : (int)ceilf(tout);
+        k1 = min(max(k1, k0), S);
+        if (k1 > k0) {
+          const int cxi = min(max(ix, 0), a.cgx - 1), cyi = min(max(iy, 0), a.cgy - 1), czi = min(max(iz, 0), a.cgz - 1);
+          const float cmax = __ldg(a.coarse + ((size_t)czi * a.cgy + cyi) * a.cgx + cxi).y;
+          if (cmax > cur) {
+            for (int k = k0; k < k1; k += 4) {
+              float v[4];
+              bool need[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float kk = (float)(k + j);
+                need[j] = false;
+                if (k + j < k1 && (!SLAB || owns_k(V, m, kk))) {
+                  const int bx = brick_coord(fmaf(kk, m.du, cx0), V.gx, BRICK_SHIFT);
+                  const int by = brick_coord(fmaf(kk, m.dv, cy0), V.gy, BRICK_SHIFT);
+                  const int bz = brick_coord(fmaf(kk, m.dw, cz0), V.gz, BRICK_SHIFT);
+                  need[j] = brick_at(V, bx, by, bz).y > cur;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[j] = need[j] ? fetch_k<DT, LINEAR, SLAB>(V, m, (float)(k + j)) : 0.f;
+                if (STATS) nfetch += need[j];
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) cur = fmaxf(cur, v[j]);
+            }
+          }
+        }
+        k0 = k1;
+        // advance to the next coarse cell along the axis whose boundary comes first
+        if (tmx <= tmy && tmx <= tmz) { ix += sx; tmx += tdx; }
+        else if (tmy <= tmz) { iy += sy; tmy += tdy; }
+        else { iz += sz; tmz += tdz; }
+      }
+      for (int k = k0; k < S; ++k) {  // only reached when the traversal was cut short: sample the rest plainly
+        if (!SLAB || owns_k(V, m, (float)k)) {
+          cur = fmaxf(cur, fetch_k<DT, LINEAR, SLAB>(V, m, (float)k));
+          if (STATS) ++nfetch;
+        }
+      }
+    }
+  }
+
+  if (STATS) {
+    unsigned long long nh = hit ? 1ull : 0ull;
+    for (int o = 16; o > 0; o >>= 1) {
+      nfetch += __shfl_down_sync(0xffffffffu, nfetch, o);
+      nh += __shfl_down_sync(0xffffffffu, nh, o);
+    }
+    if (lane == 0 && a.stats) {
+      atomicAdd(a.stats + 0, nh);
+      atomicAdd(a.stats + 1, nfetch);
+    }
+  }
+
+  // ---- epilogue ----
+  const float alphaVal = hit ? (isShort ? tnear : 1.f) : (isShort ? 0.f : -1.f);
+  float outVal;
+  float *dst;
+  if (a.flags & SPV_MIP_RAW_ONLY) {
+    outVal = hit ? cur : -1.f;  // un-windowed partial maximum (>= 0), -1 marks a miss; composited across
+    dst = a.raw;                 // GPUs with max before spv_mip_finish
+  } else {
+    outVal = hit ? window_value(cur, a.min_val, a.max_val, a.gamma) : 0.f;
+    dst = a.out;
+  }
+  const bool vec_ok = (Nx % 4 == 0) && (tx0 + 8 <= Nx) && (ty0 + 4 <= Ny) && a.current_part == 0;
+  if (vec_ok) {
+    s_out[warp][ly * 8 + lx] = outVal;
+    s_alpha[warp][ly * 8 + lx] = alphaVal;
+    __syncwarp();
+    // 8 float4 per plane: lanes 0-7 store the value plane, lanes 8-15 the alpha plane
+    if (lane < 16) {
+      const int q = lane & 7, row = q >> 1, half = q & 1;
+      const float *src = (lane < 8 ? s_out[warp] : s_alpha[warp]) + row * 8 + half * 4;
+      float *base = lane < 8 ? dst : a.alpha;
+      *reinterpret_cast<float4 *>(base + (size_t)(ty0 + row) * Nx + tx0 + half * 4) =
+          *reinterpret_cast<const float4 *>(src);
+    }
+  } else if (inb) {
+    const size_t p = x + (size_t)Nx * y;
+    if (a.current_part == 0) {
+      dst[p] = outVal;
+      a.alpha[p] = alphaVal;
+    } else {  // multi-pass rendering: merge into what earlier parts left (volume_kernel.cl:172-182)
+      dst[p] = fmaxf(outVal, dst[p]);
+      a.alpha[p] = fmaxf(alphaVal, a.alpha[p]);
+    }
+  }
+}
+
+// window + gamma of the composited raw maximum (sort-last renders)
+__global__ void mip_finish_kernel(const float *raw, float *out, int n, float minVal, float maxVal, float gamma) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = raw[i];  // -1 marks a miss (every GPU agrees: the box test does not depend on the slab)
+  out[i] = v < 0.f ? 0.f : window_value(v, minVal, maxVal, gamma);
+}
+
+// -------------------------------------------------------------------------------------------------------------
+template <int DT, bool LINEAR>
+static cudaError_t launch_fast(const MipArgs &a, bool skip, bool slab, bool stats, cudaStream_t st) {
+  dim3 grid((a.width + 15) / 16, (a.height + 7) / 8), block(128);
+#define SPV_FAST(SK, SL, STT) mip_fast_kernel<DT, LINEAR, SK, SL, STT><<<grid, block, 0, st>>>(a)
+  if (stats) {
+    if (skip) { if (slab) SPV_FAST(true, true, true); else SPV_FAST(true, false, true); }
+    else { if (slab) SPV_FAST(false, true, true); else SPV_FAST(false, false, true); }
+  } else {
+    if (skip) { if (slab) SPV_FAST(true, true, false); else SPV_FAST(true, false, false); }
+    else { if (slab) SPV_FAST(false, true, false); else SPV_FAST(false, false, false); }
+  }
+#undef SPV_FAST
+  return cudaGetLastError();
+}
+
+template <int DT, bool LINEAR>
+static cudaError_t launch_ref(const MipArgs &a, bool exact, cudaStream_t st) {
+  dim3 grid((a.width + 15) / 16, (a.height + 7) / 8), block(128);
+  if (exact) mip_ref_kernel<DT, LINEAR, true><<<grid, block, 0, st>>>(a);
+  else mip_ref_kernel<DT, LINEAR, false><<<grid, block, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <int DT>
+static cudaError_t launch_dt(const MipArgs &a, bool linear, bool fast, bool exact, bool skip, bool slab, bool stats,
+                             cudaStream_t st) {
+  if (fast) return linear ? launch_fast<DT, true>(a, skip, slab, stats, st) : launch_fast<DT, false>(a, skip, slab, stats, st);
+  return linear ? launch_ref<DT, true>(a, exact, st) : launch_ref<DT, false>(a, exact, st);
+}
+
+cudaError_t launch_mip(const MipArgs &a, int dtype, bool linear, bool fast, bool exact, bool skip, bool slab,
+                       bool stats, cudaStream_t st) {
+  switch (dtype) {
+    case 0: return launch_dt<0>(a, linear, fast, exact, skip, slab, stats, st);
+    case 1: return launch_dt<1>(a, linear, fast, exact, skip, slab, stats, st);
+    default: return launch_dt<2>(a, linear, fast, exact, skip, slab, stats, st);
+  }
+}
+
+cudaError_t launch_mip_finish(const float *raw, float *out, int n, float minVal, float maxVal, float gamma,
+                              cudaStream_t st) {
+  mip_finish_kernel<<<(n + 255) / 256, 256, 0, st>>>(raw, out, n, minVal, maxVal, gamma);
+  return cudaGetLastError();
+}
+
+}  // namespace spv

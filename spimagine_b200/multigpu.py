@@ -1,0 +1,175 @@
+"""Multi-GPU rendering: one process per GPU (torch.distributed), new relative to the reference, which is
+single-device.
+
+  partition_slabs / SlabMaxProjector   sort-last max projection of a volume split into z-slabs.  Every rank
+      marches the SAME rays (global camera, tnear/tfar, dt, sample indices) but evaluates only the samples
+      whose trilinear footprint starts in its own slices; the un-windowed partial maxima are merged with one
+      all-reduce(MAX) over NCCL / NVLink and windowed afterwards.  max is associative, commutative and
+      idempotent, so the composite equals the single-GPU render bit for bit.
+  frames_for_rank / TimelapsePlayer    3D+t playback: frame t is rendered by rank t mod world, no data-path
+      collective at all.
+
+torch is plumbing here (process group, the all-reduce on a tensor that aliases the renderer's device
+buffer); all rendering is libspimcuda.
+"""
+from __future__ import absolute_import, print_function
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .volumerender import VolumeRenderer
+
+
+def partition_slabs(nz, world):
+    """Split slices [0, nz) into `world` contiguous, near-equal, non-empty slabs -> list of (z0, z1)."""
+    if world < 1 or nz < world:
+        raise ValueError("cannot split %d slices over %d ranks" % (nz, world))
+    base, rem = divmod(nz, world)
+    out, z = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((z, z + n))
+        z += n
+    return out
+
+
+def slab_with_halo(z0, z1, nz):
+    """Slices a rank must hold to evaluate the samples it owns: one halo slice either side."""
+    return max(z0 - 1, 0), min(z1 + 1, nz)
+
+
+def frames_for_rank(n_frames, rank, world):
+    """Frame sharding for timelapse playback: frame t -> rank t mod world."""
+    return list(range(rank, n_frames, world))
+
+
+def composite_max(tensor, group=None):
+    """In-place element-wise maximum over all ranks (the sort-last composite).  Bit-exact for any rank count."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.MAX, group=group)
+    return tensor
+
+
+class _DevBuffer(object):
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can alias it without a copy."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class SlabMaxProjector(VolumeRenderer):
+    """Sort-last max projection across the ranks of a torch.distributed process group.
+
+    Same setters as VolumeRenderer.  `set_data(volume)` takes the WHOLE (Nz, Ny, Nx) volume (or anything
+    sliceable along z, e.g. a memmap) and uploads only this rank's slab + halo; `set_slab(slab, gnz, z0, z1)`
+    takes the slab directly.  `render()` leaves the composited image in `output` on every rank.
+    """
+
+    def __init__(self, size=None, interpolation='linear', group=None, rank=None, world=None, **kw):
+        import torch
+        import torch.distributed as dist
+        self._torch = torch
+        self._dist = dist
+        self.group = group
+        if rank is None or world is None:
+            if dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(group), dist.get_world_size(group)
+            else:
+                rank, world = 0, 1
+        self.rank, self.world = rank, world
+        super(SlabMaxProjector, self).__init__(size, interpolation, **kw)
+
+    def set_data(self, data, autoConvert=True, copyData=False):
+        if not autoConvert and not data.dtype in self.dtypes:
+            raise NotImplementedError("data type should be either %s not %s" % (self.dtypes, data.dtype))
+        nz = data.shape[0]
+        z0, z1 = partition_slabs(nz, self.world)[self.rank]
+        lo, hi = slab_with_halo(z0, z1, nz)
+        slab = np.asarray(data[lo:hi])
+        if slab.dtype.type not in self.dtypes:
+            slab = slab.astype(self.dtype, copy=False)
+        self.set_slab(slab, nz, z0, z1)
+
+    def set_slab(self, slab, gnz, z0, z1, device_ptr=None):
+        """slab: ndarray holding global slices [max(z0-1,0), min(z1+1,gnz)); or pass device_ptr (int) to a
+        C-order device copy of it together with slab=(dtype, ny, nx)."""
+        lo, hi = slab_with_halo(z0, z1, gnz)
+        if device_ptr is None:
+            slab = np.ascontiguousarray(slab)
+            if slab.shape[0] != hi - lo:
+                raise ValueError("slab holds %d slices, expected %d (with halo)" % (slab.shape[0], hi - lo))
+            dtype, ny, nx = slab.dtype, slab.shape[1], slab.shape[2]
+            ptr, on_dev = slab.ctypes.data, 0
+        else:
+            dtype, ny, nx = slab
+            ptr, on_dev = int(device_ptr), 1
+        dtype = np.dtype(dtype)
+        self.set_dtype(dtype.type)
+        self.dataSlices = None
+        self.set_shape((nx, ny, gnz))
+        self.slab = (z0, z1)
+        self._check(self._lib.spv_set_volume_slab(self._ctx, ptr, on_dev, _lib.DTYPE_CODES[dtype], nx, ny, gnz,
+                                                  z0, z1))
+        self._need_alloc = True
+        self.update_matrices()
+
+    def _raw_tensor(self):
+        p = C.c_void_p()
+        self._check(self._lib.spv_device_ptr(self._ctx, _lib.BUF_RAW, C.byref(p)))
+        return self._torch.as_tensor(_DevBuffer(p.value, (self.height, self.width)),
+                                     device="cuda:%d" % self.device)
+
+    def _render_max_project(self, dtype=np.float32, numParts=1, currentPart=0):
+        if self.alphaPow != 0 or numParts != 1:
+            raise NotImplementedError("sort-last compositing needs alpha_pow == 0 and numParts == 1 "
+                                      "(front-to-back attenuation is order dependent)")
+        p = _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma), 0.,
+                           1, 0, int(self.max_steps), _lib.MIP_RAW_ONLY)
+        torch = self._torch
+        if self.world > 1:
+            # render on torch's current stream so the collective is ordered after the kernel without a host sync
+            stream = torch.cuda.current_stream(self.device)
+            self._check(self._lib.spv_set_stream(self._ctx, C.c_void_p(stream.cuda_stream)))
+        self._check(self._lib.spv_render_mip(self._ctx, C.byref(p)))
+        if self.world > 1:
+            composite_max(self._raw_tensor(), self.group)
+        self._check(self._lib.spv_mip_finish(self._ctx, C.byref(p)))
+        flat, n = self._fetch(2)
+        shape = (self.height, self.width)
+        self.output = flat[:n].reshape(shape)
+        self.output_alpha = flat[n:2 * n].reshape(shape)
+
+    def _render_isosurface(self, raw_only=False):
+        raise NotImplementedError("sort-last iso_surface is not implemented yet")
+
+
+class TimelapsePlayer(object):
+    """Frame-sharded 3D+t playback: rank r renders frames r, r+world, ... of a (T, Nz, Ny, Nx) source."""
+
+    def __init__(self, size, rank=0, world=1, **kw):
+        self.rank, self.world = rank, world
+        self.rend = VolumeRenderer(size, **kw)
+
+    def my_frames(self, n_frames):
+        return frames_for_rank(n_frames, self.rank, self.world)
+
+    def render_frames(self, source, modelViews=None, **render_kw):
+        """source[t] -> (Nz, Ny, Nx) ndarray.  Returns {t: image} for the frames this rank owns."""
+        out = {}
+        first = True
+        for t in self.my_frames(len(source)):
+            vol = source[t]
+            if first:
+                self.rend.set_data(vol)
+                first = False
+            else:
+                self.rend.update_data(vol)
+            if modelViews is not None:
+                self.rend.set_modelView(modelViews[t])
+            self.rend.render(**render_kw)
+            out[t] = self.rend.output
+        return out

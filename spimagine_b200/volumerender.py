@@ -1,0 +1,369 @@
+"""VolumeRenderer -- drop-in for spimagine.volumerender.volumerender.VolumeRenderer on a B200.
+
+Same class name, method names, argument meaning, defaults and error behaviour as the reference
+(spimagine/volumerender/volumerender.py:59-547); the gputools / pyopencl plumbing underneath
+(OCLProgram.run_kernel, OCLArray, OCLImage) is replaced by ctypes calls into libspimcuda.so
+(include/spimcuda.h), hand-written CUDA for sm_100a.  There is no CPU path: constructing a renderer
+without the library or without a CUDA device raises.
+
+    rend = VolumeRenderer((400, 400))
+    rend.set_data(d)                      # float32 / uint16 / uint8, shape (Nz, Ny, Nx)
+    rend.set_units([1., 1., .1])
+    rend.set_projection(mat4_perspective(60, 1., 1, 10))
+    rend.set_modelView(np.dot(mat4_translate(0, 0, -7), mat4_scale(.7, .7, .7)))
+    rend.render()                         # returns None, like the reference
+    img = rend.output
+
+Additions that the reference does not have (all keyword-only / opt-in, defaults keep reference behaviour):
+    sampler="tmu" | "exact"      hardware-filtered texture fetches, or fp32 software trilinear that
+                                 follows the reference loop operation by operation (parity runs)
+    max_steps=200                the reference bakes config.__DEFAULTMAXSTEPS__ in at compile time
+    int_filter="linear"|"nearest" what a LINEAR sampler means for integer volumes (undefined in OpenCL)
+    pinned_outputs=False         True: rend.output* are views of pinned staging memory (no extra copy)
+    data_min / data_max          global min / max of the resident volume, computed during upload
+"""
+from __future__ import absolute_import, print_function
+
+import ctypes as C
+import logging
+import os
+from time import time
+
+import numpy as np
+from scipy.linalg import inv
+
+from . import _lib
+from .utils.transform_matrices import *  # noqa: F401,F403  (the reference module re-exports these too)
+from .utils.transform_matrices import mat4_identity, mat4_perspective, mat4_scale
+
+logger = logging.getLogger(__name__)
+
+DEFAULT_MAX_STEPS = 200  # spimagine/config/config.py:27 "max_steps"
+
+
+class _DataImage(object):
+    """What callers read from `rend.dataImg`: .shape == (Nx, Ny, Nz) and .dtype
+    (spimagine/gui/glwidget.py:333-336, volumerender.py:320)."""
+
+    def __init__(self, shape_xyz, dtype):
+        self.shape = tuple(int(s) for s in shape_xyz)
+        self.dtype = np.dtype(dtype)
+
+
+class VolumeRenderer(object):
+    """renders a data volume by ray casting / max projection"""
+    dtypes = [np.float32, np.uint16, np.uint8]
+    # the reference maps these to "-D SAMPLER_FILTER=..." build options; here: texture filter mode
+    interpolation_defines = {"linear": 1, "nearest": 0}
+
+    def __init__(self, size=None, interpolation='linear', sampler="tmu", max_steps=None, device=None,
+                 int_filter="linear", pinned_outputs=False):
+        self._lib = _lib.load()
+        self._ctx = _lib._CTX()
+        if device is None:
+            device = int(os.environ.get("SPIMAGINE_CUDA_DEVICE", "0"))
+        self.device = device
+        self.isGPU = True
+        self.max_steps = int(max_steps) if max_steps is not None else int(
+            os.environ.get("SPIMAGINE_MAX_STEPS", DEFAULT_MAX_STEPS))
+        self.pinned_outputs = bool(pinned_outputs)
+        w, h = size if size else (200, 200)
+        rc = self._lib.spv_create(int(device), int(w), int(h), C.byref(self._ctx))
+        _lib.check(rc, None)
+        # device memory is not the limit it was for OpenCL images; keep the reference's rule with the
+        # free memory of this GPU so that set_data's stride-downsampling still exists
+        self.memMax = .7 * 160e9
+        self.rebuild_program(interpolation=interpolation)
+        self.set_sampler(sampler)
+        self.set_int_filter(int_filter)
+
+        self.projection = np.zeros((4, 4))
+        self.modelView = np.zeros((4, 4))
+        self.width, self.height = int(w), int(h)
+        self.reset_buffer(_realloc=False)
+
+        self.set_dtype()
+        self.set_gamma()
+        self.set_max_val()
+        self.set_min_val()
+        self.set_occ_strength(.1)
+        self.set_occ_radius(21)
+        self.set_occ_n_points(30)
+        self.set_alpha_pow()
+        self.set_box_boundaries()
+        self.set_units()
+        self.set_modelView()
+        self.set_projection()
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.spv_destroy(self._ctx)
+            self._ctx = _lib._CTX()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        _lib.check(rc, self._ctx)
+
+    # ------------------------------------------------------------------ configuration
+    def rebuild_program(self, interpolation="linear"):
+        """The reference rebuilds its OpenCL program with -D SAMPLER_FILTER=...; here the filter mode is a
+        property of the texture object, so this only validates and records it."""
+        if interpolation not in VolumeRenderer.interpolation_defines:
+            raise KeyError("interpolation = '%s' not defined ,valid: %s" % (
+                interpolation, list(VolumeRenderer.interpolation_defines.keys())))
+        self.interpolation = interpolation
+        self._check(self._lib.spv_set_interp(self._ctx, VolumeRenderer.interpolation_defines[interpolation]))
+        self.proc = self  # callers only test for its presence
+
+    def set_sampler(self, sampler="tmu"):
+        codes = {"tmu": _lib.SAMPLER_TMU, "exact": _lib.SAMPLER_EXACT}
+        if sampler not in codes:
+            raise KeyError("sampler = '%s' not defined, valid: %s" % (sampler, list(codes.keys())))
+        self.sampler = sampler
+        self._check(self._lib.spv_set_sampler(self._ctx, codes[sampler]))
+
+    def set_int_filter(self, int_filter="linear"):
+        if int_filter not in ("linear", "nearest"):
+            raise KeyError("int_filter = '%s' not defined, valid: ['linear', 'nearest']" % int_filter)
+        self.int_filter = int_filter
+        self._check(self._lib.spv_set_int_filter(self._ctx, int(int_filter == "linear")))
+
+    def set_skipping(self, on=True):
+        self._check(self._lib.spv_set_skipping(self._ctx, int(bool(on))))
+
+    def set_dtype(self, dtype=None):
+        if hasattr(self, "dtype") and dtype is self.dtype:
+            return
+        if dtype is None:
+            dtype = self.dtypes[0]
+        if dtype in self.dtypes:
+            self.dtype = dtype
+        else:
+            raise NotImplementedError("data type should be either %s not %s" % (self.dtypes, dtype))
+        self.reset_buffer(_realloc=False)
+
+    def resize(self, size):
+        self.width, self.height = int(size[0]), int(size[1])
+        self.reset_buffer()
+
+    def reset_buffer(self, _realloc=True):
+        if _realloc:
+            self._check(self._lib.spv_resize(self._ctx, self.width, self.height))
+        self.output = np.zeros((self.height, self.width), dtype=np.float32)
+        self.output_alpha = np.zeros((self.height, self.width), dtype=np.float32)
+        self.output_depth = np.zeros((self.height, self.width), dtype=np.float32)
+        self.output_normals = np.zeros((self.height, self.width, 3), dtype=np.float32)
+        self.output_occlusion = np.zeros((self.height, self.width), dtype=np.float32)
+
+    def _get_downsampled_data_slices(self, data):
+        """in case data is bigger than the memory budget, returns the strided slices to render, else None"""
+        Nstep = int(np.ceil((1. * data.nbytes / self.memMax) ** (1. / 3)))
+        slices = tuple(slice(0, d, Nstep) for d in data.shape)
+        if Nstep > 1:
+            logger.info("downsample image by factor of  %s" % Nstep)
+            return slices
+        return None
+
+    def set_max_val(self, maxVal=0.):
+        self.maxVal = maxVal
+
+    def set_min_val(self, minVal=0.):
+        self.minVal = minVal
+
+    def set_gamma(self, gamma=1.):
+        self.gamma = gamma
+
+    def set_occ_strength(self, occ=.2):
+        self.occ_strength = occ
+
+    def set_occ_radius(self, rad=21):
+        self.occ_radius = rad
+
+    def set_occ_n_points(self, n_points=31):
+        self.occ_n_points = n_points
+
+    def set_alpha_pow(self, alphaPow=0.):
+        self.alphaPow = alphaPow
+
+    # ------------------------------------------------------------------ data
+    def set_data(self, data, autoConvert=True, copyData=False):
+        logger.debug("set_data")
+        if not autoConvert and not data.dtype in self.dtypes:
+            raise NotImplementedError("data type should be either %s not %s" % (self.dtypes, data.dtype))
+        if data.dtype.type in self.dtypes:
+            self.set_dtype(data.dtype.type)
+            _data = data
+        else:
+            print("converting type from %s to %s" % (data.dtype.type, self.dtype))
+            _data = data.astype(self.dtype, copy=False)
+        self.dataSlices = self._get_downsampled_data_slices(_data)
+        if self.dataSlices is not None:
+            self.set_shape(_data[self.dataSlices].shape[::-1])
+        else:
+            self.set_shape(_data.shape[::-1])
+        t = time()
+        self.update_data(_data, copyData=copyData)
+        logger.debug("update data: %s ms" % (1000. * (time() - t)))
+        self.update_matrices()
+
+    def set_shape(self, dataShape):
+        """dataShape = (Nx, Ny, Nz); the device array is (re)allocated on the next update_data."""
+        self.dataImg = _DataImage(dataShape, self.dtype)
+        self._need_alloc = True
+
+    def update_data(self, data, copyData=False):
+        if self.dataSlices is not None:
+            self._data = data[self.dataSlices].copy()
+        else:
+            self._data = data.copy() if copyData else data
+        if self._data.dtype != self.dtype:
+            self._data = self._data.astype(self.dtype, copy=False)
+        host = np.ascontiguousarray(self._data)
+        Nx, Ny, Nz = self.dataImg.shape
+        if host.shape != (Nz, Ny, Nx):
+            raise ValueError("data shape %s does not match the volume shape %s" % (host.shape, (Nz, Ny, Nx)))
+        if getattr(self, "_need_alloc", True):
+            rc = self._lib.spv_set_volume(self._ctx, host.ctypes.data, _lib.DTYPE_CODES[host.dtype], Nx, Ny, Nz)
+            self._need_alloc = False
+        else:
+            rc = self._lib.spv_update_volume(self._ctx, host.ctypes.data)
+        self._check(rc)
+
+    @property
+    def data_min_max(self):
+        """(min, max) of the resident volume: what GLWidget._get_min_max computes (gui/glwidget.py:328-344)."""
+        lo, hi = C.c_float(), C.c_float()
+        self._check(self._lib.spv_volume_minmax(self._ctx, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    # ------------------------------------------------------------------ camera
+    def set_box_boundaries(self, boxBounds=[-1, 1, -1, 1, -1, 1]):
+        self.boxBounds = np.array(boxBounds)
+
+    def set_units(self, stackUnits=np.ones(3)):
+        self.stackUnits = np.array(stackUnits)
+
+    def set_projection(self, projection=mat4_perspective()):
+        self.projection = projection
+        self.update_matrices()
+
+    def set_modelView(self, modelView=mat4_identity()):
+        self.modelView = 1. * modelView
+        self.update_matrices()
+
+    def update_matrices(self):
+        if hasattr(self, "dataImg"):
+            mScale = self._stack_scale_mat()
+            invM = inv(np.dot(self.modelView, mScale))
+            invP = inv(self.projection)
+            self._invM = np.ascontiguousarray(invM.flatten().astype(np.float32))
+            self._invP = np.ascontiguousarray(invP.flatten().astype(np.float32))
+            self._check(self._lib.spv_set_matrices(self._ctx, _lib.fp(self._invP), _lib.fp(self._invM)))
+
+    def _stack_scale_mat(self):
+        # scaling the data according to size and units
+        Nx, Ny, Nz = self.dataImg.shape
+        dx, dy, dz = self.stackUnits
+        maxDim = max(d * N for d, N in zip([dx, dy, dz], [Nx, Ny, Nz]))
+        return mat4_scale(1. * dx * Nx / maxDim, 1. * dy * Ny / maxDim, 1. * dz * Nz / maxDim)
+
+    # ------------------------------------------------------------------ rendering
+    def _box(self):
+        return (C.c_float * 6)(*[float(b) for b in self.boxBounds])
+
+    def _fetch(self, planes):
+        """One device->host transfer of the leading result planes [out | alpha | depth | occ | normals]."""
+        n = self.width * self.height
+        host = _lib._FP()
+        self._check(self._lib.spv_read_pinned(self._ctx, planes, C.byref(host)))
+        flat = np.ctypeslib.as_array(host, shape=(planes * n,))
+        if not self.pinned_outputs:
+            flat = flat.copy()
+        return flat, n
+
+    def _render_max_project(self, dtype=np.float32, numParts=1, currentPart=0):
+        if dtype not in [np.uint16, np.uint8, np.float32]:
+            raise NotImplementedError("wrong dtype: %s", dtype)
+        p = _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma),
+                           float(self.alphaPow), int(numParts), int(currentPart), int(self.max_steps), 0)
+        self._check(self._lib.spv_render_mip(self._ctx, C.byref(p)))
+        flat, n = self._fetch(2)
+        shape = (self.height, self.width)
+        self.output = flat[:n].reshape(shape)
+        self.output_alpha = flat[n:2 * n].reshape(shape)
+        # the reference reads back buf_depth here although max_project never writes it (garbage); zeros instead
+        if self.output_depth.shape != shape:
+            self.output_depth = np.zeros(shape, np.float32)
+
+    def _render_isosurface(self, raw_only=False):
+        """iso surface with ambient occlusion: iso_surface -> normal blur -> occlusion -> blur -> shading"""
+        p = _lib.IsoParams(self._box(), float(self.maxVal / 2), float(self.gamma), int(self.max_steps),
+                           float(self.occ_strength), int(self.occ_radius), int(self.occ_n_points),
+                           _lib.ISO_RAW_ONLY if raw_only else 0)
+        self._check(self._lib.spv_render_iso(self._ctx, C.byref(p)))
+        flat, n = self._fetch(7)
+        shape = (self.height, self.width)
+        self.output = flat[:n].reshape(shape)
+        self.output_alpha = flat[n:2 * n].reshape(shape)
+        self.output_depth = flat[2 * n:3 * n].reshape(shape)
+        self.output_occlusion = flat[3 * n:4 * n].reshape(shape)
+        self.output_normals = flat[4 * n:7 * n].reshape(shape + (3,))
+
+    def render(self, data=None, stackUnits=None,
+               minVal=None, maxVal=None, gamma=None,
+               modelView=None, projection=None,
+               boxBounds=None, return_alpha=False, method="max_project",
+               numParts=1, currentPart=0):
+        if data is not None:
+            self.set_data(data)
+        if maxVal is not None:
+            self.set_max_val(maxVal)
+        if minVal is not None:
+            self.set_min_val(minVal)
+        if gamma is not None:
+            self.set_gamma(gamma)
+        if stackUnits is not None:
+            self.set_units(stackUnits)
+        if modelView is not None:
+            self.set_modelView(modelView)
+        if projection is not None:
+            self.set_projection(projection)
+        # boxBounds and return_alpha are accepted and ignored, as in the reference (volumerender.py:508-547)
+        if not hasattr(self, 'dataImg'):
+            print("no data provided, set_data(data) before")
+            return
+        if modelView is None and not hasattr(self, 'modelView'):
+            print("no modelView provided and set_modelView() not called before!")
+            return
+        if method == "max_project":
+            self._render_max_project(self.dtype, numParts, currentPart)
+        if method == "iso_surface":
+            self._render_isosurface()
+        if method == "iso_surface_raw":  # addition: the iso_surface kernel alone (parity tests)
+            self._render_isosurface(raw_only=True)
+
+    # ------------------------------------------------------------------ diagnostics (additions)
+    def last_render_ms(self):
+        ms = C.c_float()
+        self._check(self._lib.spv_last_timing_ms(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def enable_stats(self, on=True):
+        self._check(self._lib.spv_enable_stats(self._ctx, int(bool(on))))
+
+    def last_stats(self):
+        """(hit rays, texture samples issued) of the last render; needs enable_stats()."""
+        v = (C.c_ulonglong * 2)()
+        self._check(self._lib.spv_last_stats(self._ctx, v, 2))
+        return int(v[0]), int(v[1])
+
+    def launch_count(self):
+        n = C.c_ulonglong()
+        self._check(self._lib.spv_launch_count(self._ctx, C.byref(n)))
+        return int(n.value)

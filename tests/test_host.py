@@ -1,0 +1,92 @@
+"""CPU-side checks: the C-ABI library exists and exports what include/spimcuda.h declares, the host-side
+mirror of the reference interface behaves like the reference, and the product refuses to run without CUDA."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import scenes
+from spimagine_b200 import _lib
+from spimagine_b200.utils import transform_matrices as tm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "spimcuda.h")).read()
+    return sorted(set(re.findall(r"SPV_API[^;(]*?\b(spv_[a-z_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    assert os.path.exists(_lib.LIB_PATH), "build with python -m spimagine_b200.build"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "libspimcuda.so does not export %s" % n
+        assert n in _lib.SIGNATURES, "no ctypes signature for %s" % n
+    assert set(_lib.SIGNATURES) == set(names)
+    assert _lib.load().spv_version() == 100
+
+
+def test_param_struct_layout_matches_header():
+    assert ctypes.sizeof(_lib.MipParams) == 6 * 4 + 4 * 4 + 4 * 4
+    assert ctypes.sizeof(_lib.IsoParams) == 6 * 4 + 7 * 4
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product must fail loudly, not render on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from spimagine_b200 import VolumeRenderer
+    with pytest.raises(_lib.SpvError):
+        VolumeRenderer((32, 32))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "spimagine_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower().replace("no cpu", ""), "%s mentions the oracle" % f
+
+
+def test_perspective_matches_glu():
+    P = tm.mat4_perspective(60, 1., .1, 10)
+    f = 1. / np.tan(np.pi / 6)
+    assert P.dtype == np.float32
+    np.testing.assert_allclose(P, [[f, 0, 0, 0], [0, f, 0, 0], [0, 0, -10.1 / 9.9, -2. / 9.9], [0, 0, -1, 0]],
+                               rtol=1e-6)
+
+
+def test_rotation_is_orthonormal_and_about_axis():
+    R = tm.mat4_rotation(.7, 0, 1, 0)
+    np.testing.assert_allclose(np.dot(R[:3, :3], R[:3, :3].T), np.eye(3), atol=1e-6)
+    np.testing.assert_allclose(np.dot(R, [0, 1, 0, 1]), [0, 1, 0, 1], atol=1e-7)
+    np.testing.assert_allclose(R[0, 0], np.cos(.7), atol=1e-6)
+    np.testing.assert_allclose(R[0, 2], np.sin(.7), atol=1e-6)
+    E = tm.mat4_rotation_euler(.1, .2, .3)
+    np.testing.assert_allclose(np.linalg.det(E), 1., atol=1e-6)
+
+
+def test_translate_scale_ortho_lookat():
+    np.testing.assert_array_equal(tm.mat4_translate(1, 2, 3)[:, 3], [1, 2, 3, 1])
+    np.testing.assert_array_equal(np.diag(tm.mat4_scale(2, 3, 4)), [2, 3, 4, 1])
+    O = tm.mat4_ortho(-2, 2, -1, 1, -10, 10)
+    np.testing.assert_allclose(np.dot(O, [2, 1, -10, 1]), [1, 1, 1, 1], atol=1e-6)
+    L = tm.mat4_lookat([0, 0, 10], [0, 0, 0], [0, 1, 0])
+    np.testing.assert_allclose(np.dot(L, [0, 0, 0, 1]), [0, 0, -10, 1], atol=1e-6)
+    F = tm.mat4_stereo_perspective(45, 1., .1, 10, 0)
+    np.testing.assert_allclose(F, tm.mat4_perspective(45, 1., .1, 10), rtol=1e-5, atol=1e-7)
+
+
+def test_vol_g_is_deterministic():
+    a = scenes.vol_g(24, np.uint16, seed=3)
+    b = scenes.vol_g(24, np.uint16, seed=3)
+    assert a.dtype == np.uint16 and a.max() == 60000
+    np.testing.assert_array_equal(a, b)
+    assert scenes.vol_g(16, np.float32).max() == 1.0
