@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark: max-intensity projection of a 512^3 uint16 volume to 1024x1024 over a
+360-degree modelView sweep (BASELINE.json configs[1]), frames/s and Gsamples/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step is one frame of the sweep (one launch of the max-projection kernel).  With N > 1 the frames of the sweep
+are sharded over the ranks (frame f -> rank f mod N, the 3D+t playback decomposition: no data-path collective),
+so per-GPU work is fixed: weak scaling; `value` is all frames rendered by all ranks / max-over-ranks device time.
+
+  value      device-resident: volume in HBM, camera matrices passed as kernel arguments, nothing read back
+  e2e        through the public API a spimagine caller uses: rend.set_modelView(M); rend.render(); rend.output --
+             host matrix inversion, launch, and the device->host read of output + alpha into pinned memory
+  roofline   HBM: algorithmic bytes per frame (every voxel once + both output planes) / average launch time,
+             against the measured copy bandwidth of MEASURED_PEAKS.json; plus the texture-sample view
+  cpu_baseline / --impl reference   the reference's own kernel text compiled for the host (oracle/_ref) when
+             that build is present, else the C restatement, on all host cores
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+VOL_N = 512
+IMG = 1024
+MAX_STEPS = 200
+SAMPLES_PER_RAY = (MAX_STEPS // 16 + 1) * 16  # 208, volume_kernel.cl:100-122
+PEAK_VALUE = 60000.
+SWEEP = 360
+METRIC = "MIP frames/s, 512^3 uint16 -> 1024^2, 360-degree modelView sweep"
+# ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch of the max-projection kernel on this
+# workload (profiles/); None until a capture exists
+NCU_TRAFFIC_BYTES = None
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=720)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--vol", type=int, default=VOL_N)
+    ap.add_argument("--img", type=int, default=IMG)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip", action="store_true", help="enable empty-space skipping on the min/max brick grid")
+    return ap.parse_args()
+
+
+def sweep_cameras(n=SWEEP):
+    import scenes
+    return [scenes.gui_camera(2 * math.pi * f / n, 4.0) for f in range(n)]
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled while the timed regions run."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference(vol, cams, img, steps, warmup, budget_s, report_all):
+    """Time the reference kernels on the host cores.  -> dict(fps, gsamples, kind, cores, sample, ms_per_step)"""
+    from oracle import oracle
+    kind = "reference" if oracle.available("reference") else "port"
+    r = oracle.OracleRenderer((img, img), kind=kind, max_steps=MAX_STEPS)
+    r.set_data(vol)
+    r.set_projection(cams[0][1])
+    r.set_max_val(PEAK_VALUE)
+    lib = r.lib
+    cores = int(lib.so_num_threads())
+    # one full frame to size the sample
+    r.set_modelView(cams[0][0])
+    t0 = time.perf_counter()
+    r.render()
+    t_full = time.perf_counter() - t0
+    rowstep = int(min(64, max(1, math.ceil(steps * t_full / budget_s))))
+    lib.so_set_row_sampling(0, rowstep)
+    for i in range(warmup):
+        r.set_modelView(cams[i % len(cams)][0])
+        r.render()
+    hits = 0
+    t0 = time.perf_counter()
+    for i in range(steps):
+        lib.so_set_row_sampling(i % rowstep, rowstep)
+        r.set_modelView(cams[i % len(cams)][0])
+        r.render()
+    dt = time.perf_counter() - t0
+    lib.so_set_row_sampling(0, 1)
+    for i in range(min(steps, len(cams))):
+        r.set_modelView(cams[i % len(cams)][0])
+        hits += r.count_hit_rays()
+    mean_hits = hits / float(min(steps, len(cams)))
+    frames = steps / float(rowstep)  # each step rendered 1/rowstep of the rows of its frame
+    fps = frames / dt
+    sample = "%d steps, each every %d-th row of one %dx%d frame of the sweep (1/%d of its rays); %s on %d threads" % (
+        steps, rowstep, img, img, rowstep,
+        "reference kernel text built for the host (oracle/_ref)" if kind == "reference" else
+        "C restatement of the reference kernels (oracle/)", cores)
+    return {"fps": fps, "gsamples": fps * mean_hits * SAMPLES_PER_RAY / 1e9, "kind": kind, "cores": cores,
+            "sample": sample, "ms_per_step": 1e3 * dt / steps, "seconds": dt}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import scenes
+    vol = scenes.vol_g(args.vol, np.uint16, seed=0)
+    cams = sweep_cameras()
+    res = cpu_reference(vol, cams, args.img, args.steps, min(args.warmup, 3), 100.0, True)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["fps"], "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 3), "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16->f32", "data": "synthetic",
+        "config": {"workload": "Vol-G(%d, uint16, seed 0) max_project -> %dx%d, max_steps=200" % (
+            args.vol, args.img, args.img), "camera": "perspective(60), translate(0,0,-4) . rotation(theta, y)"},
+        "gsamples_per_s": res["gsamples"],
+        "cpu_baseline": {"value": res["fps"], "unit": "frames/s", "cores": res["cores"], "kind": res["kind"],
+                         "sample": res["sample"]},
+        "e2e": {"value": res["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import scenes
+    import ctypes as C
+    from spimagine_b200 import VolumeRenderer, _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path in spimagine_b200)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    vol = scenes.vol_g(args.vol, np.uint16, seed=0)
+    cams = sweep_cameras()
+    W = H = args.img
+    rend = VolumeRenderer((W, H), device=local_rank, max_steps=MAX_STEPS, pinned_outputs=True)
+    # a dedicated (non-default) stream shared by torch and the renderer, so torch's events bracket the kernels
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    rend.use_stream(stream.cuda_stream)
+    t0 = time.perf_counter()
+    rend.set_data(vol)
+    torch.cuda.synchronize()
+    t_upload = time.perf_counter() - t0
+    rend.set_max_val(PEAK_VALUE)
+    rend.set_skipping(args.skip)
+    rend.set_projection(cams[0][1])
+
+    # camera matrices of the whole sweep as the kernels take them (volumerender.py:310-316)
+    mats = []
+    for M, P in cams:
+        rend.set_modelView(M)
+        mats.append((rend._invP.copy(), rend._invM.copy()))
+    lib, ctx = rend._lib, rend._ctx
+    params = _lib.MipParams(rend._box(), 0., PEAK_VALUE, 1., 0., 1, 0, MAX_STEPS, 0)
+
+    def frame_of(i):
+        return (i * world + rank) % SWEEP
+
+    def device_step(i):
+        invP, invM = mats[frame_of(i)]
+        lib.spv_set_matrices(ctx, _lib.fp(invP), _lib.fp(invM))
+        rc = lib.spv_render_mip(ctx, C.byref(params))
+        if rc:
+            _lib.check(rc, ctx)
+
+    # algorithmic samples: hit rays x 208, counted on the device in an untimed pass
+    rend.enable_stats(True)
+    hits, issued = [], []
+    for i in range(min(args.steps, SWEEP)):
+        device_step(i)
+        h, s = rend.last_stats()
+        hits.append(h)
+        issued.append(s)
+    rend.enable_stats(False)
+    mean_hits = float(np.mean(hits))
+    mean_issued = float(np.mean(issued))
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ----
+    launches0 = rend.launch_count()
+    for i in range(args.warmup):
+        device_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        device_step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = rend.launch_count() - launches0 - args.warmup
+
+    # ---- end to end through the public API ----
+    def api_step(i):
+        rend.set_modelView(cams[frame_of(i)][0])
+        rend.render()
+        return rend.output
+
+    for i in range(min(args.warmup, 5)):
+        api_step(i)
+    barrier()
+    checksum = 0.0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out = api_step(i)
+        checksum += float(out[H // 2, W // 2])
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([ms, t_e2e * 1e3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, t_e2e = float(t[0]), float(t[1]) / 1e3
+        cnt = torch.tensor([mean_hits, mean_issued], device="cuda", dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        mean_hits, mean_issued = float(cnt[0]) / world, float(cnt[1]) / world
+
+    if rank == 0:
+        total_frames = args.steps * world
+        fps = total_frames / (ms * 1e-3)
+        fps_e2e = total_frames / t_e2e
+        peaks, peak_src = measured_peaks()
+        launch_s = ms * 1e-3 / args.steps
+        alg_bytes = vol.nbytes + 2 * W * H * 4
+        achieved = alg_bytes / launch_s / 1e9
+        tex_peak = rend.texrate_probe(4000)
+        line = {
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u16->f32", "data": "synthetic",
+            "config": {
+                "workload": "Vol-G(%d, uint16, seed 0) max_project -> %dx%d, max_steps=200 (208 samples per hit "
+                            "ray), frames of a 360-degree sweep%s" % (
+                                args.vol, W, H, "" if world == 1 else ", frame f on rank f mod %d" % world),
+                "camera": "perspective(60,1,.1,10), translate(0,0,-4) . rotation(theta + 1e-3, y)",
+                "l2": "the %d MB volume exceeds the 126 MB L2 and the view changes every step" % (vol.nbytes >> 20),
+                "skipping": bool(args.skip), "parallelism": "frames sharded over %d GPU(s), volume replicated" % world,
+            },
+            "gsamples_per_s": fps * mean_hits * SAMPLES_PER_RAY / 1e9,
+            "hit_rays_per_frame": mean_hits,
+            "issued_samples_per_frame": mean_issued,
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 2 * W * H * 4,
+                    "note": "VolumeRenderer.set_modelView + render(): host 4x4 inversions, one launch, output + alpha "
+                            "read into pinned host memory; the volume stays resident as in the reference's frame loop",
+                    "checksum": checksum},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": launch_s * 1e6,
+                         "kernel": "spv::mip_fast_kernel<u16, linear>"},
+            "roofline_tex": {"bound": "texture samples", "issued_gsamples_per_s": mean_issued / launch_s / 1e9,
+                             "algorithmic_gsamples_per_s": mean_hits * SAMPLES_PER_RAY / launch_s / 1e9,
+                             "peak_gsamples_per_s": tex_peak / 1e9,
+                             "frac_issued": mean_issued / launch_s / tex_peak,
+                             "frac_algorithmic": mean_hits * SAMPLES_PER_RAY / launch_s / tex_peak,
+                             "peak_source": "spv_texrate_probe on this GPU: cache-resident trilinear uint16 fetches"},
+            "upload_s": t_upload,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            res = cpu_reference(vol, cams, args.img, 24, 1, 20.0, False)
+            line["cpu_baseline"] = {"value": res["fps"], "unit": "frames/s", "cores": res["cores"],
+                                    "kind": res["kind"], "sample": res["sample"],
+                                    "gsamples_per_s": res["gsamples"]}
+        print(json.dumps(line))
+    rend.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

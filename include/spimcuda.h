@@ -81,7 +81,15 @@ SPV_API int spv_set_sampler(spv_ctx *ctx, int sampler);
 /* what read_imageui + a LINEAR sampler means for integer volumes (undefined by OpenCL):
  * 1 = interpolate like a float image (default), 0 = nearest */
 SPV_API int spv_set_int_filter(spv_ctx *ctx, int linear);
-/* empty-brick skipping for the TMU max projection (default on; results are identical either way) */
+/* Storage layout of INTEGER volumes, effective at the next spv_set_volume*:
+ *   SPV_LAYOUT_3D    3-D array, one hardware trilinear fetch per sample
+ *   SPV_LAYOUT_ZPAIR (default) 2-D layered array of {v[z], v[z+1]} texel pairs: one hardware bilinear fetch plus an
+ *                    fp32 lerp along z per sample -- half the texture-unit work, twice the memory, exact z weight.
+ * float32 volumes always use SPV_LAYOUT_3D. */
+enum { SPV_LAYOUT_3D = 0, SPV_LAYOUT_ZPAIR = 1 };
+SPV_API int spv_set_layout(spv_ctx *ctx, int layout);
+/* empty-brick skipping for the TMU max projection (default off: it pays on sparse volumes only; results are
+ * identical either way) */
 SPV_API int spv_set_skipping(spv_ctx *ctx, int on);
 
 /* invPBuf / invMBuf.write_array, volumerender.py:310-316: row-major float[16] each */
@@ -135,8 +143,16 @@ SPV_API int spv_last_timing_ms(spv_ctx *ctx, float *ms);            /* device ti
 SPV_API int spv_last_stats(spv_ctx *ctx, unsigned long long *v, int n); /* [hit rays, texture samples issued] of the
                                                                 last render when stats were enabled */
 SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
+/* performance knobs that never change results; knob 0 = CTA shape of the max-projection kernel */
+SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 SPV_API const char *spv_last_error(spv_ctx *ctx);                   /* ctx may be NULL: last create error */
 SPV_API int spv_version(void);
+/* out[i] = the current sampler's value at normalised position pos[3i..3i+2] (what read_imagef(volume, sampler,
+ * pos).x is to the reference kernels): lets tests check the sampler in isolation */
+SPV_API int spv_sample_points(spv_ctx *ctx, const float *host_pos, int n, float *host_out);
+/* roofline calibration: measured rate (samples/s) of independent, cache-resident filtered fetches of the
+ * resident volume's format with the current interpolation mode */
+SPV_API int spv_texrate_probe(spv_ctx *ctx, int iters, double *samples_per_s);
 SPV_API int spv_launch_count(spv_ctx *ctx, unsigned long long *n);  /* kernels launched by this context so far */
 
 #ifdef __cplusplus

@@ -70,6 +70,8 @@ def load(kind="port"):
                                          C.c_float, C.c_int, C.c_int, _FP, _FP, _FP, _FP, _FP, _FP, _FP]
     if kind == "port":
         lib.so_max_project_raw.argtypes = [VP, C.c_int, C.c_int, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, _FP]
+    lib.so_set_row_sampling.argtypes = [C.c_int, C.c_int]
+    lib.so_set_row_sampling.restype = None
     lib.so_count_hit_rays.argtypes = [C.c_int, C.c_int, _FP, _FP, _FP]
     lib.so_count_hit_rays.restype = C.c_long
     lib.so_random.argtypes = [C.c_uint32, C.c_uint32]

@@ -207,6 +207,14 @@ static inline ray_t make_ray(unsigned x, unsigned y, unsigned Nx, unsigned Ny,
   return r;
 }
 
+/* Row sampling for timing runs (bench.py's bounded CPU samples): so_max_project visits only rows
+ * y = so_row0, so_row0 + so_rowstep, ... ; the default (0, 1) is the whole image. */
+static int so_row0 = 0, so_rowstep = 1;
+SO_EXPORT void so_set_row_sampling(int row0, int rowstep) {
+  so_row0 = row0 < 0 ? 0 : row0;
+  so_rowstep = rowstep < 1 ? 1 : rowstep;
+}
+
 /* ------------------------------------------------------------------ */
 /* max_project_float / max_project_short                               */
 /* ------------------------------------------------------------------ */
@@ -224,7 +232,7 @@ SO_EXPORT int so_max_project(const so_volume *V, int width, int height,
   const unsigned Nx = (unsigned)width, Ny = (unsigned)height;
   if (numParts < 1) return -1;
 #pragma omp parallel for schedule(dynamic, 4)
-  for (int yy = 0; yy < height; ++yy) {
+  for (int yy = so_row0; yy < height; yy += so_rowstep) {
     for (int xx = 0; xx < width; ++xx) {
       unsigned x = (unsigned)xx, y = (unsigned)yy;
       ray_t r = make_ray(x, y, Nx, Ny, invP, invM, box);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "spv_set_interp": (C.c_int, [_CTX, C.c_int]),
     "spv_set_sampler": (C.c_int, [_CTX, C.c_int]),
     "spv_set_int_filter": (C.c_int, [_CTX, C.c_int]),
+    "spv_set_layout": (C.c_int, [_CTX, C.c_int]),
     "spv_set_skipping": (C.c_int, [_CTX, C.c_int]),
     "spv_set_matrices": (C.c_int, [_CTX, _FP, _FP]),
     "spv_render_mip": (C.c_int, [_CTX, C.POINTER(MipParams)]),
@@ -65,6 +66,9 @@ SIGNATURES = {
     "spv_last_timing_ms": (C.c_int, [_CTX, _FP]),
     "spv_last_stats": (C.c_int, [_CTX, C.POINTER(C.c_ulonglong), C.c_int]),
     "spv_enable_stats": (C.c_int, [_CTX, C.c_int]),
+    "spv_set_tuning": (C.c_int, [_CTX, C.c_int, C.c_int]),
+    "spv_sample_points": (C.c_int, [_CTX, _FP, C.c_int, _FP]),
+    "spv_texrate_probe": (C.c_int, [_CTX, C.c_int, C.POINTER(C.c_double)]),
     "spv_launch_count": (C.c_int, [_CTX, C.POINTER(C.c_ulonglong)]),
 }
 

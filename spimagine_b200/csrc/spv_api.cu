@@ -22,13 +22,17 @@ struct spv_ctx {
   cudaTextureObject_t tex_lin = 0, tex_near = 0, tex_pt = 0;
   int dtype = -1, nx = 0, ny = 0, gnz = 0, local_nz = 0, z_lo = 0, z0 = 0, z1 = 0;
   bool slab = false;
+  int layout = LAYOUT_3D;        // of the resident array
+  int want_layout = LAYOUT_ZPAIR; // for integer volumes (spv_set_layout)
+  void *d_stage = nullptr;       // ingest staging (z-pair construction)
+  size_t stage_bytes = 0;
   float2 *bricks = nullptr, *coarse = nullptr;
   int gx = 0, gy = 0, gz = 0, cgx = 0, cgy = 0, cgz = 0;
   float *d_minmax = nullptr;
   float h_minmax[2] = {0.f, 0.f};
   bool minmax_valid = false;
   // settings
-  int linear = 1, sampler = SPV_SAMPLER_TMU, int_filter = 1, skipping = 1, stats_on = 0;
+  int linear = 1, sampler = SPV_SAMPLER_TMU, int_filter = 1, skipping = 0, stats_on = 0, tile_variant = 0;
   Camera cam;
   // result buffers: one allocation  [out | alpha | depth | occ | normals(3) | raw | tmp | tmp_vec(3)]
   float *dbuf = nullptr;
@@ -88,6 +92,9 @@ static void free_volume(spv_ctx *c) {
   if (c->arr) cudaFreeArray(c->arr);
   if (c->bricks) cudaFree(c->bricks);
   if (c->coarse) cudaFree(c->coarse);
+  if (c->d_stage) cudaFree(c->d_stage);
+  c->d_stage = nullptr;
+  c->stage_bytes = 0;
   c->tex_lin = c->tex_near = c->tex_pt = 0;
   c->arr = nullptr;
   c->bricks = c->coarse = nullptr;
@@ -206,12 +213,15 @@ static int make_textures(spv_ctx *ctx) {
   return 0;
 }
 
+static int fmt_of(const spv_ctx *c) { return c->dtype + 3 * c->layout; }
+
 static Volume volume_of(const spv_ctx *c) {
   Volume V;
   const bool lin = c->linear && (c->dtype == SPV_F32 || c->int_filter);
   V.filt = lin ? c->tex_lin : c->tex_near;
   V.pt = c->tex_pt;
   V.nx = c->nx; V.ny = c->ny; V.nz = c->gnz;
+  V.local_nz = c->local_nz;
   V.fnx = (float)c->nx; V.fny = (float)c->ny; V.fnz = (float)c->gnz;
   V.scale = c->dtype == SPV_F32 ? 1.f : (c->dtype == SPV_U16 ? 65535.f : 255.f);
   V.z_lo = c->z_lo; V.z0 = c->z0; V.z1 = c->z1;
@@ -220,16 +230,60 @@ static Volume volume_of(const spv_ctx *c) {
   return V;
 }
 
+// Fill the resident array from `src` (host or device, C-order, local_nz slices).
+//   LAYOUT_3D:    one cudaMemcpy3D.
+//   LAYOUT_ZPAIR: in chunks of slices -- (host -> device staging,) pair_kernel builds {v[z], v[z+1]} texels in a
+//                 linear buffer, cudaMemcpy3D moves them into the layers.
 static int upload(spv_ctx *ctx, const void *src, bool on_device) {
-  cudaMemcpy3DParms p;
-  memset(&p, 0, sizeof p);
-  p.srcPtr = make_cudaPitchedPtr(const_cast<void *>(src), (size_t)ctx->nx * elem_size(ctx->dtype), ctx->nx, ctx->ny);
-  p.dstArray = ctx->arr;
-  p.extent = make_cudaExtent(ctx->nx, ctx->ny, ctx->local_nz);
-  p.kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  CU(cudaMemcpy3DAsync(&p, ctx->stream));
+  const size_t es = elem_size(ctx->dtype);
+  const size_t slice = (size_t)ctx->nx * ctx->ny;
+  const int nz = ctx->local_nz;
+  if (ctx->layout == LAYOUT_3D) {
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof p);
+    p.srcPtr = make_cudaPitchedPtr(const_cast<void *>(src), (size_t)ctx->nx * es, ctx->nx, ctx->ny);
+    p.dstArray = ctx->arr;
+    p.extent = make_cudaExtent(ctx->nx, ctx->ny, nz);
+    p.kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CU(cudaMemcpy3DAsync(&p, ctx->stream));
+  } else {
+    const size_t budget = (size_t)256 << 20;  // bytes of paired texels per chunk
+    int zc = (int)(budget / (slice * 2 * es));
+    if (zc < 1) zc = 1;
+    if (zc > nz) zc = nz;
+    const size_t need_pair = slice * 2 * es * (size_t)zc;
+    const size_t need_stage = on_device ? 0 : slice * es * (size_t)(zc + 1);
+    if (ctx->stage_bytes < need_pair + need_stage) {
+      if (ctx->d_stage) cudaFree(ctx->d_stage);
+      ctx->d_stage = nullptr;
+      ctx->stage_bytes = 0;
+      CU(cudaMalloc(&ctx->d_stage, need_pair + need_stage));
+      ctx->stage_bytes = need_pair + need_stage;
+    }
+    char *d_pair = (char *)ctx->d_stage, *d_lin = d_pair + need_pair;
+    for (int zb = 0; zb < nz; zb += zc) {
+      const int ze = zb + zc < nz ? zb + zc : nz;
+      if (on_device) {
+        CU(launch_pair(src, d_pair, ctx->dtype, slice, nz, zb, ze, ctx->stream));
+      } else {
+        const int zs = ze < nz ? ze + 1 : nz;  // one slice more: the upper partner of the chunk's last slice
+        CU(cudaMemcpyAsync(d_lin, (const char *)src + (size_t)zb * slice * es, (size_t)(zs - zb) * slice * es,
+                           cudaMemcpyHostToDevice, ctx->stream));
+        CU(launch_pair(d_lin, d_pair, ctx->dtype, slice, zs - zb, 0, ze - zb, ctx->stream));
+      }
+      cudaMemcpy3DParms p;
+      memset(&p, 0, sizeof p);
+      p.srcPtr = make_cudaPitchedPtr(d_pair, (size_t)ctx->nx * 2 * es, ctx->nx, ctx->ny);
+      p.dstArray = ctx->arr;
+      p.dstPos = make_cudaPos(0, 0, zb);
+      p.extent = make_cudaExtent(ctx->nx, ctx->ny, ze - zb);
+      p.kind = cudaMemcpyDeviceToDevice;
+      CU(cudaMemcpy3DAsync(&p, ctx->stream));
+      ctx->launches += 1;
+    }
+  }
   Volume V = volume_of(ctx);
-  CU(launch_build_bricks(V, ctx->dtype, ctx->local_nz, ctx->bricks, ctx->coarse, ctx->cgx, ctx->cgy, ctx->cgz,
+  CU(launch_build_bricks(V, fmt_of(ctx), ctx->local_nz, ctx->bricks, ctx->coarse, ctx->cgx, ctx->cgy, ctx->cgz,
                          ctx->d_minmax, ctx->stream));
   ctx->launches += 3;
   ctx->minmax_valid = false;
@@ -247,16 +301,22 @@ static int set_volume_impl(spv_ctx *ctx, const void *src, bool on_device, int dt
   const int z_lo = slab ? (z0 > 0 ? z0 - 1 : 0) : 0;
   const int z_hi = slab ? (z1 < gnz ? z1 + 1 : gnz) : gnz;
   const int local_nz = z_hi - z_lo;
+  // z-paired layered layout for integer volumes when asked for and the layer count allows it
+  const int layout = (ctx->want_layout == LAYOUT_ZPAIR && dtype != SPV_F32 && local_nz <= 2048 && nx <= 32768 &&
+                      ny <= 32768) ? LAYOUT_ZPAIR : LAYOUT_3D;
   CU(cudaStreamSynchronize(ctx->stream));
-  const bool same = ctx->arr && ctx->dtype == dtype && ctx->nx == nx && ctx->ny == ny && ctx->local_nz == local_nz;
+  const bool same = ctx->arr && ctx->dtype == dtype && ctx->nx == nx && ctx->ny == ny && ctx->local_nz == local_nz &&
+                    ctx->layout == layout;
   if (!same) {
     free_volume(ctx);
     ctx->dtype = dtype;
+    ctx->layout = layout;
     ctx->nx = nx; ctx->ny = ny; ctx->local_nz = local_nz;
-    cudaChannelFormatDesc cd = dtype == SPV_F32 ? cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat)
-                             : dtype == SPV_U16 ? cudaCreateChannelDesc(16, 0, 0, 0, cudaChannelFormatKindUnsigned)
-                                                : cudaCreateChannelDesc(8, 0, 0, 0, cudaChannelFormatKindUnsigned);
-    CU(cudaMalloc3DArray(&ctx->arr, &cd, make_cudaExtent(nx, ny, local_nz), 0));
+    const int bits = dtype == SPV_F32 ? 32 : (dtype == SPV_U16 ? 16 : 8);
+    const cudaChannelFormatKind kind = dtype == SPV_F32 ? cudaChannelFormatKindFloat : cudaChannelFormatKindUnsigned;
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(bits, layout == LAYOUT_ZPAIR ? bits : 0, 0, 0, kind);
+    CU(cudaMalloc3DArray(&ctx->arr, &cd, make_cudaExtent(nx, ny, local_nz),
+                         layout == LAYOUT_ZPAIR ? cudaArrayLayered : cudaArrayDefault));
     int rc = make_textures(ctx);
     if (rc) return rc;
     ctx->gx = (nx + BRICK - 1) / BRICK; ctx->gy = (ny + BRICK - 1) / BRICK; ctx->gz = (local_nz + BRICK - 1) / BRICK;
@@ -314,9 +374,21 @@ SPV_API int spv_set_int_filter(spv_ctx *ctx, int linear) {
   ctx->int_filter = linear != 0;
   return 0;
 }
+SPV_API int spv_set_layout(spv_ctx *ctx, int layout) {
+  if (!ctx) return SPV_EINVAL;
+  if (layout != LAYOUT_3D && layout != LAYOUT_ZPAIR) return fail(ctx, SPV_EINVAL, "spv_set_layout: unknown layout");
+  ctx->want_layout = layout;  // takes effect at the next spv_set_volume*
+  return 0;
+}
 SPV_API int spv_set_skipping(spv_ctx *ctx, int on) {
   if (!ctx) return SPV_EINVAL;
   ctx->skipping = on != 0;
+  return 0;
+}
+SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
+  if (!ctx) return SPV_EINVAL;
+  if (knob == 0) ctx->tile_variant = value;
+  else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
   return 0;
 }
 SPV_API int spv_enable_stats(spv_ctx *ctx, int on) {
@@ -368,13 +440,14 @@ SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p) {
   memcpy(a.box, p->box, sizeof a.box);
   a.min_val = p->min_val; a.max_val = p->max_val; a.gamma = p->gamma; a.alpha_pow = p->alpha_pow;
   a.num_parts = p->num_parts; a.current_part = p->current_part; a.max_steps = p->max_steps; a.flags = p->flags;
+  a.tile_variant = ctx->tile_variant;
   a.width = ctx->width; a.height = ctx->height;
   a.out = ctx->out(); a.alpha = ctx->alpha(); a.raw = ctx->raw();
   a.stats = ctx->stats_on ? ctx->d_stats : nullptr;
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
   int rc = begin_render(ctx);
   if (rc) return rc;
-  CU(launch_mip(a, ctx->dtype, linear, fast, exact, ctx->skipping != 0, ctx->slab, ctx->stats_on != 0, ctx->stream));
+  CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, ctx->skipping != 0, ctx->slab, ctx->stats_on != 0, ctx->stream));
   ctx->launches += 1;
   ctx->last_method = 0;
   return end_render(ctx);
@@ -418,7 +491,7 @@ SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p) {
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
   int rc = begin_render(ctx);
   if (rc) return rc;
-  CU(launch_iso(a, ctx->dtype, linear, ctx->sampler == SPV_SAMPLER_EXACT, ctx->stats_on != 0, ctx->stream));
+  CU(launch_iso(a, fmt_of(ctx), linear, ctx->sampler == SPV_SAMPLER_EXACT, ctx->stats_on != 0, ctx->stream));
   ctx->launches += 1;
   if (!(p->flags & SPV_ISO_RAW_ONLY)) {
     // volumerender.py:470-497
@@ -507,6 +580,48 @@ SPV_API int spv_last_stats(spv_ctx *ctx, unsigned long long *v, int n) {
   CU(cudaStreamSynchronize(ctx->stream));
   v[0] = ctx->h_stats[0];
   v[1] = ctx->h_stats[1];
+  return 0;
+}
+
+SPV_API int spv_sample_points(spv_ctx *ctx, const float *host_pos, int n, float *host_out) {
+  BIND();
+  if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_sample_points: no volume set");
+  if (!host_pos || !host_out || n < 1) return fail(ctx, SPV_EINVAL, "spv_sample_points: bad argument");
+  if (ctx->slab) return fail(ctx, SPV_EINVAL, "spv_sample_points: not available on a slab context");
+  float *d = nullptr;
+  CU(cudaMalloc(&d, (size_t)n * 4 * sizeof(float)));
+  cudaError_t e = cudaMemcpyAsync(d, host_pos, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+  const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
+  if (e == cudaSuccess)
+    e = launch_sample_points(volume_of(ctx), fmt_of(ctx), linear, ctx->sampler == SPV_SAMPLER_EXACT, d, n, d + 3 * (size_t)n,
+                             ctx->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(host_out, d + 3 * (size_t)n, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  ctx->launches += 1;
+  if (e != cudaSuccess) return cufail(ctx, e, "spv_sample_points");
+  return 0;
+}
+
+SPV_API int spv_texrate_probe(spv_ctx *ctx, int iters, double *samples_per_s) {
+  BIND();
+  if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_texrate_probe: no volume set");
+  if (iters < 1 || !samples_per_s) return fail(ctx, SPV_EINVAL, "spv_texrate_probe: bad argument");
+  int sms = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  const int blocks = sms * 8;
+  const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
+  Volume V = volume_of(ctx);
+  CU(launch_texrate_probe(V, fmt_of(ctx), linear, blocks, 8, ctx->tmp(), ctx->stream));  // warm-up
+  CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  CU(launch_texrate_probe(V, fmt_of(ctx), linear, blocks, iters, ctx->tmp(), ctx->stream));
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  CU(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->launches += 2;
+  *samples_per_s = (double)blocks * 256.0 * 16.0 * (double)iters / ((double)ms * 1e-3);
   return 0;
 }
 

@@ -10,7 +10,7 @@
 
 namespace spv {
 
-template <int DT>
+template <int FMT>
 __global__ void __launch_bounds__(128) brick_kernel(const Volume V, int local_nz, float2 *bricks) {
   const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
   const int D = BRICK_DILATE;
@@ -22,8 +22,7 @@ __global__ void __launch_bounds__(128) brick_kernel(const Volume V, int local_nz
   float lo = __int_as_float(0x7f800000), hi = -lo;
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
     const int i = t % ex, j = (t / ex) % ey, k = t / (ex * ey);
-    const float v = (float)tex3D<typename TexelType<DT>::type>(V.pt, (float)(x0 + i) + 0.5f, (float)(y0 + j) + 0.5f,
-                                                                 (float)(z0 + k) + 0.5f);
+    const float v = texel<FMT>(V, x0 + i, y0 + j, V.z_lo + z0 + k);  // texel() takes the global slice index
     lo = fminf(lo, v);
     hi = fmaxf(hi, v);
   }
@@ -88,14 +87,45 @@ __global__ void minmax_kernel(const float2 *__restrict__ coarse, int n, float *m
 cudaError_t launch_build_bricks(const Volume &vol, int dtype, int local_nz, float2 *bricks, float2 *coarse, int cgx,
                                 int cgy, int cgz, float *minmax, cudaStream_t st) {
   dim3 grid(vol.gx, vol.gy, vol.gz);
-  switch (dtype) {
+  switch (dtype) {  // FMT = dtype + 3 * layout
     case 0: brick_kernel<0><<<grid, 128, 0, st>>>(vol, local_nz, bricks); break;
     case 1: brick_kernel<1><<<grid, 128, 0, st>>>(vol, local_nz, bricks); break;
-    default: brick_kernel<2><<<grid, 128, 0, st>>>(vol, local_nz, bricks); break;
+    case 2: brick_kernel<2><<<grid, 128, 0, st>>>(vol, local_nz, bricks); break;
+    case 4: brick_kernel<4><<<grid, 128, 0, st>>>(vol, local_nz, bricks); break;
+    case 5: brick_kernel<5><<<grid, 128, 0, st>>>(vol, local_nz, bricks); break;
+    default: return cudaErrorInvalidValue;
   }
   const int nc = cgx * cgy * cgz;
   coarse_kernel<<<(nc + 127) / 128, 128, 0, st>>>(bricks, vol.gx, vol.gy, vol.gz, coarse, cgx, cgy, cgz);
   minmax_kernel<<<1, 1024, 0, st>>>(coarse, nc, minmax);
+  return cudaGetLastError();
+}
+
+// LAYOUT_ZPAIR ingest: dst[z][y][x] = {src[z][y][x], src[min(z+1, nz-1)][y][x]} for z in [zbeg, zend), written to a
+// C-order linear buffer that is then copied into the layered array.  One thread per 4 voxels of a row segment.
+template <typename T, typename T2>
+__global__ void pair_kernel(const T *__restrict__ src, T2 *__restrict__ dst, size_t slice, int nz, int zbeg, int zend) {
+  const size_t n = slice * (size_t)(zend - zbeg);
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t z = zbeg + t / slice, o = t % slice;
+    const size_t z1 = z + 1 < (size_t)nz ? z + 1 : (size_t)nz - 1;
+    T2 v;
+    v.x = src[z * slice + o];
+    v.y = src[z1 * slice + o];
+    dst[t] = v;
+  }
+}
+
+cudaError_t launch_pair(const void *src, void *dst, int dtype, size_t slice, int nz, int zbeg, int zend,
+                        cudaStream_t st) {
+  const size_t n = slice * (size_t)(zend - zbeg);
+  const int blocks = (int)((n + 255) / 256 < 148 * 32 ? (n + 255) / 256 : 148 * 32);
+  if (dtype == SPV_U16)
+    pair_kernel<unsigned short, ushort2><<<blocks, 256, 0, st>>>((const unsigned short *)src, (ushort2 *)dst, slice, nz, zbeg, zend);
+  else if (dtype == SPV_U8)
+    pair_kernel<unsigned char, uchar2><<<blocks, 256, 0, st>>>((const unsigned char *)src, (uchar2 *)dst, slice, nz, zbeg, zend);
+  else
+    return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

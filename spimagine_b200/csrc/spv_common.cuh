@@ -105,22 +105,30 @@ __device__ __forceinline__ Ray make_ray(unsigned x, unsigned y, unsigned Nx, uns
 }
 
 // ---------------------------------------------------------------------------------------------
-// The resident volume.  A cudaArray (block-linear, i.e. hardware-bricked) bound to two texture
-// objects with UNNORMALISED coordinates and clamp addressing:
-//   filt : the sampler of the current interpolation mode; integer volumes are read as normalised
-//          floats (the only way the texture unit filters them) and scaled back by `scale`
+// The resident volume, in one of two hardware layouts (both block-linear cudaArrays, i.e. bricked by the
+// texture hardware), bound to texture objects with UNNORMALISED coordinates and clamp addressing:
+//
+//   LAYOUT_3D     3-D single-channel array; a sample is ONE trilinear fetch (two filter passes in the TMU).
+//   LAYOUT_ZPAIR  (integer volumes) 2-D layered two-channel array whose layer k holds {v[k], v[k+1]}: a sample
+//                 is ONE bilinear fetch (one filter pass: twice the texture-unit throughput) and an fp32 lerp
+//                 along z in the ALU.  Costs twice the memory; the z weight is exact instead of 8-bit.
+//
+//   filt : the sampler of the current interpolation mode; integer volumes are read as normalised floats (the
+//          only way the texture unit filters them) and scaled back by `scale`
 //   pt   : point sampling, element type; exact texel fetches
-// z_lo / z0 / z1 describe a slab of a larger volume (sort-last rendering): the array holds global
-// slices [z_lo, z_lo + local depth); this context owns samples whose footprint starts in [z0, z1).
+// z_lo / z0 / z1 describe a slab of a larger volume (sort-last rendering): the array holds global slices
+// [z_lo, z_lo + local_nz); this context owns samples whose footprint starts in [z0, z1).
 // ---------------------------------------------------------------------------------------------
+enum { LAYOUT_3D = 0, LAYOUT_ZPAIR = 1 };
 struct Volume {
   cudaTextureObject_t filt;
   cudaTextureObject_t pt;
   int nx, ny, nz;          // GLOBAL extent (nz = gnz for a slab)
+  int local_nz;            // slices resident here
   float fnx, fny, fnz;
   float scale;             // 1, 65535 or 255
   int z_lo, z0, z1;
-  // brick grid: float2 {min,max} per brick of BRICK^3 texels, dilated by DILATE texels on every side
+  // brick grid: float2 {min,max} per brick of BRICK^3 texels, dilated by BRICK_DILATE texels
   const float2 *bricks;
   int gx, gy, gz;          // grid extent (gz counts LOCAL slices from z_lo)
 };
@@ -128,15 +136,21 @@ constexpr int BRICK_SHIFT = 3;
 constexpr int BRICK = 1 << BRICK_SHIFT;
 constexpr int BRICK_DILATE = 2;  // footprint (+1) and coordinate rounding slack (+1)
 
+// Kernels are specialised on FMT = dtype + 3 * layout  (dtype: 0 f32, 1 u16, 2 u8)
+constexpr int NUM_FMT = 6;
 template <int DT> struct TexelType;
-template <> struct TexelType<0> { typedef float type; };
-template <> struct TexelType<1> { typedef unsigned short type; };
-template <> struct TexelType<2> { typedef unsigned char type; };
+template <> struct TexelType<0> { typedef float type; typedef float2 pair; };
+template <> struct TexelType<1> { typedef unsigned short type; typedef ushort2 pair; };
+template <> struct TexelType<2> { typedef unsigned char type; typedef uchar2 pair; };
 
 // exact texel (i,j,k) with GLOBAL k
-template <int DT>
+template <int FMT>
 __device__ __forceinline__ float texel(const Volume &V, int i, int j, int k) {
-  return (float)tex3D<typename TexelType<DT>::type>(V.pt, (float)i + 0.5f, (float)j + 0.5f, (float)(k - V.z_lo) + 0.5f);
+  constexpr int DT = FMT % 3;
+  if (FMT / 3 == LAYOUT_3D)
+    return (float)tex3D<typename TexelType<DT>::type>(V.pt, (float)i + 0.5f, (float)j + 0.5f,
+                                                       (float)(k - V.z_lo) + 0.5f);
+  return (float)tex2DLayered<typename TexelType<DT>::pair>(V.pt, (float)i + 0.5f, (float)j + 0.5f, k - V.z_lo).x;
 }
 
 __device__ __forceinline__ int floor_to_int(float f, int n) {
@@ -148,14 +162,14 @@ __device__ __forceinline__ int floor_to_int(float f, int n) {
 
 // SPV_SAMPLER_EXACT: the OpenCL 1.2 (section 8.2) sampler in fp32, eight-term sum in specification order.
 // pos in normalised coordinates like read_imagef(volume, sampler, pos).
-template <int DT, bool LINEAR>
+template <int FMT, bool LINEAR>
 __device__ __forceinline__ float sample_exact(const Volume &V, float px, float py, float pz) {
   float u = px * V.fnx, v = py * V.fny, w = pz * V.fnz;
   if (!LINEAR) {
     int i = clampi(floor_to_int(u, V.nx), 0, V.nx - 1);
     int j = clampi(floor_to_int(v, V.ny), 0, V.ny - 1);
     int k = clampi(floor_to_int(w, V.nz), 0, V.nz - 1);
-    return texel<DT>(V, i, j, k);
+    return texel<FMT>(V, i, j, k);
   }
   float ub = u - 0.5f, vb = v - 0.5f, wb = w - 0.5f;
   int i0 = floor_to_int(ub, V.nx), j0 = floor_to_int(vb, V.ny), k0 = floor_to_int(wb, V.nz);
@@ -168,35 +182,51 @@ __device__ __forceinline__ float sample_exact(const Volume &V, float px, float p
   j0 = clampi(j0, 0, V.ny - 1);
   k0 = clampi(k0, 0, V.nz - 1);
   float a1 = 1.f - a, b1 = 1.f - b, c1 = 1.f - c;
-  float T = a1 * b1 * c1 * texel<DT>(V, i0, j0, k0);
-  T = T + a * b1 * c1 * texel<DT>(V, i1, j0, k0);
-  T = T + a1 * b * c1 * texel<DT>(V, i0, j1, k0);
-  T = T + a * b * c1 * texel<DT>(V, i1, j1, k0);
-  T = T + a1 * b1 * c * texel<DT>(V, i0, j0, k1);
-  T = T + a * b1 * c * texel<DT>(V, i1, j0, k1);
-  T = T + a1 * b * c * texel<DT>(V, i0, j1, k1);
-  T = T + a * b * c * texel<DT>(V, i1, j1, k1);
+  float T = a1 * b1 * c1 * texel<FMT>(V, i0, j0, k0);
+  T = T + a * b1 * c1 * texel<FMT>(V, i1, j0, k0);
+  T = T + a1 * b * c1 * texel<FMT>(V, i0, j1, k0);
+  T = T + a * b * c1 * texel<FMT>(V, i1, j1, k0);
+  T = T + a1 * b1 * c * texel<FMT>(V, i0, j0, k1);
+  T = T + a * b1 * c * texel<FMT>(V, i1, j0, k1);
+  T = T + a1 * b * c * texel<FMT>(V, i0, j1, k1);
+  T = T + a * b * c * texel<FMT>(V, i1, j1, k1);
   return T;
 }
 
 // SPV_SAMPLER_TMU: one hardware-filtered fetch.  (u,v,w) are UNNORMALISED texel coordinates of the
 // global volume; subtracting the integer slab origin is exact in fp32, so a slab sees the same
 // fractional weights as the whole volume would.
-template <int DT, bool LINEAR>
+template <int FMT, bool LINEAR>
 __device__ __forceinline__ float sample_tmu_uvw(const Volume &V, float u, float v, float w) {
-  if (DT != 0 && !LINEAR)  // integer + nearest: element-type point fetch, exact voxel values
-    return (float)tex3D<typename TexelType<DT>::type>(V.pt, u, v, w - (float)V.z_lo);
-  float t = tex3D<float>(V.filt, u, v, w - (float)V.z_lo);
-  return DT == 0 ? t : t * V.scale;
+  constexpr int DT = FMT % 3;
+  const float wl = w - (float)V.z_lo;
+  if (FMT / 3 == LAYOUT_3D) {
+    if (DT != 0 && !LINEAR)  // integer + nearest: element-type point fetch, exact voxel values
+      return (float)tex3D<typename TexelType<DT>::type>(V.pt, u, v, wl);
+    float t = tex3D<float>(V.filt, u, v, wl);
+    return DT == 0 ? t : t * V.scale;
+  }
+  const float top = (float)(V.local_nz - 1);
+  if (!LINEAR) {
+    const int layer = (int)fminf(fmaxf(floorf(wl), 0.f), top);
+    return (float)tex2DLayered<typename TexelType<DT>::pair>(V.pt, u, v, layer).x;
+  }
+  // layer k = {v[k], v[k+1]} (the last layer repeats itself): bilinear in the texture unit, lerp along z here
+  const float wb = wl - 0.5f;
+  const float fl = floorf(wb);
+  const float f = fl < 0.f ? 0.f : wb - fl;  // below the first slice centre: clamp-to-edge
+  const int layer = (int)fminf(fmaxf(fl, 0.f), top);
+  const float2 t = tex2DLayered<float2>(V.filt, u, v, layer);
+  return fmaf(f, t.y - t.x, t.x) * V.scale;
 }
-template <int DT, bool LINEAR>
+template <int FMT, bool LINEAR>
 __device__ __forceinline__ float sample_tmu(const Volume &V, float px, float py, float pz) {
-  return sample_tmu_uvw<DT, LINEAR>(V, px * V.fnx, py * V.fny, pz * V.fnz);
+  return sample_tmu_uvw<FMT, LINEAR>(V, px * V.fnx, py * V.fny, pz * V.fnz);
 }
 
-template <int DT, bool LINEAR, bool EXACT>
+template <int FMT, bool LINEAR, bool EXACT>
 __device__ __forceinline__ float sample(const Volume &V, float px, float py, float pz) {
-  return EXACT ? sample_exact<DT, LINEAR>(V, px, py, pz) : sample_tmu<DT, LINEAR>(V, px, py, pz);
+  return EXACT ? sample_exact<FMT, LINEAR>(V, px, py, pz) : sample_tmu<FMT, LINEAR>(V, px, py, pz);
 }
 
 // brick grid addressing: x fastest

@@ -12,7 +12,7 @@ namespace spv {
 // iso_surface.  One warp = one 8x4 pixel tile (same lane order as the MIP kernel).  The coarse search keeps the
 // reference's sample positions (pos += delta accumulation) and its first-crossing rule; the bracket refinement
 // and the 12-tap gradient follow iso_kernel.cl:140-200 operation by operation.
-template <int DT, bool LINEAR, bool EXACT, bool STATS>
+template <int FMT, bool LINEAR, bool EXACT, bool STATS>
 __global__ void __launch_bounds__(128) iso_kernel(const IsoArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
@@ -40,13 +40,13 @@ __global__ void __launch_bounds__(128) iso_kernel(const IsoArgs a) {
     const v4 pos0 = scl4(0.5f, add4(sadd4(1.f, orig), scl4(tnear, direc)));
     v4 pos = pos0;
     // :106 reads the first sample with read_imagef whatever the image type; taken as a proper read
-    float newVal = sample<DT, LINEAR, EXACT>(V, pos.x, pos.y, pos.z);
+    float newVal = sample<FMT, LINEAR, EXACT>(V, pos.x, pos.y, pos.z);
     const bool isGreater = newVal > isoVal;
     int i = 1;
     for (i = 1; i < maxSteps; i++) {
       pos = add4(pos, delta_pos);
       t_hit = tnear + (float)i * dt;
-      newVal = sample<DT, LINEAR, EXACT>(V, pos.x, pos.y, pos.z);
+      newVal = sample<FMT, LINEAR, EXACT>(V, pos.x, pos.y, pos.z);
       if ((newVal > isoVal) != isGreater) {
         hitIso = true;
         break;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(128) iso_kernel(const IsoArgs a) {
       const float dt2 = dt / (float)maxBisect;
       pos = add4(pos0, scl4((float)(i - 1), delta_pos));
       for (int j = 1; j <= maxBisect; j++) {
-        newVal = sample<DT, LINEAR, EXACT>(V, pos.x, pos.y, pos.z);
+        newVal = sample<FMT, LINEAR, EXACT>(V, pos.x, pos.y, pos.z);
         pos = add4(pos, delta_pos2);
         t_hit += dt2;
         if (STATS) ++nfetch;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) iso_kernel(const IsoArgs a) {
       float h = dt;
       h *= (a.gamma * a.gamma);  // pow(gamma, 2.f)
       const float h2 = 2.f * h;
-#define SPV_S(dx, dy, dz) sample<DT, LINEAR, EXACT>(V, pos.x + (dx), pos.y + (dy), pos.z + (dz))
+#define SPV_S(dx, dy, dz) sample<FMT, LINEAR, EXACT>(V, pos.x + (dx), pos.y + (dy), pos.z + (dz))
       normal.x = 2.f * SPV_S(h, 0.f, 0.f) - 2.f * SPV_S(-h, 0.f, 0.f) + SPV_S(h2, 0.f, 0.f) - SPV_S(-h2, 0.f, 0.f);
       normal.y = 2.f * SPV_S(0.f, h, 0.f) - 2.f * SPV_S(0.f, -h, 0.f) + SPV_S(0.f, h2, 0.f) - SPV_S(0.f, -h2, 0.f);
       normal.z = SPV_S(0.f, 0.f, h) - SPV_S(0.f, 0.f, -h) + SPV_S(0.f, 0.f, h2) - SPV_S(0.f, 0.f, -h2);
@@ -108,10 +108,10 @@ __global__ void __launch_bounds__(128) iso_kernel(const IsoArgs a) {
   }
 }
 
-template <int DT>
+template <int FMT>
 static cudaError_t launch_iso_dt(const IsoArgs &a, bool linear, bool exact, bool stats, cudaStream_t st) {
   dim3 grid((a.width + 15) / 16, (a.height + 7) / 8), block(128);
-#define SPV_ISO(L, E, S) iso_kernel<DT, L, E, S><<<grid, block, 0, st>>>(a)
+#define SPV_ISO(L, E, S) iso_kernel<FMT, L, E, S><<<grid, block, 0, st>>>(a)
   if (stats) {
     if (linear) { if (exact) SPV_ISO(true, true, true); else SPV_ISO(true, false, true); }
     else { if (exact) SPV_ISO(false, true, true); else SPV_ISO(false, false, true); }
@@ -124,10 +124,13 @@ static cudaError_t launch_iso_dt(const IsoArgs &a, bool linear, bool exact, bool
 }
 
 cudaError_t launch_iso(const IsoArgs &a, int dtype, bool linear, bool exact, bool stats, cudaStream_t st) {
-  switch (dtype) {
+  switch (dtype) {  // FMT = dtype + 3 * layout
     case 0: return launch_iso_dt<0>(a, linear, exact, stats, st);
     case 1: return launch_iso_dt<1>(a, linear, exact, stats, st);
-    default: return launch_iso_dt<2>(a, linear, exact, stats, st);
+    case 2: return launch_iso_dt<2>(a, linear, exact, stats, st);
+    case 4: return launch_iso_dt<4>(a, linear, exact, stats, st);
+    case 5: return launch_iso_dt<5>(a, linear, exact, stats, st);
+    default: return cudaErrorInvalidValue;
   }
 }
 

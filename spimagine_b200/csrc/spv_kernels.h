@@ -13,6 +13,7 @@ struct MipArgs {
   float box[6];
   float min_val, max_val, gamma, alpha_pow;
   int num_parts, current_part, max_steps, flags;
+  int tile_variant;  // CTA shape of the fast kernel (tuning)
   int width, height;
   float *out, *alpha, *raw;
   unsigned long long *stats;  // [hit rays, texture samples issued] or nullptr
@@ -41,6 +42,11 @@ cudaError_t launch_mip(const MipArgs &a, int dtype, bool linear, bool fast, bool
 cudaError_t launch_mip_finish(const float *raw, float *out, int n, float minVal, float maxVal, float gamma,
                               cudaStream_t st);
 
+cudaError_t launch_sample_points(const Volume &V, int dtype, bool linear, bool exact, const float *pos, int n,
+                                 float *out, cudaStream_t st);
+cudaError_t launch_texrate_probe(const Volume &V, int dtype, bool linear, int blocks, int iters, float *sink,
+                                 cudaStream_t st);
+
 cudaError_t launch_iso(const IsoArgs &a, int dtype, bool linear, bool exact, bool stats, cudaStream_t st);
 // buf -> tmp (x pass), tmp -> buf (y pass); ncomp = 1 (conv_x/conv_y) or 3 (conv_vec_x/conv_vec_y)
 cudaError_t launch_conv(float *buf, float *tmp, int width, int height, int ncomp, const ConvWeights &w,
@@ -53,5 +59,9 @@ cudaError_t launch_shading(float *out, int width, int height, const Camera &cam,
 // min/max brick grids of the resident volume (built from the point texture)
 cudaError_t launch_build_bricks(const Volume &vol, int dtype, int local_nz, float2 *bricks, float2 *coarse, int cgx,
                                 int cgy, int cgz, float *minmax /* [2] device */, cudaStream_t st);
+
+// LAYOUT_ZPAIR ingest: dst (linear, z-major) = {src[z], src[min(z+1, nz-1)]} for z in [zbeg, zend)
+cudaError_t launch_pair(const void *src, void *dst, int dtype, size_t slice, int nz, int zbeg, int zend,
+                        cudaStream_t st);
 
 }  // namespace spv

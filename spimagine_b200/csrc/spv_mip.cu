@@ -20,13 +20,13 @@ __device__ __forceinline__ float window_value(float col, float minVal, float max
 }
 
 // -------------------------------------------------------------------------------------------------------------
-template <int DT, bool LINEAR, bool EXACT>
+template <int FMT, bool LINEAR, bool EXACT>
 __global__ void __launch_bounds__(128) mip_ref_kernel(const MipArgs a) {
   const unsigned x = blockIdx.x * 16 + (threadIdx.x & 15);
   const unsigned y = blockIdx.y * 8 + (threadIdx.x >> 4);
   const unsigned Nx = a.width, Ny = a.height;
   if (x >= Nx || y >= Ny) return;
-  const bool isShort = DT != 0;
+  const bool isShort = (FMT % 3) != 0;
   const size_t p = x + (size_t)Nx * y;
   Ray r = make_ray(x, y, Nx, Ny, a.cam, a.box);
   if (!r.hit) {
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128) mip_ref_kernel(const MipArgs a) {
     for (int i = 0; i <= reducedSteps / LOOPUNROLL; ++i) {
 #pragma unroll 4
       for (int j = 0; j < LOOPUNROLL; ++j) {
-        newVal = sample<DT, LINEAR, EXACT>(a.vol, pos.x, pos.y, pos.z);
+        newVal = sample<FMT, LINEAR, EXACT>(a.vol, pos.x, pos.y, pos.z);
         colVal = fmaxf(colVal, newVal);
         pos = add4(pos, delta_pos);
       }
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(128) mip_ref_kernel(const MipArgs a) {
     float cumsum = 1.f;
     for (int i = 0; i <= reducedSteps / LOOPUNROLL; ++i) {
       for (int j = 0; j < LOOPUNROLL; ++j) {
-        newVal = sample<DT, LINEAR, EXACT>(a.vol, pos.x, pos.y, pos.z);
+        newVal = sample<FMT, LINEAR, EXACT>(a.vol, pos.x, pos.y, pos.z);
         newVal = (maxVal == 0.f) ? newVal : (newVal - minVal) / (maxVal - minVal);
         colVal = fmaxf(colVal, cumsum * newVal);
         if (isShort) cumsum *= (1.f - .1f * alpha_pow * alpha_pow * newVal);         // :312
@@ -88,9 +88,9 @@ struct Marcher {
   float u0, v0, w0, du, dv, dw;  // unnormalised texel coordinates of sample k: u0 + k*du
 };
 
-template <int DT, bool LINEAR, bool SLAB>
+template <int FMT, bool LINEAR, bool SLAB>
 __device__ __forceinline__ float fetch_k(const Volume &V, const Marcher &m, float k) {
-  return sample_tmu_uvw<DT, LINEAR>(V, fmaf(k, m.du, m.u0), fmaf(k, m.dv, m.v0), fmaf(k, m.dw, m.w0));
+  return sample_tmu_uvw<FMT, LINEAR>(V, fmaf(k, m.du, m.u0), fmaf(k, m.dv, m.v0), fmaf(k, m.dw, m.w0));
 }
 
 // does sample k belong to this slab?  (its footprint starts in global slices [z0, z1))
@@ -108,18 +108,20 @@ __device__ __forceinline__ int brick_coord(float c, int g, int shift) {
   return min(max(i, 0), g - 1);
 }
 
-template <int DT, bool LINEAR, bool SKIP, bool SLAB, bool STATS>
-__global__ void __launch_bounds__(128) mip_fast_kernel(const MipArgs a) {
-  __shared__ __align__(16) float s_out[4][32];
-  __shared__ __align__(16) float s_alpha[4][32];
+// A CTA is TX x TY warps and covers (8*TX) x (4*TY) pixels.
+template <int FMT, bool LINEAR, bool SKIP, bool SLAB, int TX, int TY>
+__global__ void __launch_bounds__(32 * TX * TY) mip_fast_kernel(const MipArgs a) {
+  __shared__ __align__(16) float s_out[TX * TY][32];
+  __shared__ __align__(16) float s_alpha[TX * TY][32];
+  const bool STATS = a.stats != nullptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
   const int ly = ((lane >> 1) & 1) | ((lane >> 2) & 2);
-  const unsigned tx0 = blockIdx.x * 16 + (warp & 1) * 8, ty0 = blockIdx.y * 8 + (warp >> 1) * 4;
+  const unsigned tx0 = blockIdx.x * (8 * TX) + (warp % TX) * 8, ty0 = blockIdx.y * (4 * TY) + (warp / TX) * 4;
   const unsigned x = tx0 + lx, y = ty0 + ly;
   const unsigned Nx = a.width, Ny = a.height;
   const bool inb = x < Nx && y < Ny;
-  const bool isShort = DT != 0;
+  const bool isShort = (FMT % 3) != 0;
   const Volume &V = a.vol;
 
   Ray r = make_ray(x, y, Nx, Ny, a.cam, a.box);
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(128) mip_fast_kernel(const MipArgs a) {
   float tnear = r.tnear;
   if (tnear < 0.0f) tnear = 0.0f;
   float cur = 0.f;
-  unsigned long long nfetch = 0;
+  unsigned nfetch = 0;
 
   if (hit) {
     const int reducedSteps = a.max_steps / a.num_parts;
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(128) mip_fast_kernel(const MipArgs a) {
         for (int k = 0; k < S; k += 16) {
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fetch_k<DT, LINEAR, SLAB>(V, m, (float)(k + j));
+          for (int j = 0; j < 16; ++j) v[j] = fetch_k<FMT, LINEAR, SLAB>(V, m, (float)(k + j));
 #pragma unroll
           for (int j = 0; j < 16; ++j) cur = fmaxf(cur, v[j]);
         }
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(128) mip_fast_kernel(const MipArgs a) {
       } else {
         for (int k = 0; k < S; ++k) {
           if (owns_k(V, m, (float)k)) {
-            cur = fmaxf(cur, fetch_k<DT, LINEAR, SLAB>(V, m, (float)k));
+            cur = fmaxf(cur, fetch_k<FMT, LINEAR, SLAB>(V, m, (float)k));
             if (STATS) ++nfetch;
           }
         }
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(128) mip_fast_kernel(const MipArgs a) {
         for (int j = 0; j < 8; ++j) {
           const float kk = (float)(k + j * PRE);
           const bool ok = (k + j * PRE < S) && (!SLAB || owns_k(V, m, kk));
-          v[j] = ok ? fetch_k<DT, LINEAR, SLAB>(V, m, kk) : 0.f;
+          v[j] = ok ? fetch_k<FMT, LINEAR, SLAB>(V, m, kk) : 0.f;
           if (STATS) nfetch += ok;
         }
 #pragma unroll
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(128) mip_fast_kernel(const MipArgs a) {
               }
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                v[j] = need[j] ? fetch_k<DT, LINEAR, SLAB>(V, m, (float)(k + j)) : 0.f;
+                v[j] = need[j] ? fetch_k<FMT, LINEAR, SLAB>(V, m, (float)(k + j)) : 0.f;
                 if (STATS) nfetch += need[j];
               }
 #pragma unroll
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(128) mip_fast_kernel(const MipArgs a) {
       }
       for (int k = k0; k < S; ++k) {  // only reached when the traversal was cut short: sample the rest plainly
         if (!SLAB || owns_k(V, m, (float)k)) {
-          cur = fmaxf(cur, fetch_k<DT, LINEAR, SLAB>(V, m, (float)k));
+          cur = fmaxf(cur, fetch_k<FMT, LINEAR, SLAB>(V, m, (float)k));
           if (STATS) ++nfetch;
         }
       }
@@ -238,14 +240,14 @@ __global__ void __launch_bounds__(128) mip_fast_kernel(const MipArgs a) {
   }
 
   if (STATS) {
-    unsigned long long nh = hit ? 1ull : 0ull;
+    unsigned nf = nfetch, nh = hit ? 1u : 0u;
     for (int o = 16; o > 0; o >>= 1) {
-      nfetch += __shfl_down_sync(0xffffffffu, nfetch, o);
+      nf += __shfl_down_sync(0xffffffffu, nf, o);
       nh += __shfl_down_sync(0xffffffffu, nh, o);
     }
-    if (lane == 0 && a.stats) {
-      atomicAdd(a.stats + 0, nh);
-      atomicAdd(a.stats + 1, nfetch);
+    if (lane == 0) {
+      atomicAdd(a.stats + 0, (unsigned long long)nh);
+      atomicAdd(a.stats + 1, (unsigned long long)nf);
     }
   }
 
@@ -294,43 +296,125 @@ __global__ void mip_finish_kernel(const float *raw, float *out, int n, float min
 }
 
 // -------------------------------------------------------------------------------------------------------------
-template <int DT, bool LINEAR>
-static cudaError_t launch_fast(const MipArgs &a, bool skip, bool slab, bool stats, cudaStream_t st) {
-  dim3 grid((a.width + 15) / 16, (a.height + 7) / 8), block(128);
-#define SPV_FAST(SK, SL, STT) mip_fast_kernel<DT, LINEAR, SK, SL, STT><<<grid, block, 0, st>>>(a)
-  if (stats) {
-    if (skip) { if (slab) SPV_FAST(true, true, true); else SPV_FAST(true, false, true); }
-    else { if (slab) SPV_FAST(false, true, true); else SPV_FAST(false, false, true); }
+template <int FMT, bool LINEAR, bool SKIP, bool SLAB, int TX, int TY>
+static void launch_fast_shape(const MipArgs &a, cudaStream_t st) {
+  dim3 grid((a.width + 8 * TX - 1) / (8 * TX), (a.height + 4 * TY - 1) / (4 * TY)), block(32 * TX * TY);
+  mip_fast_kernel<FMT, LINEAR, SKIP, SLAB, TX, TY><<<grid, block, 0, st>>>(a);
+}
+
+template <int FMT, bool LINEAR>
+static cudaError_t launch_fast(const MipArgs &a, bool skip, bool slab, cudaStream_t st) {
+  if (skip) {
+    if (slab) launch_fast_shape<FMT, LINEAR, true, true, 2, 2>(a, st);
+    else launch_fast_shape<FMT, LINEAR, true, false, 2, 2>(a, st);
+  } else if (slab) {
+    launch_fast_shape<FMT, LINEAR, false, true, 2, 2>(a, st);
   } else {
-    if (skip) { if (slab) SPV_FAST(true, true, false); else SPV_FAST(true, false, false); }
-    else { if (slab) SPV_FAST(false, true, false); else SPV_FAST(false, false, false); }
+    switch (a.tile_variant) {  // CTA shape: tuning knob (spv_set_tuning)
+      case 1: launch_fast_shape<FMT, LINEAR, false, false, 2, 4>(a, st); break;   // 16x16 px, 256 threads
+      case 2: launch_fast_shape<FMT, LINEAR, false, false, 4, 4>(a, st); break;   // 32x16 px, 512 threads
+      case 3: launch_fast_shape<FMT, LINEAR, false, false, 4, 8>(a, st); break;   // 32x32 px, 1024 threads
+      case 4: launch_fast_shape<FMT, LINEAR, false, false, 8, 4>(a, st); break;   // 64x16 px, 1024 threads
+      default: launch_fast_shape<FMT, LINEAR, false, false, 2, 2>(a, st); break;  // 16x8 px, 128 threads
+    }
   }
-#undef SPV_FAST
   return cudaGetLastError();
 }
 
-template <int DT, bool LINEAR>
+template <int FMT, bool LINEAR>
 static cudaError_t launch_ref(const MipArgs &a, bool exact, cudaStream_t st) {
   dim3 grid((a.width + 15) / 16, (a.height + 7) / 8), block(128);
-  if (exact) mip_ref_kernel<DT, LINEAR, true><<<grid, block, 0, st>>>(a);
-  else mip_ref_kernel<DT, LINEAR, false><<<grid, block, 0, st>>>(a);
+  if (exact) mip_ref_kernel<FMT, LINEAR, true><<<grid, block, 0, st>>>(a);
+  else mip_ref_kernel<FMT, LINEAR, false><<<grid, block, 0, st>>>(a);
   return cudaGetLastError();
 }
 
-template <int DT>
+template <int FMT>
 static cudaError_t launch_dt(const MipArgs &a, bool linear, bool fast, bool exact, bool skip, bool slab, bool stats,
                              cudaStream_t st) {
-  if (fast) return linear ? launch_fast<DT, true>(a, skip, slab, stats, st) : launch_fast<DT, false>(a, skip, slab, stats, st);
-  return linear ? launch_ref<DT, true>(a, exact, st) : launch_ref<DT, false>(a, exact, st);
+  if (fast) return linear ? launch_fast<FMT, true>(a, skip, slab, st) : launch_fast<FMT, false>(a, skip, slab, st);
+  return linear ? launch_ref<FMT, true>(a, exact, st) : launch_ref<FMT, false>(a, exact, st);
 }
 
 cudaError_t launch_mip(const MipArgs &a, int dtype, bool linear, bool fast, bool exact, bool skip, bool slab,
                        bool stats, cudaStream_t st) {
-  switch (dtype) {
+  switch (dtype) {  // FMT = dtype + 3 * layout
     case 0: return launch_dt<0>(a, linear, fast, exact, skip, slab, stats, st);
     case 1: return launch_dt<1>(a, linear, fast, exact, skip, slab, stats, st);
-    default: return launch_dt<2>(a, linear, fast, exact, skip, slab, stats, st);
+    case 2: return launch_dt<2>(a, linear, fast, exact, skip, slab, stats, st);
+    case 4: return launch_dt<4>(a, linear, fast, exact, skip, slab, stats, st);
+    case 5: return launch_dt<5>(a, linear, fast, exact, skip, slab, stats, st);
+    default: return cudaErrorInvalidValue;
   }
+}
+
+// Direct sampler access for tests: out[i] = sample(volume, pos[i]) with pos in normalised coordinates, exactly
+// as the render kernels sample (TMU or exact sampler).
+template <int FMT, bool LINEAR, bool EXACT>
+__global__ void sample_points_kernel(const Volume V, const float *__restrict__ pos, int n, float *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = sample<FMT, LINEAR, EXACT>(V, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+}
+
+cudaError_t launch_sample_points(const Volume &V, int dtype, bool linear, bool exact, const float *pos, int n,
+                                 float *out, cudaStream_t st) {
+  const int blocks = (n + 255) / 256;
+#define SPV_SP(FMT) \
+  if (linear) { if (exact) sample_points_kernel<FMT, true, true><<<blocks, 256, 0, st>>>(V, pos, n, out); \
+                else sample_points_kernel<FMT, true, false><<<blocks, 256, 0, st>>>(V, pos, n, out); } \
+  else { if (exact) sample_points_kernel<FMT, false, true><<<blocks, 256, 0, st>>>(V, pos, n, out); \
+         else sample_points_kernel<FMT, false, false><<<blocks, 256, 0, st>>>(V, pos, n, out); }
+  switch (dtype) {
+    case 0: SPV_SP(0) break;
+    case 1: SPV_SP(1) break;
+    case 2: SPV_SP(2) break;
+    case 4: SPV_SP(4) break;
+    case 5: SPV_SP(5) break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef SPV_SP
+  return cudaGetLastError();
+}
+
+// Calibration probe for the texture-sample roofline: every lane issues independent filtered fetches inside a
+// small (cache-resident) region of the resident volume, with no dependent arithmetic between them.
+template <int FMT, bool LINEAR>
+__global__ void __launch_bounds__(256) texrate_probe_kernel(const Volume V, int iters, float *sink) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
+  const int ly = ((lane >> 1) & 1) | ((lane >> 2) & 2);
+  // an 8x4 tile of neighbouring sample positions, 0.6 texel apart, marching along z like a ray would
+  const float bx = 0.37f * (float)V.nx + 0.6f * (float)lx + 3.1f * (float)(warp & 3);
+  const float by = 0.41f * (float)V.ny + 0.6f * (float)ly + 2.7f * (float)(warp >> 2);
+  const float bz = 0.29f * (float)V.nz + 1.9f * (float)(blockIdx.x & 7);
+  float acc = 0.f;
+  for (int it = 0; it < iters; ++it) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      v[j] = sample_tmu_uvw<FMT, LINEAR>(V, bx + 0.05f * (float)j, by + 0.03f * (float)j, bz + 0.9f * (float)(j & 7) + 0.11f * (float)(it & 3));
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc = fmaxf(acc, v[j]);
+  }
+  if (acc == -12345.f) sink[0] = acc;  // never true: keeps the fetches alive
+}
+
+cudaError_t launch_texrate_probe(const Volume &V, int dtype, bool linear, int blocks, int iters, float *sink,
+                                 cudaStream_t st) {
+#define SPV_PROBE(FMT) \
+  if (linear) texrate_probe_kernel<FMT, true><<<blocks, 256, 0, st>>>(V, iters, sink); \
+  else texrate_probe_kernel<FMT, false><<<blocks, 256, 0, st>>>(V, iters, sink)
+  switch (dtype) {
+    case 0: SPV_PROBE(0); break;
+    case 1: SPV_PROBE(1); break;
+    case 2: SPV_PROBE(2); break;
+    case 4: SPV_PROBE(4); break;
+    case 5: SPV_PROBE(5); break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef SPV_PROBE
+  return cudaGetLastError();
 }
 
 cudaError_t launch_mip_finish(const float *raw, float *out, int n, float minVal, float maxVal, float gamma,

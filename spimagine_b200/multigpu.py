@@ -82,6 +82,11 @@ class SlabMaxProjector(VolumeRenderer):
                 rank, world = 0, 1
         self.rank, self.world = rank, world
         super(SlabMaxProjector, self).__init__(size, interpolation, **kw)
+        self._stream = None
+        if world > 1 and torch.cuda.is_available():
+            # one non-default stream for both the render kernels and the collective: ordered without host syncs
+            self._stream = torch.cuda.Stream(device=self.device)
+            self.use_stream(self._stream.cuda_stream)
 
     def set_data(self, data, autoConvert=True, copyData=False):
         if not autoConvert and not data.dtype in self.dtypes:
@@ -130,13 +135,10 @@ class SlabMaxProjector(VolumeRenderer):
         p = _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma), 0.,
                            1, 0, int(self.max_steps), _lib.MIP_RAW_ONLY)
         torch = self._torch
-        if self.world > 1:
-            # render on torch's current stream so the collective is ordered after the kernel without a host sync
-            stream = torch.cuda.current_stream(self.device)
-            self._check(self._lib.spv_set_stream(self._ctx, C.c_void_p(stream.cuda_stream)))
         self._check(self._lib.spv_render_mip(self._ctx, C.byref(p)))
-        if self.world > 1:
-            composite_max(self._raw_tensor(), self.group)
+        if self.world > 1 and self._dist.is_initialized():
+            with torch.cuda.stream(self._stream):
+                composite_max(self._raw_tensor(), self.group)
         self._check(self._lib.spv_mip_finish(self._ctx, C.byref(p)))
         flat, n = self._fetch(2)
         shape = (self.height, self.width)

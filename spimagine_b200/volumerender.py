@@ -134,6 +134,16 @@ class VolumeRenderer(object):
         self.int_filter = int_filter
         self._check(self._lib.spv_set_int_filter(self._ctx, int(int_filter == "linear")))
 
+    def set_layout(self, layout="zpair"):
+        """Storage of integer volumes from the next set_data on: "zpair" (layered {v[z], v[z+1]} texels, one
+        bilinear fetch + fp32 z-lerp per sample; default) or "3d" (plain 3-D array, one trilinear fetch)."""
+        codes = {"3d": 0, "zpair": 1}
+        if layout not in codes:
+            raise KeyError("layout = '%s' not defined, valid: %s" % (layout, list(codes.keys())))
+        self.layout = layout
+        self._check(self._lib.spv_set_layout(self._ctx, codes[layout]))
+        self._need_alloc = True
+
     def set_skipping(self, on=True):
         self._check(self._lib.spv_set_skipping(self._ctx, int(bool(on))))
 
@@ -362,6 +372,34 @@ class VolumeRenderer(object):
         v = (C.c_ulonglong * 2)()
         self._check(self._lib.spv_last_stats(self._ctx, v, 2))
         return int(v[0]), int(v[1])
+
+    def texrate_probe(self, iters=2000):
+        """Measured samples/s of independent cache-resident filtered fetches (roofline denominator)."""
+        v = C.c_double()
+        self._check(self._lib.spv_texrate_probe(self._ctx, int(iters), C.byref(v)))
+        return v.value
+
+    def sample_points(self, pos):
+        """Values of the resident volume at normalised positions pos (n, 3) = (x, y, z) in [0, 1], through the
+        current sampler: what read_imagef(volume, sampler, pos).x returns to the reference kernels."""
+        pos = np.ascontiguousarray(pos, np.float32)
+        out = np.empty(len(pos), np.float32)
+        self._check(self._lib.spv_sample_points(self._ctx, _lib.fp(pos), len(pos), _lib.fp(out)))
+        return out
+
+    def use_stream(self, cuda_stream=None):
+        """Run on a caller-owned CUDA stream (an int cudaStream_t, e.g. torch's current stream); None restores
+        the renderer's own stream."""
+        self._check(self._lib.spv_set_stream(self._ctx, C.c_void_p(cuda_stream or 0)))
+
+    def render_device_only(self, numParts=1, currentPart=0):
+        """Enqueue one max projection with the current settings and return without reading anything back."""
+        p = _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma),
+                           float(self.alphaPow), int(numParts), int(currentPart), int(self.max_steps), 0)
+        self._check(self._lib.spv_render_mip(self._ctx, C.byref(p)))
+
+    def sync(self):
+        self._check(self._lib.spv_sync(self._ctx))
 
     def launch_count(self):
         n = C.c_ulonglong()

@@ -44,32 +44,43 @@ def random_vol(shape, dtype, seed=0):
     return rng.integers(0, hi + 1, size=shape).astype(dtype)
 
 
-def _splitmix64(x):
-    x = (x + np.uint64(0x9E3779B97F4A7C15))
-    z = x
-    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-    return z ^ (z >> np.uint64(31))
+def _hash32(x):
+    """lowbias32 integer hash on uint32 arrays (wrap-around arithmetic)."""
+    x = x.copy()
+    x ^= x >> np.uint32(16)
+    x *= np.uint32(0x7feb352d)
+    x ^= x >> np.uint32(15)
+    x *= np.uint32(0x846ca68b)
+    x ^= x >> np.uint32(16)
+    return x
 
 
 def vol_g(N, dtype=np.uint16, seed=0, noise=0.01, shape=None, t=0):
-    """SURVEY.md 8d Vol-G: 8 Gaussian blobs + 1 % hashed noise, peak 1.0 (f32) / 60000 (u16) / 250 (u8)."""
+    """SURVEY.md 8d Vol-G: 8 Gaussian blobs (centres U(-.6,.6)^3 drifting 0.01 t, sigma U(.08,.25), amplitude
+    U(.3,1)) on linspace(-1,1) per axis, plus 1 % hashed per-voxel noise, scaled to peak 1.0 (f32), 60000 (u16)
+    or 250 (u8).  The blobs are evaluated as separable products so that 512^3 takes seconds."""
     rng = np.random.default_rng(seed)
     c = rng.uniform(-.6, .6, (8, 3)) + 0.01 * t
     s = rng.uniform(.08, .25, 8)
     a = rng.uniform(.3, 1., 8)
     nz, ny, nx = shape if shape is not None else (N, N, N)
-    z = np.linspace(-1, 1, nz, dtype=np.float32)[:, None, None]
-    y = np.linspace(-1, 1, ny, dtype=np.float32)[None, :, None]
-    x = np.linspace(-1, 1, nx, dtype=np.float32)[None, None, :]
+    z = np.linspace(-1, 1, nz, dtype=np.float32)
+    y = np.linspace(-1, 1, ny, dtype=np.float32)
+    x = np.linspace(-1, 1, nx, dtype=np.float32)
     v = np.zeros((nz, ny, nx), np.float32)
     for i in range(8):
-        v += np.float32(a[i]) * np.exp(-((x - np.float32(c[i, 2])) ** 2 + (y - np.float32(c[i, 1])) ** 2 +
-                                          (z - np.float32(c[i, 0])) ** 2) / np.float32(2 * s[i] ** 2))
-    with np.errstate(over="ignore"):
-        idx = np.arange(v.size, dtype=np.uint64) ^ np.uint64(seed)
-        h = _splitmix64(idx)
-    v += np.float32(noise) * ((h >> np.uint64(40)).astype(np.float32) / np.float32(1 << 24)).reshape(v.shape)
+        k = np.float32(1. / (2 * s[i] ** 2))
+        gz = (np.float32(a[i]) * np.exp(-k * (z - np.float32(c[i, 0])) ** 2)).astype(np.float32)
+        gy = np.exp(-k * (y - np.float32(c[i, 1])) ** 2).astype(np.float32)
+        gx = np.exp(-k * (x - np.float32(c[i, 2])) ** 2).astype(np.float32)
+        v += gz[:, None, None] * (gy[:, None] * gx[None, :])[None, :, :]
+    if noise:
+        for k0 in range(0, nz, 64):  # in slabs: bounds the temporaries for 512^3 and up
+            k1 = min(k0 + 64, nz)
+            idx = np.arange(k0 * ny * nx, k1 * ny * nx, dtype=np.uint64).astype(np.uint32)
+            h = _hash32(idx ^ np.uint32((seed * 2654435761) & 0xffffffff))
+            v[k0:k1] += (np.float32(noise) * (h >> np.uint32(8)).astype(np.float32) /
+                         np.float32(1 << 24)).reshape(k1 - k0, ny, nx)
     v /= v.max()
     if np.dtype(dtype) == np.float32:
         return v
