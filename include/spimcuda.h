@@ -143,7 +143,8 @@ SPV_API int spv_last_timing_ms(spv_ctx *ctx, float *ms);            /* device ti
 SPV_API int spv_last_stats(spv_ctx *ctx, unsigned long long *v, int n); /* [hit rays, texture samples issued] of the
                                                                 last render when stats were enabled */
 SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
-/* performance knobs that never change results; knob 0 = CTA shape of the max-projection kernel */
+/* performance knobs that never change results; knob 0 = CTA shape / occupancy target of the max-projection kernel,
+ * knob 1 = persistent CTAs pulling tiles from a counter (1) or one CTA per tile (0) */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 SPV_API const char *spv_last_error(spv_ctx *ctx);                   /* ctx may be NULL: last create error */
 SPV_API int spv_version(void);

@@ -52,14 +52,17 @@ def sweep(n=360):
 
 
 ref = None
-for variant in range(5):
-    lib.spv_set_tuning(ctx, 0, variant)
-    rend.set_modelView(cams[40][0])
-    rend.render()
-    img = rend.output.copy()
-    if ref is None:
-        ref = img
-    same = bool(np.array_equal(img, ref))
-    fps = [sweep() for _ in range(3)]
-    print("variant %d: %s frames/s  identical=%s" % (variant, ["%.0f" % f for f in fps], same), flush=True)
+for persistent in (0, 1):
+    for variant in range(5):
+        lib.spv_set_tuning(ctx, 0, variant)
+        lib.spv_set_tuning(ctx, 1, persistent)
+        rend.set_modelView(cams[40][0])
+        rend.render()
+        img = rend.output.copy()
+        if ref is None:
+            ref = img
+        same = bool(np.array_equal(img, ref))
+        fps = [sweep() for _ in range(3)]
+        print("persistent %d variant %d: %s frames/s  identical=%s" % (persistent, variant, ["%.0f" % f for f in fps], same),
+              flush=True)
 print("tex probe: %.1f Gsamples/s" % (rend.texrate_probe(4000) / 1e9))

@@ -32,7 +32,8 @@ struct spv_ctx {
   float h_minmax[2] = {0.f, 0.f};
   bool minmax_valid = false;
   // settings
-  int linear = 1, sampler = SPV_SAMPLER_TMU, int_filter = 1, skipping = 0, stats_on = 0, tile_variant = 0;
+  int linear = 1, sampler = SPV_SAMPLER_TMU, int_filter = 1, skipping = 0, stats_on = 0, tile_variant = 0, persistent = 0;
+  unsigned *d_tile_counter = nullptr;
   Camera cam;
   // result buffers: one allocation  [out | alpha | depth | occ | normals(3) | raw | tmp | tmp_vec(3)]
   float *dbuf = nullptr;
@@ -146,6 +147,7 @@ SPV_API int spv_create(int device, int width, int height, spv_ctx **out) {
   CC(cudaEventCreate(&ctx->ev1));
   CC(cudaMalloc(&ctx->d_minmax, 2 * sizeof(float)));
   CC(cudaMalloc(&ctx->d_stats, 2 * sizeof(unsigned long long)));
+  CC(cudaMalloc(&ctx->d_tile_counter, sizeof(unsigned)));
 #undef CC
   int rc = alloc_buffers(ctx, width, height);
   if (rc) {
@@ -165,6 +167,7 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
   free_buffers(ctx);
   if (ctx->d_minmax) cudaFree(ctx->d_minmax);
   if (ctx->d_stats) cudaFree(ctx->d_stats);
+  if (ctx->d_tile_counter) cudaFree(ctx->d_tile_counter);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -388,6 +391,7 @@ SPV_API int spv_set_skipping(spv_ctx *ctx, int on) {
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   if (!ctx) return SPV_EINVAL;
   if (knob == 0) ctx->tile_variant = value;
+  else if (knob == 1) ctx->persistent = value != 0;
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
   return 0;
 }
@@ -444,6 +448,7 @@ SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p) {
   a.width = ctx->width; a.height = ctx->height;
   a.out = ctx->out(); a.alpha = ctx->alpha(); a.raw = ctx->raw();
   a.stats = ctx->stats_on ? ctx->d_stats : nullptr;
+  a.tile_counter = ctx->persistent ? ctx->d_tile_counter : nullptr;
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
   int rc = begin_render(ctx);
   if (rc) return rc;

@@ -17,6 +17,7 @@ struct MipArgs {
   int width, height;
   float *out, *alpha, *raw;
   unsigned long long *stats;  // [hit rays, texture samples issued] or nullptr
+  unsigned *tile_counter;     // non-null: persistent CTAs pull tiles from this counter
 };
 
 struct IsoArgs {

@@ -108,16 +108,15 @@ __device__ __forceinline__ int brick_coord(float c, int g, int shift) {
   return min(max(i, 0), g - 1);
 }
 
-// A CTA is TX x TY warps and covers (8*TX) x (4*TY) pixels.
+// One CTA tile: TX x TY warps cover (8*TX) x (4*TY) pixels starting at CTA tile (bx, by).
 template <int FMT, bool LINEAR, bool SKIP, bool SLAB, int TX, int TY>
-__global__ void __launch_bounds__(32 * TX * TY) mip_fast_kernel(const MipArgs a) {
-  __shared__ __align__(16) float s_out[TX * TY][32];
-  __shared__ __align__(16) float s_alpha[TX * TY][32];
+__device__ __forceinline__ void mip_fast_tile(const MipArgs &a, unsigned bx, unsigned by, float (*s_out)[32],
+                                              float (*s_alpha)[32]) {
   const bool STATS = a.stats != nullptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
   const int ly = ((lane >> 1) & 1) | ((lane >> 2) & 2);
-  const unsigned tx0 = blockIdx.x * (8 * TX) + (warp % TX) * 8, ty0 = blockIdx.y * (4 * TY) + (warp / TX) * 4;
+  const unsigned tx0 = bx * (8 * TX) + (warp % TX) * 8, ty0 = by * (4 * TY) + (warp / TX) * 4;
   const unsigned x = tx0 + lx, y = ty0 + ly;
   const unsigned Nx = a.width, Ny = a.height;
   const bool inb = x < Nx && y < Ny;
@@ -287,6 +286,34 @@ __global__ void __launch_bounds__(32 * TX * TY) mip_fast_kernel(const MipArgs a)
   }
 }
 
+// Static grid: one CTA per tile.
+template <int FMT, bool LINEAR, bool SKIP, bool SLAB, int TX, int TY, int MINB>
+__global__ void __launch_bounds__(32 * TX * TY, MINB) mip_fast_kernel(const MipArgs a) {
+  __shared__ __align__(16) float s_out[TX * TY][32];
+  __shared__ __align__(16) float s_alpha[TX * TY][32];
+  mip_fast_tile<FMT, LINEAR, SKIP, SLAB, TX, TY>(a, blockIdx.x, blockIdx.y, s_out, s_alpha);
+}
+
+// Persistent grid: (SMs x resident CTAs) CTAs pull tiles from a counter, so rays that miss the box or leave it
+// early do not leave SMs idle behind a static schedule's last wave.  Tiles are handed out in row-major order:
+// the CTAs in flight then cover a band of image rows, i.e. a slab of the volume that stays in L2.
+template <int FMT, bool LINEAR, bool SKIP, bool SLAB, int TX, int TY, int MINB>
+__global__ void __launch_bounds__(32 * TX * TY, MINB) mip_fast_persistent_kernel(const MipArgs a) {
+  __shared__ __align__(16) float s_out[TX * TY][32];
+  __shared__ __align__(16) float s_alpha[TX * TY][32];
+  __shared__ unsigned s_tile;
+  const unsigned tiles_x = (a.width + 8 * TX - 1) / (8 * TX), tiles_y = (a.height + 4 * TY - 1) / (4 * TY);
+  const unsigned ntiles = tiles_x * tiles_y;
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(a.tile_counter, 1u);
+    __syncthreads();
+    const unsigned t = s_tile;
+    __syncthreads();
+    if (t >= ntiles) break;
+    mip_fast_tile<FMT, LINEAR, SKIP, SLAB, TX, TY>(a, t % tiles_x, t / tiles_x, s_out, s_alpha);
+  }
+}
+
 // window + gamma of the composited raw maximum (sort-last renders)
 __global__ void mip_finish_kernel(const float *raw, float *out, int n, float minVal, float maxVal, float gamma) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,26 +323,42 @@ __global__ void mip_finish_kernel(const float *raw, float *out, int n, float min
 }
 
 // -------------------------------------------------------------------------------------------------------------
-template <int FMT, bool LINEAR, bool SKIP, bool SLAB, int TX, int TY>
+template <int FMT, bool LINEAR, bool SKIP, bool SLAB, int TX, int TY, int MINB>
 static void launch_fast_shape(const MipArgs &a, cudaStream_t st) {
   dim3 grid((a.width + 8 * TX - 1) / (8 * TX), (a.height + 4 * TY - 1) / (4 * TY)), block(32 * TX * TY);
-  mip_fast_kernel<FMT, LINEAR, SKIP, SLAB, TX, TY><<<grid, block, 0, st>>>(a);
+  if (a.tile_counter) {
+    static int resident = 0;  // CTAs per SM x SMs for this instantiation (queried once)
+    if (resident == 0) {
+      int per_sm = 0, dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mip_fast_persistent_kernel<FMT, LINEAR, SKIP, SLAB, TX, TY, MINB>,
+                                                    32 * TX * TY, 0);
+      resident = (per_sm > 0 ? per_sm : 1) * (sms > 0 ? sms : 1);
+    }
+    const unsigned ntiles = grid.x * grid.y;
+    cudaMemsetAsync(a.tile_counter, 0, sizeof(unsigned), st);
+    mip_fast_persistent_kernel<FMT, LINEAR, SKIP, SLAB, TX, TY, MINB>
+        <<<ntiles < (unsigned)resident ? ntiles : (unsigned)resident, block, 0, st>>>(a);
+  } else {
+    mip_fast_kernel<FMT, LINEAR, SKIP, SLAB, TX, TY, MINB><<<grid, block, 0, st>>>(a);
+  }
 }
 
 template <int FMT, bool LINEAR>
 static cudaError_t launch_fast(const MipArgs &a, bool skip, bool slab, cudaStream_t st) {
   if (skip) {
-    if (slab) launch_fast_shape<FMT, LINEAR, true, true, 2, 2>(a, st);
-    else launch_fast_shape<FMT, LINEAR, true, false, 2, 2>(a, st);
+    if (slab) launch_fast_shape<FMT, LINEAR, true, true, 2, 2, 1>(a, st);
+    else launch_fast_shape<FMT, LINEAR, true, false, 2, 2, 1>(a, st);
   } else if (slab) {
-    launch_fast_shape<FMT, LINEAR, false, true, 2, 2>(a, st);
+    launch_fast_shape<FMT, LINEAR, false, true, 2, 2, 1>(a, st);
   } else {
-    switch (a.tile_variant) {  // CTA shape: tuning knob (spv_set_tuning)
-      case 1: launch_fast_shape<FMT, LINEAR, false, false, 2, 4>(a, st); break;   // 16x16 px, 256 threads
-      case 2: launch_fast_shape<FMT, LINEAR, false, false, 4, 4>(a, st); break;   // 32x16 px, 512 threads
-      case 3: launch_fast_shape<FMT, LINEAR, false, false, 4, 8>(a, st); break;   // 32x32 px, 1024 threads
-      case 4: launch_fast_shape<FMT, LINEAR, false, false, 8, 4>(a, st); break;   // 64x16 px, 1024 threads
-      default: launch_fast_shape<FMT, LINEAR, false, false, 2, 2>(a, st); break;  // 16x8 px, 128 threads
+    switch (a.tile_variant) {  // CTA shape / occupancy target: tuning knob (spv_set_tuning)
+      case 1: launch_fast_shape<FMT, LINEAR, false, false, 2, 4, 1>(a, st); break;   // 16x16 px, 256 threads
+      case 2: launch_fast_shape<FMT, LINEAR, false, false, 2, 2, 12>(a, st); break;  // 16x8 px, <= 40 registers
+      case 3: launch_fast_shape<FMT, LINEAR, false, false, 2, 2, 16>(a, st); break;  // 16x8 px, <= 32 registers
+      case 4: launch_fast_shape<FMT, LINEAR, false, false, 2, 1, 16>(a, st); break;  // 16x4 px, 64 threads
+      default: launch_fast_shape<FMT, LINEAR, false, false, 2, 2, 1>(a, st); break;  // 16x8 px, 128 threads
     }
   }
   return cudaGetLastError();
