@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--vol", type=int, default=VOL_N)
     ap.add_argument("--img", type=int, default=IMG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "slab"],
+                    help="sweep: BASELINE configs[1], frames sharded over the GPUs (default). slab: configs[3], one "
+                         "--vol^3 uint16 volume split into z-slabs over the GPUs, sort-last max composite over NCCL")
     ap.add_argument("--skip", action="store_true", help="enable empty-space skipping on the min/max brick grid")
     return ap.parse_args()
 
@@ -187,6 +190,185 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def vol_g_slab_device(N, z_lo, z_hi, seed, device):
+    """Slices [z_lo, z_hi) of Vol-G(N, uint16, seed) generated on the GPU with torch (plumbing: bench input only).
+    Same recipe as tests/scenes.py::vol_g; every rank evaluates the same expressions for a given global slice,
+    so slabs and halos agree bit for bit across ranks.  Peak scaled to 60000 by the analytic maximum bound."""
+    import torch
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-.6, .6, (8, 3))
+    sg = rng.uniform(.08, .25, 8)
+    a = rng.uniform(.3, 1., 8)
+    lin = torch.linspace(-1, 1, N, device=device, dtype=torch.float32)
+    out = torch.empty((z_hi - z_lo, N, N), dtype=torch.uint16, device=device)
+    # normalisation: maximum of the blob sum on a coarse 64^3 grid (identical on every rank)
+    g = torch.linspace(-1, 1, 64, device=device, dtype=torch.float32)
+    coarse = torch.zeros((64, 64, 64), device=device)
+    for i in range(8):
+        k = float(1. / (2 * sg[i] ** 2))
+        coarse += float(a[i]) * (torch.exp(-k * (g - float(c[i, 0])) ** 2)[:, None, None] *
+                                 torch.exp(-k * (g - float(c[i, 1])) ** 2)[None, :, None] *
+                                 torch.exp(-k * (g - float(c[i, 2])) ** 2)[None, None, :])
+    scale = 58000. / float(coarse.max())
+    step = 16
+    for zb in range(z_lo, z_hi, step):
+        ze = min(zb + step, z_hi)
+        v = torch.zeros((ze - zb, N, N), device=device)
+        for i in range(8):
+            k = float(1. / (2 * sg[i] ** 2))
+            gz = float(a[i]) * torch.exp(-k * (lin[zb:ze] - float(c[i, 0])) ** 2)
+            gy = torch.exp(-k * (lin - float(c[i, 1])) ** 2)
+            gx = torch.exp(-k * (lin - float(c[i, 2])) ** 2)
+            v += gz[:, None, None] * (gy[:, None] * gx[None, :])[None]
+        idx = torch.arange(zb * N * N, ze * N * N, device=device, dtype=torch.int64).reshape(ze - zb, N, N)
+        h = (idx * 2654435761 + seed * 40503) & 0xffffffff
+        h = ((h ^ (h >> 15)) * 2246822519) & 0xffffffff
+        h = (h ^ (h >> 13)) & 0xffffff
+        v = v * scale + (0.01 * 58000. / float(1 << 24)) * h.to(torch.float32)
+        out[zb - z_lo:ze - z_lo] = v.clamp_(0, 65535).round_().to(torch.int32).to(torch.uint16)
+    return out
+
+
+def run_slab(args, rank, local_rank, world):
+    """BASELINE configs[3]: --vol^3 uint16 split into `world` z-slabs, every frame = raw slab render on each GPU,
+    all-reduce(MAX) over NCCL, window.  Strong scaling: the total work per frame is fixed."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    import scenes
+    import ctypes as C
+    from spimagine_b200 import _lib
+    from spimagine_b200.multigpu import SlabMaxProjector, partition_slabs, slab_with_halo
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    N, W = args.vol, args.img
+    z0, z1 = partition_slabs(N, world)[rank]
+    lo, hi = slab_with_halo(z0, z1, N)
+    t0 = time.perf_counter()
+    slab = vol_g_slab_device(N, lo, hi, 2, torch.device("cuda", local_rank))
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t0
+    rend = SlabMaxProjector((W, W), rank=rank, world=world, device=local_rank, max_steps=MAX_STEPS,
+                            pinned_outputs=True)
+    if rend._stream is None:
+        rend._stream = torch.cuda.Stream(device=local_rank)
+        rend.use_stream(rend._stream.cuda_stream)
+    torch.cuda.set_stream(rend._stream)
+    t0 = time.perf_counter()
+    rend.set_slab((np.uint16, N, N), N, z0, z1, device_ptr=slab.data_ptr())
+    rend.sync()
+    t_upload = time.perf_counter() - t0
+    del slab
+    torch.cuda.empty_cache()
+    rend.set_max_val(PEAK_VALUE)
+    cams = sweep_cameras()
+    rend.set_projection(cams[0][1])
+    mats = []
+    for M, P in cams:
+        rend.set_modelView(M)
+        mats.append((rend._invP.copy(), rend._invM.copy()))
+    lib, ctx = rend._lib, rend._ctx
+    params = _lib.MipParams(rend._box(), 0., PEAK_VALUE, 1., 0., 1, 0, MAX_STEPS, _lib.MIP_RAW_ONLY)
+    raw = rend._raw_tensor()
+
+    def step(i):
+        invP, invM = mats[(i * 7) % SWEEP]
+        lib.spv_set_matrices(ctx, _lib.fp(invP), _lib.fp(invM))
+        rc = lib.spv_render_mip(ctx, C.byref(params))
+        if rc:
+            _lib.check(rc, ctx)
+        if world > 1:
+            dist.all_reduce(raw, op=dist.ReduceOp.MAX)
+        lib.spv_mip_finish(ctx, C.byref(params))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rend.enable_stats(True)
+    step(0)
+    hits0, issued0 = rend.last_stats()
+    rend.enable_stats(False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = rend.launch_count()
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = rend.launch_count() - l0 - 2 * args.warmup
+
+    # end to end: the public render() call, composited image read back to pinned host memory on every rank
+    digest = hashlib.sha1()
+    for i in range(3):
+        rend.set_modelView(cams[(i * 7) % SWEEP][0])
+        rend.render()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        rend.set_modelView(cams[(i * 7) % SWEEP][0])
+        rend.render()
+        if i < 8:
+            digest.update(rend.output.tobytes())
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms, t_e2e * 1e3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, t_e2e = float(t[0]), float(t[1]) / 1e3
+        cnt = torch.tensor([float(issued0)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        issued_total = float(cnt[0])
+    else:
+        issued_total = float(issued0)
+    if rank == 0:
+        fps = args.steps / (ms * 1e-3)
+        peaks, peak_src = measured_peaks()
+        alg_bytes = float(N) ** 3 * 2 + 2 * W * W * 4
+        line = {
+            "metric": "MIP frames/s, %d^3 uint16 -> %d^2, sort-last z-slabs + NCCL max composite" % (N, W),
+            "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u16->f32", "data": "synthetic",
+            "config": {"workload": "Vol-G(%d, uint16, seed 2) generated on device, max_project -> %dx%d, "
+                                   "max_steps=200, %d z-slab(s) with one halo slice, all-reduce(MAX) of the %d MiB raw "
+                                   "plane, then window" % (N, W, W, world, W * W * 4 >> 20),
+                       "l2": "each slab (%d MB as z-paired texels) exceeds the 126 MB L2" % (
+                           (hi - lo) * N * N * 4 >> 20),
+                       "parallelism": "sort-last, %d slab(s)" % world},
+            "gsamples_per_s": fps * hits0 * SAMPLES_PER_RAY / 1e9,
+            "hit_rays_per_frame": hits0, "issued_samples_per_frame_all_ranks": issued_total,
+            "e2e": {"value": args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128,
+                    "d2h_bytes_per_step": 2 * W * W * 4,
+                    "note": "SlabMaxProjector.set_modelView + render() on every rank, composited output + alpha read "
+                            "back into pinned host memory"},
+            "image_sha1_first8": digest.hexdigest(),
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3 / args.steps) / 1e9 / world,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s (per GPU)",
+                         "frac": alg_bytes / (ms * 1e-3 / args.steps) / 1e9 / world / peaks["hbm_gbs"],
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_frame_all_gpus": alg_bytes},
+            "gen_s": t_gen, "upload_s": t_upload,
+        }
+        print(json.dumps(line))
+    rend.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -194,6 +376,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload == "slab":
+        run_slab(args, rank, local_rank, world)
         return
 
     import torch

@@ -88,8 +88,9 @@ SPV_API int spv_set_int_filter(spv_ctx *ctx, int linear);
  * float32 volumes always use SPV_LAYOUT_3D. */
 enum { SPV_LAYOUT_3D = 0, SPV_LAYOUT_ZPAIR = 1 };
 SPV_API int spv_set_layout(spv_ctx *ctx, int layout);
-/* empty-brick skipping for the TMU max projection (default off: it pays on sparse volumes only; results are
- * identical either way) */
+/* empty-space skipping on the min/max brick grids (texture-unit sampler; results are identical either way):
+ * -1 = auto (default: on for iso surfaces, off for max projection, where it only pays on sparse volumes),
+ * 0 = off, 1 = on for both */
 SPV_API int spv_set_skipping(spv_ctx *ctx, int on);
 
 /* invPBuf / invMBuf.write_array, volumerender.py:310-316: row-major float[16] each */

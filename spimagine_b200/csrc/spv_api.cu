@@ -32,8 +32,9 @@ struct spv_ctx {
   float h_minmax[2] = {0.f, 0.f};
   bool minmax_valid = false;
   // settings
-  int linear = 1, sampler = SPV_SAMPLER_TMU, int_filter = 1, skipping = 0, stats_on = 0, tile_variant = 0, persistent = 0;
+  int linear = 1, sampler = SPV_SAMPLER_TMU, int_filter = 1, skipping = -1, stats_on = 0, tile_variant = 0, persistent = 0;
   unsigned *d_tile_counter = nullptr;
+  unsigned char *d_tile_hit = nullptr;  // per 16x8 tile: holds an iso-surface pixel
   Camera cam;
   // result buffers: one allocation  [out | alpha | depth | occ | normals(3) | raw | tmp | tmp_vec(3)]
   float *dbuf = nullptr;
@@ -83,6 +84,8 @@ static int cufail(spv_ctx *c, cudaError_t e, const char *where) {
 static void free_buffers(spv_ctx *c) {
   if (c->dbuf) cudaFree(c->dbuf);
   if (c->hpin) cudaFreeHost(c->hpin);
+  if (c->d_tile_hit) cudaFree(c->d_tile_hit);
+  c->d_tile_hit = nullptr;
   c->dbuf = nullptr;
   c->hpin = nullptr;
 }
@@ -110,6 +113,7 @@ static int alloc_buffers(spv_ctx *ctx, int w, int h) {
   const size_t n = ctx->n();
   CU(cudaMalloc(&ctx->dbuf, 12 * n * sizeof(float)));
   CU(cudaMemsetAsync(ctx->dbuf, 0, 12 * n * sizeof(float), ctx->stream));
+  CU(cudaMalloc(&ctx->d_tile_hit, (size_t)((w + 15) / 16) * ((h + 7) / 8)));
   CU(cudaMallocHost(&ctx->hpin, 7 * n * sizeof(float)));
   memset(ctx->hpin, 0, 7 * n * sizeof(float));
   return 0;
@@ -385,7 +389,7 @@ SPV_API int spv_set_layout(spv_ctx *ctx, int layout) {
 }
 SPV_API int spv_set_skipping(spv_ctx *ctx, int on) {
   if (!ctx) return SPV_EINVAL;
-  ctx->skipping = on != 0;
+  ctx->skipping = on < 0 ? -1 : (on != 0);
   return 0;
 }
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
@@ -452,7 +456,7 @@ SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p) {
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
   int rc = begin_render(ctx);
   if (rc) return rc;
-  CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, ctx->skipping != 0, ctx->slab, ctx->stats_on != 0, ctx->stream));
+  CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, ctx->skipping > 0, ctx->slab, ctx->stats_on != 0, ctx->stream));
   ctx->launches += 1;
   ctx->last_method = 0;
   return end_render(ctx);
@@ -490,6 +494,9 @@ SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p) {
   a.cgx = ctx->cgx; a.cgy = ctx->cgy; a.cgz = ctx->cgz;
   memcpy(a.box, p->box, sizeof a.box);
   a.iso_val = p->iso_val; a.gamma = p->gamma; a.max_steps = p->max_steps;
+  const bool exact_iso = ctx->sampler == SPV_SAMPLER_EXACT;
+  a.tile_hit = exact_iso ? nullptr : ctx->d_tile_hit;
+  a.skip = ctx->skipping != 0;  // auto (-1) = on: for iso surfaces the brick test is nearly free and exact
   a.width = ctx->width; a.height = ctx->height;
   a.out = ctx->out(); a.alpha = ctx->alpha(); a.depth = ctx->depth(); a.normals = ctx->normals();
   a.stats = ctx->stats_on ? ctx->d_stats : nullptr;
@@ -501,7 +508,8 @@ SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p) {
   if (!(p->flags & SPV_ISO_RAW_ONLY)) {
     // volumerender.py:470-497
     CU(launch_conv(ctx->normals(), ctx->tmp_vec(), ctx->width, ctx->height, 3, conv_weights(7, -5.f), ctx->stream));
-    CU(launch_occlusion(ctx->occ(), ctx->width, ctx->height, p->occ_radius, p->occ_n_points, ctx->depth(), ctx->stream));
+    CU(launch_occlusion(ctx->occ(), ctx->width, ctx->height, p->occ_radius, p->occ_n_points, ctx->depth(), a.tile_hit,
+                        ctx->stream));
     CU(launch_conv(ctx->occ(), ctx->tmp(), ctx->width, ctx->height, 1, conv_weights(5, -10.f), ctx->stream));
     CU(launch_shading(ctx->out(), ctx->width, ctx->height, ctx->cam, p->occ_strength, ctx->normals(), ctx->depth(),
                       ctx->occ(), ctx->stream));

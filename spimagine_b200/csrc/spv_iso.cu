@@ -108,9 +108,156 @@ __global__ void __launch_bounds__(128) iso_kernel(const IsoArgs a) {
   }
 }
 
+// -------------------------------------------------------------------------------------------------------------
+// iso_fast_kernel: the texture-unit path.  Same first-crossing rule, bracket refinement and 12-tap gradient, but
+//   * sample k sits at pos0 + k*delta (one fma per axis, unnormalised texel coordinates) instead of being
+//     accumulated, so that
+//   * the coarse search fetches BATCH samples at a time (independent fetches in flight instead of one
+//     fetch -> compare -> branch round trip per sample) and then looks for the first crossing in the batch;
+//     at most BATCH-1 samples behind the crossing are fetched in vain,
+//   * the ten refinement samples are fetched together as well.
+template <int FMT, bool LINEAR, bool SKIP>
+__global__ void __launch_bounds__(128) iso_fast_kernel(const IsoArgs a) {
+  constexpr int BATCH = 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
+  const int ly = ((lane >> 1) & 1) | ((lane >> 2) & 2);
+  const unsigned x = blockIdx.x * 16 + (warp & 1) * 8 + lx, y = blockIdx.y * 8 + (warp >> 1) * 4 + ly;
+  const unsigned Nx = a.width, Ny = a.height;
+  const bool inb = x < Nx && y < Ny;
+  const size_t p = x + (size_t)Nx * y;
+  const Volume &V = a.vol;
+  const float INF = __int_as_float(0x7f800000);
+  unsigned nfetch = 0;
+
+  Ray r = make_ray(x, y, Nx, Ny, a.cam, a.box);
+  r.hit = r.hit && inb;
+  bool hitIso = false;
+  float tnear = r.tnear, t_hit = INF;
+  v4 normal = mk4(0.f, 0.f, 0.f, 0.f);
+  float colVal = 0.f;
+  if (r.hit) {
+    const v4 direc = r.direc;
+    if (tnear < 0.0f) tnear = 0.0f;
+    const float isoVal = a.iso_val;
+    const int maxSteps = a.max_steps;
+    const float dt = 1.f * (r.tfar - tnear) / ((float)maxSteps - 1.f);
+    const v4 delta_pos = scl4(.5f * dt, direc);
+    const v4 pos0 = scl4(0.5f, add4(sadd4(1.f, r.orig), scl4(tnear, direc)));
+    const float u0 = pos0.x * V.fnx, v0 = pos0.y * V.fny, w0 = pos0.z * V.fnz;
+    const float du = delta_pos.x * V.fnx, dv = delta_pos.y * V.fny, dw = delta_pos.z * V.fnz;
+#define SPV_AT(t) sample_tmu_uvw<FMT, LINEAR>(V, fmaf((t), du, u0), fmaf((t), dv, v0), fmaf((t), dw, w0))
+    const bool isGreater = SPV_AT(0.f) > isoVal;
+    int i = maxSteps;
+    // Empty-space skipping (exact): a sample whose footprint lies in a cell with max <= iso cannot be "> iso", one
+    // in a cell with min > iso cannot be "<= iso"; such a sample cannot be the first crossing and is not fetched.
+    // Coarse cells (32^3 texels) first, the 8^3 brick only where the coarse cell straddles the threshold.
+    const float cx0 = u0 - 0.5f, cy0 = v0 - 0.5f, cz0 = w0 - 0.5f - (float)V.z_lo;
+    for (int k0 = 1; k0 < maxSteps && !hitIso; k0 += BATCH) {
+      float v[BATCH];
+      bool need[BATCH];
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) {
+        const float t = (float)min(k0 + j, maxSteps - 1);
+        need[j] = true;
+        if (SKIP) {
+          const int ix = __float2int_rd(fmaf(t, du, cx0)), iy = __float2int_rd(fmaf(t, dv, cy0)),
+                    iz = __float2int_rd(fmaf(t, dw, cz0));
+          const int cx = min(max(ix >> (BRICK_SHIFT + 2), 0), a.cgx - 1), cy = min(max(iy >> (BRICK_SHIFT + 2), 0), a.cgy - 1),
+                    cz = min(max(iz >> (BRICK_SHIFT + 2), 0), a.cgz - 1);
+          const float2 c = __ldg(a.coarse + ((size_t)cz * a.cgy + cy) * a.cgx + cx);
+          need[j] = isGreater ? !(c.x > isoVal) : (c.y > isoVal);
+          if (need[j]) {
+            const int bx = min(max(ix >> BRICK_SHIFT, 0), V.gx - 1), by = min(max(iy >> BRICK_SHIFT, 0), V.gy - 1),
+                      bz = min(max(iz >> BRICK_SHIFT, 0), V.gz - 1);
+            const float2 b = brick_at(V, bx, by, bz);
+            need[j] = isGreater ? !(b.x > isoVal) : (b.y > isoVal);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) {
+        v[j] = need[j] ? SPV_AT((float)min(k0 + j, maxSteps - 1)) : (isGreater ? INF : -INF);
+        nfetch += need[j];
+      }
+#pragma unroll
+      for (int j = BATCH - 1; j >= 0; --j)
+        if (k0 + j < maxSteps && ((v[j] > isoVal) != isGreater)) {
+          i = k0 + j;
+          hitIso = true;
+        }
+    }
+    if (hitIso) {
+      t_hit = tnear + (float)i * dt;
+      const int maxBisect = 10;
+      const float dt2 = dt / (float)maxBisect;
+      float v[maxBisect];
+#pragma unroll
+      for (int j = 0; j < maxBisect; ++j) v[j] = SPV_AT((float)(i - 1) + (float)j / (float)maxBisect);
+      int J = maxBisect;
+#pragma unroll
+      for (int j = maxBisect - 1; j >= 0; --j)
+        if ((v[j] > isoVal) != isGreater) J = j + 1;
+      for (int j = 0; j < J; ++j) t_hit += dt2;  // accumulated like the reference does
+      nfetch += maxBisect;
+      // where the reference's `pos` stands after the refinement loop, in normalised coordinates
+      const float ts = (float)(i - 1) + (float)J / (float)maxBisect;
+      const float px = fmaf(ts, delta_pos.x, pos0.x), py = fmaf(ts, delta_pos.y, pos0.y), pz = fmaf(ts, delta_pos.z, pos0.z);
+      v4 light = mk4(2.f, -1.f, -2.f, 0.f);
+      const float c_ambient = .3f, c_diffuse = .4f, c_specular = .3f;
+      light = mult(a.cam.invM, light);
+      light = normalize4(light);
+      float h = dt;
+      h *= (a.gamma * a.gamma);
+      const float h2 = 2.f * h;
+#define SPV_S(dx, dy, dz) sample_tmu<FMT, LINEAR>(V, px + (dx), py + (dy), pz + (dz))
+      const float xa = SPV_S(h, 0.f, 0.f), xb = SPV_S(-h, 0.f, 0.f), xc = SPV_S(h2, 0.f, 0.f), xd = SPV_S(-h2, 0.f, 0.f);
+      const float ya = SPV_S(0.f, h, 0.f), yb = SPV_S(0.f, -h, 0.f), yc = SPV_S(0.f, h2, 0.f), yd = SPV_S(0.f, -h2, 0.f);
+      const float za = SPV_S(0.f, 0.f, h), zb = SPV_S(0.f, 0.f, -h), zc = SPV_S(0.f, 0.f, h2), zd = SPV_S(0.f, 0.f, -h2);
+#undef SPV_S
+      nfetch += 12;
+      normal.x = 2.f * xa - 2.f * xb + xc - xd;
+      normal.y = 2.f * ya - 2.f * yb + yc - yd;
+      normal.z = za - zb + zc - zd;
+      normal.w = 0.f;
+      normal = scl4(1.f - (float)(2 * (int)isGreater), normalize4(normal));
+      const v4 reflect = sub4(scl4(2.f * dot4(light, normal), normal), light);
+      const float diffuse = fmaxf(0.f, dot4(light, normal));
+      const float specular = powf(fmaxf(0.f, dot4(normalize4(reflect), normalize4(direc))), 10.f);
+      colVal = c_ambient + c_diffuse * diffuse + (diffuse > 0.f ? 1.f : 0.f) * c_specular * specular;
+    }
+#undef SPV_AT
+  }
+  if (inb) {
+    a.out[p] = hitIso ? colVal : 0.f;
+    a.alpha[p] = hitIso ? tnear : 0.f;
+    a.depth[p] = hitIso ? t_hit : INF;
+    a.normals[3 * p + 0] = normal.x;
+    a.normals[3 * p + 1] = normal.y;
+    a.normals[3 * p + 2] = normal.z;
+  }
+  // one flag per 16x8 CTA tile: does it contain a surface pixel?  (lets the occlusion pass skip empty regions)
+  const int any = __syncthreads_or(hitIso ? 1 : 0);
+  if (threadIdx.x == 0 && a.tile_hit) a.tile_hit[blockIdx.y * gridDim.x + blockIdx.x] = (unsigned char)(any != 0);
+  if (a.stats) {
+    atomicAdd(a.stats + 0, r.hit ? 1ull : 0ull);
+    atomicAdd(a.stats + 1, (unsigned long long)nfetch);
+  }
+}
+
 template <int FMT>
 static cudaError_t launch_iso_dt(const IsoArgs &a, bool linear, bool exact, bool stats, cudaStream_t st) {
   dim3 grid((a.width + 15) / 16, (a.height + 7) / 8), block(128);
+  if (!exact) {
+    if (a.skip) {
+      if (linear) iso_fast_kernel<FMT, true, true><<<grid, block, 0, st>>>(a);
+      else iso_fast_kernel<FMT, false, true><<<grid, block, 0, st>>>(a);
+    } else {
+      if (linear) iso_fast_kernel<FMT, true, false><<<grid, block, 0, st>>>(a);
+      else iso_fast_kernel<FMT, false, false><<<grid, block, 0, st>>>(a);
+    }
+    return cudaGetLastError();
+  }
 #define SPV_ISO(L, E, S) iso_kernel<FMT, L, E, S><<<grid, block, 0, st>>>(a)
   if (stats) {
     if (linear) { if (exact) SPV_ISO(true, true, true); else SPV_ISO(true, false, true); }
@@ -191,18 +338,49 @@ __device__ __forceinline__ float rand_int_cl(uint32_t x, uint32_t y, int start, 
   return (float)(int)((float)start + random_cl(x, y) * (float)(end - start));
 }
 
-__global__ void occlusion_kernel(float *__restrict__ d_output, int Nx, int Ny, int radius, int number_points,
-                                 const float *__restrict__ input_depth) {
+// The four rand_int() arguments of a tap depend on the tap index only (occlusion.cl:60,62): they are evaluated once
+// per CTA into shared memory, which halves the hash evaluations per pixel (2 instead of 4 per tap, 10 LCG rounds
+// each).  Values are identical to evaluating them per pixel.
+__global__ void __launch_bounds__(256) occlusion_kernel(float *__restrict__ d_output, int Nx, int Ny, int radius,
+                                                        int number_points, const float *__restrict__ input_depth,
+                                                        const unsigned char *__restrict__ tile_hit, int tiles_x) {
+  extern __shared__ float s_tap[];  // 4 floats per tap
+  for (unsigned i = threadIdx.y * blockDim.x + threadIdx.x; i < (unsigned)number_points; i += blockDim.x * blockDim.y) {
+    s_tap[4 * i + 0] = rand_int_cl(i, i * i, 0, 1000);
+    s_tap[4 * i + 1] = rand_int_cl(i * i, i, 294, 97701);
+    s_tap[4 * i + 2] = rand_int_cl(i * i, i, 0, 1997);
+    s_tap[4 * i + 3] = rand_int_cl(i, i * i, 569, 17633);
+  }
+  // Every tap lands within `radius` pixels of its pixel.  If no 16x8 tile overlapping this CTA's pixels grown by
+  // `radius` holds a surface pixel, every depth read is INFINITY, `depth < depth0` is false for every tap and the
+  // result is exactly 0: skip the hashing.
+  int reach = 1;
+  if (tile_hit) {
+    const int x0 = (int)(blockIdx.x * blockDim.x) - radius, x1 = (int)(blockIdx.x * blockDim.x + blockDim.x - 1) + radius;
+    const int y0 = (int)(blockIdx.y * blockDim.y) - radius, y1 = (int)(blockIdx.y * blockDim.y + blockDim.y - 1) + radius;
+    const int tx0 = max(x0, 0) / 16, tx1 = min(x1, Nx - 1) / 16, ty0 = max(y0, 0) / 8, ty1 = min(y1, Ny - 1) / 8;
+    const int tw = tx1 - tx0 + 1, n = tw * (ty1 - ty0 + 1);
+    int mine = 0;
+    for (int t = threadIdx.y * blockDim.x + threadIdx.x; t < n; t += blockDim.x * blockDim.y)
+      mine |= tile_hit[(ty0 + t / tw) * tiles_x + tx0 + t % tw];
+    reach = __syncthreads_or(mine);
+  } else {
+    __syncthreads();
+  }
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= Nx || y >= Ny) return;
+  if (!reach) {
+    d_output[x + (size_t)Nx * y] = 0.f;
+    return;
+  }
   const float MPI_2 = 6.2831853071795f;
   const float depth0 = input_depth[x + (size_t)y * Nx];
   float occ = 0.f;
   for (unsigned i = 0; i < (unsigned)number_points; ++i) {
-    const float r = (float)(unsigned)radius * random_cl((uint32_t)((float)x + rand_int_cl(i, i * i, 0, 1000)),
-                                                        (uint32_t)((float)y + rand_int_cl(i * i, i, 294, 97701)));
-    const float phi = MPI_2 * random_cl((uint32_t)((float)x + rand_int_cl(i * i, i, 0, 1997)),
-                                        (uint32_t)((float)y + rand_int_cl(i, i * i, 569, 17633)));
+    const float r = (float)(unsigned)radius * random_cl((uint32_t)((float)x + s_tap[4 * i + 0]),
+                                                        (uint32_t)((float)y + s_tap[4 * i + 1]));
+    const float phi = MPI_2 * random_cl((uint32_t)((float)x + s_tap[4 * i + 2]),
+                                        (uint32_t)((float)y + s_tap[4 * i + 3]));
     const int x2 = clampi((int)((float)x + r * cosf(phi)), 0, Nx - 1);
     const int y2 = clampi((int)((float)y + r * sinf(phi)), 0, Ny - 1);
     const float depth = input_depth[x2 + (size_t)y2 * Nx];
@@ -212,9 +390,11 @@ __global__ void occlusion_kernel(float *__restrict__ d_output, int Nx, int Ny, i
 }
 
 cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int n_points, const float *depth,
-                             cudaStream_t st) {
+                             const unsigned char *tile_hit, cudaStream_t st) {
   dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
-  occlusion_kernel<<<grid, block, 0, st>>>(occ, width, height, radius, n_points, depth);
+  const size_t smem = (size_t)(n_points > 0 ? n_points : 1) * 4 * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;  // > 3072 taps
+  occlusion_kernel<<<grid, block, smem, st>>>(occ, width, height, radius, n_points, depth, tile_hit, (width + 15) / 16);
   return cudaGetLastError();
 }
 
@@ -224,6 +404,10 @@ __global__ void shading_kernel(float *__restrict__ d_output, int Nx, int Ny, con
                                const float *__restrict__ input_occlusion) {
   const unsigned x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= (unsigned)Nx || y >= (unsigned)Ny) return;
+  if (!(input_depth[x + (size_t)Nx * y] < __int_as_float(0x7f800000))) {  // colVal * 0 below: nothing to compute
+    d_output[x + (size_t)Nx * y] = 0.f;
+    return;
+  }
   v4 orig, direc;
   eye_ray(x, y, Nx, Ny, cam, orig, direc);
   v4 light = mk4(2.f, -1.f, -2.f, 0.f);

@@ -28,8 +28,10 @@ struct IsoArgs {
   float box[6];
   float iso_val, gamma;
   int max_steps;
+  int skip;  // empty-space skipping on the min/max grids (texture-unit path)
   int width, height;
   float *out, *alpha, *depth, *normals;
+  unsigned char *tile_hit;  // one flag per 16x8 tile (texture-unit path) or nullptr
   unsigned long long *stats;
 };
 
@@ -53,7 +55,7 @@ cudaError_t launch_iso(const IsoArgs &a, int dtype, bool linear, bool exact, boo
 cudaError_t launch_conv(float *buf, float *tmp, int width, int height, int ncomp, const ConvWeights &w,
                         cudaStream_t st);
 cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int n_points, const float *depth,
-                             cudaStream_t st);
+                             const unsigned char *tile_hit, cudaStream_t st);
 cudaError_t launch_shading(float *out, int width, int height, const Camera &cam, float occ_strength,
                            const float *normals, const float *depth, const float *occ, cudaStream_t st);
 

@@ -100,6 +100,31 @@ __device__ __forceinline__ bool owns_k(const Volume &V, const Marcher &m, float 
   return kf >= (float)V.z0 && kf < (float)V.z1;
 }
 
+// clamped slice index the footprint of sample k starts in
+__device__ __forceinline__ float slice_of_k(const Volume &V, const Marcher &m, int k) {
+  return fminf(fmaxf(floorf(fmaf((float)k, m.dw, m.w0) - 0.5f), 0.f), (float)(V.nz - 1));
+}
+// [ka, kb) = the samples k in [0, S) with slice_of_k in [z0, z1)  (same predicate as owns_k)
+__device__ __forceinline__ void owned_interval(const Volume &V, const Marcher &m, int S, int &ka, int &kb) {
+  const float z0 = (float)V.z0, z1 = (float)V.z1;
+  const bool up = m.dw >= 0.f;  // slice index non-decreasing in k
+  // first k whose slice is past the near bound / past the far bound, in marching direction
+  int lo = 0, hi = S;
+  while (lo < hi) {  // first k with (up ? slice >= z0 : slice < z1)
+    const int mid = (lo + hi) >> 1;
+    const float s = slice_of_k(V, m, mid);
+    if (up ? (s >= z0) : (s < z1)) hi = mid; else lo = mid + 1;
+  }
+  ka = lo;
+  hi = S;
+  while (lo < hi) {  // first k >= ka with (up ? slice >= z1 : slice < z0)
+    const int mid = (lo + hi) >> 1;
+    const float s = slice_of_k(V, m, mid);
+    if (up ? (s >= z1) : (s < z0)) hi = mid; else lo = mid + 1;
+  }
+  kb = lo;
+}
+
 // clamped brick coordinate of a texel-centre coordinate c = u - 0.5
 __device__ __forceinline__ int brick_coord(float c, int g, int shift) {
   // floor, then arithmetic shift; clamp handles everything outside (incl. huge/NaN -> 0)
@@ -152,12 +177,18 @@ __device__ __forceinline__ void mip_fast_tile(const MipArgs &a, unsigned bx, uns
         }
         if (STATS) nfetch += S;
       } else {
-        for (int k = 0; k < S; ++k) {
-          if (owns_k(V, m, (float)k)) {
-            cur = fmaxf(cur, fetch_k<FMT, LINEAR, SLAB>(V, m, (float)k));
-            if (STATS) ++nfetch;
-          }
+        // The slice index floor(w(k) - 1/2) is monotone in k (fma, subtraction and floor all are), so the samples
+        // this slab owns form one interval [ka, kb): two binary searches with the exact predicate, then march it.
+        int ka, kb;
+        owned_interval(V, m, S, ka, kb);
+        for (int k = ka; k < kb; k += 8) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = (k + j < kb) ? fetch_k<FMT, LINEAR, SLAB>(V, m, (float)(k + j)) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cur = fmaxf(cur, v[j]);
         }
+        if (STATS) nfetch += (unsigned)(kb - ka);
       }
     } else {
       // ---- pre-pass: every PRE-th sample gives a true lower bound of the ray maximum cheaply ----

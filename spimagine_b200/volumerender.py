@@ -145,7 +145,9 @@ class VolumeRenderer(object):
         self._need_alloc = True
 
     def set_skipping(self, on=True):
-        self._check(self._lib.spv_set_skipping(self._ctx, int(bool(on))))
+        """Empty-space skipping on the min/max brick grids: True / False, or None for the default (on for
+        iso surfaces, off for max projection).  Never changes the image."""
+        self._check(self._lib.spv_set_skipping(self._ctx, -1 if on is None else int(bool(on))))
 
     def set_dtype(self, dtype=None):
         if hasattr(self, "dtype") and dtype is self.dtype:
@@ -244,6 +246,22 @@ class VolumeRenderer(object):
         else:
             rc = self._lib.spv_update_volume(self._ctx, host.ctypes.data)
         self._check(rc)
+
+    def set_data_device(self, device_ptr, shape, dtype):
+        """Addition: take the volume from DEVICE memory (C-order (Nz, Ny, Nx) at `device_ptr`, e.g.
+        tensor.data_ptr() of a torch / cupy array on this GPU): frame sources that keep timepoints in HBM."""
+        dtype = np.dtype(dtype)
+        if dtype.type not in self.dtypes:
+            raise NotImplementedError("data type should be either %s not %s" % (self.dtypes, dtype))
+        self.set_dtype(dtype.type)
+        self.dataSlices = None
+        Nz, Ny, Nx = (int(s) for s in shape)
+        self.set_shape((Nx, Ny, Nz))
+        self._data = None
+        self._check(self._lib.spv_set_volume_device(self._ctx, C.c_void_p(int(device_ptr)), _lib.DTYPE_CODES[dtype],
+                                                    Nx, Ny, Nz))
+        self._need_alloc = False
+        self.update_matrices()
 
     @property
     def data_min_max(self):

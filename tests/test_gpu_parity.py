@@ -338,6 +338,67 @@ def test_iso_sphere_tmu_within_north_star_tolerance(oracle_mod, layout):
     assert np.percentile(np.abs(g.output_normals[same] - o.output_normals[same]), 99) < 1e-2
 
 
+@pytest.mark.parametrize("layout", ["zpair", "3d"])
+def test_iso_skipping_does_not_change_the_image(layout):
+    """Empty-space skipping in the iso-surface search is exact: identical buffers with it on and off, from
+    outside the surface and from a camera that starts inside it (isGreater == true)."""
+    for dtype, peak in ((np.uint16, 60000.), (np.float32, 1.)):
+        data = scenes.vol_g(112, dtype, seed=5)
+        g = _renderer((240, 200))
+        g.set_layout(layout)
+        g.set_data(data)
+        g.enable_stats(True)
+        for theta, dist, frac in ((0.3, 3.0, .3), (1.4, 2.4, .1), (2.0, 0.2, .05)):
+            M, P = scenes.gui_camera(theta, dist)
+            g.set_modelView(M)
+            g.set_projection(P)
+            res = []
+            for skip in (False, True):
+                g.set_skipping(skip)
+                g.render(maxVal=2 * frac * peak, method="iso_surface")
+                res.append((g.output.copy(), g.output_depth.copy(), g.output_normals.copy(), g.output_alpha.copy(),
+                            g.output_occlusion.copy(), g.last_stats()))
+            for a, b in zip(res[0][:5], res[1][:5]):
+                assert np.array_equal(a, b)
+            assert res[1][5][1] < res[0][5][1]          # fewer texture samples issued
+            assert np.isfinite(res[0][1]).sum() > 500   # the scene does show a surface
+
+
+def test_iso_post_passes_on_the_tmu_path(oracle_mod):
+    """The texture-unit path skips the occlusion hashing where no surface pixel is within reach and shades only
+    surface pixels; both shortcuts must be invisible: recompute occlusion -> blur -> shading with the oracle from
+    the GPU's own depth / normal buffers."""
+    data = scenes.vol_g(96, np.uint16, seed=3)
+    M, P = scenes.gui_camera(0.6, 4.5)     # small object in a large image: most tiles are out of reach
+    g = _renderer((320, 256))
+    g.set_data(data)
+    g.set_modelView(M)
+    g.set_projection(P)
+    g.set_occ_strength(.4)
+    g.set_occ_radius(13)
+    g.set_occ_n_points(25)
+    g.render(maxVal=40000., method="iso_surface")
+    hit = np.isfinite(g.output_depth)
+    assert 1000 < hit.sum() < 0.5 * hit.size
+    lib = oracle_mod.load("port")
+    fp = oracle_mod._fp
+    H, W = g.output_depth.shape
+    depth = np.ascontiguousarray(g.output_depth)
+    occ = np.zeros((H, W), np.float32)
+    tmp = np.zeros((H, W), np.float32)
+    lib.so_occlusion(fp(occ), W, H, 13, 25, fp(depth))
+    lib.so_convolve_scalar(fp(occ), fp(tmp), W, H, 5)
+    assert np.mean(np.abs(occ - g.output_occlusion) > 1e-6) < 0.02
+    assert _maxdiff(occ, g.output_occlusion) < 0.1
+    assert (g.output_occlusion[~hit] >= 0).all()
+    out = np.zeros((H, W), np.float32)
+    invP, invM = g._invP, g._invM
+    lib.so_shading(fp(out), W, H, fp(invP), fp(invM), .4, fp(np.ascontiguousarray(g.output_normals)), fp(depth),
+                   fp(np.ascontiguousarray(g.output_occlusion)))
+    assert _maxdiff(out, g.output) < 2e-5
+    assert (g.output[~hit] == 0).all()
+
+
 def test_iso_full_pipeline_exact(oracle_mod):
     """iso_surface -> blur(7) -> occlusion -> blur(5) -> shading against the oracle, stage by stage."""
     data = scenes.two_blobs(48)
