@@ -42,8 +42,9 @@ PEAK_VALUE = 60000.
 SWEEP = 360
 METRIC = "MIP frames/s, 512^3 uint16 -> 1024^2, 360-degree modelView sweep"
 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch of the max-projection kernel on this
-# workload (profiles/); None until a capture exists
-NCU_TRAFFIC_BYTES = None
+# workload: profiles/r01_mip_ncu_summary.json "prof_mip_zpair_session3" (407.9 MB read + 9.3 MB written; the z-paired
+# volume is 512 MiB, of which a frame touches the part its rays cross)
+NCU_TRAFFIC_BYTES = 417157120
 
 
 def parse():
