@@ -109,6 +109,12 @@ enum {
                            needs alpha_pow == 0 and num_parts == 1 */
 };
 SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p);
+/* Render + read-back in one call (replaces run_kernel followed by the blocking buf.get() / buf_alpha.get() of
+ * _render_max_project, volumerender.py:366-390).  The frame is rendered as `bands` horizontal bands (<= 0: the
+ * context's default, tuning knob 2); the rows of a finished band are copied into the selected slot's pinned staging
+ * ([out | alpha]) while the next band renders.  wait != 0: returns when the frame is in host memory; wait == 0:
+ * returns at once, collect with spv_wait_slot.  *host (may be NULL) = the slot's staging. */
+SPV_API int spv_render_mip_to_host(spv_ctx *ctx, const spv_mip_params *p, int bands, int wait, float **host);
 /* window + gamma of SPV_BUF_RAW into SPV_BUF_OUT after the cross-GPU max composite */
 SPV_API int spv_mip_finish(spv_ctx *ctx, const spv_mip_params *p);
 
@@ -139,13 +145,27 @@ SPV_API int spv_read_many(spv_ctx *ctx, float *out, float *alpha, float *depth, 
 SPV_API int spv_read_pinned(spv_ctx *ctx, int planes, float **host);
 SPV_API int spv_device_ptr(spv_ctx *ctx, int which, void **dev_ptr);
 
+/* ---- pipelined sequences (new; replaces the blocking buf.get() per frame of the GUI spin / keyframe loops,
+ *      gui/glwidget.py:636-692, volumerender.py:388-390): two output slots, each a full set of device result
+ *      buffers plus pinned staging.  Frame i renders into slot i&1 while frame i-1 is still on its way to the host. ---- */
+/* result buffers that subsequent renders write and reads fetch (0 or 1; slot 1 is allocated on first use).  A render
+ * into a slot waits on the device for an asynchronous read of that slot that is still in flight. */
+SPV_API int spv_select_slot(spv_ctx *ctx, int slot);
+/* enqueue one device->host transfer of the first `planes` planes of the selected slot on the context's copy stream,
+ * ordered after everything enqueued so far on the render stream; returns immediately */
+SPV_API int spv_read_pinned_async(spv_ctx *ctx, int planes);
+/* block until the last asynchronous read of `slot` has landed; *host = its pinned staging (valid until the next
+ * read of that slot or a resize) */
+SPV_API int spv_wait_slot(spv_ctx *ctx, int slot, float **host);
+
 /* ---- diagnostics ---- */
 SPV_API int spv_last_timing_ms(spv_ctx *ctx, float *ms);            /* device time of the last render call */
 SPV_API int spv_last_stats(spv_ctx *ctx, unsigned long long *v, int n); /* [hit rays, texture samples issued] of the
                                                                 last render when stats were enabled */
 SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
 /* performance knobs that never change results; knob 0 = CTA shape / occupancy target of the max-projection kernel,
- * knob 1 = persistent CTAs pulling tiles from a counter (1) or one CTA per tile (0) */
+ * knob 1 = persistent CTAs pulling tiles from a counter (1) or one CTA per tile (0), knob 2 = default band count of
+ * spv_render_mip_to_host */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 SPV_API const char *spv_last_error(spv_ctx *ctx);                   /* ctx may be NULL: last create error */
 SPV_API int spv_version(void);

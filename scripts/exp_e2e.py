@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""End-to-end frame rate of the synchronous render() call against the read-back strategy (C2 workload)."""
+import math, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import scenes
+from spimagine_b200 import VolumeRenderer
+
+vol = scenes.vol_g(512, np.uint16, seed=0)
+cams = [scenes.gui_camera(2 * math.pi * f / 360, 4.0) for f in range(360)]
+rend = VolumeRenderer((1024, 1024), pinned_outputs=True)
+rend.set_data(vol)
+rend.set_max_val(60000.)
+rend.set_projection(cams[0][1])
+lib, ctx = rend._lib, rend._ctx
+ref = None
+def run(label, n=360):
+    global ref
+    for i in range(5):
+        rend.set_modelView(cams[i][0]); rend.render()
+    t0 = time.perf_counter()
+    for i in range(n):
+        rend.set_modelView(cams[i][0]); rend.render()
+    dt = time.perf_counter() - t0
+    rend.set_modelView(cams[33][0]); rend.render()
+    img = rend.output.copy()
+    if ref is None: ref = img
+    print("%-28s %.0f frames/s (%.1f us/frame) identical=%s" % (label, n / dt, 1e6 * dt / n, np.array_equal(img, ref)), flush=True)
+for b in (1, 2, 4, 8, 16):
+    lib.spv_set_tuning(ctx, 2, b); run("bands=%d" % b)
+lib.spv_set_tuning(ctx, 3, 1); run("direct host stores")
+lib.spv_set_tuning(ctx, 3, 0); lib.spv_set_tuning(ctx, 2, 4)
+# host-side cost alone
+t0 = time.perf_counter()
+for i in range(360): rend.set_modelView(cams[i][0])
+print("set_modelView alone: %.1f us" % ((time.perf_counter() - t0) / 360 * 1e6))
+t0 = time.perf_counter()
+for i in range(360): rend.render_device_only()
+rend.sync()
+print("device-only launches: %.1f us/frame" % ((time.perf_counter() - t0) / 360 * 1e6))
+t0 = time.perf_counter()
+n = 0
+for r in rend.render_sequence(cams[i][0] for i in range(360)): n += 1
+print("render_sequence: %.1f us/frame" % ((time.perf_counter() - t0) / 360 * 1e6))

@@ -57,12 +57,16 @@ SIGNATURES = {
     "spv_set_skipping": (C.c_int, [_CTX, C.c_int]),
     "spv_set_matrices": (C.c_int, [_CTX, _FP, _FP]),
     "spv_render_mip": (C.c_int, [_CTX, C.POINTER(MipParams)]),
+    "spv_render_mip_to_host": (C.c_int, [_CTX, C.POINTER(MipParams), C.c_int, C.c_int, C.POINTER(_FP)]),
     "spv_mip_finish": (C.c_int, [_CTX, C.POINTER(MipParams)]),
     "spv_render_iso": (C.c_int, [_CTX, C.POINTER(IsoParams)]),
     "spv_read": (C.c_int, [_CTX, C.c_int, _FP, C.c_size_t]),
     "spv_read_many": (C.c_int, [_CTX, _FP, _FP, _FP, _FP, _FP]),
     "spv_read_pinned": (C.c_int, [_CTX, C.c_int, C.POINTER(_FP)]),
     "spv_device_ptr": (C.c_int, [_CTX, C.c_int, C.POINTER(C.c_void_p)]),
+    "spv_select_slot": (C.c_int, [_CTX, C.c_int]),
+    "spv_read_pinned_async": (C.c_int, [_CTX, C.c_int]),
+    "spv_wait_slot": (C.c_int, [_CTX, C.c_int, C.POINTER(_FP)]),
     "spv_last_timing_ms": (C.c_int, [_CTX, _FP]),
     "spv_last_stats": (C.c_int, [_CTX, C.POINTER(C.c_ulonglong), C.c_int]),
     "spv_enable_stats": (C.c_int, [_CTX, C.c_int]),

@@ -33,12 +33,22 @@ struct spv_ctx {
   bool minmax_valid = false;
   // settings
   int linear = 1, sampler = SPV_SAMPLER_TMU, int_filter = 1, skipping = -1, stats_on = 0, tile_variant = 0, persistent = 0;
+  int bands = 2;  // default band count of spv_render_mip_to_host (measured best of 1/2/4/8/16, profiles/r01_exp_e2e.txt)
+  int direct_host = 0;  // spv_render_mip_to_host: the kernel stores straight into the pinned staging (tuning knob 3)
   unsigned *d_tile_counter = nullptr;
   unsigned char *d_tile_hit = nullptr;  // per 16x8 tile: holds an iso-surface pixel
   Camera cam;
   // result buffers: one allocation  [out | alpha | depth | occ | normals(3) | raw | tmp | tmp_vec(3)]
   float *dbuf = nullptr;
   float *hpin = nullptr;  // pinned staging for [out | alpha | depth | occ | normals(3)]
+  // two output slots for pipelined sequences (spv_select_slot): dbuf / hpin alias the selected one; slot 1 is
+  // allocated on first use.  Asynchronous reads run on copy_stream, ordered against the renders by events.
+  float *dbuf_s[2] = {nullptr, nullptr};
+  float *hpin_s[2] = {nullptr, nullptr};
+  int slot = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  bool copy_pending[2] = {false, false};
   int last_method = 0;    // 0 = mip, 1 = iso
   unsigned long long *d_stats = nullptr;
   unsigned long long h_stats[2] = {0, 0};
@@ -82,12 +92,19 @@ static int cufail(spv_ctx *c, cudaError_t e, const char *where) {
   } while (0)
 
 static void free_buffers(spv_ctx *c) {
-  if (c->dbuf) cudaFree(c->dbuf);
-  if (c->hpin) cudaFreeHost(c->hpin);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  for (int s = 0; s < 2; ++s) {
+    if (c->dbuf_s[s]) cudaFree(c->dbuf_s[s]);
+    if (c->hpin_s[s]) cudaFreeHost(c->hpin_s[s]);
+    c->dbuf_s[s] = nullptr;
+    c->hpin_s[s] = nullptr;
+    c->copy_pending[s] = false;
+  }
   if (c->d_tile_hit) cudaFree(c->d_tile_hit);
   c->d_tile_hit = nullptr;
   c->dbuf = nullptr;
   c->hpin = nullptr;
+  c->slot = 0;
 }
 static void free_volume(spv_ctx *c) {
   if (c->tex_lin) cudaDestroyTextureObject(c->tex_lin);
@@ -105,17 +122,25 @@ static void free_volume(spv_ctx *c) {
   c->dtype = -1;
 }
 
+static int alloc_slot(spv_ctx *ctx, int s) {
+  const size_t n = ctx->n();
+  CU(cudaMalloc(&ctx->dbuf_s[s], 12 * n * sizeof(float)));
+  CU(cudaMemsetAsync(ctx->dbuf_s[s], 0, 12 * n * sizeof(float), ctx->stream));
+  CU(cudaMallocHost(&ctx->hpin_s[s], 7 * n * sizeof(float)));
+  memset(ctx->hpin_s[s], 0, 7 * n * sizeof(float));
+  return 0;
+}
+
 static int alloc_buffers(spv_ctx *ctx, int w, int h) {
   if (w <= 0 || h <= 0) return fail(ctx, SPV_EINVAL, "spv_resize: width and height must be positive");
   free_buffers(ctx);
   ctx->width = w;
   ctx->height = h;
-  const size_t n = ctx->n();
-  CU(cudaMalloc(&ctx->dbuf, 12 * n * sizeof(float)));
-  CU(cudaMemsetAsync(ctx->dbuf, 0, 12 * n * sizeof(float), ctx->stream));
+  int rc = alloc_slot(ctx, 0);
+  if (rc) return rc;
+  ctx->dbuf = ctx->dbuf_s[0];
+  ctx->hpin = ctx->hpin_s[0];
   CU(cudaMalloc(&ctx->d_tile_hit, (size_t)((w + 15) / 16) * ((h + 7) / 8)));
-  CU(cudaMallocHost(&ctx->hpin, 7 * n * sizeof(float)));
-  memset(ctx->hpin, 0, 7 * n * sizeof(float));
   return 0;
 }
 
@@ -149,6 +174,11 @@ SPV_API int spv_create(int device, int width, int height, spv_ctx **out) {
   ctx->stream = ctx->own_stream;
   CC(cudaEventCreate(&ctx->ev0));
   CC(cudaEventCreate(&ctx->ev1));
+  CC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; ++s) {
+    CC(cudaEventCreateWithFlags(&ctx->ev_rendered[s], cudaEventDisableTiming));
+    CC(cudaEventCreateWithFlags(&ctx->ev_copied[s], cudaEventDisableTiming));
+  }
   CC(cudaMalloc(&ctx->d_minmax, 2 * sizeof(float)));
   CC(cudaMalloc(&ctx->d_stats, 2 * sizeof(unsigned long long)));
   CC(cudaMalloc(&ctx->d_tile_counter, sizeof(unsigned)));
@@ -174,6 +204,11 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
   if (ctx->d_tile_counter) cudaFree(ctx->d_tile_counter);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int s = 0; s < 2; ++s) {
+    if (ctx->ev_rendered[s]) cudaEventDestroy(ctx->ev_rendered[s]);
+    if (ctx->ev_copied[s]) cudaEventDestroy(ctx->ev_copied[s]);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return 0;
@@ -195,6 +230,7 @@ SPV_API int spv_set_stream(spv_ctx *ctx, void *cuda_stream) {
 SPV_API int spv_sync(spv_ctx *ctx) {
   BIND();
   CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->copy_stream));
   return 0;
 }
 
@@ -396,6 +432,8 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   if (!ctx) return SPV_EINVAL;
   if (knob == 0) ctx->tile_variant = value;
   else if (knob == 1) ctx->persistent = value != 0;
+  else if (knob == 2) ctx->bands = value < 1 ? 1 : (value > 64 ? 64 : value);
+  else if (knob == 3) ctx->direct_host = value != 0;
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
   return 0;
 }
@@ -427,8 +465,9 @@ static int end_render(spv_ctx *ctx) {
 
 static bool bad_float(float f) { return !(f == f); }
 
-SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p) {
-  BIND();
+// One max projection.  bands > 1 (fast kernel only): the frame is rendered as `bands` horizontal bands launched back to
+// back, and the rows of a finished band travel to the pinned staging on the copy stream while the next band renders.
+static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, bool to_host) {
   if (!p) return fail(ctx, SPV_EINVAL, "spv_render_mip: null params");
   if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_render_mip: no volume set");
   if (p->num_parts < 1 || p->current_part < 0 || p->max_steps / p->num_parts < 16)
@@ -456,10 +495,61 @@ SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p) {
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
   int rc = begin_render(ctx);
   if (rc) return rc;
-  CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, ctx->skipping > 0, ctx->slab, ctx->stats_on != 0, ctx->stream));
-  ctx->launches += 1;
+  const int s = ctx->slot;
+  if (to_host && ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // staging about to be rewritten
+  const int H = ctx->height;
+  const bool direct = to_host && ctx->direct_host && fast && p->num_parts == 1 && !raw_only;
+  if (direct) {  // zero-copy: the result planes are written over PCIe by the kernel's own 128-bit stores
+    a.out = ctx->hpin_s[s];
+    a.alpha = ctx->hpin_s[s] + ctx->n();
+    bands = 1;
+  }
+  if (!fast || bands < 1) bands = 1;
+  int rows = ((H + bands - 1) / bands + 15) / 16 * 16;  // band height: a multiple of every CTA tile height
+  if (rows < 16) rows = 16;
+  for (int y0 = 0; y0 < H; y0 += rows) {
+    const int y1 = y0 + rows < H ? y0 + rows : H;
+    a.y_begin = y0;
+    a.y_end = y1;
+    CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, ctx->skipping > 0, ctx->slab, ctx->stats_on != 0, ctx->stream));
+    ctx->launches += 1;
+    if (to_host && !direct) {
+      const size_t off = (size_t)y0 * ctx->width, cnt = (size_t)(y1 - y0) * ctx->width, n = ctx->n();
+      CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
+      CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
+      CU(cudaMemcpyAsync(ctx->hpin_s[s] + off, ctx->dbuf_s[s] + off, cnt * sizeof(float), cudaMemcpyDeviceToHost,
+                         ctx->copy_stream));
+      CU(cudaMemcpyAsync(ctx->hpin_s[s] + n + off, ctx->dbuf_s[s] + n + off, cnt * sizeof(float), cudaMemcpyDeviceToHost,
+                         ctx->copy_stream));
+    }
+  }
   ctx->last_method = 0;
-  return end_render(ctx);
+  rc = end_render(ctx);
+  if (rc) return rc;
+  if (to_host) {
+    CU(cudaEventRecord(ctx->ev_copied[s], direct ? ctx->stream : ctx->copy_stream));
+    ctx->copy_pending[s] = true;
+  }
+  return 0;
+}
+
+SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p) {
+  BIND();
+  return render_mip_impl(ctx, p, 1, false);
+}
+
+SPV_API int spv_render_mip_to_host(spv_ctx *ctx, const spv_mip_params *p, int bands, int wait, float **host) {
+  BIND();
+  if (p && (p->flags & SPV_MIP_RAW_ONLY)) return fail(ctx, SPV_EINVAL, "spv_render_mip_to_host: not for raw renders");
+  if (bands <= 0) bands = ctx->bands;
+  int rc = render_mip_impl(ctx, p, bands, true);
+  if (rc) return rc;
+  if (wait) {
+    CU(cudaEventSynchronize(ctx->ev_copied[ctx->slot]));
+    CU(cudaStreamSynchronize(ctx->stream));  // statistics / timing events of this frame
+  }
+  if (host) *host = ctx->hpin_s[ctx->slot];
+  return 0;
 }
 
 SPV_API int spv_mip_finish(spv_ctx *ctx, const spv_mip_params *p) {
@@ -562,9 +652,47 @@ SPV_API int spv_read_many(spv_ctx *ctx, float *out, float *alpha, float *depth, 
 SPV_API int spv_read_pinned(spv_ctx *ctx, int planes, float **host) {
   BIND();
   if (planes < 1 || planes > 7 || !host) return fail(ctx, SPV_EINVAL, "spv_read_pinned: planes must be 1..7");
+  if (ctx->copy_pending[ctx->slot]) CU(cudaEventSynchronize(ctx->ev_copied[ctx->slot]));  // same staging memory
   CU(cudaMemcpyAsync(ctx->hpin, ctx->dbuf, (size_t)planes * ctx->n() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   *host = ctx->hpin;
+  return 0;
+}
+
+SPV_API int spv_select_slot(spv_ctx *ctx, int slot) {
+  BIND();
+  if (slot != 0 && slot != 1) return fail(ctx, SPV_EINVAL, "spv_select_slot: slot must be 0 or 1");
+  if (!ctx->dbuf_s[slot]) {
+    int rc = alloc_slot(ctx, slot);
+    if (rc) return rc;
+  }
+  // renders into this slot must not overtake an asynchronous read of it that is still in flight
+  if (ctx->copy_pending[slot]) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
+  ctx->slot = slot;
+  ctx->dbuf = ctx->dbuf_s[slot];
+  ctx->hpin = ctx->hpin_s[slot];
+  return 0;
+}
+
+SPV_API int spv_read_pinned_async(spv_ctx *ctx, int planes) {
+  BIND();
+  if (planes < 1 || planes > 7) return fail(ctx, SPV_EINVAL, "spv_read_pinned_async: planes must be 1..7");
+  const int s = ctx->slot;
+  CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
+  CU(cudaMemcpyAsync(ctx->hpin_s[s], ctx->dbuf_s[s], (size_t)planes * ctx->n() * sizeof(float), cudaMemcpyDeviceToHost,
+                     ctx->copy_stream));
+  CU(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));
+  ctx->copy_pending[s] = true;
+  return 0;
+}
+
+SPV_API int spv_wait_slot(spv_ctx *ctx, int slot, float **host) {
+  BIND();
+  if ((slot != 0 && slot != 1) || !host) return fail(ctx, SPV_EINVAL, "spv_wait_slot: bad argument");
+  if (!ctx->hpin_s[slot]) return fail(ctx, SPV_ENODATA, "spv_wait_slot: slot was never used");
+  if (ctx->copy_pending[slot]) CU(cudaEventSynchronize(ctx->ev_copied[slot]));
+  *host = ctx->hpin_s[slot];
   return 0;
 }
 

@@ -15,6 +15,7 @@ struct MipArgs {
   int num_parts, current_part, max_steps, flags;
   int tile_variant;  // CTA shape of the fast kernel (tuning)
   int width, height;
+  int y_begin, y_end;  // pixel rows this launch renders (a band; y_begin is a multiple of 16), fast kernel only
   float *out, *alpha, *raw;
   unsigned long long *stats;  // [hit rays, texture samples issued] or nullptr
   unsigned *tile_counter;     // non-null: persistent CTAs pull tiles from this counter

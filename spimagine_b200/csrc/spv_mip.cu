@@ -322,7 +322,7 @@ template <int FMT, bool LINEAR, bool SKIP, bool SLAB, int TX, int TY, int MINB>
 __global__ void __launch_bounds__(32 * TX * TY, MINB) mip_fast_kernel(const MipArgs a) {
   __shared__ __align__(16) float s_out[TX * TY][32];
   __shared__ __align__(16) float s_alpha[TX * TY][32];
-  mip_fast_tile<FMT, LINEAR, SKIP, SLAB, TX, TY>(a, blockIdx.x, blockIdx.y, s_out, s_alpha);
+  mip_fast_tile<FMT, LINEAR, SKIP, SLAB, TX, TY>(a, blockIdx.x, blockIdx.y + a.y_begin / (4 * TY), s_out, s_alpha);
 }
 
 // Persistent grid: (SMs x resident CTAs) CTAs pull tiles from a counter, so rays that miss the box or leave it
@@ -333,7 +333,8 @@ __global__ void __launch_bounds__(32 * TX * TY, MINB) mip_fast_persistent_kernel
   __shared__ __align__(16) float s_out[TX * TY][32];
   __shared__ __align__(16) float s_alpha[TX * TY][32];
   __shared__ unsigned s_tile;
-  const unsigned tiles_x = (a.width + 8 * TX - 1) / (8 * TX), tiles_y = (a.height + 4 * TY - 1) / (4 * TY);
+  const unsigned tiles_x = (a.width + 8 * TX - 1) / (8 * TX);
+  const unsigned tiles_y = (a.y_end - a.y_begin + 4 * TY - 1) / (4 * TY), ty0 = a.y_begin / (4 * TY);
   const unsigned ntiles = tiles_x * tiles_y;
   for (;;) {
     if (threadIdx.x == 0) s_tile = atomicAdd(a.tile_counter, 1u);
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(32 * TX * TY, MINB) mip_fast_persistent_kernel
     const unsigned t = s_tile;
     __syncthreads();
     if (t >= ntiles) break;
-    mip_fast_tile<FMT, LINEAR, SKIP, SLAB, TX, TY>(a, t % tiles_x, t / tiles_x, s_out, s_alpha);
+    mip_fast_tile<FMT, LINEAR, SKIP, SLAB, TX, TY>(a, t % tiles_x, ty0 + t / tiles_x, s_out, s_alpha);
   }
 }
 
@@ -356,7 +357,7 @@ __global__ void mip_finish_kernel(const float *raw, float *out, int n, float min
 // -------------------------------------------------------------------------------------------------------------
 template <int FMT, bool LINEAR, bool SKIP, bool SLAB, int TX, int TY, int MINB>
 static void launch_fast_shape(const MipArgs &a, cudaStream_t st) {
-  dim3 grid((a.width + 8 * TX - 1) / (8 * TX), (a.height + 4 * TY - 1) / (4 * TY)), block(32 * TX * TY);
+  dim3 grid((a.width + 8 * TX - 1) / (8 * TX), (a.y_end - a.y_begin + 4 * TY - 1) / (4 * TY)), block(32 * TX * TY);
   if (a.tile_counter) {
     static int resident = 0;  // CTAs per SM x SMs for this instantiation (queried once)
     if (resident == 0) {

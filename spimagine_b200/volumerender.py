@@ -167,6 +167,7 @@ class VolumeRenderer(object):
     def reset_buffer(self, _realloc=True):
         if _realloc:
             self._check(self._lib.spv_resize(self._ctx, self.width, self.height))
+            self.__dict__.pop("_views", None)  # the pinned staging moved
         self.output = np.zeros((self.height, self.width), dtype=np.float32)
         self.output_alpha = np.zeros((self.height, self.width), dtype=np.float32)
         self.output_depth = np.zeros((self.height, self.width), dtype=np.float32)
@@ -289,7 +290,12 @@ class VolumeRenderer(object):
         if hasattr(self, "dataImg"):
             mScale = self._stack_scale_mat()
             invM = inv(np.dot(self.modelView, mScale))
-            invP = inv(self.projection)
+            cached = getattr(self, "_invP_of", None)
+            if cached is not None and cached[0] is self.projection and np.array_equal(cached[1], self.projection):
+                invP = cached[2]
+            else:  # same scipy.linalg.inv as the reference, evaluated once per distinct projection matrix
+                invP = inv(self.projection)
+                self._invP_of = (self.projection, np.array(self.projection, copy=True), invP)
             self._invM = np.ascontiguousarray(invM.flatten().astype(np.float32))
             self._invP = np.ascontiguousarray(invP.flatten().astype(np.float32))
             self._check(self._lib.spv_set_matrices(self._ctx, _lib.fp(self._invP), _lib.fp(self._invM)))
@@ -305,12 +311,23 @@ class VolumeRenderer(object):
     def _box(self):
         return (C.c_float * 6)(*[float(b) for b in self.boxBounds])
 
+    def _pinned_view(self, host, count):
+        """numpy view of `count` floats of pinned staging at `host` (cached: building one costs ~15 us)."""
+        key = (C.cast(host, C.c_void_p).value, count)
+        cache = self.__dict__.setdefault("_views", {})
+        v = cache.get(key)
+        if v is None:
+            if len(cache) > 8:
+                cache.clear()
+            v = cache[key] = np.ctypeslib.as_array(host, shape=(count,))
+        return v
+
     def _fetch(self, planes):
         """One device->host transfer of the leading result planes [out | alpha | depth | occ | normals]."""
         n = self.width * self.height
         host = _lib._FP()
         self._check(self._lib.spv_read_pinned(self._ctx, planes, C.byref(host)))
-        flat = np.ctypeslib.as_array(host, shape=(planes * n,))
+        flat = self._pinned_view(host, planes * n)
         if not self.pinned_outputs:
             flat = flat.copy()
         return flat, n
@@ -320,8 +337,13 @@ class VolumeRenderer(object):
             raise NotImplementedError("wrong dtype: %s", dtype)
         p = _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma),
                            float(self.alphaPow), int(numParts), int(currentPart), int(self.max_steps), 0)
-        self._check(self._lib.spv_render_mip(self._ctx, C.byref(p)))
-        flat, n = self._fetch(2)
+        # render + read-back in one call: finished bands of rows travel to pinned memory while the rest renders
+        host = _lib._FP()
+        self._check(self._lib.spv_render_mip_to_host(self._ctx, C.byref(p), 0, 1, C.byref(host)))
+        n = self.width * self.height
+        flat = self._pinned_view(host, 2 * n)
+        if not self.pinned_outputs:
+            flat = flat.copy()
         shape = (self.height, self.width)
         self.output = flat[:n].reshape(shape)
         self.output_alpha = flat[n:2 * n].reshape(shape)
@@ -375,6 +397,64 @@ class VolumeRenderer(object):
             self._render_isosurface()
         if method == "iso_surface_raw":  # addition: the iso_surface kernel alone (parity tests)
             self._render_isosurface(raw_only=True)
+
+    # ------------------------------------------------------------------ pipelined sequences (addition)
+    def render_sequence(self, modelViews, method="max_project", depth=2):
+        """Generator over the frames of a camera path (a spin, a keyframe sequence): for every modelView of the
+        iterable it yields `self` with output / output_alpha (and, for "iso_surface", output_depth /
+        output_occlusion / output_normals) holding that frame.  Unlike calling render() per frame -- which, like
+        the reference, blocks on the read-back of every frame (volumerender.py:388-390) -- frame i+1 is rendered
+        while frame i is still being copied to pinned host memory (two output slots, spv_select_slot /
+        spv_read_pinned_async / spv_wait_slot).  With pinned_outputs=True the yielded arrays are views of the
+        slot's staging memory and stay valid until the frame after next has been yielded; otherwise copies."""
+        if not hasattr(self, 'dataImg'):
+            print("no data provided, set_data(data) before")
+            return
+        if method not in ("max_project", "iso_surface"):
+            raise KeyError("method = '%s' not defined, valid: ['max_project', 'iso_surface']" % method)
+        planes = 2 if method == "max_project" else 7
+        pending = []  # slots in flight, oldest first
+        i = 0
+        try:
+            for M in modelViews:
+                slot = i & 1
+                self._check(self._lib.spv_select_slot(self._ctx, slot))
+                self.set_modelView(M)
+                if method == "max_project":
+                    p = _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma),
+                                       float(self.alphaPow), 1, 0, int(self.max_steps), 0)
+                    self._check(self._lib.spv_render_mip_to_host(self._ctx, C.byref(p), 1, 0, None))
+                else:
+                    p = _lib.IsoParams(self._box(), float(self.maxVal / 2), float(self.gamma), int(self.max_steps),
+                                       float(self.occ_strength), int(self.occ_radius), int(self.occ_n_points), 0)
+                    self._check(self._lib.spv_render_iso(self._ctx, C.byref(p)))
+                    self._check(self._lib.spv_read_pinned_async(self._ctx, planes))
+                pending.append(slot)
+                i += 1
+                if len(pending) == 2:
+                    self._adopt_slot(pending.pop(0), planes)
+                    yield self
+            while pending:
+                self._adopt_slot(pending.pop(0), planes)
+                yield self
+        finally:
+            self._lib.spv_sync(self._ctx)
+            self._lib.spv_select_slot(self._ctx, 0)
+
+    def _adopt_slot(self, slot, planes):
+        host = _lib._FP()
+        self._check(self._lib.spv_wait_slot(self._ctx, slot, C.byref(host)))
+        n = self.width * self.height
+        flat = self._pinned_view(host, planes * n)
+        if not self.pinned_outputs:
+            flat = flat.copy()
+        shape = (self.height, self.width)
+        self.output = flat[:n].reshape(shape)
+        self.output_alpha = flat[n:2 * n].reshape(shape)
+        if planes == 7:
+            self.output_depth = flat[2 * n:3 * n].reshape(shape)
+            self.output_occlusion = flat[3 * n:4 * n].reshape(shape)
+            self.output_normals = flat[4 * n:7 * n].reshape(shape + (3,))
 
     # ------------------------------------------------------------------ diagnostics (additions)
     def last_render_ms(self):

@@ -1,0 +1,174 @@
+"""GPU tests of the pipelined sequence API (render_sequence: two output slots, asynchronous read-back) and of
+size-independent properties at BASELINE.json's full bench size (512^3 uint16 -> 1024^2)."""
+import math
+
+import numpy as np
+import pytest
+
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _renderer(size, **kw):
+    from spimagine_b200 import VolumeRenderer
+    return VolumeRenderer(size, **kw)
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("n_frames", [1, 2, 5])
+def test_sequence_equals_frame_by_frame_mip(pinned, n_frames):
+    data = scenes.vol_g(48, np.uint16, seed=3)
+    cams = [scenes.gui_camera(0.3 + 0.4 * f, 3.5) for f in range(n_frames)]
+    rend = _renderer((160, 96), pinned_outputs=pinned)
+    rend.set_data(data)
+    rend.set_projection(cams[0][1])
+    rend.set_max_val(60000.)
+    want = []
+    for M, _ in cams:
+        rend.set_modelView(M)
+        rend.render()
+        want.append((rend.output.copy(), rend.output_alpha.copy()))
+    got = []
+    for r in rend.render_sequence([M for M, _ in cams]):
+        assert r is rend
+        got.append((r.output.copy(), r.output_alpha.copy()))
+    assert len(got) == n_frames
+    for (o, a), (wo, wa) in zip(got, want):
+        assert np.array_equal(o, wo) and np.array_equal(a, wa)
+    # the synchronous path still works afterwards and lands in slot 0
+    rend.set_modelView(cams[0][0])
+    rend.render()
+    assert np.array_equal(rend.output, want[0][0])
+    rend.close()
+
+
+def test_sequence_equals_frame_by_frame_iso():
+    data = scenes.iso_sphere(48)
+    cams = [scenes.gui_camera(0.2 * f, 4.5) for f in range(4)]
+    rend = _renderer((128, 128))
+    rend.set_data(data)
+    rend.set_projection(cams[0][1])
+    rend.set_max_val(20.)
+    want = []
+    for M, _ in cams:
+        rend.set_modelView(M)
+        rend.render(method="iso_surface")
+        want.append([x.copy() for x in (rend.output, rend.output_alpha, rend.output_depth, rend.output_normals,
+                                        rend.output_occlusion)])
+    k = 0
+    for r in rend.render_sequence([M for M, _ in cams], method="iso_surface"):
+        for g, w in zip((r.output, r.output_alpha, r.output_depth, r.output_normals, r.output_occlusion), want[k]):
+            assert np.array_equal(g, w)
+        k += 1
+    assert k == len(cams)
+    with pytest.raises(KeyError):
+        list(rend.render_sequence([cams[0][0]], method="nope"))
+    rend.close()
+
+
+def test_sequence_abandoned_midway_leaves_renderer_usable():
+    data = scenes.vol_g(32, np.uint16, seed=1)
+    cams = [scenes.gui_camera(0.1 * f, 3.5) for f in range(6)]
+    rend = _renderer((64, 64))
+    rend.set_data(data)
+    rend.set_projection(cams[0][1])
+    rend.set_max_val(60000.)
+    it = rend.render_sequence([M for M, _ in cams])
+    next(it)
+    it.close()  # generator closed with frames in flight
+    rend.set_modelView(cams[2][0])
+    rend.render()
+    a = rend.output.copy()
+    rend.resize((80, 48))
+    rend.set_modelView(cams[2][0])
+    rend.render()
+    assert rend.output.shape == (48, 80)
+    rend.resize((64, 64))
+    rend.set_modelView(cams[2][0])
+    rend.render()
+    assert np.array_equal(rend.output, a)
+    rend.close()
+
+
+# ----------------------------------------------------------------------------- full bench size (configs[1])
+@pytest.fixture(scope="module")
+def full_c2():
+    vol = scenes.vol_g(512, np.uint16, seed=0)
+    rend = _renderer((1024, 1024))
+    rend.set_data(vol)
+    rend.set_max_val(60000.)
+    M, P = scenes.gui_camera(2 * math.pi * 40 / 360, 4.0)
+    rend.set_projection(P)
+    rend.set_modelView(M)
+    yield vol, rend, M, P
+    rend.close()
+
+
+def test_full_size_properties(full_c2):
+    vol, rend, M, P = full_c2
+    assert rend.data_min_max == (float(vol.min()), float(vol.max()))
+    rend.render()
+    img, alpha = rend.output.copy(), rend.output_alpha.copy()
+    hit = alpha > 0  # uint16 path: alpha = tnear on hit, 0 on miss (camera outside the box)
+    assert 0.25 < hit.mean() < 0.45
+    assert np.all(img[~hit] == 0) and img.min() >= 0 and img.max() <= 1
+    # idempotence
+    rend.render()
+    assert np.array_equal(rend.output, img)
+    # window linearity for alpha_pow == 0: the raw maximum does not depend on the window
+    rend.render(maxVal=30000.)
+    assert np.allclose(np.minimum(2 * img, 1), rend.output, atol=2e-7)
+    rend.set_max_val(60000.)
+    # multi-pass rendering covers more sample positions: fmax-merged result never drops below a single part
+    rend.render(numParts=2, currentPart=0)
+    p0 = rend.output.copy()
+    rend.render(numParts=2, currentPart=1)
+    assert np.all(rend.output >= p0)
+    # empty-space skipping and the plain 3-D layout agree with the default path
+    rend.set_skipping(True)
+    rend.render()
+    assert np.array_equal(rend.output, img)
+    rend.set_skipping(None)
+
+
+def test_full_size_slabs_are_bit_exact(full_c2):
+    """encode -> split -> composite round trip at the full bench size: 4 z-slabs rendered separately and merged
+    with max equal the monolithic render bit for bit."""
+    import ctypes as C
+    from spimagine_b200 import _lib
+    from spimagine_b200.multigpu import SlabMaxProjector, partition_slabs, slab_with_halo
+    vol, rend, M, P = full_c2
+    rend.render()
+    want = rend.output.copy()
+    acc = None
+    for rank, (z0, z1) in enumerate(partition_slabs(512, 4)):
+        s = SlabMaxProjector((1024, 1024), rank=rank, world=4)
+        lo, hi = slab_with_halo(z0, z1, 512)
+        s.set_slab(vol[lo:hi], 512, z0, z1)
+        s.set_projection(P)
+        s.set_modelView(M)
+        p = _lib.MipParams(s._box(), 0., 60000., 1., 0., 1, 0, 200, _lib.MIP_RAW_ONLY)
+        s._check(s._lib.spv_render_mip(s._ctx, C.byref(p)))
+        raw = np.empty((1024, 1024), np.float32)
+        s._check(s._lib.spv_read(s._ctx, _lib.BUF_RAW, _lib.fp(raw), raw.size))
+        acc = raw if acc is None else np.maximum(acc, raw)
+        s.close()
+    got = np.where(acc < 0, 0, np.clip(acc / np.float32(60000.), 0, 1)).astype(np.float32)
+    assert np.array_equal(got, want)
+
+
+def test_full_size_against_oracle_rows(full_c2, oracle_mod):
+    """The oracle on every 64th row of the full-size frame (seconds on the CPU): 1e-3 of the range."""
+    vol, rend, M, P = full_c2
+    rend.render()
+    o = oracle_mod.OracleRenderer((1024, 1024), kind="port")
+    o.set_data(vol)
+    o.set_modelView(M)
+    o.set_projection(P)
+    o.lib.so_set_row_sampling(0, 64)
+    o.render(maxVal=60000.)
+    o.lib.so_set_row_sampling(0, 1)
+    rows = slice(0, 1024, 64)
+    assert np.abs(o.output[rows] - rend.output[rows]).max() < 1e-3
+    assert np.array_equal(o.output_alpha[rows], rend.output_alpha[rows])
