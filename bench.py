@@ -60,6 +60,12 @@ def parse():
                     help="sweep: BASELINE configs[1], frames sharded over the GPUs (default). slab: configs[3], one "
                          "--vol^3 uint16 volume split into z-slabs over the GPUs, sort-last max composite over NCCL")
     ap.add_argument("--skip", action="store_true", help="enable empty-space skipping on the min/max brick grid")
+    ap.add_argument("--slabs-per-rank", type=int, default=2,
+                    help="slab workload: slabs per GPU, dealt in serpentine order (front/back slabs pair up: balanced "
+                         "sample counts for any view); with --gpus 1 this is the single-GPU-brick baseline")
+    ap.add_argument("--composite", default="peer", choices=["peer", "nccl"],
+                    help="slab workload: peer = partials stored straight into the band owners' memory over NVLink "
+                         "(spv_render_mip_composite); nccl = all-reduce(MAX) of the raw plane")
     return ap.parse_args()
 
 
@@ -239,30 +245,38 @@ def run_slab(args, rank, local_rank, world):
     import scenes
     import ctypes as C
     from spimagine_b200 import _lib
-    from spimagine_b200.multigpu import SlabMaxProjector, partition_slabs, slab_with_halo
+    from spimagine_b200.multigpu import SlabMaxProjector, partition_slabs_multi, slab_with_halo
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     N, W = args.vol, args.img
-    z0, z1 = partition_slabs(N, world)[rank]
-    lo, hi = slab_with_halo(z0, z1, N)
-    t0 = time.perf_counter()
-    slab = vol_g_slab_device(N, lo, hi, 2, torch.device("cuda", local_rank))
-    torch.cuda.synchronize()
-    t_gen = time.perf_counter() - t0
+    K = max(1, args.slabs_per_rank)
+    mine = partition_slabs_multi(N, world, K)[rank]
     rend = SlabMaxProjector((W, W), rank=rank, world=world, device=local_rank, max_steps=MAX_STEPS,
-                            pinned_outputs=True)
+                            pinned_outputs=True, composite=args.composite, slabs_per_rank=K)
     if rend._stream is None:
         rend._stream = torch.cuda.Stream(device=local_rank)
         rend.use_stream(rend._stream.cuda_stream)
     torch.cuda.set_stream(rend._stream)
-    t0 = time.perf_counter()
-    rend.set_slab((np.uint16, N, N), N, z0, z1, device_ptr=slab.data_ptr())
-    rend.sync()
-    t_upload = time.perf_counter() - t0
-    del slab
-    torch.cuda.empty_cache()
+    t_gen = t_upload = 0.
+    slab_bytes = 0
+    for i, (z0, z1) in enumerate(mine):
+        lo, hi = slab_with_halo(z0, z1, N)
+        slab_bytes = max(slab_bytes, (hi - lo) * N * N * 4)
+        t0 = time.perf_counter()
+        slab = vol_g_slab_device(N, lo, hi, 2, torch.device("cuda", local_rank))
+        torch.cuda.synchronize()
+        t_gen += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        if i + 1 < len(mine):
+            rend.add_slab((np.uint16, N, N), N, z0, z1, device_ptr=slab.data_ptr())
+        else:
+            rend.set_slab((np.uint16, N, N), N, z0, z1, device_ptr=slab.data_ptr())
+        rend.sync()
+        t_upload += time.perf_counter() - t0
+        del slab
+        torch.cuda.empty_cache()
     rend.set_max_val(PEAK_VALUE)
     cams = sweep_cameras()
     rend.set_projection(cams[0][1])
@@ -273,10 +287,24 @@ def run_slab(args, rank, local_rank, world):
     lib, ctx = rend._lib, rend._ctx
     params = _lib.MipParams(rend._box(), 0., PEAK_VALUE, 1., 0., 1, 0, MAX_STEPS, _lib.MIP_RAW_ONLY)
     raw = rend._raw_tensor()
+    peer = args.composite == "peer"
+    if peer:
+        rend.connect()
+        params = _lib.MipParams(rend._box(), 0., PEAK_VALUE, 1., 0., 1, 0, MAX_STEPS, 0)
+    launches_per_step = (4 if peer else 2) + (K - 1)
+    raw_params = _lib.MipParams(rend._box(), 0., 0., 1., 0., 1, 0, MAX_STEPS, _lib.MIP_RAW_ONLY)
 
     def step(i):
         invP, invM = mats[(i * 7) % SWEEP]
+        for h in rend._parts:  # this rank's other slabs: raw partials, max-merged along the chain on the GPU
+            lib.spv_set_matrices(h._ctx, _lib.fp(invP), _lib.fp(invM))
+            lib.spv_render_mip(h._ctx, C.byref(raw_params))
         lib.spv_set_matrices(ctx, _lib.fp(invP), _lib.fp(invM))
+        if peer:  # render + push over NVLink, counters, owner's max + window + redistribution: 4 launches, no NCCL
+            rc = lib.spv_render_mip_composite(ctx, C.byref(params))
+            if rc:
+                _lib.check(rc, ctx)
+            return
         rc = lib.spv_render_mip(ctx, C.byref(params))
         if rc:
             _lib.check(rc, ctx)
@@ -290,13 +318,21 @@ def run_slab(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     rend.enable_stats(True)
+    for h in rend._parts:
+        h.enable_stats(True)
     step(0)
     hits0, issued0 = rend.last_stats()
+    for h in rend._parts:
+        issued0 += h.last_stats()[1]
+        h.enable_stats(False)
     rend.enable_stats(False)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = rend.launch_count()
+    def n_launches():
+        return rend.launch_count() + sum(h.launch_count() for h in rend._parts)
+
+    l0 = n_launches()
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -307,7 +343,9 @@ def run_slab(args, rank, local_rank, world):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = rend.launch_count() - l0 - 2 * args.warmup
+    launches = n_launches() - l0 - launches_per_step * args.warmup
+    if peer:
+        _lib.check(lib.spv_comp_check(ctx), ctx)
 
     # end to end: the public render() call, composited image read back to pinned host memory on every rank
     digest = hashlib.sha1()
@@ -339,16 +377,20 @@ def run_slab(args, rank, local_rank, world):
         peaks, peak_src = measured_peaks()
         alg_bytes = float(N) ** 3 * 2 + 2 * W * W * 4
         line = {
-            "metric": "MIP frames/s, %d^3 uint16 -> %d^2, sort-last z-slabs + NCCL max composite" % (N, W),
+            "metric": "MIP frames/s, %d^3 uint16 -> %d^2, sort-last z-slabs + %s max composite" % (
+                N, W, "peer-memory" if peer else "NCCL"),
             "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u16->f32", "data": "synthetic",
             "config": {"workload": "Vol-G(%d, uint16, seed 2) generated on device, max_project -> %dx%d, "
-                                   "max_steps=200, %d z-slab(s) with one halo slice, all-reduce(MAX) of the %d MiB raw "
-                                   "plane, then window" % (N, W, W, world, W * W * 4 >> 20),
-                       "l2": "each slab (%d MB as z-paired texels) exceeds the 126 MB L2" % (
-                           (hi - lo) * N * N * 4 >> 20),
-                       "parallelism": "sort-last, %d slab(s)" % world},
+                                   "max_steps=200, %d z-slab(s) with one halo slice (%d per GPU, serpentine), %s" % (
+                                       N, W, W, world * K, K,
+                                       "partials stored into the band owners' memory over NVLink, owner max + window, "
+                                       "redistribution (spv_render_mip_composite, no NCCL on the data path)" if peer else
+                                       "all-reduce(MAX) of the %d MiB raw plane over NCCL, then window" % (W * W * 4 >> 20)),
+                       "composite": args.composite,
+                       "l2": "each slab (%d MB as z-paired texels) exceeds the 126 MB L2" % (slab_bytes >> 20),
+                       "parallelism": "sort-last, %d slab(s) on %d GPU(s)" % (world * K, world)},
             "gsamples_per_s": fps * hits0 * SAMPLES_PER_RAY / 1e9,
             "hit_rays_per_frame": hits0, "issued_samples_per_frame_all_ranks": issued_total,
             "e2e": {"value": args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128,

@@ -56,6 +56,8 @@ SPV_API int spv_destroy(spv_ctx *ctx);
 SPV_API int spv_resize(spv_ctx *ctx, int width, int height);
 /* run on a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the context's own stream */
 SPV_API int spv_set_stream(spv_ctx *ctx, void *cuda_stream);
+/* run on the stream `other` currently uses (several slab contexts of one GPU render in order on one stream) */
+SPV_API int spv_share_stream(spv_ctx *ctx, spv_ctx *other);
 SPV_API int spv_sync(spv_ctx *ctx);
 
 /* ---- volume: set_shape / update_data, volumerender.py:260-294 (OCLImage.empty + write_array) ----
@@ -105,8 +107,9 @@ typedef struct {
   int flags;         /* SPV_MIP_* */
 } spv_mip_params;
 enum {
-  SPV_MIP_RAW_ONLY = 1  /* write only SPV_BUF_RAW (+ alpha): the per-slab partial of a sort-last render;
+  SPV_MIP_RAW_ONLY = 1, /* write only SPV_BUF_RAW (+ alpha): the per-slab partial of a sort-last render;
                            needs alpha_pow == 0 and num_parts == 1 */
+  SPV_MIP_PUSH = 2      /* internal to spv_render_mip_composite: raw partials go to the band owners' staging */
 };
 SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p);
 /* Render + read-back in one call (replaces run_kernel followed by the blocking buf.get() / buf_alpha.get() of
@@ -117,6 +120,23 @@ SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p);
 SPV_API int spv_render_mip_to_host(spv_ctx *ctx, const spv_mip_params *p, int bands, int wait, float **host);
 /* window + gamma of SPV_BUF_RAW into SPV_BUF_OUT after the cross-GPU max composite */
 SPV_API int spv_mip_finish(spv_ctx *ctx, const spv_mip_params *p);
+
+/* ---- sort-last composite over peer memory (new).  One context per GPU, one process per GPU (handles
+ *      exchanged by the host program) or several contexts in one process.  The image is cut into `world` bands of
+ *      rows, rank o owns band o.  spv_render_mip_composite = slab render whose raw partial maxima are stored
+ *      straight into the band owners' staging (NVLink peer stores), arrival counters, the owner's max + window over
+ *      its band stored into every rank's SPV_BUF_OUT, second counter round.  Enqueue-only: follow with spv_sync /
+ *      spv_read*; the result equals the single-GPU render bit for bit on every rank. ---- */
+SPV_API int spv_comp_init(spv_ctx *ctx, int rank, int world);              /* after spv_create / spv_resize */
+SPV_API int spv_comp_export(spv_ctx *ctx, void *handles, size_t nbytes);   /* 192 bytes: 3 cudaIpcMemHandle_t */
+SPV_API int spv_comp_import(spv_ctx *ctx, int peer, const void *handles, size_t nbytes); /* another process' export */
+SPV_API int spv_comp_import_local(spv_ctx *ctx, int peer, spv_ctx *peer_ctx);            /* same process */
+SPV_API int spv_render_mip_composite(spv_ctx *ctx, const spv_mip_params *p);
+SPV_API int spv_comp_check(spv_ctx *ctx);  /* synchronises; -110 if a wait on a peer timed out (4 s) */
+/* Several slabs on one GPU (each its own context, sharing one stream): raw / composite renders of this context
+ * max-merge the given device plane (another context's SPV_BUF_RAW, w*h floats, -1 = miss) into their partial before
+ * it is written or pushed.  NULL switches it off.  The caller orders the two renders (same stream). */
+SPV_API int spv_set_merge_raw(spv_ctx *ctx, const void *dev_raw_plane);
 
 /* ---- iso surface: _render_isosurface, volumerender.py:446-506
  *      iso_surface -> conv_vec_x/y(7) -> occlusion -> conv_x/y(5) -> shading ---- */

@@ -43,6 +43,7 @@ SIGNATURES = {
     "spv_destroy": (C.c_int, [_CTX]),
     "spv_resize": (C.c_int, [_CTX, C.c_int, C.c_int]),
     "spv_set_stream": (C.c_int, [_CTX, C.c_void_p]),
+    "spv_share_stream": (C.c_int, [_CTX, _CTX]),
     "spv_sync": (C.c_int, [_CTX]),
     "spv_set_volume": (C.c_int, [_CTX, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "spv_update_volume": (C.c_int, [_CTX, C.c_void_p]),
@@ -59,6 +60,13 @@ SIGNATURES = {
     "spv_render_mip": (C.c_int, [_CTX, C.POINTER(MipParams)]),
     "spv_render_mip_to_host": (C.c_int, [_CTX, C.POINTER(MipParams), C.c_int, C.c_int, C.POINTER(_FP)]),
     "spv_mip_finish": (C.c_int, [_CTX, C.POINTER(MipParams)]),
+    "spv_comp_init": (C.c_int, [_CTX, C.c_int, C.c_int]),
+    "spv_comp_export": (C.c_int, [_CTX, C.c_void_p, C.c_size_t]),
+    "spv_comp_import": (C.c_int, [_CTX, C.c_int, C.c_void_p, C.c_size_t]),
+    "spv_comp_import_local": (C.c_int, [_CTX, C.c_int, _CTX]),
+    "spv_render_mip_composite": (C.c_int, [_CTX, C.POINTER(MipParams)]),
+    "spv_comp_check": (C.c_int, [_CTX]),
+    "spv_set_merge_raw": (C.c_int, [_CTX, C.c_void_p]),
     "spv_render_iso": (C.c_int, [_CTX, C.POINTER(IsoParams)]),
     "spv_read": (C.c_int, [_CTX, C.c_int, _FP, C.c_size_t]),
     "spv_read_many": (C.c_int, [_CTX, _FP, _FP, _FP, _FP, _FP]),

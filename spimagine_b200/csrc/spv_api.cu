@@ -49,6 +49,17 @@ struct spv_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   bool copy_pending[2] = {false, false};
+  // sort-last composite over peer memory (spv_comp_*): I own image band comp_rank
+  int comp_rank = -1, comp_world = 0, comp_band_rows = 0;
+  float *comp_part = nullptr;      // [2 parities][world][band_rows * width]
+  unsigned *comp_flags = nullptr;  // [2 phases][MAX_WORLD] arrival counters, written by the peers
+  unsigned *comp_err = nullptr;
+  float *peer_part[MAX_WORLD] = {nullptr};
+  unsigned *peer_flags[MAX_WORLD] = {nullptr};
+  float *peer_out[MAX_WORLD] = {nullptr};
+  void *ipc_opened[MAX_WORLD][3] = {{nullptr}};
+  unsigned comp_frame = 0;
+  const float *merge_raw = nullptr;  // spv_set_merge_raw
   int last_method = 0;    // 0 = mip, 1 = iso
   unsigned long long *d_stats = nullptr;
   unsigned long long h_stats[2] = {0, 0};
@@ -91,7 +102,29 @@ static int cufail(spv_ctx *c, cudaError_t e, const char *where) {
     CU(cudaSetDevice(ctx->device));                           \
   } while (0)
 
+static void free_comp(spv_ctx *c) {
+  for (int r = 0; r < MAX_WORLD; ++r) {
+    for (int k = 0; k < 3; ++k) {
+      if (c->ipc_opened[r][k]) cudaIpcCloseMemHandle(c->ipc_opened[r][k]);
+      c->ipc_opened[r][k] = nullptr;
+    }
+    c->peer_part[r] = nullptr;
+    c->peer_flags[r] = nullptr;
+    c->peer_out[r] = nullptr;
+  }
+  if (c->comp_part) cudaFree(c->comp_part);
+  if (c->comp_flags) cudaFree(c->comp_flags);
+  if (c->comp_err) cudaFree(c->comp_err);
+  c->comp_part = nullptr;
+  c->comp_flags = nullptr;
+  c->comp_err = nullptr;
+  c->comp_rank = -1;
+  c->comp_world = 0;
+  c->comp_frame = 0;
+}
+
 static void free_buffers(spv_ctx *c) {
+  free_comp(c);  // the peers' pointers into these buffers die with them: re-run spv_comp_init + exchange after a resize
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   for (int s = 0; s < 2; ++s) {
     if (c->dbuf_s[s]) cudaFree(c->dbuf_s[s]);
@@ -224,6 +257,14 @@ SPV_API int spv_set_stream(spv_ctx *ctx, void *cuda_stream) {
   BIND();
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return 0;
+}
+
+SPV_API int spv_share_stream(spv_ctx *ctx, spv_ctx *other) {
+  BIND();
+  if (!other || other->device != ctx->device) return fail(ctx, SPV_EINVAL, "spv_share_stream: need a context on the same device");
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = other->stream;
   return 0;
 }
 
@@ -467,7 +508,7 @@ static bool bad_float(float f) { return !(f == f); }
 
 // One max projection.  bands > 1 (fast kernel only): the frame is rendered as `bands` horizontal bands launched back to
 // back, and the rows of a finished band travel to the pinned staging on the copy stream while the next band renders.
-static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, bool to_host) {
+static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, bool to_host, const PushArgs *push = nullptr) {
   if (!p) return fail(ctx, SPV_EINVAL, "spv_render_mip: null params");
   if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_render_mip: no volume set");
   if (p->num_parts < 1 || p->current_part < 0 || p->max_steps / p->num_parts < 16)
@@ -492,6 +533,14 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
   a.out = ctx->out(); a.alpha = ctx->alpha(); a.raw = ctx->raw();
   a.stats = ctx->stats_on ? ctx->d_stats : nullptr;
   a.tile_counter = ctx->persistent ? ctx->d_tile_counter : nullptr;
+  a.merge_raw = (a.flags & SPV_MIP_RAW_ONLY) || push ? ctx->merge_raw : nullptr;
+  memset(&a.push, 0, sizeof a.push);
+  if (push) {
+    a.push = *push;
+    a.flags |= SPV_MIP_RAW_ONLY | SPV_MIP_PUSH;
+  } else {
+    a.flags &= ~SPV_MIP_PUSH;
+  }
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
   int rc = begin_render(ctx);
   if (rc) return rc;
@@ -549,6 +598,134 @@ SPV_API int spv_render_mip_to_host(spv_ctx *ctx, const spv_mip_params *p, int ba
     CU(cudaStreamSynchronize(ctx->stream));  // statistics / timing events of this frame
   }
   if (host) *host = ctx->hpin_s[ctx->slot];
+  return 0;
+}
+
+// ---- sort-last composite over peer memory -------------------------------------------------------------------------
+SPV_API int spv_comp_init(spv_ctx *ctx, int rank, int world) {
+  BIND();
+  if (world < 1 || world > MAX_WORLD || rank < 0 || rank >= world)
+    return fail(ctx, SPV_EINVAL, "spv_comp_init: need 0 <= rank < world <= 16");
+  if (ctx->width % 4) return fail(ctx, SPV_EINVAL, "spv_comp_init: the image width must be a multiple of 4");
+  CU(cudaStreamSynchronize(ctx->stream));
+  free_comp(ctx);
+  if (ctx->slot != 0) return fail(ctx, SPV_EINVAL, "spv_comp_init: select output slot 0 first");
+  const int rows = ((ctx->height + world - 1) / world + 3) / 4 * 4;
+  const size_t band = (size_t)rows * ctx->width;
+  CU(cudaMalloc(&ctx->comp_part, 2 * (size_t)world * band * sizeof(float)));
+  CU(cudaMalloc(&ctx->comp_flags, 2 * MAX_WORLD * sizeof(unsigned)));
+  CU(cudaMalloc(&ctx->comp_err, sizeof(unsigned)));
+  CU(cudaMemsetAsync(ctx->comp_part, 0, 2 * (size_t)world * band * sizeof(float), ctx->stream));
+  CU(cudaMemsetAsync(ctx->comp_flags, 0, 2 * MAX_WORLD * sizeof(unsigned), ctx->stream));
+  CU(cudaMemsetAsync(ctx->comp_err, 0, sizeof(unsigned), ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->comp_rank = rank;
+  ctx->comp_world = world;
+  ctx->comp_band_rows = rows;
+  ctx->peer_part[rank] = ctx->comp_part;
+  ctx->peer_flags[rank] = ctx->comp_flags;
+  ctx->peer_out[rank] = ctx->dbuf_s[0];
+  return 0;
+}
+
+SPV_API int spv_comp_export(spv_ctx *ctx, void *handles, size_t nbytes) {
+  BIND();
+  if (ctx->comp_world < 1) return fail(ctx, SPV_ENODATA, "spv_comp_export: spv_comp_init first");
+  if (!handles || nbytes < 3 * sizeof(cudaIpcMemHandle_t)) return fail(ctx, SPV_EINVAL, "spv_comp_export: need 192 bytes");
+  cudaIpcMemHandle_t *h = (cudaIpcMemHandle_t *)handles;
+  CU(cudaIpcGetMemHandle(&h[0], ctx->comp_part));
+  CU(cudaIpcGetMemHandle(&h[1], ctx->comp_flags));
+  CU(cudaIpcGetMemHandle(&h[2], ctx->dbuf_s[0]));
+  return 0;
+}
+
+SPV_API int spv_comp_import(spv_ctx *ctx, int peer, const void *handles, size_t nbytes) {
+  BIND();
+  if (ctx->comp_world < 1) return fail(ctx, SPV_ENODATA, "spv_comp_import: spv_comp_init first");
+  if (peer < 0 || peer >= ctx->comp_world || peer == ctx->comp_rank) return fail(ctx, SPV_EINVAL, "spv_comp_import: bad peer rank");
+  if (!handles || nbytes < 3 * sizeof(cudaIpcMemHandle_t)) return fail(ctx, SPV_EINVAL, "spv_comp_import: need 192 bytes");
+  const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)handles;
+  for (int k = 0; k < 3; ++k) {
+    if (ctx->ipc_opened[peer][k]) cudaIpcCloseMemHandle(ctx->ipc_opened[peer][k]);
+    ctx->ipc_opened[peer][k] = nullptr;
+    CU(cudaIpcOpenMemHandle(&ctx->ipc_opened[peer][k], h[k], cudaIpcMemLazyEnablePeerAccess));
+  }
+  ctx->peer_part[peer] = (float *)ctx->ipc_opened[peer][0];
+  ctx->peer_flags[peer] = (unsigned *)ctx->ipc_opened[peer][1];
+  ctx->peer_out[peer] = (float *)ctx->ipc_opened[peer][2];
+  return 0;
+}
+
+SPV_API int spv_comp_import_local(spv_ctx *ctx, int peer, spv_ctx *other) {
+  BIND();
+  if (ctx->comp_world < 1 || !other || other->comp_world != ctx->comp_world || other->comp_rank != peer ||
+      peer == ctx->comp_rank || other->width != ctx->width || other->height != ctx->height)
+    return fail(ctx, SPV_EINVAL, "spv_comp_import_local: the peer context does not match (rank, world, image size)");
+  if (other->device != ctx->device) {
+    cudaError_t e = cudaDeviceEnablePeerAccess(other->device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+    else if (e != cudaSuccess) return cufail(ctx, e, "cudaDeviceEnablePeerAccess");
+  }
+  ctx->peer_part[peer] = other->comp_part;
+  ctx->peer_flags[peer] = other->comp_flags;
+  ctx->peer_out[peer] = other->dbuf_s[0];
+  return 0;
+}
+
+SPV_API int spv_render_mip_composite(spv_ctx *ctx, const spv_mip_params *p) {
+  BIND();
+  const int W = ctx->comp_world, R = ctx->comp_rank;
+  if (W < 1) return fail(ctx, SPV_ENODATA, "spv_render_mip_composite: spv_comp_init first");
+  for (int r = 0; r < W; ++r)
+    if (!ctx->peer_part[r]) return fail(ctx, SPV_ENODATA, "spv_render_mip_composite: a peer has not been imported");
+  if (ctx->slot != 0) return fail(ctx, SPV_EINVAL, "spv_render_mip_composite: select output slot 0 first");
+  if (p && (p->alpha_pow != 0.f || p->num_parts != 1))
+    return fail(ctx, SPV_EINVAL, "spv_render_mip_composite: needs alpha_pow == 0 and num_parts == 1 (attenuation is order dependent)");
+  const unsigned f = ++ctx->comp_frame;
+  const unsigned parity = f & 1u;
+  const size_t band = (size_t)ctx->comp_band_rows * ctx->width;
+  PushArgs push;
+  memset(&push, 0, sizeof push);
+  for (int r = 0; r < W; ++r) push.part[r] = ctx->peer_part[r];
+  push.band_rows = ctx->comp_band_rows;
+  push.src_off = (unsigned)((parity * (unsigned)W + (unsigned)R) * band);
+  int rc = render_mip_impl(ctx, p, 1, false, &push);
+  if (rc) return rc;
+  CU(launch_comp_sync(ctx->peer_flags, ctx->comp_flags, W, R, 0, f, ctx->comp_err, ctx->stream));
+  CompFinishArgs fa;
+  memset(&fa, 0, sizeof fa);
+  fa.part = ctx->comp_part + (size_t)parity * W * band;
+  for (int r = 0; r < W; ++r) fa.out[r] = ctx->peer_out[r];
+  fa.world = W;
+  fa.band_pixels = (unsigned)band;
+  fa.first_pixel = (unsigned)((size_t)R * band);
+  const size_t total = ctx->n();
+  fa.n_pixels = fa.first_pixel >= total ? 0u : (unsigned)((total - fa.first_pixel) < band ? (total - fa.first_pixel) : band);
+  fa.min_val = p->min_val; fa.max_val = p->max_val; fa.gamma = p->gamma;
+  CU(launch_comp_finish(fa, ctx->stream));
+  CU(launch_comp_sync(ctx->peer_flags, ctx->comp_flags, W, R, 1, f, ctx->comp_err, ctx->stream));
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));  // spv_last_timing_ms covers render + composite
+  ctx->launches += 3;
+  return 0;
+}
+
+SPV_API int spv_set_merge_raw(spv_ctx *ctx, const void *dev_raw_plane) {
+  if (!ctx) return SPV_EINVAL;
+  ctx->merge_raw = (const float *)dev_raw_plane;
+  return 0;
+}
+
+SPV_API int spv_comp_check(spv_ctx *ctx) {
+  BIND();
+  if (ctx->comp_world < 1) return fail(ctx, SPV_ENODATA, "spv_comp_check: spv_comp_init first");
+  unsigned e = 0;
+  CU(cudaMemcpyAsync(&e, ctx->comp_err, sizeof e, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (e) {
+    char b[128];
+    snprintf(b, sizeof b, "sort-last composite: timed out waiting for rank %u", e - 1);
+    return fail(ctx, -110, b);
+  }
   return 0;
 }
 

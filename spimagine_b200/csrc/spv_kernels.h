@@ -5,6 +5,15 @@
 
 namespace spv {
 
+// Sort-last composite over peer memory: rank r stores the raw partial maxima of the pixels in image band o straight
+// into the staging of band o's owner (its own memory when o == r, NVLink peer memory otherwise).
+constexpr int MAX_WORLD = 16;
+struct PushArgs {
+  float *part[MAX_WORLD];  // owner o's staging [parity][src rank][band_rows * width]
+  int band_rows;           // image rows per band (multiple of 4: a warp's 8x4 tile lies in one band)
+  unsigned src_off;        // (parity * world + my rank) * band_rows * width
+};
+
 struct MipArgs {
   Camera cam;
   Volume vol;
@@ -19,6 +28,8 @@ struct MipArgs {
   float *out, *alpha, *raw;
   unsigned long long *stats;  // [hit rays, texture samples issued] or nullptr
   unsigned *tile_counter;     // non-null: persistent CTAs pull tiles from this counter
+  const float *merge_raw;     // raw renders: a partial plane of another slab on this GPU to max-merge in, or nullptr
+  PushArgs push;              // used when flags has SPV_MIP_PUSH
 };
 
 struct IsoArgs {
@@ -45,6 +56,21 @@ cudaError_t launch_mip(const MipArgs &a, int dtype, bool linear, bool fast, bool
                        bool stats, cudaStream_t st);
 cudaError_t launch_mip_finish(const float *raw, float *out, int n, float minVal, float maxVal, float gamma,
                               cudaStream_t st);
+
+// peer composite (spv_comp.cu)
+struct CompFinishArgs {
+  const float *part;          // my band's staging of this parity: [world][band_pixels]
+  float *out[MAX_WORLD];      // every rank's SPV_BUF_OUT plane
+  int world;
+  unsigned band_pixels;       // band_rows * width (multiple of 4)
+  unsigned first_pixel;       // my band's first pixel in the image
+  unsigned n_pixels;          // pixels of my band that exist (the last band may be cut by the image edge)
+  float min_val, max_val, gamma;
+};
+cudaError_t launch_comp_sync(unsigned *const *peer_flags, const unsigned *flags, int world, int rank, int phase,
+                             unsigned value, unsigned *err, cudaStream_t st);
+cudaError_t launch_comp_finish(const CompFinishArgs &a, cudaStream_t st);
+struct PeerFlagPtrs { unsigned *p[MAX_WORLD]; };
 
 cudaError_t launch_sample_points(const Volume &V, int dtype, bool linear, bool exact, const float *pos, int n,
                                  float *out, cudaStream_t st);

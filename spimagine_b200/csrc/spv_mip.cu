@@ -284,14 +284,22 @@ __device__ __forceinline__ void mip_fast_tile(const MipArgs &a, unsigned bx, uns
   // ---- epilogue ----
   const float alphaVal = hit ? (isShort ? tnear : 1.f) : (isShort ? 0.f : -1.f);
   float outVal;
-  float *dst;
+  float *dst_rows;  // start of image row ty0 in the destination plane
   if (a.flags & SPV_MIP_RAW_ONLY) {
-    outVal = hit ? cur : -1.f;  // un-windowed partial maximum (>= 0), -1 marks a miss; composited across
-    dst = a.raw;                 // GPUs with max before spv_mip_finish
+    outVal = hit ? cur : -1.f;  // un-windowed partial maximum (>= 0), -1 marks a miss; composited across GPUs
+                                // with max before the window is applied
+    if (a.merge_raw && inb) outVal = fmaxf(outVal, __ldg(a.merge_raw + x + (size_t)Nx * y));  // another local slab
+    if (a.flags & SPV_MIP_PUSH) {  // straight into the staging of the band's owner (peer memory over NVLink)
+      const unsigned o = ty0 / (unsigned)a.push.band_rows;
+      dst_rows = a.push.part[o] + a.push.src_off + (size_t)(ty0 - o * (unsigned)a.push.band_rows) * Nx;
+    } else {
+      dst_rows = a.raw + (size_t)ty0 * Nx;
+    }
   } else {
     outVal = hit ? window_value(cur, a.min_val, a.max_val, a.gamma) : 0.f;
-    dst = a.out;
+    dst_rows = a.out + (size_t)ty0 * Nx;
   }
+  float *alpha_rows = a.alpha + (size_t)ty0 * Nx;
   const bool vec_ok = (Nx % 4 == 0) && (tx0 + 8 <= Nx) && (ty0 + 4 <= Ny) && a.current_part == 0;
   if (vec_ok) {
     s_out[warp][ly * 8 + lx] = outVal;
@@ -301,18 +309,17 @@ __device__ __forceinline__ void mip_fast_tile(const MipArgs &a, unsigned bx, uns
     if (lane < 16) {
       const int q = lane & 7, row = q >> 1, half = q & 1;
       const float *src = (lane < 8 ? s_out[warp] : s_alpha[warp]) + row * 8 + half * 4;
-      float *base = lane < 8 ? dst : a.alpha;
-      *reinterpret_cast<float4 *>(base + (size_t)(ty0 + row) * Nx + tx0 + half * 4) =
-          *reinterpret_cast<const float4 *>(src);
+      float *base = lane < 8 ? dst_rows : alpha_rows;
+      *reinterpret_cast<float4 *>(base + (size_t)row * Nx + tx0 + half * 4) = *reinterpret_cast<const float4 *>(src);
     }
   } else if (inb) {
-    const size_t p = x + (size_t)Nx * y;
+    const size_t p = x + (size_t)Nx * ly;
     if (a.current_part == 0) {
-      dst[p] = outVal;
-      a.alpha[p] = alphaVal;
+      dst_rows[p] = outVal;
+      alpha_rows[p] = alphaVal;
     } else {  // multi-pass rendering: merge into what earlier parts left (volume_kernel.cl:172-182)
-      dst[p] = fmaxf(outVal, dst[p]);
-      a.alpha[p] = fmaxf(alphaVal, a.alpha[p]);
+      dst_rows[p] = fmaxf(outVal, dst_rows[p]);
+      alpha_rows[p] = fmaxf(alphaVal, alpha_rows[p]);
     }
   }
 }

@@ -35,6 +35,19 @@ def partition_slabs(nz, world):
     return out
 
 
+def partition_slabs_multi(nz, world, k):
+    """world * k contiguous slabs dealt to the ranks in serpentine order: rank r gets slabs r, 2*world-1-r,
+    2*world+r, ...  Front and back slabs pair up, so the per-rank sample counts stay balanced whatever the view
+    direction (a perspective camera puts up to 3x more samples into the slabs nearest to it).
+    -> list over ranks of lists of (z0, z1)."""
+    parts = partition_slabs(nz, world * k)
+    out = [[] for _ in range(world)]
+    for i, p in enumerate(parts):
+        rnd, j = divmod(i, world)
+        out[j if rnd % 2 == 0 else world - 1 - j].append(p)
+    return out
+
+
 def slab_with_halo(z0, z1, nz):
     """Slices a rank must hold to evaluate the samples it owns: one halo slice either side."""
     return max(z0 - 1, 0), min(z1 + 1, nz)
@@ -69,12 +82,24 @@ class SlabMaxProjector(VolumeRenderer):
     takes the slab directly.  `render()` leaves the composited image in `output` on every rank.
     """
 
-    def __init__(self, size=None, interpolation='linear', group=None, rank=None, world=None, **kw):
+    def __init__(self, size=None, interpolation='linear', group=None, rank=None, world=None, composite="nccl",
+                 slabs_per_rank=1, **kw):
+        """composite = "nccl": all-reduce(MAX) of the raw plane (torch.distributed / NCCL), then window;
+        "peer": the render kernel stores its partials straight into the band owners' memory over NVLink and the
+        owners window + redistribute (spv_render_mip_composite) -- call connect() (one process per GPU) or
+        connect_local([...]) (several renderers in one process) once after construction / resize."""
         import torch
         import torch.distributed as dist
         self._torch = torch
         self._dist = dist
         self.group = group
+        if composite not in ("nccl", "peer"):
+            raise KeyError("composite = '%s' not defined, valid: ['nccl', 'peer']" % composite)
+        self.composite = composite
+        self._connected = False
+        self.slabs_per_rank = int(slabs_per_rank)
+        self._parts = []  # helper renderers holding this rank's other slabs (slabs_per_rank > 1)
+        self._ctor = (interpolation, dict(kw))
         if rank is None or world is None:
             if dist.is_available() and dist.is_initialized():
                 rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -92,12 +117,61 @@ class SlabMaxProjector(VolumeRenderer):
         if not autoConvert and not data.dtype in self.dtypes:
             raise NotImplementedError("data type should be either %s not %s" % (self.dtypes, data.dtype))
         nz = data.shape[0]
-        z0, z1 = partition_slabs(nz, self.world)[self.rank]
-        lo, hi = slab_with_halo(z0, z1, nz)
-        slab = np.asarray(data[lo:hi])
-        if slab.dtype.type not in self.dtypes:
-            slab = slab.astype(self.dtype, copy=False)
-        self.set_slab(slab, nz, z0, z1)
+        mine = partition_slabs_multi(nz, self.world, self.slabs_per_rank)[self.rank]
+        self.clear_parts()
+        for i, (z0, z1) in enumerate(mine):
+            lo, hi = slab_with_halo(z0, z1, nz)
+            slab = np.asarray(data[lo:hi])
+            if slab.dtype.type not in self.dtypes:
+                slab = slab.astype(self.dtype, copy=False)
+            if i + 1 < len(mine):
+                self.add_slab(slab, nz, z0, z1)
+            else:
+                self.set_slab(slab, nz, z0, z1)
+
+    # ---- several slabs per rank: helper contexts on the same stream, chained through spv_set_merge_raw ----
+    def clear_parts(self):
+        for h in self._parts:
+            h.close()
+        self._parts = []
+        self._check(self._lib.spv_set_merge_raw(self._ctx, None))
+
+    def add_slab(self, slab, gnz, z0, z1, device_ptr=None):
+        """One more slab for this rank to render besides the one given to set_slab()."""
+        interpolation, kw = self._ctor
+        h = SlabMaxProjector((self.width, self.height), interpolation, rank=self.rank, world=self.world,
+                             composite="nccl", **kw)
+        h.set_layout(getattr(self, "layout", "zpair"))
+        h._check(h._lib.spv_share_stream(h._ctx, self._ctx))
+        h.set_slab(slab, gnz, z0, z1, device_ptr=device_ptr)
+        prev = self._parts[-1] if self._parts else None
+        if prev is not None:
+            h._check(h._lib.spv_set_merge_raw(h._ctx, prev._raw_ptr()))
+        self._parts.append(h)
+        self._check(self._lib.spv_set_merge_raw(self._ctx, h._raw_ptr()))
+
+    def _raw_ptr(self):
+        p = C.c_void_p()
+        self._check(self._lib.spv_device_ptr(self._ctx, _lib.BUF_RAW, C.byref(p)))
+        return p
+
+    def _render_parts(self):
+        """Raw partials of the helper slabs, in chain order, on the shared stream."""
+        for h in self._parts:
+            h._check(h._lib.spv_set_matrices(h._ctx, _lib.fp(self._invP), _lib.fp(self._invM)))
+            p = _lib.MipParams(self._box(), 0., 0., 1., 0., 1, 0, int(self.max_steps), _lib.MIP_RAW_ONLY)
+            h._check(h._lib.spv_render_mip(h._ctx, C.byref(p)))
+
+    def use_stream(self, cuda_stream=None):
+        super(SlabMaxProjector, self).use_stream(cuda_stream)
+        for h in getattr(self, "_parts", []):
+            h._check(h._lib.spv_share_stream(h._ctx, self._ctx))
+
+    def close(self):
+        for h in getattr(self, "_parts", []):
+            h.close()
+        self._parts = []
+        super(SlabMaxProjector, self).close()
 
     def set_slab(self, slab, gnz, z0, z1, device_ptr=None):
         """slab: ndarray holding global slices [max(z0-1,0), min(z1+1,gnz)); or pass device_ptr (int) to a
@@ -122,6 +196,58 @@ class SlabMaxProjector(VolumeRenderer):
         self._need_alloc = True
         self.update_matrices()
 
+    # ---- peer-memory composite ----
+    def connect(self):
+        """Exchange the IPC handles of the composite staging with every other rank of the process group."""
+        self._check(self._lib.spv_comp_init(self._ctx, self.rank, self.world))
+        if self.world > 1:
+            buf = C.create_string_buffer(192)
+            self._check(self._lib.spv_comp_export(self._ctx, buf, 192))
+            handles = [None] * self.world
+            self._dist.all_gather_object(handles, bytes(buf.raw), group=self.group)
+            for r, h in enumerate(handles):
+                if r != self.rank:
+                    self._check(self._lib.spv_comp_import(self._ctx, r, h, len(h)))
+            self._dist.barrier(group=self.group)
+        self._connected = True
+
+    @staticmethod
+    def connect_local(renderers):
+        """Several SlabMaxProjector(composite="peer") objects living in ONE process (one per rank, on one or more
+        GPUs): wire their staging buffers together directly."""
+        for r in renderers:
+            r._check(r._lib.spv_comp_init(r._ctx, r.rank, r.world))
+        for a in renderers:
+            for b in renderers:
+                if a is not b:
+                    a._check(a._lib.spv_comp_import_local(a._ctx, b.rank, b._ctx))
+            a._connected = True
+
+    def enqueue_composite(self):
+        """Enqueue one composited max projection (no host synchronisation): peers must enqueue theirs as well."""
+        if self.alphaPow != 0:
+            raise NotImplementedError("sort-last compositing needs alpha_pow == 0")
+        if not self._connected:
+            raise RuntimeError("SlabMaxProjector(composite='peer'): call connect() / connect_local() first")
+        self._render_parts()
+        p = _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma), 0.,
+                           1, 0, int(self.max_steps), 0)
+        self._check(self._lib.spv_render_mip_composite(self._ctx, C.byref(p)))
+
+    def collect(self):
+        """Wait for the enqueued composite and read output / output_alpha back."""
+        self._check(self._lib.spv_comp_check(self._ctx))
+        flat, n = self._fetch(2)
+        shape = (self.height, self.width)
+        self.output = flat[:n].reshape(shape)
+        self.output_alpha = flat[n:2 * n].reshape(shape)
+
+    def resize(self, size):
+        super(SlabMaxProjector, self).resize(size)
+        self._connected = False  # the staging moved: connect() again
+        if getattr(self, "_parts", None):
+            raise NotImplementedError("resize with several slabs per rank: set the data again")
+
     def _raw_tensor(self):
         p = C.c_void_p()
         self._check(self._lib.spv_device_ptr(self._ctx, _lib.BUF_RAW, C.byref(p)))
@@ -132,9 +258,14 @@ class SlabMaxProjector(VolumeRenderer):
         if self.alphaPow != 0 or numParts != 1:
             raise NotImplementedError("sort-last compositing needs alpha_pow == 0 and numParts == 1 "
                                       "(front-to-back attenuation is order dependent)")
+        if self.composite == "peer":
+            self.enqueue_composite()
+            self.collect()
+            return
         p = _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma), 0.,
                            1, 0, int(self.max_steps), _lib.MIP_RAW_ONLY)
         torch = self._torch
+        self._render_parts()
         self._check(self._lib.spv_render_mip(self._ctx, C.byref(p)))
         if self.world > 1 and self._dist.is_initialized():
             with torch.cuda.stream(self._stream):

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# the peer-composite tests run several contexts (two streams each) with spin-waiting kernels on ONE device: give
+# every stream its own hardware queue so that a waiting kernel cannot sit in front of the kernel it waits for
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:

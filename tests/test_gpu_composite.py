@@ -1,0 +1,96 @@
+"""GPU tests of the sort-last composite over peer memory (spv_render_mip_composite): `world` slab contexts in ONE
+process on one device stand in for the ranks -- the same kernels, counters and staging layout that run one
+process per GPU over NVLink (bench.py --workload slab --composite peer).  The composited image on EVERY rank must
+equal the monolithic render bit for bit."""
+import numpy as np
+import pytest
+
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _mono(data, size, M, P, peak, gamma=1.):
+    from spimagine_b200 import VolumeRenderer
+    r = VolumeRenderer(size)
+    r.set_data(data)
+    r.set_modelView(M)
+    r.set_projection(P)
+    r.render(maxVal=peak, gamma=gamma)
+    out = (r.output.copy(), r.output_alpha.copy())
+    r.close()
+    return out
+
+
+def _ranks(data, size, world, **kw):
+    from spimagine_b200.multigpu import SlabMaxProjector
+    rs = []
+    for rank in range(world):
+        s = SlabMaxProjector(size, rank=rank, world=world, composite="peer", **kw)
+        s.set_data(data)  # uploads this rank's slab + halo only
+        rs.append(s)
+    SlabMaxProjector.connect_local(rs)
+    return rs
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("dtype,peak", [(np.uint16, 60000.), (np.float32, 1.)])
+def test_peer_composite_is_bit_exact_on_every_rank(world, dtype, peak):
+    data = scenes.vol_g(0, dtype, seed=9, shape=(61, 70, 83))
+    size = (136, 104)  # 104 rows: bands of 16/20/24/28/52... rows, some cut by the image edge
+    rs = _ranks(data, size, world)
+    for frame, (theta, gamma) in enumerate([(0.9, 1.), (2.1, 1.), (3.3, .7), (4.0, 1.)]):  # > 2 frames: both parities reused
+        M, P = scenes.gui_camera(theta, 2.7)
+        want, want_alpha = _mono(data, size, M, P, peak, gamma)
+        for s in rs:
+            s.set_projection(P)
+            s.set_modelView(M)
+            s.set_max_val(peak)
+            s.set_gamma(gamma)
+            s.enqueue_composite()  # nobody blocks before every rank has enqueued
+        for s in rs:
+            s.collect()
+            assert np.array_equal(s.output, want), "world %d rank %d frame %d" % (world, s.rank, frame)
+            assert np.array_equal(s.output_alpha, want_alpha)
+    for s in rs:
+        s.close()
+
+
+@pytest.mark.parametrize("world,k", [(1, 4), (2, 2), (4, 2), (3, 3)])
+def test_several_slabs_per_rank_are_bit_exact(world, k):
+    """Serpentine slab assignment (rank r renders slabs r, 2*world-1-r, ...): the helper slabs' partials are
+    max-merged on the GPU before the push; the composite still equals the monolithic render bit for bit."""
+    data = scenes.vol_g(0, np.uint16, seed=5, shape=(61, 70, 83))
+    size = (136, 104)
+    rs = _ranks(data, size, world, slabs_per_rank=k)
+    assert all(len(s._parts) == k - 1 for s in rs)
+    for theta in (0.0, 1.3, 2.9):
+        M, P = scenes.gui_camera(theta, 2.7)
+        want, want_alpha = _mono(data, size, M, P, 60000.)
+        for s in rs:
+            s.set_projection(P)
+            s.set_modelView(M)
+            s.set_max_val(60000.)
+            s.enqueue_composite()
+        for s in rs:
+            s.collect()
+            assert np.array_equal(s.output, want) and np.array_equal(s.output_alpha, want_alpha)
+    for s in rs:
+        s.close()
+
+
+def test_peer_composite_needs_connect_and_reports_a_missing_peer():
+    from spimagine_b200 import _lib
+    from spimagine_b200.multigpu import SlabMaxProjector
+    data = scenes.vol_g(0, np.uint16, seed=2, shape=(20, 24, 28))
+    s = SlabMaxProjector((64, 32), rank=0, world=2, composite="peer")
+    s.set_data(data)
+    with pytest.raises(RuntimeError):
+        s.render()
+    s._check(s._lib.spv_comp_init(s._ctx, 0, 2))
+    s._connected = True
+    with pytest.raises(_lib.SpvError):  # rank 1 was never imported
+        s.render()
+    with pytest.raises(KeyError):
+        SlabMaxProjector((64, 32), rank=0, world=2, composite="nope")
+    s.close()

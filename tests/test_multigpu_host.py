@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 import scenes
-from spimagine_b200.multigpu import composite_max, frames_for_rank, partition_slabs, slab_with_halo
+from spimagine_b200.multigpu import (composite_max, frames_for_rank, partition_slabs, partition_slabs_multi,
+                                     slab_with_halo)
 
 
 def test_partition_slabs_covers_everything_once():
@@ -23,6 +24,19 @@ def test_partition_slabs_covers_everything_once():
     assert slab_with_halo(0, 10, 40) == (0, 11)
     assert slab_with_halo(10, 20, 40) == (9, 21)
     assert slab_with_halo(30, 40, 40) == (29, 40)
+
+
+def test_serpentine_slab_assignment():
+    for nz, world, k in ((2048, 8, 2), (61, 3, 3), (64, 1, 4), (37, 4, 1)):
+        per_rank = partition_slabs_multi(nz, world, k)
+        assert len(per_rank) == world and all(len(p) == k for p in per_rank)
+        flat = sorted(sum(per_rank, []))
+        assert flat == partition_slabs(nz, world * k)  # every slice exactly once
+    # front and back slabs pair up: rank r gets slab r and slab 2*world-1-r
+    parts = partition_slabs(2048, 16)
+    per_rank = partition_slabs_multi(2048, 8, 2)
+    for r in range(8):
+        assert per_rank[r] == [parts[r], parts[15 - r]]
 
 
 def test_frame_sharding():
