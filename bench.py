@@ -62,7 +62,10 @@ def parse():
     ap.add_argument("--skip", action="store_true", help="enable empty-space skipping on the min/max brick grid")
     ap.add_argument("--slabs-per-rank", type=int, default=2,
                     help="slab workload: slabs per GPU, dealt in serpentine order (front/back slabs pair up: balanced "
-                         "sample counts for any view); with --gpus 1 this is the single-GPU-brick baseline")
+                         "sample counts for any view), at most 4, all marched by one kernel launch")
+    ap.add_argument("--bricks", type=int, default=0,
+                    help="slab workload, --gpus 1 only: the single-GPU-brick baseline -- the volume as this many z-slabs, "
+                         "each rendered by its own launch one after the other, max-merged, then windowed")
     ap.add_argument("--composite", default="peer", choices=["peer", "nccl"],
                     help="slab workload: peer = partials stored straight into the band owners' memory over NVLink "
                          "(spv_render_mip_composite); nccl = all-reduce(MAX) of the raw plane")
@@ -236,6 +239,82 @@ def vol_g_slab_device(N, z_lo, z_hi, seed, device):
     return out
 
 
+def run_bricks(args):
+    """The single-GPU-brick baseline of BASELINE configs[3]: the same slab kernels on ONE GPU, the volume cut into
+    --bricks z-slabs, each rendered by its own launch one after the other (what a single GPU does when the volume
+    has to be processed brick by brick), the raw partials max-merged (torch.maximum: plumbing), then windowed."""
+    import hashlib
+    import torch
+    import ctypes as C
+    from spimagine_b200 import _lib
+    from spimagine_b200.multigpu import SlabMaxProjector, partition_slabs, slab_with_halo
+
+    torch.cuda.set_device(0)
+    N, W, B = args.vol, args.img, args.bricks
+    stream = torch.cuda.Stream(device=0)
+    torch.cuda.set_stream(stream)
+    parts = []
+    for i, (z0, z1) in enumerate(partition_slabs(N, B)):
+        lo, hi = slab_with_halo(z0, z1, N)
+        slab = vol_g_slab_device(N, lo, hi, 2, torch.device("cuda", 0))
+        r = SlabMaxProjector((W, W), rank=i, world=B, device=0, max_steps=MAX_STEPS, pinned_outputs=True)
+        r.use_stream(stream.cuda_stream)
+        r.set_slab((np.uint16, N, N), N, z0, z1, device_ptr=slab.data_ptr())
+        r.sync()
+        del slab
+        torch.cuda.empty_cache()
+        parts.append(r)
+    cams = sweep_cameras()
+    last = parts[-1]
+    last.set_max_val(PEAK_VALUE)
+    last.set_projection(cams[0][1])
+    mats = []
+    for M, P in cams:
+        last.set_modelView(M)
+        mats.append((last._invP.copy(), last._invM.copy()))
+    raws = [r._raw_tensor() for r in parts]
+    raw_params = _lib.MipParams(last._box(), 0., PEAK_VALUE, 1., 0., 1, 0, MAX_STEPS, _lib.MIP_RAW_ONLY)
+    lib = last._lib
+
+    def step(i):
+        invP, invM = mats[(i * 7) % SWEEP]
+        for r in parts:
+            lib.spv_set_matrices(r._ctx, _lib.fp(invP), _lib.fp(invM))
+            rc = lib.spv_render_mip(r._ctx, C.byref(raw_params))
+            if rc:
+                _lib.check(rc, r._ctx)
+        for t in raws[:-1]:
+            torch.maximum(raws[-1], t, out=raws[-1])
+        lib.spv_mip_finish(last._ctx, C.byref(raw_params))
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    digest = hashlib.sha1()
+    for i in range(min(8, args.steps)):
+        step(i)
+        out = np.empty((W, W), np.float32)
+        _lib.check(lib.spv_read(last._ctx, _lib.BUF_OUT, _lib.fp(out), out.size), last._ctx)
+        digest.update(out.tobytes())
+    print(json.dumps({
+        "metric": "MIP frames/s, %d^3 uint16 -> %d^2, single-GPU-brick baseline" % (N, W),
+        "value": args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u16->f32", "data": "synthetic",
+        "config": {"workload": "Vol-G(%d, uint16, seed 2) generated on device, max_project -> %dx%d, max_steps=200, "
+                               "%d z-slabs rendered one after the other on one GPU, max-merged, windowed" % (N, W, W, B)},
+        "gpu_launches": args.steps * (B + 1), "image_sha1_first8": digest.hexdigest()}))
+    for r in parts:
+        r.close()
+
+
 def run_slab(args, rank, local_rank, world):
     """BASELINE configs[3]: --vol^3 uint16 split into `world` z-slabs, every frame = raw slab render on each GPU,
     all-reduce(MAX) over NCCL, window.  Strong scaling: the total work per frame is fixed."""
@@ -291,14 +370,10 @@ def run_slab(args, rank, local_rank, world):
     if peer:
         rend.connect()
         params = _lib.MipParams(rend._box(), 0., PEAK_VALUE, 1., 0., 1, 0, MAX_STEPS, 0)
-    launches_per_step = (4 if peer else 2) + (K - 1)
-    raw_params = _lib.MipParams(rend._box(), 0., 0., 1., 0., 1, 0, MAX_STEPS, _lib.MIP_RAW_ONLY)
+    launches_per_step = 4 if peer else 2
 
     def step(i):
         invP, invM = mats[(i * 7) % SWEEP]
-        for h in rend._parts:  # this rank's other slabs: raw partials, max-merged along the chain on the GPU
-            lib.spv_set_matrices(h._ctx, _lib.fp(invP), _lib.fp(invM))
-            lib.spv_render_mip(h._ctx, C.byref(raw_params))
         lib.spv_set_matrices(ctx, _lib.fp(invP), _lib.fp(invM))
         if peer:  # render + push over NVLink, counters, owner's max + window + redistribution: 4 launches, no NCCL
             rc = lib.spv_render_mip_composite(ctx, C.byref(params))
@@ -318,19 +393,14 @@ def run_slab(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     rend.enable_stats(True)
-    for h in rend._parts:
-        h.enable_stats(True)
     step(0)
     hits0, issued0 = rend.last_stats()
-    for h in rend._parts:
-        issued0 += h.last_stats()[1]
-        h.enable_stats(False)
     rend.enable_stats(False)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     def n_launches():
-        return rend.launch_count() + sum(h.launch_count() for h in rend._parts)
+        return rend.launch_count()
 
     l0 = n_launches()
     for i in range(args.warmup):
@@ -347,7 +417,10 @@ def run_slab(args, rank, local_rank, world):
     if peer:
         _lib.check(lib.spv_comp_check(ctx), ctx)
 
-    # end to end: the public render() call, composited image read back to pinned host memory on every rank
+    # end to end: the public render() call; the composited image is complete on every GPU and read back to pinned
+    # host memory on the display rank (rank 0)
+    if peer:
+        rend.readback_ranks = {0}
     digest = hashlib.sha1()
     for i in range(3):
         rend.set_modelView(cams[(i * 7) % SWEEP][0])
@@ -396,7 +469,7 @@ def run_slab(args, rank, local_rank, world):
             "e2e": {"value": args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128,
                     "d2h_bytes_per_step": 2 * W * W * 4,
                     "note": "SlabMaxProjector.set_modelView + render() on every rank, composited output + alpha read "
-                            "back into pinned host memory"},
+                            "back into pinned host memory%s" % (" on rank 0 (the display rank)" if peer else " on every rank")},
             "image_sha1_first8": digest.hexdigest(),
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3 / args.steps) / 1e9 / world,
@@ -419,6 +492,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload == "slab" and args.bricks > 0:
+        if world != 1:
+            raise SystemExit("--bricks is the single-GPU baseline: run it with --gpus 1")
+        run_bricks(args)
         return
     if args.workload == "slab":
         run_slab(args, rank, local_rank, world)

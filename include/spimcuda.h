@@ -133,10 +133,10 @@ SPV_API int spv_comp_import(spv_ctx *ctx, int peer, const void *handles, size_t 
 SPV_API int spv_comp_import_local(spv_ctx *ctx, int peer, spv_ctx *peer_ctx);            /* same process */
 SPV_API int spv_render_mip_composite(spv_ctx *ctx, const spv_mip_params *p);
 SPV_API int spv_comp_check(spv_ctx *ctx);  /* synchronises; -110 if a wait on a peer timed out (4 s) */
-/* Several slabs on one GPU (each its own context, sharing one stream): raw / composite renders of this context
- * max-merge the given device plane (another context's SPV_BUF_RAW, w*h floats, -1 = miss) into their partial before
- * it is written or pushed.  NULL switches it off.  The caller orders the two renders (same stream). */
-SPV_API int spv_set_merge_raw(spv_ctx *ctx, const void *dev_raw_plane);
+/* Several slabs of one volume on one GPU (each uploaded into its own context with spv_set_volume_slab): slab renders
+ * of `ctx` also march the slabs of `others` (at most 3; same extent, dtype, layout and filter) -- one ray setup, one
+ * launch, one partial.  The other contexts only hold data; they must outlive the renders.  n = 0 switches it off. */
+SPV_API int spv_set_extra_slabs(spv_ctx *ctx, spv_ctx **others, int n);
 
 /* ---- iso surface: _render_isosurface, volumerender.py:446-506
  *      iso_surface -> conv_vec_x/y(7) -> occlusion -> conv_x/y(5) -> shading ---- */

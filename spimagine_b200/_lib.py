@@ -66,7 +66,7 @@ SIGNATURES = {
     "spv_comp_import_local": (C.c_int, [_CTX, C.c_int, _CTX]),
     "spv_render_mip_composite": (C.c_int, [_CTX, C.POINTER(MipParams)]),
     "spv_comp_check": (C.c_int, [_CTX]),
-    "spv_set_merge_raw": (C.c_int, [_CTX, C.c_void_p]),
+    "spv_set_extra_slabs": (C.c_int, [_CTX, C.POINTER(_CTX), C.c_int]),
     "spv_render_iso": (C.c_int, [_CTX, C.POINTER(IsoParams)]),
     "spv_read": (C.c_int, [_CTX, C.c_int, _FP, C.c_size_t]),
     "spv_read_many": (C.c_int, [_CTX, _FP, _FP, _FP, _FP, _FP]),

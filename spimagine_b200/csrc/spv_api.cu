@@ -59,7 +59,8 @@ struct spv_ctx {
   float *peer_out[MAX_WORLD] = {nullptr};
   void *ipc_opened[MAX_WORLD][3] = {{nullptr}};
   unsigned comp_frame = 0;
-  const float *merge_raw = nullptr;  // spv_set_merge_raw
+  spv_ctx *extra[MAX_EXTRA_SLABS] = {nullptr};  // spv_set_extra_slabs: contexts whose slabs my slab renders march too
+  int n_extra = 0;
   int last_method = 0;    // 0 = mip, 1 = iso
   unsigned long long *d_stats = nullptr;
   unsigned long long h_stats[2] = {0, 0};
@@ -533,7 +534,17 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
   a.out = ctx->out(); a.alpha = ctx->alpha(); a.raw = ctx->raw();
   a.stats = ctx->stats_on ? ctx->d_stats : nullptr;
   a.tile_counter = ctx->persistent ? ctx->d_tile_counter : nullptr;
-  a.merge_raw = (a.flags & SPV_MIP_RAW_ONLY) || push ? ctx->merge_raw : nullptr;
+  a.n_extra = 0;
+  if (ctx->slab && ctx->n_extra > 0) {
+    if (ctx->skipping > 0) return fail(ctx, SPV_EINVAL, "spv_render_mip: extra slabs need empty-space skipping off");
+    for (int i = 0; i < ctx->n_extra; ++i) {
+      const spv_ctx *o = ctx->extra[i];
+      if (!o->arr || !o->slab || o->dtype != ctx->dtype || o->layout != ctx->layout || o->nx != ctx->nx || o->ny != ctx->ny ||
+          o->gnz != ctx->gnz || o->linear != ctx->linear || o->int_filter != ctx->int_filter)
+        return fail(ctx, SPV_EINVAL, "spv_render_mip: an extra slab does not match this context's volume (extent, dtype, layout, filter)");
+      a.extra[a.n_extra++] = volume_of(o);
+    }
+  }
   memset(&a.push, 0, sizeof a.push);
   if (push) {
     a.push = *push;
@@ -709,9 +720,14 @@ SPV_API int spv_render_mip_composite(spv_ctx *ctx, const spv_mip_params *p) {
   return 0;
 }
 
-SPV_API int spv_set_merge_raw(spv_ctx *ctx, const void *dev_raw_plane) {
+SPV_API int spv_set_extra_slabs(spv_ctx *ctx, spv_ctx **others, int n) {
   if (!ctx) return SPV_EINVAL;
-  ctx->merge_raw = (const float *)dev_raw_plane;
+  if (n < 0 || n > MAX_EXTRA_SLABS || (n > 0 && !others)) return fail(ctx, SPV_EINVAL, "spv_set_extra_slabs: at most 3 extra slabs");
+  for (int i = 0; i < n; ++i)
+    if (!others[i] || others[i] == ctx || others[i]->device != ctx->device)
+      return fail(ctx, SPV_EINVAL, "spv_set_extra_slabs: need other contexts on the same device");
+  for (int i = 0; i < MAX_EXTRA_SLABS; ++i) ctx->extra[i] = i < n ? others[i] : nullptr;
+  ctx->n_extra = n;
   return 0;
 }
 

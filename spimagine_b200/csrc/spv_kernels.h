@@ -8,6 +8,7 @@ namespace spv {
 // Sort-last composite over peer memory: rank r stores the raw partial maxima of the pixels in image band o straight
 // into the staging of band o's owner (its own memory when o == r, NVLink peer memory otherwise).
 constexpr int MAX_WORLD = 16;
+constexpr int MAX_EXTRA_SLABS = 3;
 struct PushArgs {
   float *part[MAX_WORLD];  // owner o's staging [parity][src rank][band_rows * width]
   int band_rows;           // image rows per band (multiple of 4: a warp's 8x4 tile lies in one band)
@@ -28,7 +29,8 @@ struct MipArgs {
   float *out, *alpha, *raw;
   unsigned long long *stats;  // [hit rays, texture samples issued] or nullptr
   unsigned *tile_counter;     // non-null: persistent CTAs pull tiles from this counter
-  const float *merge_raw;     // raw renders: a partial plane of another slab on this GPU to max-merge in, or nullptr
+  Volume extra[MAX_EXTRA_SLABS];  // further slabs of the same global volume resident on this GPU (slab renders):
+  int n_extra;                    // one ray setup, every slab's owned interval marched in turn
   PushArgs push;              // used when flags has SPV_MIP_PUSH
 };
 

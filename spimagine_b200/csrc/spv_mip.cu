@@ -178,17 +178,21 @@ __device__ __forceinline__ void mip_fast_tile(const MipArgs &a, unsigned bx, uns
         if (STATS) nfetch += S;
       } else {
         // The slice index floor(w(k) - 1/2) is monotone in k (fma, subtraction and floor all are), so the samples
-        // this slab owns form one interval [ka, kb): two binary searches with the exact predicate, then march it.
-        int ka, kb;
-        owned_interval(V, m, S, ka, kb);
-        for (int k = ka; k < kb; k += 8) {
-          float v[8];
+        // a slab owns form one interval [ka, kb): two binary searches with the exact predicate, then march it.
+        // Several slabs of the same volume can be resident on this GPU (a.extra): same ray, one interval each.
+        for (int sl = 0; sl <= a.n_extra; ++sl) {
+          const Volume &VS = sl == 0 ? V : a.extra[sl - 1];
+          int ka, kb;
+          owned_interval(VS, m, S, ka, kb);
+          for (int k = ka; k < kb; k += 8) {
+            float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = (k + j < kb) ? fetch_k<FMT, LINEAR, SLAB>(V, m, (float)(k + j)) : 0.f;
+            for (int j = 0; j < 8; ++j) v[j] = (k + j < kb) ? fetch_k<FMT, LINEAR, SLAB>(VS, m, (float)(k + j)) : 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) cur = fmaxf(cur, v[j]);
+            for (int j = 0; j < 8; ++j) cur = fmaxf(cur, v[j]);
+          }
+          if (STATS) nfetch += (unsigned)(kb - ka);
         }
-        if (STATS) nfetch += (unsigned)(kb - ka);
       }
     } else {
       // ---- pre-pass: every PRE-th sample gives a true lower bound of the ray maximum cheaply ----
@@ -288,7 +292,6 @@ __device__ __forceinline__ void mip_fast_tile(const MipArgs &a, unsigned bx, uns
   if (a.flags & SPV_MIP_RAW_ONLY) {
     outVal = hit ? cur : -1.f;  // un-windowed partial maximum (>= 0), -1 marks a miss; composited across GPUs
                                 // with max before the window is applied
-    if (a.merge_raw && inb) outVal = fmaxf(outVal, __ldg(a.merge_raw + x + (size_t)Nx * y));  // another local slab
     if (a.flags & SPV_MIP_PUSH) {  // straight into the staging of the band's owner (peer memory over NVLink)
       const unsigned o = ty0 / (unsigned)a.push.band_rows;
       dst_rows = a.push.part[o] + a.push.src_off + (size_t)(ty0 - o * (unsigned)a.push.band_rows) * Nx;

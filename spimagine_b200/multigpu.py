@@ -98,6 +98,7 @@ class SlabMaxProjector(VolumeRenderer):
         self.composite = composite
         self._connected = False
         self.slabs_per_rank = int(slabs_per_rank)
+        self.readback_ranks = None  # None: every rank reads the composited image back; or a set of ranks (display rank)
         self._parts = []  # helper renderers holding this rank's other slabs (slabs_per_rank > 1)
         self._ctor = (interpolation, dict(kw))
         if rank is None or world is None:
@@ -129,38 +130,27 @@ class SlabMaxProjector(VolumeRenderer):
             else:
                 self.set_slab(slab, nz, z0, z1)
 
-    # ---- several slabs per rank: helper contexts on the same stream, chained through spv_set_merge_raw ----
+    # ---- several slabs per rank: helper contexts hold the data, this context's kernel marches all of them ----
+    def _register_parts(self):
+        arr = (_lib._CTX * max(1, len(self._parts)))(*[h._ctx for h in self._parts])
+        self._check(self._lib.spv_set_extra_slabs(self._ctx, arr, len(self._parts)))
+
     def clear_parts(self):
+        self._check(self._lib.spv_set_extra_slabs(self._ctx, None, 0))
         for h in self._parts:
             h.close()
         self._parts = []
-        self._check(self._lib.spv_set_merge_raw(self._ctx, None))
 
     def add_slab(self, slab, gnz, z0, z1, device_ptr=None):
-        """One more slab for this rank to render besides the one given to set_slab()."""
+        """One more slab (at most 3) for this rank to render besides the one given to set_slab(): every ray marches
+        the samples owned by each resident slab in the same kernel launch."""
         interpolation, kw = self._ctor
-        h = SlabMaxProjector((self.width, self.height), interpolation, rank=self.rank, world=self.world,
-                             composite="nccl", **kw)
+        h = SlabMaxProjector((16, 16), interpolation, rank=self.rank, world=self.world, composite="nccl", **kw)
         h.set_layout(getattr(self, "layout", "zpair"))
         h._check(h._lib.spv_share_stream(h._ctx, self._ctx))
         h.set_slab(slab, gnz, z0, z1, device_ptr=device_ptr)
-        prev = self._parts[-1] if self._parts else None
-        if prev is not None:
-            h._check(h._lib.spv_set_merge_raw(h._ctx, prev._raw_ptr()))
         self._parts.append(h)
-        self._check(self._lib.spv_set_merge_raw(self._ctx, h._raw_ptr()))
-
-    def _raw_ptr(self):
-        p = C.c_void_p()
-        self._check(self._lib.spv_device_ptr(self._ctx, _lib.BUF_RAW, C.byref(p)))
-        return p
-
-    def _render_parts(self):
-        """Raw partials of the helper slabs, in chain order, on the shared stream."""
-        for h in self._parts:
-            h._check(h._lib.spv_set_matrices(h._ctx, _lib.fp(self._invP), _lib.fp(self._invM)))
-            p = _lib.MipParams(self._box(), 0., 0., 1., 0., 1, 0, int(self.max_steps), _lib.MIP_RAW_ONLY)
-            h._check(h._lib.spv_render_mip(h._ctx, C.byref(p)))
+        self._register_parts()
 
     def use_stream(self, cuda_stream=None):
         super(SlabMaxProjector, self).use_stream(cuda_stream)
@@ -168,6 +158,8 @@ class SlabMaxProjector(VolumeRenderer):
             h._check(h._lib.spv_share_stream(h._ctx, self._ctx))
 
     def close(self):
+        if getattr(self, "_parts", None) and getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.spv_set_extra_slabs(self._ctx, None, 0)
         for h in getattr(self, "_parts", []):
             h.close()
         self._parts = []
@@ -229,7 +221,6 @@ class SlabMaxProjector(VolumeRenderer):
             raise NotImplementedError("sort-last compositing needs alpha_pow == 0")
         if not self._connected:
             raise RuntimeError("SlabMaxProjector(composite='peer'): call connect() / connect_local() first")
-        self._render_parts()
         p = _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma), 0.,
                            1, 0, int(self.max_steps), 0)
         self._check(self._lib.spv_render_mip_composite(self._ctx, C.byref(p)))
@@ -237,6 +228,8 @@ class SlabMaxProjector(VolumeRenderer):
     def collect(self):
         """Wait for the enqueued composite and read output / output_alpha back."""
         self._check(self._lib.spv_comp_check(self._ctx))
+        if self.readback_ranks is not None and self.rank not in self.readback_ranks:
+            return  # the image is complete in this rank's device buffer (spv_device_ptr) but stays there
         flat, n = self._fetch(2)
         shape = (self.height, self.width)
         self.output = flat[:n].reshape(shape)
@@ -245,8 +238,7 @@ class SlabMaxProjector(VolumeRenderer):
     def resize(self, size):
         super(SlabMaxProjector, self).resize(size)
         self._connected = False  # the staging moved: connect() again
-        if getattr(self, "_parts", None):
-            raise NotImplementedError("resize with several slabs per rank: set the data again")
+
 
     def _raw_tensor(self):
         p = C.c_void_p()
@@ -265,7 +257,6 @@ class SlabMaxProjector(VolumeRenderer):
         p = _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma), 0.,
                            1, 0, int(self.max_steps), _lib.MIP_RAW_ONLY)
         torch = self._torch
-        self._render_parts()
         self._check(self._lib.spv_render_mip(self._ctx, C.byref(p)))
         if self.world > 1 and self._dist.is_initialized():
             with torch.cuda.stream(self._stream):
