@@ -66,6 +66,12 @@ SPV_API int spv_sync(spv_ctx *ctx);
 SPV_API int spv_set_volume(spv_ctx *ctx, const void *host, int dtype, int nx, int ny, int nz);
 /* same shape and dtype as the current volume: re-upload only (the timelapse path, glwidget.py:372-374) */
 SPV_API int spv_update_volume(spv_ctx *ctx, const void *host);
+/* same, from PAGE-LOCKED host memory, without waiting: the transfer runs at PCIe rate on the context's stream and the
+ * call returns at once; the buffer must stay untouched until spv_sync (or any synchronising call) returns.  This is
+ * the streamed-timelapse path: the frame source fills pinned buffers (spv_host_alloc) ahead of the playback. */
+SPV_API int spv_update_volume_async(spv_ctx *ctx, const void *pinned_host);
+SPV_API int spv_host_alloc(size_t nbytes, void **host);  /* page-locked, usable from every device */
+SPV_API int spv_host_free(void *host);
 /* as above from a DEVICE pointer (C-order linear); used by frame sources that keep timepoints in HBM */
 SPV_API int spv_set_volume_device(spv_ctx *ctx, const void *dev, int dtype, int nx, int ny, int nz);
 /* One z-slab of a larger volume for sort-last rendering (new).  The host/dev pointer

@@ -47,6 +47,9 @@ SIGNATURES = {
     "spv_sync": (C.c_int, [_CTX]),
     "spv_set_volume": (C.c_int, [_CTX, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "spv_update_volume": (C.c_int, [_CTX, C.c_void_p]),
+    "spv_update_volume_async": (C.c_int, [_CTX, C.c_void_p]),
+    "spv_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "spv_host_free": (C.c_int, [C.c_void_p]),
     "spv_set_volume_device": (C.c_int, [_CTX, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "spv_set_volume_slab": (C.c_int, [_CTX, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int]),
@@ -107,6 +110,21 @@ def load():
 def fp(a):
     assert a.dtype == np.float32 and a.flags.c_contiguous
     return a.ctypes.data_as(_FP)
+
+
+def pinned_empty(shape, dtype):
+    """ndarray in page-locked host memory (spv_host_alloc): the source of asynchronous uploads at PCIe rate
+    (VolumeRenderer.update_data(..., pinned=True), TimelapsePlayer) -- freed when the array is collected."""
+    import weakref
+    lib = load()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    check(lib.spv_host_alloc(max(n, 1), C.byref(p)))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib.spv_host_free, C.c_void_p(p.value))
+    return arr
 
 
 class SpvError(RuntimeError):

@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     # no implicit contraction: the ray setup must round like the reference's fp32 expressions
     # (explicit fmaf where the fast path wants it), IEEE division and square root
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
-    "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-O2",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden,-O2,-pthread",
     "-shared", "-cudart", "static",
 ]
 

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <string>
+#include <thread>
 
 #include "spv_kernels.h"
 
@@ -24,13 +25,18 @@ struct spv_ctx {
   bool slab = false;
   int layout = LAYOUT_3D;        // of the resident array
   int want_layout = LAYOUT_ZPAIR; // for integer volumes (spv_set_layout)
-  void *d_stage = nullptr;       // ingest staging (z-pair construction)
+  void *d_stage = nullptr;       // ingest staging on the device: [paired texels | linear chunk x 2]
   size_t stage_bytes = 0;
+  char *h_ring = nullptr;        // page-locked ring (2 chunks) for pageable sources
+  size_t ring_bytes = 0;
+  cudaEvent_t ev_up_begin = nullptr, ev_h2d_done[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  bool ring_used[2] = {false, false}, lin_used[2] = {false, false};
   float2 *bricks = nullptr, *coarse = nullptr;
   int gx = 0, gy = 0, gz = 0, cgx = 0, cgy = 0, cgz = 0;
   float *d_minmax = nullptr;
   float h_minmax[2] = {0.f, 0.f};
   bool minmax_valid = false;
+  bool bricks_valid = false;  // the min/max grids are built on first use after an upload (iso, skipping, min/max query)
   // settings
   int linear = 1, sampler = SPV_SAMPLER_TMU, int_filter = 1, skipping = -1, stats_on = 0, tile_variant = 0, persistent = 0;
   int bands = 2;  // default band count of spv_render_mip_to_host (measured best of 1/2/4/8/16, profiles/r01_exp_e2e.txt)
@@ -147,9 +153,14 @@ static void free_volume(spv_ctx *c) {
   if (c->arr) cudaFreeArray(c->arr);
   if (c->bricks) cudaFree(c->bricks);
   if (c->coarse) cudaFree(c->coarse);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->d_stage) cudaFree(c->d_stage);
+  if (c->h_ring) cudaFreeHost(c->h_ring);
   c->d_stage = nullptr;
   c->stage_bytes = 0;
+  c->h_ring = nullptr;
+  c->ring_bytes = 0;
+  c->ring_used[0] = c->ring_used[1] = c->lin_used[0] = c->lin_used[1] = false;
   c->tex_lin = c->tex_near = c->tex_pt = 0;
   c->arr = nullptr;
   c->bricks = c->coarse = nullptr;
@@ -209,9 +220,12 @@ SPV_API int spv_create(int device, int width, int height, spv_ctx **out) {
   CC(cudaEventCreate(&ctx->ev0));
   CC(cudaEventCreate(&ctx->ev1));
   CC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CC(cudaEventCreateWithFlags(&ctx->ev_up_begin, cudaEventDisableTiming));
   for (int s = 0; s < 2; ++s) {
     CC(cudaEventCreateWithFlags(&ctx->ev_rendered[s], cudaEventDisableTiming));
     CC(cudaEventCreateWithFlags(&ctx->ev_copied[s], cudaEventDisableTiming));
+    CC(cudaEventCreateWithFlags(&ctx->ev_h2d_done[s], cudaEventDisableTiming));
+    CC(cudaEventCreateWithFlags(&ctx->ev_consumed[s], cudaEventDisableTiming));
   }
   CC(cudaMalloc(&ctx->d_minmax, 2 * sizeof(float)));
   CC(cudaMalloc(&ctx->d_stats, 2 * sizeof(unsigned long long)));
@@ -238,9 +252,12 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
   if (ctx->d_tile_counter) cudaFree(ctx->d_tile_counter);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev_up_begin) cudaEventDestroy(ctx->ev_up_begin);
   for (int s = 0; s < 2; ++s) {
     if (ctx->ev_rendered[s]) cudaEventDestroy(ctx->ev_rendered[s]);
     if (ctx->ev_copied[s]) cudaEventDestroy(ctx->ev_copied[s]);
+    if (ctx->ev_h2d_done[s]) cudaEventDestroy(ctx->ev_h2d_done[s]);
+    if (ctx->ev_consumed[s]) cudaEventDestroy(ctx->ev_consumed[s]);
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -315,64 +332,167 @@ static Volume volume_of(const spv_ctx *c) {
   return V;
 }
 
-// Fill the resident array from `src` (host or device, C-order, local_nz slices).
-//   LAYOUT_3D:    one cudaMemcpy3D.
-//   LAYOUT_ZPAIR: in chunks of slices -- (host -> device staging,) pair_kernel builds {v[z], v[z+1]} texels in a
-//                 linear buffer, cudaMemcpy3D moves them into the layers.
-static int upload(spv_ctx *ctx, const void *src, bool on_device) {
+// Copy n bytes with a few host threads (one thread saturates neither the memory system nor a PCIe 5 link).
+static void parallel_memcpy(void *dst, const void *src, size_t n) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  int T = n >= ((size_t)8 << 20) ? (hw >= 16 ? 8 : (hw >= 8 ? 4 : 2)) : 1;
+  const size_t part = ((n / T) + 4095) & ~(size_t)4095;
+  std::thread th[8];
+  int started = 0;
+  for (int t = 1; t < T; ++t) {
+    const size_t off = (size_t)t * part;
+    if (off >= n) break;
+    const size_t len = n - off < part ? n - off : part;
+    th[started++] = std::thread([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+  }
+  memcpy(dst, src, n < part ? n : part);
+  for (int t = 0; t < started; ++t) th[t].join();
+}
+
+enum { SRC_DEVICE = 0, SRC_PINNED = 1, SRC_PAGEABLE = 2 };
+
+// Fill the resident array from `src` (C-order, local_nz slices) -- the ingest path (replaces OCLImage.write_array,
+// volumerender.py:294).  Host sources move in chunks of ~32 MiB through a two-deep pipeline:
+//   pageable memory  : host threads copy chunk i+1 into a page-locked ring while chunk i is on the PCIe link
+//   page-locked      : the DMA engine reads the caller's buffer directly
+//   copy_stream      : H2D of chunk i+1 overlaps the device-side work on chunk i
+//   LAYOUT_ZPAIR     : pair_kernel builds {v[z], v[z+1]} texels from the linear chunk, cudaMemcpy3D moves them into
+//                      the layers (stream order on the render stream)
+//   LAYOUT_3D        : the DMA writes the array slices directly
+static int upload(spv_ctx *ctx, const void *src, bool on_device, bool no_wait = false) {
   const size_t es = elem_size(ctx->dtype);
   const size_t slice = (size_t)ctx->nx * ctx->ny;
+  const size_t slice_bytes = slice * es;
   const int nz = ctx->local_nz;
-  if (ctx->layout == LAYOUT_3D) {
+  const bool zpair = ctx->layout == LAYOUT_ZPAIR;
+  int kind = SRC_DEVICE;
+  if (!on_device) {
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, src);
+    if (e != cudaSuccess) cudaGetLastError();
+    kind = (e == cudaSuccess && at.type == cudaMemoryTypeHost) ? SRC_PINNED : SRC_PAGEABLE;
+  }
+  ctx->bricks_valid = false;  // rebuilt by ensure_bricks() when something needs them
+  ctx->minmax_valid = false;
+
+  // slices per chunk
+  const size_t budget = kind == SRC_DEVICE ? ((size_t)128 << 20) : ((size_t)32 << 20);
+  int zc = (int)(budget / slice_bytes);
+  if (zc < 1) zc = 1;
+  if (zc > nz) zc = nz;
+  const size_t lin_bytes = slice_bytes * (size_t)(zc + (zpair ? 1 : 0));  // + the upper partner of the last slice
+  const size_t pair_bytes = zpair ? slice_bytes * 2 * (size_t)zc : 0;
+  const size_t need_dev = pair_bytes + ((zpair && kind != SRC_DEVICE) ? 2 * lin_bytes : 0);
+  if (need_dev > ctx->stage_bytes) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    ctx->d_stage = nullptr;
+    ctx->stage_bytes = 0;
+    CU(cudaMalloc(&ctx->d_stage, need_dev));
+    ctx->stage_bytes = need_dev;
+  }
+  if (kind == SRC_PAGEABLE && 2 * lin_bytes > ctx->ring_bytes) {
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+    ctx->h_ring = nullptr;
+    ctx->ring_bytes = 0;
+    CU(cudaMallocHost(&ctx->h_ring, 2 * lin_bytes));
+    ctx->ring_bytes = 2 * lin_bytes;
+  }
+  char *d_pair = (char *)ctx->d_stage;
+  char *d_lin[2] = {d_pair + pair_bytes, d_pair + pair_bytes + lin_bytes};
+  char *h_ring[2] = {ctx->h_ring, ctx->h_ring ? ctx->h_ring + lin_bytes : nullptr};
+
+  auto to_layers = [&](const void *lin, int lin_nz, int zfirst, int zb, int ze) -> int {
+    // lin holds slices [zfirst, zfirst + lin_nz) of the volume; build the paired texels of [zb, ze) and store them
+    CU(launch_pair(lin, d_pair, ctx->dtype, slice, lin_nz, zb - zfirst, ze - zfirst, ctx->stream));
     cudaMemcpy3DParms p;
     memset(&p, 0, sizeof p);
-    p.srcPtr = make_cudaPitchedPtr(const_cast<void *>(src), (size_t)ctx->nx * es, ctx->nx, ctx->ny);
+    p.srcPtr = make_cudaPitchedPtr(d_pair, (size_t)ctx->nx * 2 * es, ctx->nx, ctx->ny);
     p.dstArray = ctx->arr;
-    p.extent = make_cudaExtent(ctx->nx, ctx->ny, nz);
-    p.kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    p.dstPos = make_cudaPos(0, 0, zb);
+    p.extent = make_cudaExtent(ctx->nx, ctx->ny, ze - zb);
+    p.kind = cudaMemcpyDeviceToDevice;
     CU(cudaMemcpy3DAsync(&p, ctx->stream));
-  } else {
-    const size_t budget = (size_t)256 << 20;  // bytes of paired texels per chunk
-    int zc = (int)(budget / (slice * 2 * es));
-    if (zc < 1) zc = 1;
-    if (zc > nz) zc = nz;
-    const size_t need_pair = slice * 2 * es * (size_t)zc;
-    const size_t need_stage = on_device ? 0 : slice * es * (size_t)(zc + 1);
-    if (ctx->stage_bytes < need_pair + need_stage) {
-      if (ctx->d_stage) cudaFree(ctx->d_stage);
-      ctx->d_stage = nullptr;
-      ctx->stage_bytes = 0;
-      CU(cudaMalloc(&ctx->d_stage, need_pair + need_stage));
-      ctx->stage_bytes = need_pair + need_stage;
-    }
-    char *d_pair = (char *)ctx->d_stage, *d_lin = d_pair + need_pair;
-    for (int zb = 0; zb < nz; zb += zc) {
-      const int ze = zb + zc < nz ? zb + zc : nz;
-      if (on_device) {
-        CU(launch_pair(src, d_pair, ctx->dtype, slice, nz, zb, ze, ctx->stream));
-      } else {
-        const int zs = ze < nz ? ze + 1 : nz;  // one slice more: the upper partner of the chunk's last slice
-        CU(cudaMemcpyAsync(d_lin, (const char *)src + (size_t)zb * slice * es, (size_t)(zs - zb) * slice * es,
-                           cudaMemcpyHostToDevice, ctx->stream));
-        CU(launch_pair(d_lin, d_pair, ctx->dtype, slice, zs - zb, 0, ze - zb, ctx->stream));
-      }
+    ctx->launches += 1;
+    return 0;
+  };
+
+  if (kind == SRC_DEVICE) {
+    if (!zpair) {
       cudaMemcpy3DParms p;
       memset(&p, 0, sizeof p);
-      p.srcPtr = make_cudaPitchedPtr(d_pair, (size_t)ctx->nx * 2 * es, ctx->nx, ctx->ny);
+      p.srcPtr = make_cudaPitchedPtr(const_cast<void *>(src), (size_t)ctx->nx * es, ctx->nx, ctx->ny);
+      p.dstArray = ctx->arr;
+      p.extent = make_cudaExtent(ctx->nx, ctx->ny, nz);
+      p.kind = cudaMemcpyDeviceToDevice;
+      CU(cudaMemcpy3DAsync(&p, ctx->stream));
+    } else {
+      for (int zb = 0; zb < nz; zb += zc) {
+        int rc = to_layers(src, nz, 0, zb, zb + zc < nz ? zb + zc : nz);
+        if (rc) return rc;
+      }
+    }
+    return 0;
+  }
+
+  // host sources: the DMA runs on copy_stream; it must not overtake renders that still read the array
+  CU(cudaEventRecord(ctx->ev_up_begin, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_up_begin, 0));
+  int i = 0;
+  for (int zb = 0; zb < nz; zb += zc, ++i) {
+    const int ze = zb + zc < nz ? zb + zc : nz;
+    const int zs = zpair ? (ze < nz ? ze + 1 : nz) : ze;  // slices [zb, zs) travel
+    const size_t bytes = (size_t)(zs - zb) * slice_bytes;
+    const int s = i & 1;
+    const char *from = (const char *)src + (size_t)zb * slice_bytes;
+    if (kind == SRC_PAGEABLE) {
+      if (ctx->ring_used[s]) CU(cudaEventSynchronize(ctx->ev_h2d_done[s]));  // the DMA that last read this half
+      parallel_memcpy(h_ring[s], from, bytes);
+      ctx->ring_used[s] = true;
+      from = h_ring[s];
+    }
+    if (zpair) {
+      if (ctx->lin_used[s]) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[s], 0));
+      CU(cudaMemcpyAsync(d_lin[s], from, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+      CU(cudaEventRecord(ctx->ev_h2d_done[s], ctx->copy_stream));
+      CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d_done[s], 0));
+      int rc = to_layers(d_lin[s], zs - zb, zb, zb, ze);
+      if (rc) return rc;
+      CU(cudaEventRecord(ctx->ev_consumed[s], ctx->stream));
+      ctx->lin_used[s] = true;
+    } else {
+      cudaMemcpy3DParms p;
+      memset(&p, 0, sizeof p);
+      p.srcPtr = make_cudaPitchedPtr(const_cast<char *>(from), (size_t)ctx->nx * es, ctx->nx, ctx->ny);
       p.dstArray = ctx->arr;
       p.dstPos = make_cudaPos(0, 0, zb);
       p.extent = make_cudaExtent(ctx->nx, ctx->ny, ze - zb);
-      p.kind = cudaMemcpyDeviceToDevice;
-      CU(cudaMemcpy3DAsync(&p, ctx->stream));
-      ctx->launches += 1;
+      p.kind = cudaMemcpyHostToDevice;
+      CU(cudaMemcpy3DAsync(&p, ctx->copy_stream));
+      CU(cudaEventRecord(ctx->ev_h2d_done[s], ctx->copy_stream));
     }
   }
+  if (!zpair && i > 0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d_done[(i - 1) & 1], 0));  // renders wait for the data
+  if (!no_wait) {  // the host pointer is only borrowed for this call
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+// min/max brick grids + global min/max of the resident volume: needed by iso-surface skipping, max-projection
+// skipping and spv_volume_minmax, not by the brute-force max projection -- a timelapse that only plays back
+// max projections never pays for them
+static int ensure_bricks(spv_ctx *ctx) {
+  if (ctx->bricks_valid) return 0;
   Volume V = volume_of(ctx);
   CU(launch_build_bricks(V, fmt_of(ctx), ctx->local_nz, ctx->bricks, ctx->coarse, ctx->cgx, ctx->cgy, ctx->cgz,
                          ctx->d_minmax, ctx->stream));
   ctx->launches += 3;
+  ctx->bricks_valid = true;
   ctx->minmax_valid = false;
-  if (!on_device) CU(cudaStreamSynchronize(ctx->stream));  // the host pointer is only borrowed for this call
   return 0;
 }
 
@@ -430,9 +550,37 @@ SPV_API int spv_update_volume(spv_ctx *ctx, const void *host) {
   return upload(ctx, host, false);
 }
 
+SPV_API int spv_update_volume_async(spv_ctx *ctx, const void *pinned_host) {
+  BIND();
+  if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_update_volume_async: no volume set");
+  if (!pinned_host) return fail(ctx, SPV_EINVAL, "spv_update_volume_async: null data");
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, pinned_host);
+  if (e != cudaSuccess || at.type != cudaMemoryTypeHost) {
+    cudaGetLastError();
+    return fail(ctx, SPV_EINVAL, "spv_update_volume_async: the source must be page-locked host memory (spv_host_alloc / cudaHostRegister)");
+  }
+  return upload(ctx, pinned_host, false, true);
+}
+
+SPV_API int spv_host_alloc(size_t nbytes, void **host) {
+  if (!host || nbytes == 0) return SPV_EINVAL;
+  cudaError_t e = cudaHostAlloc(host, nbytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) return cufail(nullptr, e, "cudaHostAlloc");
+  return 0;
+}
+SPV_API int spv_host_free(void *host) {
+  if (host) cudaFreeHost(host);
+  return 0;
+}
+
 SPV_API int spv_volume_minmax(spv_ctx *ctx, float *vmin, float *vmax) {
   BIND();
   if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_volume_minmax: no volume set");
+  {
+    int rc = ensure_bricks(ctx);
+    if (rc) return rc;
+  }
   if (!ctx->minmax_valid) {
     CU(cudaMemcpyAsync(ctx->h_minmax, ctx->d_minmax, 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -553,7 +701,9 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     a.flags &= ~SPV_MIP_PUSH;
   }
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
-  int rc = begin_render(ctx);
+  int rc = (fast && ctx->skipping > 0) ? ensure_bricks(ctx) : 0;
+  if (rc) return rc;
+  rc = begin_render(ctx);
   if (rc) return rc;
   const int s = ctx->slot;
   if (to_host && ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // staging about to be rewritten
@@ -780,6 +930,10 @@ SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p) {
   const bool exact_iso = ctx->sampler == SPV_SAMPLER_EXACT;
   a.tile_hit = exact_iso ? nullptr : ctx->d_tile_hit;
   a.skip = ctx->skipping != 0;  // auto (-1) = on: for iso surfaces the brick test is nearly free and exact
+  if (a.skip && ctx->sampler != SPV_SAMPLER_EXACT) {
+    int rcb = ensure_bricks(ctx);
+    if (rcb) return rcb;
+  }
   a.width = ctx->width; a.height = ctx->height;
   a.out = ctx->out(); a.alpha = ctx->alpha(); a.depth = ctx->depth(); a.normals = ctx->normals();
   a.stats = ctx->stats_on ? ctx->d_stats : nullptr;

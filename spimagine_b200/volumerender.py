@@ -230,7 +230,10 @@ class VolumeRenderer(object):
         self.dataImg = _DataImage(dataShape, self.dtype)
         self._need_alloc = True
 
-    def update_data(self, data, copyData=False):
+    def update_data(self, data, copyData=False, pinned=False):
+        """pinned=True (addition): `data` lives in page-locked memory (spimagine_b200.pinned_empty): the upload is
+        enqueued at PCIe rate and the call returns at once; do not touch `data` before the next render has
+        returned (or sync())."""
         if self.dataSlices is not None:
             self._data = data[self.dataSlices].copy()
         else:
@@ -244,6 +247,8 @@ class VolumeRenderer(object):
         if getattr(self, "_need_alloc", True):
             rc = self._lib.spv_set_volume(self._ctx, host.ctypes.data, _lib.DTYPE_CODES[host.dtype], Nx, Ny, Nz)
             self._need_alloc = False
+        elif pinned and host is data:
+            rc = self._lib.spv_update_volume_async(self._ctx, host.ctypes.data)
         else:
             rc = self._lib.spv_update_volume(self._ctx, host.ctypes.data)
         self._check(rc)

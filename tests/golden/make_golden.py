@@ -32,6 +32,11 @@ def main():
         res = golden_cases.run_case(rend, name)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **res)
         print(name, {k: (v.shape, float(np.nanmax(np.where(np.isfinite(v), v, 0)))) for k, v in res.items()})
+    for name, case in sorted(golden_cases.CONFIG_CASES.items()):
+        rend = oracle.OracleRenderer(case["size"], kind="reference")
+        res = golden_cases.run_config_case(rend, name)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **res)
+        print(name, {k: (v.shape, float(v.max())) for k, v in res.items()})
 
 
 if __name__ == "__main__":

@@ -49,6 +49,28 @@ CASES = {
 }
 
 
+# BASELINE.json configs at their own sizes; the golden file keeps every `rows`-th image row
+CONFIG_CASES = {
+    # configs[0]: max_project of a 128^3 float32 synthetic Gaussian-blob volume to 512x512
+    "c1_mip_f32_volg128_512": dict(size=(512, 512), rows=8, data=lambda: scenes.vol_g(128, np.float32, seed=0),
+                                   cam=lambda: scenes.gui_camera(2 * np.pi * 40 / 360, 4.0), render=dict(maxVal=1.)),
+}
+CASES_ALL = dict(CASES)
+CASES_ALL.update(CONFIG_CASES)
+
+
+def run_config_case(rend, name):
+    """-> dict(output, alpha), every `rows`-th row of the frame."""
+    c = CONFIG_CASES[name]
+    rend.set_data(c["data"]())
+    M, P = c["cam"]()
+    rend.set_modelView(M)
+    rend.set_projection(P)
+    rend.render(**c["render"])
+    r = c["rows"]
+    return {"output": np.array(rend.output[::r]), "alpha": np.array(rend.output_alpha[::r])}
+
+
 def run_case(rend, name):
     """Drive `rend` (OracleRenderer or VolumeRenderer: same calls) through case `name`.
     -> dict of result arrays."""

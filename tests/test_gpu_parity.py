@@ -58,6 +58,23 @@ def test_exact_sampler_matches_golden(name):
                 name, k, _maxdiff(r, g), int((r != g).sum()))
 
 
+@pytest.mark.parametrize("name", sorted(golden_cases.CONFIG_CASES))
+def test_config_case_matches_golden(name):
+    """BASELINE.json configs[0] at its own size: exact sampler bit for bit, texture-unit sampler within 1e-3 of the
+    dynamic range (north_star), hit mask identical."""
+    case = golden_cases.CONFIG_CASES[name]
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    rend = _renderer(case["size"], sampler="exact")
+    res = golden_cases.run_config_case(rend, name)
+    assert np.array_equal(res["output"], gold["output"]) and np.array_equal(res["alpha"], gold["alpha"])
+    rend.close()
+    rend = _renderer(case["size"], sampler="tmu")
+    res = golden_cases.run_config_case(rend, name)
+    assert _maxdiff(res["output"], gold["output"]) < 1e-3 * case["render"]["maxVal"]
+    assert np.array_equal(res["alpha"], gold["alpha"])
+    rend.close()
+
+
 @pytest.mark.parametrize("name", [n for n in sorted(golden_cases.CASES)
                                   if "random" not in n and "nearest" not in n and "alpha" not in n])
 def test_tmu_sampler_close_to_golden(name):

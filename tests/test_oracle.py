@@ -33,6 +33,16 @@ def test_port_matches_golden_bitwise(oracle_mod, name):
             name, k, np.nanmax(np.abs(np.where(np.isfinite(gold[k]), res[k] - gold[k], 0))))
 
 
+@pytest.mark.parametrize("name", sorted(golden_cases.CONFIG_CASES))
+def test_port_matches_config_golden_bitwise(oracle_mod, name):
+    """BASELINE.json configs[0] at its own size (128^3 float32 -> 512x512)."""
+    case = golden_cases.CONFIG_CASES[name]
+    res = golden_cases.run_config_case(oracle_mod.OracleRenderer(case["size"], kind="port"), name)
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    for k in gold.files:
+        assert _eq(res[k], gold[k]), k
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.uint16, np.uint8])
 @pytest.mark.parametrize("interp", ["linear", "nearest"])
 def test_port_matches_reference_build_on_random_volumes(oracle_mod, have_ref, dtype, interp):
