@@ -56,9 +56,12 @@ def parse():
     ap.add_argument("--vol", type=int, default=VOL_N)
     ap.add_argument("--img", type=int, default=IMG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="sweep", choices=["sweep", "slab"],
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "slab", "timelapse"],
                     help="sweep: BASELINE configs[1], frames sharded over the GPUs (default). slab: configs[3], one "
-                         "--vol^3 uint16 volume split into z-slabs over the GPUs, sort-last max composite over NCCL")
+                         "--vol^3 uint16 volume split into z-slabs over the GPUs, sort-last max composite. timelapse: "
+                         "configs[4], --frames time points of --tl-shape uint16, time point t on GPU t mod N")
+    ap.add_argument("--frames", type=int, default=100, help="timelapse workload: time points in the whole series")
+    ap.add_argument("--tl-shape", default="512,1024,1024", help="timelapse workload: (Nz,Ny,Nx) of one time point")
     ap.add_argument("--skip", action="store_true", help="enable empty-space skipping on the min/max brick grid")
     ap.add_argument("--slabs-per-rank", type=int, default=2,
                     help="slab workload: slabs per GPU, dealt in serpentine order (front/back slabs pair up: balanced "
@@ -237,6 +240,134 @@ def vol_g_slab_device(N, z_lo, z_hi, seed, device):
         v = v * scale + (0.01 * 58000. / float(1 << 24)) * h.to(torch.float32)
         out[zb - z_lo:ze - z_lo] = v.clamp_(0, 65535).round_().to(torch.int32).to(torch.uint16)
     return out
+
+
+def vol_g_device(shape, seed, t, device):
+    """One Vol-G time point (blob centres drifting 0.01 t) of shape (nz, ny, nx), uint16, generated on
+    the GPU with torch (plumbing: bench input only)."""
+    import torch
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-.6, .6, (8, 3)) + 0.01 * t
+    sg = rng.uniform(.08, .25, 8)
+    a = rng.uniform(.3, 1., 8)
+    nz, ny, nx = shape
+    lz = torch.linspace(-1, 1, nz, device=device, dtype=torch.float32)
+    ly = torch.linspace(-1, 1, ny, device=device, dtype=torch.float32)
+    lx = torch.linspace(-1, 1, nx, device=device, dtype=torch.float32)
+    out = torch.empty(shape, dtype=torch.uint16, device=device)
+    step = 16
+    for zb in range(0, nz, step):
+        ze = min(zb + step, nz)
+        v = torch.zeros((ze - zb, ny, nx), device=device)
+        for i in range(8):
+            k = float(1. / (2 * sg[i] ** 2))
+            gz = float(a[i]) * torch.exp(-k * (lz[zb:ze] - float(c[i, 0])) ** 2)
+            gy = torch.exp(-k * (ly - float(c[i, 1])) ** 2)
+            gx = torch.exp(-k * (lx - float(c[i, 2])) ** 2)
+            v += gz[:, None, None] * (gy[:, None] * gx[None, :])[None]
+        idx = torch.arange(zb * ny * nx, ze * ny * nx, device=device, dtype=torch.int64).reshape(ze - zb, ny, nx)
+        h = (idx * 2654435761 + (seed + t) * 40503) & 0xffffffff
+        h = ((h ^ (h >> 15)) * 2246822519) & 0xffffffff
+        h = (h ^ (h >> 13)) & 0xffffff
+        v = v * 30000. + (0.01 * 58000. / float(1 << 24)) * h.to(torch.float32)
+        out[zb:ze] = v.clamp_(0, 65535).round_().to(torch.int32).to(torch.uint16)
+    return out
+
+
+def run_timelapse(args, rank, local_rank, world):
+    """BASELINE configs[4]: 3D+t playback, time point t on GPU t mod N, no data-path collective (weak scaling in the
+    number of time points a GPU holds; `value` counts time points played by all GPUs per second).
+      value : the owned time points are RESIDENT in HBM (one texture array each); a step renders the next one
+      e2e   : STREAMED through the public API -- per step one time point is uploaded from page-locked host memory
+              (TimelapsePlayer.play -> update_data(pinned=True)), rendered, and output + alpha read back"""
+    import torch
+    import torch.distributed as dist
+    import scenes
+    from spimagine_b200 import pinned_empty
+    from spimagine_b200.multigpu import TimelapsePlayer, frames_for_rank
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    shape = tuple(int(x) for x in args.tl_shape.split(","))
+    W = args.img
+    mine = frames_for_rank(args.frames, rank, world)
+    player = TimelapsePlayer((W, W), rank=rank, world=world, device=local_rank, max_steps=MAX_STEPS, pinned_outputs=True)
+    ring = [pinned_empty(shape, np.uint16) for _ in range(min(4, len(mine)))]  # streamed source: distinct time points
+    t0 = time.perf_counter()
+    for j, t in enumerate(mine):
+        d = vol_g_device(shape, 100, t, dev)
+        if j < len(ring):
+            ring[j][...] = d.cpu().numpy()
+        player.preload({t: (d.data_ptr(), shape, np.uint16)}, frames=[t], device_ptrs=True)
+        del d
+    torch.cuda.synchronize()
+    t_prep = time.perf_counter() - t0
+    P = scenes.gui_camera(0, 4.0)[1]
+    cams = [scenes.gui_camera(2 * math.pi * f / 720, 4.0)[0] for f in range(720)]  # slow spin
+    for r in player.resident.values():
+        r.set_projection(P)
+        r.set_max_val(PEAK_VALUE)
+        r.set_units([1., 1., 2.])  # 512 slices of twice the pixel pitch: a cubic field of view
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step(i):
+        r = player.resident[mine[i % len(mine)]]
+        r.set_modelView(cams[i % 720])
+        r.render_device_only()
+
+    for i in range(args.warmup):
+        resident_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        resident_step(i)
+    for r in player.resident.values():
+        r.sync()
+    t_res = time.perf_counter() - t0  # contexts run on their own streams: host clock around a full drain
+    barrier()
+
+    # streamed, end to end
+    src = {i: ring[i % len(ring)] for i in range(args.steps + 3)}
+    settings = dict(projection=P, max_val=PEAK_VALUE, units=[1., 1., 2.])
+    for _ in player.play(src, {i: cams[i % 720] for i in src}, frames=range(3), pinned=True, **settings):
+        pass
+    barrier()
+    chk = 0.
+    t0 = time.perf_counter()
+    for t, r in player.play(src, {i: cams[i % 720] for i in src}, frames=range(3, args.steps + 3), pinned=True, **settings):
+        chk += float(r.output[W // 2, W // 2])
+    torch.cuda.synchronize()
+    t_str = time.perf_counter() - t0
+    barrier()
+    if world > 1:
+        tt = torch.tensor([t_res, t_str], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_res, t_str = float(tt[0]), float(tt[1])
+    if rank == 0:
+        nbytes = int(np.prod(shape)) * 2
+        print(json.dumps({
+            "metric": "3D+t max_project playback, time points/s, %d x %s uint16 -> %d^2" % (args.frames, "x".join(map(str, shape)), W),
+            "value": args.steps * world / t_res, "unit": "time points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u16->f32", "data": "synthetic",
+            "config": {"workload": "Vol-G time points (seed 100, centres drifting), time point t on GPU t mod %d, %d resident "
+                                   "per GPU (%d MiB each as z-paired texels), fixed projection + slow spin" % (
+                                       world, len(mine), 2 * nbytes >> 20)},
+            "e2e": {"value": args.steps * world / t_str, "unit": "time points/s", "h2d_bytes_per_step": nbytes + 128,
+                    "d2h_bytes_per_step": 2 * W * W * 4, "checksum": chk,
+                    "note": "streamed: TimelapsePlayer.play(pinned=True) uploads every time point from page-locked host "
+                            "memory (%.1f GB/s per GPU), renders it and reads output + alpha back" % (nbytes / (t_str / args.steps) / 1e9)},
+            "gpu_launches": args.steps, "prepare_s": t_prep}))
+    player.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_bricks(args):
@@ -492,6 +623,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.workload == "timelapse":
+        run_timelapse(args, rank, local_rank, world)
         return
     if args.workload == "slab" and args.bricks > 0:
         if world != 1:

@@ -272,28 +272,86 @@ class SlabMaxProjector(VolumeRenderer):
 
 
 class TimelapsePlayer(object):
-    """Frame-sharded 3D+t playback: rank r renders frames r, r+world, ... of a (T, Nz, Ny, Nx) source."""
+    """Frame-sharded 3D+t playback (SURVEY.md 8e): rank r plays frames r, r+world, ... of a (T, Nz, Ny, Nx) source;
+    no data-path collective.  Replaces the reference's per-time-step full re-upload from pageable memory
+    (DataModel -> GLWidget.dataModel_changed -> renderer.update_data, gui/glwidget.py:372-374).
+
+    Two ways to hold the frames this rank owns:
+      preload(source)   every owned frame becomes resident in HBM (its own texture array): playing a frame is
+                        one render, nothing is uploaded -- 2 GiB per 512x1024x1024 uint16 frame in the z-paired layout
+      play(source)      streamed: frame t+1 is uploaded while frame t is being read back; with a page-locked source
+                        (spimagine_b200.pinned_empty) the upload runs at PCIe rate and never blocks the host
+    """
 
     def __init__(self, size, rank=0, world=1, **kw):
         self.rank, self.world = rank, world
+        self.size = size
+        self._kw = dict(kw)
         self.rend = VolumeRenderer(size, **kw)
+        self.resident = {}  # t -> VolumeRenderer holding frame t
 
     def my_frames(self, n_frames):
         return frames_for_rank(n_frames, self.rank, self.world)
 
+    def close(self):
+        for r in self.resident.values():
+            r.close()
+        self.resident = {}
+        self.rend.close()
+
+    # ---- resident playback ----
+    def preload(self, source, frames=None, device_ptrs=False):
+        """Make the owned frames resident.  source[t] -> (Nz, Ny, Nx) ndarray, or with device_ptrs=True a tuple
+        (device pointer, shape, dtype) of a C-order device array on this GPU."""
+        frames = self.my_frames(len(source)) if frames is None else frames
+        for t in frames:
+            r = VolumeRenderer(self.size, **self._kw)
+            if device_ptrs:
+                ptr, shape, dtype = source[t]
+                r.set_data_device(ptr, shape, dtype)
+                r.sync()
+            else:
+                r.set_data(source[t])
+            self.resident[t] = r
+        return frames
+
+    def _configure(self, r, modelView, settings):
+        for k, v in settings.items():
+            getattr(r, "set_" + k)(v)
+        if modelView is not None:
+            r.set_modelView(modelView)
+
+    def render_resident(self, t, modelView=None, method="max_project", **settings):
+        """Render resident frame t.  settings: projection=, max_val=, min_val=, gamma=, units=, ... (set_* names)."""
+        r = self.resident[t]
+        self._configure(r, modelView, settings)
+        r.render(method=method)
+        return r
+
+    # ---- streamed playback ----
+    def play(self, source, modelViews=None, frames=None, pinned=False, method="max_project", **settings):
+        """Generator over (t, renderer) for the owned frames of `source`; renderer.output* hold frame t.
+        pinned=True: source[t] are page-locked arrays (spimagine_b200.pinned_empty) that stay untouched while the
+        generator runs -- uploads are asynchronous at PCIe rate."""
+        frames = self.my_frames(len(source)) if frames is None else frames
+        r = self.rend
+        first = not hasattr(r, "dataImg")
+        for t in frames:
+            vol = source[t]
+            if first or tuple(vol.shape[::-1]) != r.dataImg.shape or vol.dtype != r.dataImg.dtype:
+                r.set_data(vol)
+                first = False
+            else:
+                r.update_data(vol, pinned=pinned)
+            self._configure(r, None if modelViews is None else modelViews[t], settings)
+            r.render(method=method)
+            yield t, r
+
     def render_frames(self, source, modelViews=None, **render_kw):
         """source[t] -> (Nz, Ny, Nx) ndarray.  Returns {t: image} for the frames this rank owns."""
         out = {}
-        first = True
-        for t in self.my_frames(len(source)):
-            vol = source[t]
-            if first:
-                self.rend.set_data(vol)
-                first = False
-            else:
-                self.rend.update_data(vol)
-            if modelViews is not None:
-                self.rend.set_modelView(modelViews[t])
-            self.rend.render(**render_kw)
-            out[t] = self.rend.output
+        for t, r in self.play(source, modelViews):
+            if render_kw:
+                r.render(**render_kw)
+            out[t] = np.array(r.output)
         return out

@@ -226,3 +226,45 @@ def test_ingest_paths_agree(dtype, layout):
     assert np.array_equal(rend2.sample_points(pos), b[idx[:, 0], idx[:, 1], idx[:, 2]].astype(np.float32))
     rend.close()
     rend2.close()
+
+
+# ----------------------------------------------------------------------------- timelapse playback
+def test_timelapse_player_resident_and_streamed():
+    """Frame sharding for 3D+t playback: every rank's player shows exactly its own time points, resident and
+    streamed (pageable and page-locked sources) playback equal a plain per-frame render."""
+    from spimagine_b200 import pinned_empty
+    from spimagine_b200.multigpu import TimelapsePlayer
+    T, shape = 7, (24, 40, 48)
+    source = [scenes.vol_g(0, np.uint16, seed=100, shape=shape, t=t) for t in range(T)]
+    cams = [scenes.gui_camera(0.2 * t, 3.6) for t in range(T)]
+    P = cams[0][1]
+    want = []
+    ref = _renderer((96, 80))
+    for t in range(T):
+        ref.set_data(source[t])
+        ref.set_projection(P)
+        ref.set_modelView(cams[t][0])
+        ref.render(maxVal=60000.)
+        want.append(ref.output.copy())
+    ref.close()
+    seen = []
+    for rank in range(3):
+        pl = TimelapsePlayer((96, 80), rank=rank, world=3)
+        mine = pl.my_frames(T)
+        assert mine == list(range(rank, T, 3))
+        assert pl.preload(source) == mine
+        for t in mine:
+            r = pl.render_resident(t, cams[t][0], projection=P, max_val=60000.)
+            assert np.array_equal(r.output, want[t])
+        got = {t: r.output.copy() for t, r in pl.play(source, [c[0] for c in cams], projection=P, max_val=60000.)}
+        assert sorted(got) == mine and all(np.array_equal(got[t], want[t]) for t in mine)
+        pinned = []
+        for t in range(T):
+            a = pinned_empty(shape, np.uint16)
+            a[...] = source[t]
+            pinned.append(a)
+        got = {t: r.output.copy() for t, r in pl.play(pinned, [c[0] for c in cams], pinned=True, projection=P, max_val=60000.)}
+        assert all(np.array_equal(got[t], want[t]) for t in mine)
+        seen += mine
+        pl.close()
+    assert sorted(seen) == list(range(T))
