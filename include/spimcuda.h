@@ -35,7 +35,8 @@ enum { SPV_F32 = 0, SPV_U16 = 1, SPV_U8 = 2 };
 /* result buffers: VolumeRenderer.buf / buf_alpha / buf_depth / buf_normals /
  * buf_occlusion, volumerender.py:185-193.  SPV_BUF_RAW is new: the un-windowed
  * ray maximum that the sort-last composite reduces across GPUs. */
-enum { SPV_BUF_OUT = 0, SPV_BUF_ALPHA = 1, SPV_BUF_DEPTH = 2, SPV_BUF_NORMALS = 3, SPV_BUF_OCC = 4, SPV_BUF_RAW = 5 };
+enum { SPV_BUF_OUT = 0, SPV_BUF_ALPHA = 1, SPV_BUF_DEPTH = 2, SPV_BUF_NORMALS = 3, SPV_BUF_OCC = 4, SPV_BUF_RAW = 5,
+       SPV_BUF_KPLANES = 6 /* int32 [2][h][w]: first sample > iso / first sample <= iso (sort-last iso surface) */ };
 
 /* sampler implementations */
 enum {
@@ -80,6 +81,11 @@ SPV_API int spv_set_volume_device(spv_ctx *ctx, const void *dev, int dtype, int 
  * whose trilinear footprint starts in slices [z0, z1) (the last slab also owns everything beyond). */
 SPV_API int spv_set_volume_slab(spv_ctx *ctx, const void *host, int on_device, int dtype, int nx, int ny, int gnz, int z0,
                         int z1);
+/* as spv_set_volume_slab with `halo` >= 1 slices either side: the pointer holds slices [max(z0-halo,0),
+ * min(z1+halo,gnz)).  Sort-last iso surfaces need 2 * dt * gamma^2 * gnz + one ray step of halo (the 12-tap gradient
+ * reaches +-2h along z, iso_kernel.cl:163-192); max projections need 1. */
+SPV_API int spv_set_volume_slab_halo(spv_ctx *ctx, const void *src, int on_device, int dtype, int nx, int ny, int gnz,
+                                     int z0, int z1, int halo);
 /* global min/max of the resident volume (replaces GLWidget._get_min_max, gui/glwidget.py:328-344) */
 SPV_API int spv_volume_minmax(spv_ctx *ctx, float *vmin, float *vmax);
 
@@ -159,6 +165,22 @@ enum {
   SPV_ISO_RAW_ONLY = 1  /* the iso_surface kernel alone, no blur / occlusion / shading passes */
 };
 SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p);
+
+/* ---- sort-last iso surface (new): every context holds one z-slab (+ halo) and the same camera.
+ *   1. spv_iso_slab_search   per pixel over the samples the slab owns: SPV_BUF_KPLANES = {first k with s_k > iso,
+ *                            first k with s_k <= iso} (INT_MAX: none)
+ *   2. the caller reduces SPV_BUF_KPLANES element-wise with MIN over all ranks (ncclMin on int32)
+ *   3. spv_iso_slab_resolve  the slab owning a pixel's crossing sample refines, takes the gradient and shades it into
+ *                            the 7 planes starting at SPV_BUF_OUT ([out|alpha|depth|occ = 0|normals(3)]); all other
+ *                            ranks write zeros there
+ *   4. the caller reduces those 7*w*h floats element-wise with SUM over all ranks (x + 0 = x: bit-exact)
+ *   5. spv_iso_slab_post     depth = INFINITY where nothing was hit, then the blur / occlusion / shading passes
+ * The result equals spv_render_iso on the whole volume bit for bit.  spv_iso_slab_check synchronises and reports a
+ * halo that was too small for the gradient taps. ---- */
+SPV_API int spv_iso_slab_search(spv_ctx *ctx, const spv_iso_params *p);
+SPV_API int spv_iso_slab_resolve(spv_ctx *ctx, const spv_iso_params *p);
+SPV_API int spv_iso_slab_post(spv_ctx *ctx, const spv_iso_params *p);
+SPV_API int spv_iso_slab_check(spv_ctx *ctx);
 
 /* ---- results: buf.get(), volumerender.py:388-390, 499-506 ---- */
 /* copies n floats (n = w*h, or 3*w*h for normals) to host memory; synchronises */

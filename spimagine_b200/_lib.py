@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libspimcuda.so")
 
 SPV_F32, SPV_U16, SPV_U8 = 0, 1, 2
-BUF_OUT, BUF_ALPHA, BUF_DEPTH, BUF_NORMALS, BUF_OCC, BUF_RAW = range(6)
+BUF_OUT, BUF_ALPHA, BUF_DEPTH, BUF_NORMALS, BUF_OCC, BUF_RAW, BUF_KPLANES = range(7)
 SAMPLER_TMU, SAMPLER_EXACT = 0, 1
 MIP_RAW_ONLY = 1
 ISO_RAW_ONLY = 1
@@ -53,6 +53,8 @@ SIGNATURES = {
     "spv_set_volume_device": (C.c_int, [_CTX, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "spv_set_volume_slab": (C.c_int, [_CTX, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int]),
+    "spv_set_volume_slab_halo": (C.c_int, [_CTX, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int]),
     "spv_volume_minmax": (C.c_int, [_CTX, _FP, _FP]),
     "spv_set_interp": (C.c_int, [_CTX, C.c_int]),
     "spv_set_sampler": (C.c_int, [_CTX, C.c_int]),
@@ -71,6 +73,10 @@ SIGNATURES = {
     "spv_comp_check": (C.c_int, [_CTX]),
     "spv_set_extra_slabs": (C.c_int, [_CTX, C.POINTER(_CTX), C.c_int]),
     "spv_render_iso": (C.c_int, [_CTX, C.POINTER(IsoParams)]),
+    "spv_iso_slab_search": (C.c_int, [_CTX, C.POINTER(IsoParams)]),
+    "spv_iso_slab_resolve": (C.c_int, [_CTX, C.POINTER(IsoParams)]),
+    "spv_iso_slab_post": (C.c_int, [_CTX, C.POINTER(IsoParams)]),
+    "spv_iso_slab_check": (C.c_int, [_CTX]),
     "spv_read": (C.c_int, [_CTX, C.c_int, _FP, C.c_size_t]),
     "spv_read_many": (C.c_int, [_CTX, _FP, _FP, _FP, _FP, _FP]),
     "spv_read_pinned": (C.c_int, [_CTX, C.c_int, C.POINTER(_FP)]),

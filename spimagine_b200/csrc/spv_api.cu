@@ -65,6 +65,7 @@ struct spv_ctx {
   float *peer_out[MAX_WORLD] = {nullptr};
   void *ipc_opened[MAX_WORLD][3] = {{nullptr}};
   unsigned comp_frame = 0;
+  unsigned *d_iso_err = nullptr;  // sort-last iso surface: raised when a slab's halo does not cover the gradient taps
   spv_ctx *extra[MAX_EXTRA_SLABS] = {nullptr};  // spv_set_extra_slabs: contexts whose slabs my slab renders march too
   int n_extra = 0;
   int last_method = 0;    // 0 = mip, 1 = iso
@@ -230,6 +231,8 @@ SPV_API int spv_create(int device, int width, int height, spv_ctx **out) {
   CC(cudaMalloc(&ctx->d_minmax, 2 * sizeof(float)));
   CC(cudaMalloc(&ctx->d_stats, 2 * sizeof(unsigned long long)));
   CC(cudaMalloc(&ctx->d_tile_counter, sizeof(unsigned)));
+  CC(cudaMalloc(&ctx->d_iso_err, sizeof(unsigned)));
+  CC(cudaMemset(ctx->d_iso_err, 0, sizeof(unsigned)));
 #undef CC
   int rc = alloc_buffers(ctx, width, height);
   if (rc) {
@@ -250,6 +253,7 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
   if (ctx->d_minmax) cudaFree(ctx->d_minmax);
   if (ctx->d_stats) cudaFree(ctx->d_stats);
   if (ctx->d_tile_counter) cudaFree(ctx->d_tile_counter);
+  if (ctx->d_iso_err) cudaFree(ctx->d_iso_err);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev_up_begin) cudaEventDestroy(ctx->ev_up_begin);
@@ -497,14 +501,15 @@ static int ensure_bricks(spv_ctx *ctx) {
 }
 
 static int set_volume_impl(spv_ctx *ctx, const void *src, bool on_device, int dtype, int nx, int ny, int gnz, int z0,
-                           int z1, bool slab) {
+                           int z1, bool slab, int halo = 1) {
   BIND();
   if (!src) return fail(ctx, SPV_EINVAL, "spv_set_volume: null data");
   if (dtype < 0 || dtype > 2) return fail(ctx, SPV_EINVAL, "spv_set_volume: dtype must be 0 (f32), 1 (u16) or 2 (u8)");
   if (nx <= 0 || ny <= 0 || gnz <= 0 || z0 < 0 || z1 > gnz || z0 >= z1)
     return fail(ctx, SPV_EINVAL, "spv_set_volume: bad extent");
-  const int z_lo = slab ? (z0 > 0 ? z0 - 1 : 0) : 0;
-  const int z_hi = slab ? (z1 < gnz ? z1 + 1 : gnz) : gnz;
+  if (halo < 1) return fail(ctx, SPV_EINVAL, "spv_set_volume_slab: the halo must be at least one slice");
+  const int z_lo = slab ? (z0 - halo > 0 ? z0 - halo : 0) : 0;
+  const int z_hi = slab ? (z1 + halo < gnz ? z1 + halo : gnz) : gnz;
   const int local_nz = z_hi - z_lo;
   // z-paired layered layout for integer volumes when asked for and the layer count allows it
   const int layout = (ctx->want_layout == LAYOUT_ZPAIR && dtype != SPV_F32 && local_nz <= 2048 && nx <= 32768 &&
@@ -542,6 +547,10 @@ SPV_API int spv_set_volume_device(spv_ctx *ctx, const void *dev, int dtype, int 
 SPV_API int spv_set_volume_slab(spv_ctx *ctx, const void *src, int on_device, int dtype, int nx, int ny, int gnz, int z0,
                         int z1) {
   return set_volume_impl(ctx, src, on_device != 0, dtype, nx, ny, gnz, z0, z1, true);
+}
+SPV_API int spv_set_volume_slab_halo(spv_ctx *ctx, const void *src, int on_device, int dtype, int nx, int ny, int gnz,
+                                     int z0, int z1, int halo) {
+  return set_volume_impl(ctx, src, on_device != 0, dtype, nx, ny, gnz, z0, z1, true, halo);
 }
 SPV_API int spv_update_volume(spv_ctx *ctx, const void *host) {
   BIND();
@@ -956,6 +965,94 @@ SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p) {
   return end_render(ctx);
 }
 
+// ---- sort-last iso surface ----------------------------------------------------------------------------------------
+static int iso_args(spv_ctx *ctx, const spv_iso_params *p, IsoArgs &a, const char *who) {
+  if (!p) return fail(ctx, SPV_EINVAL, "sort-last iso surface: null params");
+  if (!ctx->arr || !ctx->slab) return fail(ctx, SPV_ENODATA, "sort-last iso surface: set a slab with spv_set_volume_slab_halo first");
+  if (ctx->sampler != SPV_SAMPLER_TMU) return fail(ctx, SPV_EINVAL, "sort-last iso surface: needs the TMU sampler");
+  if (p->max_steps < 2) return fail(ctx, SPV_EINVAL, "sort-last iso surface: max_steps must be >= 2");
+  (void)who;
+  a.cam = ctx->cam;
+  a.vol = volume_of(ctx);
+  a.coarse = ctx->coarse;
+  a.cgx = ctx->cgx; a.cgy = ctx->cgy; a.cgz = ctx->cgz;
+  memcpy(a.box, p->box, sizeof a.box);
+  a.iso_val = p->iso_val; a.gamma = p->gamma; a.max_steps = p->max_steps;
+  a.tile_hit = ctx->d_tile_hit;
+  a.skip = ctx->skipping != 0;
+  a.width = ctx->width; a.height = ctx->height;
+  a.out = ctx->out(); a.alpha = ctx->alpha(); a.depth = ctx->depth(); a.normals = ctx->normals();
+  a.stats = ctx->stats_on ? ctx->d_stats : nullptr;
+  return 0;
+}
+
+SPV_API int spv_iso_slab_search(spv_ctx *ctx, const spv_iso_params *p) {
+  BIND();
+  IsoArgs a;
+  int rc = iso_args(ctx, p, a, "search");
+  if (rc) return rc;
+  if (a.skip) {
+    rc = ensure_bricks(ctx);
+    if (rc) return rc;
+  }
+  rc = begin_render(ctx);
+  if (rc) return rc;
+  int *k = (int *)ctx->tmp_vec();
+  const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
+  CU(launch_iso_slab(a, fmt_of(ctx), linear, 0, k, k + ctx->n(), ctx->occ(), ctx->d_iso_err, ctx->stream));
+  ctx->launches += 1;
+  ctx->last_method = 1;
+  return end_render(ctx);
+}
+
+SPV_API int spv_iso_slab_resolve(spv_ctx *ctx, const spv_iso_params *p) {
+  BIND();
+  IsoArgs a;
+  int rc = iso_args(ctx, p, a, "resolve");
+  if (rc) return rc;
+  a.stats = nullptr;
+  int *k = (int *)ctx->tmp_vec();
+  const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
+  CU(launch_iso_slab(a, fmt_of(ctx), linear, 1, k, k + ctx->n(), ctx->occ(), ctx->d_iso_err, ctx->stream));
+  ctx->launches += 1;
+  return 0;
+}
+
+SPV_API int spv_iso_slab_post(spv_ctx *ctx, const spv_iso_params *p) {
+  BIND();
+  IsoArgs a;
+  int rc = iso_args(ctx, p, a, "post");
+  if (rc) return rc;
+  if (p->occ_n_points < 0 || p->occ_radius < 0) return fail(ctx, SPV_EINVAL, "sort-last iso surface: negative occlusion parameter");
+  int *k = (int *)ctx->tmp_vec();
+  CU(launch_iso_slab(a, fmt_of(ctx), true, 2, k, k + ctx->n(), ctx->occ(), ctx->d_iso_err, ctx->stream));
+  ctx->launches += 1;
+  if (!(p->flags & SPV_ISO_RAW_ONLY)) {
+    CU(launch_conv(ctx->normals(), ctx->tmp_vec(), ctx->width, ctx->height, 3, conv_weights(7, -5.f), ctx->stream));
+    CU(launch_occlusion(ctx->occ(), ctx->width, ctx->height, p->occ_radius, p->occ_n_points, ctx->depth(), a.tile_hit,
+                        ctx->stream));
+    CU(launch_conv(ctx->occ(), ctx->tmp(), ctx->width, ctx->height, 1, conv_weights(5, -10.f), ctx->stream));
+    CU(launch_shading(ctx->out(), ctx->width, ctx->height, ctx->cam, p->occ_strength, ctx->normals(), ctx->depth(),
+                      ctx->occ(), ctx->stream));
+    ctx->launches += 6;
+  }
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  return 0;
+}
+
+SPV_API int spv_iso_slab_check(spv_ctx *ctx) {
+  BIND();
+  unsigned e = 0;
+  CU(cudaMemcpyAsync(&e, ctx->d_iso_err, sizeof e, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (e) {
+    CU(cudaMemsetAsync(ctx->d_iso_err, 0, sizeof e, ctx->stream));
+    return fail(ctx, SPV_EINVAL, "sort-last iso surface: the slab's halo does not cover the gradient taps of a surface "
+                                 "pixel (2 * dt * gamma^2 * Nz + one ray step slices are needed): upload with a larger halo");
+  }
+  return 0;
+}
+
 static float *buf_of(spv_ctx *c, int which, size_t *count) {
   const size_t n = c->n();
   *count = n;
@@ -965,6 +1062,7 @@ static float *buf_of(spv_ctx *c, int which, size_t *count) {
     case SPV_BUF_DEPTH: return c->depth();
     case SPV_BUF_OCC: return c->occ();
     case SPV_BUF_RAW: return c->raw();
+    case SPV_BUF_KPLANES: *count = 2 * n; return c->tmp_vec();  // int32 [2][h][w], sort-last iso surface
     case SPV_BUF_NORMALS: *count = 3 * n; return c->normals();
     default: return nullptr;
   }

@@ -229,6 +229,33 @@ __device__ __forceinline__ float sample(const Volume &V, float px, float py, flo
   return EXACT ? sample_exact<FMT, LINEAR>(V, px, py, pz) : sample_tmu<FMT, LINEAR>(V, px, py, pz);
 }
 
+// ---- slab ownership (sort-last rendering) ----
+// clamped slice index the footprint of the sample at unnormalised coordinate w(k) = w0 + k*dw starts in
+__device__ __forceinline__ float slice_of_k(const Volume &V, float w0, float dw, int k) {
+  return fminf(fmaxf(floorf(fmaf((float)k, dw, w0) - 0.5f), 0.f), (float)(V.nz - 1));
+}
+// [ka, kb) = the samples k in [0, S) whose slice lies in [z0, z1).  The slice index is monotone in k (fma,
+// subtraction and floor all are), so the owned samples form one interval: two binary searches with the exact
+// predicate.
+__device__ __forceinline__ void owned_interval_w(const Volume &V, float w0, float dw, int S, int &ka, int &kb) {
+  const float z0 = (float)V.z0, z1 = (float)V.z1;
+  const bool up = dw >= 0.f;  // slice index non-decreasing in k
+  int lo = 0, hi = S;
+  while (lo < hi) {  // first k with (up ? slice >= z0 : slice < z1)
+    const int mid = (lo + hi) >> 1;
+    const float s = slice_of_k(V, w0, dw, mid);
+    if (up ? (s >= z0) : (s < z1)) hi = mid; else lo = mid + 1;
+  }
+  ka = lo;
+  hi = S;
+  while (lo < hi) {  // first k >= ka with (up ? slice >= z1 : slice < z0)
+    const int mid = (lo + hi) >> 1;
+    const float s = slice_of_k(V, w0, dw, mid);
+    if (up ? (s >= z1) : (s < z0)) hi = mid; else lo = mid + 1;
+  }
+  kb = lo;
+}
+
 // brick grid addressing: x fastest
 __device__ __forceinline__ float2 brick_at(const Volume &V, int bx, int by, int bz) {
   return __ldg(V.bricks + ((size_t)bz * V.gy + by) * V.gx + bx);

@@ -109,20 +109,120 @@ __global__ void __launch_bounds__(128) iso_kernel(const IsoArgs a) {
 }
 
 // -------------------------------------------------------------------------------------------------------------
-// iso_fast_kernel: the texture-unit path.  Same first-crossing rule, bracket refinement and 12-tap gradient, but
+// The texture-unit path.  Same first-crossing rule, bracket refinement and 12-tap gradient as iso_kernel, but
 //   * sample k sits at pos0 + k*delta (one fma per axis, unnormalised texel coordinates) instead of being
 //     accumulated, so that
 //   * the coarse search fetches BATCH samples at a time (independent fetches in flight instead of one
 //     fetch -> compare -> branch round trip per sample) and then looks for the first crossing in the batch;
 //     at most BATCH-1 samples behind the crossing are fetched in vain,
 //   * the ten refinement samples are fetched together as well.
-template <int FMT, bool LINEAR, bool SKIP>
-__global__ void __launch_bounds__(128) iso_fast_kernel(const IsoArgs a) {
-  constexpr int BATCH = 8;
+// The per-ray state is shared by the single-GPU kernel and the two sort-last kernels (search / resolve), which
+// therefore evaluate bit-identical expressions.
+struct IsoRay {
+  bool hit;                // the ray meets the box
+  float tnear, dt;
+  v4 direc, pos0, delta_pos;
+  float u0, v0, w0, du, dv, dw;  // unnormalised texel coordinates of sample t: u0 + t*du
+};
+
+__device__ __forceinline__ IsoRay iso_ray(const IsoArgs &a, unsigned x, unsigned y, bool inb) {
+  IsoRay q;
+  Ray r = make_ray(x, y, a.width, a.height, a.cam, a.box);
+  q.hit = r.hit && inb;
+  q.tnear = r.tnear;
+  if (q.tnear < 0.0f) q.tnear = 0.0f;
+  q.direc = r.direc;
+  q.dt = 1.f * (r.tfar - q.tnear) / ((float)a.max_steps - 1.f);
+  q.delta_pos = scl4(.5f * q.dt, r.direc);
+  q.pos0 = scl4(0.5f, add4(sadd4(1.f, r.orig), scl4(q.tnear, r.direc)));
+  const Volume &V = a.vol;
+  q.u0 = q.pos0.x * V.fnx; q.v0 = q.pos0.y * V.fny; q.w0 = q.pos0.z * V.fnz;
+  q.du = q.delta_pos.x * V.fnx; q.dv = q.delta_pos.y * V.fny; q.dw = q.delta_pos.z * V.fnz;
+  return q;
+}
+
+template <int FMT, bool LINEAR>
+__device__ __forceinline__ float iso_at(const Volume &V, const IsoRay &q, float t) {
+  return sample_tmu_uvw<FMT, LINEAR>(V, fmaf(t, q.du, q.u0), fmaf(t, q.dv, q.v0), fmaf(t, q.dw, q.w0));
+}
+
+// exact empty-space test for sample t: a sample whose footprint lies in a cell with max <= iso cannot be "> iso",
+// one in a cell with min > iso cannot be "<= iso".  want_greater: are we looking for a sample > iso?
+__device__ __forceinline__ bool iso_cell_may_hold(const IsoArgs &a, const IsoRay &q, float t, bool want_greater) {
+  const Volume &V = a.vol;
+  const float cx0 = q.u0 - 0.5f, cy0 = q.v0 - 0.5f, cz0 = q.w0 - 0.5f - (float)V.z_lo;
+  const int ix = __float2int_rd(fmaf(t, q.du, cx0)), iy = __float2int_rd(fmaf(t, q.dv, cy0)),
+            iz = __float2int_rd(fmaf(t, q.dw, cz0));
+  const int cx = min(max(ix >> (BRICK_SHIFT + 2), 0), a.cgx - 1), cy = min(max(iy >> (BRICK_SHIFT + 2), 0), a.cgy - 1),
+            cz = min(max(iz >> (BRICK_SHIFT + 2), 0), a.cgz - 1);
+  const float2 c = __ldg(a.coarse + ((size_t)cz * a.cgy + cy) * a.cgx + cx);
+  bool need = want_greater ? (c.y > a.iso_val) : !(c.x > a.iso_val);
+  if (need) {
+    const int bx = min(max(ix >> BRICK_SHIFT, 0), V.gx - 1), by = min(max(iy >> BRICK_SHIFT, 0), V.gy - 1),
+              bz = min(max(iz >> BRICK_SHIFT, 0), V.gz - 1);
+    const float2 b = brick_at(V, bx, by, bz);
+    need = want_greater ? (b.y > a.iso_val) : !(b.x > a.iso_val);
+  }
+  return need;
+}
+
+// bracket refinement, 12-tap gradient and Phong shading at crossing sample i (iso_kernel.cl:140-215)
+template <int FMT, bool LINEAR>
+__device__ __forceinline__ void iso_resolve(const IsoArgs &a, const IsoRay &q, int i, bool isGreater, float &t_hit,
+                                            v4 &normal, float &colVal) {
+  const Volume &V = a.vol;
+  const float isoVal = a.iso_val;
+  t_hit = q.tnear + (float)i * q.dt;
+  const int maxBisect = 10;
+  const float dt2 = q.dt / (float)maxBisect;
+  float v[maxBisect];
+#pragma unroll
+  for (int j = 0; j < maxBisect; ++j) v[j] = iso_at<FMT, LINEAR>(V, q, (float)(i - 1) + (float)j / (float)maxBisect);
+  int J = maxBisect;
+#pragma unroll
+  for (int j = maxBisect - 1; j >= 0; --j)
+    if ((v[j] > isoVal) != isGreater) J = j + 1;
+  for (int j = 0; j < J; ++j) t_hit += dt2;  // accumulated like the reference does
+  // where the reference's `pos` stands after the refinement loop, in normalised coordinates
+  const float ts = (float)(i - 1) + (float)J / (float)maxBisect;
+  const float px = fmaf(ts, q.delta_pos.x, q.pos0.x), py = fmaf(ts, q.delta_pos.y, q.pos0.y),
+              pz = fmaf(ts, q.delta_pos.z, q.pos0.z);
+  v4 light = mk4(2.f, -1.f, -2.f, 0.f);
+  const float c_ambient = .3f, c_diffuse = .4f, c_specular = .3f;
+  light = mult(a.cam.invM, light);
+  light = normalize4(light);
+  float h = q.dt;
+  h *= (a.gamma * a.gamma);
+  const float h2 = 2.f * h;
+#define SPV_S(dx, dy, dz) sample_tmu<FMT, LINEAR>(V, px + (dx), py + (dy), pz + (dz))
+  const float xa = SPV_S(h, 0.f, 0.f), xb = SPV_S(-h, 0.f, 0.f), xc = SPV_S(h2, 0.f, 0.f), xd = SPV_S(-h2, 0.f, 0.f);
+  const float ya = SPV_S(0.f, h, 0.f), yb = SPV_S(0.f, -h, 0.f), yc = SPV_S(0.f, h2, 0.f), yd = SPV_S(0.f, -h2, 0.f);
+  const float za = SPV_S(0.f, 0.f, h), zb = SPV_S(0.f, 0.f, -h), zc = SPV_S(0.f, 0.f, h2), zd = SPV_S(0.f, 0.f, -h2);
+#undef SPV_S
+  normal.x = 2.f * xa - 2.f * xb + xc - xd;
+  normal.y = 2.f * ya - 2.f * yb + yc - yd;
+  normal.z = za - zb + zc - zd;
+  normal.w = 0.f;
+  normal = scl4(1.f - (float)(2 * (int)isGreater), normalize4(normal));
+  const v4 reflect = sub4(scl4(2.f * dot4(light, normal), normal), light);
+  const float diffuse = fmaxf(0.f, dot4(light, normal));
+  const float specular = powf(fmaxf(0.f, dot4(normalize4(reflect), normalize4(q.direc))), 10.f);
+  colVal = c_ambient + c_diffuse * diffuse + (diffuse > 0.f ? 1.f : 0.f) * c_specular * specular;
+}
+
+__device__ __forceinline__ void tile_pixel(unsigned &x, unsigned &y) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
   const int ly = ((lane >> 1) & 1) | ((lane >> 2) & 2);
-  const unsigned x = blockIdx.x * 16 + (warp & 1) * 8 + lx, y = blockIdx.y * 8 + (warp >> 1) * 4 + ly;
+  x = blockIdx.x * 16 + (warp & 1) * 8 + lx;
+  y = blockIdx.y * 8 + (warp >> 1) * 4 + ly;
+}
+
+template <int FMT, bool LINEAR, bool SKIP>
+__global__ void __launch_bounds__(128) iso_fast_kernel(const IsoArgs a) {
+  constexpr int BATCH = 8;
+  unsigned x, y;
+  tile_pixel(x, y);
   const unsigned Nx = a.width, Ny = a.height;
   const bool inb = x < Nx && y < Ny;
   const size_t p = x + (size_t)Nx * y;
@@ -130,54 +230,29 @@ __global__ void __launch_bounds__(128) iso_fast_kernel(const IsoArgs a) {
   const float INF = __int_as_float(0x7f800000);
   unsigned nfetch = 0;
 
-  Ray r = make_ray(x, y, Nx, Ny, a.cam, a.box);
-  r.hit = r.hit && inb;
+  const IsoRay q = iso_ray(a, x, y, inb);
   bool hitIso = false;
-  float tnear = r.tnear, t_hit = INF;
+  float t_hit = INF;
   v4 normal = mk4(0.f, 0.f, 0.f, 0.f);
   float colVal = 0.f;
-  if (r.hit) {
-    const v4 direc = r.direc;
-    if (tnear < 0.0f) tnear = 0.0f;
+  if (q.hit) {
     const float isoVal = a.iso_val;
     const int maxSteps = a.max_steps;
-    const float dt = 1.f * (r.tfar - tnear) / ((float)maxSteps - 1.f);
-    const v4 delta_pos = scl4(.5f * dt, direc);
-    const v4 pos0 = scl4(0.5f, add4(sadd4(1.f, r.orig), scl4(tnear, direc)));
-    const float u0 = pos0.x * V.fnx, v0 = pos0.y * V.fny, w0 = pos0.z * V.fnz;
-    const float du = delta_pos.x * V.fnx, dv = delta_pos.y * V.fny, dw = delta_pos.z * V.fnz;
-#define SPV_AT(t) sample_tmu_uvw<FMT, LINEAR>(V, fmaf((t), du, u0), fmaf((t), dv, v0), fmaf((t), dw, w0))
-    const bool isGreater = SPV_AT(0.f) > isoVal;
+    const bool isGreater = iso_at<FMT, LINEAR>(V, q, 0.f) > isoVal;
     int i = maxSteps;
-    // Empty-space skipping (exact): a sample whose footprint lies in a cell with max <= iso cannot be "> iso", one
-    // in a cell with min > iso cannot be "<= iso"; such a sample cannot be the first crossing and is not fetched.
-    // Coarse cells (32^3 texels) first, the 8^3 brick only where the coarse cell straddles the threshold.
-    const float cx0 = u0 - 0.5f, cy0 = v0 - 0.5f, cz0 = w0 - 0.5f - (float)V.z_lo;
+    // Empty-space skipping (exact): samples that cannot be the first crossing are not fetched.  Coarse cells
+    // (32^3 texels) first, the 8^3 brick only where the coarse cell straddles the threshold.
     for (int k0 = 1; k0 < maxSteps && !hitIso; k0 += BATCH) {
       float v[BATCH];
       bool need[BATCH];
 #pragma unroll
       for (int j = 0; j < BATCH; ++j) {
         const float t = (float)min(k0 + j, maxSteps - 1);
-        need[j] = true;
-        if (SKIP) {
-          const int ix = __float2int_rd(fmaf(t, du, cx0)), iy = __float2int_rd(fmaf(t, dv, cy0)),
-                    iz = __float2int_rd(fmaf(t, dw, cz0));
-          const int cx = min(max(ix >> (BRICK_SHIFT + 2), 0), a.cgx - 1), cy = min(max(iy >> (BRICK_SHIFT + 2), 0), a.cgy - 1),
-                    cz = min(max(iz >> (BRICK_SHIFT + 2), 0), a.cgz - 1);
-          const float2 c = __ldg(a.coarse + ((size_t)cz * a.cgy + cy) * a.cgx + cx);
-          need[j] = isGreater ? !(c.x > isoVal) : (c.y > isoVal);
-          if (need[j]) {
-            const int bx = min(max(ix >> BRICK_SHIFT, 0), V.gx - 1), by = min(max(iy >> BRICK_SHIFT, 0), V.gy - 1),
-                      bz = min(max(iz >> BRICK_SHIFT, 0), V.gz - 1);
-            const float2 b = brick_at(V, bx, by, bz);
-            need[j] = isGreater ? !(b.x > isoVal) : (b.y > isoVal);
-          }
-        }
+        need[j] = SKIP ? iso_cell_may_hold(a, q, t, !isGreater) : true;
       }
 #pragma unroll
       for (int j = 0; j < BATCH; ++j) {
-        v[j] = need[j] ? SPV_AT((float)min(k0 + j, maxSteps - 1)) : (isGreater ? INF : -INF);
+        v[j] = need[j] ? iso_at<FMT, LINEAR>(V, q, (float)min(k0 + j, maxSteps - 1)) : (isGreater ? INF : -INF);
         nfetch += need[j];
       }
 #pragma unroll
@@ -188,49 +263,13 @@ __global__ void __launch_bounds__(128) iso_fast_kernel(const IsoArgs a) {
         }
     }
     if (hitIso) {
-      t_hit = tnear + (float)i * dt;
-      const int maxBisect = 10;
-      const float dt2 = dt / (float)maxBisect;
-      float v[maxBisect];
-#pragma unroll
-      for (int j = 0; j < maxBisect; ++j) v[j] = SPV_AT((float)(i - 1) + (float)j / (float)maxBisect);
-      int J = maxBisect;
-#pragma unroll
-      for (int j = maxBisect - 1; j >= 0; --j)
-        if ((v[j] > isoVal) != isGreater) J = j + 1;
-      for (int j = 0; j < J; ++j) t_hit += dt2;  // accumulated like the reference does
-      nfetch += maxBisect;
-      // where the reference's `pos` stands after the refinement loop, in normalised coordinates
-      const float ts = (float)(i - 1) + (float)J / (float)maxBisect;
-      const float px = fmaf(ts, delta_pos.x, pos0.x), py = fmaf(ts, delta_pos.y, pos0.y), pz = fmaf(ts, delta_pos.z, pos0.z);
-      v4 light = mk4(2.f, -1.f, -2.f, 0.f);
-      const float c_ambient = .3f, c_diffuse = .4f, c_specular = .3f;
-      light = mult(a.cam.invM, light);
-      light = normalize4(light);
-      float h = dt;
-      h *= (a.gamma * a.gamma);
-      const float h2 = 2.f * h;
-#define SPV_S(dx, dy, dz) sample_tmu<FMT, LINEAR>(V, px + (dx), py + (dy), pz + (dz))
-      const float xa = SPV_S(h, 0.f, 0.f), xb = SPV_S(-h, 0.f, 0.f), xc = SPV_S(h2, 0.f, 0.f), xd = SPV_S(-h2, 0.f, 0.f);
-      const float ya = SPV_S(0.f, h, 0.f), yb = SPV_S(0.f, -h, 0.f), yc = SPV_S(0.f, h2, 0.f), yd = SPV_S(0.f, -h2, 0.f);
-      const float za = SPV_S(0.f, 0.f, h), zb = SPV_S(0.f, 0.f, -h), zc = SPV_S(0.f, 0.f, h2), zd = SPV_S(0.f, 0.f, -h2);
-#undef SPV_S
-      nfetch += 12;
-      normal.x = 2.f * xa - 2.f * xb + xc - xd;
-      normal.y = 2.f * ya - 2.f * yb + yc - yd;
-      normal.z = za - zb + zc - zd;
-      normal.w = 0.f;
-      normal = scl4(1.f - (float)(2 * (int)isGreater), normalize4(normal));
-      const v4 reflect = sub4(scl4(2.f * dot4(light, normal), normal), light);
-      const float diffuse = fmaxf(0.f, dot4(light, normal));
-      const float specular = powf(fmaxf(0.f, dot4(normalize4(reflect), normalize4(direc))), 10.f);
-      colVal = c_ambient + c_diffuse * diffuse + (diffuse > 0.f ? 1.f : 0.f) * c_specular * specular;
+      iso_resolve<FMT, LINEAR>(a, q, i, isGreater, t_hit, normal, colVal);
+      nfetch += 22;
     }
-#undef SPV_AT
   }
   if (inb) {
     a.out[p] = hitIso ? colVal : 0.f;
-    a.alpha[p] = hitIso ? tnear : 0.f;
+    a.alpha[p] = hitIso ? q.tnear : 0.f;
     a.depth[p] = hitIso ? t_hit : INF;
     a.normals[3 * p + 0] = normal.x;
     a.normals[3 * p + 1] = normal.y;
@@ -240,8 +279,161 @@ __global__ void __launch_bounds__(128) iso_fast_kernel(const IsoArgs a) {
   const int any = __syncthreads_or(hitIso ? 1 : 0);
   if (threadIdx.x == 0 && a.tile_hit) a.tile_hit[blockIdx.y * gridDim.x + blockIdx.x] = (unsigned char)(any != 0);
   if (a.stats) {
-    atomicAdd(a.stats + 0, r.hit ? 1ull : 0ull);
+    atomicAdd(a.stats + 0, q.hit ? 1ull : 0ull);
     atomicAdd(a.stats + 1, (unsigned long long)nfetch);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// Sort-last iso surface: every rank holds one z-slab (+ halo) of the volume and marches the SAME rays.
+//   iso_slab_search   per pixel, over the samples this slab owns: k1 = first k with s_k > iso, k0 = first k with
+//                     s_k <= iso (INT_MAX if none).  After an element-wise MIN over the ranks, s_0 > iso <=> k1 == 0
+//                     and the first crossing is i = (k1 == 0) ? k0 : k1 -- exactly the sample the single-GPU search
+//                     stops at.  Samples whose brick bounds decide the comparison are classified without a fetch.
+//   iso_slab_resolve  the rank owning sample i refines the bracket, takes the gradient and shades (it needs
+//                     2 h N_z + one ray step of halo slices; checked per pixel, *err is raised if the resident
+//                     slices do not cover the taps); every other rank writes zeros, so that an element-wise SUM over
+//                     the ranks assembles the planes bit for bit.
+//   iso_slab_fix      after the SUM: depth = INFINITY on pixels without a crossing, tile flags for the occlusion pass
+constexpr int K_NONE = 0x7fffffff;
+
+template <int FMT, bool LINEAR, bool SKIP>
+__global__ void __launch_bounds__(128) iso_slab_search_kernel(const IsoArgs a, int *__restrict__ k1_plane,
+                                                              int *__restrict__ k0_plane) {
+  constexpr int BATCH = 8;
+  unsigned x, y;
+  tile_pixel(x, y);
+  const bool inb = x < (unsigned)a.width && y < (unsigned)a.height;
+  const Volume &V = a.vol;
+  const IsoRay q = iso_ray(a, x, y, inb);
+  int k1 = K_NONE, k0 = K_NONE;
+  unsigned nfetch = 0;
+  if (q.hit) {
+    const float isoVal = a.iso_val;
+    int ka, kb;
+    owned_interval_w(V, q.w0, q.dw, a.max_steps, ka, kb);
+    for (int kk = ka; kk < kb && (k1 == K_NONE || k0 == K_NONE); kk += BATCH) {
+      float v[BATCH];
+      int cls[BATCH];  // 0: fetch, 1: certainly > iso, 2: certainly <= iso, 3: not a sample
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) {
+        const int k = kk + j;
+        cls[j] = k < kb ? 0 : 3;
+        if (SKIP && k < kb) {
+          const float t = (float)k;
+          if (!iso_cell_may_hold(a, q, t, true)) cls[j] = 2;        // cell max <= iso
+          else if (!iso_cell_may_hold(a, q, t, false)) cls[j] = 1;  // cell min > iso
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) {
+        v[j] = cls[j] == 0 ? iso_at<FMT, LINEAR>(V, q, (float)(kk + j)) : 0.f;
+        nfetch += cls[j] == 0;
+      }
+#pragma unroll
+      for (int j = BATCH - 1; j >= 0; --j) {
+        if (cls[j] == 3) continue;
+        const bool greater = cls[j] == 0 ? (v[j] > isoVal) : (cls[j] == 1);
+        if (greater) k1 = min(k1, kk + j); else k0 = min(k0, kk + j);
+      }
+    }
+  }
+  if (inb) {
+    const size_t p = x + (size_t)a.width * y;
+    k1_plane[p] = k1;
+    k0_plane[p] = k0;
+  }
+  if (a.stats) {
+    atomicAdd(a.stats + 0, q.hit ? 1ull : 0ull);
+    atomicAdd(a.stats + 1, (unsigned long long)nfetch);
+  }
+}
+
+template <int FMT, bool LINEAR>
+__global__ void __launch_bounds__(128) iso_slab_resolve_kernel(const IsoArgs a, const int *__restrict__ k1_plane,
+                                                               const int *__restrict__ k0_plane, float *__restrict__ occ,
+                                                               unsigned *err) {
+  unsigned x, y;
+  tile_pixel(x, y);
+  const bool inb = x < (unsigned)a.width && y < (unsigned)a.height;
+  if (!inb) return;
+  const size_t p = x + (size_t)a.width * y;
+  const Volume &V = a.vol;
+  const int k1 = k1_plane[p], k0 = k0_plane[p];
+  const bool isGreater = k1 == 0;
+  const int i = isGreater ? k0 : k1;
+  float colVal = 0.f, t_hit = 0.f, tn = 0.f;
+  v4 normal = mk4(0.f, 0.f, 0.f, 0.f);
+  if (i != K_NONE) {
+    const IsoRay q = iso_ray(a, x, y, true);
+    const float s = slice_of_k(V, q.w0, q.dw, i);
+    if (s >= (float)V.z0 && s < (float)V.z1) {  // this slab owns the crossing sample
+      // slices the refinement samples (t in [i-1, i)) and the gradient taps (+-2h along z around them) touch
+      const float wa = fmaf((float)(i - 1), q.dw, q.w0), wb = fmaf((float)i, q.dw, q.w0);
+      const float h2w = 2.f * fabsf(q.dt * (a.gamma * a.gamma)) * V.fnz;
+      const float wmin = fminf(wa, wb) - h2w - 0.5f, wmax = fmaxf(wa, wb) + h2w - 0.5f;
+      const float lo_need = fmaxf(floorf(wmin) - 1.f, 0.f), hi_need = fminf(floorf(wmax) + 2.f, (float)(V.nz - 1));
+      if (lo_need < (float)V.z_lo || hi_need > (float)(V.z_lo + V.local_nz - 1)) atomicExch(err, 1u);
+      iso_resolve<FMT, LINEAR>(a, q, i, isGreater, t_hit, normal, colVal);
+      tn = q.tnear;
+    }
+  }
+  a.out[p] = colVal;
+  a.alpha[p] = tn;
+  a.depth[p] = t_hit;
+  occ[p] = 0.f;
+  a.normals[3 * p + 0] = normal.x;
+  a.normals[3 * p + 1] = normal.y;
+  a.normals[3 * p + 2] = normal.z;
+}
+
+__global__ void __launch_bounds__(128) iso_slab_fix_kernel(int width, int height, const int *__restrict__ k1_plane,
+                                                           const int *__restrict__ k0_plane, float *__restrict__ depth,
+                                                           unsigned char *tile_hit) {
+  unsigned x, y;
+  tile_pixel(x, y);
+  const bool inb = x < (unsigned)width && y < (unsigned)height;
+  bool hit = false;
+  if (inb) {
+    const size_t p = x + (size_t)width * y;
+    const int k1 = k1_plane[p], k0 = k0_plane[p];
+    hit = (k1 == 0 ? k0 : k1) != K_NONE;
+    if (!hit) depth[p] = __int_as_float(0x7f800000);
+  }
+  const int any = __syncthreads_or(hit ? 1 : 0);
+  if (threadIdx.x == 0 && tile_hit) tile_hit[blockIdx.y * gridDim.x + blockIdx.x] = (unsigned char)(any != 0);
+}
+
+template <int FMT>
+static cudaError_t launch_iso_slab_dt(const IsoArgs &a, bool linear, int phase, int *k1, int *k0, float *occ,
+                                      unsigned *err, cudaStream_t st) {
+  dim3 grid((a.width + 15) / 16, (a.height + 7) / 8), block(128);
+  if (phase == 0) {
+    if (a.skip) {
+      if (linear) iso_slab_search_kernel<FMT, true, true><<<grid, block, 0, st>>>(a, k1, k0);
+      else iso_slab_search_kernel<FMT, false, true><<<grid, block, 0, st>>>(a, k1, k0);
+    } else {
+      if (linear) iso_slab_search_kernel<FMT, true, false><<<grid, block, 0, st>>>(a, k1, k0);
+      else iso_slab_search_kernel<FMT, false, false><<<grid, block, 0, st>>>(a, k1, k0);
+    }
+  } else if (phase == 1) {
+    if (linear) iso_slab_resolve_kernel<FMT, true><<<grid, block, 0, st>>>(a, k1, k0, occ, err);
+    else iso_slab_resolve_kernel<FMT, false><<<grid, block, 0, st>>>(a, k1, k0, occ, err);
+  } else {
+    iso_slab_fix_kernel<<<grid, block, 0, st>>>(a.width, a.height, k1, k0, a.depth, a.tile_hit);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_iso_slab(const IsoArgs &a, int dtype, bool linear, int phase, int *k1, int *k0, float *occ,
+                            unsigned *err, cudaStream_t st) {
+  switch (dtype) {  // FMT = dtype + 3 * layout
+    case 0: return launch_iso_slab_dt<0>(a, linear, phase, k1, k0, occ, err, st);
+    case 1: return launch_iso_slab_dt<1>(a, linear, phase, k1, k0, occ, err, st);
+    case 2: return launch_iso_slab_dt<2>(a, linear, phase, k1, k0, occ, err, st);
+    case 4: return launch_iso_slab_dt<4>(a, linear, phase, k1, k0, occ, err, st);
+    case 5: return launch_iso_slab_dt<5>(a, linear, phase, k1, k0, occ, err, st);
+    default: return cudaErrorInvalidValue;
   }
 }
 

@@ -80,6 +80,9 @@ cudaError_t launch_texrate_probe(const Volume &V, int dtype, bool linear, int bl
                                  cudaStream_t st);
 
 cudaError_t launch_iso(const IsoArgs &a, int dtype, bool linear, bool exact, bool stats, cudaStream_t st);
+// sort-last iso surface: phase 0 = search (writes k1 / k0), 1 = resolve (reads them), 2 = fix-up after the SUM
+cudaError_t launch_iso_slab(const IsoArgs &a, int dtype, bool linear, int phase, int *k1, int *k0, float *occ,
+                            unsigned *err, cudaStream_t st);
 // buf -> tmp (x pass), tmp -> buf (y pass); ncomp = 1 (conv_x/conv_y) or 3 (conv_vec_x/conv_vec_y)
 cudaError_t launch_conv(float *buf, float *tmp, int width, int height, int ncomp, const ConvWeights &w,
                         cudaStream_t st);

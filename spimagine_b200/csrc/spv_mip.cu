@@ -100,29 +100,9 @@ __device__ __forceinline__ bool owns_k(const Volume &V, const Marcher &m, float 
   return kf >= (float)V.z0 && kf < (float)V.z1;
 }
 
-// clamped slice index the footprint of sample k starts in
-__device__ __forceinline__ float slice_of_k(const Volume &V, const Marcher &m, int k) {
-  return fminf(fmaxf(floorf(fmaf((float)k, m.dw, m.w0) - 0.5f), 0.f), (float)(V.nz - 1));
-}
-// [ka, kb) = the samples k in [0, S) with slice_of_k in [z0, z1)  (same predicate as owns_k)
+// [ka, kb) = the samples k in [0, S) this slab owns
 __device__ __forceinline__ void owned_interval(const Volume &V, const Marcher &m, int S, int &ka, int &kb) {
-  const float z0 = (float)V.z0, z1 = (float)V.z1;
-  const bool up = m.dw >= 0.f;  // slice index non-decreasing in k
-  // first k whose slice is past the near bound / past the far bound, in marching direction
-  int lo = 0, hi = S;
-  while (lo < hi) {  // first k with (up ? slice >= z0 : slice < z1)
-    const int mid = (lo + hi) >> 1;
-    const float s = slice_of_k(V, m, mid);
-    if (up ? (s >= z0) : (s < z1)) hi = mid; else lo = mid + 1;
-  }
-  ka = lo;
-  hi = S;
-  while (lo < hi) {  // first k >= ka with (up ? slice >= z1 : slice < z0)
-    const int mid = (lo + hi) >> 1;
-    const float s = slice_of_k(V, m, mid);
-    if (up ? (s >= z1) : (s < z0)) hi = mid; else lo = mid + 1;
-  }
-  kb = lo;
+  owned_interval_w(V, m.w0, m.dw, S, ka, kb);
 }
 
 // clamped brick coordinate of a texel-centre coordinate c = u - 0.5

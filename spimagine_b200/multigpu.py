@@ -48,9 +48,19 @@ def partition_slabs_multi(nz, world, k):
     return out
 
 
-def slab_with_halo(z0, z1, nz):
-    """Slices a rank must hold to evaluate the samples it owns: one halo slice either side."""
-    return max(z0 - 1, 0), min(z1 + 1, nz)
+def slab_with_halo(z0, z1, nz, halo=1):
+    """Slices a rank must hold to evaluate the samples it owns: `halo` slices either side (1 for max projection;
+    iso surfaces need iso_halo(...) because the gradient taps reach +-2h along z)."""
+    return max(z0 - halo, 0), min(z1 + halo, nz)
+
+
+def iso_halo(nz, max_steps=200, gamma=1., path=2 * 3 ** .5):
+    """Halo slices a slab needs for sort-last iso surfaces: the 12-tap gradient reaches +-2h with h = dt * gamma^2 in
+    normalised texture units (iso_kernel.cl:163-192), dt = path / (max_steps - 1), plus one ray step for the
+    bracket refinement.  `path` = longest in-box ray length in eye-ray units (box diagonal for an unscaled
+    modelView).  The kernels check the actual requirement per pixel and the render raises if this was too small."""
+    dt = path / (max_steps - 1.)
+    return int(np.ceil(2 * dt * gamma * gamma * nz + 0.5 * dt * nz)) + 3
 
 
 def frames_for_rank(n_frames, rank, world):
@@ -98,6 +108,7 @@ class SlabMaxProjector(VolumeRenderer):
         self.composite = composite
         self._connected = False
         self.slabs_per_rank = int(slabs_per_rank)
+        self.halo = int(kw.pop("halo", 1))  # slices either side of the owned slab (iso surfaces: iso_halo(nz))
         self.readback_ranks = None  # None: every rank reads the composited image back; or a set of ranks (display rank)
         self._parts = []  # helper renderers holding this rank's other slabs (slabs_per_rank > 1)
         self._ctor = (interpolation, dict(kw))
@@ -121,7 +132,7 @@ class SlabMaxProjector(VolumeRenderer):
         mine = partition_slabs_multi(nz, self.world, self.slabs_per_rank)[self.rank]
         self.clear_parts()
         for i, (z0, z1) in enumerate(mine):
-            lo, hi = slab_with_halo(z0, z1, nz)
+            lo, hi = slab_with_halo(z0, z1, nz, self.halo)
             slab = np.asarray(data[lo:hi])
             if slab.dtype.type not in self.dtypes:
                 slab = slab.astype(self.dtype, copy=False)
@@ -145,7 +156,8 @@ class SlabMaxProjector(VolumeRenderer):
         """One more slab (at most 3) for this rank to render besides the one given to set_slab(): every ray marches
         the samples owned by each resident slab in the same kernel launch."""
         interpolation, kw = self._ctor
-        h = SlabMaxProjector((16, 16), interpolation, rank=self.rank, world=self.world, composite="nccl", **kw)
+        h = SlabMaxProjector((16, 16), interpolation, rank=self.rank, world=self.world, composite="nccl",
+                             halo=self.halo, **kw)
         h.set_layout(getattr(self, "layout", "zpair"))
         h._check(h._lib.spv_share_stream(h._ctx, self._ctx))
         h.set_slab(slab, gnz, z0, z1, device_ptr=device_ptr)
@@ -166,9 +178,9 @@ class SlabMaxProjector(VolumeRenderer):
         super(SlabMaxProjector, self).close()
 
     def set_slab(self, slab, gnz, z0, z1, device_ptr=None):
-        """slab: ndarray holding global slices [max(z0-1,0), min(z1+1,gnz)); or pass device_ptr (int) to a
-        C-order device copy of it together with slab=(dtype, ny, nx)."""
-        lo, hi = slab_with_halo(z0, z1, gnz)
+        """slab: ndarray holding global slices [max(z0-halo,0), min(z1+halo,gnz)) with halo = self.halo; or pass
+        device_ptr (int) to a C-order device copy of it together with slab=(dtype, ny, nx)."""
+        lo, hi = slab_with_halo(z0, z1, gnz, self.halo)
         if device_ptr is None:
             slab = np.ascontiguousarray(slab)
             if slab.shape[0] != hi - lo:
@@ -183,8 +195,8 @@ class SlabMaxProjector(VolumeRenderer):
         self.dataSlices = None
         self.set_shape((nx, ny, gnz))
         self.slab = (z0, z1)
-        self._check(self._lib.spv_set_volume_slab(self._ctx, ptr, on_dev, _lib.DTYPE_CODES[dtype], nx, ny, gnz,
-                                                  z0, z1))
+        self._check(self._lib.spv_set_volume_slab_halo(self._ctx, ptr, on_dev, _lib.DTYPE_CODES[dtype], nx, ny, gnz,
+                                                       z0, z1, self.halo))
         self._need_alloc = True
         self.update_matrices()
 
@@ -267,8 +279,60 @@ class SlabMaxProjector(VolumeRenderer):
         self.output = flat[:n].reshape(shape)
         self.output_alpha = flat[n:2 * n].reshape(shape)
 
+    # ---- sort-last iso surface ----
+    def _iso_params(self, raw_only=False):
+        return _lib.IsoParams(self._box(), float(self.maxVal / 2), float(self.gamma), int(self.max_steps),
+                              float(self.occ_strength), int(self.occ_radius), int(self.occ_n_points),
+                              _lib.ISO_RAW_ONLY if raw_only else 0)
+
+    def _dev_tensor(self, which, shape, typestr):
+        p = C.c_void_p()
+        self._check(self._lib.spv_device_ptr(self._ctx, which, C.byref(p)))
+        buf = _DevBuffer(p.value, shape)
+        buf.__cuda_array_interface__["typestr"] = typestr
+        return self._torch.as_tensor(buf, device="cuda:%d" % self.device)
+
+    def iso_k_tensor(self):
+        """int32 (2, H, W) view of the crossing-candidate planes (element-wise MIN over the ranks)."""
+        return self._dev_tensor(_lib.BUF_KPLANES, (2, self.height, self.width), "<i4")
+
+    def iso_planes_tensor(self):
+        """float32 (7, H, W) view of [out | alpha | depth | occ | normals(3)] (element-wise SUM over the ranks)."""
+        return self._dev_tensor(_lib.BUF_OUT, (7, self.height, self.width), "<f4")
+
+    def iso_search(self):
+        if self._parts:
+            raise NotImplementedError("sort-last iso_surface renders one slab per rank")
+        self._check(self._lib.spv_iso_slab_search(self._ctx, C.byref(self._iso_params())))
+
+    def iso_resolve(self):
+        self._check(self._lib.spv_iso_slab_resolve(self._ctx, C.byref(self._iso_params())))
+
+    def iso_finish(self, raw_only=False):
+        self._check(self._lib.spv_iso_slab_post(self._ctx, C.byref(self._iso_params(raw_only))))
+        flat, n = self._fetch(7)
+        self._check(self._lib.spv_iso_slab_check(self._ctx))
+        shape = (self.height, self.width)
+        self.output = flat[:n].reshape(shape)
+        self.output_alpha = flat[n:2 * n].reshape(shape)
+        self.output_depth = flat[2 * n:3 * n].reshape(shape)
+        self.output_occlusion = flat[3 * n:4 * n].reshape(shape)
+        self.output_normals = flat[4 * n:7 * n].reshape(shape + (3,))
+
     def _render_isosurface(self, raw_only=False):
-        raise NotImplementedError("sort-last iso_surface is not implemented yet")
+        """search on every slab -> all-reduce(MIN) of the candidate sample indices -> the owner of each crossing
+        resolves it -> all-reduce(SUM) assembles the planes -> post passes on every rank."""
+        torch, dist = self._torch, self._dist
+        multi = self.world > 1 and dist.is_initialized()
+        self.iso_search()
+        if multi:
+            with torch.cuda.stream(self._stream):
+                dist.all_reduce(self.iso_k_tensor(), op=dist.ReduceOp.MIN, group=self.group)
+        self.iso_resolve()
+        if multi:
+            with torch.cuda.stream(self._stream):
+                dist.all_reduce(self.iso_planes_tensor(), op=dist.ReduceOp.SUM, group=self.group)
+        self.iso_finish(raw_only)
 
 
 class TimelapsePlayer(object):

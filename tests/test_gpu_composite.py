@@ -94,3 +94,83 @@ def test_peer_composite_needs_connect_and_reports_a_missing_peer():
     with pytest.raises(KeyError):
         SlabMaxProjector((64, 32), rank=0, world=2, composite="nope")
     s.close()
+
+
+# ----------------------------------------------------------------------------- sort-last iso surface
+def _iso_ranks(data, size, world, halo, **kw):
+    from spimagine_b200.multigpu import SlabMaxProjector
+    rs = []
+    for rank in range(world):
+        s = SlabMaxProjector(size, rank=rank, world=world, halo=halo, **kw)
+        s.set_data(data)
+        rs.append(s)
+    return rs
+
+
+def _iso_all(rs, raw_only=False):
+    """What SlabMaxProjector._render_isosurface does over NCCL, with the two reductions done here across the
+    contexts of one process: MIN over the candidate planes, SUM over the resolved planes."""
+    import torch
+    for s in rs:
+        s.iso_search()
+        s.sync()
+    k = torch.stack([s.iso_k_tensor() for s in rs]).amin(0)
+    for s in rs:
+        s.iso_k_tensor().copy_(k)
+    torch.cuda.synchronize()
+    for s in rs:
+        s.iso_resolve()
+        s.sync()
+    planes = torch.stack([s.iso_planes_tensor() for s in rs]).sum(0)
+    for s in rs:
+        s.iso_planes_tensor().copy_(planes)
+    torch.cuda.synchronize()
+    for s in rs:
+        s.iso_finish(raw_only)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5])
+@pytest.mark.parametrize("dtype,maxval", [(np.uint16, 24000.), (np.float32, .5)])
+def test_sort_last_iso_surface_is_bit_exact(world, dtype, maxval):
+    """Every rank ends up with the single-GPU iso-surface render: hit mask, depth, normals, occlusion, shading."""
+    from spimagine_b200 import VolumeRenderer
+    from spimagine_b200.multigpu import iso_halo
+    data = scenes.vol_g(0, dtype, seed=7, shape=(64, 72, 80))
+    size = (136, 104)
+    rs = _iso_ranks(data, size, world, iso_halo(64))
+    mono = VolumeRenderer(size)
+    mono.set_data(data)
+    for theta, skip, gamma in [(0.4, None, 1.), (1.9, False, 1.), (3.0, None, .8)]:
+        M, P = scenes.gui_camera(theta, 3.2)
+        for r in rs + [mono]:
+            r.set_projection(P)
+            r.set_modelView(M)
+            r.set_max_val(maxval)
+            r.set_gamma(gamma)
+            r.set_skipping(skip)
+        mono.render(method="iso_surface")
+        assert np.isfinite(mono.output_depth).sum() > 500  # there is a surface to talk about
+        _iso_all(rs)
+        for s in rs:
+            assert np.array_equal(s.output_depth, mono.output_depth), (world, s.rank, theta)
+            assert np.array_equal(s.output_alpha, mono.output_alpha)
+            assert np.array_equal(s.output_normals, mono.output_normals)
+            assert np.array_equal(s.output_occlusion, mono.output_occlusion)
+            assert np.array_equal(s.output, mono.output)
+    for r in rs + [mono]:
+        r.close()
+
+
+def test_sort_last_iso_surface_reports_a_halo_that_is_too_small():
+    from spimagine_b200 import _lib
+    data = scenes.vol_g(0, np.uint16, seed=7, shape=(64, 72, 80))
+    rs = _iso_ranks(data, (96, 80), 4, halo=1)
+    M, P = scenes.gui_camera(0.4, 3.2)
+    for r in rs:
+        r.set_projection(P)
+        r.set_modelView(M)
+        r.set_max_val(24000.)
+    with pytest.raises(_lib.SpvError, match="halo"):
+        _iso_all(rs)
+    for r in rs:
+        r.close()
