@@ -56,10 +56,11 @@ def parse():
     ap.add_argument("--vol", type=int, default=VOL_N)
     ap.add_argument("--img", type=int, default=IMG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="sweep", choices=["sweep", "slab", "timelapse"],
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "slab", "timelapse", "iso"],
                     help="sweep: BASELINE configs[1], frames sharded over the GPUs (default). slab: configs[3], one "
                          "--vol^3 uint16 volume split into z-slabs over the GPUs, sort-last max composite. timelapse: "
-                         "configs[4], --frames time points of --tl-shape uint16, time point t on GPU t mod N")
+                         "configs[4], --frames time points of --tl-shape uint16, time point t on GPU t mod N. iso: "
+                         "configs[2], --vol^3 uint16 iso_surface with ambient occlusion and shading; N > 1: sort-last")
     ap.add_argument("--frames", type=int, default=100, help="timelapse workload: time points in the whole series")
     ap.add_argument("--tl-shape", default="512,1024,1024", help="timelapse workload: (Nz,Ny,Nx) of one time point")
     ap.add_argument("--skip", action="store_true", help="enable empty-space skipping on the min/max brick grid")
@@ -370,6 +371,114 @@ def run_timelapse(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_iso(args, rank, local_rank, world):
+    """BASELINE configs[2]: --vol^3 uint16 iso_surface at maxVal/2 with the AO defaults (.1, 21, 30) -> --img^2, 36-frame
+    sweep.  One GPU: VolumeRenderer.  N GPUs: z-slabs with an iso halo, sort-last (MIN-reduce of the candidate
+    sample indices, owner resolves, SUM-reduce, post passes) -- strong scaling, same image on every rank."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    import scenes
+    import ctypes as C
+    from spimagine_b200 import VolumeRenderer, _lib
+    from spimagine_b200.multigpu import SlabMaxProjector, iso_halo, partition_slabs, slab_with_halo
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    N, W = args.vol, args.img
+    dev = torch.device("cuda", local_rank)
+    iso_max = 30000.
+    if world == 1:
+        rend = VolumeRenderer((W, W), device=local_rank, max_steps=MAX_STEPS, pinned_outputs=True)
+        stream = torch.cuda.Stream(device=local_rank)
+        torch.cuda.set_stream(stream)
+        rend.use_stream(stream.cuda_stream)
+        vol = vol_g_slab_device(N, 0, N, 1, dev)
+        rend.set_data_device(vol.data_ptr(), (N, N, N), np.uint16)
+        halo = 0
+    else:
+        halo = iso_halo(N, MAX_STEPS)
+        z0, z1 = partition_slabs(N, world)[rank]
+        lo, hi = slab_with_halo(z0, z1, N, halo)
+        rend = SlabMaxProjector((W, W), rank=rank, world=world, device=local_rank, max_steps=MAX_STEPS,
+                                pinned_outputs=True, halo=halo)
+        torch.cuda.set_stream(rend._stream)
+        vol = vol_g_slab_device(N, lo, hi, 1, dev)
+        rend.set_slab((np.uint16, N, N), N, z0, z1, device_ptr=vol.data_ptr())
+    rend.sync()
+    del vol
+    torch.cuda.empty_cache()
+    rend.set_max_val(iso_max)
+    NF = 36
+    cams = [scenes.gui_camera(2 * math.pi * f / NF, 4.0) for f in range(NF)]
+    rend.set_projection(cams[0][1])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(i):
+        rend.set_modelView(cams[i % NF][0])
+        if world == 1:
+            p = _lib.IsoParams(rend._box(), iso_max / 2, 1., MAX_STEPS, .1, 21, 30, 0)
+            _lib.check(rend._lib.spv_render_iso(rend._ctx, C.byref(p)), rend._ctx)
+        else:
+            rend.iso_search()
+            dist.all_reduce(rend.iso_k_tensor(), op=dist.ReduceOp.MIN)
+            rend.iso_resolve()
+            dist.all_reduce(rend.iso_planes_tensor(), op=dist.ReduceOp.SUM)
+            _lib.check(rend._lib.spv_iso_slab_post(rend._ctx, C.byref(rend._iso_params())), rend._ctx)
+
+    for i in range(args.warmup):
+        device_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        device_step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    digest = hashlib.sha1()
+    hit_px = 0
+    for i in range(8):  # untimed: hash of everything the first frames produce (compared across GPU counts)
+        rend.set_modelView(cams[i][0])
+        rend.render(method="iso_surface")
+        for a in (rend.output, rend.output_depth, rend.output_normals, rend.output_occlusion):
+            digest.update(np.ascontiguousarray(a).tobytes())
+        hit_px = int(np.isfinite(rend.output_depth).sum())
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        rend.set_modelView(cams[i % NF][0])
+        rend.render(method="iso_surface")
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    if world > 1:
+        t = torch.tensor([ms, t_e2e * 1e3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, t_e2e = float(t[0]), float(t[1]) / 1e3
+    if rank == 0:
+        print(json.dumps({
+            "metric": "iso_surface frames/s, %d^3 uint16 -> %d^2, AO + shading, 36-frame sweep" % (N, W),
+            "value": args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u16->f32", "data": "synthetic",
+            "config": {"workload": "Vol-G(%d, uint16, seed 1) generated on device, iso at %g, AO (.1, 21, 30), max_steps=200%s" % (
+                N, iso_max / 2, "" if world == 1 else ", %d z-slabs with %d halo slices, sort-last over NCCL (MIN int32 "
+                "2 planes, SUM float32 7 planes)" % (world, halo))},
+            "e2e": {"value": args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 2 * W * W * 4,
+                    "note": "set_modelView + render(method='iso_surface'): output + alpha read back per frame (8 MiB); depth, normals and occlusion stay on the device until they are looked at (lazy attributes)"},
+            "surface_pixels_last": hit_px, "image_sha1_first8": digest.hexdigest(),
+            "gpu_launches": args.steps * (7 if world == 1 else 9)}))
+    rend.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_bricks(args):
     """The single-GPU-brick baseline of BASELINE configs[3]: the same slab kernels on ONE GPU, the volume cut into
     --bricks z-slabs, each rendered by its own launch one after the other (what a single GPU does when the volume
@@ -553,16 +662,16 @@ def run_slab(args, rank, local_rank, world):
     if peer:
         rend.readback_ranks = {0}
     digest = hashlib.sha1()
-    for i in range(3):
+    for i in range(8):  # untimed: image hash of the first frames (compared across GPU counts and composites)
         rend.set_modelView(cams[(i * 7) % SWEEP][0])
         rend.render()
+        if rend.readback_ranks is None or rank in rend.readback_ranks:
+            digest.update(rend.output.tobytes())
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         rend.set_modelView(cams[(i * 7) % SWEEP][0])
         rend.render()
-        if i < 8:
-            digest.update(rend.output.tobytes())
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
@@ -626,6 +735,9 @@ def main():
         return
     if args.workload == "timelapse":
         run_timelapse(args, rank, local_rank, world)
+        return
+    if args.workload == "iso":
+        run_iso(args, rank, local_rank, world)
         return
     if args.workload == "slab" and args.bricks > 0:
         if world != 1:

@@ -98,6 +98,10 @@ class VolumeRenderer(object):
     # ------------------------------------------------------------------ lifetime
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            try:
+                self._fetch_iso_extras()  # results of the last iso render stay readable after close()
+            except Exception:
+                pass
             self._lib.spv_destroy(self._ctx)
             self._ctx = _lib._CTX()
 
@@ -165,6 +169,7 @@ class VolumeRenderer(object):
         self.reset_buffer()
 
     def reset_buffer(self, _realloc=True):
+        self._iso_pending = False
         if _realloc:
             self._check(self._lib.spv_resize(self._ctx, self.width, self.height))
             self.__dict__.pop("_views", None)  # the pinned staging moved
@@ -357,18 +362,47 @@ class VolumeRenderer(object):
             self.output_depth = np.zeros(shape, np.float32)
 
     def _render_isosurface(self, raw_only=False):
-        """iso surface with ambient occlusion: iso_surface -> normal blur -> occlusion -> blur -> shading"""
+        """iso surface with ambient occlusion: iso_surface -> normal blur -> occlusion -> blur -> shading.
+        output and output_alpha are read back at once; output_depth / output_normals / output_occlusion are read
+        back when they are first looked at (they stay on the device otherwise: 5 of the 7 result planes)."""
         p = _lib.IsoParams(self._box(), float(self.maxVal / 2), float(self.gamma), int(self.max_steps),
                            float(self.occ_strength), int(self.occ_radius), int(self.occ_n_points),
                            _lib.ISO_RAW_ONLY if raw_only else 0)
         self._check(self._lib.spv_render_iso(self._ctx, C.byref(p)))
-        flat, n = self._fetch(7)
+        flat, n = self._fetch(2)
         shape = (self.height, self.width)
         self.output = flat[:n].reshape(shape)
         self.output_alpha = flat[n:2 * n].reshape(shape)
-        self.output_depth = flat[2 * n:3 * n].reshape(shape)
-        self.output_occlusion = flat[3 * n:4 * n].reshape(shape)
-        self.output_normals = flat[4 * n:7 * n].reshape(shape + (3,))
+        self._iso_pending = True
+
+    # output_depth / output_normals / output_occlusion: plain attributes in the reference (volumerender.py:122-130);
+    # here they are fetched from the device on first access after an iso-surface render
+    def _fetch_iso_extras(self):
+        if self.__dict__.get("_iso_pending") and getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._iso_pending = False
+            flat, n = self._fetch(7)
+            shape = (self.height, self.width)
+            if self.pinned_outputs:  # the staging was rewritten: re-point the eager planes as well (same values)
+                self.__dict__["output"] = flat[:n].reshape(shape)
+                self.__dict__["output_alpha"] = flat[n:2 * n].reshape(shape)
+            self.__dict__["_output_depth"] = flat[2 * n:3 * n].reshape(shape)
+            self.__dict__["_output_occlusion"] = flat[3 * n:4 * n].reshape(shape)
+            self.__dict__["_output_normals"] = flat[4 * n:7 * n].reshape(shape + (3,))
+
+    def _lazy_get(self, name):
+        self._fetch_iso_extras()
+        return self.__dict__["_" + name]
+
+    def _lazy_set(self, name, value):
+        self._fetch_iso_extras()  # a pending read-back must not overwrite what the caller assigns
+        self.__dict__["_" + name] = value
+
+    output_depth = property(lambda self: self._lazy_get("output_depth"),
+                            lambda self, v: self._lazy_set("output_depth", v))
+    output_normals = property(lambda self: self._lazy_get("output_normals"),
+                              lambda self, v: self._lazy_set("output_normals", v))
+    output_occlusion = property(lambda self: self._lazy_get("output_occlusion"),
+                                lambda self, v: self._lazy_set("output_occlusion", v))
 
     def render(self, data=None, stackUnits=None,
                minVal=None, maxVal=None, gamma=None,
@@ -418,6 +452,7 @@ class VolumeRenderer(object):
         if method not in ("max_project", "iso_surface"):
             raise KeyError("method = '%s' not defined, valid: ['max_project', 'iso_surface']" % method)
         planes = 2 if method == "max_project" else 7
+        self._fetch_iso_extras()  # a deferred read-back of an earlier render() happens before the slots are reused
         pending = []  # slots in flight, oldest first
         i = 0
         try:
