@@ -73,6 +73,15 @@ SPV_API int spv_update_volume(spv_ctx *ctx, const void *host);
 SPV_API int spv_update_volume_async(spv_ctx *ctx, const void *pinned_host);
 SPV_API int spv_host_alloc(size_t nbytes, void **host);  /* page-locked, usable from every device */
 SPV_API int spv_host_free(void *host);
+/* Host arrays of ANOTHER element type (replaces the host-side `data.astype(self.dtype)` of set_data / update_data,
+ * volumerender.py:245-246, 290-291): the source bytes travel over PCIe as they are and are converted to `dtype`
+ * texels on the device, chunk by chunk inside the ingest pipeline, with the semantics of the C cast numpy's astype
+ * performs (float targets: round to nearest; integer targets: integers wrap, floats truncate towards zero and wrap
+ * within the int32 range). */
+enum { SPV_SRC_I8 = 0, SPV_SRC_U8 = 1, SPV_SRC_I16 = 2, SPV_SRC_U16 = 3, SPV_SRC_I32 = 4, SPV_SRC_U32 = 5,
+       SPV_SRC_I64 = 6, SPV_SRC_U64 = 7, SPV_SRC_F16 = 8, SPV_SRC_F32 = 9, SPV_SRC_F64 = 10, SPV_SRC_BOOL = 11 };
+SPV_API int spv_set_volume_from(spv_ctx *ctx, const void *host, int src_type, int dtype, int nx, int ny, int nz);
+SPV_API int spv_update_volume_from(spv_ctx *ctx, const void *host, int src_type);
 /* as above from a DEVICE pointer (C-order linear); used by frame sources that keep timepoints in HBM */
 SPV_API int spv_set_volume_device(spv_ctx *ctx, const void *dev, int dtype, int nx, int ny, int nz);
 /* One z-slab of a larger volume for sort-last rendering (new).  The host/dev pointer
@@ -213,7 +222,9 @@ SPV_API int spv_last_stats(spv_ctx *ctx, unsigned long long *v, int n); /* [hit 
 SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
 /* performance knobs that never change results; knob 0 = CTA shape / occupancy target of the max-projection kernel,
  * knob 1 = persistent CTAs pulling tiles from a counter (1) or one CTA per tile (0), knob 2 = default band count of
- * spv_render_mip_to_host */
+ * spv_render_mip_to_host, knob 3 = spv_render_mip_to_host stores straight into pinned host memory, knob 4 = warps per
+ * CTA of the iso-surface search (1, 2 or 4), knob 5 = its CTAs are dealt from the image centre outwards (1, default) or
+ * row by row (0) */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 SPV_API const char *spv_last_error(spv_ctx *ctx);                   /* ctx may be NULL: last create error */
 SPV_API int spv_version(void);

@@ -37,19 +37,29 @@ for M, P in cams:
     rend.set_modelView(M)
     mats.append((rend._invP.copy(), rend._invM.copy()))
 lib, ctx = rend._lib, rend._ctx
-for flags, name in ((_lib.ISO_RAW_ONLY, "iso_surface kernel alone"), (0, "full chain (7 launches)")):
-    p = _lib.IsoParams(rend._box(), maxVal / 2, 1., 200, .1, 21, 30, flags)
-    for rep in range(2):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(NF):
-            lib.spv_set_matrices(ctx, _lib.fp(mats[i][0]), _lib.fp(mats[i][1]))
-            rc = lib.spv_render_iso(ctx, C.byref(p))
-            assert rc == 0
-        e1.record()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / NF
-    print("%s: %.3f ms/frame  %.0f frames/s" % (name, ms, 1e3 / ms), flush=True)
+import hashlib
+for variant in os.environ.get("EXP_ISO_VARIANTS", "4:1").split(","):
+    cta_warps, centre = (int(v) for v in variant.split(":"))
+    lib.spv_set_tuning(ctx, 4, cta_warps)
+    lib.spv_set_tuning(ctx, 5, centre)
+    print("iso search CTA = %d warp(s), centre-out order %d" % (cta_warps, centre))
+    for flags, name in ((_lib.ISO_RAW_ONLY, "iso_surface kernel alone"), (0, "full chain (5 launches)")):
+        p = _lib.IsoParams(rend._box(), maxVal / 2, 1., 200, .1, 21, 30, flags)
+        for rep in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(NF):
+                lib.spv_set_matrices(ctx, _lib.fp(mats[i][0]), _lib.fp(mats[i][1]))
+                rc = lib.spv_render_iso(ctx, C.byref(p))
+                assert rc == 0
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / NF
+        print("%s: %.3f ms/frame  %.0f frames/s" % (name, ms, 1e3 / ms), flush=True)
+    rend.set_modelView(cams[3][0])
+    rend.render(method="iso_surface")
+    print("    image sha1", hashlib.sha1(rend.output.tobytes() + rend.output_depth.tobytes() +
+                                         rend.output_normals.tobytes()).hexdigest()[:12])
 rend.enable_stats(True)
 rend.set_modelView(cams[3][0])
 rend.render(method="iso_surface")

@@ -18,6 +18,9 @@ MIP_RAW_ONLY = 1
 ISO_RAW_ONLY = 1
 
 DTYPE_CODES = {np.dtype(np.float32): SPV_F32, np.dtype(np.uint16): SPV_U16, np.dtype(np.uint8): SPV_U8}
+# host element types the ingest path converts on the device (SPV_SRC_*)
+SRC_CODES = {np.dtype(t): i for i, t in enumerate([np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32,
+                                                   np.int64, np.uint64, np.float16, np.float32, np.float64, np.bool_])}
 
 
 class MipParams(C.Structure):
@@ -48,6 +51,8 @@ SIGNATURES = {
     "spv_set_volume": (C.c_int, [_CTX, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "spv_update_volume": (C.c_int, [_CTX, C.c_void_p]),
     "spv_update_volume_async": (C.c_int, [_CTX, C.c_void_p]),
+    "spv_set_volume_from": (C.c_int, [_CTX, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "spv_update_volume_from": (C.c_int, [_CTX, C.c_void_p, C.c_int]),
     "spv_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "spv_host_free": (C.c_int, [C.c_void_p]),
     "spv_set_volume_device": (C.c_int, [_CTX, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),

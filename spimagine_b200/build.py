@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, "libspimcuda.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-std=c++17", "-lineinfo",
+    "-O3", "-std=c++17", "-lineinfo", "--threads", "0",
     # no implicit contraction: the ray setup must round like the reference's fp32 expressions
     # (explicit fmaf where the fast path wants it), IEEE division and square root
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true",

@@ -27,11 +27,12 @@ struct spv_ctx {
   int want_layout = LAYOUT_ZPAIR; // for integer volumes (spv_set_layout)
   void *d_stage = nullptr;       // ingest staging on the device: [paired texels | linear chunk x 2]
   size_t stage_bytes = 0;
+  size_t stage_sig[3] = {0, 0, 0};  // partition of d_stage used by the last upload
   char *h_ring = nullptr;        // page-locked ring (2 chunks) for pageable sources
   size_t ring_bytes = 0;
   cudaEvent_t ev_up_begin = nullptr, ev_h2d_done[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   bool ring_used[2] = {false, false}, lin_used[2] = {false, false};
-  float2 *bricks = nullptr, *coarse = nullptr;
+  float2 *bricks = nullptr, *coarse = nullptr, *top = nullptr;
   int gx = 0, gy = 0, gz = 0, cgx = 0, cgy = 0, cgz = 0;
   float *d_minmax = nullptr;
   float h_minmax[2] = {0.f, 0.f};
@@ -40,9 +41,16 @@ struct spv_ctx {
   // settings
   int linear = 1, sampler = SPV_SAMPLER_TMU, int_filter = 1, skipping = -1, stats_on = 0, tile_variant = 0, persistent = 0;
   int bands = 2;  // default band count of spv_render_mip_to_host (measured best of 1/2/4/8/16, profiles/r01_exp_e2e.txt)
+  int iso_cta_warps = 4;  // tuning knob 4
+  int iso_centre_out = 1; // tuning knob 5
   int direct_host = 0;  // spv_render_mip_to_host: the kernel stores straight into the pinned staging (tuning knob 3)
   unsigned *d_tile_counter = nullptr;
-  unsigned char *d_tile_hit = nullptr;  // per 16x8 tile: holds an iso-surface pixel
+  unsigned char *d_tile_hit = nullptr;  // per 8x4 warp tile: holds an iso-surface pixel
+  unsigned *d_occ_queue = nullptr;      // occlusion work queue (launch_occlusion), per image size
+  unsigned occ_frame = 0;
+  int sms = 0;
+  float4 *d_taps = nullptr;             // occlusion tap table (launch_occ_taps), valid for taps_n taps
+  int taps_n = 0;
   Camera cam;
   // result buffers: one allocation  [out | alpha | depth | occ | normals(3) | raw | tmp | tmp_vec(3)]
   float *dbuf = nullptr;
@@ -143,6 +151,8 @@ static void free_buffers(spv_ctx *c) {
   }
   if (c->d_tile_hit) cudaFree(c->d_tile_hit);
   c->d_tile_hit = nullptr;
+  if (c->d_occ_queue) cudaFree(c->d_occ_queue);
+  c->d_occ_queue = nullptr;
   c->dbuf = nullptr;
   c->hpin = nullptr;
   c->slot = 0;
@@ -154,6 +164,7 @@ static void free_volume(spv_ctx *c) {
   if (c->arr) cudaFreeArray(c->arr);
   if (c->bricks) cudaFree(c->bricks);
   if (c->coarse) cudaFree(c->coarse);
+  if (c->top) cudaFree(c->top);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->d_stage) cudaFree(c->d_stage);
   if (c->h_ring) cudaFreeHost(c->h_ring);
@@ -164,7 +175,7 @@ static void free_volume(spv_ctx *c) {
   c->ring_used[0] = c->ring_used[1] = c->lin_used[0] = c->lin_used[1] = false;
   c->tex_lin = c->tex_near = c->tex_pt = 0;
   c->arr = nullptr;
-  c->bricks = c->coarse = nullptr;
+  c->bricks = c->coarse = c->top = nullptr;
   c->dtype = -1;
 }
 
@@ -186,7 +197,9 @@ static int alloc_buffers(spv_ctx *ctx, int w, int h) {
   if (rc) return rc;
   ctx->dbuf = ctx->dbuf_s[0];
   ctx->hpin = ctx->hpin_s[0];
-  CU(cudaMalloc(&ctx->d_tile_hit, (size_t)((w + 15) / 16) * ((h + 7) / 8)));
+  CU(cudaMalloc(&ctx->d_tile_hit, (size_t)((w + 7) / 8) * ((h + 3) / 4)));  // one flag per 8x4 warp tile
+  CU(cudaMalloc(&ctx->d_occ_queue, occ_queue_bytes(w, h)));
+  CU(cudaMemsetAsync(ctx->d_occ_queue, 0, occ_queue_bytes(w, h), ctx->stream));
   return 0;
 }
 
@@ -216,6 +229,7 @@ SPV_API int spv_create(int device, int width, int height, spv_ctx **out) {
     }                                              \
   } while (0)
   CC(cudaSetDevice(device));
+  CC(cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device));
   CC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
   CC(cudaEventCreate(&ctx->ev0));
@@ -254,6 +268,7 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
   if (ctx->d_stats) cudaFree(ctx->d_stats);
   if (ctx->d_tile_counter) cudaFree(ctx->d_tile_counter);
   if (ctx->d_iso_err) cudaFree(ctx->d_iso_err);
+  if (ctx->d_taps) cudaFree(ctx->d_taps);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev_up_begin) cudaEventDestroy(ctx->ev_up_begin);
@@ -363,10 +378,15 @@ enum { SRC_DEVICE = 0, SRC_PINNED = 1, SRC_PAGEABLE = 2 };
 //   LAYOUT_ZPAIR     : pair_kernel builds {v[z], v[z+1]} texels from the linear chunk, cudaMemcpy3D moves them into
 //                      the layers (stream order on the render stream)
 //   LAYOUT_3D        : the DMA writes the array slices directly
-static int upload(spv_ctx *ctx, const void *src, bool on_device, bool no_wait = false) {
+//   src_type >= 0    : the host array has another element type (SPV_SRC_*): its bytes travel as they are, convert_kernel
+//                      turns each chunk into texels on the device (instead of a host-side astype), then as above
+static int upload(spv_ctx *ctx, const void *src, bool on_device, bool no_wait = false, int src_type = -1) {
   const size_t es = elem_size(ctx->dtype);
   const size_t slice = (size_t)ctx->nx * ctx->ny;
   const size_t slice_bytes = slice * es;
+  const bool conv = src_type >= 0;
+  const size_t in_slice_bytes = conv ? slice * src_elem_size(src_type) : slice_bytes;  // as the chunk travels
+  if (conv && (on_device || in_slice_bytes == 0)) return fail(ctx, SPV_EINVAL, "upload: bad source element type");
   const int nz = ctx->local_nz;
   const bool zpair = ctx->layout == LAYOUT_ZPAIR;
   int kind = SRC_DEVICE;
@@ -381,12 +401,13 @@ static int upload(spv_ctx *ctx, const void *src, bool on_device, bool no_wait = 
 
   // slices per chunk
   const size_t budget = kind == SRC_DEVICE ? ((size_t)128 << 20) : ((size_t)32 << 20);
-  int zc = (int)(budget / slice_bytes);
+  int zc = (int)(budget / (slice_bytes > in_slice_bytes ? slice_bytes : in_slice_bytes));
   if (zc < 1) zc = 1;
   if (zc > nz) zc = nz;
   const size_t lin_bytes = slice_bytes * (size_t)(zc + (zpair ? 1 : 0));  // + the upper partner of the last slice
+  const size_t in_bytes = in_slice_bytes * (size_t)(zc + (zpair ? 1 : 0));
   const size_t pair_bytes = zpair ? slice_bytes * 2 * (size_t)zc : 0;
-  const size_t need_dev = pair_bytes + ((zpair && kind != SRC_DEVICE) ? 2 * lin_bytes : 0);
+  const size_t need_dev = pair_bytes + (((zpair || conv) && kind != SRC_DEVICE) ? 2 * lin_bytes : 0) + (conv ? 2 * in_bytes : 0);
   if (need_dev > ctx->stage_bytes) {
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->copy_stream));
@@ -396,17 +417,25 @@ static int upload(spv_ctx *ctx, const void *src, bool on_device, bool no_wait = 
     CU(cudaMalloc(&ctx->d_stage, need_dev));
     ctx->stage_bytes = need_dev;
   }
-  if (kind == SRC_PAGEABLE && 2 * lin_bytes > ctx->ring_bytes) {
+  if (kind == SRC_PAGEABLE && 2 * in_bytes > ctx->ring_bytes) {
     CU(cudaStreamSynchronize(ctx->copy_stream));
     if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
     ctx->h_ring = nullptr;
     ctx->ring_bytes = 0;
-    CU(cudaMallocHost(&ctx->h_ring, 2 * lin_bytes));
-    ctx->ring_bytes = 2 * lin_bytes;
+    CU(cudaMallocHost(&ctx->h_ring, 2 * in_bytes));
+    ctx->ring_bytes = 2 * in_bytes;
+  }
+  if (ctx->stage_sig[0] != pair_bytes || ctx->stage_sig[1] != lin_bytes || ctx->stage_sig[2] != in_bytes) {
+    // the staging is cut differently than by the previous upload (which may still be in flight after an asynchronous
+    // call): the per-half events no longer describe these regions
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stage_sig[0] = pair_bytes; ctx->stage_sig[1] = lin_bytes; ctx->stage_sig[2] = in_bytes;
   }
   char *d_pair = (char *)ctx->d_stage;
   char *d_lin[2] = {d_pair + pair_bytes, d_pair + pair_bytes + lin_bytes};
-  char *h_ring[2] = {ctx->h_ring, ctx->h_ring ? ctx->h_ring + lin_bytes : nullptr};
+  char *d_in[2] = {d_pair + pair_bytes + 2 * lin_bytes, d_pair + pair_bytes + 2 * lin_bytes + in_bytes};  // conv only
+  char *h_ring[2] = {ctx->h_ring, ctx->h_ring ? ctx->h_ring + in_bytes : nullptr};
 
   auto to_layers = [&](const void *lin, int lin_nz, int zfirst, int zb, int ze) -> int {
     // lin holds slices [zfirst, zfirst + lin_nz) of the volume; build the paired texels of [zb, ze) and store them
@@ -448,22 +477,37 @@ static int upload(spv_ctx *ctx, const void *src, bool on_device, bool no_wait = 
   for (int zb = 0; zb < nz; zb += zc, ++i) {
     const int ze = zb + zc < nz ? zb + zc : nz;
     const int zs = zpair ? (ze < nz ? ze + 1 : nz) : ze;  // slices [zb, zs) travel
-    const size_t bytes = (size_t)(zs - zb) * slice_bytes;
+    const size_t bytes = (size_t)(zs - zb) * in_slice_bytes;
     const int s = i & 1;
-    const char *from = (const char *)src + (size_t)zb * slice_bytes;
+    const char *from = (const char *)src + (size_t)zb * in_slice_bytes;
     if (kind == SRC_PAGEABLE) {
       if (ctx->ring_used[s]) CU(cudaEventSynchronize(ctx->ev_h2d_done[s]));  // the DMA that last read this half
       parallel_memcpy(h_ring[s], from, bytes);
       ctx->ring_used[s] = true;
       from = h_ring[s];
     }
-    if (zpair) {
+    if (zpair || conv) {
       if (ctx->lin_used[s]) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[s], 0));
-      CU(cudaMemcpyAsync(d_lin[s], from, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+      CU(cudaMemcpyAsync(conv ? d_in[s] : d_lin[s], from, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
       CU(cudaEventRecord(ctx->ev_h2d_done[s], ctx->copy_stream));
       CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d_done[s], 0));
-      int rc = to_layers(d_lin[s], zs - zb, zb, zb, ze);
-      if (rc) return rc;
+      if (conv) {
+        CU(launch_convert(d_in[s], d_lin[s], src_type, ctx->dtype, (size_t)(zs - zb) * slice, ctx->stream));
+        ctx->launches += 1;
+      }
+      if (zpair) {
+        int rc = to_layers(d_lin[s], zs - zb, zb, zb, ze);
+        if (rc) return rc;
+      } else {
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof p);
+        p.srcPtr = make_cudaPitchedPtr(d_lin[s], (size_t)ctx->nx * es, ctx->nx, ctx->ny);
+        p.dstArray = ctx->arr;
+        p.dstPos = make_cudaPos(0, 0, zb);
+        p.extent = make_cudaExtent(ctx->nx, ctx->ny, ze - zb);
+        p.kind = cudaMemcpyDeviceToDevice;
+        CU(cudaMemcpy3DAsync(&p, ctx->stream));
+      }
       CU(cudaEventRecord(ctx->ev_consumed[s], ctx->stream));
       ctx->lin_used[s] = true;
     } else {
@@ -478,7 +522,7 @@ static int upload(spv_ctx *ctx, const void *src, bool on_device, bool no_wait = 
       CU(cudaEventRecord(ctx->ev_h2d_done[s], ctx->copy_stream));
     }
   }
-  if (!zpair && i > 0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d_done[(i - 1) & 1], 0));  // renders wait for the data
+  if (!zpair && !conv && i > 0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d_done[(i - 1) & 1], 0));  // renders wait for the data
   if (!no_wait) {  // the host pointer is only borrowed for this call
     CU(cudaStreamSynchronize(ctx->copy_stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -493,15 +537,15 @@ static int ensure_bricks(spv_ctx *ctx) {
   if (ctx->bricks_valid) return 0;
   Volume V = volume_of(ctx);
   CU(launch_build_bricks(V, fmt_of(ctx), ctx->local_nz, ctx->bricks, ctx->coarse, ctx->cgx, ctx->cgy, ctx->cgz,
-                         ctx->d_minmax, ctx->stream));
-  ctx->launches += 3;
+                         ctx->top, ctx->d_minmax, ctx->stream));
+  ctx->launches += 4;
   ctx->bricks_valid = true;
   ctx->minmax_valid = false;
   return 0;
 }
 
 static int set_volume_impl(spv_ctx *ctx, const void *src, bool on_device, int dtype, int nx, int ny, int gnz, int z0,
-                           int z1, bool slab, int halo = 1) {
+                           int z1, bool slab, int halo = 1, int src_type = -1) {
   BIND();
   if (!src) return fail(ctx, SPV_EINVAL, "spv_set_volume: null data");
   if (dtype < 0 || dtype > 2) return fail(ctx, SPV_EINVAL, "spv_set_volume: dtype must be 0 (f32), 1 (u16) or 2 (u8)");
@@ -533,9 +577,10 @@ static int set_volume_impl(spv_ctx *ctx, const void *src, bool on_device, int dt
     ctx->cgx = (ctx->gx + 3) / 4; ctx->cgy = (ctx->gy + 3) / 4; ctx->cgz = (ctx->gz + 3) / 4;
     CU(cudaMalloc(&ctx->bricks, (size_t)ctx->gx * ctx->gy * ctx->gz * sizeof(float2)));
     CU(cudaMalloc(&ctx->coarse, (size_t)ctx->cgx * ctx->cgy * ctx->cgz * sizeof(float2)));
+    CU(cudaMalloc(&ctx->top, (size_t)((ctx->cgx + 3) / 4) * ((ctx->cgy + 3) / 4) * ((ctx->cgz + 3) / 4) * sizeof(float2)));
   }
   ctx->gnz = gnz; ctx->z_lo = z_lo; ctx->z0 = z0; ctx->z1 = z1; ctx->slab = slab;
-  return upload(ctx, src, on_device);
+  return upload(ctx, src, on_device, false, src_type);
 }
 
 SPV_API int spv_set_volume(spv_ctx *ctx, const void *host, int dtype, int nx, int ny, int nz) {
@@ -557,6 +602,23 @@ SPV_API int spv_update_volume(spv_ctx *ctx, const void *host) {
   if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_update_volume: no volume set");
   if (!host) return fail(ctx, SPV_EINVAL, "spv_update_volume: null data");
   return upload(ctx, host, false);
+}
+
+// a source type that already is the texel type needs no conversion pass
+static int native_src(int src_type, int dtype) {
+  return (src_type == SPV_SRC_F32 && dtype == SPV_F32) || (src_type == SPV_SRC_U16 && dtype == SPV_U16) ||
+         (src_type == SPV_SRC_U8 && dtype == SPV_U8);
+}
+SPV_API int spv_set_volume_from(spv_ctx *ctx, const void *host, int src_type, int dtype, int nx, int ny, int nz) {
+  if (src_elem_size(src_type) == 0) return fail(ctx, SPV_EINVAL, "spv_set_volume_from: unknown source element type");
+  return set_volume_impl(ctx, host, false, dtype, nx, ny, nz, 0, nz, false, 1, native_src(src_type, dtype) ? -1 : src_type);
+}
+SPV_API int spv_update_volume_from(spv_ctx *ctx, const void *host, int src_type) {
+  BIND();
+  if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_update_volume_from: no volume set");
+  if (!host) return fail(ctx, SPV_EINVAL, "spv_update_volume_from: null data");
+  if (src_elem_size(src_type) == 0) return fail(ctx, SPV_EINVAL, "spv_update_volume_from: unknown source element type");
+  return upload(ctx, host, false, false, native_src(src_type, ctx->dtype) ? -1 : src_type);
 }
 
 SPV_API int spv_update_volume_async(spv_ctx *ctx, const void *pinned_host) {
@@ -633,6 +695,8 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   else if (knob == 1) ctx->persistent = value != 0;
   else if (knob == 2) ctx->bands = value < 1 ? 1 : (value > 64 ? 64 : value);
   else if (knob == 3) ctx->direct_host = value != 0;
+  else if (knob == 4) ctx->iso_cta_warps = value;
+  else if (knob == 5) ctx->iso_centre_out = value != 0;
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
   return 0;
 }
@@ -913,6 +977,22 @@ SPV_API int spv_mip_finish(spv_ctx *ctx, const spv_mip_params *p) {
   return 0;
 }
 
+// the occlusion tap table covers taps [0, taps_n); it is extended when a render asks for more
+static int ensure_taps(spv_ctx *ctx, int n) {
+  if (n <= ctx->taps_n) return 0;
+  int cap = 64;
+  while (cap < n) cap *= 2;
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_taps) cudaFree(ctx->d_taps);
+  ctx->d_taps = nullptr;
+  ctx->taps_n = 0;
+  CU(cudaMalloc(&ctx->d_taps, (size_t)cap * sizeof(float4)));
+  CU(launch_occ_taps(ctx->d_taps, cap, ctx->stream));
+  ctx->launches += 1;
+  ctx->taps_n = cap;
+  return 0;
+}
+
 static ConvWeights conv_weights(int Nh, float coef) {
   ConvWeights w;
   memset(&w, 0, sizeof w);
@@ -934,8 +1014,12 @@ SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p) {
   a.vol = volume_of(ctx);
   a.coarse = ctx->coarse;
   a.cgx = ctx->cgx; a.cgy = ctx->cgy; a.cgz = ctx->cgz;
+  a.top = ctx->top;
+  a.tgx = (ctx->cgx + 3) / 4; a.tgy = (ctx->cgy + 3) / 4; a.tgz = (ctx->cgz + 3) / 4;
   memcpy(a.box, p->box, sizeof a.box);
   a.iso_val = p->iso_val; a.gamma = p->gamma; a.max_steps = p->max_steps;
+  a.cta_warps = ctx->iso_cta_warps;
+  a.centre_out = ctx->iso_centre_out;
   const bool exact_iso = ctx->sampler == SPV_SAMPLER_EXACT;
   a.tile_hit = exact_iso ? nullptr : ctx->d_tile_hit;
   a.skip = ctx->skipping != 0;  // auto (-1) = on: for iso surfaces the brick test is nearly free and exact
@@ -944,22 +1028,28 @@ SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p) {
     if (rcb) return rcb;
   }
   a.width = ctx->width; a.height = ctx->height;
-  a.out = ctx->out(); a.alpha = ctx->alpha(); a.depth = ctx->depth(); a.normals = ctx->normals();
+  const bool post = !(p->flags & SPV_ISO_RAW_ONLY);
+  // with post passes the march writes the raw normals into tmp_vec and the fused blur moves them to their plane
+  a.out = ctx->out(); a.alpha = ctx->alpha(); a.depth = ctx->depth(); a.normals = post ? ctx->tmp_vec() : ctx->normals();
   a.stats = ctx->stats_on ? ctx->d_stats : nullptr;
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
-  int rc = begin_render(ctx);
+  int rc = post ? ensure_taps(ctx, p->occ_n_points) : 0;
+  if (rc) return rc;
+  rc = begin_render(ctx);
   if (rc) return rc;
   CU(launch_iso(a, fmt_of(ctx), linear, ctx->sampler == SPV_SAMPLER_EXACT, ctx->stats_on != 0, ctx->stream));
   ctx->launches += 1;
-  if (!(p->flags & SPV_ISO_RAW_ONLY)) {
+  if (post) {
     // volumerender.py:470-497
-    CU(launch_conv(ctx->normals(), ctx->tmp_vec(), ctx->width, ctx->height, 3, conv_weights(7, -5.f), ctx->stream));
-    CU(launch_occlusion(ctx->occ(), ctx->width, ctx->height, p->occ_radius, p->occ_n_points, ctx->depth(), a.tile_hit,
-                        ctx->stream));
-    CU(launch_conv(ctx->occ(), ctx->tmp(), ctx->width, ctx->height, 1, conv_weights(5, -10.f), ctx->stream));
+    CU(launch_conv_xy(ctx->tmp_vec(), ctx->normals(), ctx->width, ctx->height, 3, conv_weights(7, -5.f), a.tile_hit, 0,
+                      ctx->stream));
+    CU(launch_occlusion(ctx->tmp(), ctx->width, ctx->height, p->occ_radius, p->occ_n_points, ctx->depth(), a.tile_hit,
+                        ctx->d_taps, ctx->d_occ_queue, ctx->occ_frame++, ctx->sms, ctx->stream));
+    CU(launch_conv_xy(ctx->tmp(), ctx->occ(), ctx->width, ctx->height, 1, conv_weights(5, -10.f), a.tile_hit,
+                      p->occ_radius, ctx->stream));
     CU(launch_shading(ctx->out(), ctx->width, ctx->height, ctx->cam, p->occ_strength, ctx->normals(), ctx->depth(),
                       ctx->occ(), ctx->stream));
-    ctx->launches += 6;
+    ctx->launches += a.tile_hit ? 5 : 4;
   }
   ctx->last_method = 1;
   return end_render(ctx);
@@ -976,8 +1066,12 @@ static int iso_args(spv_ctx *ctx, const spv_iso_params *p, IsoArgs &a, const cha
   a.vol = volume_of(ctx);
   a.coarse = ctx->coarse;
   a.cgx = ctx->cgx; a.cgy = ctx->cgy; a.cgz = ctx->cgz;
+  a.top = ctx->top;
+  a.tgx = (ctx->cgx + 3) / 4; a.tgy = (ctx->cgy + 3) / 4; a.tgz = (ctx->cgz + 3) / 4;
   memcpy(a.box, p->box, sizeof a.box);
   a.iso_val = p->iso_val; a.gamma = p->gamma; a.max_steps = p->max_steps;
+  a.cta_warps = ctx->iso_cta_warps;
+  a.centre_out = ctx->iso_centre_out;
   a.tile_hit = ctx->d_tile_hit;
   a.skip = ctx->skipping != 0;
   a.width = ctx->width; a.height = ctx->height;
@@ -1028,13 +1122,15 @@ SPV_API int spv_iso_slab_post(spv_ctx *ctx, const spv_iso_params *p) {
   CU(launch_iso_slab(a, fmt_of(ctx), true, 2, k, k + ctx->n(), ctx->occ(), ctx->d_iso_err, ctx->stream));
   ctx->launches += 1;
   if (!(p->flags & SPV_ISO_RAW_ONLY)) {
+    rc = ensure_taps(ctx, p->occ_n_points);
+    if (rc) return rc;
     CU(launch_conv(ctx->normals(), ctx->tmp_vec(), ctx->width, ctx->height, 3, conv_weights(7, -5.f), ctx->stream));
     CU(launch_occlusion(ctx->occ(), ctx->width, ctx->height, p->occ_radius, p->occ_n_points, ctx->depth(), a.tile_hit,
-                        ctx->stream));
+                        ctx->d_taps, ctx->d_occ_queue, ctx->occ_frame++, ctx->sms, ctx->stream));
     CU(launch_conv(ctx->occ(), ctx->tmp(), ctx->width, ctx->height, 1, conv_weights(5, -10.f), ctx->stream));
     CU(launch_shading(ctx->out(), ctx->width, ctx->height, ctx->cam, p->occ_strength, ctx->normals(), ctx->depth(),
                       ctx->occ(), ctx->stream));
-    ctx->launches += 6;
+    ctx->launches += 7;
   }
   CU(cudaEventRecord(ctx->ev1, ctx->stream));
   return 0;

@@ -8,6 +8,10 @@
 
 namespace spv {
 
+#ifndef SPV_ISO_MINB
+#define SPV_ISO_MINB 6  // resident CTAs per SM the texture-unit search is compiled for (register budget)
+#endif
+
 // -------------------------------------------------------------------------------------------------------------
 // iso_surface.  One warp = one 8x4 pixel tile (same lane order as the MIP kernel).  The coarse search keeps the
 // reference's sample positions (pos += delta accumulation) and its first-crossing rule; the bracket refinement
@@ -148,15 +152,21 @@ __device__ __forceinline__ float iso_at(const Volume &V, const IsoRay &q, float 
 
 // exact empty-space test for sample t: a sample whose footprint lies in a cell with max <= iso cannot be "> iso",
 // one in a cell with min > iso cannot be "<= iso".  want_greater: are we looking for a sample > iso?
+// COARSE_FIRST: look at the 32^3 cell first (cheaper when most of them are decided); false where the caller has
+// just established that the ray is inside an undecided coarse cell.
+template <bool COARSE_FIRST = true>
 __device__ __forceinline__ bool iso_cell_may_hold(const IsoArgs &a, const IsoRay &q, float t, bool want_greater) {
   const Volume &V = a.vol;
   const float cx0 = q.u0 - 0.5f, cy0 = q.v0 - 0.5f, cz0 = q.w0 - 0.5f - (float)V.z_lo;
   const int ix = __float2int_rd(fmaf(t, q.du, cx0)), iy = __float2int_rd(fmaf(t, q.dv, cy0)),
             iz = __float2int_rd(fmaf(t, q.dw, cz0));
-  const int cx = min(max(ix >> (BRICK_SHIFT + 2), 0), a.cgx - 1), cy = min(max(iy >> (BRICK_SHIFT + 2), 0), a.cgy - 1),
-            cz = min(max(iz >> (BRICK_SHIFT + 2), 0), a.cgz - 1);
-  const float2 c = __ldg(a.coarse + ((size_t)cz * a.cgy + cy) * a.cgx + cx);
-  bool need = want_greater ? (c.y > a.iso_val) : !(c.x > a.iso_val);
+  bool need = true;
+  if (COARSE_FIRST) {
+    const int cx = min(max(ix >> (BRICK_SHIFT + 2), 0), a.cgx - 1), cy = min(max(iy >> (BRICK_SHIFT + 2), 0), a.cgy - 1),
+              cz = min(max(iz >> (BRICK_SHIFT + 2), 0), a.cgz - 1);
+    const float2 c = __ldg(a.coarse + ((size_t)cz * a.cgy + cy) * a.cgx + cx);
+    need = want_greater ? (c.y > a.iso_val) : !(c.x > a.iso_val);
+  }
   if (need) {
     const int bx = min(max(ix >> BRICK_SHIFT, 0), V.gx - 1), by = min(max(iy >> BRICK_SHIFT, 0), V.gy - 1),
               bz = min(max(iz >> BRICK_SHIFT, 0), V.gz - 1);
@@ -165,6 +175,84 @@ __device__ __forceinline__ bool iso_cell_may_hold(const IsoArgs &a, const IsoRay
   }
   return need;
 }
+
+// class of sample t by the 8^3 brick its footprint starts in: 2 = certainly <= iso, 1 = certainly > iso, 0 = fetch it
+__device__ __forceinline__ int iso_brick_class(const IsoArgs &a, const IsoRay &q, float t) {
+  const Volume &V = a.vol;
+  const float cx0 = q.u0 - 0.5f, cy0 = q.v0 - 0.5f, cz0 = q.w0 - 0.5f - (float)V.z_lo;
+  const int ix = __float2int_rd(fmaf(t, q.du, cx0)), iy = __float2int_rd(fmaf(t, q.dv, cy0)),
+            iz = __float2int_rd(fmaf(t, q.dw, cz0));
+  const int bx = min(max(ix >> BRICK_SHIFT, 0), V.gx - 1), by = min(max(iy >> BRICK_SHIFT, 0), V.gy - 1),
+            bz = min(max(iz >> BRICK_SHIFT, 0), V.gz - 1);
+  const float2 b = brick_at(V, bx, by, bz);
+  return !(b.y > a.iso_val) ? 2 : ((b.x > a.iso_val) ? 1 : 0);
+}
+
+// ---- hierarchical empty-space traversal --------------------------------------------------------------------------
+// The per-sample test above costs ~25 instructions for every one of the max_steps samples of a ray, although most
+// rays spend most of their length in cells that cannot hold a crossing.  The traversal below jumps over such a cell
+// in one step.  It stays exact: the texel index floor(fma(t, d, c)) of every axis is monotone in t, so if samples k and
+// e lie in the same cell, every sample in between does; the parametric exit is only a guess for e, which is then
+// checked with the very expression that classifies a single sample.
+struct IsoDda {
+  float cx0, cy0, cz0;  // footprint origin of sample 0 in texel units (z: local slices)
+  float rdu, rdv, rdw;  // 1 / step per axis (unused where the step is 0)
+};
+__device__ __forceinline__ IsoDda iso_dda(const IsoArgs &a, const IsoRay &q) {
+  IsoDda d;
+  d.cx0 = q.u0 - 0.5f; d.cy0 = q.v0 - 0.5f; d.cz0 = q.w0 - 0.5f - (float)a.vol.z_lo;
+  d.rdu = 1.f / q.du; d.rdv = 1.f / q.dv; d.rdw = 1.f / q.dw;
+  return d;
+}
+struct IsoLevel {
+  const float2 *grid;
+  int gx, gy, gz;
+};
+template <int SHIFT>
+__device__ __forceinline__ void iso_cell_of(const IsoRay &q, const IsoDda &d, const IsoLevel &L, float t, int &cx, int &cy,
+                                            int &cz) {
+  cx = min(max(__float2int_rd(fmaf(t, q.du, d.cx0)) >> SHIFT, 0), L.gx - 1);
+  cy = min(max(__float2int_rd(fmaf(t, q.dv, d.cy0)) >> SHIFT, 0), L.gy - 1);
+  cz = min(max(__float2int_rd(fmaf(t, q.dw, d.cz0)) >> SHIFT, 0), L.gz - 1);
+}
+// first sample after k (at most kend) that lies in another cell than sample k, whose cell is (cx, cy, cz)
+template <int SHIFT>
+__device__ __forceinline__ int iso_cell_exit(const IsoRay &q, const IsoDda &d, const IsoLevel &L, int k, int kend, int cx,
+                                             int cy, int cz) {
+  float te = (float)(kend - 1);
+  if (q.du > 0.f) { if (cx < L.gx - 1) te = fminf(te, ((float)((cx + 1) << SHIFT) - d.cx0) * d.rdu); }
+  else if (q.du < 0.f) { if (cx > 0) te = fminf(te, ((float)(cx << SHIFT) - d.cx0) * d.rdu); }
+  if (q.dv > 0.f) { if (cy < L.gy - 1) te = fminf(te, ((float)((cy + 1) << SHIFT) - d.cy0) * d.rdv); }
+  else if (q.dv < 0.f) { if (cy > 0) te = fminf(te, ((float)(cy << SHIFT) - d.cy0) * d.rdv); }
+  if (q.dw > 0.f) { if (cz < L.gz - 1) te = fminf(te, ((float)((cz + 1) << SHIFT) - d.cz0) * d.rdw); }
+  else if (q.dw < 0.f) { if (cz > 0) te = fminf(te, ((float)(cz << SHIFT) - d.cz0) * d.rdw); }
+  int e = max(__float2int_rd(te), k);  // guess: the last sample inside
+  int ex, ey, ez;
+  if (e > k) {
+    iso_cell_of<SHIFT>(q, d, L, (float)e, ex, ey, ez);
+    if (ex != cx || ey != cy || ez != cz) {
+      --e;
+      if (e > k) {
+        iso_cell_of<SHIFT>(q, d, L, (float)e, ex, ey, ez);
+        if (ex != cx || ey != cy || ez != cz) e = k;
+      }
+    }
+  }
+  return e + 1;
+}
+// class of the cell sample k lies in: 2 = every sample in it is <= iso, 1 = every sample is > iso, 0 = undecided;
+// kexit = first sample outside the cell when the class is not 0
+template <int SHIFT>
+__device__ __forceinline__ int iso_cell_class(const IsoArgs &a, const IsoRay &q, const IsoDda &d, const IsoLevel &L, int k,
+                                              int kend, int &kexit) {
+  int cx, cy, cz;
+  iso_cell_of<SHIFT>(q, d, L, (float)k, cx, cy, cz);
+  const float2 c = __ldg(L.grid + ((size_t)cz * L.gy + cy) * L.gx + cx);
+  const int cls = !(c.y > a.iso_val) ? 2 : ((c.x > a.iso_val) ? 1 : 0);
+  if (cls) kexit = iso_cell_exit<SHIFT>(q, d, L, k, kend, cx, cy, cz);
+  return cls;
+}
+constexpr int COARSE_SHIFT = BRICK_SHIFT + 2, TOP_SHIFT = BRICK_SHIFT + 4;
 
 // bracket refinement, 12-tap gradient and Phong shading at crossing sample i (iso_kernel.cl:140-215)
 template <int FMT, bool LINEAR>
@@ -210,19 +298,51 @@ __device__ __forceinline__ void iso_resolve(const IsoArgs &a, const IsoRay &q, i
   colVal = c_ambient + c_diffuse * diffuse + (diffuse > 0.f ? 1.f : 0.f) * c_specular * specular;
 }
 
-__device__ __forceinline__ void tile_pixel(unsigned &x, unsigned &y) {
+// CTA of 4 warps = 16x8 pixels (2x2 warp tiles), 2 warps = 16x4, 1 warp = 8x4.
+// CTA (bx, by) of the grid renders tile (tile_x, tile_y).  centre_out: the grid's rows and columns are dealt from the
+// middle of the image outwards (0 -> mid, 1 -> mid-1, 2 -> mid+1, ...), so the CTAs launched first are the ones whose
+// rays cross the most of the volume and the last ones launched are cheap: the launch ends without a tail of long CTAs.
+__device__ __forceinline__ unsigned centre_out(unsigned r, unsigned n) {
+  const unsigned mid = n >> 1;
+  return (r & 1u) ? mid - ((r + 1u) >> 1) : mid + (r >> 1);
+}
+__device__ __forceinline__ void tile_of_cta(bool centre, unsigned &tile_x, unsigned &tile_y) {
+  tile_x = centre ? centre_out(blockIdx.x, gridDim.x) : blockIdx.x;
+  tile_y = centre ? centre_out(blockIdx.y, gridDim.y) : blockIdx.y;
+}
+__device__ __forceinline__ void tile_pixel(unsigned &x, unsigned &y, bool centre = false) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
   const int ly = ((lane >> 1) & 1) | ((lane >> 2) & 2);
-  x = blockIdx.x * 16 + (warp & 1) * 8 + lx;
-  y = blockIdx.y * 8 + (warp >> 1) * 4 + ly;
+  const int cw = blockDim.x >= 64 ? 16 : 8, ch = blockDim.x >= 128 ? 8 : 4;
+  unsigned tx, ty;
+  tile_of_cta(centre, tx, ty);
+  x = tx * cw + (warp & 1) * 8 + lx;
+  y = ty * ch + (warp >> 1) * 4 + ly;
+}
+static dim3 iso_grid(int width, int height, int cta_warps) {
+  const int cw = cta_warps >= 2 ? 16 : 8, ch = cta_warps >= 4 ? 8 : 4;
+  return dim3((width + cw - 1) / cw, (height + ch - 1) / ch);
+}
+
+// One flag per 8x4 warp tile: does it contain a surface pixel?  (lets the occlusion pass skip empty regions.)  Every
+// warp owns its flag, so no CTA barrier and no atomics are needed.  All 32 lanes must call this.
+__device__ __forceinline__ void set_tile_flag(unsigned char *tile_hit, int width, int height, bool hit, bool centre = false) {
+  const unsigned any = __any_sync(0xffffffffu, hit);
+  if (!tile_hit || (threadIdx.x & 31) != 0) return;
+  const int warp = threadIdx.x >> 5;
+  unsigned cx, cy;
+  tile_of_cta(centre, cx, cy);
+  const int tx = cx * (blockDim.x >= 64 ? 2 : 1) + (warp & 1), ty = cy * (blockDim.x >= 128 ? 2 : 1) + (warp >> 1);
+  const int tiles_x = (width + 7) / 8, tiles_y = (height + 3) / 4;
+  if (tx < tiles_x && ty < tiles_y) tile_hit[ty * tiles_x + tx] = (unsigned char)(any != 0);
 }
 
 template <int FMT, bool LINEAR, bool SKIP>
-__global__ void __launch_bounds__(128) iso_fast_kernel(const IsoArgs a) {
+__global__ void __launch_bounds__(128, SPV_ISO_MINB) iso_fast_kernel(const IsoArgs a) {
   constexpr int BATCH = 8;
   unsigned x, y;
-  tile_pixel(x, y);
+  tile_pixel(x, y, a.centre_out != 0);
   const unsigned Nx = a.width, Ny = a.height;
   const bool inb = x < Nx && y < Ny;
   const size_t p = x + (size_t)Nx * y;
@@ -240,15 +360,29 @@ __global__ void __launch_bounds__(128) iso_fast_kernel(const IsoArgs a) {
     const int maxSteps = a.max_steps;
     const bool isGreater = iso_at<FMT, LINEAR>(V, q, 0.f) > isoVal;
     int i = maxSteps;
-    // Empty-space skipping (exact): samples that cannot be the first crossing are not fetched.  Coarse cells
-    // (32^3 texels) first, the 8^3 brick only where the coarse cell straddles the threshold.
-    for (int k0 = 1; k0 < maxSteps && !hitIso; k0 += BATCH) {
+    // Empty-space skipping (exact): samples that cannot be the first crossing are not fetched.  Cells of 128^3 and
+    // 32^3 texels that cannot hold a sample on the other side of the threshold are crossed in one step; inside the
+    // others every sample is classified by its 8^3 brick and the survivors are fetched BATCH at a time.
+    const IsoDda d = iso_dda(a, q);
+    const IsoLevel Ltop = {a.top, a.tgx, a.tgy, a.tgz}, Lco = {a.coarse, a.cgx, a.cgy, a.cgz};
+    const int skip_cls = isGreater ? 1 : 2;  // cells of this class hold no crossing
+    int k0 = 1;
+    while (k0 < maxSteps) {
+      if (SKIP) {
+        while (k0 < maxSteps) {
+          int kexit;
+          if (iso_cell_class<TOP_SHIFT>(a, q, d, Ltop, k0, maxSteps, kexit) == skip_cls) { k0 = kexit; continue; }
+          if (iso_cell_class<COARSE_SHIFT>(a, q, d, Lco, k0, maxSteps, kexit) == skip_cls) { k0 = kexit; continue; }
+          break;
+        }
+        if (k0 >= maxSteps) break;
+      }
       float v[BATCH];
       bool need[BATCH];
 #pragma unroll
       for (int j = 0; j < BATCH; ++j) {
         const float t = (float)min(k0 + j, maxSteps - 1);
-        need[j] = SKIP ? iso_cell_may_hold(a, q, t, !isGreater) : true;
+        need[j] = SKIP ? iso_cell_may_hold<false>(a, q, t, !isGreater) : true;
       }
 #pragma unroll
       for (int j = 0; j < BATCH; ++j) {
@@ -261,6 +395,8 @@ __global__ void __launch_bounds__(128) iso_fast_kernel(const IsoArgs a) {
           i = k0 + j;
           hitIso = true;
         }
+      if (hitIso) break;
+      k0 += BATCH;
     }
     if (hitIso) {
       iso_resolve<FMT, LINEAR>(a, q, i, isGreater, t_hit, normal, colVal);
@@ -275,9 +411,7 @@ __global__ void __launch_bounds__(128) iso_fast_kernel(const IsoArgs a) {
     a.normals[3 * p + 1] = normal.y;
     a.normals[3 * p + 2] = normal.z;
   }
-  // one flag per 16x8 CTA tile: does it contain a surface pixel?  (lets the occlusion pass skip empty regions)
-  const int any = __syncthreads_or(hitIso ? 1 : 0);
-  if (threadIdx.x == 0 && a.tile_hit) a.tile_hit[blockIdx.y * gridDim.x + blockIdx.x] = (unsigned char)(any != 0);
+  set_tile_flag(a.tile_hit, a.width, a.height, hitIso, a.centre_out != 0);
   if (a.stats) {
     atomicAdd(a.stats + 0, q.hit ? 1ull : 0ull);
     atomicAdd(a.stats + 1, (unsigned long long)nfetch);
@@ -312,18 +446,27 @@ __global__ void __launch_bounds__(128) iso_slab_search_kernel(const IsoArgs a, i
     const float isoVal = a.iso_val;
     int ka, kb;
     owned_interval_w(V, q.w0, q.dw, a.max_steps, ka, kb);
-    for (int kk = ka; kk < kb && (k1 == K_NONE || k0 == K_NONE); kk += BATCH) {
+    const IsoDda d = iso_dda(a, q);
+    const IsoLevel Ltop = {a.top, a.tgx, a.tgy, a.tgz}, Lco = {a.coarse, a.cgx, a.cgy, a.cgz};
+    int kk = ka;
+    while (kk < kb && (k1 == K_NONE || k0 == K_NONE)) {
+      if (SKIP) {
+        // a decided cell classifies all of its samples at once: only the first one can lower k1 / k0
+        int kexit, c = iso_cell_class<TOP_SHIFT>(a, q, d, Ltop, kk, kb, kexit);
+        if (!c) c = iso_cell_class<COARSE_SHIFT>(a, q, d, Lco, kk, kb, kexit);
+        if (c) {
+          if (c == 1) k1 = min(k1, kk); else k0 = min(k0, kk);
+          kk = kexit;
+          continue;
+        }
+      }
       float v[BATCH];
       int cls[BATCH];  // 0: fetch, 1: certainly > iso, 2: certainly <= iso, 3: not a sample
 #pragma unroll
       for (int j = 0; j < BATCH; ++j) {
         const int k = kk + j;
         cls[j] = k < kb ? 0 : 3;
-        if (SKIP && k < kb) {
-          const float t = (float)k;
-          if (!iso_cell_may_hold(a, q, t, true)) cls[j] = 2;        // cell max <= iso
-          else if (!iso_cell_may_hold(a, q, t, false)) cls[j] = 1;  // cell min > iso
-        }
+        if (SKIP && k < kb) cls[j] = iso_brick_class(a, q, (float)k);
       }
 #pragma unroll
       for (int j = 0; j < BATCH; ++j) {
@@ -336,6 +479,7 @@ __global__ void __launch_bounds__(128) iso_slab_search_kernel(const IsoArgs a, i
         const bool greater = cls[j] == 0 ? (v[j] > isoVal) : (cls[j] == 1);
         if (greater) k1 = min(k1, kk + j); else k0 = min(k0, kk + j);
       }
+      kk += BATCH;
     }
   }
   if (inb) {
@@ -400,8 +544,7 @@ __global__ void __launch_bounds__(128) iso_slab_fix_kernel(int width, int height
     hit = (k1 == 0 ? k0 : k1) != K_NONE;
     if (!hit) depth[p] = __int_as_float(0x7f800000);
   }
-  const int any = __syncthreads_or(hit ? 1 : 0);
-  if (threadIdx.x == 0 && tile_hit) tile_hit[blockIdx.y * gridDim.x + blockIdx.x] = (unsigned char)(any != 0);
+  set_tile_flag(tile_hit, width, height, hit);
 }
 
 template <int FMT>
@@ -441,12 +584,15 @@ template <int FMT>
 static cudaError_t launch_iso_dt(const IsoArgs &a, bool linear, bool exact, bool stats, cudaStream_t st) {
   dim3 grid((a.width + 15) / 16, (a.height + 7) / 8), block(128);
   if (!exact) {
+    const int cta_warps = a.cta_warps == 1 || a.cta_warps == 2 ? a.cta_warps : 4;
+    const dim3 fgrid = iso_grid(a.width, a.height, cta_warps), fblock(32 * cta_warps);
+    if (fgrid.y > 65535u) return cudaErrorInvalidValue;
     if (a.skip) {
-      if (linear) iso_fast_kernel<FMT, true, true><<<grid, block, 0, st>>>(a);
-      else iso_fast_kernel<FMT, false, true><<<grid, block, 0, st>>>(a);
+      if (linear) iso_fast_kernel<FMT, true, true><<<fgrid, fblock, 0, st>>>(a);
+      else iso_fast_kernel<FMT, false, true><<<fgrid, fblock, 0, st>>>(a);
     } else {
-      if (linear) iso_fast_kernel<FMT, true, false><<<grid, block, 0, st>>>(a);
-      else iso_fast_kernel<FMT, false, false><<<grid, block, 0, st>>>(a);
+      if (linear) iso_fast_kernel<FMT, true, false><<<fgrid, fblock, 0, st>>>(a);
+      else iso_fast_kernel<FMT, false, false><<<fgrid, fblock, 0, st>>>(a);
     }
     return cudaGetLastError();
   }
@@ -515,6 +661,122 @@ cudaError_t launch_conv(float *buf, float *tmp, int width, int height, int ncomp
   return cudaGetLastError();
 }
 
+// The screen-space passes only have work near surface pixels, which the march flags per 8x4 tile:
+//   occlusion  every tap lands within `radius` pixels of its pixel; if no tile in reach holds a surface pixel, every
+//              depth read is INFINITY, `depth < depth0` is false for every tap and the result is exactly 0
+//   blur       a window over zeros (the normals of non-surface pixels; the occlusion out of reach) is exactly +0
+// Flags of the tiles in reach of pixels [px0, px1] x [py0, py1], OR-ed over the strided share `first, first + step, ...`
+// of the calling thread.
+__device__ __forceinline__ int tiles_in_reach(const unsigned char *__restrict__ tile_hit, int tiles_x, int Nx, int Ny,
+                                              int px0, int px1, int py0, int py1, int radius, int first, int step) {
+  const int tx0 = max(px0 - radius, 0) / 8, tx1 = min(px1 + radius, Nx - 1) / 8;
+  const int ty0 = max(py0 - radius, 0) / 4, ty1 = min(py1 + radius, Ny - 1) / 4;
+  const int tw = tx1 - tx0 + 1, n = tw * (ty1 - ty0 + 1);
+  int mine = 0;
+  for (int t = first; t < n; t += step) mine |= tile_hit[(ty0 + t / tw) * tiles_x + tx0 + t % tw];
+  return mine;
+}
+
+// Both passes in one launch: the x pass of the rows a 32x16 output tile needs (Nh-1 halo rows) goes to shared memory,
+// the y pass reads it from there.  Every output is the same sequence of fp32 operations as conv_kernel<.,false>
+// followed by conv_kernel<.,true>, so the result is bit-identical to the two-launch form; it needs `in` != `out`.
+// A thread owns one FLOAT of the interleaved row (component k of pixel i sits at 3i+k; its x taps are 3 floats
+// apart), so every global and shared access of a warp is unit-stride.
+// NH > 0: the tap count is a compile-time constant and pixels whose taps all lie inside the image (nearly all) run an
+// unrolled loop with the weights in registers; NH == 0: any tap count up to 32.
+// tile_hit != nullptr: the input is known to be +0 on every pixel further than `reach` pixels from a flagged 8x4 tile;
+// a CTA whose taps see only such pixels stores zeros (what the arithmetic would give) and is done.
+constexpr int CONV_TH = 16;
+template <int NCOMP, int NH>
+__global__ void __launch_bounds__(256) conv_xy_kernel(const float *__restrict__ input, float *__restrict__ output, int Nx,
+                                                      int Ny, const ConvWeights cw,
+                                                      const unsigned char *__restrict__ tile_hit, int tiles_x, int reach) {
+  extern __shared__ float s_row[];  // [CONV_TH + Nh - 1][32]
+  const int Nh = NH > 0 ? NH : cw.nh, R = Nh / 2;
+  const int c = blockIdx.x * 32 + threadIdx.x;  // column of the interleaved image (NCOMP * Nx floats per row)
+  const int i = c / NCOMP, y0 = blockIdx.y * CONV_TH;
+  const int rows = CONV_TH + Nh - 1;
+  const int pitch = NCOMP * Nx;
+  if (tile_hit) {
+    const int px0 = (int)(blockIdx.x * 32) / NCOMP, px1 = min((int)(blockIdx.x * 32 + 31) / NCOMP, Nx - 1);
+    const int live = __syncthreads_or(tiles_in_reach(tile_hit, tiles_x, Nx, Ny, px0, px1, y0, min(y0 + CONV_TH, Ny) - 1,
+                                                     reach + Nh, threadIdx.y * 32 + threadIdx.x, 256));
+    if (!live) {
+      if (c < pitch)
+        for (int r = threadIdx.y; r < CONV_TH && y0 + r < Ny; r += blockDim.y) output[(size_t)(y0 + r) * pitch + c] = 0.f;
+      return;
+    }
+  }
+  float w[NH > 0 ? NH : 1];
+  float sum_full = 0.f;  // the weight sum of a pixel with all its taps, added up in tap order
+  if (NH > 0) {
+#pragma unroll
+    for (int ht = 0; ht < NH; ++ht) {
+      w[ht] = cw.w[ht];
+      sum_full += w[ht];
+    }
+  }
+  if (c < pitch) {
+    const int h_start = ((i - R) < 0) ? R - i : 0;
+    const int h_end = ((i + R) >= Nx) ? Nh - (i + R - Nx + 1) : Nh;
+    const bool inner = NH > 0 && h_start == 0 && h_end == Nh;
+    for (int r = threadIdx.y; r < rows; r += blockDim.y) {
+      const int j = y0 - R + r;
+      if (j < 0 || j >= Ny) continue;
+      const float *row = input + (size_t)j * pitch + (c - NCOMP * R);  // tap ht at row[NCOMP * ht]
+      float res = 0.f, sum_val = 0.f;
+      if (inner) {
+#pragma unroll
+        for (int ht = 0; ht < (NH > 0 ? NH : 1); ++ht) res += w[ht] * row[NCOMP * ht];
+        sum_val = sum_full;
+      } else {
+        for (int ht = h_start; ht < h_end; ++ht) {
+          const float val = cw.w[ht];
+          sum_val += val;
+          res += val * row[NCOMP * ht];
+        }
+      }
+      s_row[r * 32 + threadIdx.x] = res / sum_val;
+    }
+  }
+  __syncthreads();
+  if (c >= pitch) return;
+  for (int r = threadIdx.y; r < CONV_TH; r += blockDim.y) {
+    const int j = y0 + r;
+    if (j >= Ny) break;
+    const int h_start = ((j - R) < 0) ? R - j : 0;
+    const int h_end = ((j + R) >= Ny) ? Nh - (j + R - Ny + 1) : Nh;
+    const float *col = s_row + r * 32 + threadIdx.x;  // tap ht at col[32 * ht]
+    float res = 0.f, sum_val = 0.f;
+    if (NH > 0 && h_start == 0 && h_end == Nh) {
+#pragma unroll
+      for (int ht = 0; ht < (NH > 0 ? NH : 1); ++ht) res += w[ht] * col[32 * ht];
+      sum_val = sum_full;
+    } else {
+      for (int ht = h_start; ht < h_end; ++ht) {
+        const float val = cw.w[ht];
+        sum_val += val;
+        res += val * col[32 * ht];
+      }
+    }
+    output[(size_t)j * pitch + c] = res / sum_val;
+  }
+}
+
+cudaError_t launch_conv_xy(const float *in, float *out, int width, int height, int ncomp, const ConvWeights &w,
+                           const unsigned char *tile_hit, int reach, cudaStream_t st) {
+  if (in == out || w.nh < 1 || w.nh > 32 || (ncomp != 1 && ncomp != 3)) return cudaErrorInvalidValue;
+  dim3 block(32, 8), grid((ncomp * width + 31) / 32, (height + CONV_TH - 1) / CONV_TH);
+  if (grid.y > 65535u) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(CONV_TH + w.nh - 1) * 32 * sizeof(float);
+  const int tx = (width + 7) / 8;
+  if (ncomp == 3 && w.nh == 7) conv_xy_kernel<3, 7><<<grid, block, smem, st>>>(in, out, width, height, w, tile_hit, tx, reach);
+  else if (ncomp == 1 && w.nh == 5) conv_xy_kernel<1, 5><<<grid, block, smem, st>>>(in, out, width, height, w, tile_hit, tx, reach);
+  else if (ncomp == 1) conv_xy_kernel<1, 0><<<grid, block, smem, st>>>(in, out, width, height, w, tile_hit, tx, reach);
+  else conv_xy_kernel<3, 0><<<grid, block, smem, st>>>(in, out, width, height, w, tile_hit, tx, reach);
+  return cudaGetLastError();
+}
+
 // -------------------------------------------------------------------------------------------------------------
 // utils.cl:10-38, uint32 wrap-around arithmetic
 __device__ __forceinline__ uint32_t lcg_hash(uint32_t x, uint32_t y) {
@@ -531,62 +793,142 @@ __device__ __forceinline__ float rand_int_cl(uint32_t x, uint32_t y, int start, 
 }
 
 // The four rand_int() arguments of a tap depend on the tap index only (occlusion.cl:60,62): they are evaluated once
-// per CTA into shared memory, which halves the hash evaluations per pixel (2 instead of 4 per tap, 10 LCG rounds
-// each).  Values are identical to evaluating them per pixel.
-__global__ void __launch_bounds__(256) occlusion_kernel(float *__restrict__ d_output, int Nx, int Ny, int radius,
-                                                        int number_points, const float *__restrict__ input_depth,
-                                                        const unsigned char *__restrict__ tile_hit, int tiles_x) {
-  extern __shared__ float s_tap[];  // 4 floats per tap
-  for (unsigned i = threadIdx.y * blockDim.x + threadIdx.x; i < (unsigned)number_points; i += blockDim.x * blockDim.y) {
-    s_tap[4 * i + 0] = rand_int_cl(i, i * i, 0, 1000);
-    s_tap[4 * i + 1] = rand_int_cl(i * i, i, 294, 97701);
-    s_tap[4 * i + 2] = rand_int_cl(i * i, i, 0, 1997);
-    s_tap[4 * i + 3] = rand_int_cl(i, i * i, 569, 17633);
-  }
-  // Every tap lands within `radius` pixels of its pixel.  If no 16x8 tile overlapping this CTA's pixels grown by
-  // `radius` holds a surface pixel, every depth read is INFINITY, `depth < depth0` is false for every tap and the
-  // result is exactly 0: skip the hashing.
-  int reach = 1;
-  if (tile_hit) {
-    const int x0 = (int)(blockIdx.x * blockDim.x) - radius, x1 = (int)(blockIdx.x * blockDim.x + blockDim.x - 1) + radius;
-    const int y0 = (int)(blockIdx.y * blockDim.y) - radius, y1 = (int)(blockIdx.y * blockDim.y + blockDim.y - 1) + radius;
-    const int tx0 = max(x0, 0) / 16, tx1 = min(x1, Nx - 1) / 16, ty0 = max(y0, 0) / 8, ty1 = min(y1, Ny - 1) / 8;
-    const int tw = tx1 - tx0 + 1, n = tw * (ty1 - ty0 + 1);
-    int mine = 0;
-    for (int t = threadIdx.y * blockDim.x + threadIdx.x; t < n; t += blockDim.x * blockDim.y)
-      mine |= tile_hit[(ty0 + t / tw) * tiles_x + tx0 + t % tw];
-    reach = __syncthreads_or(mine);
-  } else {
-    __syncthreads();
-  }
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= Nx || y >= Ny) return;
-  if (!reach) {
-    d_output[x + (size_t)Nx * y] = 0.f;
-    return;
-  }
+// into a table (occ_taps_kernel, cached by the context), which halves the hash evaluations per pixel (2 instead of 4
+// per tap, 10 LCG rounds each).  Values are identical to evaluating them per pixel.
+__global__ void occ_taps_kernel(float4 *taps, int n) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)n) return;
+  taps[i] = make_float4(rand_int_cl(i, i * i, 0, 1000), rand_int_cl(i * i, i, 294, 97701), rand_int_cl(i * i, i, 0, 1997),
+                        rand_int_cl(i, i * i, 569, 17633));
+}
+cudaError_t launch_occ_taps(float4 *taps, int n, cudaStream_t st) {
+  occ_taps_kernel<<<(n + 127) / 128, 128, 0, st>>>(taps, n);
+  return cudaGetLastError();
+}
+
+// occlusion.cl:54-77 for one pixel
+__device__ __forceinline__ float occlusion_pixel(int x, int y, int Nx, int Ny, int radius, int number_points,
+                                                 const float *__restrict__ input_depth, const float4 *__restrict__ taps) {
   const float MPI_2 = 6.2831853071795f;
   const float depth0 = input_depth[x + (size_t)y * Nx];
   float occ = 0.f;
   for (unsigned i = 0; i < (unsigned)number_points; ++i) {
-    const float r = (float)(unsigned)radius * random_cl((uint32_t)((float)x + s_tap[4 * i + 0]),
-                                                        (uint32_t)((float)y + s_tap[4 * i + 1]));
-    const float phi = MPI_2 * random_cl((uint32_t)((float)x + s_tap[4 * i + 2]),
-                                        (uint32_t)((float)y + s_tap[4 * i + 3]));
+    const float4 tp = __ldg(taps + i);
+    const float r = (float)(unsigned)radius * random_cl((uint32_t)((float)x + tp.x), (uint32_t)((float)y + tp.y));
+    const float phi = MPI_2 * random_cl((uint32_t)((float)x + tp.z), (uint32_t)((float)y + tp.w));
     const int x2 = clampi((int)((float)x + r * cosf(phi)), 0, Nx - 1);
     const int y2 = clampi((int)((float)y + r * sinf(phi)), 0, Ny - 1);
     const float depth = input_depth[x2 + (size_t)y2 * Nx];
     occ += (depth < depth0 ? 1.f : 0.f);
   }
-  d_output[x + (size_t)Nx * y] = occ / (float)(unsigned)number_points;
+  return occ / (float)(unsigned)number_points;
+}
+
+// Plain form, one CTA per block of 32x2 pixels (used when there are no tile flags: the exact-sampler path).
+__global__ void __launch_bounds__(64) occlusion_kernel(float *__restrict__ d_output, int Nx, int Ny, int radius,
+                                                       int number_points, const float *__restrict__ input_depth,
+                                                       const unsigned char *__restrict__ tile_hit, int tiles_x,
+                                                       const float4 *__restrict__ taps) {
+  int reach = 1;
+  if (tile_hit) {
+    const int bx = blockIdx.x * blockDim.x, by = blockIdx.y * blockDim.y;
+    reach = __syncthreads_or(tiles_in_reach(tile_hit, tiles_x, Nx, Ny, bx, bx + blockDim.x - 1, by, by + blockDim.y - 1,
+                                            radius, threadIdx.y * blockDim.x + threadIdx.x, blockDim.x * blockDim.y));
+  }
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= Nx || y >= Ny) return;
+  d_output[x + (size_t)Nx * y] = reach ? occlusion_pixel(x, y, Nx, Ny, radius, number_points, input_depth, taps) : 0.f;
+}
+
+// Queue form.  Only the blocks near a surface do any work (60 hash chains per pixel) and they are few and clustered:
+// handed out as CTAs they land unevenly on the SMs (measured: SMs busy 62 % of the launch).  Instead
+//   occ_list_kernel   one warp per 32x2 block: out of reach -> writes the zeros, in reach -> appends the block to a list
+//   occ_queue_kernel  a fixed grid (a few CTAs per SM) pulls work items off the list until it is empty
+// The counters {count, head} are double-buffered by frame parity; the list kernel clears the other pair for the next
+// frame, so there is no memset on the stream.
+constexpr int OCC_BW = 32, OCC_BH = 2;
+__global__ void __launch_bounds__(256) occ_list_kernel(float *__restrict__ d_output, int Nx, int Ny, int radius,
+                                                       const unsigned char *__restrict__ tile_hit, int tiles_x, int obx,
+                                                       int n_ob, unsigned *__restrict__ cnt, unsigned *__restrict__ cnt_next,
+                                                       unsigned *__restrict__ list) {
+  const int ob = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (ob == 0 && lane == 0) cnt_next[0] = cnt_next[1] = 0u;
+  if (ob >= n_ob) return;
+  const int px = (ob % obx) * OCC_BW, py = (ob / obx) * OCC_BH;
+  const int mine = tiles_in_reach(tile_hit, tiles_x, Nx, Ny, px, px + OCC_BW - 1, py, py + OCC_BH - 1, radius, lane, 32);
+  if (__any_sync(0xffffffffu, mine != 0)) {
+    if (lane == 0) list[atomicAdd(cnt, 1u)] = (unsigned)ob;
+  } else {
+    const int x = px + lane;
+    if (x < Nx) {
+#pragma unroll
+      for (int r = 0; r < OCC_BH; ++r)
+        if (py + r < Ny) d_output[x + (size_t)Nx * (py + r)] = 0.f;
+    }
+  }
+}
+
+// A work item is 8 pixels of a row; a warp gives 4 lanes to each pixel, lane g takes taps g, g+4, ... and the four
+// partial counts are added with shuffles (sums of 0/1 floats: exact in any order, so the result is unchanged).  Small
+// items (a quarter of a warp-row's 30 taps) keep the SMs evenly loaded up to the last ~2 us.
+__global__ void __launch_bounds__(128) occ_queue_kernel(float *__restrict__ d_output, int Nx, int Ny, int radius,
+                                                        int number_points, const float *__restrict__ input_depth,
+                                                        const float4 *__restrict__ taps, int obx,
+                                                        unsigned *__restrict__ cnt, const unsigned *__restrict__ list) {
+  __shared__ unsigned s_base;
+  constexpr unsigned ITEMS_PER_BLOCK = OCC_BW * OCC_BH / 8;
+  const unsigned total = cnt[0] * ITEMS_PER_BLOCK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane & 3;
+  const float MPI_2 = 6.2831853071795f;
+  for (;;) {
+    if (threadIdx.x == 0) s_base = atomicAdd(cnt + 1, 4u);
+    __syncthreads();
+    const unsigned base = s_base;
+    __syncthreads();
+    if (base >= total) break;
+    const unsigned item = base + warp;
+    if (item >= total) continue;
+    const int ob = (int)list[item / ITEMS_PER_BLOCK], sub = (int)(item % ITEMS_PER_BLOCK);
+    const int x = (ob % obx) * OCC_BW + (sub % (OCC_BW / 8)) * 8 + (lane >> 2), y = (ob / obx) * OCC_BH + sub / (OCC_BW / 8);
+    const bool inb = x < Nx && y < Ny;
+    float occ = 0.f;
+    if (inb) {  // occlusion.cl:54-77, taps g, g + 4, ...
+      const float depth0 = input_depth[x + (size_t)y * Nx];
+      for (unsigned i = g; i < (unsigned)number_points; i += 4) {
+        const float4 tp = __ldg(taps + i);
+        const float r = (float)(unsigned)radius * random_cl((uint32_t)((float)x + tp.x), (uint32_t)((float)y + tp.y));
+        const float phi = MPI_2 * random_cl((uint32_t)((float)x + tp.z), (uint32_t)((float)y + tp.w));
+        const int x2 = clampi((int)((float)x + r * cosf(phi)), 0, Nx - 1);
+        const int y2 = clampi((int)((float)y + r * sinf(phi)), 0, Ny - 1);
+        occ += (input_depth[x2 + (size_t)y2 * Nx] < depth0 ? 1.f : 0.f);
+      }
+    }
+    occ += __shfl_xor_sync(0xffffffffu, occ, 1);
+    occ += __shfl_xor_sync(0xffffffffu, occ, 2);
+    if (inb && g == 0) d_output[x + (size_t)Nx * y] = occ / (float)(unsigned)number_points;
+  }
+}
+
+size_t occ_queue_bytes(int width, int height) {
+  const size_t n_ob = (size_t)((width + OCC_BW - 1) / OCC_BW) * ((height + OCC_BH - 1) / OCC_BH);
+  return (4 + n_ob) * sizeof(unsigned);  // [2 parities][count, head] + the list
 }
 
 cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int n_points, const float *depth,
-                             const unsigned char *tile_hit, cudaStream_t st) {
-  dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
-  const size_t smem = (size_t)(n_points > 0 ? n_points : 1) * 4 * sizeof(float);
-  if (smem > 48 * 1024) return cudaErrorInvalidValue;  // > 3072 taps
-  occlusion_kernel<<<grid, block, smem, st>>>(occ, width, height, radius, n_points, depth, tile_hit, (width + 15) / 16);
+                             const unsigned char *tile_hit, const float4 *taps, unsigned *queue, unsigned frame, int sms,
+                             cudaStream_t st) {
+  if (tile_hit && queue) {
+    const int obx = (width + OCC_BW - 1) / OCC_BW, n_ob = obx * ((height + OCC_BH - 1) / OCC_BH);
+    unsigned *cnt = queue + 2 * (frame & 1u), *cnt_next = queue + 2 * ((frame + 1u) & 1u), *list = queue + 4;
+    occ_list_kernel<<<(n_ob + 7) / 8, 256, 0, st>>>(occ, width, height, radius, tile_hit, (width + 7) / 8, obx, n_ob, cnt,
+                                                    cnt_next, list);
+    occ_queue_kernel<<<(sms > 0 ? sms : 148) * 5, 128, 0, st>>>(occ, width, height, radius, n_points, depth, taps, obx, cnt,
+                                                                 list);
+    return cudaGetLastError();
+  }
+  dim3 block(32, 2), grid((width + 31) / 32, (height + 1) / 2);
+  if (grid.y > 65535) return cudaErrorInvalidValue;
+  occlusion_kernel<<<grid, block, 0, st>>>(occ, width, height, radius, n_points, depth, tile_hit, (width + 7) / 8, taps);
   return cudaGetLastError();
 }
 

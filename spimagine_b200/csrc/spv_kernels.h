@@ -39,13 +39,17 @@ struct IsoArgs {
   Volume vol;
   const float2 *coarse;
   int cgx, cgy, cgz;
+  const float2 *top;  // min/max over 4^3 coarse cells (128^3 texels)
+  int tgx, tgy, tgz;
   float box[6];
   float iso_val, gamma;
   int max_steps;
   int skip;  // empty-space skipping on the min/max grids (texture-unit path)
+  int cta_warps;  // warps per CTA of the texture-unit search: 1, 2 or 4 (default; tuning knob 4)
+  int centre_out; // CTAs are dealt from the image centre outwards (tuning knob 5, default on)
   int width, height;
   float *out, *alpha, *depth, *normals;
-  unsigned char *tile_hit;  // one flag per 16x8 tile (texture-unit path) or nullptr
+  unsigned char *tile_hit;  // one flag per 8x4 warp tile (texture-unit path) or nullptr
   unsigned long long *stats;
 };
 
@@ -86,17 +90,31 @@ cudaError_t launch_iso_slab(const IsoArgs &a, int dtype, bool linear, int phase,
 // buf -> tmp (x pass), tmp -> buf (y pass); ncomp = 1 (conv_x/conv_y) or 3 (conv_vec_x/conv_vec_y)
 cudaError_t launch_conv(float *buf, float *tmp, int width, int height, int ncomp, const ConvWeights &w,
                         cudaStream_t st);
+// both passes in one launch (in != out), bit-identical to launch_conv.  tile_hit (may be null): `in` is +0 on every
+// pixel further than `reach` pixels from a flagged 8x4 tile; such regions are filled with zeros without the arithmetic
+cudaError_t launch_conv_xy(const float *in, float *out, int width, int height, int ncomp, const ConvWeights &w,
+                           const unsigned char *tile_hit, int reach, cudaStream_t st);
+// taps[i] = the four rand_int() values of occlusion tap i (they depend on i only)
+cudaError_t launch_occ_taps(float4 *taps, int n, cudaStream_t st);
+// queue (occ_queue_bytes, zero-initialised) + tile flags: only the pixel blocks in reach of a surface are computed, handed
+// out dynamically; `frame` must change parity from call to call on the same queue.  Without: every block, in place.
+size_t occ_queue_bytes(int width, int height);
 cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int n_points, const float *depth,
-                             const unsigned char *tile_hit, cudaStream_t st);
+                             const unsigned char *tile_hit, const float4 *taps, unsigned *queue, unsigned frame, int sms,
+                             cudaStream_t st);
 cudaError_t launch_shading(float *out, int width, int height, const Camera &cam, float occ_strength,
                            const float *normals, const float *depth, const float *occ, cudaStream_t st);
 
 // min/max brick grids of the resident volume (built from the point texture)
 cudaError_t launch_build_bricks(const Volume &vol, int dtype, int local_nz, float2 *bricks, float2 *coarse, int cgx,
-                                int cgy, int cgz, float *minmax /* [2] device */, cudaStream_t st);
+                                int cgy, int cgz, float2 *top, float *minmax /* [2] device */, cudaStream_t st);
 
 // LAYOUT_ZPAIR ingest: dst (linear, z-major) = {src[z], src[min(z+1, nz-1)]} for z in [zbeg, zend)
 cudaError_t launch_pair(const void *src, void *dst, int dtype, size_t slice, int nz, int zbeg, int zend,
                         cudaStream_t st);
+
+// ingest of host arrays of another element type: dst[i] = (dst type) src[i], n elements (src_type: SPV_SRC_*)
+size_t src_elem_size(int src_type);
+cudaError_t launch_convert(const void *src, void *dst, int src_type, int dtype, size_t n, cudaStream_t st);
 
 }  // namespace spv

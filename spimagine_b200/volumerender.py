@@ -181,7 +181,8 @@ class VolumeRenderer(object):
 
     def _get_downsampled_data_slices(self, data):
         """in case data is bigger than the memory budget, returns the strided slices to render, else None"""
-        Nstep = int(np.ceil((1. * data.nbytes / self.memMax) ** (1. / 3)))
+        nbytes = data.size * np.dtype(self.dtype).itemsize  # of the volume as it will be resident
+        Nstep = int(np.ceil((1. * nbytes / self.memMax) ** (1. / 3)))
         slices = tuple(slice(0, d, Nstep) for d in data.shape)
         if Nstep > 1:
             logger.info("downsample image by factor of  %s" % Nstep)
@@ -219,7 +220,9 @@ class VolumeRenderer(object):
             _data = data
         else:
             print("converting type from %s to %s" % (data.dtype.type, self.dtype))
-            _data = data.astype(self.dtype, copy=False)
+            # the reference converts on the host here (astype); update_data converts on the device instead where
+            # the element type allows it, so the array keeps its type until then
+            _data = data if self._device_converts(data.dtype) else data.astype(self.dtype, copy=False)
         self.dataSlices = self._get_downsampled_data_slices(_data)
         if self.dataSlices is not None:
             self.set_shape(_data[self.dataSlices].shape[::-1])
@@ -229,6 +232,11 @@ class VolumeRenderer(object):
         self.update_data(_data, copyData=copyData)
         logger.debug("update data: %s ms" % (1000. * (time() - t)))
         self.update_matrices()
+
+    @staticmethod
+    def _device_converts(dtype):
+        dtype = np.dtype(dtype)
+        return dtype in _lib.SRC_CODES and dtype.isnative
 
     def set_shape(self, dataShape):
         """dataShape = (Nx, Ny, Nz); the device array is (re)allocated on the next update_data."""
@@ -243,15 +251,25 @@ class VolumeRenderer(object):
             self._data = data[self.dataSlices].copy()
         else:
             self._data = data.copy() if copyData else data
+        src_type = None
         if self._data.dtype != self.dtype:
-            self._data = self._data.astype(self.dtype, copy=False)
+            if self._device_converts(self._data.dtype):
+                src_type = _lib.SRC_CODES[np.dtype(self._data.dtype)]  # converted inside the ingest pipeline
+            else:
+                self._data = self._data.astype(self.dtype, copy=False)
         host = np.ascontiguousarray(self._data)
         Nx, Ny, Nz = self.dataImg.shape
         if host.shape != (Nz, Ny, Nx):
             raise ValueError("data shape %s does not match the volume shape %s" % (host.shape, (Nz, Ny, Nx)))
+        code = _lib.DTYPE_CODES[np.dtype(self.dtype)]
         if getattr(self, "_need_alloc", True):
-            rc = self._lib.spv_set_volume(self._ctx, host.ctypes.data, _lib.DTYPE_CODES[host.dtype], Nx, Ny, Nz)
+            if src_type is None:
+                rc = self._lib.spv_set_volume(self._ctx, host.ctypes.data, code, Nx, Ny, Nz)
+            else:
+                rc = self._lib.spv_set_volume_from(self._ctx, host.ctypes.data, src_type, code, Nx, Ny, Nz)
             self._need_alloc = False
+        elif src_type is not None:
+            rc = self._lib.spv_update_volume_from(self._ctx, host.ctypes.data, src_type)
         elif pinned and host is data:
             rc = self._lib.spv_update_volume_async(self._ctx, host.ctypes.data)
         else:

@@ -381,6 +381,38 @@ def test_iso_skipping_does_not_change_the_image(layout):
             assert np.isfinite(res[0][1]).sum() > 500   # the scene does show a surface
 
 
+@pytest.mark.parametrize("shape", [(300, 300, 300), (150, 330, 270)])
+def test_iso_cell_traversal_is_exact_on_large_and_anisotropic_volumes(shape):
+    """The hierarchical traversal (128^3 / 32^3 cells crossed in one step) only pays off on volumes with several
+    top-level cells per axis; it must stay invisible there too, for non-cubic grids, anisotropic voxels, a reduced
+    box, a box larger than the volume (clamp-to-edge samples) and tilted cameras."""
+    data = scenes.vol_g(0, np.uint16, seed=7, shape=shape)
+    g = _renderer((256, 192))
+    g.set_data(data)
+    g.set_units([1., .7, 2.1])
+    g.enable_stats(True)
+    M2 = np.dot(mat4_translate(0.1, -0.05, -3.1), np.dot(mat4_rotation(0.8, 0.3, 1, 0.25), mat4_rotation(0.5, 1, 0, 0)))
+    cams = [scenes.gui_camera(0.4, 3.4), (M2, mat4_perspective(50, 1., .1, 10)), scenes.gui_camera(2.2, 0.3)]
+    boxes = [[-1, 1, -1, 1, -1, 1], [-.6, .9, -.8, .5, -1, .7], [-1.3, 1.3, -1.2, 1.2, -1.4, 1.4]]
+    n_hit = 0
+    for (M, P), box in zip(cams, boxes):
+        g.set_modelView(M)
+        g.set_projection(P)
+        g.set_box_boundaries(box)
+        for frac in (.08, .5):
+            res = []
+            for skip in (False, True):
+                g.set_skipping(skip)
+                g.render(maxVal=2 * frac * 60000., method="iso_surface")
+                res.append((g.output.copy(), g.output_depth.copy(), g.output_normals.copy(), g.output_alpha.copy(),
+                            g.output_occlusion.copy(), g.last_stats()))
+            for a, b in zip(res[0][:5], res[1][:5]):
+                assert np.array_equal(a, b)
+            assert res[1][5][1] < res[0][5][1]
+            n_hit += int(np.isfinite(res[0][1]).sum())
+    assert n_hit > 5000
+
+
 def test_iso_post_passes_on_the_tmu_path(oracle_mod):
     """The texture-unit path skips the occlusion hashing where no surface pixel is within reach and shades only
     surface pixels; both shortcuts must be invisible: recompute occlusion -> blur -> shading with the oracle from

@@ -228,6 +228,58 @@ def test_ingest_paths_agree(dtype, layout):
     rend2.close()
 
 
+@pytest.mark.parametrize("target,layout", [(np.float32, "3d"), (np.uint16, "zpair"), (np.uint16, "3d"), (np.uint8, "zpair")])
+def test_device_conversion_equals_host_astype(target, layout):
+    """set_data / update_data of an array whose element type is not a texel type: the reference converts on the host
+    (`astype(self.dtype)`, volumerender.py:245-246, 290-291); here the source bytes travel and are converted on the
+    device.  Every voxel must come out as numpy's astype would have made it -- integers wrap, floats round to
+    nearest (float target) or truncate (integer targets) -- for sources larger than one pipeline chunk."""
+    from spimagine_b200 import pinned_empty
+    rng = np.random.default_rng(5)
+    shape = (45, 384, 512)
+    hi = 250 if np.dtype(target) == np.uint8 else 60000
+    sources = {
+        np.int8: rng.integers(-128, 128, shape).astype(np.int8),
+        np.int16: rng.integers(-32768, 32768, shape).astype(np.int16),
+        np.int32: rng.integers(-70000, 200000, shape).astype(np.int32),
+        np.uint32: rng.integers(0, 2 ** 32, shape, dtype=np.uint64).astype(np.uint32),
+        np.int64: rng.integers(-2 ** 40, 2 ** 40, shape).astype(np.int64),
+        np.uint64: rng.integers(0, 2 ** 63, shape, dtype=np.uint64),
+        np.float16: (rng.random(shape) * min(hi, 2000)).astype(np.float16),
+        np.float64: rng.random(shape) * hi,
+        np.bool_: rng.random(shape) > .5,
+    }
+    if np.dtype(target) == np.float32:   # a float source with more mantissa than the texel: rounding matters
+        sources[np.float64] = rng.random(shape) * 1e6 - 5e5
+    idx = np.stack([rng.integers(0, s, 6000) for s in shape], 1)  # (z, y, x)
+    pos = ((idx[:, ::-1] + 0.5) / np.array(shape[::-1])).astype(np.float32)
+    rend = _renderer((64, 64), interpolation="nearest", sampler="exact")
+    rend.set_layout(layout)
+    rend.set_dtype(target)
+    first = True
+    for st, a in sources.items():
+        want = a.astype(target)
+        if first:
+            rend.set_data(a)                       # allocating path: spv_set_volume_from
+            first = False
+        else:
+            rend.update_data(a)                    # spv_update_volume_from
+        assert rend.dtype == target and rend.dataImg.dtype == np.dtype(target)
+        got = rend.sample_points(pos)
+        assert np.array_equal(got, want[idx[:, 0], idx[:, 1], idx[:, 2]].astype(np.float32)), st
+        assert rend.data_min_max == (float(want.min()), float(want.max())), st
+    # a page-locked source of another element type is converted as well (synchronously)
+    p = pinned_empty(shape, np.int16)
+    p[...] = sources[np.int16]
+    rend.update_data(p, pinned=True)
+    want = sources[np.int16].astype(target)
+    assert np.array_equal(rend.sample_points(pos), want[idx[:, 0], idx[:, 1], idx[:, 2]].astype(np.float32))
+    # unsupported element types still raise when autoConvert is off, like the reference
+    with pytest.raises(NotImplementedError):
+        rend.set_data(sources[np.int32], autoConvert=False)
+    rend.close()
+
+
 # ----------------------------------------------------------------------------- timelapse playback
 def test_timelapse_player_resident_and_streamed():
     """Frame sharding for 3D+t playback: every rank's player shows exactly its own time points, resident and
