@@ -473,7 +473,9 @@ def run_iso(args, rank, local_rank, world):
             "e2e": {"value": args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 2 * W * W * 4,
                     "note": "set_modelView + render(method='iso_surface'): output + alpha read back per frame (8 MiB); depth, normals and occlusion stay on the device until they are looked at (lazy attributes)"},
             "surface_pixels_last": hit_px, "image_sha1_first8": digest.hexdigest(),
-            "gpu_launches": args.steps * (7 if world == 1 else 9)}))
+            # iso_fast, blur, occlusion list + queue, blur, shading; sort-last: search, resolve, fix-up, 2+2 blur
+            # launches, occlusion list + queue, shading (the two NCCL reductions are not counted)
+            "gpu_launches": args.steps * (6 if world == 1 else 10)}))
     rend.close()
     if world > 1:
         dist.destroy_process_group()

@@ -42,6 +42,7 @@ for variant in os.environ.get("EXP_ISO_VARIANTS", "4:1").split(","):
     cta_warps, centre = (int(v) for v in variant.split(":"))
     lib.spv_set_tuning(ctx, 4, cta_warps)
     lib.spv_set_tuning(ctx, 5, centre)
+    lib.spv_set_tuning(ctx, 6, int(os.environ.get("EXP_OCC_CTAS", "5")))
     print("iso search CTA = %d warp(s), centre-out order %d" % (cta_warps, centre))
     for flags, name in ((_lib.ISO_RAW_ONLY, "iso_surface kernel alone"), (0, "full chain (5 launches)")):
         p = _lib.IsoParams(rend._box(), maxVal / 2, 1., 200, .1, 21, 30, flags)

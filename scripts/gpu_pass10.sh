@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q -k "iso or sort_last or smoke or post" > gpurun_out/pytest_gpu_iso.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu_iso.log
 tail -5 gpurun_out/pytest_gpu_iso.log
-EXP_ISO_VARIANTS=4:0,4:1,2:1,1:1 timeout 300 python scripts/exp_iso.py 2>&1 | tee gpurun_out/exp_iso_variants.txt
+EXP_ISO_VARIANTS=4:1 timeout 300 python scripts/exp_iso.py 2>&1 | tee gpurun_out/exp_iso_variants.txt
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"iso|conv|occ|shading" -s 18 -c 24 --csv --log-file gpurun_out/launches_iso.csv python scripts/exp_iso_e2e.py > /dev/null 2>&1
 python - <<'PY'
 import csv,collections

@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libspimcuda.so")
+# SPIMCUDA_LIB: another build of the same library (kernel-tuning experiments); never a different implementation
+LIB_PATH = os.environ.get("SPIMCUDA_LIB") or os.path.join(HERE, "libspimcuda.so")
 
 SPV_F32, SPV_U16, SPV_U8 = 0, 1, 2
 BUF_OUT, BUF_ALPHA, BUF_DEPTH, BUF_NORMALS, BUF_OCC, BUF_RAW, BUF_KPLANES = range(7)

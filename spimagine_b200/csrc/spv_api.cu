@@ -697,6 +697,7 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   else if (knob == 3) ctx->direct_host = value != 0;
   else if (knob == 4) ctx->iso_cta_warps = value;
   else if (knob == 5) ctx->iso_centre_out = value != 0;
+  else if (knob == 6) occ_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : value);  // process-wide
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
   return 0;
 }

@@ -253,6 +253,26 @@ __device__ __forceinline__ int iso_cell_class(const IsoArgs &a, const IsoRay &q,
   return cls;
 }
 constexpr int COARSE_SHIFT = BRICK_SHIFT + 2, TOP_SHIFT = BRICK_SHIFT + 4;
+// One traversal step over both levels: the two cells of sample k are looked up together (independent loads: a warp
+// deep in the traversal is bound by their latency).  Returns k if neither cell is of class `skip_cls`, else the first
+// sample outside the larger skippable cell.
+__device__ __forceinline__ int iso_skip_step(const IsoArgs &a, const IsoRay &q, const IsoDda &d, const IsoLevel &Lt,
+                                             const IsoLevel &Lc, int k, int kend, int skip_cls) {
+  const float t = (float)k;
+  const int ix = __float2int_rd(fmaf(t, q.du, d.cx0)), iy = __float2int_rd(fmaf(t, q.dv, d.cy0)),
+            iz = __float2int_rd(fmaf(t, q.dw, d.cz0));
+  const int tx = min(max(ix >> TOP_SHIFT, 0), Lt.gx - 1), ty = min(max(iy >> TOP_SHIFT, 0), Lt.gy - 1),
+            tz = min(max(iz >> TOP_SHIFT, 0), Lt.gz - 1);
+  const int cx = min(max(ix >> COARSE_SHIFT, 0), Lc.gx - 1), cy = min(max(iy >> COARSE_SHIFT, 0), Lc.gy - 1),
+            cz = min(max(iz >> COARSE_SHIFT, 0), Lc.gz - 1);
+  const float2 vt = __ldg(Lt.grid + ((size_t)tz * Lt.gy + ty) * Lt.gx + tx);
+  const float2 vc = __ldg(Lc.grid + ((size_t)cz * Lc.gy + cy) * Lc.gx + cx);
+  const int cls_t = !(vt.y > a.iso_val) ? 2 : ((vt.x > a.iso_val) ? 1 : 0);
+  const int cls_c = !(vc.y > a.iso_val) ? 2 : ((vc.x > a.iso_val) ? 1 : 0);
+  if (cls_t == skip_cls) return iso_cell_exit<TOP_SHIFT>(q, d, Lt, k, kend, tx, ty, tz);
+  if (cls_c == skip_cls) return iso_cell_exit<COARSE_SHIFT>(q, d, Lc, k, kend, cx, cy, cz);
+  return k;
+}
 
 // bracket refinement, 12-tap gradient and Phong shading at crossing sample i (iso_kernel.cl:140-215)
 template <int FMT, bool LINEAR>
@@ -370,10 +390,9 @@ __global__ void __launch_bounds__(128, SPV_ISO_MINB) iso_fast_kernel(const IsoAr
     while (k0 < maxSteps) {
       if (SKIP) {
         while (k0 < maxSteps) {
-          int kexit;
-          if (iso_cell_class<TOP_SHIFT>(a, q, d, Ltop, k0, maxSteps, kexit) == skip_cls) { k0 = kexit; continue; }
-          if (iso_cell_class<COARSE_SHIFT>(a, q, d, Lco, k0, maxSteps, kexit) == skip_cls) { k0 = kexit; continue; }
-          break;
+          const int kn = iso_skip_step(a, q, d, Ltop, Lco, k0, maxSteps, skip_cls);
+          if (kn == k0) break;
+          k0 = kn;
         }
         if (k0 >= maxSteps) break;
       }
@@ -914,6 +933,7 @@ size_t occ_queue_bytes(int width, int height) {
   return (4 + n_ob) * sizeof(unsigned);  // [2 parities][count, head] + the list
 }
 
+int occ_ctas_per_sm = 10;  // resident CTAs (4 warps each) per SM of the occlusion queue kernel (tuning knob 6)
 cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int n_points, const float *depth,
                              const unsigned char *tile_hit, const float4 *taps, unsigned *queue, unsigned frame, int sms,
                              cudaStream_t st) {
@@ -922,7 +942,7 @@ cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int 
     unsigned *cnt = queue + 2 * (frame & 1u), *cnt_next = queue + 2 * ((frame + 1u) & 1u), *list = queue + 4;
     occ_list_kernel<<<(n_ob + 7) / 8, 256, 0, st>>>(occ, width, height, radius, tile_hit, (width + 7) / 8, obx, n_ob, cnt,
                                                     cnt_next, list);
-    occ_queue_kernel<<<(sms > 0 ? sms : 148) * 5, 128, 0, st>>>(occ, width, height, radius, n_points, depth, taps, obx, cnt,
+    occ_queue_kernel<<<(sms > 0 ? sms : 148) * occ_ctas_per_sm, 128, 0, st>>>(occ, width, height, radius, n_points, depth, taps, obx, cnt,
                                                                  list);
     return cudaGetLastError();
   }

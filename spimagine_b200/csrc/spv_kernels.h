@@ -99,6 +99,7 @@ cudaError_t launch_occ_taps(float4 *taps, int n, cudaStream_t st);
 // queue (occ_queue_bytes, zero-initialised) + tile flags: only the pixel blocks in reach of a surface are computed, handed
 // out dynamically; `frame` must change parity from call to call on the same queue.  Without: every block, in place.
 size_t occ_queue_bytes(int width, int height);
+extern int occ_ctas_per_sm;
 cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int n_points, const float *depth,
                              const unsigned char *tile_hit, const float4 *taps, unsigned *queue, unsigned frame, int sms,
                              cudaStream_t st);
