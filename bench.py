@@ -899,9 +899,10 @@ def main():
             "issued_samples_per_frame": mean_issued,
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 2 * W * H * 4,
                     "note": "the drop-in call of the reference's frame loop, synchronous per frame: "
-                            "VolumeRenderer.set_modelView + render() = host 4x4 inversion, 4 band launches, output + "
-                            "alpha copied band by band into pinned host memory, wait; the volume stays resident as in "
-                            "the reference's frame loop",
+                            "VolumeRenderer.set_modelView + render() = host 4x4 inversion, one launch whose tile rows "
+                            "are dealt from the image edges inwards, output + alpha copied in 12 bands into pinned host "
+                            "memory by two copy streams that wait on per-band completion counters "
+                            "(cuStreamWaitValue32), wait; the volume stays resident as in the reference's frame loop",
                     "checksum": checksum},
             "e2e_pipelined": {"value": total_frames / t_seq, "unit": "frames/s", "h2d_bytes_per_step": 128,
                               "d2h_bytes_per_step": 2 * W * H * 4,

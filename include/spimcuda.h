@@ -134,9 +134,11 @@ enum {
 };
 SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p);
 /* Render + read-back in one call (replaces run_kernel followed by the blocking buf.get() / buf_alpha.get() of
- * _render_max_project, volumerender.py:366-390).  The frame is rendered as `bands` horizontal bands (<= 0: the
+ * _render_max_project, volumerender.py:366-390).  The frame is cut into `bands` horizontal bands (<= 0: the
  * context's default, tuning knob 2); the rows of a finished band are copied into the selected slot's pinned staging
- * ([out | alpha]) while the next band renders.  wait != 0: returns when the frame is in host memory; wait == 0:
+ * ([out | alpha]) while the rest renders.  Where the driver offers stream memory operations the whole frame is ONE
+ * launch: its CTAs are dealt from the top and bottom rows inwards and count themselves into per-band counters that the
+ * copy streams wait on (cuStreamWaitValue32); otherwise one launch per band.  wait != 0: returns when the frame is in host memory; wait == 0:
  * returns at once, collect with spv_wait_slot.  *host (may be NULL) = the slot's staging. */
 SPV_API int spv_render_mip_to_host(spv_ctx *ctx, const spv_mip_params *p, int bands, int wait, float **host);
 /* window + gamma of SPV_BUF_RAW into SPV_BUF_OUT after the cross-GPU max composite */
@@ -174,6 +176,12 @@ enum {
   SPV_ISO_RAW_ONLY = 1  /* the iso_surface kernel alone, no blur / occlusion / shading passes */
 };
 SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p);
+/* Render + read-back of [out | alpha] in one call (replaces the run_kernel chain followed by the blocking buf.get() /
+ * buf_alpha.get() of _render_isosurface, volumerender.py:499-506): the alpha plane is final once the march has run and
+ * travels to the selected slot's pinned staging while the blur / occlusion / shading passes run; the value plane
+ * follows.  depth / normals / occlusion stay on the device (spv_read_pinned fetches them).  wait / host as for
+ * spv_render_mip_to_host. */
+SPV_API int spv_render_iso_to_host(spv_ctx *ctx, const spv_iso_params *p, int wait, float **host);
 
 /* ---- sort-last iso surface (new): every context holds one z-slab (+ halo) and the same camera.
  *   1. spv_iso_slab_search   per pixel over the samples the slab owns: SPV_BUF_KPLANES = {first k with s_k > iso,
@@ -224,7 +232,8 @@ SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
  * knob 1 = persistent CTAs pulling tiles from a counter (1) or one CTA per tile (0), knob 2 = default band count of
  * spv_render_mip_to_host, knob 3 = spv_render_mip_to_host stores straight into pinned host memory, knob 4 = warps per
  * CTA of the iso-surface search (1, 2 or 4), knob 5 = its CTAs are dealt from the image centre outwards (1, default) or
- * row by row (0) */
+ * row by row (0), knob 6 = resident CTAs per SM of the occlusion queue kernel, knob 7 = copy streams the band copies of
+ * spv_render_mip_to_host alternate between (1 or 2) */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 SPV_API const char *spv_last_error(spv_ctx *ctx);                   /* ctx may be NULL: last create error */
 SPV_API int spv_version(void);

@@ -23,14 +23,26 @@ def run(label, n=360):
     for i in range(n):
         rend.set_modelView(cams[i][0]); rend.render()
     dt = time.perf_counter() - t0
+    dev = []
+    for i in range(0, 360, 30):
+        rend.set_modelView(cams[i][0]); rend.render(); dev.append(rend.last_render_ms() * 1e3)
+    t1 = time.perf_counter()
+    for i in range(n):
+        rend.set_modelView(cams[33][0]); rend.render()
+    dt33 = (time.perf_counter() - t1) / n * 1e6
     rend.set_modelView(cams[33][0]); rend.render()
+    k33 = rend.last_render_ms() * 1e3
+    label += " [kernel %.0f us avg; frame 33: kernel %.0f us, e2e %.0f us]" % (sum(dev) / len(dev), k33, dt33)
     img = rend.output.copy()
     if ref is None: ref = img
-    print("%-28s %.0f frames/s (%.1f us/frame) identical=%s" % (label, n / dt, 1e6 * dt / n, np.array_equal(img, ref)), flush=True)
-for b in (1, 2, 4, 8, 16):
-    lib.spv_set_tuning(ctx, 2, b); run("bands=%d" % b)
+    print("%-90s %.0f frames/s (%.1f us/frame) identical=%s" % (label, n / dt, 1e6 * dt / n, np.array_equal(img, ref)), flush=True)
+for cs in (2,):
+    lib.spv_set_tuning(ctx, 7, cs)
+    for b in (1, 12):
+        lib.spv_set_tuning(ctx, 2, b); run("copy streams=%d bands=%d" % (cs, b))
+lib.spv_set_tuning(ctx, 7, 1)
 lib.spv_set_tuning(ctx, 3, 1); run("direct host stores")
-lib.spv_set_tuning(ctx, 3, 0); lib.spv_set_tuning(ctx, 2, 4)
+lib.spv_set_tuning(ctx, 3, 0); lib.spv_set_tuning(ctx, 2, 12)
 # host-side cost alone
 t0 = time.perf_counter()
 for i in range(360): rend.set_modelView(cams[i][0])

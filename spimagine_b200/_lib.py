@@ -79,6 +79,7 @@ SIGNATURES = {
     "spv_comp_check": (C.c_int, [_CTX]),
     "spv_set_extra_slabs": (C.c_int, [_CTX, C.POINTER(_CTX), C.c_int]),
     "spv_render_iso": (C.c_int, [_CTX, C.POINTER(IsoParams)]),
+    "spv_render_iso_to_host": (C.c_int, [_CTX, C.POINTER(IsoParams), C.c_int, C.POINTER(_FP)]),
     "spv_iso_slab_search": (C.c_int, [_CTX, C.POINTER(IsoParams)]),
     "spv_iso_slab_resolve": (C.c_int, [_CTX, C.POINTER(IsoParams)]),
     "spv_iso_slab_post": (C.c_int, [_CTX, C.POINTER(IsoParams)]),

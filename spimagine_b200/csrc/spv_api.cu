@@ -8,6 +8,8 @@
 #include <string>
 #include <thread>
 
+#include <cuda.h>
+
 #include "spv_kernels.h"
 
 using namespace spv;
@@ -40,11 +42,14 @@ struct spv_ctx {
   bool bricks_valid = false;  // the min/max grids are built on first use after an upload (iso, skipping, min/max query)
   // settings
   int linear = 1, sampler = SPV_SAMPLER_TMU, int_filter = 1, skipping = -1, stats_on = 0, tile_variant = 0, persistent = 0;
-  int bands = 2;  // default band count of spv_render_mip_to_host (measured best of 1/2/4/8/16, profiles/r01_exp_e2e.txt)
+  int bands = 0;  // default band count of spv_render_mip_to_host (knob 2); 0 = 12 where the copy stream can wait on the
+                  // band counters (one launch per frame), else 2 (one launch per band) -- profiles/r01_exp_e2e.txt
   int iso_cta_warps = 4;  // tuning knob 4
   int iso_centre_out = 1; // tuning knob 5
   int direct_host = 0;  // spv_render_mip_to_host: the kernel stores straight into the pinned staging (tuning knob 3)
   unsigned *d_tile_counter = nullptr;
+  unsigned *d_band_done = nullptr;   // [MAX_BANDS] CTAs finished per band, counting up across frames (never reset)
+  unsigned band_expect[64] = {0};    // value band b's counter reaches when the current frame's band is complete
   unsigned char *d_tile_hit = nullptr;  // per 8x4 warp tile: holds an iso-surface pixel
   unsigned *d_occ_queue = nullptr;      // occlusion work queue (launch_occlusion), per image size
   unsigned occ_frame = 0;
@@ -60,7 +65,9 @@ struct spv_ctx {
   float *dbuf_s[2] = {nullptr, nullptr};
   float *hpin_s[2] = {nullptr, nullptr};
   int slot = 0;
-  cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream = nullptr, copy_stream2 = nullptr;  // band copies alternate between the two
+  cudaEvent_t ev_copy2 = nullptr;
+  int copy_streams = 2;  // tuning knob 7 (measured: 267 us per synchronous C2 frame with 2, 280 with 1)
   cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   bool copy_pending[2] = {false, false};
   // sort-last composite over peer memory (spv_comp_*): I own image band comp_rank
@@ -235,6 +242,8 @@ SPV_API int spv_create(int device, int width, int height, spv_ctx **out) {
   CC(cudaEventCreate(&ctx->ev0));
   CC(cudaEventCreate(&ctx->ev1));
   CC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CC(cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
+  CC(cudaEventCreateWithFlags(&ctx->ev_copy2, cudaEventDisableTiming));
   CC(cudaEventCreateWithFlags(&ctx->ev_up_begin, cudaEventDisableTiming));
   for (int s = 0; s < 2; ++s) {
     CC(cudaEventCreateWithFlags(&ctx->ev_rendered[s], cudaEventDisableTiming));
@@ -245,6 +254,8 @@ SPV_API int spv_create(int device, int width, int height, spv_ctx **out) {
   CC(cudaMalloc(&ctx->d_minmax, 2 * sizeof(float)));
   CC(cudaMalloc(&ctx->d_stats, 2 * sizeof(unsigned long long)));
   CC(cudaMalloc(&ctx->d_tile_counter, sizeof(unsigned)));
+  CC(cudaMalloc(&ctx->d_band_done, 64 * sizeof(unsigned)));
+  CC(cudaMemset(ctx->d_band_done, 0, 64 * sizeof(unsigned)));
   CC(cudaMalloc(&ctx->d_iso_err, sizeof(unsigned)));
   CC(cudaMemset(ctx->d_iso_err, 0, sizeof(unsigned)));
 #undef CC
@@ -267,6 +278,7 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
   if (ctx->d_minmax) cudaFree(ctx->d_minmax);
   if (ctx->d_stats) cudaFree(ctx->d_stats);
   if (ctx->d_tile_counter) cudaFree(ctx->d_tile_counter);
+  if (ctx->d_band_done) cudaFree(ctx->d_band_done);
   if (ctx->d_iso_err) cudaFree(ctx->d_iso_err);
   if (ctx->d_taps) cudaFree(ctx->d_taps);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -279,6 +291,8 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
     if (ctx->ev_consumed[s]) cudaEventDestroy(ctx->ev_consumed[s]);
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
+  if (ctx->ev_copy2) cudaEventDestroy(ctx->ev_copy2);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return 0;
@@ -697,6 +711,7 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   else if (knob == 3) ctx->direct_host = value != 0;
   else if (knob == 4) ctx->iso_cta_warps = value;
   else if (knob == 5) ctx->iso_centre_out = value != 0;
+  else if (knob == 7) ctx->copy_streams = value > 1 ? 2 : 1;
   else if (knob == 6) occ_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : value);  // process-wide
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
   return 0;
@@ -729,6 +744,25 @@ static int end_render(spv_ctx *ctx) {
 
 static bool bad_float(float f) { return !(f == f); }
 
+// cuStreamWaitValue32 through the runtime's driver entry point lookup (no link-time dependency on libcuda);
+// nullptr where the driver does not offer it
+typedef CUresult (*wait_value_t)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static wait_value_t wait_value_fn() {
+  static wait_value_t fn = nullptr;
+  static bool looked = false;
+  if (!looked) {
+    looked = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (wait_value_t)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
 // One max projection.  bands > 1 (fast kernel only): the frame is rendered as `bands` horizontal bands launched back to
 // back, and the rows of a finished band travel to the pinned staging on the copy stream while the next band renders.
 static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, bool to_host, const PushArgs *push = nullptr) {
@@ -756,6 +790,8 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
   a.out = ctx->out(); a.alpha = ctx->alpha(); a.raw = ctx->raw();
   a.stats = ctx->stats_on ? ctx->d_stats : nullptr;
   a.tile_counter = ctx->persistent ? ctx->d_tile_counter : nullptr;
+  a.band_done = nullptr;
+  a.band_rows = 0;
   a.n_extra = 0;
   if (ctx->slab && ctx->n_extra > 0) {
     if (ctx->skipping > 0) return fail(ctx, SPV_EINVAL, "spv_render_mip: extra slabs need empty-space skipping off");
@@ -789,8 +825,47 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     bands = 1;
   }
   if (!fast || bands < 1) bands = 1;
+  if (bands > 64) bands = 64;
   int rows = ((H + bands - 1) / bands + 15) / 16 * 16;  // band height: a multiple of every CTA tile height
   if (rows < 16) rows = 16;
+  // One launch for the whole frame where the driver offers stream memory operations: the CTAs count themselves into
+  // their band's counter and the copy stream waits for each counter to reach the band's CTA total (cuStreamWaitValue32)
+  // before it moves the band -- no per-band launch, no per-band tail, the bands can be small.
+  if (to_host && !direct && bands > 1 && ctx->tile_variant == 0 && !ctx->persistent && !ctx->slab && !raw_only &&
+      p->num_parts == 1 && !(ctx->skipping > 0) && wait_value_fn()) {
+    a.y_begin = 0;
+    a.y_end = H;
+    a.band_done = ctx->d_band_done;
+    a.band_rows = rows;
+    CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, false, false, ctx->stats_on != 0, ctx->stream));
+    ctx->launches += 1;
+    const unsigned ctas_x = (unsigned)(ctx->width + 15) / 16;
+    const int nb = (H + rows - 1) / rows;
+    for (int i = 0; i < nb; ++i) {
+      // the kernel deals tile rows from the top and bottom edges inwards: enqueue the copies in the order the bands
+      // complete (0, nb-1, 1, nb-2, ...), alternating between the copy streams
+      const int b = (i & 1) ? nb - 1 - (i >> 1) : (i >> 1);
+      const int y0 = b * rows, y1 = y0 + rows < H ? y0 + rows : H;
+      ctx->band_expect[b] += ctas_x * (unsigned)((y1 - y0 + 7) / 8);
+      const size_t off = (size_t)y0 * ctx->width, cnt = (size_t)(y1 - y0) * ctx->width, n = ctx->n();
+      cudaStream_t cs = (ctx->copy_streams > 1 && (i & 1)) ? ctx->copy_stream2 : ctx->copy_stream;
+      CUresult wr = wait_value_fn()(cs, (CUdeviceptr)(uintptr_t)(ctx->d_band_done + b), ctx->band_expect[b],
+                                    CU_STREAM_WAIT_VALUE_GEQ);
+      if (wr != CUDA_SUCCESS) return fail(ctx, (int)wr, "cuStreamWaitValue32 failed");
+      CU(cudaMemcpy2DAsync(ctx->hpin_s[s] + off, n * sizeof(float), ctx->dbuf_s[s] + off, n * sizeof(float),
+                           cnt * sizeof(float), 2, cudaMemcpyDeviceToHost, cs));
+    }
+    ctx->last_method = 0;
+    rc = end_render(ctx);
+    if (rc) return rc;
+    if (ctx->copy_streams > 1) {
+      CU(cudaEventRecord(ctx->ev_copy2, ctx->copy_stream2));
+      CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy2, 0));
+    }
+    CU(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));
+    ctx->copy_pending[s] = true;
+    return 0;
+  }
   for (int y0 = 0; y0 < H; y0 += rows) {
     const int y1 = y0 + rows < H ? y0 + rows : H;
     a.y_begin = y0;
@@ -801,10 +876,9 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
       const size_t off = (size_t)y0 * ctx->width, cnt = (size_t)(y1 - y0) * ctx->width, n = ctx->n();
       CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
       CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
-      CU(cudaMemcpyAsync(ctx->hpin_s[s] + off, ctx->dbuf_s[s] + off, cnt * sizeof(float), cudaMemcpyDeviceToHost,
-                         ctx->copy_stream));
-      CU(cudaMemcpyAsync(ctx->hpin_s[s] + n + off, ctx->dbuf_s[s] + n + off, cnt * sizeof(float), cudaMemcpyDeviceToHost,
-                         ctx->copy_stream));
+      // the band's rows of the value plane and of the alpha plane in ONE 2-D copy (2 "rows" one plane apart)
+      CU(cudaMemcpy2DAsync(ctx->hpin_s[s] + off, n * sizeof(float), ctx->dbuf_s[s] + off, n * sizeof(float),
+                           cnt * sizeof(float), 2, cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
   }
   ctx->last_method = 0;
@@ -825,7 +899,7 @@ SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p) {
 SPV_API int spv_render_mip_to_host(spv_ctx *ctx, const spv_mip_params *p, int bands, int wait, float **host) {
   BIND();
   if (p && (p->flags & SPV_MIP_RAW_ONLY)) return fail(ctx, SPV_EINVAL, "spv_render_mip_to_host: not for raw renders");
-  if (bands <= 0) bands = ctx->bands;
+  if (bands <= 0) bands = ctx->bands > 0 ? ctx->bands : (wait_value_fn() ? 12 : 2);
   int rc = render_mip_impl(ctx, p, bands, true);
   if (rc) return rc;
   if (wait) {
@@ -1003,8 +1077,9 @@ static ConvWeights conv_weights(int Nh, float coef) {
   return w;
 }
 
-SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p) {
-  BIND();
+// to_host: the alpha plane (final once the march has run) travels to the selected slot's pinned staging while the
+// blur / occlusion / shading passes run, the value plane follows after the shading pass
+static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) {
   if (!p) return fail(ctx, SPV_EINVAL, "spv_render_iso: null params");
   if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_render_iso: no volume set");
   if (ctx->slab) return fail(ctx, SPV_EINVAL, "spv_render_iso: not available on a slab context");
@@ -1038,8 +1113,16 @@ SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p) {
   if (rc) return rc;
   rc = begin_render(ctx);
   if (rc) return rc;
+  const int s = ctx->slot;
+  const size_t n = ctx->n();
+  if (to_host && ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // staging about to be rewritten
   CU(launch_iso(a, fmt_of(ctx), linear, ctx->sampler == SPV_SAMPLER_EXACT, ctx->stats_on != 0, ctx->stream));
   ctx->launches += 1;
+  if (to_host && post) {
+    CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
+    CU(cudaMemcpyAsync(ctx->hpin_s[s] + n, ctx->dbuf_s[s] + n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  }
   if (post) {
     // volumerender.py:470-497
     CU(launch_conv_xy(ctx->tmp_vec(), ctx->normals(), ctx->width, ctx->height, 3, conv_weights(7, -5.f), a.tile_hit, 0,
@@ -1053,7 +1136,34 @@ SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p) {
     ctx->launches += a.tile_hit ? 5 : 4;
   }
   ctx->last_method = 1;
-  return end_render(ctx);
+  rc = end_render(ctx);
+  if (rc) return rc;
+  if (to_host) {
+    CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
+    CU(cudaMemcpyAsync(ctx->hpin_s[s], ctx->dbuf_s[s], (post ? 1 : 2) * n * sizeof(float), cudaMemcpyDeviceToHost,
+                       ctx->copy_stream));
+    CU(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));
+    ctx->copy_pending[s] = true;
+  }
+  return 0;
+}
+
+SPV_API int spv_render_iso(spv_ctx *ctx, const spv_iso_params *p) {
+  BIND();
+  return render_iso_impl(ctx, p, false);
+}
+
+SPV_API int spv_render_iso_to_host(spv_ctx *ctx, const spv_iso_params *p, int wait, float **host) {
+  BIND();
+  int rc = render_iso_impl(ctx, p, true);
+  if (rc) return rc;
+  if (wait) {
+    CU(cudaEventSynchronize(ctx->ev_copied[ctx->slot]));
+    CU(cudaStreamSynchronize(ctx->stream));  // statistics / timing events of this frame
+  }
+  if (host) *host = ctx->hpin_s[ctx->slot];
+  return 0;
 }
 
 // ---- sort-last iso surface ----------------------------------------------------------------------------------------

@@ -29,6 +29,8 @@ struct MipArgs {
   float *out, *alpha, *raw;
   unsigned long long *stats;  // [hit rays, texture samples issued] or nullptr
   unsigned *tile_counter;     // non-null: persistent CTAs pull tiles from this counter
+  unsigned *band_done;        // non-null (static grid only): band_done[b] counts the CTAs of band b (band_rows image
+  int band_rows;              // rows each) whose results are in memory -- the copy stream waits on these counters
   Volume extra[MAX_EXTRA_SLABS];  // further slabs of the same global volume resident on this GPU (slab renders):
   int n_extra;                    // one ray setup, every slab's owned interval marched in turn
   PushArgs push;              // used when flags has SPV_MIP_PUSH

@@ -312,7 +312,19 @@ template <int FMT, bool LINEAR, bool SKIP, bool SLAB, int TX, int TY, int MINB>
 __global__ void __launch_bounds__(32 * TX * TY, MINB) mip_fast_kernel(const MipArgs a) {
   __shared__ __align__(16) float s_out[TX * TY][32];
   __shared__ __align__(16) float s_alpha[TX * TY][32];
-  mip_fast_tile<FMT, LINEAR, SKIP, SLAB, TX, TY>(a, blockIdx.x, blockIdx.y + a.y_begin / (4 * TY), s_out, s_alpha);
+  unsigned by = blockIdx.y + a.y_begin / (4 * TY);
+  // Read-back overlap (spv_render_mip_to_host): tile rows are dealt from the top and bottom edges inwards.  The rows whose
+  // rays miss the volume (typically the outer ones) are done at once and travel while the rest renders, and the band
+  // that completes last is a single one in the middle instead of the whole lower part of the image.
+  if (a.band_done) by = (blockIdx.y & 1u) ? gridDim.y - 1u - (blockIdx.y >> 1) : (blockIdx.y >> 1);
+  mip_fast_tile<FMT, LINEAR, SKIP, SLAB, TX, TY>(a, blockIdx.x, by, s_out, s_alpha);
+  if (a.band_done) {  // this CTA's rows are stored: tell the copy stream
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(a.band_done + (by * (4 * TY)) / (unsigned)a.band_rows, 1u);
+    }
+  }
 }
 
 // Persistent grid: (SMs x resident CTAs) CTAs pull tiles from a counter, so rays that miss the box or leave it

@@ -31,6 +31,7 @@ from time import time
 
 import numpy as np
 from scipy.linalg import inv
+from scipy.linalg.lapack import get_lapack_funcs
 
 from . import _lib
 from .utils.transform_matrices import *  # noqa: F401,F403  (the reference module re-exports these too)
@@ -39,6 +40,25 @@ from .utils.transform_matrices import mat4_identity, mat4_perspective, mat4_scal
 logger = logging.getLogger(__name__)
 
 DEFAULT_MAX_STEPS = 200  # spimagine/config/config.py:27 "max_steps"
+
+
+_getrf, _getri = get_lapack_funcs(("getrf", "getri"), (np.empty((4, 4), np.float64),))
+
+
+def _inv4(a):
+    """scipy.linalg.inv(a), which the reference calls per set_modelView (volumerender.py:312-313), without its
+    per-call validation overhead (15 -> 4 us per 4x4 matrix): the same LAPACK getrf + getri on the same values.
+    Inputs for which scipy takes another route (not float64, not finite, singular, lower triangular -> trtri) go
+    through scipy.linalg.inv itself, so the result is bit-identical in every case (tests/test_host.py)."""
+    a = np.asarray(a)
+    if (a.dtype == np.float64 and a.shape == (4, 4) and np.isfinite(a).all()
+            and (a[0, 1] != 0 or a[0, 2] != 0 or a[0, 3] != 0 or a[1, 2] != 0 or a[1, 3] != 0 or a[2, 3] != 0)):
+        lu, piv, info = _getrf(a)
+        if info == 0:
+            r, info = _getri(lu, piv, lwork=64, overwrite_lu=1)
+            if info == 0:
+                return r
+    return inv(a)
 
 
 class _DataImage(object):
@@ -77,6 +97,9 @@ class VolumeRenderer(object):
         self.set_sampler(sampler)
         self.set_int_filter(int_filter)
 
+        self._invM = np.zeros(16, np.float32)
+        self._invP = np.zeros(16, np.float32)
+        self._invM_ptr, self._invP_ptr = _lib.fp(self._invM), _lib.fp(self._invP)
         self.projection = np.zeros((4, 4))
         self.modelView = np.zeros((4, 4))
         self.width, self.height = int(w), int(h)
@@ -316,17 +339,23 @@ class VolumeRenderer(object):
 
     def update_matrices(self):
         if hasattr(self, "dataImg"):
-            mScale = self._stack_scale_mat()
-            invM = inv(np.dot(self.modelView, mScale))
+            # host cost matters here: this runs once per frame of a spin (set_modelView).  mScale only changes with
+            # the volume shape or the units, invP only with the projection; the float32 copies the kernels take
+            # live in two persistent buffers whose ctypes pointers are made once.
+            key = (self.dataImg.shape, tuple(np.asarray(self.stackUnits, dtype=float).ravel()))
+            cached = getattr(self, "_mscale_of", None)
+            if cached is None or cached[0] != key:
+                cached = self._mscale_of = (key, self._stack_scale_mat())
+            invM = _inv4(np.dot(self.modelView, cached[1]))
             cached = getattr(self, "_invP_of", None)
             if cached is not None and cached[0] is self.projection and np.array_equal(cached[1], self.projection):
                 invP = cached[2]
             else:  # same scipy.linalg.inv as the reference, evaluated once per distinct projection matrix
-                invP = inv(self.projection)
+                invP = _inv4(self.projection)
                 self._invP_of = (self.projection, np.array(self.projection, copy=True), invP)
-            self._invM = np.ascontiguousarray(invM.flatten().astype(np.float32))
-            self._invP = np.ascontiguousarray(invP.flatten().astype(np.float32))
-            self._check(self._lib.spv_set_matrices(self._ctx, _lib.fp(self._invP), _lib.fp(self._invM)))
+                self._invP[:] = invP.ravel()
+            self._invM[:] = invM.ravel()  # float64 -> float32 like .astype(np.float32)
+            self._check(self._lib.spv_set_matrices(self._ctx, self._invP_ptr, self._invM_ptr))
 
     def _stack_scale_mat(self):
         # scaling the data according to size and units
@@ -386,8 +415,13 @@ class VolumeRenderer(object):
         p = _lib.IsoParams(self._box(), float(self.maxVal / 2), float(self.gamma), int(self.max_steps),
                            float(self.occ_strength), int(self.occ_radius), int(self.occ_n_points),
                            _lib.ISO_RAW_ONLY if raw_only else 0)
-        self._check(self._lib.spv_render_iso(self._ctx, C.byref(p)))
-        flat, n = self._fetch(2)
+        # render + read-back in one call: the alpha plane travels while the screen-space passes run
+        host = _lib._FP()
+        self._check(self._lib.spv_render_iso_to_host(self._ctx, C.byref(p), 1, C.byref(host)))
+        n = self.width * self.height
+        flat = self._pinned_view(host, 2 * n)
+        if not self.pinned_outputs:
+            flat = flat.copy()
         shape = (self.height, self.width)
         self.output = flat[:n].reshape(shape)
         self.output_alpha = flat[n:2 * n].reshape(shape)

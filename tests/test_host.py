@@ -90,3 +90,26 @@ def test_vol_g_is_deterministic():
     assert a.dtype == np.uint16 and a.max() == 60000
     np.testing.assert_array_equal(a, b)
     assert scenes.vol_g(16, np.float32).max() == 1.0
+
+
+def test_fast_4x4_inverse_is_scipy_inv_bit_for_bit():
+    """update_matrices inverts with the LAPACK routines scipy.linalg.inv uses (the reference's call,
+    volumerender.py:312-313) minus scipy's per-call validation; every matrix family a camera produces, and the ones
+    scipy routes elsewhere (lower triangular, float32, singular, non-finite), must give the identical result."""
+    from scipy.linalg import inv
+    from spimagine_b200.volumerender import _inv4
+    rng = np.random.default_rng(1)
+    for i in range(200):
+        s = tm.mat4_scale(*(rng.random(3) + .2))
+        rot = tm.mat4_rotation(rng.uniform(0, 6), *rng.normal(size=3))
+        for c in (np.dot(tm.mat4_translate(*rng.normal(size=3)), s), np.dot(tm.mat4_identity(), s),
+                  tm.mat4_translate(0, 0, -4.), tm.mat4_perspective(rng.uniform(20, 90), rng.uniform(.5, 2), .1, 10),
+                  tm.mat4_ortho(-1, 1, -1, 1, -1, 1), np.dot(np.dot(tm.mat4_translate(0, 0, -4), rot), s),
+                  np.tril(rng.random((4, 4)) + np.eye(4)), np.triu(rng.random((4, 4)) + np.eye(4)),
+                  rng.random((4, 4)).astype(np.float32)):
+            want, got = inv(c), _inv4(c)
+            assert want.dtype == got.dtype and np.array_equal(want, got)
+    with pytest.raises(np.linalg.LinAlgError):
+        _inv4(np.zeros((4, 4)))
+    with pytest.raises(ValueError):
+        _inv4(np.full((4, 4), np.nan))
