@@ -210,6 +210,15 @@ SPV_API int spv_read_many(spv_ctx *ctx, float *out, float *alpha, float *depth, 
 SPV_API int spv_read_pinned(spv_ctx *ctx, int planes, float **host);
 SPV_API int spv_device_ptr(spv_ctx *ctx, int which, void **dev_ptr);
 
+/* ---- display hand-off (replaces buf.get() + the glTexImage2D re-upload + the LUT look-up of the fragment shader:
+ *      volumerender.py:388-390, gui/gui_utils.py:121-162, gui/glwidget.py:412-444, gui/shaders/texture.frag:8-38).
+ *      spv_set_lut: the colour map, n RGB triples in [0,1] (what GLWidget.set_colormap uploads as texture_LUT).
+ *      spv_read_rgba8: one device pass turns the current value plane into packed RGBA8 exactly as texture.frag would
+ *      shade it (rgb = LUT(v) in black mode / LUT(1-v) otherwise, linear LUT filtering, a = v, all-zero where the
+ *      alpha plane is negative) and copies the h*w*4 bytes to host_dst: a quarter of the bytes of the float planes. */
+SPV_API int spv_set_lut(spv_ctx *ctx, const float *rgb, int n);
+SPV_API int spv_read_rgba8(spv_ctx *ctx, int mode_black, unsigned char *host_dst, size_t nbytes);
+
 /* ---- pipelined sequences (new; replaces the blocking buf.get() per frame of the GUI spin / keyframe loops,
  *      gui/glwidget.py:636-692, volumerender.py:388-390): two output slots, each a full set of device result
  *      buffers plus pinned staging.  Frame i renders into slot i&1 while frame i-1 is still on its way to the host. ---- */

@@ -222,3 +222,27 @@ class OracleRenderer(object):
         invP, invM = self.matrices()
         box = np.ascontiguousarray(self.boxBounds, np.float32)
         return int(self.lib.so_count_hit_rays(self.width, self.height, _fp(invP), _fp(invM), _fp(box)))
+
+
+def display_rgba8(value, alpha, lut, mode_black=True):
+    """The reference's display path for one frame, restated in numpy fp32 (test infrastructure, like the rest of
+    oracle/): value plane uploaded as a GL_RED texture (spimagine/gui/gui_utils.py:146-149: col = (v, 0, 0), unorm
+    clamp), LUT look-up and alpha of spimagine/gui/shaders/texture.frag:8-38 with the LUT a 1 x N GL_LINEAR /
+    CLAMP_TO_EDGE texture (gui_utils.py:136-145), 8-bit frame buffer conversion rint(255 x)."""
+    f32 = np.float32
+    v = np.clip(np.nan_to_num(np.asarray(value, f32), nan=0.), f32(0), f32(1)).astype(f32)
+    lut = np.asarray(lut, f32)[:, :3]
+    N = lut.shape[0]
+    s = v if mode_black else (f32(1) - v)
+    u = s * f32(N) - f32(0.5)
+    fl = np.floor(u)
+    f = (u - fl).astype(f32)
+    i0 = np.clip(fl.astype(np.int64), 0, N - 1)
+    i1 = np.clip(fl.astype(np.int64) + 1, 0, N - 1)
+    w0 = (f32(1) - f).astype(f32)
+    rgb = (w0[..., None] * lut[i0]).astype(f32) + (f[..., None] * lut[i1]).astype(f32)
+    out = np.empty(v.shape + (4,), np.uint8)
+    out[..., :3] = np.rint(f32(255) * np.clip(rgb, f32(0), f32(1))).astype(np.uint8)
+    out[..., 3] = np.rint(f32(255) * v).astype(np.uint8)
+    out[np.asarray(alpha) < 0] = 0
+    return out

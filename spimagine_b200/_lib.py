@@ -88,6 +88,8 @@ SIGNATURES = {
     "spv_read_many": (C.c_int, [_CTX, _FP, _FP, _FP, _FP, _FP]),
     "spv_read_pinned": (C.c_int, [_CTX, C.c_int, C.POINTER(_FP)]),
     "spv_device_ptr": (C.c_int, [_CTX, C.c_int, C.POINTER(C.c_void_p)]),
+    "spv_set_lut": (C.c_int, [_CTX, _FP, C.c_int]),
+    "spv_read_rgba8": (C.c_int, [_CTX, C.c_int, C.c_void_p, C.c_size_t]),
     "spv_select_slot": (C.c_int, [_CTX, C.c_int]),
     "spv_read_pinned_async": (C.c_int, [_CTX, C.c_int]),
     "spv_wait_slot": (C.c_int, [_CTX, C.c_int, C.POINTER(_FP)]),

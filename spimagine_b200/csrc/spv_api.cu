@@ -54,6 +54,9 @@ struct spv_ctx {
   unsigned *d_occ_queue = nullptr;      // occlusion work queue (launch_occlusion), per image size
   unsigned occ_frame = 0;
   int sms = 0;
+  float *d_lut = nullptr;               // colour map of the display pass, n_lut RGB triples
+  int n_lut = 0;
+  unsigned char *d_rgba = nullptr, *h_rgba = nullptr;  // packed display image (device, pinned host), per image size
   float4 *d_taps = nullptr;             // occlusion tap table (launch_occ_taps), valid for taps_n taps
   int taps_n = 0;
   Camera cam;
@@ -160,6 +163,9 @@ static void free_buffers(spv_ctx *c) {
   c->d_tile_hit = nullptr;
   if (c->d_occ_queue) cudaFree(c->d_occ_queue);
   c->d_occ_queue = nullptr;
+  if (c->d_rgba) cudaFree(c->d_rgba);
+  if (c->h_rgba) cudaFreeHost(c->h_rgba);
+  c->d_rgba = c->h_rgba = nullptr;
   c->dbuf = nullptr;
   c->hpin = nullptr;
   c->slot = 0;
@@ -281,6 +287,7 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
   if (ctx->d_band_done) cudaFree(ctx->d_band_done);
   if (ctx->d_iso_err) cudaFree(ctx->d_iso_err);
   if (ctx->d_taps) cudaFree(ctx->d_taps);
+  if (ctx->d_lut) cudaFree(ctx->d_lut);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev_up_begin) cudaEventDestroy(ctx->ev_up_begin);
@@ -1345,6 +1352,39 @@ SPV_API int spv_wait_slot(spv_ctx *ctx, int slot, float **host) {
   if (!ctx->hpin_s[slot]) return fail(ctx, SPV_ENODATA, "spv_wait_slot: slot was never used");
   if (ctx->copy_pending[slot]) CU(cudaEventSynchronize(ctx->ev_copied[slot]));
   *host = ctx->hpin_s[slot];
+  return 0;
+}
+
+SPV_API int spv_set_lut(spv_ctx *ctx, const float *rgb, int n) {
+  BIND();
+  if (!rgb || n < 1 || n > 65536) return fail(ctx, SPV_EINVAL, "spv_set_lut: need 1..65536 RGB triples");
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (n != ctx->n_lut) {
+    if (ctx->d_lut) cudaFree(ctx->d_lut);
+    ctx->d_lut = nullptr;
+    ctx->n_lut = 0;
+    CU(cudaMalloc(&ctx->d_lut, (size_t)n * 3 * sizeof(float)));
+    ctx->n_lut = n;
+  }
+  CU(cudaMemcpyAsync(ctx->d_lut, rgb, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // the host pointer is only borrowed for this call
+  return 0;
+}
+
+SPV_API int spv_read_rgba8(spv_ctx *ctx, int mode_black, unsigned char *host_dst, size_t nbytes) {
+  BIND();
+  if (!ctx->d_lut) return fail(ctx, SPV_ENODATA, "spv_read_rgba8: no colour map (spv_set_lut)");
+  const size_t n = ctx->n();
+  if (!host_dst || nbytes != 4 * n) return fail(ctx, SPV_EINVAL, "spv_read_rgba8: need a destination of width*height*4 bytes");
+  if (!ctx->d_rgba) {
+    CU(cudaMalloc(&ctx->d_rgba, 4 * n));
+    CU(cudaMallocHost(&ctx->h_rgba, 4 * n));
+  }
+  CU(launch_display(ctx->out(), ctx->alpha(), ctx->d_lut, ctx->n_lut, mode_black != 0, ctx->d_rgba, n, ctx->stream));
+  ctx->launches += 1;
+  CU(cudaMemcpyAsync(ctx->h_rgba, ctx->d_rgba, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(host_dst, ctx->h_rgba, 4 * n);
   return 0;
 }
 

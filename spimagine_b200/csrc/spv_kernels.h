@@ -116,6 +116,10 @@ cudaError_t launch_build_bricks(const Volume &vol, int dtype, int local_nz, floa
 cudaError_t launch_pair(const void *src, void *dst, int dtype, size_t slice, int nz, int zbeg, int zend,
                         cudaStream_t st);
 
+// display hand-off (spv_display.cu): value plane + LUT -> packed RGBA8
+cudaError_t launch_display(const float *value, const float *alpha, const float *lut, int n_lut, int mode_black,
+                           void *rgba, size_t n, cudaStream_t st);
+
 // ingest of host arrays of another element type: dst[i] = (dst type) src[i], n elements (src_type: SPV_SRC_*)
 size_t src_elem_size(int src_type);
 cudaError_t launch_convert(const void *src, void *dst, int src_type, int dtype, size_t n, cudaStream_t st);

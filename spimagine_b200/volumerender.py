@@ -591,6 +591,22 @@ class VolumeRenderer(object):
     def sync(self):
         self._check(self._lib.spv_sync(self._ctx))
 
+    # ------------------------------------------------------------------ display hand-off (addition)
+    def set_lut(self, rgb):
+        """Colour map of output_rgba(): (N, 3) or (N, 4) floats in [0, 1] -- what GLWidget.set_colormap uploads as
+        texture_LUT (gui/glwidget.py, arrayFromImage of the colormap png)."""
+        rgb = np.ascontiguousarray(np.asarray(rgb, dtype=np.float32)[:, :3])
+        self._check(self._lib.spv_set_lut(self._ctx, _lib.fp(rgb.reshape(-1)), int(rgb.shape[0])))
+
+    def output_rgba(self, mode_black=True):
+        """(height, width, 4) uint8: the current result shaded the way the reference's fragment shader does
+        (gui/shaders/texture.frag:8-38: LUT colour, alpha = value, transparent where output_alpha < 0), computed on
+        the device and read back as 4 bytes per pixel instead of the two float planes.  Use after render() or
+        render_device_only()."""
+        img = np.empty((self.height, self.width, 4), np.uint8)
+        self._check(self._lib.spv_read_rgba8(self._ctx, int(bool(mode_black)), img.ctypes.data, img.nbytes))
+        return img
+
     def launch_count(self):
         n = C.c_ulonglong()
         self._check(self._lib.spv_launch_count(self._ctx, C.byref(n)))

@@ -320,3 +320,46 @@ def test_timelapse_player_resident_and_streamed():
         seen += mine
         pl.close()
     assert sorted(seen) == list(range(T))
+
+
+# ----------------------------------------------------------------------------- display hand-off
+@pytest.mark.parametrize("dtype,n_lut", [(np.float32, 256), (np.uint16, 37)])
+def test_display_pass_matches_the_shader_restatement(dtype, n_lut, oracle_mod):
+    """output_rgba(): LUT colour + alpha computed on the device (texture.frag:8-38) equals the numpy restatement
+    applied to the float planes byte for byte, in black and white mode, after max projection and iso surface; the
+    float32 kernel's misses (alpha = -1) come out transparent."""
+    rng = np.random.default_rng(3)
+    lut = rng.random((n_lut, 3)).astype(np.float32)
+    lut[0] = 0
+    data = scenes.vol_g(64, dtype, seed=2)
+    peak = float(data.max())
+    rend = _renderer((200, 144))
+    rend.set_data(data)
+    M, P = scenes.gui_camera(0.5, 3.4)
+    rend.set_projection(P)
+    rend.set_modelView(M)
+    rend.set_lut(lut)
+    for method, maxVal in (("max_project", .6 * peak), ("iso_surface", .5 * peak)):
+        rend.render(maxVal=maxVal, method=method)
+        for black in (True, False):
+            got = rend.output_rgba(mode_black=black)
+            want = oracle_mod.display_rgba8(rend.output, rend.output_alpha, lut, mode_black=black)
+            assert got.shape == (144, 200, 4) and got.dtype == np.uint8
+            assert np.array_equal(got, want)
+        if method == "max_project":
+            miss = rend.output_alpha < 0 if np.dtype(dtype) == np.float32 else rend.output_alpha == 0
+            assert 0 < miss.sum() < miss.size
+            if np.dtype(dtype) == np.float32:
+                assert not got[miss].any()
+            assert got[..., 3].max() == 255          # values above maxVal saturate
+    # the device-only path feeds the display pass without the float read-back
+    rend.render(maxVal=.6 * peak)
+    want = rend.output_rgba()
+    rend.resize((96, 80))
+    rend.resize((200, 144))
+    rend.set_modelView(M)
+    rend.render_device_only()
+    assert np.array_equal(rend.output_rgba(), want)
+    with pytest.raises(Exception):
+        _renderer((32, 32)).output_rgba()            # no colour map set
+    rend.close()

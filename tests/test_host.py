@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "spimcuda.h")).read()
-    return sorted(set(re.findall(r"SPV_API[^;(]*?\b(spv_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"SPV_API[^;(]*?\b(spv_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_are_exported_and_bound():

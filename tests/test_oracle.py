@@ -240,3 +240,24 @@ def test_sort_last_partition_is_bit_exact(oracle_mod, world):
     full = r.render_raw()
     parts = [r.render_raw(z0, z1) for z0, z1 in partition_slabs(40, world)]
     np.testing.assert_array_equal(np.maximum.reduce(parts), full)
+
+
+def test_display_restatement_known_answers():
+    """oracle.display_rgba8 (texture.frag:8-38): LUT end points, linear LUT filtering between texel centres, alpha
+    = value, transparent misses, inverted look-up in white mode."""
+    from oracle import oracle
+    lut = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [1, 1, 1]], np.float32)          # N = 4: texel centres at 1/8, 3/8, ...
+    v = np.array([[0., 1 / 8, 2 / 8, 3 / 8, 1., 2., -1., 0.5]], np.float32)
+    a = np.array([[1., 1., 1., 1., 1., 1., 1., -1.]], np.float32)
+    img = oracle.display_rgba8(v, a, lut)
+    assert img.shape == (1, 8, 4) and img.dtype == np.uint8
+    assert img[0, 0].tolist() == [0, 0, 0, 0]            # below the first texel centre: clamp to edge
+    assert img[0, 1].tolist() == [0, 0, 0, 32]           # exactly texel 0
+    assert img[0, 2].tolist() == [128, 0, 0, 64]         # half way between texels 0 and 1
+    assert img[0, 3].tolist() == [255, 0, 0, 96]         # texel 1
+    assert img[0, 4].tolist() == [255, 255, 255, 255]
+    assert img[0, 5].tolist() == [255, 255, 255, 255]    # values are clamped like a unorm texture
+    assert img[0, 6].tolist() == [0, 0, 0, 0]
+    assert img[0, 7].tolist() == [0, 0, 0, 0]            # tnear < 0: transparent
+    white = oracle.display_rgba8(v, a, lut, mode_black=False)
+    assert white[0, 0].tolist() == [255, 255, 255, 0] and white[0, 4].tolist() == [0, 0, 0, 255]
