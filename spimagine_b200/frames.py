@@ -1,0 +1,324 @@
+"""Frame sources for 3D+t playback: the data containers either side of VolumeRenderer.update_data.
+
+Mirrors the part of the reference's data model that feeds the renderer during timelapse playback
+(spimagine/models/data_model.py: GenericData :59-95, SpimData :97-148, RawData :221-261, NumpyData :408-432, the
+prefetching DataLoadThread / DataModel :600-757; spimagine/utils/imgutils.py: parseIndexFile :48-66, parseMetaFile
+:69-86, fromSpimFolder :129-146, createSpimFolder :162-191) -- same class names, same `sizeT() / size() /
+stackUnits / container[pos]` protocol -- with one change in where the bytes land: `FrameSource` reads time points
+AHEAD of the playback position straight from the file into PAGE-LOCKED buffers (file.readinto, no intermediate
+array), so that TimelapsePlayer.play(..., pinned=True) / VolumeRenderer.update_data(..., pinned=True) can move them
+at PCIe rate without staging.  The reference reads every time point into fresh pageable memory (np.fromfile) on the
+GUI thread or a Qt thread and re-uploads it synchronously (gui/glwidget.py:372-374).
+
+Only containers whose bytes are laid out as the renderer wants them (C-order stacks of one element type) are
+rebuilt here; the TIFF / CZI readers of the reference decode through third-party libraries (tifffile, czifile) and
+can be wrapped in NumpyData or any object with the same protocol.
+"""
+from __future__ import absolute_import, print_function
+
+import logging
+import os
+import re
+import threading
+
+import numpy as np
+
+from . import _lib
+
+logger = logging.getLogger(__name__)
+
+
+# ---------------------------------------------------------------------------------------------- containers
+class GenericData(object):
+    """abstract base class for 4d data: overwrite size() and __getitem__() (data_model.py:59-95)"""
+    dataFileError = Exception("not a valid file")
+
+    def __init__(self, name=""):
+        self.stackSize = None
+        self.stackUnits = None
+        self.name = name
+
+    def sizeT(self):
+        return self.size()[0]
+
+    def size(self):
+        return self.stackSize
+
+    def __len__(self):
+        return int(self.sizeT())
+
+    def __getitem__(self, pos):
+        return None
+
+    # additions used by FrameSource: element type of a time point and a way to read one into caller memory
+    @property
+    def dtype(self):
+        return np.dtype(np.uint16)
+
+    def read_into(self, pos, out):
+        """Fill `out` (C-contiguous, shape size()[1:], this container's dtype) with time point `pos`."""
+        np.copyto(out, self[pos], casting="no")
+
+
+def parseIndexFile(fname):
+    """returns (t,z,y,x) dimensions of a spim stack (imgutils.py:48-66)"""
+    try:
+        lines = open(fname).readlines()
+    except IOError:
+        print("could not open and read ", fname)
+        return None
+    items = lines[0].replace("\t", ",").split(",")
+    try:
+        stackSize = [int(i) for i in items[-4:-1]] + [len(lines)]
+    except Exception as e:
+        print(e)
+        print("couldnt parse ", fname)
+        return None
+    stackSize.reverse()
+    return stackSize
+
+
+def parseMetaFile(fName):
+    """returns pixelSizes (dx,dy,dz) (imgutils.py:69-86; np.float is gone from numpy: float())"""
+    with open(fName) as f:
+        s = f.read()
+        try:
+            z1 = float(re.findall("StartZ.*", s)[0].split("\t")[2])
+            z2 = float(re.findall("StopZ.*", s)[0].split("\t")[2])
+            zN = float(re.findall("NumberOfPlanes.*", s)[0].split("\t")[2])
+            return (.162, .162, (1. * z2 - z1) / (zN - 1.))
+        except Exception as e:
+            print(e)
+            print("coulndt parse ", fName)
+            return (1., 1., 1.)
+
+
+class SpimData(GenericData):
+    """data class for spim data saved in folder fName (data_model.py:97-148)
+    fname/
+    |-- metadata.txt
+    |-- data/
+       |--data.bin      little-endian uint16, (t, z, y, x)
+       |--index.txt
+    """
+
+    def __init__(self, fName=""):
+        super(SpimData, self).__init__(fName)
+        self.load(fName)
+
+    def load(self, fName):
+        if fName:
+            try:
+                self.stackSize = parseIndexFile(os.path.join(fName, "data/index.txt"))
+                self.stackUnits = parseMetaFile(os.path.join(fName, "metadata.txt"))
+                if self.stackSize is None:
+                    raise IOError("no index file")
+                self.fName = fName
+            except Exception as e:
+                print(e)
+                self.fName = ""
+                raise Exception("couldnt open %s as SpimData" % fName)
+
+    def _offset(self, pos):
+        if pos < 0 or pos >= self.stackSize[0]:
+            raise IndexError("0 <= pos <= %i, but pos = %i" % (self.stackSize[0] - 1, pos))
+        voxels = int(np.prod(self.stackSize[1:], dtype=np.int64))
+        return 2 * int(pos) * voxels, voxels  # python ints: no overflow for big files
+
+    def __getitem__(self, pos):
+        if self.stackSize and self.fName:
+            offset, voxels = self._offset(pos)
+            with open(os.path.join(self.fName, "data/data.bin"), "rb") as f:
+                f.seek(offset)
+                return np.fromfile(f, dtype="<u2", count=voxels).reshape(self.stackSize[1:])
+        return None
+
+    def read_into(self, pos, out):
+        offset, voxels = self._offset(pos)
+        buf = memoryview(out.reshape(-1)).cast("B")
+        assert out.dtype == np.dtype("<u2") and out.flags.c_contiguous and len(buf) == 2 * voxels
+        with open(os.path.join(self.fName, "data/data.bin"), "rb", buffering=0) as f:
+            f.seek(offset)
+            got = 0
+            while got < len(buf):
+                n = f.readinto(buf[got:])
+                if not n:
+                    raise IOError("%s: short read of time point %d" % (self.fName, pos))
+                got += n
+
+
+class RawData(GenericData):
+    """one raw file holding a (t,) z, y, x stack of `dtype` (data_model.py:221-261).  The reference loads the whole
+    file with np.fromfile; here it is memory-mapped, so that a timelapse larger than host memory plays too."""
+
+    def __init__(self, fName="", shape=None, dtype=np.uint16):
+        GenericData.__init__(self, fName)
+        self.load(fName, shape, dtype)
+
+    def load(self, fname, shape=None, dtype=np.uint16, stackUnits=[1., 1., 1.]):
+        if fname:
+            if shape is None or dtype is None:
+                raise ValueError("RawData needs shape and dtype (the reference asks for them in a dialog)")
+            shape = tuple(int(s) for s in shape)
+            if len(shape) < 4:
+                shape = (1,) * (4 - len(shape)) + shape
+            elif len(shape) > 4:
+                raise ValueError("shape should have length of 4!")
+            try:
+                self.data = np.memmap(fname, dtype=np.dtype(dtype), mode="r", shape=shape)
+            except Exception as e:
+                print(e)
+                self.fName = ""
+                raise Exception("couldnt open %s as RawData" % fname)
+            self.stackSize = shape
+            self.stackUnits = stackUnits
+            self.fName = fname
+            self._dtype = np.dtype(dtype)
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    def __getitem__(self, pos):
+        if self.stackSize and self.fName:
+            return self.data[pos]
+        return None
+
+
+class NumpyData(GenericData):
+    """a (t,) z, y, x array already in memory (data_model.py:408-432)"""
+
+    def __init__(self, data, stackUnits=[1., 1., 1.], copy=False):
+        GenericData.__init__(self, "NumpyData")
+        if data.ndim not in (3, 4):
+            raise TypeError("data should be 3 or 4 dimensional! shape = %s" % str(data.shape))
+        self.data = (data.copy() if copy else data).reshape((1,) * (4 - data.ndim) + data.shape)
+        self.stackSize = self.data.shape
+        self.stackUnits = stackUnits
+
+    @property
+    def dtype(self):
+        return self.data.dtype
+
+    def __getitem__(self, pos):
+        return self.data[pos]
+
+
+def createSpimFolder(fName, data=None, stackSize=[10, 10, 32, 32], stackUnits=(.162, .162, .162)):
+    """Write a SpimData folder (imgutils.py:162-191; the reference opens data.bin with the invalid mode "wa")."""
+    os.makedirs(os.path.join(fName, "data"), exist_ok=True)
+    if data is not None:
+        stackSize = data.shape
+        with open(os.path.join(fName, "data/data.bin"), "wb") as f:
+            np.ascontiguousarray(data).astype("<u2").tofile(f)
+    Nt, Nz, Ny, Nx = stackSize
+    with open(os.path.join(fName, "data/index.txt"), "w") as f:
+        for i in range(Nt):
+            f.write("%i\t0.0000\t1,%i,%i,%i\t0\n" % (i, Nx, Ny, Nz))
+    with open(os.path.join(fName, "metadata.txt"), "w") as f:
+        f.write("timelapse.NumberOfPlanes\t=\t%i\t0\n" % Nz)
+        f.write("timelapse.StartZ\t=\t0\t0\n")
+        f.write("timelapse.StopZ\t=\t%.2f\t0\n" % (stackUnits[2] * (Nz - 1.)))
+
+
+# ---------------------------------------------------------------------------------------------- prefetching source
+class FrameSource(object):
+    """Time points of a container, read ahead into a ring of page-locked buffers by a background thread.
+
+        src = FrameSource(SpimData(folder), frames=player.my_frames(n), depth=3)
+        for t, rend in player.play(src, frames=src.frames, pinned=True, max_val=...):
+            ...
+
+    source[t] blocks until time point t is in memory and returns a page-locked ndarray (shape size()[1:]) that stays
+    valid until the frame after the next one has been requested -- long enough for the asynchronous upload and the
+    render of frame t (TimelapsePlayer.play touches one frame at a time); the reader runs depth - 2 frames ahead
+    (depth = 2: no read-ahead, every request waits for the disk).  Frames must be requested in
+    the order given by `frames` (a playback order, possibly a rank's share t = rank, rank + world, ...; it wraps
+    around for looping playback).  Replaces DataLoadThread / DataModel.prefetch (data_model.py:600-757): same idea --
+    the neighbourhood ahead of the position is loaded in the background -- without the per-frame allocation and with
+    the bytes landing where the DMA engine can read them.
+    """
+
+    def __init__(self, container, frames=None, depth=3, pinned=True):
+        if depth < 2:
+            raise ValueError("depth must be at least 2")
+        self.container = container
+        self.frames = list(range(len(container))) if frames is None else list(frames)
+        self.depth = int(depth)
+        shape = tuple(int(s) for s in container.size()[1:])
+        alloc = _lib.pinned_empty if pinned else (lambda s, d: np.empty(s, d))
+        self._ring = [alloc(shape, container.dtype) for _ in range(self.depth)]
+        self._slot_frame = [None] * self.depth   # play-order index held by each slot
+        self._next_load = 0                      # play-order index the reader loads next
+        self._next_get = 0                       # play-order index the consumer asks for next
+        self._cv = threading.Condition()
+        self._stop = False
+        self._error = None
+        self.bytes_read = 0
+        self._thread = threading.Thread(target=self._run, name="spimagine-frame-reader", daemon=True)
+        self._thread.start()
+
+    # container protocol
+    def __len__(self):
+        return len(self.container)
+
+    def sizeT(self):
+        return self.container.sizeT()
+
+    def size(self):
+        return self.container.size()
+
+    @property
+    def stackUnits(self):
+        return self.container.stackUnits
+
+    def _run(self):
+        try:
+            while True:
+                with self._cv:
+                    # The consumer keeps the frame it asked for last and the one before (G = frames asked for so
+                    # far: G-1 and G-2 are in use), frame k lives in slot k % depth, so frame k may be loaded once
+                    # k - depth <= G - 3: the reader runs depth - 2 frames ahead of the one being shown.
+                    while not self._stop and (not self.frames or self._next_load > self._next_get + self.depth - 3):
+                        self._cv.wait()
+                    if self._stop:
+                        return
+                    k = self._next_load
+                    slot = k % self.depth
+                t = self.frames[k % len(self.frames)]
+                self.container.read_into(t, self._ring[slot])   # file.readinto releases the GIL
+                with self._cv:
+                    self._slot_frame[slot] = k
+                    self._next_load = k + 1
+                    self.bytes_read += self._ring[slot].nbytes
+                    self._cv.notify_all()
+        except Exception as e:  # surfaced by the next __getitem__
+            with self._cv:
+                self._error = e
+                self._cv.notify_all()
+
+    def __getitem__(self, t):
+        with self._cv:
+            k = self._next_get
+            if not self.frames or self.frames[k % len(self.frames)] != t:
+                raise IndexError("FrameSource: time point %r requested out of play order (next is %r)" % (
+                    t, self.frames[k % len(self.frames)] if self.frames else None))
+            self._next_get = k + 1
+            self._cv.notify_all()          # frame k - 2 is released: the reader may go one frame further
+            while self._slot_frame[k % self.depth] != k:
+                if self._error is not None:   # the reader died before it got to this frame
+                    raise self._error
+                self._cv.wait()
+            return self._ring[k % self.depth]
+
+    def close(self):
+        with self._cv:
+            self._stop = True
+            self._cv.notify_all()
+        self._thread.join()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,153 @@
+"""Frame sources (spimagine_b200/frames.py): the containers either side of update_data and the prefetching reader.
+CPU tests use pageable ring buffers; the page-locked path is exercised in the GPU test at the bottom."""
+import os
+import threading
+import time
+
+import numpy as np
+import pytest
+
+import scenes
+from spimagine_b200 import frames
+
+REF_FIXTURE = "/root/reference/tests/data/spimdata"
+
+
+def _timelapse(nt=7, shape=(12, 10, 14), seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 65536, size=(nt,) + shape).astype(np.uint16)
+
+
+def test_spim_folder_round_trip(tmp_path):
+    data = _timelapse()
+    folder = str(tmp_path / "spim")
+    frames.createSpimFolder(folder, data, stackUnits=(.162, .162, .5))
+    d = frames.SpimData(folder)
+    assert d.size() == list(data.shape) and d.sizeT() == 7 and len(d) == 7
+    assert d.stackUnits[:2] == (.162, .162) and abs(d.stackUnits[2] - .5) < 1e-2   # StopZ is written with 2 decimals
+    for t in (0, 3, 6):
+        assert np.array_equal(d[t], data[t]) and d[t].dtype == np.uint16
+    with pytest.raises(IndexError):
+        d[7]
+    with pytest.raises(IndexError):
+        d[-1]
+    out = np.empty(data.shape[1:], np.uint16)
+    d.read_into(5, out)
+    assert np.array_equal(out, data[5])
+    with pytest.raises(Exception):
+        frames.SpimData(str(tmp_path / "nothing_here"))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_FIXTURE), reason="the reference tree is only present in the build container")
+def test_reads_the_references_own_spim_fixture():
+    """tests/data/spimdata of the reference: 10 x 32^3 uint16, read by the rules of imgutils.fromSpimFolder."""
+    d = frames.SpimData(REF_FIXTURE)
+    assert d.size() == [10, 32, 32, 32]
+    raw = np.fromfile(os.path.join(REF_FIXTURE, "data/data.bin"), dtype="<u2").reshape(10, 32, 32, 32)
+    for t in range(10):
+        assert np.array_equal(d[t], raw[t])
+    assert d.stackUnits == (.162, .162, (5.02 - 0) / (32 - 1.))
+
+
+def test_raw_and_numpy_containers(tmp_path):
+    data = _timelapse(4, (6, 5, 8), seed=1).astype(np.float32)
+    fn = str(tmp_path / "stack.raw")
+    data.tofile(fn)
+    r = frames.RawData(fn, shape=data.shape, dtype=np.float32)
+    assert r.size() == data.shape and r.dtype == np.float32
+    assert np.array_equal(r[2], data[2])
+    r3 = frames.RawData(fn, shape=(24, 5, 8), dtype=np.float32)      # 3-D shape -> one time point
+    assert r3.size() == (1, 24, 5, 8) and np.array_equal(r3[0], data.reshape(24, 5, 8))
+    with pytest.raises(ValueError):
+        frames.RawData(fn, shape=(1, 1, 4, 6, 5, 8), dtype=np.float32)
+    n = frames.NumpyData(data[1])
+    assert n.size() == (1, 6, 5, 8) and np.array_equal(n[0], data[1])
+    with pytest.raises(TypeError):
+        frames.NumpyData(np.zeros((3, 3)))
+
+
+@pytest.mark.parametrize("depth", [2, 3, 5])
+def test_frame_source_plays_in_order_and_keeps_frames_valid(tmp_path, depth):
+    data = _timelapse(9, (8, 6, 10), seed=2)
+    folder = str(tmp_path / "spim")
+    frames.createSpimFolder(folder, data)
+    order = [1, 4, 7]                                   # rank 1 of 3
+    src = frames.FrameSource(frames.SpimData(folder), frames=order, depth=depth, pinned=False)
+    try:
+        assert len(src) == 9 and src.size() == list(data.shape)
+        prev = None
+        for lap in range(3):                            # looping playback wraps around
+            for t in order:
+                a = src[t]
+                assert np.array_equal(a, data[t])
+                if prev is not None:                    # the previous frame is still intact
+                    assert np.array_equal(prev[1], data[prev[0]])
+                prev = (t, a)
+        with pytest.raises(IndexError):
+            src[order[1]]                               # out of play order (next would be order[0])
+        assert src.bytes_read >= 9 * data[0].nbytes
+    finally:
+        src.close()
+
+
+def test_frame_source_reads_ahead_and_reports_errors(tmp_path):
+    data = _timelapse(6, (8, 6, 10), seed=3)
+
+    class Slow(frames.NumpyData):
+        def __init__(self, d):
+            frames.NumpyData.__init__(self, d)
+            self.reads = []
+
+        def read_into(self, pos, out):
+            if pos == 4:
+                raise IOError("disk on fire")
+            time.sleep(0.02)
+            self.reads.append(pos)
+            frames.NumpyData.read_into(self, pos, out)
+
+    c = Slow(data)
+    src = frames.FrameSource(c, depth=4, pinned=False)
+    try:
+        assert np.array_equal(src[0], data[0])
+        time.sleep(0.15)
+        assert c.reads == [0, 1, 2]                     # depth - 2 = 2 frames ahead of the one in use, not more
+        assert np.array_equal(src[1], data[1])
+        assert np.array_equal(src[2], data[2])
+        assert np.array_equal(src[3], data[3])
+        with pytest.raises(IOError):
+            src[4]
+    finally:
+        src.close()
+    assert not any(t.name == "spimagine-frame-reader" and t.is_alive() for t in threading.enumerate())
+
+
+@pytest.mark.gpu
+def test_timelapse_player_streams_from_a_spim_folder(tmp_path):
+    """disk -> page-locked ring -> asynchronous upload -> render: every owned time point of a SpimData folder shows
+    the image a plain set_data + render of that time point gives."""
+    from spimagine_b200 import VolumeRenderer
+    from spimagine_b200.multigpu import TimelapsePlayer
+    vols = np.stack([scenes.vol_g(40, np.uint16, seed=100 + t, t=t) for t in range(6)])
+    folder = str(tmp_path / "spim")
+    frames.createSpimFolder(folder, vols)
+    M, P = scenes.gui_camera(0.4, 3.3)
+    ref = VolumeRenderer((96, 80))
+    ref.set_projection(P)
+    ref.set_modelView(M)
+    want = {}
+    for t in range(6):
+        ref.set_data(vols[t])
+        ref.render(maxVal=60000.)
+        want[t] = ref.output.copy()
+    ref.close()
+    for rank in range(2):
+        player = TimelapsePlayer((96, 80), rank=rank, world=2)
+        src = frames.FrameSource(frames.SpimData(folder), frames=player.my_frames(6), depth=3)
+        seen = []
+        for t, r in player.play(src, frames=src.frames, pinned=True, projection=P, max_val=60000.,
+                                modelViews={t: M for t in range(6)}):
+            assert np.array_equal(r.output, want[t])
+            seen.append(t)
+        assert seen == list(range(rank, 6, 2))
+        src.close()
+        player.close()
