@@ -402,10 +402,12 @@ def run_iso(args, rank, local_rank, world):
         z0, z1 = partition_slabs(N, world)[rank]
         lo, hi = slab_with_halo(z0, z1, N, halo)
         rend = SlabMaxProjector((W, W), rank=rank, world=world, device=local_rank, max_steps=MAX_STEPS,
-                                pinned_outputs=True, halo=halo)
+                                pinned_outputs=True, halo=halo, composite=args.composite)
         torch.cuda.set_stream(rend._stream)
         vol = vol_g_slab_device(N, lo, hi, 1, dev)
         rend.set_slab((np.uint16, N, N), N, z0, z1, device_ptr=vol.data_ptr())
+        if args.composite == "peer":
+            rend.connect()
     rend.sync()
     del vol
     torch.cuda.empty_cache()
@@ -424,6 +426,8 @@ def run_iso(args, rank, local_rank, world):
         if world == 1:
             p = _lib.IsoParams(rend._box(), iso_max / 2, 1., MAX_STEPS, .1, 21, 30, 0)
             _lib.check(rend._lib.spv_render_iso(rend._ctx, C.byref(p)), rend._ctx)
+        elif args.composite == "peer":
+            rend.enqueue_iso_composite()
         else:
             rend.iso_search()
             dist.all_reduce(rend.iso_k_tensor(), op=dist.ReduceOp.MIN)
@@ -468,14 +472,16 @@ def run_iso(args, rank, local_rank, world):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u16->f32", "data": "synthetic",
             "config": {"workload": "Vol-G(%d, uint16, seed 1) generated on device, iso at %g, AO (.1, 21, 30), max_steps=200%s" % (
-                N, iso_max / 2, "" if world == 1 else ", %d z-slabs with %d halo slices, sort-last over NCCL (MIN int32 "
-                "2 planes, SUM float32 7 planes)" % (world, halo))},
+                N, iso_max / 2, "" if world == 1 else (", %d z-slabs with %d halo slices, sort-last over " % (world, halo) + (
+                    "peer memory (candidates pushed to the band owners, MIN + redistribution by the owners, finished "
+                    "pixels stored into every rank by the crossing's owner; arrival counters, no NCCL on the data path)"
+                    if args.composite == "peer" else "NCCL (MIN int32 2 planes, SUM float32 7 planes)")))},
             "e2e": {"value": args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 2 * W * W * 4,
                     "note": "set_modelView + render(method='iso_surface'): output + alpha read back per frame (8 MiB); depth, normals and occlusion stay on the device until they are looked at (lazy attributes)"},
             "surface_pixels_last": hit_px, "image_sha1_first8": digest.hexdigest(),
             # iso_fast, blur, occlusion list + queue, blur, shading; sort-last: search, resolve, fix-up, 2+2 blur
             # launches, occlusion list + queue, shading (the two NCCL reductions are not counted)
-            "gpu_launches": args.steps * (6 if world == 1 else 10)}))
+            "gpu_launches": args.steps * (6 if world == 1 else (11 if args.composite == "peer" else 10))}))
     rend.close()
     if world > 1:
         dist.destroy_process_group()

@@ -198,6 +198,12 @@ SPV_API int spv_iso_slab_search(spv_ctx *ctx, const spv_iso_params *p);
 SPV_API int spv_iso_slab_resolve(spv_ctx *ctx, const spv_iso_params *p);
 SPV_API int spv_iso_slab_post(spv_ctx *ctx, const spv_iso_params *p);
 SPV_API int spv_iso_slab_check(spv_ctx *ctx);
+/* The same result with every exchange over peer memory instead of the two caller-side reductions (needs spv_comp_init +
+ * the handle exchange, slot 0, one slab per context): the search stores the candidates of image band o into owner o's
+ * staging, the owner takes the MIN and stores the band's final candidates into every rank, the rank owning a pixel's
+ * crossing stores the finished pixel into every rank's planes; arrival counters in between; then the post passes.
+ * Enqueue-only: follow with spv_comp_check + spv_iso_slab_check, then read. */
+SPV_API int spv_render_iso_composite(spv_ctx *ctx, const spv_iso_params *p);
 
 /* ---- results: buf.get(), volumerender.py:388-390, 499-506 ---- */
 /* copies n floats (n = w*h, or 3*w*h for normals) to host memory; synchronises */

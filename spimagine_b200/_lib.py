@@ -84,6 +84,7 @@ SIGNATURES = {
     "spv_iso_slab_resolve": (C.c_int, [_CTX, C.POINTER(IsoParams)]),
     "spv_iso_slab_post": (C.c_int, [_CTX, C.POINTER(IsoParams)]),
     "spv_iso_slab_check": (C.c_int, [_CTX]),
+    "spv_render_iso_composite": (C.c_int, [_CTX, C.POINTER(IsoParams)]),
     "spv_read": (C.c_int, [_CTX, C.c_int, _FP, C.c_size_t]),
     "spv_read_many": (C.c_int, [_CTX, _FP, _FP, _FP, _FP, _FP]),
     "spv_read_pinned": (C.c_int, [_CTX, C.c_int, C.POINTER(_FP)]),

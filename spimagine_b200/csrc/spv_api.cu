@@ -75,8 +75,9 @@ struct spv_ctx {
   bool copy_pending[2] = {false, false};
   // sort-last composite over peer memory (spv_comp_*): I own image band comp_rank
   int comp_rank = -1, comp_world = 0, comp_band_rows = 0;
-  float *comp_part = nullptr;      // [2 parities][world][band_rows * width]
-  unsigned *comp_flags = nullptr;  // [2 phases][MAX_WORLD] arrival counters, written by the peers
+  float *comp_part = nullptr;      // [2 parities][world][band_rows * width] floats (max-projection partials), then
+                                   // [2 parities][world][2][band_rows * width] ints (iso-surface k1 / k0 candidates)
+  unsigned *comp_flags = nullptr;  // [COMP_PHASES][MAX_WORLD] arrival counters, written by the peers
   unsigned *comp_err = nullptr;
   float *peer_part[MAX_WORLD] = {nullptr};
   unsigned *peer_flags[MAX_WORLD] = {nullptr};
@@ -102,6 +103,9 @@ struct spv_ctx {
   float *tmp() const { return dbuf + 8 * n(); }
   float *tmp_vec() const { return dbuf + 9 * n(); }
 };
+
+// arrival-counter phases of the peer composites: 0, 1 max projection; 2, 3, 4 iso surface
+constexpr int COMP_PHASES = 5;
 
 static thread_local std::string g_create_err;
 
@@ -928,11 +932,11 @@ SPV_API int spv_comp_init(spv_ctx *ctx, int rank, int world) {
   if (ctx->slot != 0) return fail(ctx, SPV_EINVAL, "spv_comp_init: select output slot 0 first");
   const int rows = ((ctx->height + world - 1) / world + 3) / 4 * 4;
   const size_t band = (size_t)rows * ctx->width;
-  CU(cudaMalloc(&ctx->comp_part, 2 * (size_t)world * band * sizeof(float)));
-  CU(cudaMalloc(&ctx->comp_flags, 2 * MAX_WORLD * sizeof(unsigned)));
+  CU(cudaMalloc(&ctx->comp_part, 6 * (size_t)world * band * sizeof(float)));
+  CU(cudaMalloc(&ctx->comp_flags, COMP_PHASES * MAX_WORLD * sizeof(unsigned)));
   CU(cudaMalloc(&ctx->comp_err, sizeof(unsigned)));
-  CU(cudaMemsetAsync(ctx->comp_part, 0, 2 * (size_t)world * band * sizeof(float), ctx->stream));
-  CU(cudaMemsetAsync(ctx->comp_flags, 0, 2 * MAX_WORLD * sizeof(unsigned), ctx->stream));
+  CU(cudaMemsetAsync(ctx->comp_part, 0, 6 * (size_t)world * band * sizeof(float), ctx->stream));
+  CU(cudaMemsetAsync(ctx->comp_flags, 0, COMP_PHASES * MAX_WORLD * sizeof(unsigned), ctx->stream));
   CU(cudaMemsetAsync(ctx->comp_err, 0, sizeof(unsigned), ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->comp_rank = rank;
@@ -1209,7 +1213,7 @@ SPV_API int spv_iso_slab_search(spv_ctx *ctx, const spv_iso_params *p) {
   }
   rc = begin_render(ctx);
   if (rc) return rc;
-  int *k = (int *)ctx->tmp_vec();
+  int *k = (int *)ctx->raw();  // the two candidate planes live in [raw | tmp]
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
   CU(launch_iso_slab(a, fmt_of(ctx), linear, 0, k, k + ctx->n(), ctx->occ(), ctx->d_iso_err, ctx->stream));
   ctx->launches += 1;
@@ -1223,7 +1227,7 @@ SPV_API int spv_iso_slab_resolve(spv_ctx *ctx, const spv_iso_params *p) {
   int rc = iso_args(ctx, p, a, "resolve");
   if (rc) return rc;
   a.stats = nullptr;
-  int *k = (int *)ctx->tmp_vec();
+  int *k = (int *)ctx->raw();  // the two candidate planes live in [raw | tmp]
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
   CU(launch_iso_slab(a, fmt_of(ctx), linear, 1, k, k + ctx->n(), ctx->occ(), ctx->d_iso_err, ctx->stream));
   ctx->launches += 1;
@@ -1236,7 +1240,7 @@ SPV_API int spv_iso_slab_post(spv_ctx *ctx, const spv_iso_params *p) {
   int rc = iso_args(ctx, p, a, "post");
   if (rc) return rc;
   if (p->occ_n_points < 0 || p->occ_radius < 0) return fail(ctx, SPV_EINVAL, "sort-last iso surface: negative occlusion parameter");
-  int *k = (int *)ctx->tmp_vec();
+  int *k = (int *)ctx->raw();  // the two candidate planes live in [raw | tmp]
   CU(launch_iso_slab(a, fmt_of(ctx), true, 2, k, k + ctx->n(), ctx->occ(), ctx->d_iso_err, ctx->stream));
   ctx->launches += 1;
   if (!(p->flags & SPV_ISO_RAW_ONLY)) {
@@ -1267,6 +1271,84 @@ SPV_API int spv_iso_slab_check(spv_ctx *ctx) {
   return 0;
 }
 
+// Sort-last iso surface with every exchange over peer memory (no NCCL on the data path), enqueue-only:
+//   search: k1 / k0 candidates of band o's pixels are stored into owner o's staging   | barrier (arrival counters)
+//   owner : MIN over the ranks, the band's final k planes stored into EVERY rank      | barrier
+//   resolve: the rank owning a pixel's crossing stores the finished pixel into EVERY rank's planes | barrier
+//   post passes on every rank
+SPV_API int spv_render_iso_composite(spv_ctx *ctx, const spv_iso_params *p) {
+  BIND();
+  const int W = ctx->comp_world, R = ctx->comp_rank;
+  if (W < 1) return fail(ctx, SPV_ENODATA, "spv_render_iso_composite: spv_comp_init first");
+  for (int r = 0; r < W; ++r)
+    if (!ctx->peer_part[r]) return fail(ctx, SPV_ENODATA, "spv_render_iso_composite: a peer has not been imported");
+  if (ctx->slot != 0) return fail(ctx, SPV_EINVAL, "spv_render_iso_composite: select output slot 0 first");
+  IsoArgs a;
+  int rc = iso_args(ctx, p, a, "composite");
+  if (rc) return rc;
+  if (p->occ_n_points < 0 || p->occ_radius < 0) return fail(ctx, SPV_EINVAL, "sort-last iso surface: negative occlusion parameter");
+  if (a.skip) {
+    rc = ensure_bricks(ctx);
+    if (rc) return rc;
+  }
+  const bool post = !(p->flags & SPV_ISO_RAW_ONLY);
+  if (post) {
+    rc = ensure_taps(ctx, p->occ_n_points);
+    if (rc) return rc;
+  }
+  const unsigned f = ++ctx->comp_frame;
+  const unsigned parity = f & 1u;
+  const size_t band = (size_t)ctx->comp_band_rows * ctx->width, n = ctx->n();
+  IsoPeer peer;
+  memset(&peer, 0, sizeof peer);
+  peer.world = W;
+  peer.band_rows = ctx->comp_band_rows;
+  peer.src = (unsigned)R;
+  peer.band = (unsigned)band;
+  for (int r = 0; r < W; ++r) {
+    peer.kpart[r] = (int *)(ctx->peer_part[r] + 2 * (size_t)W * band) + (size_t)parity * W * 2 * band;
+    peer.planes[r] = ctx->peer_out[r];
+  }
+  // with post passes the resolved normals go to tmp_vec and the fused blur moves them to their plane
+  peer.normals_plane = post ? 9 : 4;
+  rc = begin_render(ctx);
+  if (rc) return rc;
+  int *k = (int *)ctx->raw();  // the two candidate planes live in [raw | tmp]
+  const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
+  CU(launch_iso_slab(a, fmt_of(ctx), linear, 0, k, k + n, ctx->occ(), ctx->d_iso_err, ctx->stream, &peer));
+  CU(launch_comp_sync(ctx->peer_flags, ctx->comp_flags, W, R, 2, f, ctx->comp_err, ctx->stream));
+  KReduceArgs ka;
+  memset(&ka, 0, sizeof ka);
+  ka.part = peer.kpart[R];
+  for (int r = 0; r < W; ++r) ka.kplanes[r] = (int *)(ctx->peer_out[r] + 7 * n);  // [raw | tmp]: the k planes
+  ka.world = W;
+  ka.band = (unsigned)band;
+  ka.first_pixel = (unsigned)((size_t)R * band);
+  ka.n_pixels = ka.first_pixel >= n ? 0u : (unsigned)((n - ka.first_pixel) < band ? (n - ka.first_pixel) : band);
+  ka.n_image = n;
+  CU(launch_k_reduce(ka, ctx->stream));
+  CU(launch_comp_sync(ctx->peer_flags, ctx->comp_flags, W, R, 3, f, ctx->comp_err, ctx->stream));
+  a.stats = nullptr;
+  CU(launch_iso_slab(a, fmt_of(ctx), linear, 1, k, k + n, ctx->occ(), ctx->d_iso_err, ctx->stream, &peer));
+  CU(launch_comp_sync(ctx->peer_flags, ctx->comp_flags, W, R, 4, f, ctx->comp_err, ctx->stream));
+  ctx->launches += 6;
+  if (post) {
+    CU(launch_conv_xy(ctx->tmp_vec(), ctx->normals(), ctx->width, ctx->height, 3, conv_weights(7, -5.f), a.tile_hit, 0,
+                      ctx->stream));
+    CU(launch_occlusion(ctx->tmp(), ctx->width, ctx->height, p->occ_radius, p->occ_n_points, ctx->depth(), a.tile_hit,
+                        ctx->d_taps, ctx->d_occ_queue, ctx->occ_frame++, ctx->sms, ctx->stream));
+    CU(launch_conv_xy(ctx->tmp(), ctx->occ(), ctx->width, ctx->height, 1, conv_weights(5, -10.f), a.tile_hit,
+                      p->occ_radius, ctx->stream));
+    CU(launch_shading(ctx->out(), ctx->width, ctx->height, ctx->cam, p->occ_strength, ctx->normals(), ctx->depth(),
+                      ctx->occ(), ctx->stream));
+    ctx->launches += 5;
+  } else {
+    CU(cudaMemsetAsync(ctx->occ(), 0, n * sizeof(float), ctx->stream));  // what the NCCL path's resolve leaves there
+  }
+  ctx->last_method = 1;
+  return end_render(ctx);
+}
+
 static float *buf_of(spv_ctx *c, int which, size_t *count) {
   const size_t n = c->n();
   *count = n;
@@ -1276,7 +1358,7 @@ static float *buf_of(spv_ctx *c, int which, size_t *count) {
     case SPV_BUF_DEPTH: return c->depth();
     case SPV_BUF_OCC: return c->occ();
     case SPV_BUF_RAW: return c->raw();
-    case SPV_BUF_KPLANES: *count = 2 * n; return c->tmp_vec();  // int32 [2][h][w], sort-last iso surface
+    case SPV_BUF_KPLANES: *count = 2 * n; return c->raw();  // int32 [2][h][w] in [raw | tmp], sort-last iso surface
     case SPV_BUF_NORMALS: *count = 3 * n; return c->normals();
     default: return nullptr;
   }

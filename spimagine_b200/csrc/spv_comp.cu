@@ -74,6 +74,29 @@ __global__ void __launch_bounds__(256) comp_finish_kernel(const CompFinishArgs a
   for (int r = 0; r < a.world; ++r) *reinterpret_cast<float4 *>(a.out[r] + a.first_pixel + i) = m;
 }
 
+// Sort-last iso surface: one thread = 4 consecutive pixels of my band; MIN over the ranks' candidates (INT_MAX = none)
+__global__ void __launch_bounds__(256) k_reduce_kernel(const KReduceArgs a) {
+  const unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+  if (i >= a.n_pixels) return;
+#pragma unroll
+  for (int plane = 0; plane < 2; ++plane) {
+    int4 m = *reinterpret_cast<const int4 *>(a.part + (size_t)plane * a.band + i);
+    for (int s = 1; s < a.world; ++s) {
+      const int4 v = *reinterpret_cast<const int4 *>(a.part + ((size_t)s * 2 + plane) * a.band + i);
+      m.x = min(m.x, v.x); m.y = min(m.y, v.y); m.z = min(m.z, v.z); m.w = min(m.w, v.w);
+    }
+    for (int r = 0; r < a.world; ++r)
+      *reinterpret_cast<int4 *>(a.kplanes[r] + (size_t)plane * a.n_image + a.first_pixel + i) = m;
+  }
+}
+
+cudaError_t launch_k_reduce(const KReduceArgs &a, cudaStream_t st) {
+  if (a.n_pixels == 0) return cudaSuccess;
+  const unsigned threads = (a.n_pixels + 3) / 4;
+  k_reduce_kernel<<<(threads + 255) / 256, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_comp_sync(unsigned *const *peer_flags, const unsigned *flags, int world, int rank, int phase,
                              unsigned value, unsigned *err, cudaStream_t st) {
   PeerFlagPtrs p;

@@ -4,6 +4,8 @@
 //   occlusion              spimagine/volumerender/kernels/occlusion.cl:41-82  (+ utils.cl:10-38)
 //   shading                spimagine/volumerender/kernels/iso_kernel.cl:505-588
 // in the launch order of VolumeRenderer._render_isosurface (volumerender.py:446-506).
+#include <string.h>
+
 #include "spv_kernels.h"
 
 namespace spv {
@@ -452,7 +454,7 @@ constexpr int K_NONE = 0x7fffffff;
 
 template <int FMT, bool LINEAR, bool SKIP>
 __global__ void __launch_bounds__(128) iso_slab_search_kernel(const IsoArgs a, int *__restrict__ k1_plane,
-                                                              int *__restrict__ k0_plane) {
+                                                              int *__restrict__ k0_plane, const IsoPeer peer) {
   constexpr int BATCH = 8;
   unsigned x, y;
   tile_pixel(x, y);
@@ -502,9 +504,17 @@ __global__ void __launch_bounds__(128) iso_slab_search_kernel(const IsoArgs a, i
     }
   }
   if (inb) {
-    const size_t p = x + (size_t)a.width * y;
-    k1_plane[p] = k1;
-    k0_plane[p] = k0;
+    if (peer.world > 0) {  // straight into the staging of the band's owner (peer memory over NVLink)
+      const unsigned o = y / (unsigned)peer.band_rows;
+      const size_t idx = (size_t)(y - o * (unsigned)peer.band_rows) * a.width + x;
+      int *dst = peer.kpart[o] + (size_t)peer.src * 2 * peer.band;
+      dst[idx] = k1;
+      dst[peer.band + idx] = k0;
+    } else {
+      const size_t p = x + (size_t)a.width * y;
+      k1_plane[p] = k1;
+      k0_plane[p] = k0;
+    }
   }
   if (a.stats) {
     atomicAdd(a.stats + 0, q.hit ? 1ull : 0ull);
@@ -515,18 +525,18 @@ __global__ void __launch_bounds__(128) iso_slab_search_kernel(const IsoArgs a, i
 template <int FMT, bool LINEAR>
 __global__ void __launch_bounds__(128) iso_slab_resolve_kernel(const IsoArgs a, const int *__restrict__ k1_plane,
                                                                const int *__restrict__ k0_plane, float *__restrict__ occ,
-                                                               unsigned *err) {
+                                                               unsigned *err, const IsoPeer peer) {
   unsigned x, y;
   tile_pixel(x, y);
   const bool inb = x < (unsigned)a.width && y < (unsigned)a.height;
-  if (!inb) return;
-  const size_t p = x + (size_t)a.width * y;
+  const size_t p = inb ? x + (size_t)a.width * y : 0;
   const Volume &V = a.vol;
-  const int k1 = k1_plane[p], k0 = k0_plane[p];
+  const int k1 = inb ? k1_plane[p] : K_NONE, k0 = inb ? k0_plane[p] : K_NONE;
   const bool isGreater = k1 == 0;
   const int i = isGreater ? k0 : k1;
   float colVal = 0.f, t_hit = 0.f, tn = 0.f;
   v4 normal = mk4(0.f, 0.f, 0.f, 0.f);
+  bool mine = false;  // this slab owns the crossing sample
   if (i != K_NONE) {
     const IsoRay q = iso_ray(a, x, y, true);
     const float s = slice_of_k(V, q.w0, q.dw, i);
@@ -539,8 +549,30 @@ __global__ void __launch_bounds__(128) iso_slab_resolve_kernel(const IsoArgs a, 
       if (lo_need < (float)V.z_lo || hi_need > (float)(V.z_lo + V.local_nz - 1)) atomicExch(err, 1u);
       iso_resolve<FMT, LINEAR>(a, q, i, isGreater, t_hit, normal, colVal);
       tn = q.tnear;
+      mine = true;
     }
   }
+  if (peer.world > 0) {
+    // exactly one rank owns a crossing: it stores the finished pixel into every rank's planes (its own included);
+    // a pixel without a crossing is cleared by every rank for itself; nobody else touches a pixel
+    const size_t n = (size_t)a.width * a.height;
+    if (inb && (mine || i == K_NONE)) {
+      if (i == K_NONE) t_hit = __int_as_float(0x7f800000);
+      for (int r = 0; r < (mine ? peer.world : 1); ++r) {
+        float *P = mine ? peer.planes[r] : peer.planes[peer.src];
+        P[p] = colVal;
+        P[n + p] = tn;
+        P[2 * n + p] = t_hit;
+        float *N3 = P + (size_t)peer.normals_plane * n + 3 * p;
+        N3[0] = normal.x;
+        N3[1] = normal.y;
+        N3[2] = normal.z;
+      }
+    }
+    set_tile_flag(a.tile_hit, a.width, a.height, inb && i != K_NONE);
+    return;
+  }
+  if (!inb) return;
   a.out[p] = colVal;
   a.alpha[p] = tn;
   a.depth[p] = t_hit;
@@ -568,19 +600,19 @@ __global__ void __launch_bounds__(128) iso_slab_fix_kernel(int width, int height
 
 template <int FMT>
 static cudaError_t launch_iso_slab_dt(const IsoArgs &a, bool linear, int phase, int *k1, int *k0, float *occ,
-                                      unsigned *err, cudaStream_t st) {
+                                      unsigned *err, cudaStream_t st, const IsoPeer &peer) {
   dim3 grid((a.width + 15) / 16, (a.height + 7) / 8), block(128);
   if (phase == 0) {
     if (a.skip) {
-      if (linear) iso_slab_search_kernel<FMT, true, true><<<grid, block, 0, st>>>(a, k1, k0);
-      else iso_slab_search_kernel<FMT, false, true><<<grid, block, 0, st>>>(a, k1, k0);
+      if (linear) iso_slab_search_kernel<FMT, true, true><<<grid, block, 0, st>>>(a, k1, k0, peer);
+      else iso_slab_search_kernel<FMT, false, true><<<grid, block, 0, st>>>(a, k1, k0, peer);
     } else {
-      if (linear) iso_slab_search_kernel<FMT, true, false><<<grid, block, 0, st>>>(a, k1, k0);
-      else iso_slab_search_kernel<FMT, false, false><<<grid, block, 0, st>>>(a, k1, k0);
+      if (linear) iso_slab_search_kernel<FMT, true, false><<<grid, block, 0, st>>>(a, k1, k0, peer);
+      else iso_slab_search_kernel<FMT, false, false><<<grid, block, 0, st>>>(a, k1, k0, peer);
     }
   } else if (phase == 1) {
-    if (linear) iso_slab_resolve_kernel<FMT, true><<<grid, block, 0, st>>>(a, k1, k0, occ, err);
-    else iso_slab_resolve_kernel<FMT, false><<<grid, block, 0, st>>>(a, k1, k0, occ, err);
+    if (linear) iso_slab_resolve_kernel<FMT, true><<<grid, block, 0, st>>>(a, k1, k0, occ, err, peer);
+    else iso_slab_resolve_kernel<FMT, false><<<grid, block, 0, st>>>(a, k1, k0, occ, err, peer);
   } else {
     iso_slab_fix_kernel<<<grid, block, 0, st>>>(a.width, a.height, k1, k0, a.depth, a.tile_hit);
   }
@@ -588,13 +620,15 @@ static cudaError_t launch_iso_slab_dt(const IsoArgs &a, bool linear, int phase, 
 }
 
 cudaError_t launch_iso_slab(const IsoArgs &a, int dtype, bool linear, int phase, int *k1, int *k0, float *occ,
-                            unsigned *err, cudaStream_t st) {
+                            unsigned *err, cudaStream_t st, const IsoPeer *peer_in) {
+  IsoPeer peer;
+  if (peer_in) peer = *peer_in; else memset(&peer, 0, sizeof peer);
   switch (dtype) {  // FMT = dtype + 3 * layout
-    case 0: return launch_iso_slab_dt<0>(a, linear, phase, k1, k0, occ, err, st);
-    case 1: return launch_iso_slab_dt<1>(a, linear, phase, k1, k0, occ, err, st);
-    case 2: return launch_iso_slab_dt<2>(a, linear, phase, k1, k0, occ, err, st);
-    case 4: return launch_iso_slab_dt<4>(a, linear, phase, k1, k0, occ, err, st);
-    case 5: return launch_iso_slab_dt<5>(a, linear, phase, k1, k0, occ, err, st);
+    case 0: return launch_iso_slab_dt<0>(a, linear, phase, k1, k0, occ, err, st, peer);
+    case 1: return launch_iso_slab_dt<1>(a, linear, phase, k1, k0, occ, err, st, peer);
+    case 2: return launch_iso_slab_dt<2>(a, linear, phase, k1, k0, occ, err, st, peer);
+    case 4: return launch_iso_slab_dt<4>(a, linear, phase, k1, k0, occ, err, st, peer);
+    case 5: return launch_iso_slab_dt<5>(a, linear, phase, k1, k0, occ, err, st, peer);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -86,9 +86,32 @@ cudaError_t launch_texrate_probe(const Volume &V, int dtype, bool linear, int bl
                                  cudaStream_t st);
 
 cudaError_t launch_iso(const IsoArgs &a, int dtype, bool linear, bool exact, bool stats, cudaStream_t st);
+// Sort-last iso surface over peer memory (spv_render_iso_composite): world > 0 switches the two slab kernels from
+// their local planes to the peers' memory.
+//   search   k1 / k0 of band o's pixels go to owner o's staging  kpart[o][src][plane][band]
+//   resolve  the rank owning a pixel's crossing stores the finished pixel into EVERY rank's result planes; pixels
+//            without a crossing are cleared locally (depth = INFINITY), pixels resolved elsewhere are left alone
+struct IsoPeer {
+  int world;                 // 0: off (local planes; the caller reduces with NCCL)
+  int band_rows;             // image rows per band
+  unsigned src;              // my rank
+  unsigned band;             // band_rows * width
+  int *kpart[MAX_WORLD];     // owner o's staging of this frame's parity
+  float *planes[MAX_WORLD];  // rank r's [out | alpha | depth | occ | normals(3) | ...] planes
+  int normals_plane;         // plane index the resolved normals go to: 4 (normals) or 9 (tmp_vec, blurred into 4 later)
+};
 // sort-last iso surface: phase 0 = search (writes k1 / k0), 1 = resolve (reads them), 2 = fix-up after the SUM
 cudaError_t launch_iso_slab(const IsoArgs &a, int dtype, bool linear, int phase, int *k1, int *k0, float *occ,
-                            unsigned *err, cudaStream_t st);
+                            unsigned *err, cudaStream_t st, const IsoPeer *peer = nullptr);
+// owner of a band: element-wise MIN of the k1 / k0 partials of all ranks, stored into every rank's k planes
+struct KReduceArgs {
+  const int *part;           // my staging of this parity: [world][2][band]
+  int *kplanes[MAX_WORLD];   // rank r's k planes: [2][n_image]
+  int world;
+  unsigned band, first_pixel, n_pixels;  // as CompFinishArgs
+  size_t n_image;            // width * height
+};
+cudaError_t launch_k_reduce(const KReduceArgs &a, cudaStream_t st);
 // buf -> tmp (x pass), tmp -> buf (y pass); ncomp = 1 (conv_x/conv_y) or 3 (conv_vec_x/conv_vec_y)
 cudaError_t launch_conv(float *buf, float *tmp, int width, int height, int ncomp, const ConvWeights &w,
                         cudaStream_t st);

@@ -319,9 +319,36 @@ class SlabMaxProjector(VolumeRenderer):
         self.output_occlusion = flat[3 * n:4 * n].reshape(shape)
         self.output_normals = flat[4 * n:7 * n].reshape(shape + (3,))
 
+    def enqueue_iso_composite(self, raw_only=False):
+        """Enqueue one sort-last iso surface whose exchanges all run over peer memory (spv_render_iso_composite); no
+        host synchronisation: the peers must enqueue theirs as well."""
+        if not self._connected:
+            raise RuntimeError("SlabMaxProjector(composite='peer'): call connect() / connect_local() first")
+        if self._parts:
+            raise NotImplementedError("sort-last iso_surface renders one slab per rank")
+        self._check(self._lib.spv_render_iso_composite(self._ctx, C.byref(self._iso_params(raw_only))))
+
+    def collect_iso(self):
+        """Wait for the enqueued iso composite and read all planes back."""
+        self._check(self._lib.spv_comp_check(self._ctx))
+        self._check(self._lib.spv_iso_slab_check(self._ctx))
+        if self.readback_ranks is not None and self.rank not in self.readback_ranks:
+            return
+        flat, n = self._fetch(7)
+        shape = (self.height, self.width)
+        self.output = flat[:n].reshape(shape)
+        self.output_alpha = flat[n:2 * n].reshape(shape)
+        self.output_depth = flat[2 * n:3 * n].reshape(shape)
+        self.output_occlusion = flat[3 * n:4 * n].reshape(shape)
+        self.output_normals = flat[4 * n:7 * n].reshape(shape + (3,))
+
     def _render_isosurface(self, raw_only=False):
-        """search on every slab -> all-reduce(MIN) of the candidate sample indices -> the owner of each crossing
+        """composite="peer": spv_render_iso_composite.  composite="nccl": search on every slab -> all-reduce(MIN) of the candidate sample indices -> the owner of each crossing
         resolves it -> all-reduce(SUM) assembles the planes -> post passes on every rank."""
+        if self.composite == "peer":
+            self.enqueue_iso_composite(raw_only)
+            self.collect_iso()
+            return
         torch, dist = self._torch, self._dist
         multi = self.world > 1 and dist.is_initialized()
         self.iso_search()

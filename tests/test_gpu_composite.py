@@ -174,3 +174,84 @@ def test_sort_last_iso_surface_reports_a_halo_that_is_too_small():
         _iso_all(rs)
     for r in rs:
         r.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("dtype,maxval", [(np.uint16, 24000.), (np.float32, .5)])
+def test_peer_iso_composite_is_bit_exact_on_every_rank(world, dtype, maxval):
+    """spv_render_iso_composite: candidates pushed to the band owners, MIN + redistribution by the owners, finished
+    pixels stored into every rank by the rank that owns the crossing -- no reduction on the host side.  Every rank
+    ends up with the single-GPU render, frame after frame (the staging alternates by frame parity), also when
+    max projections are composited in between on the same contexts."""
+    from spimagine_b200 import VolumeRenderer
+    from spimagine_b200.multigpu import SlabMaxProjector, iso_halo
+    data = scenes.vol_g(0, dtype, seed=7, shape=(64, 72, 80))
+    size = (136, 104)
+    rs = _iso_ranks(data, size, world, iso_halo(64), composite="peer")
+    SlabMaxProjector.connect_local(rs)
+    mono = VolumeRenderer(size)
+    mono.set_data(data)
+    for theta, skip, gamma in [(0.4, None, 1.), (1.9, False, 1.), (3.0, None, .8), (4.4, None, 1.)]:
+        M, P = scenes.gui_camera(theta, 3.2)
+        for r in rs + [mono]:
+            r.set_projection(P)
+            r.set_modelView(M)
+            r.set_max_val(maxval)
+            r.set_gamma(gamma)
+            r.set_skipping(skip)
+        mono.render(method="iso_surface")
+        assert np.isfinite(mono.output_depth).sum() > 500
+        for s in rs:
+            s.enqueue_iso_composite()
+        for s in rs:
+            s.collect_iso()
+        for s in rs:
+            assert np.array_equal(s.output_depth, mono.output_depth), (world, s.rank, theta)
+            assert np.array_equal(s.output_alpha, mono.output_alpha)
+            assert np.array_equal(s.output_normals, mono.output_normals)
+            assert np.array_equal(s.output_occlusion, mono.output_occlusion)
+            assert np.array_equal(s.output, mono.output)
+        if theta > 1.5 and theta < 2.:   # a max projection through the same staging / counters in between
+            for r in rs:
+                r.set_skipping(False)
+            mono.set_skipping(False)
+            mono.render(method="max_project")
+            for s in rs:
+                s.enqueue_composite()
+            for s in rs:
+                s.collect()
+                assert np.array_equal(s.output, mono.output)
+    # the iso_surface kernel alone (no post passes)
+    mono.render(method="iso_surface_raw")
+    for s in rs:
+        s.enqueue_iso_composite(raw_only=True)
+    for s in rs:
+        s.collect_iso()
+        assert np.array_equal(s.output_depth, mono.output_depth) and np.array_equal(s.output, mono.output)
+        assert np.array_equal(s.output_normals, mono.output_normals)
+    for r in rs + [mono]:
+        r.close()
+
+
+def test_peer_iso_composite_reports_a_halo_that_is_too_small():
+    from spimagine_b200 import _lib
+    from spimagine_b200.multigpu import SlabMaxProjector
+    data = scenes.vol_g(0, np.uint16, seed=7, shape=(64, 72, 80))
+    rs = _iso_ranks(data, (96, 80), 4, halo=1, composite="peer")
+    SlabMaxProjector.connect_local(rs)
+    M, P = scenes.gui_camera(0.4, 3.2)
+    for r in rs:
+        r.set_projection(P)
+        r.set_modelView(M)
+        r.set_max_val(24000.)
+        r.enqueue_iso_composite()
+    errors = 0
+    for r in rs:
+        try:
+            r.collect_iso()
+        except _lib.SpvError as e:
+            assert "halo" in str(e)
+            errors += 1
+    assert errors >= 1      # the ranks that own a crossing whose taps leave their halo report it
+    for r in rs:
+        r.close()
