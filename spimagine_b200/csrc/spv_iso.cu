@@ -895,29 +895,32 @@ __global__ void __launch_bounds__(64) occlusion_kernel(float *__restrict__ d_out
 
 // Queue form.  Only the blocks near a surface do any work (60 hash chains per pixel) and they are few and clustered:
 // handed out as CTAs they land unevenly on the SMs (measured: SMs busy 62 % of the launch).  Instead
-//   occ_list_kernel   one warp per 32x2 block: out of reach -> writes the zeros, in reach -> appends the block to a list
+//   occ_list_kernel   one warp per 32x8 pixels: out of reach -> writes the zeros, in reach -> appends its 32x2 blocks to a list
 //   occ_queue_kernel  a fixed grid (a few CTAs per SM) pulls work items off the list until it is empty
 // The counters {count, head} are double-buffered by frame parity; the list kernel clears the other pair for the next
 // frame, so there is no memset on the stream.
-constexpr int OCC_BW = 32, OCC_BH = 2;
+constexpr int OCC_BW = 32, OCC_BH = 2, OCC_GROUP = 4;  // the list kernel classifies OCC_GROUP stacked blocks at once
 __global__ void __launch_bounds__(256) occ_list_kernel(float *__restrict__ d_output, int Nx, int Ny, int radius,
                                                        const unsigned char *__restrict__ tile_hit, int tiles_x, int obx,
-                                                       int n_ob, unsigned *__restrict__ cnt, unsigned *__restrict__ cnt_next,
+                                                       int oby, unsigned *__restrict__ cnt, unsigned *__restrict__ cnt_next,
                                                        unsigned *__restrict__ list) {
-  const int ob = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (ob == 0 && lane == 0) cnt_next[0] = cnt_next[1] = 0u;
-  if (ob >= n_ob) return;
-  const int px = (ob % obx) * OCC_BW, py = (ob / obx) * OCC_BH;
-  const int mine = tiles_in_reach(tile_hit, tiles_x, Nx, Ny, px, px + OCC_BW - 1, py, py + OCC_BH - 1, radius, lane, 32);
+  // one warp per group of OCC_GROUP vertically adjacent blocks (32 x 8 pixels): their reach rectangles differ by a
+  // few rows only, so one scan of the tile flags over the union decides all of them (conservatively: a block that
+  // is computed although nothing is in reach still gets the right answer, 0)
+  const int g = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (g == 0 && lane == 0) cnt_next[0] = cnt_next[1] = 0u;
+  const int gy = (oby + OCC_GROUP - 1) / OCC_GROUP;
+  if (g >= obx * gy) return;
+  const int bx = g % obx, by0 = (g / obx) * OCC_GROUP, nb = min(OCC_GROUP, oby - by0);
+  const int px = bx * OCC_BW, py = by0 * OCC_BH;
+  const int mine = tiles_in_reach(tile_hit, tiles_x, Nx, Ny, px, px + OCC_BW - 1, py, py + nb * OCC_BH - 1, radius, lane, 32);
   if (__any_sync(0xffffffffu, mine != 0)) {
-    if (lane == 0) list[atomicAdd(cnt, 1u)] = (unsigned)ob;
+    if (lane < nb) list[atomicAdd(cnt, 1u)] = (unsigned)((by0 + lane) * obx + bx);
   } else {
     const int x = px + lane;
-    if (x < Nx) {
-#pragma unroll
-      for (int r = 0; r < OCC_BH; ++r)
+    if (x < Nx)
+      for (int r = 0; r < nb * OCC_BH; ++r)
         if (py + r < Ny) d_output[x + (size_t)Nx * (py + r)] = 0.f;
-    }
   }
 }
 
@@ -972,10 +975,11 @@ cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int 
                              const unsigned char *tile_hit, const float4 *taps, unsigned *queue, unsigned frame, int sms,
                              cudaStream_t st) {
   if (tile_hit && queue) {
-    const int obx = (width + OCC_BW - 1) / OCC_BW, n_ob = obx * ((height + OCC_BH - 1) / OCC_BH);
+    const int obx = (width + OCC_BW - 1) / OCC_BW, oby = (height + OCC_BH - 1) / OCC_BH;
+    const int groups = obx * ((oby + OCC_GROUP - 1) / OCC_GROUP);
     unsigned *cnt = queue + 2 * (frame & 1u), *cnt_next = queue + 2 * ((frame + 1u) & 1u), *list = queue + 4;
-    occ_list_kernel<<<(n_ob + 7) / 8, 256, 0, st>>>(occ, width, height, radius, tile_hit, (width + 7) / 8, obx, n_ob, cnt,
-                                                    cnt_next, list);
+    occ_list_kernel<<<(groups + 7) / 8, 256, 0, st>>>(occ, width, height, radius, tile_hit, (width + 7) / 8, obx, oby, cnt,
+                                                     cnt_next, list);
     occ_queue_kernel<<<(sms > 0 ? sms : 148) * occ_ctas_per_sm, 128, 0, st>>>(occ, width, height, radius, n_points, depth, taps, obx, cnt,
                                                                  list);
     return cudaGetLastError();
