@@ -245,10 +245,10 @@ SPV_API int spv_last_stats(spv_ctx *ctx, unsigned long long *v, int n); /* [hit 
 SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
 /* performance knobs that never change results; knob 0 = CTA shape / occupancy target of the max-projection kernel,
  * knob 1 = persistent CTAs pulling tiles from a counter (1) or one CTA per tile (0), knob 2 = default band count of
- * spv_render_mip_to_host, knob 3 = spv_render_mip_to_host stores straight into pinned host memory, knob 4 = warps per
- * CTA of the iso-surface search (1, 2 or 4), knob 5 = its CTAs are dealt from the image centre outwards (1, default) or
- * row by row (0), knob 6 = resident CTAs per SM of the occlusion queue kernel, knob 7 = copy streams the band copies of
- * spv_render_mip_to_host alternate between (1 or 2) */
+ * spv_render_mip_to_host, knob 3 = spv_render_mip_to_host stores straight into pinned host memory, knob 4 = warps that share a
+ * ray of the iso-surface search, each taking a segment of its samples (1, 2 or 4), knob 5 = its CTAs are dealt from the
+ * image centre outwards (1, default) or row by row (0), knob 6 = resident CTAs per SM of the occlusion queue kernel,
+ * knob 7 = copy streams the band copies of spv_render_mip_to_host alternate between (1 or 2) */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 SPV_API const char *spv_last_error(spv_ctx *ctx);                   /* ctx may be NULL: last create error */
 SPV_API int spv_version(void);

@@ -39,11 +39,11 @@ for M, P in cams:
 lib, ctx = rend._lib, rend._ctx
 import hashlib
 for variant in os.environ.get("EXP_ISO_VARIANTS", "4:1").split(","):
-    cta_warps, centre = (int(v) for v in variant.split(":"))
-    lib.spv_set_tuning(ctx, 4, cta_warps)
+    segments, centre = (int(v) for v in variant.split(":")[:2])
+    lib.spv_set_tuning(ctx, 4, segments)
     lib.spv_set_tuning(ctx, 5, centre)
     lib.spv_set_tuning(ctx, 6, int(os.environ.get("EXP_OCC_CTAS", "5")))
-    print("iso search CTA = %d warp(s), centre-out order %d" % (cta_warps, centre))
+    print("iso search: %d segment(s) per ray, centre-out order %d" % (segments, centre))
     for flags, name in ((_lib.ISO_RAW_ONLY, "iso_surface kernel alone"), (0, "full chain (5 launches)")):
         p = _lib.IsoParams(rend._box(), maxVal / 2, 1., 200, .1, 21, 30, flags)
         for rep in range(2):
@@ -62,6 +62,17 @@ for variant in os.environ.get("EXP_ISO_VARIANTS", "4:1").split(","):
     print("    image sha1", hashlib.sha1(rend.output.tobytes() + rend.output_depth.tobytes() +
                                          rend.output_normals.tobytes()).hexdigest()[:12])
 rend.enable_stats(True)
+for split in (1, 2, 4):
+    lib.spv_set_tuning(ctx, 4, split)
+    for f in (3, 12):
+        rend.set_modelView(cams[f][0])
+        rend.render(method="iso_surface")
+        mx, sm = rend.last_warp_cycles()
+        nw = (IMG // 8) * (IMG // 4) * split
+        print("segments %d frame %2d: longest warp %d cycles (%.1f us at 1.9 GHz): %d search iterations, %d lockstep skip "
+              "steps; mean warp %.0f cycles" % (split, f, mx >> 32, (mx >> 32) / 1.9e3, (mx >> 16) & 0xffff, mx & 0xffff,
+                                                sm / nw))
+        print("    warps by log2(cycles):", {b: c for b, c in enumerate(rend.last_warp_histogram) if c})
 rend.set_modelView(cams[3][0])
 rend.render(method="iso_surface")
 print("hit rays, samples:", rend.last_stats(), " hit pixels:", int(np.isfinite(rend.output_depth).sum()))

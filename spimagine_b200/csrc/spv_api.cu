@@ -44,7 +44,7 @@ struct spv_ctx {
   int linear = 1, sampler = SPV_SAMPLER_TMU, int_filter = 1, skipping = -1, stats_on = 0, tile_variant = 0, persistent = 0;
   int bands = 0;  // default band count of spv_render_mip_to_host (knob 2); 0 = 12 where the copy stream can wait on the
                   // band counters (one launch per frame), else 2 (one launch per band) -- profiles/r01_exp_e2e.txt
-  int iso_cta_warps = 4;  // tuning knob 4
+  int iso_segments = 1;   // tuning knob 4 (measured on configs[2]: 1 -> 97 us, 2 -> 110 us, 4 -> 178 us)
   int iso_centre_out = 1; // tuning knob 5
   int direct_host = 0;  // spv_render_mip_to_host: the kernel stores straight into the pinned staging (tuning knob 3)
   unsigned *d_tile_counter = nullptr;
@@ -89,7 +89,7 @@ struct spv_ctx {
   int n_extra = 0;
   int last_method = 0;    // 0 = mip, 1 = iso
   unsigned long long *d_stats = nullptr;
-  unsigned long long h_stats[2] = {0, 0};
+  unsigned long long h_stats[40] = {0};  // hit rays, samples fetched, longest warp / sum over warps (cycles; iso search)
   unsigned long long launches = 0;
   std::string err;
 
@@ -262,7 +262,7 @@ SPV_API int spv_create(int device, int width, int height, spv_ctx **out) {
     CC(cudaEventCreateWithFlags(&ctx->ev_consumed[s], cudaEventDisableTiming));
   }
   CC(cudaMalloc(&ctx->d_minmax, 2 * sizeof(float)));
-  CC(cudaMalloc(&ctx->d_stats, 2 * sizeof(unsigned long long)));
+  CC(cudaMalloc(&ctx->d_stats, 40 * sizeof(unsigned long long)));
   CC(cudaMalloc(&ctx->d_tile_counter, sizeof(unsigned)));
   CC(cudaMalloc(&ctx->d_band_done, 64 * sizeof(unsigned)));
   CC(cudaMemset(ctx->d_band_done, 0, 64 * sizeof(unsigned)));
@@ -720,7 +720,7 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   else if (knob == 1) ctx->persistent = value != 0;
   else if (knob == 2) ctx->bands = value < 1 ? 1 : (value > 64 ? 64 : value);
   else if (knob == 3) ctx->direct_host = value != 0;
-  else if (knob == 4) ctx->iso_cta_warps = value;
+  else if (knob == 4) ctx->iso_segments = value == 4 ? 4 : (value == 2 ? 2 : 1);
   else if (knob == 5) ctx->iso_centre_out = value != 0;
   else if (knob == 7) ctx->copy_streams = value > 1 ? 2 : 1;
   else if (knob == 6) occ_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : value);  // process-wide
@@ -741,7 +741,7 @@ SPV_API int spv_set_matrices(spv_ctx *ctx, const float *invP, const float *invM)
 }
 
 static int begin_render(spv_ctx *ctx) {
-  if (ctx->stats_on) CU(cudaMemsetAsync(ctx->d_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  if (ctx->stats_on) CU(cudaMemsetAsync(ctx->d_stats, 0, 40 * sizeof(unsigned long long), ctx->stream));
   CU(cudaEventRecord(ctx->ev0, ctx->stream));
   return 0;
 }
@@ -749,7 +749,7 @@ static int end_render(spv_ctx *ctx) {
   CU(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
   if (ctx->stats_on)
-    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, 40 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   return 0;
 }
 
@@ -1105,7 +1105,7 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   a.tgx = (ctx->cgx + 3) / 4; a.tgy = (ctx->cgy + 3) / 4; a.tgz = (ctx->cgz + 3) / 4;
   memcpy(a.box, p->box, sizeof a.box);
   a.iso_val = p->iso_val; a.gamma = p->gamma; a.max_steps = p->max_steps;
-  a.cta_warps = ctx->iso_cta_warps;
+  a.segments = ctx->iso_segments;
   a.centre_out = ctx->iso_centre_out;
   const bool exact_iso = ctx->sampler == SPV_SAMPLER_EXACT;
   a.tile_hit = exact_iso ? nullptr : ctx->d_tile_hit;
@@ -1192,7 +1192,7 @@ static int iso_args(spv_ctx *ctx, const spv_iso_params *p, IsoArgs &a, const cha
   a.tgx = (ctx->cgx + 3) / 4; a.tgy = (ctx->cgy + 3) / 4; a.tgz = (ctx->cgz + 3) / 4;
   memcpy(a.box, p->box, sizeof a.box);
   a.iso_val = p->iso_val; a.gamma = p->gamma; a.max_steps = p->max_steps;
-  a.cta_warps = ctx->iso_cta_warps;
+  a.segments = ctx->iso_segments;
   a.centre_out = ctx->iso_centre_out;
   a.tile_hit = ctx->d_tile_hit;
   a.skip = ctx->skipping != 0;
@@ -1493,8 +1493,7 @@ SPV_API int spv_last_stats(spv_ctx *ctx, unsigned long long *v, int n) {
   if (!v || n < 2) return fail(ctx, SPV_EINVAL, "spv_last_stats: need room for 2 counters");
   if (!ctx->stats_on) return fail(ctx, SPV_ENODATA, "spv_last_stats: statistics are not enabled");
   CU(cudaStreamSynchronize(ctx->stream));
-  v[0] = ctx->h_stats[0];
-  v[1] = ctx->h_stats[1];
+  for (int k = 0; k < (n < 40 ? n : 40); ++k) v[k] = ctx->h_stats[k];
   return 0;
 }
 

@@ -360,82 +360,146 @@ __device__ __forceinline__ void set_tile_flag(unsigned char *tile_hit, int width
   if (tx < tiles_x && ty < tiles_y) tile_hit[ty * tiles_x + tx] = (unsigned char)(any != 0);
 }
 
+constexpr int K_NONE = 0x7fffffff;  // no such sample
+
+// One step of the search for the first crossing among samples [k0, kend) of a ray: cross the cells that cannot hold
+// one (hierarchical skipping, exact), then classify the next BATCH samples by their bricks and fetch the survivors
+// together (independent fetches in flight instead of one fetch -> compare -> branch round trip per sample; at most
+// BATCH-1 samples behind the crossing are fetched in vain).  Returns true while the range is not exhausted and nothing
+// was found; `found` receives the crossing sample.
+template <int FMT, bool LINEAR, bool SKIP>
+__device__ __forceinline__ bool iso_search_step(const IsoArgs &a, const IsoRay &q, const IsoDda &d, const IsoLevel &Ltop,
+                                                const IsoLevel &Lco, bool isGreater, int &k0, int kend, int &found,
+                                                unsigned &nfetch, unsigned &nskip) {
+  constexpr int BATCH = 8;
+  const Volume &V = a.vol;
+  const float INF = __int_as_float(0x7f800000);
+  if (SKIP) {
+    const int skip_cls = isGreater ? 1 : 2;  // cells of this class hold no crossing
+    while (k0 < kend) {
+      const int kn = iso_skip_step(a, q, d, Ltop, Lco, k0, kend, skip_cls);
+      if (kn == k0) break;
+      k0 = kn;
+      ++nskip;
+    }
+    if (k0 >= kend) return false;
+  }
+  float v[BATCH];
+  bool need[BATCH];
+#pragma unroll
+  for (int j = 0; j < BATCH; ++j) {
+    const float t = (float)min(k0 + j, kend - 1);
+    need[j] = SKIP ? iso_cell_may_hold<false>(a, q, t, !isGreater) : true;
+  }
+#pragma unroll
+  for (int j = 0; j < BATCH; ++j) {
+    v[j] = need[j] ? iso_at<FMT, LINEAR>(V, q, (float)min(k0 + j, kend - 1)) : (isGreater ? INF : -INF);
+    nfetch += need[j];
+  }
+  bool hit = false;
+#pragma unroll
+  for (int j = BATCH - 1; j >= 0; --j)
+    if (k0 + j < kend && ((v[j] > a.iso_val) != isGreater)) {
+      found = k0 + j;
+      hit = true;
+    }
+  if (hit) return false;
+  k0 += BATCH;
+  return k0 < kend;
+}
+
+// One lane per ray (a.segments == 1, the default) or per ray segment: a CTA of 4 warps covers 4 / SEG tiles of 8x4
+// pixels, the samples [1, max_steps) of every ray are cut into SEG equal segments searched by SEG different warps, and
+// the minimum over the segments' first crossings is the ray's first crossing.  Segments were meant to shorten the
+// launch's longest warps (rays that graze blobs for most of their length: 230 k cycles against a mean of 13 k, see
+// spv_last_stats); measured, the SEG ray setups per ray and the barrier cost more than the shorter searches save
+// (97 / 110 / 178 us for 1 / 2 / 4 segments on configs[2]), so it stays a tuning knob.
 template <int FMT, bool LINEAR, bool SKIP>
 __global__ void __launch_bounds__(128, SPV_ISO_MINB) iso_fast_kernel(const IsoArgs a) {
-  constexpr int BATCH = 8;
-  unsigned x, y;
-  tile_pixel(x, y, a.centre_out != 0);
+  __shared__ int s_found[4][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int SEG = a.segments;                    // 1, 2 or 4
+  const int seg = warp % SEG, tile = warp / SEG, tiles = 4 / SEG;
+  // tile geometry of the CTA: 4 tiles = 2x2 (16x8 pixels), 2 = 2x1, 1 = 1x1
+  const int lx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
+  const int ly = ((lane >> 1) & 1) | ((lane >> 2) & 2);
+  unsigned cx, cy;
+  tile_of_cta(a.centre_out != 0, cx, cy);
+  const unsigned tx = cx * (tiles >= 2 ? 2 : 1) + (tile & 1), ty = cy * (tiles >= 4 ? 2 : 1) + (tile >> 1);
+  const unsigned x = tx * 8 + lx, y = ty * 4 + ly;
   const unsigned Nx = a.width, Ny = a.height;
   const bool inb = x < Nx && y < Ny;
   const size_t p = x + (size_t)Nx * y;
   const Volume &V = a.vol;
   const float INF = __int_as_float(0x7f800000);
+  const int maxSteps = a.max_steps;
   unsigned nfetch = 0;
+  const long long t_begin = a.stats ? clock64() : 0;
+  unsigned dbg_iters = 0, dbg_walk = 0;  // statistics: search iterations of this warp, skip steps it waited for
 
   const IsoRay q = iso_ray(a, x, y, inb);
-  bool hitIso = false;
-  float t_hit = INF;
-  v4 normal = mk4(0.f, 0.f, 0.f, 0.f);
-  float colVal = 0.f;
-  if (q.hit) {
-    const float isoVal = a.iso_val;
-    const int maxSteps = a.max_steps;
-    const bool isGreater = iso_at<FMT, LINEAR>(V, q, 0.f) > isoVal;
-    int i = maxSteps;
-    // Empty-space skipping (exact): samples that cannot be the first crossing are not fetched.  Cells of 128^3 and
-    // 32^3 texels that cannot hold a sample on the other side of the threshold are crossed in one step; inside the
-    // others every sample is classified by its 8^3 brick and the survivors are fetched BATCH at a time.
-    const IsoDda d = iso_dda(a, q);
-    const IsoLevel Ltop = {a.top, a.tgx, a.tgy, a.tgz}, Lco = {a.coarse, a.cgx, a.cgy, a.cgz};
-    const int skip_cls = isGreater ? 1 : 2;  // cells of this class hold no crossing
-    int k0 = 1;
-    while (k0 < maxSteps) {
-      if (SKIP) {
-        while (k0 < maxSteps) {
-          const int kn = iso_skip_step(a, q, d, Ltop, Lco, k0, maxSteps, skip_cls);
-          if (kn == k0) break;
-          k0 = kn;
-        }
-        if (k0 >= maxSteps) break;
-      }
-      float v[BATCH];
-      bool need[BATCH];
-#pragma unroll
-      for (int j = 0; j < BATCH; ++j) {
-        const float t = (float)min(k0 + j, maxSteps - 1);
-        need[j] = SKIP ? iso_cell_may_hold<false>(a, q, t, !isGreater) : true;
-      }
-#pragma unroll
-      for (int j = 0; j < BATCH; ++j) {
-        v[j] = need[j] ? iso_at<FMT, LINEAR>(V, q, (float)min(k0 + j, maxSteps - 1)) : (isGreater ? INF : -INF);
-        nfetch += need[j];
-      }
-#pragma unroll
-      for (int j = BATCH - 1; j >= 0; --j)
-        if (k0 + j < maxSteps && ((v[j] > isoVal) != isGreater)) {
-          i = k0 + j;
-          hitIso = true;
-        }
-      if (hitIso) break;
-      k0 += BATCH;
+  const IsoDda d = iso_dda(a, q);
+  const IsoLevel Ltop = {a.top, a.tgx, a.tgy, a.tgz}, Lco = {a.coarse, a.cgx, a.cgy, a.cgz};
+  const bool isGreater = q.hit && iso_at<FMT, LINEAR>(V, q, 0.f) > a.iso_val;
+  const int seg_len = (maxSteps - 1 + SEG - 1) / SEG;
+  int i = K_NONE, k0 = 1 + seg * seg_len;
+  const int kend = min(k0 + seg_len, maxSteps);
+  bool active = q.hit && k0 < kend;
+  for (;;) {
+    unsigned nskip = 0;
+    if (active) active = iso_search_step<FMT, LINEAR, SKIP>(a, q, d, Ltop, Lco, isGreater, k0, kend, i, nfetch, nskip);
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (a.stats) {
+      ++dbg_iters;
+      dbg_walk += __reduce_max_sync(0xffffffffu, nskip);
     }
+    if (act == 0u) break;
+  }
+  if (SEG > 1) {
+    s_found[warp][lane] = i;
+    __syncthreads();
+    if (seg == 0)
+      for (int s2 = 1; s2 < SEG; ++s2) i = min(i, s_found[warp + s2][lane]);
+  }
+  if (seg == 0) {
+    const bool hitIso = i != K_NONE;
+    float t_hit = INF;
+    v4 normal = mk4(0.f, 0.f, 0.f, 0.f);
+    float colVal = 0.f;
     if (hitIso) {
       iso_resolve<FMT, LINEAR>(a, q, i, isGreater, t_hit, normal, colVal);
       nfetch += 22;
     }
+    if (inb) {
+      a.out[p] = hitIso ? colVal : 0.f;
+      a.alpha[p] = hitIso ? q.tnear : 0.f;
+      a.depth[p] = hitIso ? t_hit : INF;
+      a.normals[3 * p + 0] = normal.x;
+      a.normals[3 * p + 1] = normal.y;
+      a.normals[3 * p + 2] = normal.z;
+    }
+    const unsigned any = __any_sync(0xffffffffu, hitIso);
+    if (lane == 0 && a.tile_hit) {
+      const int tiles_x = (a.width + 7) / 8, tiles_y = (a.height + 3) / 4;
+      if ((int)tx < tiles_x && (int)ty < tiles_y) a.tile_hit[ty * tiles_x + tx] = (unsigned char)(any != 0);
+    }
   }
-  if (inb) {
-    a.out[p] = hitIso ? colVal : 0.f;
-    a.alpha[p] = hitIso ? q.tnear : 0.f;
-    a.depth[p] = hitIso ? t_hit : INF;
-    a.normals[3 * p + 0] = normal.x;
-    a.normals[3 * p + 1] = normal.y;
-    a.normals[3 * p + 2] = normal.z;
-  }
-  set_tile_flag(a.tile_hit, a.width, a.height, hitIso, a.centre_out != 0);
   if (a.stats) {
-    atomicAdd(a.stats + 0, q.hit ? 1ull : 0ull);
-    atomicAdd(a.stats + 1, (unsigned long long)nfetch);
+    const unsigned long long dur = (unsigned long long)(clock64() - t_begin);
+    unsigned nh = (q.hit && seg == 0) ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) {
+      nh += __shfl_down_sync(0xffffffffu, nh, o);
+      nfetch += __shfl_down_sync(0xffffffffu, nfetch, o);
+    }
+    if (lane == 0) {
+      atomicAdd(a.stats + 0, (unsigned long long)nh);
+      atomicAdd(a.stats + 1, (unsigned long long)nfetch);
+      // how long this warp lived (the longest one bounds the launch from below), with what it did:
+      // cycles << 32 | search iterations << 16 | skip steps the warp executed in lockstep
+      atomicMax(a.stats + 2, (dur << 32) | ((unsigned long long)min(dbg_iters, 65535u) << 16) | min(dbg_walk, 65535u));
+      atomicAdd(a.stats + 3, dur);
+      atomicAdd(a.stats + 4 + min(63 - __clzll(dur | 1ull), 35), 1ull);  // histogram of log2(cycles)
+    }
   }
 }
 
@@ -450,7 +514,6 @@ __global__ void __launch_bounds__(128, SPV_ISO_MINB) iso_fast_kernel(const IsoAr
 //                     slices do not cover the taps); every other rank writes zeros, so that an element-wise SUM over
 //                     the ranks assembles the planes bit for bit.
 //   iso_slab_fix      after the SUM: depth = INFINITY on pixels without a crossing, tile flags for the occlusion pass
-constexpr int K_NONE = 0x7fffffff;
 
 template <int FMT, bool LINEAR, bool SKIP>
 __global__ void __launch_bounds__(128) iso_slab_search_kernel(const IsoArgs a, int *__restrict__ k1_plane,
@@ -637,8 +700,9 @@ template <int FMT>
 static cudaError_t launch_iso_dt(const IsoArgs &a, bool linear, bool exact, bool stats, cudaStream_t st) {
   dim3 grid((a.width + 15) / 16, (a.height + 7) / 8), block(128);
   if (!exact) {
-    const int cta_warps = a.cta_warps == 1 || a.cta_warps == 2 ? a.cta_warps : 4;
-    const dim3 fgrid = iso_grid(a.width, a.height, cta_warps), fblock(32 * cta_warps);
+    // a.segments in {1, 2, 4}: the CTA's 4 warps cover 4, 2 or 1 tiles
+    const int tiles = a.segments == 4 ? 1 : (a.segments == 2 ? 2 : 4);
+    const dim3 fgrid = iso_grid(a.width, a.height, tiles), fblock(128);
     if (fgrid.y > 65535u) return cudaErrorInvalidValue;
     if (a.skip) {
       if (linear) iso_fast_kernel<FMT, true, true><<<fgrid, fblock, 0, st>>>(a);

@@ -47,7 +47,8 @@ struct IsoArgs {
   float iso_val, gamma;
   int max_steps;
   int skip;  // empty-space skipping on the min/max grids (texture-unit path)
-  int cta_warps;  // warps per CTA of the texture-unit search: 1, 2 or 4 (default; tuning knob 4)
+  int segments;   // warps that share a ray of the texture-unit search, each taking a segment of its samples: 1, 2 or 4
+                  // (tuning knob 4)
   int centre_out; // CTAs are dealt from the image centre outwards (tuning knob 5, default on)
   int width, height;
   float *out, *alpha, *depth, *normals;

@@ -334,13 +334,11 @@ class SlabMaxProjector(VolumeRenderer):
         self._check(self._lib.spv_iso_slab_check(self._ctx))
         if self.readback_ranks is not None and self.rank not in self.readback_ranks:
             return
-        flat, n = self._fetch(7)
+        flat, n = self._fetch(2)  # depth / normals / occlusion follow when they are first looked at, as on one GPU
         shape = (self.height, self.width)
         self.output = flat[:n].reshape(shape)
         self.output_alpha = flat[n:2 * n].reshape(shape)
-        self.output_depth = flat[2 * n:3 * n].reshape(shape)
-        self.output_occlusion = flat[3 * n:4 * n].reshape(shape)
-        self.output_normals = flat[4 * n:7 * n].reshape(shape + (3,))
+        self._iso_pending = True
 
     def _render_isosurface(self, raw_only=False):
         """composite="peer": spv_render_iso_composite.  composite="nccl": search on every slab -> all-reduce(MIN) of the candidate sample indices -> the owner of each crossing

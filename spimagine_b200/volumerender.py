@@ -563,6 +563,13 @@ class VolumeRenderer(object):
         self._check(self._lib.spv_last_stats(self._ctx, v, 2))
         return int(v[0]), int(v[1])
 
+    def last_warp_cycles(self):
+        """(longest warp, sum over warps) of the last iso-surface search in SM cycles; needs enable_stats()."""
+        v = (C.c_ulonglong * 40)()
+        self._check(self._lib.spv_last_stats(self._ctx, v, 40))
+        self.last_warp_histogram = [int(x) for x in v[4:40]]  # warps by floor(log2(cycles))
+        return int(v[2]), int(v[3])
+
     def texrate_probe(self, iters=2000):
         """Measured samples/s of independent cache-resident filtered fetches (roofline denominator)."""
         v = C.c_double()
