@@ -56,11 +56,13 @@ def parse():
     ap.add_argument("--vol", type=int, default=VOL_N)
     ap.add_argument("--img", type=int, default=IMG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="sweep", choices=["sweep", "slab", "timelapse", "iso"],
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "slab", "timelapse", "iso", "blur"],
                     help="sweep: BASELINE configs[1], frames sharded over the GPUs (default). slab: configs[3], one "
                          "--vol^3 uint16 volume split into z-slabs over the GPUs, sort-last max composite. timelapse: "
                          "configs[4], --frames time points of --tl-shape uint16, time point t on GPU t mod N. iso: "
-                         "configs[2], --vol^3 uint16 iso_surface with ambient occlusion and shading; N > 1: sort-last")
+                         "configs[2], --vol^3 uint16 iso_surface with ambient occlusion and shading; N > 1: sort-last. "
+                         "blur: SURVEY 8f-4, BlurProcessor(sigma=4) on a --vol^3 uint16 volume into the renderer's resident "
+                         "array (one GPU)")
     ap.add_argument("--frames", type=int, default=100, help="timelapse workload: time points in the whole series")
     ap.add_argument("--tl-shape", default="512,1024,1024", help="timelapse workload: (Nz,Ny,Nx) of one time point")
     ap.add_argument("--skip", action="store_true", help="enable empty-space skipping on the min/max brick grid")
@@ -487,6 +489,103 @@ def run_iso(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_blur(args, rank, local_rank, world):
+    """the reference's default image processor, BlurProcessor(sigma=4) = gputools.convolve_sep3 with 19
+    taps per axis (models/imageprocessor.py:47-56), on a --vol^3 uint16 volume whose result goes to
+    renderer.update_data (gui/mainwidget.py:455-465).  value: volumes/s of the three device passes on a resident
+    volume; e2e: host volume -> processor chain -> renderer's resident array (apply_chain), against the
+    reference-shaped host path timed beside it (apply() to a host array, then update_data)."""
+    import torch
+    import scenes
+    from oracle import filters as forc
+    from spimagine_b200 import VolumeRenderer, imageprocessor as ip
+
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"metric": "blur", "unavailable": "the blur workload is single-GPU (replicas only)"}))
+        return
+    torch.cuda.set_device(local_rank)
+    N = args.vol
+    steps, warmup = min(args.steps, 50), max(3, min(args.warmup, 5))
+    vol = scenes.vol_g(N, np.uint16, seed=0)
+    proc = ip.BlurProcessor(sigma=4.)
+    taps = proc._taps()
+    vf = ip.VolumeFilter(local_rank)
+    dvol = torch.from_numpy(vol.view(np.int16)).to("cuda:%d" % local_rank)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms = []
+    for i in range(warmup + steps):
+        vf.load_device(dvol.data_ptr(), vol.shape, np.uint16)  # read in place: 512 MiB result > L2 between steps
+        vf.convolve_sep3(*taps)
+        vf.sync()
+        if i >= warmup:
+            ms.append(vf.last_ms())
+    dev_ms = float(np.mean(ms))
+    got = vf.result()
+    # parity on the spot: a corner block against the CPU restatement (outputs within 9 voxels of the block's cut
+    # faces would see voxels the block does not have)
+    b = min(N, 96)
+    want = forc.convolve_sep3(vol[:b, :b, :b], *taps)
+    k = b if b == N else b - 9
+    parity = bool(np.array_equal(got[:k, :k, :k], want[:k, :k, :k]))
+    rend = VolumeRenderer((args.img, args.img), device=local_rank)
+    rend.set_data(vol)
+    t_chain, t_host = [], []
+    for i in range(3 + 5):
+        t0 = time.perf_counter()
+        ip.apply_chain(rend, vol, [proc])
+        rend.sync()
+        t1 = time.perf_counter()
+        rend.update_data(proc.apply(vol))  # the reference's shape: result to the host, cast, upload again
+        rend.sync()
+        t2 = time.perf_counter()
+        if i >= 3:
+            t_chain.append(t1 - t0)
+            t_host.append(t2 - t1)
+    clk = clocks.stop()
+    t_chain, t_host = float(np.mean(t_chain)), float(np.mean(t_host))
+    # CPU restatement on all host cores, a bounded sample of the same workload
+    cb = min(N, 256)
+    sample = np.ascontiguousarray(vol[:cb, :cb, :cb])
+    forc.convolve_sep3(sample[:32], *taps)
+    t0 = time.perf_counter()
+    forc.convolve_sep3(sample, *taps)
+    t_cpu = (time.perf_counter() - t0) * (N / cb) ** 3
+    peaks, peak_src = measured_peaks()
+    nvox = float(N) ** 3
+    alg = nvox * (2 + 4)  # every voxel read once (uint16) and the float32 result written once
+    moved = nvox * (2 + 4 + 4 + 4 + 4 + 4)  # what the three passes move: x u16 -> f32, y f32 -> f32, z f32 -> f32
+    achieved = alg / (dev_ms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "BlurProcessor(sigma=4) volumes/s, %d^3 uint16 -> float32 (separable 19-tap convolution)" % N,
+        "value": 1e3 / dev_ms, "unit": "volumes/s", "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": dev_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16->f32", "data": "synthetic",
+        "config": {"workload": "Vol-G(%d, uint16, seed 0), BlurProcessor(sigma=4): gputools.convolve_sep3 with 19 taps "
+                               "per axis, zero boundary" % N,
+                   "l2": "the %d MiB float32 result and the work volumes exceed the 126 MB L2" % (nvox * 4 / 2 ** 20)},
+        "gvoxels_per_s": nvox / (dev_ms * 1e-3) / 1e9, "parity_subblock_bitwise": parity,
+        "e2e": {"value": 1. / t_chain, "unit": "volumes/s", "h2d_bytes_per_step": int(nvox * 2), "d2h_bytes_per_step": 0,
+                "note": "apply_chain(renderer, host volume, [BlurProcessor(4)]): upload (pageable host memory), three "
+                        "passes, conversion to the renderer's uint16 texels and the z-pair array build on the device; "
+                        "the call returns when the renderer's volume is replaced",
+                "host_round_trip_value": 1. / t_host,
+                "host_round_trip_note": "the reference's shape with the same kernels: proc.apply(data) -> float32 host "
+                                        "array -> renderer.update_data(result)"},
+        "gpu_launches": steps * 3, "clocks": clk,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg / 3, "bytes_moved_by_three_passes": moved,
+                     "frac_of_moved_bytes": moved / (dev_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "kernel": "spv::conv_x_kernel<u16,19> + 2 x spv::conv_axis_kernel<19> (one third of the time each)"},
+        "cpu_baseline": {"value": 1. / t_cpu, "unit": "volumes/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "one %d^3 corner block of the volume through oracle/filter_oracle.c (OpenMP, all host "
+                                   "cores), time scaled by (%d/%d)^3" % (cb, N, cb)}}))
+    rend.close()
+    vf.close()
+
+
 def run_bricks(args):
     """The single-GPU-brick baseline of BASELINE configs[3]: the same slab kernels on ONE GPU, the volume cut into
     --bricks z-slabs, each rendered by its own launch one after the other (what a single GPU does when the volume
@@ -744,6 +843,8 @@ def main():
     if args.workload == "timelapse":
         run_timelapse(args, rank, local_rank, world)
         return
+    if args.workload == "blur":
+        return run_blur(args, rank, local_rank, world)
     if args.workload == "iso":
         run_iso(args, rank, local_rank, world)
         return

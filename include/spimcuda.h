@@ -84,6 +84,11 @@ SPV_API int spv_set_volume_from(spv_ctx *ctx, const void *host, int src_type, in
 SPV_API int spv_update_volume_from(spv_ctx *ctx, const void *host, int src_type);
 /* as above from a DEVICE pointer (C-order linear); used by frame sources that keep timepoints in HBM */
 SPV_API int spv_set_volume_device(spv_ctx *ctx, const void *dev, int dtype, int nx, int ny, int nz);
+/* update_data (volumerender.py:279-294) from a DEVICE array of the current shape and of element type src_type
+ * (SPV_SRC_*): converted to the volume's texel type on the device with astype semantics where the types differ, then
+ * stored into the resident array.  Enqueue-only on the context's stream; whatever produced `dev` must have finished.
+ * This is how a filtered volume (spv_filter_*) reaches the renderer without crossing PCIe. */
+SPV_API int spv_update_volume_device_from(spv_ctx *ctx, const void *dev, int src_type);
 /* One z-slab of a larger volume for sort-last rendering (new).  The host/dev pointer
  * holds slices [z_lo, z_hi) of a global volume of gnz slices, where z_lo = max(z0-1,0) and
  * z_hi = min(z1+1,gnz) (one halo slice either side); the context then renders only the ray samples
@@ -238,6 +243,30 @@ SPV_API int spv_read_pinned_async(spv_ctx *ctx, int planes);
  * read of that slot or a resize) */
 SPV_API int spv_wait_slot(spv_ctx *ctx, int slot, float **host);
 
+/* ---- volume filters: the image-processor chain between the data model and update_data
+ *      (gui/mainwidget.py:455-465).  spv_filter_convolve_sep3 replaces gputools.convolve_sep3(data, hx, hy, hz) as
+ *      BlurProcessor.apply / BlurXYZProcessor.apply call it (models/imageprocessor.py:47-71): three float32 passes
+ *      (x, then y, then z), each out[i] = sum_ht h[ht] * in[i + Nh/2 - ht] over the taps that stay inside the volume,
+ *      accumulated in ascending tap order with one fused multiply-add per tap.  gputools is not vendored in the
+ *      reference tree: the algorithm is restated from its published kernel (parity unpinned).
+ *      A filter object owns a stream and two float32 work volumes on `device`; it is not thread-safe. ---- */
+typedef struct spv_filter spv_filter;
+SPV_API int spv_filter_create(int device, spv_filter **out);
+SPV_API int spv_filter_destroy(spv_filter *f);
+/* the volume the next convolution reads: C-order (z,y,x), element type SPV_SRC_*.  Host sources are copied (the
+ * pointer is borrowed for the call only); device sources of type float32 / uint16 / uint8 are read in place by the
+ * next convolution and must stay valid until it has run.  Other types become float32 first (gputools: astype). */
+SPV_API int spv_filter_load(spv_filter *f, const void *src, int on_device, int src_type, int nx, int ny, int nz);
+/* convolves the loaded volume -- or, when called again, the previous result (a processor chain) */
+SPV_API int spv_filter_convolve_sep3(spv_filter *f, const float *hx, int nhx, const float *hy, int nhy, const float *hz,
+                                     int nhz);
+SPV_API int spv_filter_sync(spv_filter *f);
+/* the float32 result: in device memory (valid until the next load / convolution of this filter) or copied to the host */
+SPV_API int spv_filter_result_device(spv_filter *f, float **dev);
+SPV_API int spv_filter_read(spv_filter *f, float *host_dst, size_t n);
+SPV_API int spv_filter_last_ms(spv_filter *f, float *ms);  /* device time of the last convolution (three passes) */
+SPV_API const char *spv_filter_last_error(spv_filter *f);  /* f may be NULL: last create error */
+
 /* ---- diagnostics ---- */
 SPV_API int spv_last_timing_ms(spv_ctx *ctx, float *ms);            /* device time of the last render call */
 SPV_API int spv_last_stats(spv_ctx *ctx, unsigned long long *v, int n); /* [hit rays, texture samples issued] of the
@@ -248,7 +277,9 @@ SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
  * spv_render_mip_to_host, knob 3 = spv_render_mip_to_host stores straight into pinned host memory, knob 4 = warps that share a
  * ray of the iso-surface search, each taking a segment of its samples (1, 2 or 4), knob 5 = its CTAs are dealt from the
  * image centre outwards (1, default) or row by row (0), knob 6 = resident CTAs per SM of the occlusion queue kernel,
- * knob 7 = copy streams the band copies of spv_render_mip_to_host alternate between (1 or 2) */
+ * knob 7 = copy streams the band copies of spv_render_mip_to_host alternate between (1 or 2), knob 8 = order in which
+ * the one-launch path of spv_render_mip_to_host deals its tile rows: 0 = from the top and bottom edges inwards, 1 = the rows
+ * the projected box cannot touch first, then the box's rows top to bottom */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 SPV_API const char *spv_last_error(spv_ctx *ctx);                   /* ctx may be NULL: last create error */
 SPV_API int spv_version(void);

@@ -36,13 +36,14 @@ def run(label, n=360):
     img = rend.output.copy()
     if ref is None: ref = img
     print("%-90s %.0f frames/s (%.1f us/frame) identical=%s" % (label, n / dt, 1e6 * dt / n, np.array_equal(img, ref)), flush=True)
-for cs in (2,):
-    lib.spv_set_tuning(ctx, 7, cs)
-    for b in (1, 12):
-        lib.spv_set_tuning(ctx, 2, b); run("copy streams=%d bands=%d" % (cs, b))
-lib.spv_set_tuning(ctx, 7, 1)
-lib.spv_set_tuning(ctx, 3, 1); run("direct host stores")
-lib.spv_set_tuning(ctx, 3, 0); lib.spv_set_tuning(ctx, 2, 12)
+lib.spv_set_tuning(ctx, 7, 2)
+for mode in (0, 1):
+    lib.spv_set_tuning(ctx, 8, mode)
+    for b in (12, 16, 24, 32):
+        lib.spv_set_tuning(ctx, 2, b); run("row order=%d copy streams=2 bands=%d" % (mode, b))
+lib.spv_set_tuning(ctx, 7, 1); lib.spv_set_tuning(ctx, 8, 1); lib.spv_set_tuning(ctx, 2, 16)
+run("row order=1 copy streams=1 bands=16")
+lib.spv_set_tuning(ctx, 7, 2); lib.spv_set_tuning(ctx, 8, 0); lib.spv_set_tuning(ctx, 2, 12)
 # host-side cost alone
 t0 = time.perf_counter()
 for i in range(360): rend.set_modelView(cams[i][0])
@@ -51,7 +52,9 @@ t0 = time.perf_counter()
 for i in range(360): rend.render_device_only()
 rend.sync()
 print("device-only launches: %.1f us/frame" % ((time.perf_counter() - t0) / 360 * 1e6))
-t0 = time.perf_counter()
-n = 0
-for r in rend.render_sequence(cams[i][0] for i in range(360)): n += 1
-print("render_sequence: %.1f us/frame" % ((time.perf_counter() - t0) / 360 * 1e6))
+for mode in (0, 1):
+    lib.spv_set_tuning(ctx, 8, mode)
+    t0 = time.perf_counter()
+    n = 0
+    for r in rend.render_sequence(cams[i][0] for i in range(360)): n += 1
+    print("render_sequence (row order %d): %.1f us/frame" % (mode, (time.perf_counter() - t0) / 360 * 1e6))

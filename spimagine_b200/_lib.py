@@ -101,6 +101,16 @@ SIGNATURES = {
     "spv_sample_points": (C.c_int, [_CTX, _FP, C.c_int, _FP]),
     "spv_texrate_probe": (C.c_int, [_CTX, C.c_int, C.POINTER(C.c_double)]),
     "spv_launch_count": (C.c_int, [_CTX, C.POINTER(C.c_ulonglong)]),
+    "spv_update_volume_device_from": (C.c_int, [_CTX, C.c_void_p, C.c_int]),
+    "spv_filter_create": (C.c_int, [C.c_int, C.POINTER(_CTX)]),
+    "spv_filter_destroy": (C.c_int, [_CTX]),
+    "spv_filter_load": (C.c_int, [_CTX, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "spv_filter_convolve_sep3": (C.c_int, [_CTX, _FP, C.c_int, _FP, C.c_int, _FP, C.c_int]),
+    "spv_filter_sync": (C.c_int, [_CTX]),
+    "spv_filter_result_device": (C.c_int, [_CTX, C.POINTER(_FP)]),
+    "spv_filter_read": (C.c_int, [_CTX, _FP, C.c_size_t]),
+    "spv_filter_last_ms": (C.c_int, [_CTX, _FP]),
+    "spv_filter_last_error": (C.c_char_p, [_CTX]),
 }
 
 _lib = None

@@ -29,6 +29,8 @@ struct spv_ctx {
   int want_layout = LAYOUT_ZPAIR; // for integer volumes (spv_set_layout)
   void *d_stage = nullptr;       // ingest staging on the device: [paired texels | linear chunk x 2]
   size_t stage_bytes = 0;
+  void *d_conv = nullptr;        // texels converted from a device array of another element type (spv_update_volume_device_from)
+  size_t conv_bytes = 0;
   size_t stage_sig[3] = {0, 0, 0};  // partition of d_stage used by the last upload
   char *h_ring = nullptr;        // page-locked ring (2 chunks) for pageable sources
   size_t ring_bytes = 0;
@@ -46,6 +48,7 @@ struct spv_ctx {
                   // band counters (one launch per frame), else 2 (one launch per band) -- profiles/r01_exp_e2e.txt
   int iso_segments = 1;   // tuning knob 4 (measured on configs[2]: 1 -> 97 us, 2 -> 110 us, 4 -> 178 us)
   int iso_centre_out = 1; // tuning knob 5
+  int row_mode = 0;     // spv_render_mip_to_host, one-launch path: order of the tile rows (tuning knob 8, MipArgs::row_mode)
   int direct_host = 0;  // spv_render_mip_to_host: the kernel stores straight into the pinned staging (tuning knob 3)
   unsigned *d_tile_counter = nullptr;
   unsigned *d_band_done = nullptr;   // [MAX_BANDS] CTAs finished per band, counting up across frames (never reset)
@@ -184,8 +187,11 @@ static void free_volume(spv_ctx *c) {
   if (c->top) cudaFree(c->top);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->d_stage) cudaFree(c->d_stage);
+  if (c->d_conv) cudaFree(c->d_conv);
   if (c->h_ring) cudaFreeHost(c->h_ring);
   c->d_stage = nullptr;
+  c->d_conv = nullptr;
+  c->conv_bytes = 0;
   c->stage_bytes = 0;
   c->h_ring = nullptr;
   c->ring_bytes = 0;
@@ -646,6 +652,26 @@ SPV_API int spv_update_volume_from(spv_ctx *ctx, const void *host, int src_type)
   return upload(ctx, host, false, false, native_src(src_type, ctx->dtype) ? -1 : src_type);
 }
 
+SPV_API int spv_update_volume_device_from(spv_ctx *ctx, const void *dev, int src_type) {
+  BIND();
+  if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_update_volume_device_from: no volume set");
+  if (!dev) return fail(ctx, SPV_EINVAL, "spv_update_volume_device_from: null data");
+  if (src_elem_size(src_type) == 0) return fail(ctx, SPV_EINVAL, "spv_update_volume_device_from: unknown source element type");
+  if (native_src(src_type, ctx->dtype)) return upload(ctx, dev, true);
+  const size_t n = (size_t)ctx->nx * ctx->ny * ctx->local_nz, need = n * elem_size(ctx->dtype);
+  if (need > ctx->conv_bytes) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_conv) cudaFree(ctx->d_conv);
+    ctx->d_conv = nullptr;
+    ctx->conv_bytes = 0;
+    CU(cudaMalloc(&ctx->d_conv, need));
+    ctx->conv_bytes = need;
+  }
+  CU(launch_convert(dev, ctx->d_conv, src_type, ctx->dtype, n, ctx->stream));
+  ctx->launches += 1;
+  return upload(ctx, ctx->d_conv, true);
+}
+
 SPV_API int spv_update_volume_async(spv_ctx *ctx, const void *pinned_host) {
   BIND();
   if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_update_volume_async: no volume set");
@@ -723,6 +749,7 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   else if (knob == 4) ctx->iso_segments = value == 4 ? 4 : (value == 2 ? 2 : 1);
   else if (knob == 5) ctx->iso_centre_out = value != 0;
   else if (knob == 7) ctx->copy_streams = value > 1 ? 2 : 1;
+  else if (knob == 8) ctx->row_mode = value == 1 ? 1 : 0;
   else if (knob == 6) occ_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : value);  // process-wide
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
   return 0;
@@ -774,6 +801,62 @@ static wait_value_t wait_value_fn() {
   return fn;
 }
 
+// 4x4 inverse (Gauss-Jordan with partial pivoting, double); false if singular
+static bool invert4(const float *m, double *inv) {
+  double a[4][8];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      a[r][c] = m[4 * r + c];
+      a[r][4 + c] = r == c ? 1. : 0.;
+    }
+  for (int c = 0; c < 4; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 4; ++r)
+      if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+    if (fabs(a[piv][c]) < 1e-300) return false;
+    if (piv != c)
+      for (int k = 0; k < 8; ++k) { const double t = a[c][k]; a[c][k] = a[piv][k]; a[piv][k] = t; }
+    const double d = 1. / a[c][c];
+    for (int k = 0; k < 8; ++k) a[c][k] *= d;
+    for (int r = 0; r < 4; ++r)
+      if (r != c) {
+        const double f = a[r][c];
+        if (f != 0.)
+          for (int k = 0; k < 8; ++k) a[r][k] -= f * a[c][k];
+      }
+  }
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) inv[4 * r + c] = a[r][4 + c];
+  return true;
+}
+
+// Tile rows [ta, tb) (8 pixels each) of an image of H rows that the box can project to: the hull of its eight corners
+// through projection . modelView, one pixel of slack.  The whole image when a corner lies behind the eye (or anything
+// is degenerate).  Scheduling only: pixels are correct for any answer.
+static void hit_tile_rows(const Camera &cam, const float *box, int H, unsigned tiles_y, unsigned &ta, unsigned &tb) {
+  ta = 0;
+  tb = tiles_y;
+  double P[16], M[16];
+  if (!invert4(cam.invP, P) || !invert4(cam.invM, M)) return;
+  double ymin = 1e300, ymax = -1e300;
+  for (int i = 0; i < 8; ++i) {
+    const double c[4] = {box[i & 1], box[2 + ((i >> 1) & 1)], box[4 + ((i >> 2) & 1)], 1.};
+    double e[4], q[4];
+    for (int r = 0; r < 4; ++r) e[r] = M[4 * r] * c[0] + M[4 * r + 1] * c[1] + M[4 * r + 2] * c[2] + M[4 * r + 3] * c[3];
+    for (int r = 0; r < 4; ++r) q[r] = P[4 * r] * e[0] + P[4 * r + 1] * e[1] + P[4 * r + 2] * e[2] + P[4 * r + 3] * e[3];
+    if (!(q[3] > 1e-9)) return;
+    const double y = (q[1] / q[3] + 1.) * 0.5 * H;  // v = (y / Ny) * 2 - 1
+    if (!(y == y)) return;
+    ymin = y < ymin ? y : ymin;
+    ymax = y > ymax ? y : ymax;
+  }
+  const double lo = floor((ymin - 1.) / 8.), hi = ceil((ymax + 1.) / 8.) + 1.;
+  if (lo >= (double)tiles_y || hi <= 0.) { ta = tb = 0; return; }  // the box is off screen: nothing to order
+  ta = lo > 0. ? (unsigned)lo : 0u;
+  tb = hi < (double)tiles_y ? (unsigned)hi : tiles_y;
+  if (tb < ta) tb = ta;
+}
+
 // One max projection.  bands > 1 (fast kernel only): the frame is rendered as `bands` horizontal bands launched back to
 // back, and the rows of a finished band travel to the pinned staging on the copy stream while the next band renders.
 static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, bool to_host, const PushArgs *push = nullptr) {
@@ -803,6 +886,8 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
   a.tile_counter = ctx->persistent ? ctx->d_tile_counter : nullptr;
   a.band_done = nullptr;
   a.band_rows = 0;
+  a.row_mode = 0;
+  a.hit_tile_a = a.hit_tile_b = 0;
   a.n_extra = 0;
   if (ctx->slab && ctx->n_extra > 0) {
     if (ctx->skipping > 0) return fail(ctx, SPV_EINVAL, "spv_render_mip: extra slabs need empty-space skipping off");
@@ -848,14 +933,30 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     a.y_end = H;
     a.band_done = ctx->d_band_done;
     a.band_rows = rows;
+    const int nb = (H + rows - 1) / rows;
+    int order[64];
+    if (ctx->row_mode == 1) {
+      // rows the box cannot project to are dealt first, then its rows top to bottom: bands without any of those rows
+      // complete at once, the others in ascending order
+      a.row_mode = 1;
+      hit_tile_rows(a.cam, a.box, H, (unsigned)((H + 7) / 8), a.hit_tile_a, a.hit_tile_b);
+      const int ya = (int)a.hit_tile_a * 8, yb = (int)a.hit_tile_b * 8;
+      int k = 0;
+      for (int b = 0; b < nb; ++b)
+        if (b * rows + rows <= ya || b * rows >= yb) order[k++] = b;
+      for (int b = 0; b < nb; ++b)
+        if (!(b * rows + rows <= ya || b * rows >= yb)) order[k++] = b;
+    } else {
+      // the kernel deals tile rows from the top and bottom edges inwards: the bands complete in the order
+      // 0, nb-1, 1, nb-2, ...
+      for (int i = 0; i < nb; ++i) order[i] = (i & 1) ? nb - 1 - (i >> 1) : (i >> 1);
+    }
     CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, false, false, ctx->stats_on != 0, ctx->stream));
     ctx->launches += 1;
     const unsigned ctas_x = (unsigned)(ctx->width + 15) / 16;
-    const int nb = (H + rows - 1) / rows;
     for (int i = 0; i < nb; ++i) {
-      // the kernel deals tile rows from the top and bottom edges inwards: enqueue the copies in the order the bands
-      // complete (0, nb-1, 1, nb-2, ...), alternating between the copy streams
-      const int b = (i & 1) ? nb - 1 - (i >> 1) : (i >> 1);
+      // enqueue the copies in the order the bands complete, alternating between the copy streams
+      const int b = order[i];
       const int y0 = b * rows, y1 = y0 + rows < H ? y0 + rows : H;
       ctx->band_expect[b] += ctas_x * (unsigned)((y1 - y0 + 7) / 8);
       const size_t off = (size_t)y0 * ctx->width, cnt = (size_t)(y1 - y0) * ctx->width, n = ctx->n();

@@ -1,0 +1,433 @@
+// spv_filter.cu -- separable 3-D convolution of a volume on the device: what
+// BlurProcessor / BlurXYZProcessor.apply get from gputools.convolve_sep3 (spimagine/models/imageprocessor.py:47-71),
+// whose result the GUI hands to renderer.update_data (spimagine/gui/mainwidget.py:455-465).
+//
+// gputools is a third-party dependency that is not vendored in the reference tree (setup.py:31, unpinned).  Its
+// published algorithm (gputools/convolve/kernels/convolve_sep.cl: conv_sep3_x / _y / _z, run in that order through
+// float32 buffers) is restated here:
+//
+//     out[i] = sum_{ht = h_start}^{h_end - 1} h[ht] * in[i + Nh/2 - ht]        (per axis; integer Nh/2)
+//     h_start = i + Nh/2 >= N ? i + Nh/2 + 1 - N : 0,   h_end = i - Nh/2 < 0 ? i + Nh/2 + 1 : Nh
+//
+// i.e. a true convolution centred on tap Nh/2 whose taps outside the volume are dropped, accumulated in float32 in
+// ascending tap order.  `res += h * in` is evaluated as ONE fused multiply-add per tap (what OpenCL's default
+// contraction gives on a GPU); the CPU restatement the tests compare against follows the same convention, bit for bit.
+//
+// Kernels.  A thread keeps R consecutive outputs of one line in registers and streams the R + Nh - 1 inputs they need
+// from the highest position down, so that every output meets its taps in ascending order; after full unrolling every
+// tap index is a compile-time constant and the weight is a constant-bank operand of the FMA (the taps travel as a
+// kernel argument).  Dropped taps become fma(h, 0, acc) = acc.  Kernels are instantiated for the tap counts
+// NHMAX in FILT_SIZES; other counts run in the next larger instantiation with zero weights appended, and the steps
+// beyond the real window feed zeros (fma(0, 0, acc) = acc), so a voxel never meets a tap the reference would not
+// give it (NaN / Inf voxels spread exactly as far as in the reference).
+//   conv_axis_kernel  y and z passes: lanes along x (coalesced), the line runs along the strided axis
+//   conv_x_kernel     x pass: 32 lines x (XW + Nh - 1) inputs staged in shared memory (odd pitch: a lane per line
+//                     reads conflict-free), results staged back for coalesced stores; reads the source element type
+#include <string>
+
+#include "spimcuda.h"
+#include "spv_kernels.h"
+
+namespace spv {
+
+// One pass along a strided axis.  in/out: float volumes; the line of (x, o) starts at base + o * so + x, positions
+// along the axis are `sa` elements apart.  grid = (ceil(nx / 128), ceil(na / R), no).  The instantiation serves tap
+// counts NHMIN <= nh <= NHMAX: steps beyond the real window (jj >= R + nh - 1, possible only for jj >= R + NHMIN - 1)
+// load nothing, so a voxel never meets a padded tap.
+template <int NHMAX, int NHMIN, int R>
+__global__ void __launch_bounds__(128) conv_axis_kernel(const float *__restrict__ in, float *__restrict__ out, int nx, int na,
+                                                        size_t sa, size_t so, int nh, const FilterTaps t) {
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  if (x >= nx) return;
+  const int p0 = blockIdx.y * R;
+  const float *src = in + (size_t)blockIdx.z * so + x;
+  float *dst = out + (size_t)blockIdx.z * so + x;
+  const int half = nh / 2;
+  const int qtop = p0 + R - 1 + half;  // input position met first (tap 0 of the last output)
+  const int nsteps = R + nh - 1;       // positions qtop, qtop - 1, ... the R outputs read
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  if (qtop < na && qtop - (nsteps - 1) >= 0) {  // the whole window lies inside the volume (uniform per CTA)
+    const float *ptr = src + (size_t)qtop * sa;
+#pragma unroll
+    for (int jj = 0; jj < R + NHMAX - 1; ++jj) {
+      float v;
+      if (jj < R + NHMIN - 1) v = __ldg(ptr);
+      else v = jj < nsteps ? __ldg(ptr) : 0.f;
+      ptr -= sa;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int ht = jj - (R - 1 - r);
+        if (ht >= 0 && ht < NHMAX) acc[r] = fmaf(t.w[ht], v, acc[r]);
+      }
+    }
+  } else {  // window cut by a volume face: positions outside contribute fma(h, 0, acc) = acc
+#pragma unroll
+    for (int jj = 0; jj < R + NHMAX - 1; ++jj) {
+      const int q = qtop - jj;
+      float v = 0.f;
+      if (jj < nsteps && q >= 0 && q < na) v = __ldg(src + (size_t)q * sa);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int ht = jj - (R - 1 - r);
+        if (ht >= 0 && ht < NHMAX) acc[r] = fmaf(t.w[ht], v, acc[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (p0 + r < na) dst[(size_t)(p0 + r) * sa] = acc[r];
+}
+
+// The x pass.  Lines are the nrows = ny * nz rows of the volume, nx elements each; a CTA of NW warps takes 32
+// consecutive rows x XW = NW * R outputs.  grid = (ceil(nrows / 32), ceil(nx / XW)).
+template <typename TIN, int NHMAX, int NHMIN, int R, int NW>
+__global__ void __launch_bounds__(32 * NW) conv_x_kernel(const TIN *__restrict__ in, float *__restrict__ out, int nx,
+                                                         long long nrows, int nh, const FilterTaps t) {
+  constexpr int XW = NW * R, TW = XW + NHMAX - 1, PITCH = TW | 1, OPITCH = XW | 1;
+  __shared__ float s_in[32][PITCH];
+  __shared__ float s_out[32][OPITCH];
+  const int x0 = blockIdx.y * XW;
+  const long long row0 = (long long)blockIdx.x * 32;
+  const int half = nh / 2;
+  const int qbase = x0 + half - (NHMAX - 1);  // input position of tile column 0
+  for (int i = threadIdx.x; i < 32 * TW; i += 32 * NW) {
+    const int rr = i / TW, c = i - rr * TW;
+    const int q = qbase + c;
+    const long long row = row0 + rr;
+    float v = 0.f;
+    if (row < nrows && q >= 0 && q < nx) v = (float)in[(size_t)row * nx + q];
+    s_in[rr][c] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nsteps = R + nh - 1;
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  const float *line = s_in[lane] + warp * R + R - 1 + NHMAX - 1;  // column of the position met first
+#pragma unroll
+  for (int jj = 0; jj < R + NHMAX - 1; ++jj) {
+    float v = line[-jj];
+    if (jj >= R + NHMIN - 1 && jj >= nsteps) v = 0.f;  // beyond the real window: only padded taps would meet it
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int ht = jj - (R - 1 - r);
+      if (ht >= 0 && ht < NHMAX) acc[r] = fmaf(t.w[ht], v, acc[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) s_out[lane][warp * R + r] = acc[r];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * XW; i += 32 * NW) {
+    const int rr = i / XW, c = i - rr * XW;
+    const long long row = row0 + rr;
+    if (row < nrows && x0 + c < nx) out[(size_t)row * nx + x0 + c] = s_out[rr][c];
+  }
+}
+
+// any tap count: one output per thread, taps read from device memory with a runtime index (slow path; lanes run
+// along the index with stride sx, the line along the axis with stride sa)
+template <typename TIN>
+__global__ void __launch_bounds__(256) conv_generic_kernel(const TIN *__restrict__ in, float *__restrict__ out, int nl, int na,
+                                                           size_t sx, size_t sa, size_t so, int nh,
+                                                           const float *__restrict__ taps) {
+  const int l = blockIdx.x * 256 + threadIdx.x;
+  if (l >= nl) return;
+  const int p = blockIdx.y;
+  const size_t base = (size_t)blockIdx.z * so + (size_t)l * sx;
+  const int half = nh / 2;
+  const int h_start = (p + half >= na) ? p + half + 1 - na : 0;
+  const int h_end = (p - half < 0) ? p + half + 1 : nh;
+  float res = 0.f;
+  for (int ht = h_start; ht < h_end; ++ht) res = fmaf(taps[ht], (float)in[base + (size_t)(p + half - ht) * sa], res);
+  out[base + (size_t)p * sa] = res;
+}
+
+static const int FILT_SIZES[] = {3, 7, 11, 15, 19, 23, 27, 31, 35, 39, 47, 63};
+
+static int pick_size(int nh) {
+  for (int s : FILT_SIZES)
+    if (nh <= s) return s;
+  return 0;
+}
+
+template <int NHMAX, int NHMIN>
+static void launch_axis_n(const float *in, float *out, int nx, int na, int no, size_t sa, size_t so, int nh,
+                          const FilterTaps &t, cudaStream_t st) {
+  constexpr int R = 16;
+  dim3 grid((nx + 127) / 128, (na + R - 1) / R, no);
+  conv_axis_kernel<NHMAX, NHMIN, R><<<grid, 128, 0, st>>>(in, out, nx, na, sa, so, nh, t);
+}
+
+template <typename TIN, int NHMAX, int NHMIN>
+static void launch_x_n(const TIN *in, float *out, int nx, long long nrows, int nh, const FilterTaps &t, cudaStream_t st) {
+  constexpr int R = 16, NW = 8;
+  dim3 grid((unsigned)((nrows + 31) / 32), (nx + NW * R - 1) / (NW * R));
+  conv_x_kernel<TIN, NHMAX, NHMIN, R, NW><<<grid, 32 * NW, 0, st>>>(in, out, nx, nrows, nh, t);
+}
+
+// CALL(NHMAX, NHMIN): the instantiation for tap counts NHMIN..NHMAX
+#define SPV_FILT_DISPATCH(CALL)                 \
+  switch (size) {                               \
+    case 3: CALL(3, 1); break;                  \
+    case 7: CALL(7, 4); break;                  \
+    case 11: CALL(11, 8); break;                \
+    case 15: CALL(15, 12); break;               \
+    case 19: CALL(19, 16); break;               \
+    case 23: CALL(23, 20); break;               \
+    case 27: CALL(27, 24); break;               \
+    case 31: CALL(31, 28); break;               \
+    case 35: CALL(35, 32); break;               \
+    case 39: CALL(39, 36); break;               \
+    case 47: CALL(47, 40); break;               \
+    default: CALL(63, 48); break;               \
+  }
+
+static FilterTaps padded(const float *h, int nh) {
+  FilterTaps t;
+  for (int i = 0; i < FILTER_MAX_TAPS; ++i) t.w[i] = i < nh ? h[i] : 0.f;
+  return t;
+}
+
+// y (axis 1) or z (axis 2) pass over a float volume
+cudaError_t launch_filter_axis(const float *in, float *out, int nx, int ny, int nz, int axis, const float *h, int nh,
+                               const float *d_taps, cudaStream_t st) {
+  const int na = axis == 1 ? ny : nz, no = axis == 1 ? nz : ny;
+  const size_t sa = axis == 1 ? (size_t)nx : (size_t)nx * ny, so = axis == 1 ? (size_t)nx * ny : (size_t)nx;
+  const int size = pick_size(nh);
+  if (size == 0) {
+    // grid y / z limits (65535) cannot be hit by volumes that fit a texture (<= 16384 per axis)
+    dim3 grid((nx + 255) / 256, na, no);
+    conv_generic_kernel<float><<<grid, 256, 0, st>>>(in, out, nx, na, 1, sa, so, nh, d_taps);
+    return cudaGetLastError();
+  }
+  const FilterTaps t = padded(h, nh);
+#define SPV_AXIS(N, M) launch_axis_n<N, M>(in, out, nx, na, no, sa, so, nh, t, st)
+  SPV_FILT_DISPATCH(SPV_AXIS)
+#undef SPV_AXIS
+  return cudaGetLastError();
+}
+
+template <typename TIN>
+static cudaError_t filter_x_typed(const TIN *in, float *out, int nx, int ny, int nz, const float *h, int nh,
+                                  const float *d_taps, cudaStream_t st) {
+  const int size = pick_size(nh);
+  if (size == 0) {  // lanes over y (stride nx), the line along x (stride 1), one grid layer per slice
+    dim3 grid((ny + 255) / 256, nx, nz);
+    conv_generic_kernel<TIN><<<grid, 256, 0, st>>>(in, out, ny, nx, (size_t)nx, 1, (size_t)nx * ny, nh, d_taps);
+    return cudaGetLastError();
+  }
+  const FilterTaps t = padded(h, nh);
+  const long long nrows = (long long)ny * nz;
+#define SPV_X(N, M) launch_x_n<TIN, N, M>(in, out, nx, nrows, nh, t, st)
+  SPV_FILT_DISPATCH(SPV_X)
+#undef SPV_X
+  return cudaGetLastError();
+}
+
+// x pass from a volume of element type dtype (SPV_F32 / SPV_U16 / SPV_U8) into a float volume
+cudaError_t launch_filter_x(const void *in, int dtype, float *out, int nx, int ny, int nz, const float *h, int nh,
+                            const float *d_taps, cudaStream_t st) {
+  switch (dtype) {
+    case 0: return filter_x_typed((const float *)in, out, nx, ny, nz, h, nh, d_taps, st);
+    case 1: return filter_x_typed((const unsigned short *)in, out, nx, ny, nz, h, nh, d_taps, st);
+    case 2: return filter_x_typed((const unsigned char *)in, out, nx, ny, nz, h, nh, d_taps, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace spv
+
+// ---- C ABI -------------------------------------------------------------------------------------------------------
+using namespace spv;
+
+struct spv_filter {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  void *d_src = nullptr;   // the loaded volume in its own element type (host sources and converted ones)
+  size_t src_cap = 0;
+  float *buf[2] = {nullptr, nullptr};
+  size_t buf_cap = 0;      // floats per buffer
+  float *d_taps = nullptr; // 3 x FILT_LONG_TAPS, for tap counts beyond the unrolled instantiations
+  int nx = 0, ny = 0, nz = 0;
+  const void *cur = nullptr;  // what the next convolution reads: the loaded volume or the last result
+  int cur_dtype = 0;          // SPV_F32 / SPV_U16 / SPV_U8
+  bool have_result = false, timed = false;
+  std::string err;
+};
+
+static const int FILT_LONG_TAPS = 1024;
+static thread_local std::string g_filter_create_err;
+
+static int ffail(spv_filter *f, int code, const char *what) {
+  (f ? f->err : g_filter_create_err) = what;
+  return code;
+}
+static int fcufail(spv_filter *f, cudaError_t e, const char *where) {
+  (f ? f->err : g_filter_create_err) = std::string(where) + ": " + cudaGetErrorString(e);
+  cudaGetLastError();
+  return (int)e;
+}
+#define FCU(call)                                          \
+  do {                                                     \
+    cudaError_t e_ = (call);                               \
+    if (e_ != cudaSuccess) return fcufail(f, e_, #call);   \
+  } while (0)
+#define FBIND()                                                       \
+  if (!f) return SPV_EINVAL;                                          \
+  do {                                                                \
+    cudaError_t e_ = cudaSetDevice(f->device);                        \
+    if (e_ != cudaSuccess) return fcufail(f, e_, "cudaSetDevice");    \
+  } while (0)
+
+SPV_API const char *spv_filter_last_error(spv_filter *f) { return f ? f->err.c_str() : g_filter_create_err.c_str(); }
+
+SPV_API int spv_filter_create(int device, spv_filter **out) {
+  if (!out) return SPV_EINVAL;
+  *out = nullptr;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fcufail(nullptr, e, "spv_filter_create: cudaSetDevice (libspimcuda needs a CUDA device; there is no CPU path)");
+  spv_filter *f = new spv_filter;
+  f->device = device;
+  if ((e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&f->ev0)) != cudaSuccess || (e = cudaEventCreate(&f->ev1)) != cudaSuccess ||
+      (e = cudaMalloc(&f->d_taps, 3 * FILT_LONG_TAPS * sizeof(float))) != cudaSuccess) {
+    int rc = fcufail(nullptr, e, "spv_filter_create");
+    spv_filter_destroy(f);
+    return rc;
+  }
+  *out = f;
+  return 0;
+}
+
+SPV_API int spv_filter_destroy(spv_filter *f) {
+  if (!f) return 0;
+  cudaSetDevice(f->device);
+  if (f->stream) cudaStreamSynchronize(f->stream);
+  if (f->d_src) cudaFree(f->d_src);
+  for (int i = 0; i < 2; ++i)
+    if (f->buf[i]) cudaFree(f->buf[i]);
+  if (f->d_taps) cudaFree(f->d_taps);
+  if (f->ev0) cudaEventDestroy(f->ev0);
+  if (f->ev1) cudaEventDestroy(f->ev1);
+  if (f->stream) cudaStreamDestroy(f->stream);
+  cudaGetLastError();
+  delete f;
+  return 0;
+}
+
+static int filter_reserve(spv_filter *f, size_t n, size_t src_bytes) {
+  if (n > f->buf_cap) {
+    FCU(cudaStreamSynchronize(f->stream));
+    for (int i = 0; i < 2; ++i) {
+      if (f->buf[i]) cudaFree(f->buf[i]);
+      f->buf[i] = nullptr;
+    }
+    f->buf_cap = 0;
+    FCU(cudaMalloc(&f->buf[0], n * sizeof(float)));
+    FCU(cudaMalloc(&f->buf[1], n * sizeof(float)));
+    f->buf_cap = n;
+  }
+  if (src_bytes > f->src_cap) {
+    FCU(cudaStreamSynchronize(f->stream));
+    if (f->d_src) cudaFree(f->d_src);
+    f->d_src = nullptr;
+    f->src_cap = 0;
+    FCU(cudaMalloc(&f->d_src, src_bytes));
+    f->src_cap = src_bytes;
+  }
+  return 0;
+}
+
+SPV_API int spv_filter_load(spv_filter *f, const void *src, int on_device, int src_type, int nx, int ny, int nz) {
+  FBIND();
+  if (!src) return ffail(f, SPV_EINVAL, "spv_filter_load: null data");
+  if (nx <= 0 || ny <= 0 || nz <= 0 || ny > 65535 || nz > 65535)
+    return ffail(f, SPV_EINVAL, "spv_filter_load: bad extent (1 <= nx, 1 <= ny, nz <= 65535)");
+  const size_t es = src_elem_size(src_type);
+  if (es == 0) return ffail(f, SPV_EINVAL, "spv_filter_load: unknown source element type");
+  const size_t n = (size_t)nx * ny * nz;
+  const int native = src_type == SPV_SRC_F32 ? SPV_F32 : (src_type == SPV_SRC_U16 ? SPV_U16 : (src_type == SPV_SRC_U8 ? SPV_U8 : -1));
+  const bool borrow = on_device && native >= 0;  // read in place by the next convolution
+  int rc = filter_reserve(f, n, borrow ? 0 : n * es);
+  if (rc) return rc;
+  f->nx = nx; f->ny = ny; f->nz = nz;
+  f->have_result = false;
+  if (borrow) {
+    f->cur = src;
+    f->cur_dtype = native;
+    return 0;
+  }
+  FCU(cudaMemcpyAsync(f->d_src, src, n * es, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, f->stream));
+  if (native >= 0) {
+    f->cur = f->d_src;
+    f->cur_dtype = native;
+  } else {  // other element types become float32 first, as gputools' data.astype(np.float32) does on the host
+    FCU(launch_convert(f->d_src, f->buf[1], src_type, SPV_F32, n, f->stream));
+    f->cur = f->buf[1];
+    f->cur_dtype = SPV_F32;
+  }
+  if (!on_device) FCU(cudaStreamSynchronize(f->stream));  // the host pointer is only borrowed for this call
+  return 0;
+}
+
+SPV_API int spv_filter_convolve_sep3(spv_filter *f, const float *hx, int nhx, const float *hy, int nhy, const float *hz,
+                                     int nhz) {
+  FBIND();
+  if (!f->cur) return ffail(f, SPV_ENODATA, "spv_filter_convolve_sep3: no volume loaded");
+  if (!hx || !hy || !hz || nhx < 1 || nhy < 1 || nhz < 1 || nhx > FILT_LONG_TAPS || nhy > FILT_LONG_TAPS || nhz > FILT_LONG_TAPS)
+    return ffail(f, SPV_EINVAL, "spv_filter_convolve_sep3: need 1 <= taps <= 1024 per axis");
+  if (nhx > FILTER_MAX_TAPS || nhy > FILTER_MAX_TAPS || nhz > FILTER_MAX_TAPS) {
+    FCU(cudaMemcpyAsync(f->d_taps, hx, nhx * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+    FCU(cudaMemcpyAsync(f->d_taps + FILT_LONG_TAPS, hy, nhy * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+    FCU(cudaMemcpyAsync(f->d_taps + 2 * FILT_LONG_TAPS, hz, nhz * sizeof(float), cudaMemcpyHostToDevice, f->stream));
+    FCU(cudaStreamSynchronize(f->stream));  // the tap arrays are only borrowed for this call
+  }
+  const int i = f->cur == f->buf[0] ? 1 : 0;  // x: cur -> buf[i], y: buf[i] -> buf[1-i], z: buf[1-i] -> buf[i]
+  FCU(cudaEventRecord(f->ev0, f->stream));
+  FCU(launch_filter_x(f->cur, f->cur_dtype, f->buf[i], f->nx, f->ny, f->nz, hx, nhx, f->d_taps, f->stream));
+  FCU(launch_filter_axis(f->buf[i], f->buf[1 - i], f->nx, f->ny, f->nz, 1, hy, nhy, f->d_taps + FILT_LONG_TAPS, f->stream));
+  FCU(launch_filter_axis(f->buf[1 - i], f->buf[i], f->nx, f->ny, f->nz, 2, hz, nhz, f->d_taps + 2 * FILT_LONG_TAPS, f->stream));
+  FCU(cudaEventRecord(f->ev1, f->stream));
+  f->cur = f->buf[i];
+  f->cur_dtype = SPV_F32;
+  f->have_result = true;
+  f->timed = true;
+  return 0;
+}
+
+SPV_API int spv_filter_sync(spv_filter *f) {
+  FBIND();
+  FCU(cudaStreamSynchronize(f->stream));
+  return 0;
+}
+
+SPV_API int spv_filter_result_device(spv_filter *f, float **dev) {
+  FBIND();
+  if (!dev) return ffail(f, SPV_EINVAL, "spv_filter_result_device: null pointer");
+  if (!f->have_result) return ffail(f, SPV_ENODATA, "spv_filter_result_device: nothing convolved yet");
+  *dev = const_cast<float *>((const float *)f->cur);
+  return 0;
+}
+
+SPV_API int spv_filter_read(spv_filter *f, float *host_dst, size_t n) {
+  FBIND();
+  if (!host_dst) return ffail(f, SPV_EINVAL, "spv_filter_read: null destination");
+  if (!f->have_result) return ffail(f, SPV_ENODATA, "spv_filter_read: nothing convolved yet");
+  if (n != (size_t)f->nx * f->ny * f->nz) return ffail(f, SPV_EINVAL, "spv_filter_read: n must be nx * ny * nz");
+  FCU(cudaMemcpyAsync(host_dst, f->cur, n * sizeof(float), cudaMemcpyDeviceToHost, f->stream));
+  FCU(cudaStreamSynchronize(f->stream));
+  return 0;
+}
+
+SPV_API int spv_filter_last_ms(spv_filter *f, float *ms) {
+  FBIND();
+  if (!ms) return ffail(f, SPV_EINVAL, "spv_filter_last_ms: null pointer");
+  if (!f->timed) return ffail(f, SPV_ENODATA, "spv_filter_last_ms: nothing convolved yet");
+  FCU(cudaEventSynchronize(f->ev1));
+  FCU(cudaEventElapsedTime(ms, f->ev0, f->ev1));
+  return 0;
+}

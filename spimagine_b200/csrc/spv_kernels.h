@@ -31,6 +31,9 @@ struct MipArgs {
   unsigned *tile_counter;     // non-null: persistent CTAs pull tiles from this counter
   unsigned *band_done;        // non-null (static grid only): band_done[b] counts the CTAs of band b (band_rows image
   int band_rows;              // rows each) whose results are in memory -- the copy stream waits on these counters
+  int row_mode;               // order the tile rows are dealt in when band_done is set: 0 = from the top and bottom edges
+                              // inwards, 1 = the rows outside [hit_tile_a, hit_tile_b) first, then that range top to bottom
+  unsigned hit_tile_a, hit_tile_b;  // tile rows (8 pixels) the projected box can touch (conservative; any value is correct)
   Volume extra[MAX_EXTRA_SLABS];  // further slabs of the same global volume resident on this GPU (slab renders):
   int n_extra;                    // one ray setup, every slab's owned interval marched in turn
   PushArgs push;              // used when flags has SPV_MIP_PUSH
@@ -147,5 +150,14 @@ cudaError_t launch_display(const float *value, const float *alpha, const float *
 // ingest of host arrays of another element type: dst[i] = (dst type) src[i], n elements (src_type: SPV_SRC_*)
 size_t src_elem_size(int src_type);
 cudaError_t launch_convert(const void *src, void *dst, int src_type, int dtype, size_t n, cudaStream_t st);
+
+// separable 3-D convolution of a volume (spv_filter.cu; gputools.convolve_sep3 behind BlurProcessor.apply,
+// models/imageprocessor.py:47-71).  h: host taps; d_taps: the same taps in device memory (used for nh > FILTER_MAX_TAPS)
+constexpr int FILTER_MAX_TAPS = 63;
+struct FilterTaps { float w[FILTER_MAX_TAPS + 1]; };
+cudaError_t launch_filter_x(const void *in, int dtype, float *out, int nx, int ny, int nz, const float *h, int nh,
+                            const float *d_taps, cudaStream_t st);
+cudaError_t launch_filter_axis(const float *in, float *out, int nx, int ny, int nz, int axis, const float *h, int nh,
+                               const float *d_taps, cudaStream_t st);
 
 }  // namespace spv

@@ -316,7 +316,16 @@ __global__ void __launch_bounds__(32 * TX * TY, MINB) mip_fast_kernel(const MipA
   // Read-back overlap (spv_render_mip_to_host): tile rows are dealt from the top and bottom edges inwards.  The rows whose
   // rays miss the volume (typically the outer ones) are done at once and travel while the rest renders, and the band
   // that completes last is a single one in the middle instead of the whole lower part of the image.
-  if (a.band_done) by = (blockIdx.y & 1u) ? gridDim.y - 1u - (blockIdx.y >> 1) : (blockIdx.y >> 1);
+  // row_mode 1: the rows the projected box cannot touch first (top part, then bottom part), then the rows of the box
+  // top to bottom -- one front moving through the volume (L2 locality of the plain order) and one band completing last.
+  if (a.band_done) {
+    if (a.row_mode == 1) {
+      const unsigned ta = a.hit_tile_a, tb = a.hit_tile_b, nout = gridDim.y - (tb - ta);
+      by = blockIdx.y < nout ? (blockIdx.y < ta ? blockIdx.y : tb + (blockIdx.y - ta)) : ta + (blockIdx.y - nout);
+    } else {
+      by = (blockIdx.y & 1u) ? gridDim.y - 1u - (blockIdx.y >> 1) : (blockIdx.y >> 1);
+    }
+  }
   mip_fast_tile<FMT, LINEAR, SKIP, SLAB, TX, TY>(a, blockIdx.x, by, s_out, s_alpha);
   if (a.band_done) {  // this CTA's rows are stored: tell the copy stream
     __syncthreads();
@@ -392,6 +401,10 @@ static cudaError_t launch_fast(const MipArgs &a, bool skip, bool slab, cudaStrea
       case 2: launch_fast_shape<FMT, LINEAR, false, false, 2, 2, 12>(a, st); break;  // 16x8 px, <= 40 registers
       case 3: launch_fast_shape<FMT, LINEAR, false, false, 2, 2, 16>(a, st); break;  // 16x8 px, <= 32 registers
       case 4: launch_fast_shape<FMT, LINEAR, false, false, 2, 1, 16>(a, st); break;  // 16x4 px, 64 threads
+      // finer launch granularity at the default register budget: the last wave of box-hitting CTAs is shorter
+      case 5: launch_fast_shape<FMT, LINEAR, false, false, 2, 1, 1>(a, st); break;   // 16x4 px, 64 threads
+      case 6: launch_fast_shape<FMT, LINEAR, false, false, 1, 1, 1>(a, st); break;   // 8x4 px, one warp
+      case 7: launch_fast_shape<FMT, LINEAR, false, false, 1, 2, 1>(a, st); break;   // 8x8 px, 64 threads
       default: launch_fast_shape<FMT, LINEAR, false, false, 2, 2, 1>(a, st); break;  // 16x8 px, 128 threads
     }
   }

@@ -1,0 +1,256 @@
+"""Volume processors between the data model and the renderer -- the drop-in for spimagine/models/imageprocessor.py
+(ImageProcessor, CopyProcessor, BlurProcessor, BlurXYZProcessor, NoiseProcessor, LucyRichProcessor, FuncProcessor:
+same names, constructor arguments, `kwargs` attribute access and `apply(data) -> ndarray`), with the separable blur
+running on the B200 through libspimcuda (spv_filter_*) instead of gputools.convolve_sep3.
+
+The reference chain is host -> device -> host per processor and then host -> device again for the renderer
+(gui/mainwidget.py:455-465: data = imp.proc.apply(data) ...; renderer.update_data(data)).  Here a chain can stay on
+the device: `apply_chain(renderer, data, processors)` uploads the volume once, runs every device-capable processor
+in place and hands the float32 result to the renderer's resident array (spv_update_volume_device_from), so neither
+the filtered volume nor its re-upload crosses PCIe.
+
+FFTProcessor is not provided (it needs gputools.fft / pad_to_power2; SURVEY 8f-4 lists it as a later widening).
+There is no CPU implementation of the blur: without libspimcuda / a CUDA device, apply() raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class VolumeFilter(object):
+    """Device-side separable convolution (owns a stream and two float32 work volumes on `device`)."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        self._f = C.c_void_p()
+        rc = self._lib.spv_filter_create(int(device), C.byref(self._f))
+        if rc != 0:
+            msg = self._lib.spv_filter_last_error(None)
+            raise _lib.SpvError("libspimcuda: %s" % (msg.decode() if msg else "error %d" % rc))
+        self.shape = None
+
+    def close(self):
+        if getattr(self, "_f", None) is not None and self._f.value:
+            self._lib.spv_filter_destroy(self._f)
+            self._f = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.spv_filter_last_error(self._f)
+            raise _lib.SpvError("libspimcuda: %s" % (msg.decode() if msg else "error %d" % rc))
+
+    def load(self, data):
+        """data: ndarray (Nz, Ny, Nx) of any element type the ingest path knows; others go through float32."""
+        data = np.asarray(data)
+        if data.ndim != 3:
+            raise ValueError("need a 3-D volume, got shape %s" % (data.shape,))
+        if np.dtype(data.dtype) not in _lib.SRC_CODES or not data.dtype.isnative:
+            data = data.astype(np.float32)
+        host = np.ascontiguousarray(data)
+        nz, ny, nx = host.shape
+        self._check(self._lib.spv_filter_load(self._f, host.ctypes.data, 0, _lib.SRC_CODES[np.dtype(host.dtype)],
+                                              nx, ny, nz))
+        self.shape = (nz, ny, nx)
+
+    def load_device(self, device_ptr, shape, dtype):
+        nz, ny, nx = (int(s) for s in shape)
+        self._check(self._lib.spv_filter_load(self._f, C.c_void_p(int(device_ptr)), 1,
+                                              _lib.SRC_CODES[np.dtype(dtype)], nx, ny, nz))
+        self.shape = (nz, ny, nx)
+
+    def convolve_sep3(self, hx, hy, hz):
+        """gputools.convolve_sep3(data, hx, hy, hz) on the loaded volume (or on the previous result)."""
+        hs = [np.ascontiguousarray(np.asarray(h, dtype=np.float64).astype(np.float32)) for h in (hx, hy, hz)]
+        self._check(self._lib.spv_filter_convolve_sep3(self._f, _lib.fp(hs[0]), len(hs[0]), _lib.fp(hs[1]), len(hs[1]),
+                                                       _lib.fp(hs[2]), len(hs[2])))
+
+    def result(self):
+        out = np.empty(self.shape, np.float32)
+        self._check(self._lib.spv_filter_read(self._f, _lib.fp(out), out.size))
+        return out
+
+    def result_device(self):
+        """(device pointer, shape) of the float32 result; valid until the next load / convolution."""
+        p = _lib._FP()
+        self._check(self._lib.spv_filter_result_device(self._f, C.byref(p)))
+        return C.cast(p, C.c_void_p).value, self.shape
+
+    def sync(self):
+        self._check(self._lib.spv_filter_sync(self._f))
+
+    def last_ms(self):
+        ms = C.c_float()
+        self._check(self._lib.spv_filter_last_ms(self._f, C.byref(ms)))
+        return ms.value
+
+
+_shared = {}
+
+
+def _shared_filter(device=0):
+    f = _shared.get(device)
+    if f is None:
+        f = _shared[device] = VolumeFilter(device)
+    return f
+
+
+def convolve_sep3(data, hx, hy, hz, device=0):
+    """Drop-in for gputools.convolve_sep3(data, hx, hy, hz) with a numpy volume: float32 result (Nz, Ny, Nx)."""
+    f = _shared_filter(device)
+    f.load(data)
+    f.convolve_sep3(hx, hy, hz)
+    return f.result()
+
+
+class ImageProcessor(object):
+    """models/imageprocessor.py:18-33"""
+
+    def __init__(self, name="", **kwargs):
+        self.name = name
+        self.set_params(**kwargs)
+
+    def set_params(self, **kwargs):
+        self.kwargs = kwargs
+
+    def apply(self, data):
+        raise NotImplementedError()
+
+    def __getattr__(self, attr):
+        if attr != "kwargs" and attr in self.__dict__.get("kwargs", {}):
+            return self.kwargs[attr]
+        raise AttributeError(attr)
+
+
+class CopyProcessor(ImageProcessor):
+    """models/imageprocessor.py:37-43"""
+
+    def __init__(self):
+        super(CopyProcessor, self).__init__("copy")
+
+    def apply(self, data):
+        return data
+
+
+def _gauss_taps(sigma):
+    # models/imageprocessor.py:52-55 / :65-70 -- N = 2 sigma + 1, x = arange(-N, N + 1), h = exp(-x^2 / 2 sigma^2) / sum
+    N = 2 * sigma + 1
+    x = np.arange(-N, N + 1)
+    h = np.exp(-x ** 2 / 2. / sigma ** 2)
+    return 1. * h / sum(h)
+
+
+class BlurProcessor(ImageProcessor):
+    """models/imageprocessor.py:46-56"""
+
+    def __init__(self, sigma=4.):
+        super(BlurProcessor, self).__init__("blur", sigma=sigma)
+
+    def _taps(self):
+        h = _gauss_taps(self.sigma)
+        return h, h, h
+
+    def apply(self, data):
+        return convolve_sep3(data, *self._taps())
+
+    def apply_device(self, vfilter):
+        """addition: blur the volume resident in `vfilter` in place (no host round trip)"""
+        vfilter.convolve_sep3(*self._taps())
+
+
+class BlurXYZProcessor(ImageProcessor):
+    """models/imageprocessor.py:59-71 (hx from sx, hy from sy, hz from sz)"""
+
+    def __init__(self, sx=4., sy=4., sz=4.):
+        super(BlurXYZProcessor, self).__init__("blur_xyz", sx=sx, sy=sy, sz=sz)
+
+    def _taps(self):
+        return tuple(_gauss_taps(s) for s in (self.sx, self.sy, self.sz))
+
+    def apply(self, data):
+        return convolve_sep3(data, *self._taps())
+
+    def apply_device(self, vfilter):
+        """addition: blur the volume resident in `vfilter` in place (no host round trip)"""
+        vfilter.convolve_sep3(*self._taps())
+
+
+class NoiseProcessor(ImageProcessor):
+    """models/imageprocessor.py:73-78 (host-side numpy in the reference as well)"""
+
+    def __init__(self, sigma=10):
+        super(NoiseProcessor, self).__init__("noise", sigma=sigma)
+
+    def apply(self, data):
+        return np.maximum(0, data + self.sigma * np.random.normal(0, 1, data.shape))
+
+
+class LucyRichProcessor(ImageProcessor):
+    """models/imageprocessor.py:101-120: the deconvolution is commented out in the reference; apply returns its input"""
+
+    def __init__(self, rad=4., niter=6):
+        super(LucyRichProcessor, self).__init__("RL-Deconv", rad=rad, niter=niter)
+        self.rad0 = rad
+        self.niter0 = niter
+        self.hshape = (1,) * 3
+
+    def reset_psf(self, dshape):
+        pass
+
+    def apply(self, data):
+        if self.hshape != data.shape or self.rad != self.rad0:
+            self.reset_psf(data.shape)
+            self.rad0 = self.rad
+        return data
+
+
+class FuncProcessor(ImageProcessor):
+    """models/imageprocessor.py:123-130"""
+
+    def __init__(self, func, name="func processor", **kwargs):
+        super(FuncProcessor, self).__init__(name, **kwargs)
+        self.func = func
+
+    def apply(self, data):
+        return self.func(data, **self.kwargs)
+
+
+def apply_chain(renderer, data, processors, device=None):
+    """What MainWidget.impStateChanged does (gui/mainwidget.py:455-465) -- data through every processor, then
+    renderer.update_data(result) -- without the round trips: the volume is uploaded once, the blurs run on the
+    resident copy (a host-only processor in between gets a host array and its result is uploaded again), and the
+    final float32 volume goes from the filter's memory straight into the renderer's resident array, converted to
+    the renderer's element type like update_data's astype.  `renderer` must already hold a volume of the same shape
+    (set_data).  Returns the device time of the filters in ms."""
+    dev = device if device is not None else (renderer.device or 0)
+    vf = _shared_filter(dev)
+    data = np.asarray(data)
+    resident, ms = False, 0.
+    for p in processors:
+        if isinstance(p, (BlurProcessor, BlurXYZProcessor)):
+            if not resident:
+                vf.load(data)
+                resident = True
+            p.apply_device(vf)
+            ms += vf.last_ms()
+        elif isinstance(p, (CopyProcessor, LucyRichProcessor)):
+            continue  # identity in the reference as well
+        else:
+            if resident:
+                data = vf.result()
+                resident = False
+            data = np.asarray(p.apply(data))
+    if not resident:
+        renderer.update_data(data)
+        return ms
+    ptr, shape = vf.result_device()
+    vf.sync()
+    renderer.update_data_device(ptr, shape, np.float32)
+    return ms

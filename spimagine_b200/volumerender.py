@@ -315,6 +315,22 @@ class VolumeRenderer(object):
         self._need_alloc = False
         self.update_matrices()
 
+    def update_data_device(self, device_ptr, shape, dtype):
+        """Addition: update_data (volumerender.py:279-294) from DEVICE memory -- a C-order (Nz, Ny, Nx) array of any
+        element type the ingest path knows, of the current volume shape; converted to the volume's element type on the
+        device like update_data's astype.  Whatever produced the array must have finished; the copy is enqueued on
+        the renderer's stream."""
+        dtype = np.dtype(dtype)
+        if dtype not in _lib.SRC_CODES:
+            raise NotImplementedError("element type %s cannot be converted on the device" % dtype)
+        Nx, Ny, Nz = self.dataImg.shape
+        if tuple(int(s) for s in shape) != (Nz, Ny, Nx) or getattr(self, "_need_alloc", True):
+            raise ValueError("update_data_device needs a resident volume of shape %s (set_data first), got %s"
+                             % ((Nz, Ny, Nx), tuple(shape)))
+        self._data = None
+        self._check(self._lib.spv_update_volume_device_from(self._ctx, C.c_void_p(int(device_ptr)),
+                                                            _lib.SRC_CODES[dtype]))
+
     @property
     def data_min_max(self):
         """(min, max) of the resident volume: what GLWidget._get_min_max computes (gui/glwidget.py:328-344)."""

@@ -363,3 +363,39 @@ def test_display_pass_matches_the_shader_restatement(dtype, n_lut, oracle_mod):
     with pytest.raises(Exception):
         _renderer((32, 32)).output_rgba()            # no colour map set
     rend.close()
+
+
+@pytest.mark.parametrize("size", [(256, 200), (1024, 1024)])
+def test_read_back_row_orders_and_band_counts_give_the_same_frame(size):
+    """spv_render_mip_to_host deals its tile rows in an order chosen for the read-back overlap (tuning knob 8) and cuts
+    the frame into bands (knob 2): scheduling only -- every combination returns the planes of the plain render, for
+    boxes in the middle of the image, off centre, filling it, partly behind the eye and off screen."""
+    import ctypes as C
+    from spimagine_b200 import _lib
+    from spimagine_b200.utils.transform_matrices import mat4_perspective, mat4_rotation, mat4_translate
+    data = scenes.vol_g(64, np.uint16, seed=5)
+    rend = _renderer(size)
+    rend.set_data(data)
+    rend.set_max_val(60000.)
+    P = mat4_perspective(60, 1., .1, 10)
+    views = [np.dot(mat4_translate(0, 0, -4), mat4_rotation(0.4, 0, 1, 0)),          # centred
+             np.dot(mat4_translate(0.3, 1.4, -4), mat4_rotation(1.1, 1, 1, 0)),     # near the top edge, partly outside
+             np.dot(mat4_translate(0, 0, -1.6), mat4_rotation(0.2, 0, 1, 0)),       # fills the image
+             np.dot(mat4_translate(0, 0, -0.5), mat4_rotation(0.2, 0, 1, 0)),       # corners behind the eye
+             np.dot(mat4_translate(0, 9., -4), mat4_rotation(0.2, 0, 1, 0))]        # off screen
+    rend.set_projection(P)
+    n = size[0] * size[1]
+    for M in views:
+        rend.set_modelView(M)
+        rend.render_device_only()
+        rend.sync()
+        want, _ = rend._fetch(2)
+        want = want.copy()
+        for mode in (0, 1):
+            for bands in (1, 5, 12, 32):
+                rend._check(rend._lib.spv_set_tuning(rend._ctx, 8, mode))
+                rend._check(rend._lib.spv_set_tuning(rend._ctx, 2, bands))
+                rend.render()
+                got = np.concatenate([rend.output.ravel(), rend.output_alpha.ravel()])
+                assert got.size == 2 * n and np.array_equal(got, want), (mode, bands)
+    rend.close()
