@@ -266,6 +266,10 @@ SPV_API int spv_filter_result_device(spv_filter *f, float **dev);
 SPV_API int spv_filter_read(spv_filter *f, float *host_dst, size_t n);
 SPV_API int spv_filter_last_ms(spv_filter *f, float *ms);  /* device time of the last convolution (three passes) */
 SPV_API const char *spv_filter_last_error(spv_filter *f);  /* f may be NULL: last create error */
+/* knob 0: the x and y pass run as one kernel where both tap counts fall into the same size class of at most 31 taps
+ * (1, default) or always as separate passes (0); results are identical */
+SPV_API int spv_filter_set_tuning(spv_filter *f, int knob, int value);
+SPV_API int spv_filter_launch_count(spv_filter *f, unsigned long long *n);  /* kernels launched by this filter so far */
 
 /* ---- diagnostics ---- */
 SPV_API int spv_last_timing_ms(spv_ctx *ctx, float *ms);            /* device time of the last render call */

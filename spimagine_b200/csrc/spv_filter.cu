@@ -127,6 +127,82 @@ __global__ void __launch_bounds__(32 * NW) conv_x_kernel(const TIN *__restrict__
   }
 }
 
+// x and y pass in one kernel (both tap counts in the same size class NHMAX <= 31): a CTA of 8 warps produces
+// 128 (x) x YT (y) outputs of one slice, YT = 65 - NHMAX, from the 64 rows x (128 + NHMAX - 1) inputs they need.
+//   stage 1  the x pass of conv_x_kernel for 2 x 32 rows (a lane per row), results into s_mid (odd pitch)
+//   stage 2  the y pass out of s_mid: a thread per column and half of the YT outputs, streamed as in
+//            conv_axis_kernel, stored straight to global memory (coalesced along x)
+// Every intermediate value is the one the separate passes would have stored (same fma sequence), rows outside the
+// volume are zeros as the dropped taps of the y pass require.  Saves one float32 write + read of the volume.
+template <typename TIN, int NHMAX, int NHMIN>
+__global__ void __launch_bounds__(256) conv_xy_fused_kernel(const TIN *__restrict__ in, float *__restrict__ out, int nx, int ny,
+                                                            int nhx, int nhy, const FilterTaps tx, const FilterTaps ty) {
+  constexpr int R = 16, NW = 8, XW = NW * R, TW = XW + NHMAX - 1, PITCH = TW | 1, MP = XW + 1;
+  constexpr int YT = 65 - NHMAX, RY = YT / 2;
+  extern __shared__ float smem[];
+  float(*s_in)[PITCH] = reinterpret_cast<float(*)[PITCH]>(smem);             // [32][PITCH]
+  float(*s_mid)[MP] = reinterpret_cast<float(*)[MP]>(smem + 32 * PITCH);      // [64][MP]
+  const int x0 = blockIdx.x * XW, y0 = blockIdx.y * YT;
+  const size_t slice = (size_t)blockIdx.z * nx * ny;
+  const int halfx = nhx / 2, halfy = nhy / 2;
+  const int qxbase = x0 + halfx - (NHMAX - 1);  // x position of tile column 0
+  const int qybase = y0 + halfy - (NHMAX - 1);  // y position of tile row 0
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nstepsx = R + nhx - 1;
+  for (int round = 0; round < 2; ++round) {
+    if (round) __syncthreads();  // everyone is done reading s_in
+    for (int i = threadIdx.x; i < 32 * TW; i += 256) {
+      const int rr = i / TW, c = i - rr * TW;
+      const int qx = qxbase + c, qy = qybase + round * 32 + rr;
+      float v = 0.f;
+      if (qy >= 0 && qy < ny && qx >= 0 && qx < nx) v = (float)in[slice + (size_t)qy * nx + qx];
+      s_in[rr][c] = v;
+    }
+    __syncthreads();
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+    const float *line = s_in[lane] + warp * R + R - 1 + NHMAX - 1;
+#pragma unroll
+    for (int jj = 0; jj < R + NHMAX - 1; ++jj) {
+      float v = line[-jj];
+      if (jj >= R + NHMIN - 1 && jj >= nstepsx) v = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int ht = jj - (R - 1 - r);
+        if (ht >= 0 && ht < NHMAX) acc[r] = fmaf(tx.w[ht], v, acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) s_mid[round * 32 + lane][warp * R + r] = acc[r];
+  }
+  __syncthreads();
+  // stage 2: column c of the tile, outputs y0 + half * RY + r
+  const int c = threadIdx.x & (XW - 1), hchunk = threadIdx.x >> 7;
+  const int nstepsy = RY + nhy - 1;
+  float acc[RY];
+#pragma unroll
+  for (int r = 0; r < RY; ++r) acc[r] = 0.f;
+  const int top = hchunk * RY + RY - 1 + NHMAX - 1;  // tile row of the position met first
+#pragma unroll
+  for (int jj = 0; jj < RY + NHMAX - 1; ++jj) {
+    float v = s_mid[top - jj][c];
+    if (jj >= RY + NHMIN - 1 && jj >= nstepsy) v = 0.f;
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+      const int ht = jj - (RY - 1 - r);
+      if (ht >= 0 && ht < NHMAX) acc[r] = fmaf(ty.w[ht], v, acc[r]);
+    }
+  }
+  if (x0 + c < nx) {
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+      const int y = y0 + hchunk * RY + r;
+      if (y < ny) out[slice + (size_t)y * nx + x0 + c] = acc[r];
+    }
+  }
+}
+
 // any tap count: one output per thread, taps read from device memory with a runtime index (slow path; lanes run
 // along the index with stride sx, the line along the axis with stride sa)
 template <typename TIN>
@@ -227,6 +303,57 @@ static cudaError_t filter_x_typed(const TIN *in, float *out, int nx, int ny, int
   return cudaGetLastError();
 }
 
+template <typename TIN, int NHMAX, int NHMIN>
+static cudaError_t launch_xy_n(const TIN *in, float *out, int nx, int ny, int nz, int nhx, int nhy, const FilterTaps &tx,
+                               const FilterTaps &ty, cudaStream_t st) {
+  constexpr int TW = 128 + NHMAX - 1, PITCH = TW | 1, YT = 65 - NHMAX;
+  const size_t smem = (size_t)(32 * PITCH + 64 * 129) * sizeof(float);
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_xy_fused_kernel<TIN, NHMAX, NHMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((nx + 127) / 128, (ny + YT - 1) / YT, nz);
+  conv_xy_fused_kernel<TIN, NHMAX, NHMIN><<<grid, 256, smem, st>>>(in, out, nx, ny, nhx, nhy, tx, ty);
+  return cudaGetLastError();
+}
+
+template <typename TIN>
+static cudaError_t filter_xy_typed(const TIN *in, float *out, int nx, int ny, int nz, const float *hx, int nhx,
+                                   const float *hy, int nhy, cudaStream_t st) {
+  const int size = pick_size(nhx);
+  const FilterTaps tx = padded(hx, nhx), ty = padded(hy, nhy);
+  switch (size) {
+    case 3: return launch_xy_n<TIN, 3, 1>(in, out, nx, ny, nz, nhx, nhy, tx, ty, st);
+    case 7: return launch_xy_n<TIN, 7, 4>(in, out, nx, ny, nz, nhx, nhy, tx, ty, st);
+    case 11: return launch_xy_n<TIN, 11, 8>(in, out, nx, ny, nz, nhx, nhy, tx, ty, st);
+    case 15: return launch_xy_n<TIN, 15, 12>(in, out, nx, ny, nz, nhx, nhy, tx, ty, st);
+    case 19: return launch_xy_n<TIN, 19, 16>(in, out, nx, ny, nz, nhx, nhy, tx, ty, st);
+    case 23: return launch_xy_n<TIN, 23, 20>(in, out, nx, ny, nz, nhx, nhy, tx, ty, st);
+    case 27: return launch_xy_n<TIN, 27, 24>(in, out, nx, ny, nz, nhx, nhy, tx, ty, st);
+    case 31: return launch_xy_n<TIN, 31, 28>(in, out, nx, ny, nz, nhx, nhy, tx, ty, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// can the x and y passes run as one kernel?  (both tap counts in the same size class, at most 31 taps)
+bool filter_xy_fusable(int nhx, int nhy) {
+  const int sx = pick_size(nhx), sy = pick_size(nhy);
+  return sx != 0 && sx == sy && sx <= 31;
+}
+
+// fused x + y pass (filter_xy_fusable) from a volume of element type dtype into a float volume
+cudaError_t launch_filter_xy(const void *in, int dtype, float *out, int nx, int ny, int nz, const float *hx, int nhx,
+                             const float *hy, int nhy, cudaStream_t st) {
+  switch (dtype) {
+    case 0: return filter_xy_typed((const float *)in, out, nx, ny, nz, hx, nhx, hy, nhy, st);
+    case 1: return filter_xy_typed((const unsigned short *)in, out, nx, ny, nz, hx, nhx, hy, nhy, st);
+    case 2: return filter_xy_typed((const unsigned char *)in, out, nx, ny, nz, hx, nhx, hy, nhy, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 // x pass from a volume of element type dtype (SPV_F32 / SPV_U16 / SPV_U8) into a float volume
 cudaError_t launch_filter_x(const void *in, int dtype, float *out, int nx, int ny, int nz, const float *h, int nh,
                             const float *d_taps, cudaStream_t st) {
@@ -256,6 +383,8 @@ struct spv_filter {
   const void *cur = nullptr;  // what the next convolution reads: the loaded volume or the last result
   int cur_dtype = 0;          // SPV_F32 / SPV_U16 / SPV_U8
   bool have_result = false, timed = false;
+  int fuse_xy = 1;  // x and y pass in one kernel where the tap counts allow it (spv_filter_set_tuning knob 0)
+  unsigned long long launches = 0;
   std::string err;
 };
 
@@ -388,9 +517,22 @@ SPV_API int spv_filter_convolve_sep3(spv_filter *f, const float *hx, int nhx, co
   }
   const int i = f->cur == f->buf[0] ? 1 : 0;  // x: cur -> buf[i], y: buf[i] -> buf[1-i], z: buf[1-i] -> buf[i]
   FCU(cudaEventRecord(f->ev0, f->stream));
+  if (f->fuse_xy && filter_xy_fusable(nhx, nhy)) {  // x + y in one kernel: cur -> buf[i], then z: buf[i] -> buf[1-i]
+    const int j = i;  // buf[i] is not the source
+    FCU(launch_filter_xy(f->cur, f->cur_dtype, f->buf[j], f->nx, f->ny, f->nz, hx, nhx, hy, nhy, f->stream));
+    FCU(launch_filter_axis(f->buf[j], f->buf[1 - j], f->nx, f->ny, f->nz, 2, hz, nhz, f->d_taps + 2 * FILT_LONG_TAPS, f->stream));
+    f->launches += 2;
+    FCU(cudaEventRecord(f->ev1, f->stream));
+    f->cur = f->buf[1 - j];
+    f->cur_dtype = SPV_F32;
+    f->have_result = true;
+    f->timed = true;
+    return 0;
+  }
   FCU(launch_filter_x(f->cur, f->cur_dtype, f->buf[i], f->nx, f->ny, f->nz, hx, nhx, f->d_taps, f->stream));
   FCU(launch_filter_axis(f->buf[i], f->buf[1 - i], f->nx, f->ny, f->nz, 1, hy, nhy, f->d_taps + FILT_LONG_TAPS, f->stream));
   FCU(launch_filter_axis(f->buf[1 - i], f->buf[i], f->nx, f->ny, f->nz, 2, hz, nhz, f->d_taps + 2 * FILT_LONG_TAPS, f->stream));
+  f->launches += 3;
   FCU(cudaEventRecord(f->ev1, f->stream));
   f->cur = f->buf[i];
   f->cur_dtype = SPV_F32;
@@ -429,5 +571,19 @@ SPV_API int spv_filter_last_ms(spv_filter *f, float *ms) {
   if (!f->timed) return ffail(f, SPV_ENODATA, "spv_filter_last_ms: nothing convolved yet");
   FCU(cudaEventSynchronize(f->ev1));
   FCU(cudaEventElapsedTime(ms, f->ev0, f->ev1));
+  return 0;
+}
+
+/* knob 0: 1 = x and y pass in one kernel where the tap counts allow it (default), 0 = always three passes */
+SPV_API int spv_filter_set_tuning(spv_filter *f, int knob, int value) {
+  FBIND();
+  if (knob == 0) f->fuse_xy = value != 0;
+  else return ffail(f, SPV_EINVAL, "spv_filter_set_tuning: unknown knob");
+  return 0;
+}
+
+SPV_API int spv_filter_launch_count(spv_filter *f, unsigned long long *n) {
+  if (!f || !n) return SPV_EINVAL;
+  *n = f->launches;
   return 0;
 }

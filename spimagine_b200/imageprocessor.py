@@ -86,6 +86,15 @@ class VolumeFilter(object):
     def sync(self):
         self._check(self._lib.spv_filter_sync(self._f))
 
+    def set_tuning(self, knob, value):
+        """knob 0: x and y pass as one kernel where the tap counts allow it (1, default) or three passes (0)"""
+        self._check(self._lib.spv_filter_set_tuning(self._f, int(knob), int(value)))
+
+    def launch_count(self):
+        n = C.c_ulonglong()
+        self._check(self._lib.spv_filter_launch_count(self._f, C.byref(n)))
+        return n.value
+
     def last_ms(self):
         ms = C.c_float()
         self._check(self._lib.spv_filter_last_ms(self._f, C.byref(ms)))

@@ -99,25 +99,34 @@ def test_processor_interface_matches_the_reference():
 
 
 # ------------------------------------------------------------------------------------------------ GPU
-def _gpu_sep3(data, hx, hy, hz):
-    from spimagine_b200.imageprocessor import convolve_sep3
-    return convolve_sep3(data, hx, hy, hz)
+def _gpu_sep3(data, hx, hy, hz, fuse=1):
+    from spimagine_b200 import imageprocessor as ip
+    vf = ip._shared_filter(0)
+    vf.set_tuning(0, fuse)
+    try:
+        return ip.convolve_sep3(data, hx, hy, hz)
+    finally:
+        vf.set_tuning(0, 1)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fuse", [1, 0])
 @pytest.mark.parametrize("dtype", [np.float32, np.uint16, np.uint8])
 @pytest.mark.parametrize("shape,taps", [((40, 50, 300), (19, 19, 19)),   # several x tiles, interior + face chunks
+                                        ((3, 100, 130), (17, 19, 5)),    # fused x + y, padded, several y tiles
+                                        ((5, 70, 260), (31, 29, 3)),     # fused, the largest class
+                                        ((4, 64, 128), (3, 2, 7)),       # fused, the smallest class
                                         ((33, 17, 129), (7, 11, 3)),     # ragged extents, exact instantiations
                                         ((20, 35, 64), (5, 13, 17)),     # padded instantiations (5 -> 7, 13 -> 15, 17 -> 19)
                                         ((9, 6, 5), (19, 19, 19)),       # volume smaller than the kernel on every axis
                                         ((18, 20, 40), (4, 6, 2)),       # even tap counts
                                         ((24, 8, 33), (1, 1, 63)),
                                         ((70, 5, 6), (3, 3, 101))])      # beyond the unrolled sizes: generic kernel
-def test_gpu_convolve_sep3_equals_the_oracle_bitwise(forc, dtype, shape, taps):
+def test_gpu_convolve_sep3_equals_the_oracle_bitwise(forc, dtype, shape, taps, fuse):
     rng = np.random.default_rng(len(shape) + sum(taps))
     data = scenes.random_vol(shape, dtype, seed=sum(shape))
     hs = [rng.random(n) - .2 for n in taps]
-    got = _gpu_sep3(data, *hs)
+    got = _gpu_sep3(data, *hs, fuse=fuse)
     want = forc.convolve_sep3(data, *hs)
     assert got.dtype == np.float32 and got.shape == shape
     assert np.array_equal(got, want)
@@ -137,11 +146,12 @@ def test_gpu_non_finite_voxels_spread_exactly_as_in_the_reference(forc):
     data = scenes.random_vol((30, 40, 200), np.float32, seed=3)
     data[15, 20, 100] = np.nan
     data[3, 2, 7] = np.inf
-    hs = [np.abs(np.random.default_rng(1).random(n)) + .1 for n in (5, 13, 17)]  # padded instantiations
-    got, want = _gpu_sep3(data, *hs), forc.convolve_sep3(data, *hs)
-    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isinf(got), np.isinf(want))
-    ok = np.isfinite(want)
-    assert np.array_equal(got[ok], want[ok])
+    for taps in ((5, 13, 17), (16, 17, 18)):  # padded instantiations: three passes / fused x + y
+        hs = [np.abs(np.random.default_rng(1).random(n)) + .1 for n in taps]
+        got, want = _gpu_sep3(data, *hs), forc.convolve_sep3(data, *hs)
+        assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isinf(got), np.isinf(want))
+        ok = np.isfinite(want)
+        assert np.array_equal(got[ok], want[ok])
 
 
 @pytest.mark.gpu
@@ -159,7 +169,7 @@ def test_gpu_blur_processors_and_chains(forc):
     ip.BlurXYZProcessor(1., 2., 3.).apply_device(vf)
     want = forc.convolve_sep3(forc.convolve_sep3(data, h2, h2, h2), hx, hy, hz)
     assert np.array_equal(vf.result(), want)
-    assert vf.last_ms() > 0
+    assert vf.last_ms() > 0 and vf.launch_count() == 4  # two convolutions of a fused x + y kernel and a z pass each
     vf.close()
 
 
