@@ -48,7 +48,7 @@ struct spv_ctx {
                   // band counters (one launch per frame), else 2 (one launch per band) -- profiles/r01_exp_e2e.txt
   int iso_segments = 1;   // tuning knob 4 (measured on configs[2]: 1 -> 97 us, 2 -> 110 us, 4 -> 178 us)
   int iso_centre_out = 1; // tuning knob 5
-  int row_mode = 0;     // spv_render_mip_to_host, one-launch path: order of the tile rows (tuning knob 8, MipArgs::row_mode)
+  int row_mode = 1;     // spv_render_mip_to_host, one-launch path: order of the tile rows (tuning knob 8, MipArgs::row_mode)
   int direct_host = 0;  // spv_render_mip_to_host: the kernel stores straight into the pinned staging (tuning knob 3)
   unsigned *d_tile_counter = nullptr;
   unsigned *d_band_done = nullptr;   // [MAX_BANDS] CTAs finished per band, counting up across frames (never reset)

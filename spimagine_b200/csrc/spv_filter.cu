@@ -17,9 +17,9 @@
 // from the highest position down, so that every output meets its taps in ascending order; after full unrolling every
 // tap index is a compile-time constant and the weight is a constant-bank operand of the FMA (the taps travel as a
 // kernel argument).  Dropped taps become fma(h, 0, acc) = acc.  Kernels are instantiated for the tap counts
-// NHMAX in FILT_SIZES; other counts run in the next larger instantiation with zero weights appended, and the steps
-// beyond the real window feed zeros (fma(0, 0, acc) = acc), so a voxel never meets a tap the reference would not
-// give it (NaN / Inf voxels spread exactly as far as in the reference).
+// NHMAX in FILT_SIZES; other counts run in the next larger instantiation, whose taps beyond the real count are
+// predicated off (a handful of predicates `nh > ht`, computed once), so a voxel never meets a tap the reference
+// would not give it (NaN / Inf voxels spread exactly as far as in the reference).
 //   conv_axis_kernel  y and z passes: lanes along x (coalesced), the line runs along the strided axis
 //   conv_x_kernel     x pass: 32 lines x (XW + Nh - 1) inputs staged in shared memory (odd pitch: a lane per line
 //                     reads conflict-free), results staged back for coalesced stores; reads the source element type
@@ -29,6 +29,14 @@
 #include "spv_kernels.h"
 
 namespace spv {
+
+// base + step * k as ONE instruction (IMAD.WIDE.U32 with an immediate k after unrolling); kept opaque so that the
+// compiler does not turn the unrolled address sequence back into chains of 64-bit additions
+__device__ __forceinline__ const char *mad_wide(unsigned step, unsigned k, const char *base) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(step), "r"(k), "l"((unsigned long long)base));
+  return reinterpret_cast<const char *>(r);
+}
 
 // One pass along a strided axis.  in/out: float volumes; the line of (x, o) starts at base + o * so + x, positions
 // along the axis are `sa` elements apart.  grid = (ceil(nx / 128), ceil(na / R), no).  The instantiation serves tap
@@ -49,17 +57,22 @@ __global__ void __launch_bounds__(128) conv_axis_kernel(const float *__restrict_
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = 0.f;
   if (qtop < na && qtop - (nsteps - 1) >= 0) {  // the whole window lies inside the volume (uniform per CTA)
-    const float *ptr = src + (size_t)qtop * sa;
+    // addresses as low + step * constant with a 32-bit byte step: one IMAD.WIDE.U32 per load (the launcher checks
+    // that the step fits); `low` is the position of the last unrolled step and is only dereferenced where a real tap
+    // reads it
+    constexpr int K = R + NHMAX - 2;
+    const unsigned step = (unsigned)(sa * sizeof(float));
+    const char *low = reinterpret_cast<const char *>(src) + ((long long)qtop - K) * (long long)(sa * sizeof(float));
 #pragma unroll
     for (int jj = 0; jj < R + NHMAX - 1; ++jj) {
+      const float *ptr = reinterpret_cast<const float *>(mad_wide(step, (unsigned)(K - jj), low));
       float v;
       if (jj < R + NHMIN - 1) v = __ldg(ptr);
       else v = jj < nsteps ? __ldg(ptr) : 0.f;
-      ptr -= sa;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int ht = jj - (R - 1 - r);
-        if (ht >= 0 && ht < NHMAX) acc[r] = fmaf(t.w[ht], v, acc[r]);
+        if (ht >= 0 && ht < NHMAX && (ht < NHMIN || ht < nh)) acc[r] = fmaf(t.w[ht], v, acc[r]);
       }
     }
   } else {  // window cut by a volume face: positions outside contribute fma(h, 0, acc) = acc
@@ -71,34 +84,121 @@ __global__ void __launch_bounds__(128) conv_axis_kernel(const float *__restrict_
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int ht = jj - (R - 1 - r);
-        if (ht >= 0 && ht < NHMAX) acc[r] = fmaf(t.w[ht], v, acc[r]);
+        if (ht >= 0 && ht < NHMAX && (ht < NHMIN || ht < nh)) acc[r] = fmaf(t.w[ht], v, acc[r]);
       }
     }
   }
+  char *obase = reinterpret_cast<char *>(dst + (size_t)p0 * sa);
+  const unsigned ostep = (unsigned)(sa * sizeof(float));
 #pragma unroll
   for (int r = 0; r < R; ++r)
-    if (p0 + r < na) dst[(size_t)(p0 + r) * sa] = acc[r];
+    if (p0 + r < na) *reinterpret_cast<float *>(const_cast<char *>(mad_wide(ostep, (unsigned)r, obase))) = acc[r];
 }
 
+// The same pass W = 2 or 4 columns wide: a thread owns x = W t .. W t + W - 1 (one 64- or 128-bit load / store per
+// position: 1/W of the address arithmetic and memory instructions per output) and R outputs of each column.  Needs
+// nx % W == 0 and volumes aligned to 4 W bytes.  grid = (ceil(nx / (128 W)), ceil(na / R), no).
+template <int W> struct VecOf;
+template <> struct VecOf<2> { typedef float2 type; };
+template <> struct VecOf<4> { typedef float4 type; };
+
+template <int NHMAX, int NHMIN, int R, int W>
+__global__ void __launch_bounds__(128) conv_axisw_kernel(const float *__restrict__ in, float *__restrict__ out, int nx, int na,
+                                                         size_t sa, size_t so, int nh, const FilterTaps t) {
+  typedef typename VecOf<W>::type vec;
+  const int x = (blockIdx.x * 128 + threadIdx.x) * W;
+  if (x >= nx) return;
+  const int p0 = blockIdx.y * R;
+  const float *src = in + (size_t)blockIdx.z * so + x;
+  float *dst = out + (size_t)blockIdx.z * so + x;
+  const int half = nh / 2;
+  const int qtop = p0 + R - 1 + half;
+  const int nsteps = R + nh - 1;
+  float acc[R][W];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int k = 0; k < W; ++k) acc[r][k] = 0.f;
+  const bool interior = qtop < na && qtop - (nsteps - 1) >= 0;  // uniform per CTA
+  const float *ptr = src + (size_t)qtop * sa;
+#pragma unroll
+  for (int jj = 0; jj < R + NHMAX - 1; ++jj) {
+    const int q = qtop - jj;
+    float v[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) v[k] = 0.f;
+    if ((jj < R + NHMIN - 1 || jj < nsteps) && (interior || (q >= 0 && q < na))) {
+      const vec l = __ldg(reinterpret_cast<const vec *>(ptr));
+      v[0] = l.x;
+      v[1] = l.y;
+      if (W == 4) {
+        v[2] = reinterpret_cast<const float *>(&l)[2];
+        v[3] = reinterpret_cast<const float *>(&l)[3];
+      }
+    }
+    ptr -= sa;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int ht = jj - (R - 1 - r);
+      if (ht >= 0 && ht < NHMAX && (ht < NHMIN || ht < nh)) {
+        const float w = t.w[ht];
+#pragma unroll
+        for (int k = 0; k < W; ++k) acc[r][k] = fmaf(w, v[k], acc[r][k]);
+      }
+    }
+  }
+  float *o = dst + (size_t)p0 * sa;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (p0 + r < na) {
+      vec sv;
+      sv.x = acc[r][0];
+      sv.y = acc[r][1];
+      if (W == 4) {
+        reinterpret_cast<float *>(&sv)[2] = acc[r][2];
+        reinterpret_cast<float *>(&sv)[3] = acc[r][3];
+      }
+      *reinterpret_cast<vec *>(o) = sv;
+    }
+    o += sa;
+  }
+}
+
+// loaded values wait in 32-bit registers (no sub-word packing)
+template <typename T> struct Held { typedef unsigned type; };
+template <> struct Held<float> { typedef float type; };
+// exact uint8 / uint16 -> float on the FMA / ALU pipes (I2F runs on the slow conversion pipe): 2^23 + v has v in its
+// mantissa for v < 2^23
+__device__ __forceinline__ float to_float(unsigned v) { return __int_as_float(0x4b000000u | v) - 8388608.f; }
+__device__ __forceinline__ float to_float(float v) { return v; }
+
 // The x pass.  Lines are the nrows = ny * nz rows of the volume, nx elements each; a CTA of NW warps takes 32
-// consecutive rows x XW = NW * R outputs.  grid = (ceil(nrows / 32), ceil(nx / XW)).
+// consecutive rows x XW = NW * R outputs.  grid = ceil(nx / XW) * ceil(nrows / 32), x tiles fastest.
 template <typename TIN, int NHMAX, int NHMIN, int R, int NW>
 __global__ void __launch_bounds__(32 * NW) conv_x_kernel(const TIN *__restrict__ in, float *__restrict__ out, int nx,
                                                          long long nrows, int nh, const FilterTaps t) {
   constexpr int XW = NW * R, TW = XW + NHMAX - 1, PITCH = TW | 1, OPITCH = XW | 1;
   __shared__ float s_in[32][PITCH];
   __shared__ float s_out[32][OPITCH];
-  const int x0 = blockIdx.y * XW;
-  const long long row0 = (long long)blockIdx.x * 32;
+  const unsigned ntx = (unsigned)((nx + XW - 1) / XW);  // x tiles are dealt fastest: concurrent CTAs read whole rows
+  const int x0 = (int)(blockIdx.x % ntx) * XW;
+  const long long row0 = (long long)(blockIdx.x / ntx) * 32;
   const int half = nh / 2;
   const int qbase = x0 + half - (NHMAX - 1);  // input position of tile column 0
-  for (int i = threadIdx.x; i < 32 * TW; i += 32 * NW) {
-    const int rr = i / TW, c = i - rr * TW;
-    const int q = qbase + c;
-    const long long row = row0 + rr;
-    float v = 0.f;
-    if (row < nrows && q >= 0 && q < nx) v = (float)in[(size_t)row * nx + q];
-    s_in[rr][c] = v;
+  static_assert(TW <= 32 * NW, "one thread per tile column");
+  if (threadIdx.x < TW) {  // a thread per tile column, walking down the 32 rows (coalesced across the warp)
+    const int q = qbase + (int)threadIdx.x;
+    const bool okx = q >= 0 && q < nx;
+    const TIN *p = in + (size_t)row0 * nx + (okx ? q : 0);
+    const int nr = nrows - row0 < 32 ? (int)(nrows - row0) : 32;
+    typename Held<TIN>::type held[32];  // every load of the column is in flight before the first one is needed
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) {
+      held[rr] = (okx && rr < nr) ? __ldg(p) : (TIN)0;
+      p += nx;
+    }
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) s_in[rr][threadIdx.x] = to_float(held[rr]);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,16 +214,24 @@ __global__ void __launch_bounds__(32 * NW) conv_x_kernel(const TIN *__restrict__
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int ht = jj - (R - 1 - r);
-      if (ht >= 0 && ht < NHMAX) acc[r] = fmaf(t.w[ht], v, acc[r]);
+      if (ht >= 0 && ht < NHMAX && (ht < NHMIN || ht < nh)) acc[r] = fmaf(t.w[ht], v, acc[r]);
     }
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) s_out[lane][warp * R + r] = acc[r];
   __syncthreads();
-  for (int i = threadIdx.x; i < 32 * XW; i += 32 * NW) {
-    const int rr = i / XW, c = i - rr * XW;
-    const long long row = row0 + rr;
-    if (row < nrows && x0 + c < nx) out[(size_t)row * nx + x0 + c] = s_out[rr][c];
+  {  // a thread per output column and every (256 / XW)-th row
+    const int c = threadIdx.x % XW, g = threadIdx.x / XW;
+    constexpr int G = 32 * NW / XW;
+    static_assert(32 % G == 0, "rows split evenly");
+    if (x0 + c < nx) {
+      float *o = out + (size_t)(row0 + g) * nx + x0 + c;
+#pragma unroll 8
+      for (int rr = g; rr < 32; rr += G) {
+        if (row0 + rr < nrows) *o = s_out[rr][c];
+        o += (size_t)G * nx;
+      }
+    }
   }
 }
 
@@ -151,12 +259,17 @@ __global__ void __launch_bounds__(256) conv_xy_fused_kernel(const TIN *__restric
   const int nstepsx = R + nhx - 1;
   for (int round = 0; round < 2; ++round) {
     if (round) __syncthreads();  // everyone is done reading s_in
-    for (int i = threadIdx.x; i < 32 * TW; i += 256) {
-      const int rr = i / TW, c = i - rr * TW;
-      const int qx = qxbase + c, qy = qybase + round * 32 + rr;
-      float v = 0.f;
-      if (qy >= 0 && qy < ny && qx >= 0 && qx < nx) v = (float)in[slice + (size_t)qy * nx + qx];
-      s_in[rr][c] = v;
+    if (threadIdx.x < TW) {  // a thread per tile column, walking down the 32 rows of this round
+      const int qx = qxbase + (int)threadIdx.x;
+      const bool okx = qx >= 0 && qx < nx;
+      const int qy0 = qybase + round * 32;
+      const TIN *p = in + slice + (long long)qy0 * nx + (okx ? qx : 0);  // only dereferenced for rows inside the slice
+#pragma unroll 8
+      for (int rr = 0; rr < 32; ++rr) {
+        const int qy = qy0 + rr;
+        s_in[rr][threadIdx.x] = (okx && qy >= 0 && qy < ny) ? to_float((typename Held<TIN>::type)__ldg(p)) : 0.f;
+        p += nx;
+      }
     }
     __syncthreads();
     float acc[R];
@@ -170,7 +283,7 @@ __global__ void __launch_bounds__(256) conv_xy_fused_kernel(const TIN *__restric
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int ht = jj - (R - 1 - r);
-        if (ht >= 0 && ht < NHMAX) acc[r] = fmaf(tx.w[ht], v, acc[r]);
+        if (ht >= 0 && ht < NHMAX && (ht < NHMIN || ht < nhx)) acc[r] = fmaf(tx.w[ht], v, acc[r]);
       }
     }
 #pragma unroll
@@ -191,14 +304,16 @@ __global__ void __launch_bounds__(256) conv_xy_fused_kernel(const TIN *__restric
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
       const int ht = jj - (RY - 1 - r);
-      if (ht >= 0 && ht < NHMAX) acc[r] = fmaf(ty.w[ht], v, acc[r]);
+      if (ht >= 0 && ht < NHMAX && (ht < NHMIN || ht < nhy)) acc[r] = fmaf(ty.w[ht], v, acc[r]);
     }
   }
   if (x0 + c < nx) {
+    const int ya = y0 + hchunk * RY;
+    float *o = out + slice + (size_t)ya * nx + x0 + c;
 #pragma unroll
     for (int r = 0; r < RY; ++r) {
-      const int y = y0 + hchunk * RY + r;
-      if (y < ny) out[slice + (size_t)y * nx + x0 + c] = acc[r];
+      if (ya + r < ny) *o = acc[r];
+      o += nx;
     }
   }
 }
@@ -221,6 +336,9 @@ __global__ void __launch_bounds__(256) conv_generic_kernel(const TIN *__restrict
   out[base + (size_t)p * sa] = res;
 }
 
+int filter_axis_wide = 1;  // columns per thread of the y / z passes where the row length allows it: 1, 2 or 4 (tuning; measured: 1 is
+                            // fastest -- the wider variants hold too few warps to hide the load latency)
+
 static const int FILT_SIZES[] = {3, 7, 11, 15, 19, 23, 27, 31, 35, 39, 47, 63};
 
 static int pick_size(int nh) {
@@ -232,6 +350,17 @@ static int pick_size(int nh) {
 template <int NHMAX, int NHMIN>
 static void launch_axis_n(const float *in, float *out, int nx, int na, int no, size_t sa, size_t so, int nh,
                           const FilterTaps &t, cudaStream_t st) {
+  constexpr int RW = 16;
+  if (filter_axis_wide == 4 && nx % 4 == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
+    dim3 grid((nx + 511) / 512, (na + RW - 1) / RW, no);
+    conv_axisw_kernel<NHMAX, NHMIN, RW, 4><<<grid, 128, 0, st>>>(in, out, nx, na, sa, so, nh, t);
+    return;
+  }
+  if (filter_axis_wide == 2 && nx % 2 == 0 && (((uintptr_t)in | (uintptr_t)out) & 7) == 0) {
+    dim3 grid((nx + 255) / 256, (na + RW - 1) / RW, no);
+    conv_axisw_kernel<NHMAX, NHMIN, RW, 2><<<grid, 128, 0, st>>>(in, out, nx, na, sa, so, nh, t);
+    return;
+  }
   constexpr int R = 16;
   dim3 grid((nx + 127) / 128, (na + R - 1) / R, no);
   conv_axis_kernel<NHMAX, NHMIN, R><<<grid, 128, 0, st>>>(in, out, nx, na, sa, so, nh, t);
@@ -240,7 +369,7 @@ static void launch_axis_n(const float *in, float *out, int nx, int na, int no, s
 template <typename TIN, int NHMAX, int NHMIN>
 static void launch_x_n(const TIN *in, float *out, int nx, long long nrows, int nh, const FilterTaps &t, cudaStream_t st) {
   constexpr int R = 16, NW = 8;
-  dim3 grid((unsigned)((nrows + 31) / 32), (nx + NW * R - 1) / (NW * R));
+  dim3 grid((unsigned)(((nrows + 31) / 32) * ((nx + NW * R - 1) / (NW * R))));
   conv_x_kernel<TIN, NHMAX, NHMIN, R, NW><<<grid, 32 * NW, 0, st>>>(in, out, nx, nrows, nh, t);
 }
 
@@ -272,7 +401,8 @@ cudaError_t launch_filter_axis(const float *in, float *out, int nx, int ny, int 
                                const float *d_taps, cudaStream_t st) {
   const int na = axis == 1 ? ny : nz, no = axis == 1 ? nz : ny;
   const size_t sa = axis == 1 ? (size_t)nx : (size_t)nx * ny, so = axis == 1 ? (size_t)nx * ny : (size_t)nx;
-  const int size = pick_size(nh);
+  int size = pick_size(nh);
+  if (sa * sizeof(float) > 0xffffffffull) size = 0;  // the unrolled kernel steps with a 32-bit byte stride
   if (size == 0) {
     // grid y / z limits (65535) cannot be hit by volumes that fit a texture (<= 16384 per axis)
     dim3 grid((nx + 255) / 256, na, no);
@@ -383,7 +513,8 @@ struct spv_filter {
   const void *cur = nullptr;  // what the next convolution reads: the loaded volume or the last result
   int cur_dtype = 0;          // SPV_F32 / SPV_U16 / SPV_U8
   bool have_result = false, timed = false;
-  int fuse_xy = 1;  // x and y pass in one kernel where the tap counts allow it (spv_filter_set_tuning knob 0)
+  int fuse_xy = 1;  // x and y pass in one kernel: 0 = never, 1 = where it pays (see spv_filter_convolve_sep3), 2 = wherever the
+                    // tap counts allow it (spv_filter_set_tuning knob 0)
   unsigned long long launches = 0;
   std::string err;
 };
@@ -517,7 +648,10 @@ SPV_API int spv_filter_convolve_sep3(spv_filter *f, const float *hx, int nhx, co
   }
   const int i = f->cur == f->buf[0] ? 1 : 0;  // x: cur -> buf[i], y: buf[i] -> buf[1-i], z: buf[1-i] -> buf[i]
   FCU(cudaEventRecord(f->ev0, f->stream));
-  if (f->fuse_xy && filter_xy_fusable(nhx, nhy)) {  // x + y in one kernel: cur -> buf[i], then z: buf[i] -> buf[1-i]
+  // measured on B200 (profiles/r01_exp_blur.txt): the fused kernel wins for integer sources up to 27 taps (it reads 1 or 2
+  // bytes per voxel instead of writing and re-reading 4); float32 sources and longer kernels are faster as three passes
+  const bool fuse = f->fuse_xy == 2 || (f->fuse_xy == 1 && f->cur_dtype != SPV_F32 && nhx <= 27 && nhy <= 27);
+  if (fuse && filter_xy_fusable(nhx, nhy)) {  // x + y in one kernel: cur -> buf[i], then z: buf[i] -> buf[1-i]
     const int j = i;  // buf[i] is not the source
     FCU(launch_filter_xy(f->cur, f->cur_dtype, f->buf[j], f->nx, f->ny, f->nz, hx, nhx, hy, nhy, f->stream));
     FCU(launch_filter_axis(f->buf[j], f->buf[1 - j], f->nx, f->ny, f->nz, 2, hz, nhz, f->d_taps + 2 * FILT_LONG_TAPS, f->stream));
@@ -574,10 +708,12 @@ SPV_API int spv_filter_last_ms(spv_filter *f, float *ms) {
   return 0;
 }
 
-/* knob 0: 1 = x and y pass in one kernel where the tap counts allow it (default), 0 = always three passes */
+/* knob 0: x and y pass in one kernel: 0 = never, 1 = where it pays (default), 2 = wherever the tap counts allow it;
+ * knob 1: columns per thread of the y / z passes where the row length allows it: 1, 2 or 4 */
 SPV_API int spv_filter_set_tuning(spv_filter *f, int knob, int value) {
   FBIND();
-  if (knob == 0) f->fuse_xy = value != 0;
+  if (knob == 0) f->fuse_xy = value < 0 ? 0 : (value > 2 ? 2 : value);
+  else if (knob == 1) filter_axis_wide = value == 4 ? 4 : (value == 2 ? 2 : 1);  // process-wide
   else return ffail(f, SPV_EINVAL, "spv_filter_set_tuning: unknown knob");
   return 0;
 }
