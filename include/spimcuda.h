@@ -266,9 +266,10 @@ SPV_API int spv_filter_result_device(spv_filter *f, float **dev);
 SPV_API int spv_filter_read(spv_filter *f, float *host_dst, size_t n);
 SPV_API int spv_filter_last_ms(spv_filter *f, float *ms);  /* device time of the last convolution (three passes) */
 SPV_API const char *spv_filter_last_error(spv_filter *f);  /* f may be NULL: last create error */
-/* knob 0: the x and y pass run as one kernel (possible where both tap counts fall into the same size class of at most
- * 31 taps): 0 = never, 1 = where it is faster (integer sources, at most 27 taps; default), 2 = wherever possible; knob 1: columns per thread of the y / z passes where the row
- * length allows it (1, 2 or 4; process-wide); results are identical */
+/* knob 0: 1 = the x and y pass run as one kernel where both tap counts fall into the same size class of at most 31
+ * taps (one float32 round trip of the volume less; measured slower than the three passes so far), 0 = three passes
+ * (default); knob 1: variant of the y / z passes (process-wide): 1 = automatic,
+ * 16 / 32 = outputs per thread, 2 / 4 = columns per thread where the row length allows it; results are identical */
 SPV_API int spv_filter_set_tuning(spv_filter *f, int knob, int value);
 SPV_API int spv_filter_launch_count(spv_filter *f, unsigned long long *n);  /* kernels launched by this filter so far */
 

@@ -383,22 +383,6 @@ static Volume volume_of(const spv_ctx *c) {
 }
 
 // Copy n bytes with a few host threads (one thread saturates neither the memory system nor a PCIe 5 link).
-static void parallel_memcpy(void *dst, const void *src, size_t n) {
-  const unsigned hw = std::thread::hardware_concurrency();
-  int T = n >= ((size_t)8 << 20) ? (hw >= 16 ? 8 : (hw >= 8 ? 4 : 2)) : 1;
-  const size_t part = ((n / T) + 4095) & ~(size_t)4095;
-  std::thread th[8];
-  int started = 0;
-  for (int t = 1; t < T; ++t) {
-    const size_t off = (size_t)t * part;
-    if (off >= n) break;
-    const size_t len = n - off < part ? n - off : part;
-    th[started++] = std::thread([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
-  }
-  memcpy(dst, src, n < part ? n : part);
-  for (int t = 0; t < started; ++t) th[t].join();
-}
-
 enum { SRC_DEVICE = 0, SRC_PINNED = 1, SRC_PAGEABLE = 2 };
 
 // Fill the resident array from `src` (C-order, local_nz slices) -- the ingest path (replaces OCLImage.write_array,

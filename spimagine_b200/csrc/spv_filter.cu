@@ -23,7 +23,10 @@
 //   conv_axis_kernel  y and z passes: lanes along x (coalesced), the line runs along the strided axis
 //   conv_x_kernel     x pass: 32 lines x (XW + Nh - 1) inputs staged in shared memory (odd pitch: a lane per line
 //                     reads conflict-free), results staged back for coalesced stores; reads the source element type
+#include <string.h>
+
 #include <string>
+#include <thread>
 
 #include "spimcuda.h"
 #include "spv_kernels.h"
@@ -176,21 +179,49 @@ __device__ __forceinline__ float to_float(float v) { return v; }
 // consecutive rows x XW = NW * R outputs.  grid = ceil(nx / XW) * ceil(nrows / 32), x tiles fastest.
 template <typename TIN, int NHMAX, int NHMIN, int R, int NW>
 __global__ void __launch_bounds__(32 * NW) conv_x_kernel(const TIN *__restrict__ in, float *__restrict__ out, int nx,
-                                                         long long nrows, int nh, const FilterTaps t) {
-  constexpr int XW = NW * R, TW = XW + NHMAX - 1, PITCH = TW | 1, OPITCH = XW | 1;
+                                                         long long nrows, int nh, const FilterTaps t, int words) {
+  constexpr int E = 4 / (int)sizeof(TIN);  // voxels per 32-bit word
+  constexpr int XW = NW * R, TW = XW + NHMAX - 1, PITCH = (TW + E - 1) | 1, OPITCH = XW | 1;
   __shared__ float s_in[32][PITCH];
   __shared__ float s_out[32][OPITCH];
   const unsigned ntx = (unsigned)((nx + XW - 1) / XW);  // x tiles are dealt fastest: concurrent CTAs read whole rows
   const int x0 = (int)(blockIdx.x % ntx) * XW;
   const long long row0 = (long long)(blockIdx.x / ntx) * 32;
   const int half = nh / 2;
-  const int qbase = x0 + half - (NHMAX - 1);  // input position of tile column 0
-  static_assert(TW <= 32 * NW, "one thread per tile column");
-  if (threadIdx.x < TW) {  // a thread per tile column, walking down the 32 rows (coalesced across the warp)
+  const int qbase = x0 + half - (NHMAX - 1);  // input position of the first tile column the taps read
+  static_assert(TW + E - 1 <= 32 * NW, "one thread per tile column");
+  const int nr = nrows - row0 < 32 ? (int)(nrows - row0) : 32;
+  int shift = 0;  // tile column 0 holds position qbase - shift
+  if (E > 1 && words) {
+    // uint8 / uint16 rows whose pitch and base are multiples of 4 bytes: a thread loads whole 32-bit words (E voxels),
+    // so that a warp reads full 128-byte lines like the float32 path; a word lies entirely inside or outside a row
+    shift = ((qbase % E) + E) % E;
+    const int qa = qbase - shift;  // multiple of E
+    constexpr int NWORDS = (TW + 2 * (E - 1)) / E;
+    if (threadIdx.x < NWORDS) {
+      const int q = qa + (int)threadIdx.x * E;
+      const bool okx = q >= 0 && q < nx;
+      const unsigned *p = reinterpret_cast<const unsigned *>(in + (size_t)row0 * nx + (okx ? q : 0));
+      const size_t pitch_words = (size_t)nx / E;
+      unsigned held[32];
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) {
+        held[rr] = (okx && rr < nr) ? __ldg(p) : 0u;
+        p += pitch_words;
+      }
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr)
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          const int c = (int)threadIdx.x * E + k;
+          constexpr unsigned BITS = (8u * sizeof(TIN)) & 31u;  // 8 or 16 here (0 for float32: branch not taken)
+          if (c < PITCH) s_in[rr][c] = to_float((held[rr] >> (BITS * k)) & ((1u << BITS) - 1u));
+        }
+    }
+  } else if (threadIdx.x < TW) {  // a thread per tile column, walking down the 32 rows (coalesced across the warp)
     const int q = qbase + (int)threadIdx.x;
     const bool okx = q >= 0 && q < nx;
     const TIN *p = in + (size_t)row0 * nx + (okx ? q : 0);
-    const int nr = nrows - row0 < 32 ? (int)(nrows - row0) : 32;
     typename Held<TIN>::type held[32];  // every load of the column is in flight before the first one is needed
 #pragma unroll
     for (int rr = 0; rr < 32; ++rr) {
@@ -206,7 +237,7 @@ __global__ void __launch_bounds__(32 * NW) conv_x_kernel(const TIN *__restrict__
   float acc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = 0.f;
-  const float *line = s_in[lane] + warp * R + R - 1 + NHMAX - 1;  // column of the position met first
+  const float *line = s_in[lane] + shift + warp * R + R - 1 + NHMAX - 1;  // column of the position met first
 #pragma unroll
   for (int jj = 0; jj < R + NHMAX - 1; ++jj) {
     float v = line[-jj];
@@ -244,8 +275,10 @@ __global__ void __launch_bounds__(32 * NW) conv_x_kernel(const TIN *__restrict__
 // volume are zeros as the dropped taps of the y pass require.  Saves one float32 write + read of the volume.
 template <typename TIN, int NHMAX, int NHMIN>
 __global__ void __launch_bounds__(256) conv_xy_fused_kernel(const TIN *__restrict__ in, float *__restrict__ out, int nx, int ny,
-                                                            int nhx, int nhy, const FilterTaps tx, const FilterTaps ty) {
-  constexpr int R = 16, NW = 8, XW = NW * R, TW = XW + NHMAX - 1, PITCH = TW | 1, MP = XW + 1;
+                                                            int nhx, int nhy, const FilterTaps tx, const FilterTaps ty,
+                                                            int words) {
+  constexpr int E = 4 / (int)sizeof(TIN);  // voxels per 32-bit word
+  constexpr int R = 16, NW = 8, XW = NW * R, TW = XW + NHMAX - 1, PITCH = (TW + E - 1) | 1, MP = XW + 1;
   constexpr int YT = 65 - NHMAX, RY = YT / 2;
   extern __shared__ float smem[];
   float(*s_in)[PITCH] = reinterpret_cast<float(*)[PITCH]>(smem);             // [32][PITCH]
@@ -257,12 +290,33 @@ __global__ void __launch_bounds__(256) conv_xy_fused_kernel(const TIN *__restric
   const int qybase = y0 + halfy - (NHMAX - 1);  // y position of tile row 0
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nstepsx = R + nhx - 1;
+  const int shift = (E > 1 && words) ? ((qxbase % E) + E) % E : 0;  // tile column 0 holds x position qxbase - shift
   for (int round = 0; round < 2; ++round) {
     if (round) __syncthreads();  // everyone is done reading s_in
-    if (threadIdx.x < TW) {  // a thread per tile column, walking down the 32 rows of this round
+    const int qy0 = qybase + round * 32;
+    if (E > 1 && words) {  // whole 32-bit words of uint8 / uint16 rows, as in conv_x_kernel
+      constexpr int NWORDS = (TW + 2 * (E - 1)) / E;
+      if (threadIdx.x < NWORDS) {
+        const int qx = qxbase - shift + (int)threadIdx.x * E;
+        const bool okx = qx >= 0 && qx < nx;
+        const unsigned *p = reinterpret_cast<const unsigned *>(in + slice + (long long)qy0 * nx + (okx ? qx : 0));
+        const long long pitch_words = nx / E;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+          const int qy = qy0 + rr;
+          const unsigned w = (okx && qy >= 0 && qy < ny) ? __ldg(p) : 0u;
+          p += pitch_words;
+#pragma unroll
+          for (int k = 0; k < E; ++k) {
+            constexpr unsigned BITS = (8u * sizeof(TIN)) & 31u;
+            const int c = (int)threadIdx.x * E + k;
+            if (c < PITCH) s_in[rr][c] = to_float((w >> (BITS * k)) & ((1u << BITS) - 1u));
+          }
+        }
+      }
+    } else if (threadIdx.x < TW) {  // a thread per tile column, walking down the 32 rows of this round
       const int qx = qxbase + (int)threadIdx.x;
       const bool okx = qx >= 0 && qx < nx;
-      const int qy0 = qybase + round * 32;
       const TIN *p = in + slice + (long long)qy0 * nx + (okx ? qx : 0);  // only dereferenced for rows inside the slice
 #pragma unroll 8
       for (int rr = 0; rr < 32; ++rr) {
@@ -275,7 +329,7 @@ __global__ void __launch_bounds__(256) conv_xy_fused_kernel(const TIN *__restric
     float acc[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.f;
-    const float *line = s_in[lane] + warp * R + R - 1 + NHMAX - 1;
+    const float *line = s_in[lane] + shift + warp * R + R - 1 + NHMAX - 1;
 #pragma unroll
     for (int jj = 0; jj < R + NHMAX - 1; ++jj) {
       float v = line[-jj];
@@ -361,6 +415,13 @@ static void launch_axis_n(const float *in, float *out, int nx, int na, int no, s
     conv_axisw_kernel<NHMAX, NHMIN, RW, 2><<<grid, 128, 0, st>>>(in, out, nx, na, sa, so, nh, t);
     return;
   }
+  // 32 outputs per thread from 11 taps up (1.56 instead of 2.1 loads per output: 3-5 % faster), 16 below
+  if (filter_axis_wide == 32 || (filter_axis_wide == 1 && NHMAX >= 11)) {
+    constexpr int R = 32;
+    dim3 grid((nx + 127) / 128, (na + R - 1) / R, no);
+    conv_axis_kernel<NHMAX, NHMIN, R><<<grid, 128, 0, st>>>(in, out, nx, na, sa, so, nh, t);
+    return;
+  }
   constexpr int R = 16;
   dim3 grid((nx + 127) / 128, (na + R - 1) / R, no);
   conv_axis_kernel<NHMAX, NHMIN, R><<<grid, 128, 0, st>>>(in, out, nx, na, sa, so, nh, t);
@@ -370,7 +431,8 @@ template <typename TIN, int NHMAX, int NHMIN>
 static void launch_x_n(const TIN *in, float *out, int nx, long long nrows, int nh, const FilterTaps &t, cudaStream_t st) {
   constexpr int R = 16, NW = 8;
   dim3 grid((unsigned)(((nrows + 31) / 32) * ((nx + NW * R - 1) / (NW * R))));
-  conv_x_kernel<TIN, NHMAX, NHMIN, R, NW><<<grid, 32 * NW, 0, st>>>(in, out, nx, nrows, nh, t);
+  const int words = sizeof(TIN) < 4 && ((size_t)nx * sizeof(TIN)) % 4 == 0 && ((uintptr_t)in & 3) == 0;
+  conv_x_kernel<TIN, NHMAX, NHMIN, R, NW><<<grid, 32 * NW, 0, st>>>(in, out, nx, nrows, nh, t, words);
 }
 
 // CALL(NHMAX, NHMIN): the instantiation for tap counts NHMIN..NHMAX
@@ -436,8 +498,9 @@ static cudaError_t filter_x_typed(const TIN *in, float *out, int nx, int ny, int
 template <typename TIN, int NHMAX, int NHMIN>
 static cudaError_t launch_xy_n(const TIN *in, float *out, int nx, int ny, int nz, int nhx, int nhy, const FilterTaps &tx,
                                const FilterTaps &ty, cudaStream_t st) {
-  constexpr int TW = 128 + NHMAX - 1, PITCH = TW | 1, YT = 65 - NHMAX;
+  constexpr int E = 4 / (int)sizeof(TIN), TW = 128 + NHMAX - 1, PITCH = (TW + E - 1) | 1, YT = 65 - NHMAX;
   const size_t smem = (size_t)(32 * PITCH + 64 * 129) * sizeof(float);
+  const int words = sizeof(TIN) < 4 && ((size_t)nx * sizeof(TIN)) % 4 == 0 && ((uintptr_t)in & 3) == 0;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_xy_fused_kernel<TIN, NHMAX, NHMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -445,7 +508,7 @@ static cudaError_t launch_xy_n(const TIN *in, float *out, int nx, int ny, int nz
     attr_set = true;
   }
   dim3 grid((nx + 127) / 128, (ny + YT - 1) / YT, nz);
-  conv_xy_fused_kernel<TIN, NHMAX, NHMIN><<<grid, 256, smem, st>>>(in, out, nx, ny, nhx, nhy, tx, ty);
+  conv_xy_fused_kernel<TIN, NHMAX, NHMIN><<<grid, 256, smem, st>>>(in, out, nx, ny, nhx, nhy, tx, ty, words);
   return cudaGetLastError();
 }
 
@@ -495,6 +558,25 @@ cudaError_t launch_filter_x(const void *in, int dtype, float *out, int nx, int n
   }
 }
 
+// memcpy on several host threads: pageable memory moves into the page-locked staging rings of the ingest paths at
+// several times the rate of one thread (shared with spv_api.cu)
+void parallel_memcpy(void *dst, const void *src, size_t n) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  int T = n >= ((size_t)8 << 20) ? (hw >= 16 ? 8 : (hw >= 8 ? 4 : 2)) : 1;
+  const size_t part = ((n / T) + 4095) & ~(size_t)4095;
+  std::thread th[8];
+  int started = 0;
+  for (int t = 1; t < T; ++t) {
+    const size_t off = (size_t)t * part;
+    if (off >= n) break;
+    const size_t len = n - off < part ? n - off : part;
+    th[started++] = std::thread([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+  }
+  memcpy(dst, src, n < part ? n : part);
+  for (int t = 0; t < started; ++t) th[t].join();
+}
+
+
 }  // namespace spv
 
 // ---- C ABI -------------------------------------------------------------------------------------------------------
@@ -509,12 +591,14 @@ struct spv_filter {
   float *buf[2] = {nullptr, nullptr};
   size_t buf_cap = 0;      // floats per buffer
   float *d_taps = nullptr; // 3 x FILT_LONG_TAPS, for tap counts beyond the unrolled instantiations
+  char *h_ring = nullptr;  // 2 x 32 MiB page-locked staging for pageable host sources
+  cudaEvent_t ev_ring[2] = {nullptr, nullptr};
   int nx = 0, ny = 0, nz = 0;
   const void *cur = nullptr;  // what the next convolution reads: the loaded volume or the last result
   int cur_dtype = 0;          // SPV_F32 / SPV_U16 / SPV_U8
   bool have_result = false, timed = false;
-  int fuse_xy = 1;  // x and y pass in one kernel: 0 = never, 1 = where it pays (see spv_filter_convolve_sep3), 2 = wherever the
-                    // tap counts allow it (spv_filter_set_tuning knob 0)
+  int fuse_xy = 0;  // x and y pass in one kernel wherever the tap counts allow it (spv_filter_set_tuning knob 0; off: see
+                    // spv_filter_convolve_sep3)
   unsigned long long launches = 0;
   std::string err;
 };
@@ -571,6 +655,9 @@ SPV_API int spv_filter_destroy(spv_filter *f) {
   for (int i = 0; i < 2; ++i)
     if (f->buf[i]) cudaFree(f->buf[i]);
   if (f->d_taps) cudaFree(f->d_taps);
+  if (f->h_ring) cudaFreeHost(f->h_ring);
+  for (int i = 0; i < 2; ++i)
+    if (f->ev_ring[i]) cudaEventDestroy(f->ev_ring[i]);
   if (f->ev0) cudaEventDestroy(f->ev0);
   if (f->ev1) cudaEventDestroy(f->ev1);
   if (f->stream) cudaStreamDestroy(f->stream);
@@ -621,7 +708,35 @@ SPV_API int spv_filter_load(spv_filter *f, const void *src, int on_device, int s
     f->cur_dtype = native;
     return 0;
   }
-  FCU(cudaMemcpyAsync(f->d_src, src, n * es, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, f->stream));
+  if (on_device) {
+    FCU(cudaMemcpyAsync(f->d_src, src, n * es, cudaMemcpyDeviceToDevice, f->stream));
+  } else {
+    cudaPointerAttributes at;
+    cudaError_t pe = cudaPointerGetAttributes(&at, src);
+    if (pe != cudaSuccess) cudaGetLastError();
+    if (pe == cudaSuccess && at.type == cudaMemoryTypeHost) {  // page-locked: the DMA engine reads it at PCIe rate
+      FCU(cudaMemcpyAsync(f->d_src, src, n * es, cudaMemcpyHostToDevice, f->stream));
+    } else {
+      // pageable memory: host threads copy chunk i+1 into a page-locked ring while chunk i is on the PCIe link (the
+      // ingest pipeline of spv_set_volume; a plain cudaMemcpy from pageable memory runs at a third of this rate)
+      const size_t chunk = (size_t)32 << 20;
+      if (!f->h_ring) {
+        FCU(cudaMallocHost(&f->h_ring, 2 * chunk));
+        FCU(cudaEventCreateWithFlags(&f->ev_ring[0], cudaEventDisableTiming));
+        FCU(cudaEventCreateWithFlags(&f->ev_ring[1], cudaEventDisableTiming));
+      }
+      const size_t total = n * es;
+      int i = 0;
+      for (size_t off = 0; off < total; off += chunk, ++i) {
+        const size_t len = total - off < chunk ? total - off : chunk;
+        const int h = i & 1;
+        if (i >= 2) FCU(cudaEventSynchronize(f->ev_ring[h]));  // the DMA that last read this half
+        parallel_memcpy(f->h_ring + (size_t)h * chunk, (const char *)src + off, len);
+        FCU(cudaMemcpyAsync((char *)f->d_src + off, f->h_ring + (size_t)h * chunk, len, cudaMemcpyHostToDevice, f->stream));
+        FCU(cudaEventRecord(f->ev_ring[h], f->stream));
+      }
+    }
+  }
   if (native >= 0) {
     f->cur = f->d_src;
     f->cur_dtype = native;
@@ -648,9 +763,10 @@ SPV_API int spv_filter_convolve_sep3(spv_filter *f, const float *hx, int nhx, co
   }
   const int i = f->cur == f->buf[0] ? 1 : 0;  // x: cur -> buf[i], y: buf[i] -> buf[1-i], z: buf[1-i] -> buf[i]
   FCU(cudaEventRecord(f->ev0, f->stream));
-  // measured on B200 (profiles/r01_exp_blur.txt): the fused kernel wins for integer sources up to 27 taps (it reads 1 or 2
-  // bytes per voxel instead of writing and re-reading 4); float32 sources and longer kernels are faster as three passes
-  const bool fuse = f->fuse_xy == 2 || (f->fuse_xy == 1 && f->cur_dtype != SPV_F32 && nhx <= 27 && nhy <= 27);
+  // measured on B200 (profiles/r01_exp_blur.txt): the three passes each run at 65-80 % of the HBM copy rate; the fused
+  // kernel saves a float32 round trip of the volume but is instruction-bound (39 % more x-pass FMAs, two barriers per
+  // tile) and does not beat them yet -- opt-in
+  const bool fuse = f->fuse_xy != 0;
   if (fuse && filter_xy_fusable(nhx, nhy)) {  // x + y in one kernel: cur -> buf[i], then z: buf[i] -> buf[1-i]
     const int j = i;  // buf[i] is not the source
     FCU(launch_filter_xy(f->cur, f->cur_dtype, f->buf[j], f->nx, f->ny, f->nz, hx, nhx, hy, nhy, f->stream));
@@ -708,12 +824,13 @@ SPV_API int spv_filter_last_ms(spv_filter *f, float *ms) {
   return 0;
 }
 
-/* knob 0: x and y pass in one kernel: 0 = never, 1 = where it pays (default), 2 = wherever the tap counts allow it;
- * knob 1: columns per thread of the y / z passes where the row length allows it: 1, 2 or 4 */
+/* knob 0: x and y pass in one kernel wherever the tap counts allow it (default 0: three passes);
+ * knob 1: the y / z pass variant: 1 = automatic (one column per thread, 16 or 32 outputs), 16 / 32 = outputs per thread,
+ * 2 / 4 = columns per thread where the row length allows it */
 SPV_API int spv_filter_set_tuning(spv_filter *f, int knob, int value) {
   FBIND();
-  if (knob == 0) f->fuse_xy = value < 0 ? 0 : (value > 2 ? 2 : value);
-  else if (knob == 1) filter_axis_wide = value == 4 ? 4 : (value == 2 ? 2 : 1);  // process-wide
+  if (knob == 0) f->fuse_xy = value != 0;
+  else if (knob == 1) filter_axis_wide = (value == 4 || value == 2 || value == 32 || value == 16) ? value : 1;  // process-wide
   else return ffail(f, SPV_EINVAL, "spv_filter_set_tuning: unknown knob");
   return 0;
 }

@@ -155,6 +155,7 @@ cudaError_t launch_convert(const void *src, void *dst, int src_type, int dtype, 
 // models/imageprocessor.py:47-71).  h: host taps; d_taps: the same taps in device memory (used for nh > FILTER_MAX_TAPS)
 constexpr int FILTER_MAX_TAPS = 63;
 struct FilterTaps { float w[FILTER_MAX_TAPS + 1]; };
+void parallel_memcpy(void *dst, const void *src, size_t n);  // several host threads (spv_filter.cu)
 cudaError_t launch_filter_x(const void *in, int dtype, float *out, int nx, int ny, int nz, const float *h, int nh,
                             const float *d_taps, cudaStream_t st);
 cudaError_t launch_filter_axis(const float *in, float *out, int nx, int ny, int nz, int axis, const float *h, int nh,

@@ -87,8 +87,8 @@ class VolumeFilter(object):
         self._check(self._lib.spv_filter_sync(self._f))
 
     def set_tuning(self, knob, value):
-        """knob 0: x and y pass as one kernel: 0 never, 1 where it is faster (default), 2 wherever the tap counts allow
-        it; knob 1: columns per thread of the y / z passes (1, 2 or 4)"""
+        """knob 0: x and y pass as one kernel where the tap counts allow it (default 0: three passes);
+        knob 1: columns per thread of the y / z passes (1, 2 or 4; default 1)"""
         self._check(self._lib.spv_filter_set_tuning(self._f, int(knob), int(value)))
 
     def launch_count(self):
