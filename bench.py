@@ -142,9 +142,23 @@ class ClockSampler(object):
                 "samples": len(sm)}
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms are meant to use every host core (the other
+    ranks of the reference arm exit at once, and the GPU arm's host work is negligible).  libgomp is process-global:
+    setting the count through it reaches the oracle libraries, which link the same runtime."""
+    import ctypes
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+    return n
+
+
 def cpu_reference(vol, cams, img, steps, warmup, budget_s, report_all):
     """Time the reference kernels on the host cores.  -> dict(fps, gsamples, kind, cores, sample, ms_per_step)"""
     from oracle import oracle
+    use_all_host_threads()
     kind = "reference" if oracle.available("reference") else "port"
     r = oracle.OracleRenderer((img, img), kind=kind, max_steps=MAX_STEPS)
     r.set_data(vol)
@@ -553,6 +567,7 @@ def run_blur(args, rank, local_rank, world):
     # CPU restatement on all host cores, a bounded sample of the same workload
     cb = min(N, 256)
     sample = np.ascontiguousarray(vol[:cb, :cb, :cb])
+    use_all_host_threads()
     forc.convolve_sep3(sample[:32], *taps)
     t0 = time.perf_counter()
     forc.convolve_sep3(sample, *taps)
@@ -584,7 +599,7 @@ def run_blur(args, rank, local_rank, world):
                      "algorithmic_bytes_per_step": alg, "bytes_moved_by_the_three_passes": moved,
                      "frac_of_moved_bytes": moved / (dev_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                      "kernel": "spv::conv_x_kernel<u16,19> + 2 x spv::conv_axis_kernel<19> (y, z), timed together"},
-        "cpu_baseline": {"value": 1. / t_cpu, "unit": "volumes/s", "cores": os.cpu_count(), "kind": "port",
+        "cpu_baseline": {"value": 1. / t_cpu, "unit": "volumes/s", "cores": use_all_host_threads(), "kind": "port",
                          "sample": "one %d^3 corner block of the volume through oracle/filter_oracle.c (OpenMP, all host "
                                    "cores), time scaled by (%d/%d)^3" % (cb, N, cb)}}))
     rend.close()
