@@ -11,8 +11,9 @@ at PCIe rate without staging.  The reference reads every time point into fresh p
 GUI thread or a Qt thread and re-uploads it synchronously (gui/glwidget.py:372-374).
 
 Only containers whose bytes are laid out as the renderer wants them (C-order stacks of one element type) are
-rebuilt here; the TIFF / CZI readers of the reference decode through third-party libraries (tifffile, czifile) and
-can be wrapped in NumpyData or any object with the same protocol.
+rebuilt here: raw files, SpimData folders and uncompressed TIFF stacks (TiffData over utils/tiffio.py).  Compressed
+TIFF and CZI decode through third-party libraries in the reference (tifffile, czifile); their arrays can be wrapped
+in NumpyData or any object with the same protocol.
 """
 from __future__ import absolute_import, print_function
 
@@ -182,6 +183,53 @@ class RawData(GenericData):
     def __getitem__(self, pos):
         if self.stackSize and self.fName:
             return self.data[pos]
+        return None
+
+
+class TiffData(GenericData):
+    """2/3/4d tiff data (data_model.py:178-218).  The reference decodes the whole file into memory with tifffile;
+    here only the page directory is parsed (utils/tiffio.py: uncompressed strips, classic / BigTIFF, ImageJ
+    hyperstacks) and a time point is read from the file when it is asked for -- by FrameSource straight into a
+    page-locked buffer.  Big-endian files are byte-swapped after the read."""
+
+    def __init__(self, fName=""):
+        GenericData.__init__(self, fName)
+        self.load(fName)
+
+    def load(self, fName, stackUnits=[1., 1., 1.]):
+        if fName:
+            from .utils.tiffio import TiffFile
+            try:
+                tif = TiffFile(fName)
+                # np.squeeze of the leading axes as in the reference: (1, Y, X) is one slice, (T, 1, Y, X) one volume
+                shape = tuple(s for s in tif.shape[:-2] if s != 1) + tuple(tif.shape[-2:])
+                self.stackSize = (1,) * (4 - len(shape)) + shape
+            except Exception as e:
+                print(e)
+                self.fName = ""
+                raise Exception("couldnt open %s as TiffData (%s)" % (fName, str(e)))
+            self._tif = tif
+            self.stackUnits = stackUnits
+            self.fName = fName
+
+    @property
+    def dtype(self):
+        return self._tif.dtype.newbyteorder("=")
+
+    def read_into(self, pos, out):
+        if pos < 0 or pos >= self.stackSize[0]:
+            raise IndexError("0 <= pos <= %i, but pos = %i" % (self.stackSize[0] - 1, pos))
+        nz = self.stackSize[1]
+        raw = out.view(self._tif.dtype) if out.dtype.itemsize > 1 else out
+        self._tif.read_into(raw, first=int(pos) * nz, count=nz)
+        if not self._tif.dtype.isnative:
+            out.byteswap(inplace=True)
+
+    def __getitem__(self, pos):
+        if self.stackSize and self.fName:
+            out = np.empty(self.stackSize[1:], self.dtype)
+            self.read_into(pos, out)
+            return out
         return None
 
 
