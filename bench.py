@@ -56,13 +56,15 @@ def parse():
     ap.add_argument("--vol", type=int, default=VOL_N)
     ap.add_argument("--img", type=int, default=IMG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="sweep", choices=["sweep", "slab", "timelapse", "iso", "blur"],
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "slab", "timelapse", "iso", "blur", "keyframes"],
                     help="sweep: BASELINE configs[1], frames sharded over the GPUs (default). slab: configs[3], one "
                          "--vol^3 uint16 volume split into z-slabs over the GPUs, sort-last max composite. timelapse: "
                          "configs[4], --frames time points of --tl-shape uint16, time point t on GPU t mod N. iso: "
                          "configs[2], --vol^3 uint16 iso_surface with ambient occlusion and shading; N > 1: sort-last. "
                          "blur: SURVEY 8f-4, BlurProcessor(sigma=4) on a --vol^3 uint16 volume into the renderer's resident "
-                         "array (one GPU)")
+                         "array (one GPU). keyframes: SURVEY 8f-3, the GUI's record loop over a keyframe path (max projection "
+                         "and iso-surface stretches) on a --vol^3 uint16 volume, pipelined against the reference-shaped "
+                         "synchronous loop, plus the TIFF time-point reader (one GPU)")
     ap.add_argument("--frames", type=int, default=100, help="timelapse workload: time points in the whole series")
     ap.add_argument("--tl-shape", default="512,1024,1024", help="timelapse workload: (Nz,Ny,Nx) of one time point")
     ap.add_argument("--skip", action="store_true", help="enable empty-space skipping on the min/max brick grid")
@@ -606,6 +608,120 @@ def run_blur(args, rank, local_rank, world):
     vf.close()
 
 
+def run_keyframes(args, rank, local_rank, world):
+    """the record loop of the keyframe panel (gui/keyframe_view.py:644-653 -> GLWidget.render,
+    gui/glwidget.py:610-636) over a path with max-projection and iso-surface stretches on a --vol^3 uint16 volume.
+    value: frames/s of keyframes.render_keyframes (every frame lands in pinned host memory; frame i+1 renders while
+    frame i is read back); beside it the reference-shaped loop (apply the transform, render(), blocking read-back)
+    with the same kernels.  Also times frames.TiffData.read_into (a time point from an uncompressed TIFF straight
+    into page-locked memory) against np.fromfile of the same bytes."""
+    import tempfile
+    import torch
+    import scenes
+    from spimagine_b200 import VolumeRenderer, frames, keyframes as kf, pinned_empty
+    from spimagine_b200.utils import tiffio
+    from spimagine_b200.utils.quaternion import Quaternion
+
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"metric": "keyframes", "unavailable": "the keyframes workload is single-GPU (replicas only)"}))
+        return
+    torch.cuda.set_device(local_rank)
+    N, W = args.vol, args.img
+    n_frames = max(8, min(args.steps, 720))
+    vol = scenes.vol_g(N, np.uint16, seed=0)
+    keys = kf.KeyFrameList()
+    keys.addItem(kf.KeyFrame(0., kf.TransformData(quatRot=Quaternion(1, 0, 0, 0), zoom=1., maxVal=PEAK_VALUE)))
+    keys.addItem(kf.KeyFrame(.35, kf.TransformData(quatRot=Quaternion(.6, .2, .7, .1), zoom=1.25, maxVal=PEAK_VALUE * .7,
+                                                  gamma=.8), 2.))
+    keys.addItem(kf.KeyFrame(.6, kf.TransformData(quatRot=Quaternion(.1, .9, -.3, .2), zoom=.9, maxVal=PEAK_VALUE,
+                                                 isIso=True)))
+    keys.addItem(kf.KeyFrame(.8, kf.TransformData(quatRot=Quaternion(-.3, .5, .6, .4), zoom=1.1, maxVal=PEAK_VALUE,
+                                                 bounds=[-.8, .8, -1, 1, -1, 1])))
+    keys.addItem(kf.KeyFrame(1., kf.TransformData(quatRot=Quaternion(0, 0, 1, 0), zoom=1., maxVal=PEAK_VALUE)))
+    rend = VolumeRenderer((W, W), device=local_rank, max_steps=MAX_STEPS, pinned_outputs=True)
+    rend.set_data(vol)
+    clocks = ClockSampler(local_rank)
+
+    def pipelined():
+        acc = 0.
+        for pos, td, r in kf.render_keyframes(rend, keys, n_frames, iso_planes=2):
+            acc += float(r.output[W // 2, W // 2])
+        return acc
+
+    def synchronous():
+        acc = 0.
+        for pos, t in kf.keyframe_times(n_frames):
+            _, method = kf.apply_transform(rend, keys.getTransform(t))
+            rend.render(method=method)
+            acc += float(rend.output[W // 2, W // 2])
+        return acc
+
+    n_iso = sum(1 for _, t in kf.keyframe_times(n_frames) if keys.getTransform(t).isIso)
+    for _ in range(3):
+        pipelined()
+    synchronous()
+    clocks.start()
+    l0 = rend.launch_count()
+    t0 = time.perf_counter()
+    chk_p = pipelined()
+    t_pipe = time.perf_counter() - t0
+    launches = rend.launch_count() - l0
+    t0 = time.perf_counter()
+    chk_s = synchronous()
+    t_sync = time.perf_counter() - t0
+    clk = clocks.stop()
+    rend.close()
+
+    # the TIFF time-point reader (page cache warm: the rate is the reader's, not the disk's)
+    tmp = tempfile.mkdtemp(prefix="spv_bench_")
+    fn = os.path.join(tmp, "vol.tif")
+    tiffio.write3dTiff(vol, fn)
+    d = frames.TiffData(fn)
+    dst = pinned_empty(vol.shape, np.uint16)
+    d.read_into(0, dst)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        d.read_into(0, dst)
+    t_tif = (time.perf_counter() - t0) / 3
+    same = bool(np.array_equal(dst, vol))
+    vol.tofile(os.path.join(tmp, "vol.raw"))
+    np.fromfile(os.path.join(tmp, "vol.raw"), dtype=np.uint16)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        np.fromfile(os.path.join(tmp, "vol.raw"), dtype=np.uint16)
+    t_raw = (time.perf_counter() - t0) / 3
+    for f in ("vol.tif", "vol.raw"):
+        os.remove(os.path.join(tmp, f))
+    os.rmdir(tmp)
+    fps = n_frames / t_pipe
+    print(json.dumps({
+        "metric": "keyframe record loop frames/s, %d^3 uint16 -> %d^2 (max_project + iso_surface stretches)" % (N, W),
+        "value": fps, "unit": "frames/s", "n_gpus": 1, "steps": n_frames, "warmup": 3 * n_frames,
+        "ms_per_step": 1e3 * t_pipe / n_frames, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16->f32", "data": "synthetic",
+        "config": {"workload": "Vol-G(%d, uint16, seed 0), 5 keyframes (slerp, eased stretch, window / gamma / box "
+                               "changes, one iso_surface stretch of %d frames), %d frames at recordPos / nFrames" % (
+                                   N, n_iso, n_frames),
+                   "l2": "the %d MiB z-paired volume exceeds the 126 MB L2 and the view changes every frame" % (
+                       float(N) ** 3 * 4 / 2 ** 20)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 128,
+                "d2h_bytes_per_step": 2 * W * W * 4,
+                "note": "keyframes.render_keyframes: host interpolation of the path, setters, one render per frame, "
+                        "output + alpha of every frame read back into pinned host memory (the planes a recorded frame "
+                        "shows; iso_planes=2), two frames in flight; wall clock",
+                "synchronous_value": n_frames / t_sync,
+                "synchronous_note": "the reference's loop with the same kernels: apply the transform, render(), "
+                                    "blocking read-back per frame",
+                "checksums_agree": bool(chk_p == chk_s)},
+        "gpu_launches": int(launches), "clocks": clk,
+        "tiff_reader": {"gbytes_per_s": vol.nbytes / t_tif / 1e9, "np_fromfile_raw_gbytes_per_s": vol.nbytes / t_raw / 1e9,
+                        "bytes": int(vol.nbytes), "identical": same,
+                        "note": "frames.TiffData.read_into: one readinto per time point into page-locked memory "
+                                "(contiguous pages), page cache warm; beside it np.fromfile of the raw bytes into "
+                                "fresh pageable memory (the reference's SpimData path)"}}))
+
+
 def run_bricks(args):
     """The single-GPU-brick baseline of BASELINE configs[3]: the same slab kernels on ONE GPU, the volume cut into
     --bricks z-slabs, each rendered by its own launch one after the other (what a single GPU does when the volume
@@ -868,6 +984,8 @@ def main():
     if args.workload == "iso":
         run_iso(args, rank, local_rank, world)
         return
+    if args.workload == "keyframes":
+        return run_keyframes(args, rank, local_rank, world)
     if args.workload == "slab" and args.bricks > 0:
         if world != 1:
             raise SystemExit("--bricks is the single-GPU baseline: run it with --gpus 1")

@@ -289,7 +289,8 @@ def keyframe_times(nFrames):
     return [(k, 1. * k / nFrames) for k in range(1, nFrames + 1)]
 
 
-def render_keyframes(renderer, keyList, nFrames, source=None, isPerspective=True, pinned=False, pipelined=True):
+def render_keyframes(renderer, keyList, nFrames, source=None, isPerspective=True, pinned=False, pipelined=True,
+                     iso_planes=7):
     """Generator over (recordPos, transformData, renderer) for the nFrames frames of the record loop;
     renderer.output / output_alpha (+ the iso planes) hold that frame when it is yielded.
 
@@ -298,7 +299,9 @@ def render_keyframes(renderer, keyList, nFrames, source=None, isPerspective=True
                 whenever the interpolated dataPos changes (DataModel.setPos -> GLWidget.dataModel_changed,
                 glwidget.py:372-374), clipped to the source's length
     pinned      source[t] are page-locked arrays (asynchronous uploads)
-    pipelined   runs of frames with the same render method go through render_sequence"""
+    pipelined   runs of frames with the same render method go through render_sequence
+    iso_planes  7: every result plane of an iso-surface frame is read back; 2: only output and output_alpha (what a
+                recorded frame shows), the other planes stay on the device and read as None"""
     times = keyframe_times(nFrames)
     tds = [keyList.getTransform(t) for _, t in times]
     state = {"pos": None}
@@ -333,7 +336,7 @@ def render_keyframes(renderer, keyList, nFrames, source=None, isPerspective=True
                 yield times[k][0], tds[k], renderer
         else:
             views = (prepare(tds[k])[0] for k in range(i, j))
-            for k, r in zip(range(i, j), renderer.render_sequence(views, method=method)):
+            for k, r in zip(range(i, j), renderer.render_sequence(views, method=method, iso_planes=iso_planes)):
                 yield times[k][0], tds[k], r
         i = j
 

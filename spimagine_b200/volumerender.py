@@ -421,7 +421,7 @@ class VolumeRenderer(object):
         self.output = flat[:n].reshape(shape)
         self.output_alpha = flat[n:2 * n].reshape(shape)
         # the reference reads back buf_depth here although max_project never writes it (garbage); zeros instead
-        if self.output_depth.shape != shape:
+        if self.output_depth is None or self.output_depth.shape != shape:
             self.output_depth = np.zeros(shape, np.float32)
 
     def _render_isosurface(self, raw_only=False):
@@ -506,20 +506,25 @@ class VolumeRenderer(object):
             self._render_isosurface(raw_only=True)
 
     # ------------------------------------------------------------------ pipelined sequences (addition)
-    def render_sequence(self, modelViews, method="max_project", depth=2):
+    def render_sequence(self, modelViews, method="max_project", depth=2, iso_planes=7):
         """Generator over the frames of a camera path (a spin, a keyframe sequence): for every modelView of the
         iterable it yields `self` with output / output_alpha (and, for "iso_surface", output_depth /
         output_occlusion / output_normals) holding that frame.  Unlike calling render() per frame -- which, like
         the reference, blocks on the read-back of every frame (volumerender.py:388-390) -- frame i+1 is rendered
         while frame i is still being copied to pinned host memory (two output slots, spv_select_slot /
         spv_read_pinned_async / spv_wait_slot).  With pinned_outputs=True the yielded arrays are views of the
-        slot's staging memory and stay valid until the frame after next has been yielded; otherwise copies."""
+        slot's staging memory and stay valid until the frame after next has been yielded; otherwise copies.
+        iso_planes=2 reads back only what a display needs of an iso-surface frame (output, output_alpha: 8 of the
+        28 bytes per pixel); output_depth / output_normals / output_occlusion are None for such frames."""
         if not hasattr(self, 'dataImg'):
             print("no data provided, set_data(data) before")
             return
         if method not in ("max_project", "iso_surface"):
             raise KeyError("method = '%s' not defined, valid: ['max_project', 'iso_surface']" % method)
-        planes = 2 if method == "max_project" else 7
+        if iso_planes not in (2, 7):
+            raise ValueError("iso_planes must be 2 (output, alpha) or 7 (all result planes)")
+        planes = 2 if method == "max_project" else iso_planes
+        clear = method == "iso_surface" and planes == 2
         self._fetch_iso_extras()  # a deferred read-back of an earlier render() happens before the slots are reused
         pending = []  # slots in flight, oldest first
         i = 0
@@ -540,16 +545,16 @@ class VolumeRenderer(object):
                 pending.append(slot)
                 i += 1
                 if len(pending) == 2:
-                    self._adopt_slot(pending.pop(0), planes)
+                    self._adopt_slot(pending.pop(0), planes, clear)
                     yield self
             while pending:
-                self._adopt_slot(pending.pop(0), planes)
+                self._adopt_slot(pending.pop(0), planes, clear)
                 yield self
         finally:
             self._lib.spv_sync(self._ctx)
             self._lib.spv_select_slot(self._ctx, 0)
 
-    def _adopt_slot(self, slot, planes):
+    def _adopt_slot(self, slot, planes, clear_extras=False):
         host = _lib._FP()
         self._check(self._lib.spv_wait_slot(self._ctx, slot, C.byref(host)))
         n = self.width * self.height
@@ -559,6 +564,8 @@ class VolumeRenderer(object):
         shape = (self.height, self.width)
         self.output = flat[:n].reshape(shape)
         self.output_alpha = flat[n:2 * n].reshape(shape)
+        if clear_extras:
+            self.output_depth = self.output_occlusion = self.output_normals = None
         if planes == 7:
             self.output_depth = flat[2 * n:3 * n].reshape(shape)
             self.output_occlusion = flat[3 * n:4 * n].reshape(shape)

@@ -201,6 +201,19 @@ def test_render_keyframes_equals_the_synchronous_loop():
         a = [np.array(r.output) for _, _, r in kf.render_keyframes(rend, keys, 6, source=source, pipelined=False)]
         b = [np.array(r.output) for _, _, r in kf.render_keyframes(rend, keys, 6, source=source)]
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        # display planes only: same images, the other iso planes are not read back
+        seen_iso = False
+        for (_, td, r), want in zip(kf.render_keyframes(rend, keys, 20, source=source, iso_planes=2),
+                                    kf.render_keyframes(ref, keys, 20, source=source, pipelined=False)):
+            assert np.array_equal(r.output, want[2].output) and np.array_equal(r.output_alpha, want[2].output_alpha)
+            if td.isIso:
+                seen_iso = True
+                assert r.output_depth is None and r.output_normals is None and r.output_occlusion is None
+        assert seen_iso
+        rend.render(method="max_project")
+        assert rend.output_depth.shape == (128, 160)
+        with pytest.raises(ValueError):
+            next(rend.render_sequence([np.eye(4)], method="iso_surface", iso_planes=3))
     finally:
         rend.close()
         ref.close()
