@@ -1,7 +1,8 @@
 """Frame sources for 3D+t playback: the data containers either side of VolumeRenderer.update_data.
 
 Mirrors the part of the reference's data model that feeds the renderer during timelapse playback
-(spimagine/models/data_model.py: GenericData :59-95, SpimData :97-148, RawData :221-261, NumpyData :408-432, the
+(spimagine/models/data_model.py: GenericData :59-95, SpimData :97-148, TiffData :178-218, RawData :221-261,
+RawMultipleFiles / TiffFolderData / TiffMultipleFiles :262-404, NumpyData :408-432, the
 prefetching DataLoadThread / DataModel :600-757; spimagine/utils/imgutils.py: parseIndexFile :48-66, parseMetaFile
 :69-86, fromSpimFolder :129-146, createSpimFolder :162-191) -- same class names, same `sizeT() / size() /
 stackUnits / container[pos]` protocol -- with one change in where the bytes land: `FrameSource` reads time points
@@ -17,6 +18,7 @@ in NumpyData or any object with the same protocol.
 """
 from __future__ import absolute_import, print_function
 
+import glob
 import logging
 import os
 import re
@@ -231,6 +233,116 @@ class TiffData(GenericData):
             self.read_into(pos, out)
             return out
         return None
+
+
+class _FilePerTimePoint(GenericData):
+    """Time point t is file t of a sorted list (data_model.py:262-404: RawMultipleFiles, TiffFolderData,
+    TiffMultipleFiles).  Sizes come from the first file; every read goes straight into the caller's buffer."""
+
+    def _read_file_into(self, fname, out):
+        raise NotImplementedError
+
+    def read_into(self, pos, out):
+        if pos < 0 or pos >= len(self.fNames):
+            raise IndexError("0 <= pos <= %i, but pos = %i" % (len(self.fNames) - 1, pos))
+        self._read_file_into(self.fNames[pos], out)
+
+    def __getitem__(self, pos):
+        if len(self.fNames) > 0 and pos < len(self.fNames):
+            out = np.empty(tuple(self.stackSize[1:]), self.dtype)
+            self.read_into(pos, out)
+            return out
+        return None
+
+
+class RawMultipleFiles(_FilePerTimePoint):
+    """2/3d raw data, one file per time point (data_model.py:262-308; shape = (z, y, x) or (y, x) of ONE file)"""
+
+    def __init__(self, fnames=[], shape=None, dtype=None):
+        GenericData.__init__(self, "[" + ", ".join(fnames) + "]")
+        self.fNames = self.fnames = list(fnames)
+        self.load(self.fNames, shape, dtype)
+
+    def load(self, fnames, shape, dtype, stackUnits=[1., 1., 1.]):
+        if fnames:
+            if shape is None or dtype is None:
+                raise ValueError("RawMultipleFiles needs shape and dtype (the reference asks for them in a dialog)")
+            shape = tuple(int(s) for s in shape)
+            shape = (1,) * (3 - len(shape)) + shape
+            self._dtype = np.dtype(dtype)
+            need = int(np.prod(shape, dtype=np.int64)) * self._dtype.itemsize
+            if os.path.getsize(fnames[0]) < need:
+                raise Exception("couldnt open %s as RawData" % fnames[0])
+            self.stackSize = (len(fnames),) + shape
+            self.stackUnits = stackUnits
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    def _read_file_into(self, fname, out):
+        buf = memoryview(out.reshape(-1)).cast("B")
+        with open(fname, "rb", buffering=0) as f:
+            got = 0
+            while got < len(buf):
+                n = f.readinto(buf[got:])
+                if not n:
+                    raise IOError("%s: short read" % fname)
+                got += n
+
+
+class TiffMultipleFiles(_FilePerTimePoint):
+    """2/3d tiff data, one file per time point (data_model.py:364-404)"""
+
+    def __init__(self, fName=[]):
+        GenericData.__init__(self, "[" + ", ".join(fName) + "]")
+        self.fNames = list(fName)
+        self.load(self.fNames)
+
+    def load(self, fNames, stackUnits=[1., 1., 1.]):
+        if fNames:
+            from .utils.tiffio import TiffFile
+            try:
+                first = TiffFile(fNames[0])
+                single = tuple(first.shape)
+                if len(single) != 3:
+                    raise Exception("tiff stacks seem to be neither 2d nor 3d")
+                self._file_dtype = first.dtype
+                self.stackSize = (len(fNames),) + single
+            except Exception as e:
+                print(e)
+                self.fName = ""
+                raise Exception("couldnt open %s as TiffData" % fNames[0])
+            self.stackUnits = stackUnits
+
+    @property
+    def dtype(self):
+        return self._file_dtype.newbyteorder("=")
+
+    def _read_file_into(self, fname, out):
+        from .utils.tiffio import TiffFile
+        tif = TiffFile(fname)
+        if tuple(tif.shape) != tuple(self.stackSize[1:]) or tif.dtype.newbyteorder("=") != self.dtype:
+            raise ValueError("%s: %s %s, expected %s %s" % (fname, tif.shape, tif.dtype, self.stackSize[1:], self.dtype))
+        tif.read_into(out.view(tif.dtype) if out.dtype.itemsize > 1 else out)
+        if not tif.dtype.isnative:
+            out.byteswap(inplace=True)
+
+
+class TiffFolderData(TiffMultipleFiles):
+    """3d tiff data inside a folder: every *.tif / *.tiff, sorted by name (data_model.py:311-361)"""
+
+    def __init__(self, fName=""):
+        GenericData.__init__(self, fName)
+        self.fNames = []
+        self.fName = ""
+        if fName:
+            names = sorted(f for f in glob.glob(os.path.join(fName, "*")) if re.match(r".*\.(tif|tiff)", f))
+            if len(names) == 0:
+                raise Exception("folder %s seems to be empty" % fName)
+            self.fNames = names
+            self.load(names)
+            self.fName = fName
 
 
 class NumpyData(GenericData):

@@ -201,3 +201,51 @@ def test_tiffdata_container_and_frame_source(tmp_path):
     tiffio.write3dTiff(f32, fn)
     d = frames.TiffData(fn)
     assert d.dtype == np.float32 and np.array_equal(d[0], f32)
+
+
+def test_one_file_per_time_point(tmp_path):
+    """data_model.py:262-404: RawMultipleFiles, TiffFolderData, TiffMultipleFiles."""
+    data = _stack((4, 3, 6, 7), np.uint16, seed=8)
+    folder = tmp_path / "series"
+    folder.mkdir()
+    names = []
+    for t in (2, 0, 3, 1):                                  # written out of order: the folder is sorted by name
+        fn = str(folder / ("t%03d.tif" % t))
+        tiffio.write3dTiff(data[t], fn)
+        names.append(fn)
+    (folder / "notes.txt").write_text("not an image")
+    d = frames.TiffFolderData(str(folder))
+    assert d.size() == data.shape and d.sizeT() == 4 and d.dtype == np.uint16
+    for t in range(4):
+        assert np.array_equal(d[t], data[t])
+    assert d[4] is None
+    with pytest.raises(IndexError):
+        d.read_into(4, np.empty(data.shape[1:], np.uint16))
+    m = frames.TiffMultipleFiles(sorted(names)[::-1])
+    assert m.size() == data.shape and np.array_equal(m[0], data[3])
+    tiffio.write3dTiff(data[0, :2], str(folder / "t001.tif"))   # a file that does not match the first one
+    with pytest.raises(ValueError):
+        d[1]
+    with pytest.raises(Exception, match="empty"):
+        frames.TiffFolderData(str(tmp_path))
+    src = frames.FrameSource(d, frames=[0, 2, 3], depth=3, pinned=False)
+    try:
+        for t in (0, 2, 3):
+            assert np.array_equal(src[t], data[t])
+    finally:
+        src.close()
+    # raw files
+    raws = []
+    f32 = _stack((3, 4, 5, 6), np.float32, seed=9)
+    for t in range(3):
+        fn = str(tmp_path / ("r%d.raw" % t))
+        f32[t].tofile(fn)
+        raws.append(fn)
+    r = frames.RawMultipleFiles(raws, shape=(4, 5, 6), dtype=np.float32)
+    assert r.size() == f32.shape and r.dtype == np.float32 and np.array_equal(r[2], f32[2])
+    r2 = frames.RawMultipleFiles(raws, shape=(20, 6), dtype=np.float32)      # 2-d shape -> one slice per file
+    assert r2.size() == (3, 1, 20, 6) and np.array_equal(r2[1][0], f32[1].reshape(20, 6))
+    with pytest.raises(Exception, match="couldnt open"):
+        frames.RawMultipleFiles(raws, shape=(40, 5, 6), dtype=np.float32)
+    with pytest.raises(ValueError):
+        frames.RawMultipleFiles(raws)
