@@ -544,6 +544,15 @@ def run_blur(args, rank, local_rank, world):
         by_mode[fuse] = float(np.mean(ms))
     dev_ms = by_mode[0]
     got = vf.result()
+    # the spectrum processor (FFTProcessor, libspimfft.so) on the same resident volume, timed beside the blur
+    plan = ip.SpectrumPlan(local_rank)
+    fft_ms = []
+    for i in range(3 + 10):
+        plan.spectrum_device(dvol.data_ptr(), vol.shape, np.uint16)
+        if i >= 3:
+            fft_ms.append(plan.last_ms())
+    fft_ms = float(np.mean(fft_ms))
+    plan.close()
     # parity on the spot: a corner block against the CPU restatement (outputs within 9 voxels of the block's cut
     # faces would see voxels the block does not have)
     b = min(N, 96)
@@ -596,6 +605,9 @@ def run_blur(args, rank, local_rank, world):
                 "host_round_trip_note": "the reference's shape with the same kernels: proc.apply(data) -> float32 host "
                                         "array -> renderer.update_data(result)"},
         "gpu_launches": steps * 3, "clocks": clk,
+        "fft_processor": {"ms": fft_ms, "volumes_per_s": 1e3 / fft_ms,
+                          "note": "FFTProcessor on the same resident volume: pad + convert pass, real-to-complex cuFFT "
+                                  "(library), fused magnitude / shift / scale / crop pass; device time of the three"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_step": alg, "bytes_moved_by_the_three_passes": moved,

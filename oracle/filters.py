@@ -60,3 +60,45 @@ def gauss_taps(sigma):
     x = np.arange(-N, N + 1)
     h = np.exp(-x ** 2 / 2. / sigma ** 2)
     return 1. * h / sum(h)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FFTProcessor (spimagine/models/imageprocessor.py:82-98).  The expression is in the reference; gputools' helpers it
+# calls are not (gputools is an unpinned, un-vendored PyPI dependency, see filter_oracle.c): pad_to_shape /
+# pad_to_power2 are restated from gputools 0.2.x (gputools/utils/utils.py) and gputools.fft is the unnormalised
+# forward transform over all axes.  PARITY UNPINNED for these three; the expression around them is the reference's.
+def _next_power_of_2(n):
+    return int(2 ** np.ceil(np.log2(n)))
+
+
+def pad_to_shape(d, dshape, mode="constant"):
+    """gputools.pad_to_shape: centre-crop the axes that are too long (floor(k/2) elements dropped in front,
+    ceil(k/2) behind), then pad the axes that are too short (ceil(k/2) in front, floor(k/2) behind)."""
+    if tuple(d.shape) == tuple(dshape):
+        return d
+    diff = np.array(dshape) - np.array(d.shape)
+    slices = tuple(slice(-x // 2, x // 2) if x < 0 else slice(None, None) for x in diff)
+    res = d[slices]
+    return np.pad(res, [(int(np.ceil(k / 2.)), int(k - int(np.ceil(k / 2.)))) if k > 0 else (0, 0) for k in diff],
+                  mode=mode)
+
+
+def pad_to_power2(data, mode="constant"):
+    """gputools.pad_to_power2 over all axes"""
+    if all(_next_power_of_2(n) == n for n in data.shape):
+        return data
+    return pad_to_shape(data, [_next_power_of_2(n) for n in data.shape], mode)
+
+
+def fft_spectrum(data, log=False, precise=False):
+    """FFTProcessor.apply.  precise=True carries the transform in complex128 (the checker's yardstick: float32
+    transforms of different libraries differ by rounding), otherwise complex64 as in the reference."""
+    dshape = data.shape
+    res = pad_to_power2(data.astype(np.complex128 if precise else np.complex64), mode="wrap")
+    # float(...): the reference ran under value-based casting, where the float64 scalar 1/sqrt(size) does not
+    # promote a float32 array; under NEP 50 (numpy >= 2) only a Python float behaves that way
+    res = float(1. / np.sqrt(res.size)) * np.fft.fftshift(abs(np.fft.fftn(res)))
+    res = pad_to_shape(res, dshape)
+    if log:
+        return np.log2(0.001 + res)
+    return res

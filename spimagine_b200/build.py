@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Build spimagine_b200/libspimcuda.so with nvcc for sm_100a (cross-compiles without a GPU).
+"""Build spimagine_b200/libspimcuda.so (and libspimfft.so) with nvcc for sm_100a (cross-compiles without a GPU).
 
     python -m spimagine_b200.build [--force] [--verbose]
 
@@ -36,6 +36,32 @@ def nvcc():
     return exe
 
 
+# the spectrum processor lives in its own library: only it depends on cuFFT
+FFT_LIB = os.path.join(HERE, "libspimfft.so")
+FFT_SOURCES = ["spv_fft.cu"]
+FFT_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+             "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "-shared", "-cudart", "static"]
+
+
+def fft_up_to_date():
+    if not os.path.exists(FFT_LIB):
+        return False
+    t = os.path.getmtime(FFT_LIB)
+    deps = [os.path.join(CSRC, f) for f in FFT_SOURCES] + [os.path.join(INCLUDE, "spimfft.h"), __file__]
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def build_fft(force=False, verbose=False):
+    if not force and fft_up_to_date():
+        return FFT_LIB
+    cmd = [nvcc()] + FFT_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-I", INCLUDE, "-o", FFT_LIB] + [os.path.join(CSRC, f) for f in FFT_SOURCES] + ["-lcufft"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return FFT_LIB
+
+
 def up_to_date():
     if not os.path.exists(LIB):
         return False
@@ -57,3 +83,4 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_fft(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

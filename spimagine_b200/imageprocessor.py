@@ -1,5 +1,6 @@
 """Volume processors between the data model and the renderer -- the drop-in for spimagine/models/imageprocessor.py
-(ImageProcessor, CopyProcessor, BlurProcessor, BlurXYZProcessor, NoiseProcessor, LucyRichProcessor, FuncProcessor:
+(ImageProcessor, CopyProcessor, BlurProcessor, BlurXYZProcessor, NoiseProcessor, FFTProcessor, LucyRichProcessor,
+FuncProcessor:
 same names, constructor arguments, `kwargs` attribute access and `apply(data) -> ndarray`), with the separable blur
 running on the B200 through libspimcuda (spv_filter_*) instead of gputools.convolve_sep3.
 
@@ -9,10 +10,12 @@ the device: `apply_chain(renderer, data, processors)` uploads the volume once, r
 in place and hands the float32 result to the renderer's resident array (spv_update_volume_device_from), so neither
 the filtered volume nor its re-upload crosses PCIe.
 
-FFTProcessor is not provided (it needs gputools.fft / pad_to_power2; SURVEY 8f-4 lists it as a later widening).
-There is no CPU implementation of the blur: without libspimcuda / a CUDA device, apply() raises.
+FFTProcessor (the Fourier spectrum of the volume) runs through libspimfft.so (include/spimfft.h): wrap-padding and
+element conversion, a real-to-complex cuFFT, and a fused magnitude / fftshift / scale / crop / log pass.
+There is no CPU implementation of the blur or the spectrum: without the libraries / a CUDA device, apply() raises.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -202,6 +205,141 @@ class NoiseProcessor(ImageProcessor):
         return np.maximum(0, data + self.sigma * np.random.normal(0, 1, data.shape))
 
 
+FFT_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libspimfft.so")
+_FFT_TYPES = (np.uint8, np.int16, np.uint16, np.float32)
+_fft_lib = None
+
+
+def load_fft():
+    """Load libspimfft.so (once) and declare the signatures of include/spimfft.h."""
+    global _fft_lib
+    if _fft_lib is not None:
+        return _fft_lib
+    if not os.path.exists(FFT_LIB_PATH):
+        raise ImportError("%s not found: build it with `python -m spimagine_b200.build` "
+                          "(needs nvcc and cuFFT; there is no CPU fallback)" % FFT_LIB_PATH)
+    lib = C.CDLL(FFT_LIB_PATH)
+    P, FP = C.c_void_p, C.POINTER(C.c_float)
+    sig = {"spf_create": (C.c_int, [C.c_int, C.POINTER(P)]),
+           "spf_destroy": (C.c_int, [P]),
+           "spf_spectrum": (C.c_int, [P, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, FP]),
+           "spf_result_device": (C.c_int, [P, C.POINTER(FP)]),
+           "spf_read": (C.c_int, [P, FP, C.c_size_t]),
+           "spf_padded_shape": (C.c_int, [P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+           "spf_last_ms": (C.c_int, [P, FP]),
+           "spf_launch_count": (C.c_int, [P, C.POINTER(C.c_ulonglong)]),
+           "spf_last_error": (C.c_char_p, [P])}
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    lib._signatures = sig
+    _fft_lib = lib
+    return lib
+
+
+class SpectrumPlan(object):
+    """Device side of FFTProcessor (owns a stream, the padded work arrays and the cuFFT plan on `device`)."""
+
+    def __init__(self, device=0):
+        self._lib = load_fft()
+        self._p = C.c_void_p()
+        rc = self._lib.spf_create(int(device), C.byref(self._p))
+        if rc != 0:
+            msg = self._lib.spf_last_error(None)
+            raise _lib.SpvError("libspimfft: %s" % (msg.decode() if msg else "error %d" % rc))
+        self.shape = None
+
+    def close(self):
+        if getattr(self, "_p", None) is not None and self._p.value:
+            self._lib.spf_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.spf_last_error(self._p)
+            raise _lib.SpvError("libspimfft: %s" % (msg.decode() if msg else "error %d" % rc))
+
+    def spectrum(self, data, log=False, read_back=True):
+        """data: (Nz, Ny, Nx) ndarray -> float32 spectrum of the same shape (None with read_back=False: the result
+        stays on the device, see result_device)."""
+        data = np.asarray(data)
+        if data.ndim != 3:
+            raise ValueError("need a 3-D volume, got shape %s" % (data.shape,))
+        if data.dtype.type not in _FFT_TYPES or not data.dtype.isnative:
+            data = data.astype(np.float32)  # the reference's astype(complex64) has float32 parts
+        host = np.ascontiguousarray(data)
+        nz, ny, nx = host.shape
+        out = np.empty(host.shape, np.float32) if read_back else None
+        self._check(self._lib.spf_spectrum(self._p, host.ctypes.data, 0, _lib.SRC_CODES[np.dtype(host.dtype)],
+                                           nx, ny, nz, int(bool(log)), _lib.fp(out) if read_back else None))
+        self.shape = host.shape
+        return out
+
+    def spectrum_device(self, device_ptr, shape, dtype, log=False):
+        nz, ny, nx = (int(v) for v in shape)
+        if np.dtype(dtype).type not in _FFT_TYPES:
+            raise NotImplementedError("element type %s: uint8, int16, uint16 or float32" % np.dtype(dtype))
+        self._check(self._lib.spf_spectrum(self._p, C.c_void_p(int(device_ptr)), 1, _lib.SRC_CODES[np.dtype(dtype)],
+                                           nx, ny, nz, int(bool(log)), None))
+        self.shape = (nz, ny, nx)
+
+    def result(self):
+        out = np.empty(self.shape, np.float32)
+        self._check(self._lib.spf_read(self._p, _lib.fp(out), out.size))
+        return out
+
+    def result_device(self):
+        """-> (device pointer, (Nz, Ny, Nx)) of the float32 result"""
+        dev = C.POINTER(C.c_float)()
+        self._check(self._lib.spf_result_device(self._p, C.byref(dev)))
+        return C.cast(dev, C.c_void_p).value, self.shape
+
+    def padded_shape(self):
+        x, y, z = C.c_int(), C.c_int(), C.c_int()
+        self._check(self._lib.spf_padded_shape(self._p, C.byref(x), C.byref(y), C.byref(z)))
+        return z.value, y.value, x.value
+
+    def last_ms(self):
+        ms = C.c_float()
+        self._check(self._lib.spf_last_ms(self._p, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_ulonglong()
+        self._check(self._lib.spf_launch_count(self._p, C.byref(n)))
+        return int(n.value)
+
+
+_spectrum_plans = {}
+
+
+def _shared_plan(device=0):
+    if device not in _spectrum_plans:
+        _spectrum_plans[device] = SpectrumPlan(device)
+    return _spectrum_plans[device]
+
+
+class FFTProcessor(ImageProcessor):
+    """models/imageprocessor.py:82-98: the centred, cropped magnitude spectrum of the wrap-padded volume (log2 of it
+    with log=True)."""
+
+    def __init__(self, log=False):
+        super(FFTProcessor, self).__init__("fft", log=log)
+        self.log = log
+
+    def apply(self, data):
+        return _shared_plan().spectrum(data, log=self.log)
+
+    def apply_device(self, plan, device_ptr, shape, dtype):
+        plan.spectrum_device(device_ptr, shape, dtype, log=self.log)
+
+
 class LucyRichProcessor(ImageProcessor):
     """models/imageprocessor.py:101-120: the deconvolution is commented out in the reference; apply returns its input"""
 
@@ -234,33 +372,54 @@ class FuncProcessor(ImageProcessor):
 
 def apply_chain(renderer, data, processors, device=None):
     """What MainWidget.impStateChanged does (gui/mainwidget.py:455-465) -- data through every processor, then
-    renderer.update_data(result) -- without the round trips: the volume is uploaded once, the blurs run on the
-    resident copy (a host-only processor in between gets a host array and its result is uploaded again), and the
-    final float32 volume goes from the filter's memory straight into the renderer's resident array, converted to
-    the renderer's element type like update_data's astype.  `renderer` must already hold a volume of the same shape
-    (set_data).  Returns the device time of the filters in ms."""
+    renderer.update_data(result) -- without the round trips: the volume is uploaded once, the blurs and the spectrum
+    run on the resident copy (a host-only processor in between gets a host array and its result is uploaded again),
+    and the final float32 volume goes from the processor's memory straight into the renderer's resident array,
+    converted to the renderer's element type like update_data's astype.  `renderer` must already hold a volume of
+    the same shape (set_data).  Returns the device time of the processors in ms."""
     dev = device if device is not None else (renderer.device or 0)
     vf = _shared_filter(dev)
     data = np.asarray(data)
-    resident, ms = False, 0.
+    where, ms = "host", 0.  # "host": `data`; "filter" / "plan": float32 result in that object's device memory
+    plan = None
+
+    def device_result():
+        if where == "filter":
+            ptr, shape = vf.result_device()
+            vf.sync()
+            return ptr, shape
+        return plan.result_device()  # spf_spectrum returns when its stream has finished
+
     for p in processors:
         if isinstance(p, (BlurProcessor, BlurXYZProcessor)):
-            if not resident:
+            if where == "host":
                 vf.load(data)
-                resident = True
+            elif where == "plan":
+                ptr, shape = device_result()
+                vf.load_device(ptr, shape, np.float32)
+            where = "filter"
             p.apply_device(vf)
             ms += vf.last_ms()
+        elif isinstance(p, FFTProcessor):
+            plan = _shared_plan(dev) if plan is None else plan
+            if where == "host":
+                plan.spectrum(data, log=p.log, read_back=False)
+            else:
+                ptr, shape = device_result()
+                p.apply_device(plan, ptr, shape, np.float32)
+            where = "plan"
+            ms += plan.last_ms()
         elif isinstance(p, (CopyProcessor, LucyRichProcessor)):
             continue  # identity in the reference as well
         else:
-            if resident:
-                data = vf.result()
-                resident = False
+            if where != "host":
+                ptr, shape = device_result()
+                data = plan.result() if where == "plan" else vf.result()
+                where = "host"
             data = np.asarray(p.apply(data))
-    if not resident:
+    if where == "host":
         renderer.update_data(data)
         return ms
-    ptr, shape = vf.result_device()
-    vf.sync()
+    ptr, shape = device_result()
     renderer.update_data_device(ptr, shape, np.float32)
     return ms
