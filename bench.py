@@ -1139,6 +1139,19 @@ def main():
         alg_bytes = vol.nbytes + 2 * W * H * 4
         achieved = alg_bytes / launch_s / 1e9
         tex_peak = rend.texrate_probe(4000)
+        # the same probe with the benchmark camera's footprint: neighbouring rays one pixel apart at the volume's
+        # centre (2 d tan(fovy/2) / W box units, d = 4), samples L/192 apart along the view direction (mean in-box
+        # path L = 1.23 box units), at 12 angles of the sweep; every fetch hits L1
+        tpu = args.vol / 2.                       # texels per box unit
+        pitch = 2. * 4. * np.tan(np.radians(30.)) / W * tpu
+        step = 1.23 / (MAX_STEPS // 16 * 16) * tpu
+        foot = []
+        for f in range(0, 360, 30):
+            th = 2 * np.pi * f / 360. + 1e-3
+            c, s_ = np.cos(th), np.sin(th)
+            foot.append(rend.texrate_probe(2000, footprint=[[pitch * c, 0., -pitch * s_], [0., pitch, 0.],
+                                                            [-step * s_, 0., -step * c]]))
+        tex_foot = len(foot) / sum(1. / r for r in foot)   # equal samples per angle: harmonic mean
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -1177,7 +1190,17 @@ def main():
                              "peak_gsamples_per_s": tex_peak / 1e9,
                              "frac_issued": mean_issued / launch_s / tex_peak,
                              "frac_algorithmic": mean_hits * SAMPLES_PER_RAY / launch_s / tex_peak,
-                             "peak_source": "spv_texrate_probe on this GPU: cache-resident trilinear uint16 fetches"},
+                             "peak_source": "spv_texrate_probe on this GPU: cache-resident trilinear uint16 fetches",
+                             "peak_at_render_footprint_gsamples_per_s": tex_foot / 1e9,
+                             "frac_issued_at_render_footprint": mean_issued / launch_s / tex_foot,
+                             "render_footprint": {"ray_spacing_texels": pitch, "sample_spacing_texels": step,
+                                                  "gsamples_per_s_by_angle_deg": dict(
+                                                      (str(f), r / 1e9) for f, r in zip(range(0, 360, 30), foot)),
+                                                  "note": "spv_texrate_probe_footprint: the same independent fetches "
+                                                          "laid out like this camera's rays (a warp's 8x4 tile one "
+                                                          "pixel apart, 16 samples in flight along the view "
+                                                          "direction), all warps on one L1-resident region: what the "
+                                                          "texture unit delivers for this footprint without misses"}},
             "upload_s": t_upload,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -295,6 +295,10 @@ SPV_API int spv_sample_points(spv_ctx *ctx, const float *host_pos, int n, float 
 /* roofline calibration: measured rate (samples/s) of independent, cache-resident filtered fetches of the
  * resident volume's format with the current interpolation mode */
 SPV_API int spv_texrate_probe(spv_ctx *ctx, int iters, double *samples_per_s);
+/* the same probe with a given footprint: lane (lx, ly) of a warp's 8x4 tile fetches at base + lx*a + ly*b + j*m,
+ * j = 0..15, with vec9 = {a, b, m} in texels (x, y, z).  All warps walk the same small region (every fetch hits L1):
+ * the rate the texture unit can deliver for the ray and sample spacing of a given camera */
+SPV_API int spv_texrate_probe_footprint(spv_ctx *ctx, int iters, const float *vec9, double *samples_per_s);
 SPV_API int spv_launch_count(spv_ctx *ctx, unsigned long long *n);  /* kernels launched by this context so far */
 
 #ifdef __cplusplus

@@ -1603,18 +1603,20 @@ SPV_API int spv_sample_points(spv_ctx *ctx, const float *host_pos, int n, float 
   return 0;
 }
 
-SPV_API int spv_texrate_probe(spv_ctx *ctx, int iters, double *samples_per_s) {
-  BIND();
+static int texrate_probe_impl(spv_ctx *ctx, int iters, const float *vec9, double *samples_per_s) {
   if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_texrate_probe: no volume set");
   if (iters < 1 || !samples_per_s) return fail(ctx, SPV_EINVAL, "spv_texrate_probe: bad argument");
+  if (vec9)
+    for (int i = 0; i < 9; ++i)
+      if (!(fabsf(vec9[i]) <= 8.f)) return fail(ctx, SPV_EINVAL, "spv_texrate_probe_footprint: |component| <= 8 texels");
   int sms = 0;
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
   const int blocks = sms * 8;
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
   Volume V = volume_of(ctx);
-  CU(launch_texrate_probe(V, fmt_of(ctx), linear, blocks, 8, ctx->tmp(), ctx->stream));  // warm-up
+  CU(launch_texrate_probe(V, fmt_of(ctx), linear, blocks, 8, vec9, ctx->tmp(), ctx->stream));  // warm-up
   CU(cudaEventRecord(ctx->ev0, ctx->stream));
-  CU(launch_texrate_probe(V, fmt_of(ctx), linear, blocks, iters, ctx->tmp(), ctx->stream));
+  CU(launch_texrate_probe(V, fmt_of(ctx), linear, blocks, iters, vec9, ctx->tmp(), ctx->stream));
   CU(cudaEventRecord(ctx->ev1, ctx->stream));
   CU(cudaEventSynchronize(ctx->ev1));
   float ms = 0.f;
@@ -1622,6 +1624,17 @@ SPV_API int spv_texrate_probe(spv_ctx *ctx, int iters, double *samples_per_s) {
   ctx->launches += 2;
   *samples_per_s = (double)blocks * 256.0 * 16.0 * (double)iters / ((double)ms * 1e-3);
   return 0;
+}
+
+SPV_API int spv_texrate_probe(spv_ctx *ctx, int iters, double *samples_per_s) {
+  BIND();
+  return texrate_probe_impl(ctx, iters, nullptr, samples_per_s);
+}
+
+SPV_API int spv_texrate_probe_footprint(spv_ctx *ctx, int iters, const float *vec9, double *samples_per_s) {
+  BIND();
+  if (!vec9) return fail(ctx, SPV_EINVAL, "spv_texrate_probe_footprint: null vectors");
+  return texrate_probe_impl(ctx, iters, vec9, samples_per_s);
 }
 
 SPV_API int spv_launch_count(spv_ctx *ctx, unsigned long long *n) {

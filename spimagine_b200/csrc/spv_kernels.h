@@ -86,8 +86,8 @@ struct PeerFlagPtrs { unsigned *p[MAX_WORLD]; };
 
 cudaError_t launch_sample_points(const Volume &V, int dtype, bool linear, bool exact, const float *pos, int n,
                                  float *out, cudaStream_t st);
-cudaError_t launch_texrate_probe(const Volume &V, int dtype, bool linear, int blocks, int iters, float *sink,
-                                 cudaStream_t st);
+cudaError_t launch_texrate_probe(const Volume &V, int dtype, bool linear, int blocks, int iters, const float *vec9,
+                                 float *sink, cudaStream_t st);
 
 cudaError_t launch_iso(const IsoArgs &a, int dtype, bool linear, bool exact, bool stats, cudaStream_t st);
 // Sort-last iso surface over peer memory (spv_render_iso_composite): world > 0 switches the two slab kernels from

@@ -469,32 +469,57 @@ cudaError_t launch_sample_points(const Volume &V, int dtype, bool linear, bool e
 
 // Calibration probe for the texture-sample roofline: every lane issues independent filtered fetches inside a
 // small (cache-resident) region of the resident volume, with no dependent arithmetic between them.
+// Lane (lx, ly) of the 8x4 tile samples at base + lx*a + ly*b + j*m (texels; j = 0..15 independent fetches in flight).
+// The default vectors (a = .6 x, b = .6 y, m mostly along z, 8 slices deep) keep a 2x2 quad's footprint inside one
+// cache line most of the time: the unit's peak.  With the benchmark camera's vectors (rays 1.15 texels apart, samples
+// 1.6 texels apart along the view direction) it measures what the unit can deliver for THAT footprint when every
+// fetch hits L1: all warps of all CTAs walk the same small region.
+struct ProbeVecs {
+  float a[3], b[3], m[3];
+  int wrap8;  // z advances with (j & 7): the default probe
+};
 template <int FMT, bool LINEAR>
-__global__ void __launch_bounds__(256) texrate_probe_kernel(const Volume V, int iters, float *sink) {
+__global__ void __launch_bounds__(256) texrate_probe_kernel(const Volume V, int iters, const ProbeVecs pv, float *sink) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
   const int ly = ((lane >> 1) & 1) | ((lane >> 2) & 2);
-  // an 8x4 tile of neighbouring sample positions, 0.6 texel apart, marching along z like a ray would
-  const float bx = 0.37f * (float)V.nx + 0.6f * (float)lx + 3.1f * (float)(warp & 3);
-  const float by = 0.41f * (float)V.ny + 0.6f * (float)ly + 2.7f * (float)(warp >> 2);
-  const float bz = 0.29f * (float)V.nz + 1.9f * (float)(blockIdx.x & 7);
+  const float fx = (float)lx, fy = (float)ly;
+  float bx = 0.37f * (float)V.nx + fx * pv.a[0] + fy * pv.b[0];
+  float by = 0.41f * (float)V.ny + fx * pv.a[1] + fy * pv.b[1];
+  float bz = 0.29f * (float)V.nz + fx * pv.a[2] + fy * pv.b[2];
+  if (pv.wrap8) {  // warps and CTAs next to each other, as the first calibration of this round measured it
+    bx += 3.1f * (float)(warp & 3);
+    by += 2.7f * (float)(warp >> 2);
+    bz += 1.9f * (float)(blockIdx.x & 7);
+  }
   float acc = 0.f;
   for (int it = 0; it < iters; ++it) {
     float v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      v[j] = sample_tmu_uvw<FMT, LINEAR>(V, bx + 0.05f * (float)j, by + 0.03f * (float)j, bz + 0.9f * (float)(j & 7) + 0.11f * (float)(it & 3));
+    for (int j = 0; j < 16; ++j) {
+      const float fj = (float)j, fz = pv.wrap8 ? (float)(j & 7) : fj;
+      v[j] = sample_tmu_uvw<FMT, LINEAR>(V, bx + pv.m[0] * fj, by + pv.m[1] * fj, bz + pv.m[2] * fz + 0.11f * (float)(it & 3));
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc = fmaxf(acc, v[j]);
   }
   if (acc == -12345.f) sink[0] = acc;  // never true: keeps the fetches alive
 }
 
-cudaError_t launch_texrate_probe(const Volume &V, int dtype, bool linear, int blocks, int iters, float *sink,
-                                 cudaStream_t st) {
+cudaError_t launch_texrate_probe(const Volume &V, int dtype, bool linear, int blocks, int iters, const float *vec9,
+                                 float *sink, cudaStream_t st) {
+  ProbeVecs pv = {{.6f, 0.f, 0.f}, {0.f, .6f, 0.f}, {.05f, .03f, .9f}, 1};
+  if (vec9) {
+    for (int i = 0; i < 3; ++i) {
+      pv.a[i] = vec9[i];
+      pv.b[i] = vec9[3 + i];
+      pv.m[i] = vec9[6 + i];
+    }
+    pv.wrap8 = 0;
+  }
 #define SPV_PROBE(FMT) \
-  if (linear) texrate_probe_kernel<FMT, true><<<blocks, 256, 0, st>>>(V, iters, sink); \
-  else texrate_probe_kernel<FMT, false><<<blocks, 256, 0, st>>>(V, iters, sink)
+  if (linear) texrate_probe_kernel<FMT, true><<<blocks, 256, 0, st>>>(V, iters, pv, sink); \
+  else texrate_probe_kernel<FMT, false><<<blocks, 256, 0, st>>>(V, iters, pv, sink)
   switch (dtype) {
     case 0: SPV_PROBE(0); break;
     case 1: SPV_PROBE(1); break;

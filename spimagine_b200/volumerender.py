@@ -593,10 +593,17 @@ class VolumeRenderer(object):
         self.last_warp_histogram = [int(x) for x in v[4:40]]  # warps by floor(log2(cycles))
         return int(v[2]), int(v[3])
 
-    def texrate_probe(self, iters=2000):
-        """Measured samples/s of independent cache-resident filtered fetches (roofline denominator)."""
+    def texrate_probe(self, iters=2000, footprint=None):
+        """Measured samples/s of independent cache-resident filtered fetches (roofline denominator).  footprint=None:
+        neighbouring lanes 0.6 texel apart (the unit's peak); otherwise (a, b, m), three vectors in texels (x, y, z):
+        lane (lx, ly) of a warp's 8x4 tile fetches at base + lx*a + ly*b + j*m -- the attainable rate for the ray
+        spacing (a, b) and sample spacing (m) of a camera."""
         v = C.c_double()
-        self._check(self._lib.spv_texrate_probe(self._ctx, int(iters), C.byref(v)))
+        if footprint is None:
+            self._check(self._lib.spv_texrate_probe(self._ctx, int(iters), C.byref(v)))
+        else:
+            vec = np.ascontiguousarray(np.asarray(footprint, np.float32).reshape(9))
+            self._check(self._lib.spv_texrate_probe_footprint(self._ctx, int(iters), _lib.fp(vec), C.byref(v)))
         return v.value
 
     def sample_points(self, pos):

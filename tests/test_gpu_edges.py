@@ -175,3 +175,25 @@ def test_empty_volume_and_cameras_that_see_nothing(oracle_mod):
     assert np.array_equal(g.output_depth, o.output_depth)
     g.close()
     t.close()
+
+
+@pytest.mark.gpu
+def test_texture_rate_probes():
+    """Roofline calibration (bench.py): the peak probe and the footprint probe return plausible rates, a footprint
+    that spreads a quad over several layers is slower than one inside a layer, bad vectors are refused."""
+    from spimagine_b200 import VolumeRenderer, _lib
+    r = VolumeRenderer((64, 64))
+    try:
+        with pytest.raises(_lib.SpvError):
+            r.texrate_probe(10)                                  # no volume yet
+        r.set_data(scenes.vol_g(64, np.uint16, seed=0))
+        peak = r.texrate_probe(400)
+        in_layer = r.texrate_probe(400, footprint=[[1.15, 0, 0], [0, 1.15, 0], [0, 0, 1.6]])
+        across = r.texrate_probe(400, footprint=[[0, 0, 1.15], [0, 1.15, 0], [1.6, 0, 0]])
+        assert 1e11 < across < in_layer <= 1.1 * peak < 3e12, (peak, in_layer, across)
+        with pytest.raises(_lib.SpvError):
+            r.texrate_probe(400, footprint=[[100., 0, 0], [0, 1, 0], [0, 0, 1]])
+        with pytest.raises(_lib.SpvError):
+            r.texrate_probe(0)
+    finally:
+        r.close()
