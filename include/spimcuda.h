@@ -285,7 +285,10 @@ SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
  * image centre outwards (1, default) or row by row (0), knob 6 = resident CTAs per SM of the occlusion queue kernel,
  * knob 7 = copy streams the band copies of spv_render_mip_to_host alternate between (1 or 2), knob 8 = order in which
  * the one-launch path of spv_render_mip_to_host deals its tile rows: 0 = from the top and bottom edges inwards, 1 = the rows
- * the projected box cannot touch first, then the box's rows top to bottom */
+ * the projected box cannot touch first, then the box's rows top to bottom (default), knob 9 = with knob 8 = 1, rows
+ * outside the hull of the projected box corners (+ 9 pixels) are not copied by spv_render_mip_to_host: every ray there
+ * misses, and the pinned staging rows already hold the miss values (out 0, alpha 0 / -1), which the library keeps
+ * track of per output slot (1, default; 0 = copy every row).  The staging memory must be treated as read-only. */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 SPV_API const char *spv_last_error(spv_ctx *ctx);                   /* ctx may be NULL: last create error */
 SPV_API int spv_version(void);

@@ -49,6 +49,12 @@ struct spv_ctx {
   int iso_segments = 1;   // tuning knob 4 (measured on configs[2]: 1 -> 97 us, 2 -> 110 us, 4 -> 178 us)
   int iso_centre_out = 1; // tuning knob 5
   int row_mode = 1;     // spv_render_mip_to_host, one-launch path: order of the tile rows (tuning knob 8, MipArgs::row_mode)
+  int clip_copies = 1;  // spv_render_mip_to_host, one-launch path: rows the box cannot project to are not copied
+                        // (tuning knob 9); their staging rows hold the miss values already
+  // per output slot: rows [dirty_lo, dirty_hi) of the pinned out / alpha staging may differ from the miss values
+  // (out 0, alpha clean_alpha); every other row holds them
+  int dirty_lo[2] = {0, 0}, dirty_hi[2] = {0, 0};
+  float clean_alpha[2] = {0.f, 0.f};
   int direct_host = 0;  // spv_render_mip_to_host: the kernel stores straight into the pinned staging (tuning knob 3)
   unsigned *d_tile_counter = nullptr;
   unsigned *d_band_done = nullptr;   // [MAX_BANDS] CTAs finished per band, counting up across frames (never reset)
@@ -208,7 +214,35 @@ static int alloc_slot(spv_ctx *ctx, int s) {
   CU(cudaMemsetAsync(ctx->dbuf_s[s], 0, 12 * n * sizeof(float), ctx->stream));
   CU(cudaMallocHost(&ctx->hpin_s[s], 7 * n * sizeof(float)));
   memset(ctx->hpin_s[s], 0, 7 * n * sizeof(float));
+  ctx->dirty_lo[s] = ctx->dirty_hi[s] = 0;
+  ctx->clean_alpha[s] = 0.f;
   return 0;
+}
+
+// another path is about to write slot s's pinned staging: nothing is known about its rows any more
+static void staging_dirty(spv_ctx *ctx, int s) {
+  ctx->dirty_lo[s] = 0;
+  ctx->dirty_hi[s] = ctx->height;
+}
+// make rows outside [ya, yb) of slot s's out / alpha staging hold the miss values (the staging is quiescent)
+static void staging_clean_outside(spv_ctx *ctx, int s, int ya, int yb, float miss_alpha) {
+  const int H = ctx->height;
+  const size_t W = (size_t)ctx->width, n = ctx->n();
+  if (ctx->clean_alpha[s] != miss_alpha) staging_dirty(ctx, s);
+  const int parts[2][2] = {{ctx->dirty_lo[s], ctx->dirty_hi[s] < ya ? ctx->dirty_hi[s] : ya},
+                           {ctx->dirty_lo[s] > yb ? ctx->dirty_lo[s] : yb, ctx->dirty_hi[s]}};
+  for (int k = 0; k < 2; ++k) {
+    const int r0 = parts[k][0] < 0 ? 0 : parts[k][0], r1 = parts[k][1] > H ? H : parts[k][1];
+    if (r0 >= r1) continue;
+    float *o = ctx->hpin_s[s] + (size_t)r0 * W, *al = ctx->hpin_s[s] + n + (size_t)r0 * W;
+    const size_t cnt = (size_t)(r1 - r0) * W;
+    memset(o, 0, cnt * sizeof(float));
+    if (miss_alpha == 0.f) memset(al, 0, cnt * sizeof(float));
+    else for (size_t i = 0; i < cnt; ++i) al[i] = miss_alpha;
+  }
+  ctx->clean_alpha[s] = miss_alpha;
+  ctx->dirty_lo[s] = ya < yb ? ya : 0;
+  ctx->dirty_hi[s] = ya < yb ? yb : 0;
 }
 
 static int alloc_buffers(spv_ctx *ctx, int w, int h) {
@@ -734,6 +768,7 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   else if (knob == 5) ctx->iso_centre_out = value != 0;
   else if (knob == 7) ctx->copy_streams = value > 1 ? 2 : 1;
   else if (knob == 8) ctx->row_mode = value == 1 ? 1 : 0;
+  else if (knob == 9) ctx->clip_copies = value != 0;
   else if (knob == 6) occ_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : value);  // process-wide
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
   return 0;
@@ -900,6 +935,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
   const int H = ctx->height;
   const bool direct = to_host && ctx->direct_host && fast && p->num_parts == 1 && !raw_only;
   if (direct) {  // zero-copy: the result planes are written over PCIe by the kernel's own 128-bit stores
+    staging_dirty(ctx, s);
     a.out = ctx->hpin_s[s];
     a.alpha = ctx->hpin_s[s] + ctx->n();
     bands = 1;
@@ -919,12 +955,25 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     a.band_rows = rows;
     const int nb = (H + rows - 1) / rows;
     int order[64];
+    int clip_a = 0, clip_b = H;  // rows that are copied; the others are known to be misses and are not
     if (ctx->row_mode == 1) {
       // rows the box cannot project to are dealt first, then its rows top to bottom: bands without any of those rows
       // complete at once, the others in ascending order
       a.row_mode = 1;
       hit_tile_rows(a.cam, a.box, H, (unsigned)((H + 7) / 8), a.hit_tile_a, a.hit_tile_b);
       const int ya = (int)a.hit_tile_a * 8, yb = (int)a.hit_tile_b * 8;
+      if (ctx->clip_copies) {
+        // A ray of a row outside the hull of the projected corners runs along a line that does not meet the box, so
+        // it is a miss: out 0, alpha 0 (integer volumes) / -1 (float32), which the staging rows hold already.  The
+        // hull is taken in double precision with one pixel of slack; one more tile row on either side here (the
+        // kernel's fp32 slab test can differ from the exact geometry by ~1e-4 pixel at most).
+        clip_a = ya - 8 > 0 ? ya - 8 : 0;
+        clip_b = yb + 8 < H ? yb + 8 : H;
+        if (clip_a >= clip_b) clip_a = clip_b = 0;
+        staging_clean_outside(ctx, s, clip_a, clip_b, ctx->dtype == SPV_F32 ? -1.f : 0.f);
+      } else {
+        staging_dirty(ctx, s);
+      }
       int k = 0;
       for (int b = 0; b < nb; ++b)
         if (b * rows + rows <= ya || b * rows >= yb) order[k++] = b;
@@ -934,6 +983,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
       // the kernel deals tile rows from the top and bottom edges inwards: the bands complete in the order
       // 0, nb-1, 1, nb-2, ...
       for (int i = 0; i < nb; ++i) order[i] = (i & 1) ? nb - 1 - (i >> 1) : (i >> 1);
+      staging_dirty(ctx, s);
     }
     CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, false, false, ctx->stats_on != 0, ctx->stream));
     ctx->launches += 1;
@@ -943,7 +993,9 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
       const int b = order[i];
       const int y0 = b * rows, y1 = y0 + rows < H ? y0 + rows : H;
       ctx->band_expect[b] += ctas_x * (unsigned)((y1 - y0 + 7) / 8);
-      const size_t off = (size_t)y0 * ctx->width, cnt = (size_t)(y1 - y0) * ctx->width, n = ctx->n();
+      const int c0 = y0 > clip_a ? y0 : clip_a, c1 = y1 < clip_b ? y1 : clip_b;  // the band's rows that can hold hits
+      if (c0 >= c1) continue;
+      const size_t off = (size_t)c0 * ctx->width, cnt = (size_t)(c1 - c0) * ctx->width, n = ctx->n();
       cudaStream_t cs = (ctx->copy_streams > 1 && (i & 1)) ? ctx->copy_stream2 : ctx->copy_stream;
       CUresult wr = wait_value_fn()(cs, (CUdeviceptr)(uintptr_t)(ctx->d_band_done + b), ctx->band_expect[b],
                                     CU_STREAM_WAIT_VALUE_GEQ);
@@ -962,14 +1014,29 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     ctx->copy_pending[s] = true;
     return 0;
   }
+  // band-per-launch path (and the single band of pipelined sequences): the same row clipping as above
+  int clip_a = 0, clip_b = H;
+  if (to_host && !direct) {
+    if (ctx->clip_copies && ctx->row_mode == 1 && !ctx->slab && !raw_only && p->num_parts == 1) {
+      unsigned ta, tb;
+      hit_tile_rows(a.cam, a.box, H, (unsigned)((H + 7) / 8), ta, tb);
+      clip_a = (int)ta * 8 - 8 > 0 ? (int)ta * 8 - 8 : 0;
+      clip_b = (int)tb * 8 + 8 < H ? (int)tb * 8 + 8 : H;
+      if (clip_a >= clip_b) clip_a = clip_b = 0;
+      staging_clean_outside(ctx, s, clip_a, clip_b, ctx->dtype == SPV_F32 ? -1.f : 0.f);
+    } else {
+      staging_dirty(ctx, s);
+    }
+  }
   for (int y0 = 0; y0 < H; y0 += rows) {
     const int y1 = y0 + rows < H ? y0 + rows : H;
     a.y_begin = y0;
     a.y_end = y1;
     CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, ctx->skipping > 0, ctx->slab, ctx->stats_on != 0, ctx->stream));
     ctx->launches += 1;
-    if (to_host && !direct) {
-      const size_t off = (size_t)y0 * ctx->width, cnt = (size_t)(y1 - y0) * ctx->width, n = ctx->n();
+    const int c0 = y0 > clip_a ? y0 : clip_a, c1 = y1 < clip_b ? y1 : clip_b;
+    if (to_host && !direct && c0 < c1) {
+      const size_t off = (size_t)c0 * ctx->width, cnt = (size_t)(c1 - c0) * ctx->width, n = ctx->n();
       CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
       CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
       // the band's rows of the value plane and of the alpha plane in ONE 2-D copy (2 "rows" one plane apart)
@@ -1212,6 +1279,7 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   const int s = ctx->slot;
   const size_t n = ctx->n();
   if (to_host && ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // staging about to be rewritten
+  if (to_host) staging_dirty(ctx, s);
   CU(launch_iso(a, fmt_of(ctx), linear, ctx->sampler == SPV_SAMPLER_EXACT, ctx->stats_on != 0, ctx->stream));
   ctx->launches += 1;
   if (to_host && post) {
@@ -1465,6 +1533,7 @@ SPV_API int spv_read_many(spv_ctx *ctx, float *out, float *alpha, float *depth, 
   const size_t n = ctx->n();
   // [out | alpha | depth | occ | normals]: MIP wrote the first two planes, iso all seven
   const size_t planes = (depth || normals || occ) ? 7 : 2;
+  staging_dirty(ctx, ctx->slot);
   CU(cudaMemcpyAsync(ctx->hpin, ctx->dbuf, planes * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (out) memcpy(out, ctx->hpin, n * sizeof(float));
@@ -1479,6 +1548,7 @@ SPV_API int spv_read_pinned(spv_ctx *ctx, int planes, float **host) {
   BIND();
   if (planes < 1 || planes > 7 || !host) return fail(ctx, SPV_EINVAL, "spv_read_pinned: planes must be 1..7");
   if (ctx->copy_pending[ctx->slot]) CU(cudaEventSynchronize(ctx->ev_copied[ctx->slot]));  // same staging memory
+  staging_dirty(ctx, ctx->slot);
   CU(cudaMemcpyAsync(ctx->hpin, ctx->dbuf, (size_t)planes * ctx->n() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   *host = ctx->hpin;
@@ -1504,6 +1574,7 @@ SPV_API int spv_read_pinned_async(spv_ctx *ctx, int planes) {
   BIND();
   if (planes < 1 || planes > 7) return fail(ctx, SPV_EINVAL, "spv_read_pinned_async: planes must be 1..7");
   const int s = ctx->slot;
+  staging_dirty(ctx, s);
   CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
   CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
   CU(cudaMemcpyAsync(ctx->hpin_s[s], ctx->dbuf_s[s], (size_t)planes * ctx->n() * sizeof(float), cudaMemcpyDeviceToHost,

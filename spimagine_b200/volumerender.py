@@ -393,6 +393,9 @@ class VolumeRenderer(object):
             if len(cache) > 8:
                 cache.clear()
             v = cache[key] = np.ctypeslib.as_array(host, shape=(count,))
+            # read-only: libspimcuda keeps track of which staging rows already hold the miss values and does not
+            # copy them again (spv_set_tuning knob 9); callers get views (pinned_outputs=True) or copies of this
+            v.flags.writeable = False
         return v
 
     def _fetch(self, planes):

@@ -399,3 +399,70 @@ def test_read_back_row_orders_and_band_counts_give_the_same_frame(size):
                 got = np.concatenate([rend.output.ravel(), rend.output_alpha.ravel()])
                 assert got.size == 2 * n and np.array_equal(got, want), (mode, bands)
     rend.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32])
+def test_rows_that_cannot_hold_hits_are_not_copied_but_read_the_same(dtype):
+    """spv_render_mip_to_host leaves out the rows the box cannot project to (tuning knob 9): the pinned staging holds
+    their miss values already.  Every frame must equal the frame with all rows copied -- across cameras that move the
+    box around the image, box boundaries, both projections, interleaved iso-surface frames and other read paths
+    that scribble over the same staging, both output slots, and a change of the volume's element type."""
+    from spimagine_b200 import VolumeRenderer
+    from spimagine_b200.utils.transform_matrices import mat4_ortho, mat4_translate, mat4_rotation, mat4_perspective
+    vol = scenes.vol_g(48, dtype, seed=4)
+    peak = float(vol.max())
+    a = VolumeRenderer((256, 384), pinned_outputs=True)      # clipped copies (default)
+    b = VolumeRenderer((256, 384))
+    try:
+        b._check(b._lib.spv_set_tuning(b._ctx, 9, 0))         # every row copied
+        for r in (a, b):
+            r.set_data(vol)
+            r.set_max_val(peak)
+        rng = np.random.default_rng(0)
+        cams = []
+        for i in range(40):
+            M = np.dot(mat4_translate(rng.uniform(-1.5, 1.5), rng.uniform(-2.5, 2.5), rng.uniform(-9, -2.2)),
+                       mat4_rotation(rng.uniform(0, 6.3), *rng.normal(size=3)))
+            cams.append((M, mat4_perspective(60, 1., .1, 20) if i % 5 else mat4_ortho(-2, 2, -3, 3, -10, 10)))
+        cams.append((mat4_translate(0, 0, -.5), mat4_perspective(60, 1., .1, 20)))      # inside the volume
+        cams.append((mat4_translate(0, 40., -4), mat4_perspective(60, 1., .1, 20)))     # box off screen
+        n_clipped = 0
+        for i, (M, P) in enumerate(cams):
+            box = [-1, 1, -1, 1, -1, 1] if i % 3 else [-.5, .8, -.3, .4, -1, 1]
+            for r in (a, b):
+                r.set_projection(P)
+                r.set_modelView(M)
+                r.set_box_boundaries(box)
+            if i % 7 == 3:                                     # other writers of the same staging in between
+                a.render(method="iso_surface", maxVal=peak)
+                _ = a.output_depth
+            if i % 11 == 5:
+                for _ in a.render_sequence([M, M, M], method="iso_surface" if i % 2 else "max_project"):
+                    pass
+            a.render()
+            b.render()
+            assert np.array_equal(a.output, b.output), i
+            assert np.array_equal(a.output_alpha, b.output_alpha), i
+            assert not a.output.flags.writeable
+            n_clipped += int(not (a.output_alpha[0] != a.output_alpha[0, 0]).any())
+        assert n_clipped > 10
+        seq = [M for M, _ in cams[:12]]
+        a.set_box_boundaries([-1, 1, -1, 1, -1, 1])
+        b.set_box_boundaries([-1, 1, -1, 1, -1, 1])
+        got = [(np.array(r.output), np.array(r.output_alpha)) for r in a.render_sequence(seq)]
+        for M, (o, al) in zip(seq, got):
+            b.set_modelView(M)
+            b.render()
+            assert np.array_equal(o, b.output) and np.array_equal(al, b.output_alpha)
+        # another element type: the alpha plane's miss value changes (0 <-> -1)
+        other = scenes.vol_g(48, np.float32 if dtype == np.uint16 else np.uint16, seed=5)
+        for r in (a, b):
+            r.set_data(other)
+            r.set_max_val(float(other.max()))
+            r.set_modelView(cams[1][0])
+            r.render()
+        assert np.array_equal(a.output, b.output) and np.array_equal(a.output_alpha, b.output_alpha)
+    finally:
+        a.close()
+        b.close()
