@@ -436,7 +436,14 @@ def test_rows_that_cannot_hold_hits_are_not_copied_but_read_the_same(dtype):
                 r.set_box_boundaries(box)
             if i % 7 == 3:                                     # other writers of the same staging in between
                 a.render(method="iso_surface", maxVal=peak)
-                _ = a.output_depth
+                b.render(method="iso_surface", maxVal=peak)
+                assert np.array_equal(a.output, b.output) and np.array_equal(a.output_alpha, b.output_alpha), i
+                if i % 2:
+                    assert np.array_equal(a.output_depth, b.output_depth)
+                    assert np.array_equal(a.output, b.output) and np.array_equal(a.output_alpha, b.output_alpha), i
+                a.render(method="iso_surface_raw", maxVal=peak)
+                b.render(method="iso_surface_raw", maxVal=peak)
+                assert np.array_equal(a.output, b.output) and np.array_equal(a.output_alpha, b.output_alpha), i
             if i % 11 == 5:
                 for _ in a.render_sequence([M, M, M], method="iso_surface" if i % 2 else "max_project"):
                     pass
