@@ -53,7 +53,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=720)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--vol", type=int, default=VOL_N)
+    ap.add_argument("--vol", type=int, default=None,
+                    help="edge of the synthetic volume (default: %d; 1024 for the iso workload = configs[2])" % VOL_N)
     ap.add_argument("--img", type=int, default=IMG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="sweep", choices=["sweep", "slab", "timelapse", "iso", "blur", "keyframes"],
@@ -77,7 +78,10 @@ def parse():
     ap.add_argument("--composite", default="peer", choices=["peer", "nccl"],
                     help="slab workload: peer = partials stored straight into the band owners' memory over NVLink "
                          "(spv_render_mip_composite); nccl = all-reduce(MAX) of the raw plane")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.vol is None:
+        args.vol = 1024 if args.workload == "iso" else VOL_N
+    return args
 
 
 def sweep_cameras(n=SWEEP):
