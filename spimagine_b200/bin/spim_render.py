@@ -125,7 +125,9 @@ def main(argv=None):
     pos = min(max(args.pos, 0), len(container) - 1)  # fromSpimFolder clamps (imgutils.py:133-135)
     data = container[pos]
 
-    rend = VolumeRenderer((args.width, args.width), device=args.device)
+    device = args.device if args.device is not None else (
+        int(os.environ["LOCAL_RANK"]) if "LOCAL_RANK" in os.environ else None)
+    rend = VolumeRenderer((args.width, args.width), device=device)
     try:
         rend.set_data(data)
         rend.set_units(args.units)
@@ -138,9 +140,12 @@ def main(argv=None):
             outdir = args.output if os.path.isdir(args.output) or not os.path.splitext(args.output)[1] \
                 else (os.path.dirname(args.output) or ".")
             lut = np.repeat(np.linspace(0, 1, 256)[:, None], 3, 1)
+            # under torchrun (one process per GPU) every rank records its share of the frames
             names = keyframes.record_keyframes(rend, keyList, args.frames, outdir, lut=lut,
                                                source=container if len(container) > 1 else None,
-                                               isPerspective=not args.ortho)
+                                               isPerspective=not args.ortho,
+                                               rank=int(os.environ.get("RANK", "0")),
+                                               world=int(os.environ.get("WORLD_SIZE", "1")))
             print("%d frames written to %s" % (len(names), outdir))
             return 0
 

@@ -24,7 +24,8 @@ from .utils.quaternion import Quaternion, quaternion_slerp
 from .utils.transform_matrices import mat4_translate, mat4_scale, mat4_perspective, mat4_ortho
 
 __all__ = ["create_interp_func", "TransformData", "KeyFrame", "KeyFrameList", "KeyFrameEncoder",
-           "KeyFrameDecoder", "camera_of", "apply_transform", "render_keyframes", "record_keyframes"]
+           "KeyFrameDecoder", "camera_of", "apply_transform", "render_keyframes", "record_keyframes",
+           "keyframe_data_positions", "keyframe_times", "frame_name"]
 
 
 def create_interp_func(a):
@@ -290,7 +291,7 @@ def keyframe_times(nFrames):
 
 
 def render_keyframes(renderer, keyList, nFrames, source=None, isPerspective=True, pinned=False, pipelined=True,
-                     iso_planes=7):
+                     iso_planes=7, rank=0, world=1):
     """Generator over (recordPos, transformData, renderer) for the nFrames frames of the record loop;
     renderer.output / output_alpha (+ the iso planes) hold that frame when it is yielded.
 
@@ -301,8 +302,13 @@ def render_keyframes(renderer, keyList, nFrames, source=None, isPerspective=True
     pinned      source[t] are page-locked arrays (asynchronous uploads)
     pipelined   runs of frames with the same render method go through render_sequence
     iso_planes  7: every result plane of an iso-surface frame is read back; 2: only output and output_alpha (what a
-                recorded frame shows), the other planes stay on the device and read as None"""
-    times = keyframe_times(nFrames)
+                recorded frame shows), the other planes stay on the device and read as None
+    rank, world this process renders frames rank + 1, rank + 1 + world, ... of the loop (one process per GPU, every one
+                with the whole volume or time series; no data-path collective: frames are independent)"""
+    if not (0 <= rank < world):
+        raise ValueError("need 0 <= rank < world")
+    times = keyframe_times(nFrames)[rank::world]
+    nFrames = len(times)
     tds = [keyList.getTransform(t) for _, t in times]
     state = {"pos": None}
 
@@ -346,6 +352,17 @@ def frame_name(recordPos, nFrames):
     return "output_%s.png" % str(recordPos).zfill(int(np.log10(nFrames) + 1))
 
 
+def keyframe_data_positions(keyList, nFrames, n_time_points, rank=0, world=1):
+    """Time points the record loop asks for, in order and without immediate repeats: the `frames` argument of a
+    frames.FrameSource that feeds render_keyframes(source=...) (its reader prefetches in exactly this order)."""
+    out = []
+    for _, t in keyframe_times(nFrames)[rank::world]:
+        pos = int(np.clip(keyList.getTransform(t).dataPos, 0, n_time_points - 1))
+        if not out or out[-1] != pos:
+            out.append(pos)
+    return out
+
+
 def record_keyframes(renderer, keyList, nFrames, dirName, lut=None, mode_black=True, **kw):
     """The GUI's record button without the GUI: every frame of the path as dirName/output_NNN.png.  The reference
     grabs the GL frame buffer (LUT-coloured, alpha-blended onto the background, texture.frag:8-38); here the same
@@ -355,7 +372,7 @@ def record_keyframes(renderer, keyList, nFrames, dirName, lut=None, mode_black=T
     if lut is not None:
         renderer.set_lut(lut)
     names = []
-    for pos, td, r in render_keyframes(renderer, keyList, nFrames, pipelined=False, **kw):
+    for pos, td, r in render_keyframes(renderer, keyList, nFrames, pipelined=False, **kw):  # kw: rank=, world=, source=, ...
         rgba = r.output_rgba(mode_black=mode_black)
         name = os.path.join(dirName, frame_name(pos, nFrames))
         Image.fromarray(np.ascontiguousarray(rgba[::-1]), "RGBA").save(name)

@@ -272,3 +272,88 @@ def test_record_and_cli(tmp_path):
         r.close()
     with pytest.raises(ValueError):
         spim_render.main(["-f", "czi", "-i", tif])
+
+
+# ------------------------------------------------------------------ frames of the record loop sharded over ranks
+class _FakeRenderer(object):
+    """stands in for VolumeRenderer on the CPU: records the setter calls, render() does nothing"""
+
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        if name.startswith("set_"):
+            return lambda v: self.calls.append((name, v))
+        raise AttributeError(name)
+
+    def update_data(self, vol, pinned=False):
+        self.calls.append(("update_data", int(vol[0, 0, 0])))
+
+    def set_data(self, vol):
+        self.dataImg = type("I", (), {"shape": vol.shape[::-1], "dtype": vol.dtype})()
+        self.calls.append(("set_data", int(vol[0, 0, 0])))
+
+    def render(self, method="max_project"):
+        self.calls.append(("render", method))
+
+
+def _shard(rank, world, n_frames=23, n_t=6):
+    keys = _path(n_t)
+    source = [np.full((2, 2, 2), t, np.uint16) for t in range(n_t)]
+    r = _FakeRenderer()
+    got = [(pos, td.dataPos, td.isIso) for pos, td, _ in kf.render_keyframes(
+        r, keys, n_frames, source=source, pipelined=False, rank=rank, world=world)]
+    uploads = [v for name, v in r.calls if name in ("set_data", "update_data")]
+    return got, uploads, kf.keyframe_data_positions(keys, n_frames, n_t, rank, world)
+
+
+def test_record_loop_sharded_over_ranks_covers_every_frame_once():
+    keys = _path(6)
+    for world in (1, 2, 3, 8):
+        shards = [_shard(r, world) for r in range(world)]
+        frames = sorted(f for got, _, _ in shards for f in got)
+        assert [f[0] for f in frames] == list(range(1, 24))
+        for pos, data_pos, iso in frames:
+            td = keys.getTransform(pos / 23.)
+            assert (data_pos, iso) == (td.dataPos, td.isIso)
+        for r, (got, uploads, order) in enumerate(shards):
+            assert [g[0] for g in got] == list(range(r + 1, 24, world))
+            assert uploads == order                     # a time point is uploaded only when dataPos changes
+    with pytest.raises(ValueError):
+        next(kf.render_keyframes(_FakeRenderer(), keys, 5, rank=2, world=2))
+
+
+def _kf_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        got, uploads, order = _shard(rank, world)
+        mine = torch.zeros(24, dtype=torch.int64)
+        for pos, _, _ in got:
+            mine[pos] += 1
+        dist.all_reduce(mine)                            # how often every frame was rendered, over all ranks
+        q.put((rank, mine[1:].tolist(), uploads == order))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_record_loop_over_a_gloo_group():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_kf_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(counts == [1] * 23 and ok for _, counts, ok in results)
