@@ -50,6 +50,33 @@ __global__ void __launch_bounds__(256) pad_kernel(const T *__restrict__ src, flo
   }
 }
 
+// pad_kernel where x needs no padding (nx a power of two, a multiple of 4) and the rows are 4-element aligned: four
+// elements per thread through one vector load (a 2-byte load per thread leaves most of every sector request unused:
+// 462 us against 250 us for the 512^3 uint16 volume)
+template <typename T> struct alignas(4 * sizeof(T)) Vec4 { T v[4]; };
+template <typename T>
+__global__ void __launch_bounds__(256) pad_rows_kernel(const T *__restrict__ src, float *__restrict__ dst, Dims d) {
+  const int by = (d.py - d.ny + 1) >> 1, bz = (d.pz - d.nz + 1) >> 1;
+  const size_t rows = (size_t)d.py * d.pz;
+  const int quads = d.nx >> 2;                     // a power of two (nx is one)
+  const int qt = quads < 256 ? quads : 256;        // threads along a row; the CTA covers 256 / qt rows at a time
+  const int rpb = 256 / qt, tq = threadIdx.x % qt, tr = threadIdx.x / qt;
+  for (size_t row = (size_t)blockIdx.x * rpb + tr; row < rows; row += (size_t)gridDim.x * rpb) {
+    const int y = (int)(row % (size_t)d.py), z = (int)(row / (size_t)d.py);
+    int sy = y - by, sz = z - bz;
+    sy += sy < 0 ? d.ny : 0;
+    sy -= sy >= d.ny ? d.ny : 0;
+    sz += sz < 0 ? d.nz : 0;
+    sz -= sz >= d.nz ? d.nz : 0;
+    const Vec4<T> *s = reinterpret_cast<const Vec4<T> *>(src + ((size_t)sz * d.ny + sy) * d.nx);
+    float4 *o = reinterpret_cast<float4 *>(dst + row * d.px);
+    for (int q = tq; q < quads; q += qt) {
+      const Vec4<T> t = s[q];
+      o[q] = make_float4((float)t.v[0], (float)t.v[1], (float)t.v[2], (float)t.v[3]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) spectrum_kernel(const float2 *__restrict__ F, float *__restrict__ out, Dims d,
                                                        float scale, int take_log) {
   const int ox = (d.px - d.nx) >> 1, oy = (d.py - d.ny) >> 1, oz = (d.pz - d.nz) >> 1;
@@ -211,6 +238,18 @@ SPF_API int spf_spectrum(spf_plan *p, const void *src, int on_device, int src_ty
   PCU(cudaEventRecord(p->ev0, p->stream));
   {
     const dim3 block(256), grid((unsigned)((d.px + 255) / 256), (unsigned)((size_t)d.py * d.pz < 65535 ? (size_t)d.py * d.pz : 65535));
+    const bool rows_fast = d.px == d.nx && d.nx % 4 == 0 && ((uintptr_t)dsrc % (4 * es)) == 0;
+    if (rows_fast) {
+      const int quads = d.nx / 4, rpb = 256 / (quads < 256 ? quads : 256);
+      const size_t ctas = ((size_t)d.py * d.pz + rpb - 1) / rpb;
+      const dim3 g4((unsigned)(ctas < (size_t)148 * 64 ? ctas : (size_t)148 * 64));
+      switch (src_type) {
+        case SRC_U8: pad_rows_kernel<uint8_t><<<g4, block, 0, p->stream>>>((const uint8_t *)dsrc, p->d_real, d); break;
+        case SRC_I16: pad_rows_kernel<int16_t><<<g4, block, 0, p->stream>>>((const int16_t *)dsrc, p->d_real, d); break;
+        case SRC_U16: pad_rows_kernel<uint16_t><<<g4, block, 0, p->stream>>>((const uint16_t *)dsrc, p->d_real, d); break;
+        default: pad_rows_kernel<float><<<g4, block, 0, p->stream>>>((const float *)dsrc, p->d_real, d); break;
+      }
+    } else
     switch (src_type) {
       case SRC_U8: pad_kernel<uint8_t><<<grid, block, 0, p->stream>>>((const uint8_t *)dsrc, p->d_real, d); break;
       case SRC_I16: pad_kernel<int16_t><<<grid, block, 0, p->stream>>>((const int16_t *)dsrc, p->d_real, d); break;
