@@ -2,7 +2,7 @@
 
 Mirrors the part of the reference's data model that feeds the renderer during timelapse playback
 (spimagine/models/data_model.py: GenericData :59-95, SpimData :97-148, TiffData :178-218, RawData :221-261,
-RawMultipleFiles / TiffFolderData / TiffMultipleFiles :262-404, NumpyData :408-432, the
+RawMultipleFiles / TiffFolderData / TiffMultipleFiles :262-404, NumpyData :408-432, XwingData :475-515, the
 prefetching DataLoadThread / DataModel :600-757; spimagine/utils/imgutils.py: parseIndexFile :48-66, parseMetaFile
 :69-86, fromSpimFolder :129-146, createSpimFolder :162-191) -- same class names, same `sizeT() / size() /
 stackUnits / container[pos]` protocol -- with one change in where the bytes land: `FrameSource` reads time points
@@ -289,6 +289,62 @@ class RawMultipleFiles(_FilePerTimePoint):
                 if not n:
                     raise IOError("%s: short read" % fname)
                 got += n
+
+
+def parse_index_xwing(fname):
+    """(z, y, x) of an xwing stack: the last three numbers of the first line of default.index.txt, reversed
+    (imgutils.py:89-107)"""
+    try:
+        with open(fname) as f:
+            items = f.readline().replace("\t", ",").replace("\n", "").split(",")
+        return [int(i) for i in items[-3:]][::-1]
+    except Exception as e:
+        print(e)
+        print("couldnt parse ", fname)
+        return None
+
+
+def parse_meta_xwing(fName):
+    """pixel sizes (dx, dy, dz) from the JSON on the first line of default.metadata.txt (imgutils.py:110-127)"""
+    import json
+    try:
+        with open(fName) as f:
+            s = json.loads(f.readline())
+        return (float(s["VoxelDimX"]), float(s["VoxelDimY"]), float(s["VoxelDimZ"]))
+    except Exception as e:
+        print(e)
+        print("coulndt parse ", fName)
+        return (1., 1., 1.)
+
+
+class XwingData(RawMultipleFiles):
+    """xwing data saved in folder fName (data_model.py:475-515): default.index.txt, default.metadata.txt and one
+    little-endian uint16 stack per time point under stacks/default/*.raw"""
+
+    def __init__(self, dirname=""):
+        GenericData.__init__(self, dirname)
+        self.fNames = self.fnames = self._stack_names = []
+        if dirname:
+            try:
+                names = sorted(glob.glob(os.path.join(dirname, "stacks", "default", "*.raw")))
+                shape = parse_index_xwing(os.path.join(dirname, "default.index.txt"))
+                if shape is None or not names:
+                    raise IOError("no index file or no stacks")
+                self.fNames = self.fnames = self._stack_names = names
+                self._dtype = np.dtype("<u2")
+                self.stackSize = [len(names)] + shape
+                self.stackUnits = parse_meta_xwing(os.path.join(dirname, "default.metadata.txt"))
+            except Exception as e:
+                print(e)
+                self.fNames = self.fnames = self._stack_names = []
+                raise Exception("couldnt open %s as XwingData" % dirname)
+
+    def __getitem__(self, pos):
+        if self.stackSize and len(self._stack_names) > 0:
+            if pos < 0 or pos >= self.stackSize[0]:
+                raise IndexError("0 <= pos <= %i, but pos = %i" % (self.stackSize[0] - 1, pos))
+            return super(XwingData, self).__getitem__(pos)
+        return None
 
 
 class TiffMultipleFiles(_FilePerTimePoint):

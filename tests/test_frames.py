@@ -151,3 +151,27 @@ def test_timelapse_player_streams_from_a_spim_folder(tmp_path):
         assert seen == list(range(rank, 6, 2))
         src.close()
         player.close()
+
+
+def test_xwing_folder(tmp_path):
+    """data_model.py:475-515 / imgutils.py:89-127: index, JSON metadata, one raw stack per time point."""
+    data = _timelapse(3, (5, 6, 7), seed=3)
+    root = tmp_path / "xw"
+    (root / "stacks" / "default").mkdir(parents=True)
+    for t in range(3):
+        data[t].astype("<u2").tofile(str(root / "stacks" / "default" / ("%06d.raw" % t)))
+    (root / "default.index.txt").write_text("0\t0.000\t7, 6, 5\n1\t0.100\t7, 6, 5\n")
+    (root / "default.metadata.txt").write_text('{"VoxelDimX": 0.26, "VoxelDimY": 0.26, "VoxelDimZ": 1.5}\n{"x": 1}\n')
+    d = frames.XwingData(str(root))
+    assert d.size() == [3, 5, 6, 7] and d.stackUnits == (.26, .26, 1.5) and d.dtype == np.uint16
+    for t in range(3):
+        assert np.array_equal(d[t], data[t])
+    with pytest.raises(IndexError):
+        d[3]
+    out = np.empty((5, 6, 7), np.uint16)
+    d.read_into(1, out)
+    assert np.array_equal(out, data[1])
+    (root / "default.metadata.txt").write_text("not json\n")
+    assert frames.XwingData(str(root)).stackUnits == (1., 1., 1.)
+    with pytest.raises(Exception, match="couldnt open"):
+        frames.XwingData(str(tmp_path / "missing"))
