@@ -4,7 +4,8 @@
 //                    (np.pad(mode="wrap") of gputools.pad_to_shape), element type converted on the fly
 //   cufftExecR2C     (Pz, Py, Px) real -> (Pz, Py, Px/2 + 1) complex: the volume is real, so F[-k] = conj F[k]
 //   spectrum_kernel  out[z][y][x] = s |F[k]|, k = (i + o + P/2) mod P per axis, o = floor(d / 2), s = 1/sqrt(Pz Py Px);
-//                    coefficients with kx > Px/2 are read from the mirrored index; optional log2(0.001 + .)
+//                    outputs with kx > Px/2 take the magnitude of the mirrored (stored) coefficient; optional
+//                    log2(0.001 + .)
 // Both passes are HBM-bound streaming kernels (4 + es bytes per padded voxel, 8 + 4 bytes per output voxel).
 #include <cuda_runtime.h>
 #include <cufft.h>
@@ -77,24 +78,34 @@ __global__ void __launch_bounds__(256) pad_rows_kernel(const T *__restrict__ src
   }
 }
 
+// One thread per stored coefficient F[kz][ky][kx], kx <= Px/2: its magnitude goes to the output voxel it maps to
+// (i = (k - o - P/2) mod P per axis, if inside the crop) and, for 0 < kx < Px/2, to the voxel of the mirrored index -k
+// as well (F[-k] = conj F[k] is not stored).  Every coefficient is read once and every output written once: the
+// first version computed every output from its own read, i.e. read the half spectrum twice (1.03 GB instead of 0.54).
 __global__ void __launch_bounds__(256) spectrum_kernel(const float2 *__restrict__ F, float *__restrict__ out, Dims d,
                                                        float scale, int take_log) {
   const int ox = (d.px - d.nx) >> 1, oy = (d.py - d.ny) >> 1, oz = (d.pz - d.nz) >> 1;
   const int hx = d.px >> 1, cx = hx + 1;  // complex coefficients per row
-  const size_t rows = (size_t)d.ny * d.nz;
-  for (size_t row = blockIdx.y; row < rows; row += gridDim.y) {
-    const int y = (int)(row % (size_t)d.ny), z = (int)(row / (size_t)d.ny);
-    const int ky = (y + oy + (d.py >> 1)) & (d.py - 1), kz = (z + oz + (d.pz >> 1)) & (d.pz - 1);
-    const int my = (d.py - ky) & (d.py - 1), mz = (d.pz - kz) & (d.pz - 1);  // the mirrored row
-    const float2 *direct = F + ((size_t)kz * d.py + ky) * cx;
-    const float2 *mirror = F + ((size_t)mz * d.py + my) * cx;
-    float *o = out + row * d.nx;
-    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < d.nx; x += gridDim.x * blockDim.x) {
-      const int kx = (x + ox + hx) & (d.px - 1);
-      const float2 c = kx <= hx ? direct[kx] : mirror[d.px - kx];
+  const int mx = d.px - 1, my_ = d.py - 1, mz_ = d.pz - 1;
+  const size_t rows = (size_t)d.py * d.pz;
+  for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int ky = (int)(row % (size_t)d.py), kz = (int)(row / (size_t)d.py);
+    const int y = (ky - oy - (d.py >> 1)) & my_, z = (kz - oz - (d.pz >> 1)) & mz_;                    // direct row
+    const int y2 = (((d.py - ky) & my_) - oy - (d.py >> 1)) & my_, z2 = (((d.pz - kz) & mz_) - oz - (d.pz >> 1)) & mz_;
+    const bool drow = y < d.ny && z < d.nz, mrow = y2 < d.ny && z2 < d.nz;
+    if (!drow && !mrow) continue;
+    const float2 *f = F + row * cx;
+    float *od = out + ((size_t)z * d.ny + y) * d.nx, *om = out + ((size_t)z2 * d.ny + y2) * d.nx;
+    for (int kx = threadIdx.x; kx <= hx; kx += blockDim.x) {
+      const float2 c = f[kx];
       float v = scale * sqrtf(c.x * c.x + c.y * c.y);
       if (take_log) v = log2f(0.001f + v);
-      o[x] = v;
+      const int x = (kx - ox - hx) & mx;
+      if (drow && x < d.nx) od[x] = v;
+      if (kx > 0 && kx < hx) {
+        const int x2 = (d.px - kx - ox - hx) & mx;
+        if (mrow && x2 < d.nx) om[x2] = v;
+      }
     }
   }
 }
@@ -261,7 +272,8 @@ SPF_API int spf_spectrum(spf_plan *p, const void *src, int on_device, int src_ty
   }
   PFFT(cufftExecR2C(p->fft, p->d_real, (cufftComplex *)p->d_freq));
   {
-    const dim3 block(256), grid((unsigned)((nx + 255) / 256), (unsigned)((size_t)ny * nz < 65535 ? (size_t)ny * nz : 65535));
+    const size_t prow = (size_t)d.py * d.pz;
+    const dim3 block(256), grid((unsigned)(prow < (size_t)148 * 64 ? prow : (size_t)148 * 64));
     const float scale = (float)(1. / sqrt((double)np));
     spectrum_kernel<<<grid, block, 0, p->stream>>>(p->d_freq, p->d_out, d, scale, take_log != 0);
     PCU(cudaGetLastError());
