@@ -113,3 +113,16 @@ def test_fast_4x4_inverse_is_scipy_inv_bit_for_bit():
         _inv4(np.zeros((4, 4)))
     with pytest.raises(ValueError):
         _inv4(np.full((4, 4), np.nan))
+
+
+def test_matrix_helpers_equal_the_references_own(tmp_path):
+    """tests/golden/matrices_ref.json holds the reference's transform_matrices.py evaluated on fixed arguments
+    (tests/golden/make_matrix_golden.py): same values, same dtypes."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "matrices_ref.json")) as f:
+        calls = json.load(f)["calls"]
+    assert len(calls) >= 20
+    for c in calls:
+        got = np.asarray(getattr(tm, c["fn"])(*c["args"]))
+        assert str(got.dtype) == c["dtype"], (c["fn"], got.dtype, c["dtype"])
+        assert np.array_equal(got.astype(np.float64), np.array(c["value"])), (c["fn"], c["args"])
