@@ -152,7 +152,9 @@ class SpimData(GenericData):
 
 class RawData(GenericData):
     """one raw file holding a (t,) z, y, x stack of `dtype` (data_model.py:221-261).  The reference loads the whole
-    file with np.fromfile; here it is memory-mapped, so that a timelapse larger than host memory plays too."""
+    file with np.fromfile; here it is memory-mapped, so that a timelapse larger than host memory plays too.  A 3-d
+    shape is one time point here; the reference's padding expression ((1,) * (len(shape) - 4), :236-237) is a no-op
+    and leaves it 3-d, which makes every slice a time point of a 2-d image."""
 
     def __init__(self, fName="", shape=None, dtype=np.uint16):
         GenericData.__init__(self, fName)
@@ -256,7 +258,9 @@ class _FilePerTimePoint(GenericData):
 
 
 class RawMultipleFiles(_FilePerTimePoint):
-    """2/3d raw data, one file per time point (data_model.py:262-308; shape = (z, y, x) or (y, x) of ONE file)"""
+    """2/3d raw data, one file per time point (data_model.py:262-308).  shape describes ONE file: (1, z, y, x) as
+    the reference wants it (it drops the first entry, :290), or (z, y, x) / (y, x), which the reference cannot
+    reshape."""
 
     def __init__(self, fnames=[], shape=None, dtype=None):
         GenericData.__init__(self, "[" + ", ".join(fnames) + "]")
@@ -268,6 +272,12 @@ class RawMultipleFiles(_FilePerTimePoint):
             if shape is None or dtype is None:
                 raise ValueError("RawMultipleFiles needs shape and dtype (the reference asks for them in a dialog)")
             shape = tuple(int(s) for s in shape)
+            if len(shape) == 4:
+                if shape[0] != 1:
+                    raise ValueError("a 4-d shape describes one file: its first entry must be 1")
+                shape = shape[1:]
+            elif len(shape) > 4:
+                raise ValueError("shape should have length of at most 4!")
             shape = (1,) * (3 - len(shape)) + shape
             self._dtype = np.dtype(dtype)
             need = int(np.prod(shape, dtype=np.int64)) * self._dtype.itemsize
@@ -406,7 +416,7 @@ class NumpyData(GenericData):
 
     def __init__(self, data, stackUnits=[1., 1., 1.], copy=False):
         GenericData.__init__(self, "NumpyData")
-        if data.ndim not in (3, 4):
+        if data.ndim not in (2, 3, 4):
             raise TypeError("data should be 3 or 4 dimensional! shape = %s" % str(data.shape))
         self.data = (data.copy() if copy else data).reshape((1,) * (4 - data.ndim) + data.shape)
         self.stackSize = self.data.shape

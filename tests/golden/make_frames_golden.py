@@ -1,0 +1,86 @@
+"""Generates tests/golden/frames_ref.json by reading the synthetic inputs of tests/golden/frames_inputs.py with the
+REFERENCE's own containers (/root/reference/spimagine/models/data_model.py, utils/imgutils.py: SpimData, RawData,
+RawMultipleFiles, XwingData, NumpyData, fromSpimFolder), Qt / tifffile / czifile stubbed, `spimagine` entered as a bare
+namespace.  Recorded per container: size(), sizeT(), stackUnits and dtype / shape / sha1 of every time point.
+np.float and np.asscalar (removed from numpy, used by parseMetaFile) are restored for the run.
+
+    python tests/golden/make_frames_golden.py
+"""
+import hashlib
+import json
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, HERE)
+REF = "/root/reference"
+
+
+def import_reference():
+    class _Anything(object):
+        def __init__(self, *a, **k):
+            pass
+
+        def __getattr__(self, name):
+            return _Anything()
+
+        def __call__(self, *a, **k):
+            return _Anything()
+
+    for name in ("PyQt5", "PyQt5.QtCore", "PyQt5.QtWidgets", "PyQt5.QtGui", "tifffile", "spimagine.lib",
+                 "spimagine.lib.czifile", "spimagine.gui", "spimagine.gui.shape_dtype_dialog"):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+    core = sys.modules["PyQt5.QtCore"]
+    core.QObject = core.QThread = type("QObject", (object,), {"__init__": lambda self, *a, **k: None})
+    core.pyqtSignal = core.QReadWriteLock = _Anything
+    sys.modules["PyQt5"].QtCore = core
+    t = sys.modules["tifffile"]
+    t.TiffFile = t.imsave = t.imread = _Anything
+    sys.modules["spimagine.lib.czifile"].CziFile = _Anything
+    sys.modules["spimagine.gui.shape_dtype_dialog"].ShapeDtypeDialog = _Anything
+    for name in ("spimagine", "spimagine.models", "spimagine.utils"):
+        m = types.ModuleType(name)
+        m.__path__ = [os.path.join(REF, *name.split("."))]
+        sys.modules[name] = m
+    if not hasattr(np, "float"):
+        np.float = float
+    import spimagine.utils.imgutils as imgutils
+    sys.modules["spimagine.utils"].imgutils = imgutils
+    import spimagine.models.data_model as dm
+    return dm, imgutils
+
+
+def describe(c):
+    size = [int(s) for s in c.size()]
+    pts = []
+    for t in range(int(c.sizeT())):
+        a = np.ascontiguousarray(c[t])
+        pts.append({"shape": list(a.shape), "dtype": a.dtype.newbyteorder("=").name if a.dtype.byteorder in "<>" else a.dtype.name,
+                    "sha1": hashlib.sha1(a.tobytes()).hexdigest()})
+    return {"size": size, "sizeT": int(c.sizeT()), "stackUnits": [float(u) for u in c.stackUnits], "points": pts}
+
+
+def main():
+    import frames_inputs
+    dm, imgutils = import_reference()
+    out = {}
+    with tempfile.TemporaryDirectory() as root:
+        for key, (cls, args, kw) in frames_inputs.build(root).items():
+            out[key] = describe(getattr(dm, cls)(*args, **kw))
+        sub = imgutils.fromSpimFolder(os.path.join(root, "spim"), pos=2, count=2)
+        out["fromSpimFolder_pos2_count2"] = {"shape": list(sub.shape), "sha1": hashlib.sha1(np.ascontiguousarray(sub).tobytes()).hexdigest()}
+    with open(os.path.join(HERE, "frames_ref.json"), "w") as f:
+        json.dump({"generator": "tests/golden/make_frames_golden.py (reference data_model / imgutils)", "containers": out}, f, indent=1)
+    for k, v in out.items():
+        print(k, v.get("size"), v.get("stackUnits"))
+
+
+if __name__ == "__main__":
+    main()

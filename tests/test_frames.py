@@ -62,8 +62,9 @@ def test_raw_and_numpy_containers(tmp_path):
         frames.RawData(fn, shape=(1, 1, 4, 6, 5, 8), dtype=np.float32)
     n = frames.NumpyData(data[1])
     assert n.size() == (1, 6, 5, 8) and np.array_equal(n[0], data[1])
+    assert frames.NumpyData(np.zeros((3, 4))).size() == (1, 1, 3, 4)     # 2-d: one slice (data_model.py:416-418)
     with pytest.raises(TypeError):
-        frames.NumpyData(np.zeros((3, 3)))
+        frames.NumpyData(np.zeros(3))
 
 
 @pytest.mark.parametrize("depth", [2, 3, 5])
@@ -175,3 +176,38 @@ def test_xwing_folder(tmp_path):
     assert frames.XwingData(str(root)).stackUnits == (1., 1., 1.)
     with pytest.raises(Exception, match="couldnt open"):
         frames.XwingData(str(tmp_path / "missing"))
+
+
+def test_containers_read_what_the_references_containers_read(tmp_path):
+    """tests/golden/frames_ref.json: the reference's own SpimData / RawData / RawMultipleFiles / XwingData / NumpyData
+    and fromSpimFolder run on the seeded inputs of tests/golden/frames_inputs.py (make_frames_golden.py); this
+    package's containers must report the same sizes and units and return the same bytes for every time point."""
+    import hashlib
+    import json
+    import sys
+    golden_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, golden_dir)
+    try:
+        import frames_inputs
+    finally:
+        sys.path.remove(golden_dir)
+    with open(os.path.join(golden_dir, "frames_ref.json")) as f:
+        ref = json.load(f)["containers"]
+    specs = frames_inputs.build(str(tmp_path))
+    assert set(specs) | {"fromSpimFolder_pos2_count2"} == set(ref)
+    for key, (cls, args, kw) in specs.items():
+        c = getattr(frames, cls)(*args, **kw)
+        want = ref[key]
+        assert [int(s) for s in c.size()] == want["size"] and int(c.sizeT()) == want["sizeT"] == len(c), key
+        assert np.allclose([float(u) for u in c.stackUnits], want["stackUnits"], rtol=1e-12, atol=0), key
+        for t, p in enumerate(want["points"]):
+            a = np.ascontiguousarray(c[t])
+            assert list(a.shape) == p["shape"] and a.dtype.name == p["dtype"], (key, t)
+            assert hashlib.sha1(a.tobytes()).hexdigest() == p["sha1"], (key, t)
+            out = np.empty(a.shape, c.dtype)
+            c.read_into(t, out)
+            assert np.array_equal(out, a)
+    d = frames.SpimData(specs["SpimData"][1][0])
+    sub = np.stack([d[2], d[3]])                       # fromSpimFolder(pos=2, count=2), imgutils.py:129-146
+    want = ref["fromSpimFolder_pos2_count2"]
+    assert list(sub.shape) == want["shape"] and hashlib.sha1(sub.tobytes()).hexdigest() == want["sha1"]
