@@ -167,7 +167,12 @@ class BlurProcessor(ImageProcessor):
         super(BlurProcessor, self).__init__("blur", sigma=sigma)
 
     def _taps(self):
-        h = _gauss_taps(self.sigma)
+        # models/imageprocessor.py:52-55 normalises with `h *= 1. / sum(h)` (BlurXYZProcessor divides, :69): the two
+        # differ in the last float64 bit, so each processor follows its own line
+        N = 2 * self.sigma + 1
+        x = np.arange(-N, N + 1)
+        h = np.exp(-x ** 2 / 2. / self.sigma ** 2)
+        h *= 1. / sum(h)
         return h, h, h
 
     def apply(self, data):

@@ -238,3 +238,40 @@ def test_gpu_filter_errors():
     with pytest.raises(ValueError):
         vf.load(np.zeros((4, 4), np.float32))
     vf.close()
+
+
+def test_processors_against_the_references_own_classes(forc):
+    """tests/golden/processors_ref.json: the reference's imageprocessor.py executed with gputools replaced by a
+    recorder (tests/golden/make_processor_golden.py).  Taps are float64-exact; the spectrum expression agrees with the
+    restatement the GPU tests use; names, kwargs and identity behaviour are the reference's."""
+    import json
+    import os
+    from spimagine_b200 import imageprocessor as ip
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "processors_ref.json")) as f:
+        ref = json.load(f)
+    for key, want in ref["taps"].items():
+        if key.startswith("blur_xyz"):
+            got = ip.BlurXYZProcessor(sx=1., sy=2., sz=3.)._taps()
+        else:
+            got = ip.BlurProcessor(sigma=float(key.split("_")[1]))._taps()
+        assert len(got) == 3
+        for g, w in zip(got, want):
+            assert np.array_equal(np.asarray(g, np.float64), np.array(w)), key
+    data = np.array(ref["fft"]["data"], dtype=ref["fft"]["dtype"])
+    for log in (False, True):
+        want = np.array(ref["fft"]["log_%s" % log]["value"])
+        got = forc.fft_spectrum(data, log=log)
+        assert got.shape == want.shape
+        # the reference's product with the float64 scalar 1/sqrt(size) is float64 under NEP 50, float32 before
+        assert np.allclose(got, want, rtol=3e-7, atol=1e-6 * np.abs(want).max())
+    made = {"copy": ip.CopyProcessor(), "blur": ip.BlurProcessor(), "blur_xyz": ip.BlurXYZProcessor(),
+            "noise": ip.NoiseProcessor(), "fft": ip.FFTProcessor(), "lucy": ip.LucyRichProcessor(),
+            "func": ip.FuncProcessor(lambda d, k=2: d * k, "times", k=3)}
+    for key, want in ref["interface"].items():
+        assert made[key].name == want["name"] and made[key].kwargs == want["kwargs"], key
+        for k, v in want["kwargs"].items():
+            assert getattr(made[key], k) == v
+    vol = np.zeros((2, 2, 2), np.float32)
+    assert (ip.CopyProcessor().apply(vol) is vol) == ref["identity"]["copy"]
+    assert (ip.LucyRichProcessor().apply(vol) is vol) == ref["identity"]["lucy"]
+    assert float(made["func"].apply(np.ones(1))[0]) == ref["identity"]["func"]
