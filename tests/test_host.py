@@ -126,3 +126,58 @@ def test_matrix_helpers_equal_the_references_own(tmp_path):
         got = np.asarray(getattr(tm, c["fn"])(*c["args"]))
         assert str(got.dtype) == c["dtype"], (c["fn"], got.dtype, c["dtype"])
         assert np.array_equal(got.astype(np.float64), np.array(c["value"])), (c["fn"], c["args"])
+
+
+def _host_only_renderer():
+    """A VolumeRenderer without a device: the host-side methods only (the C calls are recorded, not made)."""
+    from spimagine_b200 import VolumeRenderer
+
+    class _NoLib(object):
+        def spv_set_matrices(self, ctx, invP, invM):
+            return 0
+
+    r = VolumeRenderer.__new__(VolumeRenderer)
+    r._lib, r._ctx = _NoLib(), None
+    r._check = lambda rc: None
+    r._invM = np.zeros(16, np.float32)
+    r._invP = np.zeros(16, np.float32)
+    r._invM_ptr, r._invP_ptr = _lib.fp(r._invM), _lib.fp(r._invP)
+    r.projection = tm.mat4_perspective()
+    r.modelView = tm.mat4_identity()      # the constructor's defaults (set before a volume exists)
+    return r
+
+
+def test_host_side_equals_the_references_volumerenderer():
+    """tests/golden/renderer_host_ref.json: the reference's own VolumeRenderer.set_units / set_projection /
+    set_modelView -> update_matrices, _stack_scale_mat and _get_downsampled_data_slices run without OpenCL
+    (tests/golden/make_renderer_host_golden.py).  The float32 matrices handed to the kernels are bit-identical."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "renderer_host_ref.json")) as f:
+        ref = json.load(f)
+    assert len(ref["matrices"]) >= 18
+    for c in ref["matrices"]:
+        r = _host_only_renderer()
+        r.dataImg = type("Img", (), {"shape": tuple(c["shape_xyz"]), "dtype": np.uint16})()
+        r.set_units(c["units"])
+        P = np.array(c["projection"]).astype(c["projection_dtype"])   # the helpers return float32 for some, float64
+        M = np.array(c["modelView"]).astype(c["modelView_dtype"])     # for others: the inverse is taken in that type
+        r.set_projection(P)
+        r.set_modelView(M)
+        assert np.array_equal(np.asarray(r._stack_scale_mat(), np.float64), np.array(c["mScale"]))
+        assert r._invM.dtype == np.float32 == np.dtype(c["invM_dtype"])
+        assert np.array_equal(r._invM.astype(np.float64), np.array(c["invM_f32"])), c["shape_xyz"]
+        assert np.array_equal(r._invP.astype(np.float64), np.array(c["invP_f32"])), c["shape_xyz"]
+        # the caches (scale matrix per shape / units, inverse per projection) must not go stale
+        r.set_units([3., 1., 2.])
+        r.set_units(c["units"])
+        r.set_projection(tm.mat4_perspective(33, 1., .2, 7))
+        r.set_projection(P)
+        assert np.array_equal(r._invM.astype(np.float64), np.array(c["invM_f32"]))
+        assert np.array_equal(r._invP.astype(np.float64), np.array(c["invP_f32"]))
+    for c in ref["downsample"]:
+        r = _host_only_renderer()
+        r.memMax = c["memMax"]
+        r.dtype = np.dtype(c["dtype"]).type
+        s = r._get_downsampled_data_slices(np.zeros(c["shape"], c["dtype"]))
+        got = None if s is None else [[x.start, x.stop, x.step] for x in s]
+        assert got == c["slices"], c
