@@ -181,3 +181,60 @@ def test_host_side_equals_the_references_volumerenderer():
         s = r._get_downsampled_data_slices(np.zeros(c["shape"], c["dtype"]))
         got = None if s is None else [[x.start, x.stop, x.step] for x in s]
         assert got == c["slices"], c
+
+
+def test_set_data_follows_the_references_rules():
+    """tests/golden/setdata_ref.json: the reference's own set_data / set_dtype / set_shape / update_data run with
+    recorders in place of gputools (tests/golden/make_setdata_golden.py) on seeded arrays of eleven element types:
+    the element type the renderer settles on, the image shape, the strided downsampling under a memory budget, the
+    texels that reach the device and the exceptions are the same here.  (Arrays of a type the device converts travel
+    as they are: their texels are what astype gives, which the GPU tests check on the device.)"""
+    import hashlib
+    import json
+    import sys
+    golden = os.path.join(ROOT, "tests", "golden")
+    sys.path.insert(0, golden)
+    try:
+        from make_setdata_golden import make
+    finally:
+        sys.path.remove(golden)
+    with open(os.path.join(golden, "setdata_ref.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) == 32
+
+    class _RecLib(object):
+        def __init__(self):
+            self.calls = []
+
+        def __getattr__(self, name):
+            if not name.startswith("spv_"):
+                raise AttributeError(name)
+            return lambda *a: (self.calls.append((name,) + a[1:]), 0)[1]
+
+    for c in cases:
+        r = _host_only_renderer()
+        r._lib = _RecLib()
+        r.width = r.height = 8
+        r.memMax = c["memMax"]
+        r.stackUnits = np.ones(3)
+        r.set_dtype(np.dtype(c["first"]).type)
+        data = make(c["seed"], tuple(c["shape"]), c["dtype"])
+        if c.get("raises"):
+            with pytest.raises(NotImplementedError):
+                r.set_data(data, autoConvert=c["autoConvert"], copyData=c["copyData"])
+            continue
+        r.set_data(data, autoConvert=c["autoConvert"], copyData=c["copyData"])
+        tag = (c["first"], c["dtype"], c["memMax"])
+        assert np.dtype(r.dtype).name == c["renderer_dtype"], tag
+        assert list(r.dataImg.shape) == c["image_shape_xyz"] and np.dtype(r.dataImg.dtype).name == c["image_dtype"], tag
+        got = None if r.dataSlices is None else [[s.start, s.stop, s.step] for s in r.dataSlices]
+        assert got == c["slices"], tag
+        texels = np.ascontiguousarray(r._data).astype(r.dtype)       # what the device holds after its conversion
+        assert list(texels.shape) == c["uploaded_shape"] and texels.dtype.name == c["uploaded_dtype"], tag
+        assert hashlib.sha1(texels.tobytes()).hexdigest() == c["uploaded_sha1"], tag
+        if np.dtype(c["dtype"]).name == c["renderer_dtype"]:           # no conversion: same reference semantics
+            assert (r._data is data) == c["keeps_callers_array"], tag
+        uploads = [call for call in r._lib.calls if call[0].startswith(("spv_set_volume", "spv_update_volume"))]
+        assert len(uploads) == 1 and uploads[0][0] in ("spv_set_volume", "spv_set_volume_from"), tag
+        nx, ny, nz = uploads[0][-3:]
+        assert [nx, ny, nz] == c["image_shape_xyz"], tag
