@@ -238,3 +238,118 @@ def test_set_data_follows_the_references_rules():
         assert len(uploads) == 1 and uploads[0][0] in ("spv_set_volume", "spv_set_volume_from"), tag
         nx, ny, nz = uploads[0][-3:]
         assert [nx, ny, nz] == c["image_shape_xyz"], tag
+
+
+class _RecordingLib(object):
+    """Stands in for libspimcuda on the CPU: every spv_* call is recorded and answers 0; the two render-to-host
+    calls hand back a zeroed staging buffer, so that the Python side of a frame runs to the end."""
+
+    def __init__(self):
+        self.calls = []
+        self._bufs = []
+
+    def _give_host(self, ref, floats):
+        buf = (ctypes.c_float * floats)()
+        self._bufs.append(buf)
+        ptr = ctypes.cast(buf, _lib._FP)
+        ctypes.memmove(ctypes.addressof(ref._obj), ctypes.addressof(ptr), ctypes.sizeof(ptr))
+
+    def __getattr__(self, name):
+        if not name.startswith("spv_"):
+            raise AttributeError(name)
+
+        def call(*a):
+            rec = [name]
+            for x in a[1:]:
+                obj = getattr(x, "_obj", None)
+                if isinstance(obj, (_lib.MipParams, _lib.IsoParams)):
+                    rec.append({f: (list(getattr(obj, f)) if f == "box" else getattr(obj, f)) for f, _ in obj._fields_})
+                elif isinstance(x, (int, float)):
+                    rec.append(x)
+            self.calls.append(rec)
+            if name in ("spv_render_mip_to_host", "spv_render_iso_to_host") and getattr(a[-1], "_obj", None) is not None:
+                self._give_host(a[-1], 7 * self.size[0] * self.size[1])
+            return 0
+        return call
+
+
+def test_render_dispatch_follows_the_references(monkeypatch):
+    """tests/golden/dispatch_ref.json: the reference's VolumeRenderer constructed and driven through render() with
+    gputools replaced by a recorder (tests/golden/make_dispatch_golden.py): constructor defaults, interpolation
+    defines, the kernel an element type selects and every scalar the kernels receive.  Here the same calls on the real
+    Python class over a recording stand-in for the library must put the same numbers across the C ABI."""
+    import json
+    from spimagine_b200 import VolumeRenderer
+    with open(os.path.join(ROOT, "tests", "golden", "dispatch_ref.json")) as f:
+        rows = json.load(f)["rows"]
+    f32 = lambda v: float(np.float32(v))  # noqa: E731
+
+    def make(size=(48, 32), **kw):
+        lib = _RecordingLib()
+        lib.size = size
+        monkeypatch.setattr(_lib, "load", lambda: lib)
+        return VolumeRenderer(size, **kw), lib
+
+    n_render = 0
+    for row in rows:
+        if row["what"] == "constructor":
+            r, lib = make(interpolation=row["interpolation"])
+            d = row["defaults"]
+            assert (float(r.gamma), float(r.maxVal), float(r.minVal), float(r.alphaPow)) == (
+                d["gamma"], d["maxVal"], d["minVal"], d["alphaPow"])
+            assert (float(r.occ_strength), int(r.occ_radius), int(r.occ_n_points)) == (
+                d["occ_strength"], d["occ_radius"], d["occ_n_points"])
+            assert [float(b) for b in r.boxBounds] == d["boxBounds"] and [float(u) for u in r.stackUnits] == d["stackUnits"]
+            assert np.dtype(r.dtype).name == d["dtype"] and (r.width, r.height) == (d["width"], d["height"])
+            assert np.array_equal(np.asarray(r.projection, np.float64), np.array(d["projection"]))
+            assert np.array_equal(np.asarray(r.modelView, np.float64), np.array(d["modelView"]))
+            opts = row["log"][0]["build_options"]
+            linear = "SAMPLER_FILTER=CLK_FILTER_LINEAR" in opts
+            assert ["spv_set_interp", 1 if linear else 0] in lib.calls
+            assert "maxSteps=%d" % r.max_steps in opts
+            assert r.output.shape == (d["height"], d["width"]) and r.isGPU
+        elif row["what"] == "bad interpolation":
+            assert row["raises"] == "KeyError"
+            with pytest.raises(KeyError):
+                make(interpolation="cubic")
+        elif row["what"] == "render without data":
+            r, lib = make()
+            del lib.calls[:]
+            assert (r.render() is None) == row["returns_none"]
+            assert not [c for c in lib.calls if c[0].startswith("spv_render")] and not row["log"]
+        else:
+            r, lib = make()
+            r.set_data(np.zeros((5, 6, 7), row["dtype"]))
+            for name, v in row["setters"]:
+                getattr(r, name)(v)
+            del lib.calls[:]
+            assert (r.render(**row["kwargs"]) is None) == row["returns_none"]
+            renders = [c for c in lib.calls if c[0].startswith("spv_render")]
+            kernels = [e["kernel"] for e in row["log"]]
+            assert list(r.output.shape) == row["output_shape"]
+            if not kernels:
+                assert not renders
+                continue
+            n_render += 1
+            assert len(renders) == 1
+            p = renders[0][1]
+            s = [v for _, v in row["log"][0]["scalars"]]
+            assert s[:2] == [r.width, r.height] and p["box"] == s[2:8]
+            if kernels == ["max_project_short"] or kernels == ["max_project_float"]:
+                assert renders[0][0] == "spv_render_mip_to_host"
+                assert (kernels[0] == "max_project_short") == (np.dtype(r.dtype).name in ("uint16", "uint8"))
+                assert [p["min_val"], p["max_val"], p["gamma"], p["alpha_pow"]] == s[8:12]
+                assert [p["num_parts"], p["current_part"]] == s[12:14] and p["flags"] == 0 and p["max_steps"] == 200
+            else:
+                assert kernels == ["iso_surface", "conv_vec_x", "conv_vec_y", "occlusion", "conv_x", "conv_y", "shading"]
+                assert renders[0][0] == "spv_render_iso_to_host"
+                assert [p["iso_val"], p["gamma"]] == s[8:10] and p["flags"] == 0 and p["max_steps"] == 200
+                assert s[10] == float(np.dtype(r.dtype).name in ("uint16", "uint8"))        # isShortType
+                # the blur radii are constants of the library (spv_api.cu render_iso_impl: 7 and 5 taps)
+                assert [e["scalars"][-1][1] for e in row["log"][1:3]] == [7., 7.]
+                assert [e["scalars"][-1][1] for e in row["log"][4:6]] == [5., 5.]
+                occ = [v for _, v in row["log"][3]["scalars"]]
+                assert [p["occ_radius"], p["occ_n_points"]] == occ[2:4]
+                shade = [v for _, v in row["log"][6]["scalars"]]
+                assert p["occ_strength"] == shade[2] == f32(r.occ_strength)
+    assert n_render == 8
