@@ -88,13 +88,14 @@ def model_view(args):
 
 
 def to_uint8(out):
-    return (np.clip(out, 0, 1) * 255 + 0.499999999).astype(np.uint8)
+    # in float64 like imageio's conversion of float images in [0, 1] (x * 255 + 0.499999999, truncated)
+    return (np.clip(np.asarray(out, np.float64), 0, 1) * 255 + 0.499999999).astype(np.uint8)
 
 
 def to_uint16(out, low, high):
     cmin, cmax = float(np.amin(out)), float(np.amax(out))
     scale = (high - low) / (cmax - cmin) if cmax > cmin else 0.
-    return np.clip((out * 1.0 - cmin) * scale + low, 0, 65535).astype(np.uint16)
+    return np.clip((np.asarray(out, np.float64) - cmin) * scale + low, 0, 65535).astype(np.uint16)
 
 
 def save_image(fName, out, is16Bit=False, rng=None):

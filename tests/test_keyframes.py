@@ -357,3 +357,56 @@ def test_record_loop_over_a_gloo_group():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(counts == [1] * 23 and ok for _, counts, ok in results)
+
+
+def test_record_writes_the_gui_file_names(tmp_path):
+    """keyframe_view.py:644-653: output_<recordPos zero-filled to the digits of nFrames>.png, one per frame; images
+    upright (the renderer's row 0 is the bottom row of the view)."""
+    from PIL import Image
+
+    class _Fake(_FakeRenderer):
+        n = 0
+
+        def set_lut(self, lut):
+            self.lut = np.asarray(lut)
+
+        def output_rgba(self, mode_black=True):
+            _Fake.n += 1
+            img = np.zeros((4, 6, 4), np.uint8)
+            img[0, :, 0] = _Fake.n            # marks row 0
+            img[..., 3] = 255
+            return img
+
+    keys = _path(1)
+    lut = np.linspace(0, 1, 8)[:, None].repeat(3, 1)
+    r = _Fake()
+    names = kf.record_keyframes(r, keys, 12, str(tmp_path / "movie"), lut=lut)
+    assert [os.path.basename(n) for n in names] == ["output_%02d.png" % i for i in range(1, 13)]
+    assert np.array_equal(r.lut, lut)
+    first = np.array(Image.open(names[0]))
+    assert first.shape == (4, 6, 4) and first[-1, 0, 0] == 1 and first[0, 0, 0] == 0      # flipped: row 0 at the bottom
+    mine = kf.record_keyframes(_Fake(), keys, 12, str(tmp_path / "part"), rank=1, world=3)
+    assert [os.path.basename(n) for n in mine] == ["output_%02d.png" % i for i in (2, 5, 8, 11)]
+
+
+def test_cli_without_a_device(tmp_path, capsys):
+    """What spim_render does before it needs the GPU: help without arguments (bin/spim_render.py:96-98), the
+    reference's defaults, the camera it builds, the formats it knows."""
+    from spimagine_b200.bin import spim_render
+    from spimagine_b200.utils.transform_matrices import mat4_rotation, mat4_scale, mat4_translate
+    assert spim_render.main([]) == 0
+    assert "renders max projections" in capsys.readouterr().out
+    a = spim_render.build_parser().parse_args(["-i", "x.tif"])
+    assert (a.format, a.output, a.pos, a.width, a.scale, a.units, a.translate, a.rotation, a.range, a.ortho, a.is16Bit) == (
+        "tif", "out.png", 0, 400, [1.], [1., 1., 5.], [0, 0, -4], [0, 1, 0, 0], None, False, False)
+    a = spim_render.build_parser().parse_args(["-i", "x", "-s", "2", "-r", ".3", "0", "1", "0", "-t", "1", "2", "-5"])
+    want = np.dot(mat4_translate(1, 2, -5), np.dot(mat4_rotation(.3, 0, 1, 0), mat4_scale(2, 2, 2)))
+    assert np.array_equal(spim_render.model_view(a), want)
+    with pytest.raises(ValueError, match="not supported"):
+        spim_render.main(["-f", "czi", "-i", str(tmp_path / "x.czi")])
+    with pytest.raises(SystemExit):
+        spim_render.build_parser().parse_args([])             # -i is required
+    out = np.array([[0., .5], [1., 2.]], np.float32)
+    assert spim_render.to_uint8(out).tolist() == [[0, 127], [255, 255]]
+    assert spim_render.to_uint16(out, 0., 1000.).tolist() == [[0, 250], [500, 1000]]
+    assert spim_render.to_uint16(np.ones((2, 2), np.float32), 5., 9.).tolist() == [[5, 5], [5, 5]]
