@@ -358,17 +358,21 @@ class VolumeRenderer(object):
             # host cost matters here: this runs once per frame of a spin (set_modelView).  mScale only changes with
             # the volume shape or the units, invP only with the projection; the float32 copies the kernels take
             # live in two persistent buffers whose ctypes pointers are made once.
-            key = (self.dataImg.shape, tuple(np.asarray(self.stackUnits, dtype=float).ravel()))
+            # (the cache keys are the arrays' bytes: a caller may assign or modify stackUnits / projection in place)
+            su = self.stackUnits
+            key = (self.dataImg.shape, su.tobytes() if isinstance(su, np.ndarray) else tuple(float(u) for u in su))
             cached = getattr(self, "_mscale_of", None)
             if cached is None or cached[0] != key:
                 cached = self._mscale_of = (key, self._stack_scale_mat())
             invM = _inv4(np.dot(self.modelView, cached[1]))
+            proj = self.projection
+            pkey = (proj.dtype, proj.tobytes()) if isinstance(proj, np.ndarray) else None
             cached = getattr(self, "_invP_of", None)
-            if cached is not None and cached[0] is self.projection and np.array_equal(cached[1], self.projection):
-                invP = cached[2]
+            if cached is not None and pkey is not None and cached[0] == pkey:
+                invP = cached[1]
             else:  # same scipy.linalg.inv as the reference, evaluated once per distinct projection matrix
-                invP = _inv4(self.projection)
-                self._invP_of = (self.projection, np.array(self.projection, copy=True), invP)
+                invP = _inv4(proj)
+                self._invP_of = (pkey, invP)
                 self._invP[:] = invP.ravel()
             self._invM[:] = invM.ravel()  # float64 -> float32 like .astype(np.float32)
             self._check(self._lib.spv_set_matrices(self._ctx, self._invP_ptr, self._invM_ptr))

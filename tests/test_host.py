@@ -353,3 +353,35 @@ def test_render_dispatch_follows_the_references(monkeypatch):
                 shade = [v for _, v in row["log"][6]["scalars"]]
                 assert p["occ_strength"] == shade[2] == f32(r.occ_strength)
     assert n_render == 8
+
+
+def test_matrix_caches_notice_in_place_changes():
+    """update_matrices caches the scale matrix and the projection inverse; a caller that modifies stackUnits or the
+    projection array in place (or assigns a list) must still get the matrices of the current values."""
+    from scipy.linalg import inv
+    r = _host_only_renderer()
+    r.dataImg = type("Img", (), {"shape": (40, 30, 20), "dtype": np.uint16})()
+    M = np.dot(tm.mat4_translate(0, 0, -4), tm.mat4_rotation(.4, 0, 1, 0))
+    P = tm.mat4_perspective(60, 1., .1, 10)
+    r.set_units([1., 1., 2.])
+    r.set_projection(P)
+    r.set_modelView(M)
+
+    def expect():
+        want_m = inv(np.dot(r.modelView, r._stack_scale_mat())).flatten().astype(np.float32)
+        want_p = inv(r.projection).flatten().astype(np.float32)
+        assert np.array_equal(r._invM, want_m) and np.array_equal(r._invP, want_p)
+
+    expect()
+    r.stackUnits[2] = 5.          # in place
+    r.update_matrices()
+    expect()
+    r.stackUnits = [2., 1., 1.]   # a plain list assigned by the caller
+    r.update_matrices()
+    expect()
+    P[0, 0] *= 1.5                # the projection array modified in place
+    r.update_matrices()
+    expect()
+    r.projection = P.astype(np.float64)   # same values, another element type: the inverse is taken in that type
+    r.update_matrices()
+    expect()
