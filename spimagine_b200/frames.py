@@ -2,7 +2,7 @@
 
 Mirrors the part of the reference's data model that feeds the renderer during timelapse playback
 (spimagine/models/data_model.py: GenericData :59-95, SpimData :97-148, TiffData :178-218, RawData :221-261,
-RawMultipleFiles / TiffFolderData / TiffMultipleFiles :262-404, NumpyData :408-432, XwingData :475-515, the
+RawMultipleFiles / TiffFolderData / TiffMultipleFiles :262-404, NumpyData :408-432, XwingData :475-515, DataModel :652-757, the
 prefetching DataLoadThread / DataModel :600-757; spimagine/utils/imgutils.py: parseIndexFile :48-66, parseMetaFile
 :69-86, fromSpimFolder :129-146, createSpimFolder :162-191) -- same class names, same `sizeT() / size() /
 stackUnits / container[pos]` protocol -- with one change in where the bytes land: `FrameSource` reads time points
@@ -548,3 +548,152 @@ class FrameSource(object):
             self.close()
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------------- data model
+class DataModel(object):
+    """The reference's data model without Qt (data_model.py:652-757): a container plus a position, time points cached
+    in `data` (pos -> array), the neighbourhood pos .. pos + prefetchSize (mod sizeT) kept loaded by a background
+    thread (DataLoadThread, :600-649), container chosen from a path by loadFromPath.  Same method names; the Qt
+    signals _dataSourceChanged / _dataPosChanged are lists of callables here (source_changed, pos_changed).
+    For playback at PCIe rate use FrameSource (page-locked ring, fixed play order); this class is the drop-in for
+    callers that hop around the time axis (the GUI's slider)."""
+
+    def __init__(self, dataContainer=None, prefetchSize=0):
+        assert prefetchSize >= 0
+        self.source_changed, self.pos_changed = [], []
+        self._lock = threading.Lock()
+        self._wake = threading.Condition(self._lock)
+        self._thread = None
+        self._stopped = True
+        self.dataContainer = None
+        if dataContainer:
+            self.setContainer(dataContainer, prefetchSize)
+
+    @classmethod
+    def fromPath(cls, fName, prefetchSize=0):
+        d = cls()
+        d.loadFromPath(fName, prefetchSize)
+        return d
+
+    def setContainer(self, dataContainer=None, prefetchSize=0):
+        self.stopDataLoadThread()
+        self.dataContainer = dataContainer
+        self.prefetchSize = prefetchSize
+        self.nset = [0]
+        self.data = {}
+        self.__dict__.pop("pos", None)
+        if self.dataContainer:
+            self._stopped = False
+            self._thread = threading.Thread(target=self._run, name="spimagine-data-load", daemon=True)
+            self._thread.start()
+            for f in self.source_changed:
+                f()
+            self.setPos(0)
+
+    def __repr__(self):
+        return "DataModel: %s \t %s" % (self.dataContainer.name, self.size())
+
+    def stopDataLoadThread(self):
+        with self._wake:
+            self._stopped = True
+            self._wake.notify_all()
+        if self._thread is not None:
+            self._thread.join()
+            self._thread = None
+
+    close = stopDataLoadThread
+
+    def __del__(self):
+        try:
+            self.stopDataLoadThread()
+        except Exception:
+            pass
+
+    def _run(self):
+        """keep exactly the neighbourhood loaded: drop what left it, load what entered it"""
+        while True:
+            with self._wake:
+                while not self._stopped and set(self.data) == set(self.nset):
+                    self._wake.wait()
+                if self._stopped:
+                    return
+                want = list(self.nset)
+                for k in set(self.data).difference(want):
+                    del self.data[k]
+                missing = [k for k in want if k not in self.data]
+                container = self.dataContainer
+            for k in missing:
+                newdata = container[k]           # the read happens outside the lock
+                with self._wake:
+                    if self._stopped or container is not self.dataContainer:
+                        return
+                    if k in self.nset:
+                        self.data[k] = newdata
+
+    def prefetch(self, pos):
+        with self._wake:
+            self.nset[:] = [int(k) for k in self.neighborhood(pos)]
+            self._wake.notify_all()
+
+    def sizeT(self):
+        if self.dataContainer:
+            return self.dataContainer.sizeT()
+
+    def size(self):
+        if self.dataContainer:
+            return self.dataContainer.size()
+
+    def name(self):
+        if self.dataContainer:
+            return self.dataContainer.name
+
+    def stackUnits(self):
+        if self.dataContainer:
+            return self.dataContainer.stackUnits
+
+    def setPos(self, pos):
+        if pos < 0 or pos >= self.sizeT():
+            raise IndexError("setPos(pos): %i outside of [0,%i]!" % (pos, self.sizeT() - 1))
+        if not hasattr(self, "pos") or self.pos != pos:
+            self.pos = pos
+            for f in self.pos_changed:
+                f(pos)
+            self.prefetch(self.pos)
+
+    def __getitem__(self, pos):
+        if not hasattr(self, "data"):
+            print("something is wrong in datamodel as its lacking a 'data' atttribute!")
+            return None
+        with self._wake:
+            newdata = self.data.get(pos)
+        if newdata is None:
+            newdata = self.dataContainer[pos]
+            with self._wake:
+                self.data[pos] = newdata
+        self.prefetch(pos)
+        return newdata
+
+    def neighborhood(self, pos):
+        return np.arange(pos, pos + self.prefetchSize + 1) % self.sizeT()
+
+    def loadFromPath(self, fName, prefetchSize=0):
+        """data_model.py:733-757: lists of tif / raw files, a tif / raw file, a SpimData / xwing / tiff folder.
+        (png / jpg / bmp images and czi files need decoders this package does not have; raw files need a shape: give
+        RawData / RawMultipleFiles to setContainer instead.)"""
+        if isinstance(fName, (tuple, list)):
+            if re.match(r".*\.(tif|tiff)", fName[0]):
+                self.setContainer(TiffMultipleFiles(fName), prefetchSize)
+            else:
+                raise ValueError("a list of %s: only lists of tif files can be opened from their paths alone" % fName[0])
+        elif re.match(r".*\.(tif|tiff)", fName):
+            self.setContainer(TiffData(fName), prefetchSize=0)
+        elif os.path.isdir(fName):
+            if os.path.exists(os.path.join(fName, "metadata.txt")):
+                self.setContainer(SpimData(fName), prefetchSize)
+            elif os.path.exists(os.path.join(fName, "default.index.txt")):
+                self.setContainer(XwingData(fName), prefetchSize)
+            else:
+                self.setContainer(TiffFolderData(fName), prefetchSize=prefetchSize)
+        else:
+            raise ValueError("%s: no container for this path (tif file, SpimData / xwing / tiff folder)" % fName)

@@ -211,3 +211,88 @@ def test_containers_read_what_the_references_containers_read(tmp_path):
     sub = np.stack([d[2], d[3]])                       # fromSpimFolder(pos=2, count=2), imgutils.py:129-146
     want = ref["fromSpimFolder_pos2_count2"]
     assert list(sub.shape) == want["shape"] and hashlib.sha1(sub.tobytes()).hexdigest() == want["sha1"]
+
+
+class _Counting(frames.NumpyData):
+    def __init__(self, data):
+        frames.NumpyData.__init__(self, data)
+        self.reads = []
+
+    def __getitem__(self, pos):
+        self.reads.append(int(pos))
+        return self.data[pos]
+
+
+def _wait_for(cond, timeout=10.):
+    t0 = time.time()
+    while not cond():
+        if time.time() - t0 > timeout:
+            return False
+        time.sleep(.002)
+    return True
+
+
+def test_data_model_keeps_the_neighbourhood_loaded():
+    """data_model.py:600-757: position, cache, neighbourhood pos .. pos + prefetchSize (mod sizeT) kept loaded in the
+    background, everything else dropped."""
+    data = _timelapse(8, (3, 4, 5), seed=5)
+    c = _Counting(data)
+    seen = []
+    m = frames.DataModel(c, prefetchSize=2)
+    try:
+        m.pos_changed.append(seen.append)
+        assert m.sizeT() == 8 and m.size() == (8, 3, 4, 5) and m.name() == "NumpyData" and m.stackUnits() == [1., 1., 1.]
+        assert m.neighborhood(6).tolist() == [6, 7, 0] and m.pos == 0
+        assert _wait_for(lambda: set(m.data) == {0, 1, 2})
+        assert np.array_equal(m[1], data[1])                 # already there: no second read of time point 1
+        assert _wait_for(lambda: set(m.data) == {1, 2, 3}) and c.reads.count(1) == 1
+        m.setPos(6)
+        assert seen == [6] and _wait_for(lambda: set(m.data) == {6, 7, 0})
+        m.setPos(6)
+        assert seen == [6]                                   # unchanged position: no signal
+        assert np.array_equal(m[4], data[4]) and _wait_for(lambda: set(m.data) == {4, 5, 6})
+        with pytest.raises(IndexError):
+            m.setPos(8)
+        with pytest.raises(IndexError):
+            m.setPos(-1)
+        # a new container: the cache starts over, the old reader is gone
+        c2 = _Counting(data[:2])
+        m.setContainer(c2, prefetchSize=0)
+        assert m.sizeT() == 2 and m.pos == 0 and _wait_for(lambda: set(m.data) == {0}) and np.array_equal(m[1], data[1])
+    finally:
+        m.close()
+    assert m._thread is None
+    assert frames.DataModel().sizeT() is None
+
+
+def test_data_model_chooses_the_container_from_the_path(tmp_path):
+    """data_model.py:733-757"""
+    from spimagine_b200.utils import tiffio
+    data = _timelapse(3, (4, 5, 6), seed=6)
+    spim = str(tmp_path / "spim")
+    frames.createSpimFolder(spim, data)
+    xw = tmp_path / "xw"
+    (xw / "stacks" / "default").mkdir(parents=True)
+    for t in range(3):
+        data[t].astype("<u2").tofile(str(xw / "stacks" / "default" / ("%06d.raw" % t)))
+    (xw / "default.index.txt").write_text("0\t0.0\t6, 5, 4\n")
+    (xw / "default.metadata.txt").write_text('{"VoxelDimX": 1, "VoxelDimY": 1, "VoxelDimZ": 2}\n')
+    tifs = tmp_path / "tifs"
+    tifs.mkdir()
+    names = []
+    for t in range(3):
+        names.append(str(tifs / ("t%d.tif" % t)))
+        tiffio.write3dTiff(data[t], names[-1])
+    one = str(tmp_path / "all.tiff")
+    tiffio.write3dTiff(data, one)
+    for path, cls, prefetch in ((spim, frames.SpimData, 1), (str(xw), frames.XwingData, 1), (str(tifs), frames.TiffFolderData, 1),
+                                (names, frames.TiffMultipleFiles, 1), (one, frames.TiffData, 0)):
+        m = frames.DataModel.fromPath(path, prefetchSize=1)
+        try:
+            assert type(m.dataContainer) is cls and m.prefetchSize == prefetch, path
+            assert m.sizeT() == 3 and np.array_equal(m[2], data[2]), path
+        finally:
+            m.close()
+    for bad in (str(tmp_path / "x.czi"), [str(tmp_path / "a.raw")]):
+        with pytest.raises(ValueError):
+            frames.DataModel.fromPath(bad)
