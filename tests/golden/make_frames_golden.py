@@ -38,7 +38,9 @@ def import_reference():
         m.__path__ = []
         sys.modules[name] = m
     core = sys.modules["PyQt5.QtCore"]
-    core.QObject = core.QThread = type("QObject", (object,), {"__init__": lambda self, *a, **k: None})
+    core.QObject = type("QObject", (object,), {"__init__": lambda self, *a, **k: None})
+    core.QThread = type("QThread", (object,), {"__init__": lambda self, *a, **k: None, "LowPriority": 0,
+                                               "start": lambda self, priority=None: None})   # the prefetch thread never runs
     core.pyqtSignal = core.QReadWriteLock = _Anything
     sys.modules["PyQt5"].QtCore = core
     t = sys.modules["tifffile"]
@@ -74,6 +76,16 @@ def main():
     with tempfile.TemporaryDirectory() as root:
         for key, (cls, args, kw) in frames_inputs.build(root).items():
             out[key] = describe(getattr(dm, cls)(*args, **kw))
+        # DataModel: the container loadFromPath picks, the neighbourhood it prefetches, what model[pos] returns
+        model = {}
+        for key, path in (("spim", os.path.join(root, "spim")), ("xwing", os.path.join(root, "xwing"))):
+            m = dm.DataModel.fromPath(path, prefetchSize=2)
+            a = np.ascontiguousarray(m[1])
+            model[key] = {"container": type(m.dataContainer).__name__, "prefetchSize": int(m.prefetchSize),
+                          "sizeT": int(m.sizeT()), "pos_after_init": int(m.pos),
+                          "neighborhood": {str(p): [int(k) for k in m.neighborhood(p)] for p in range(int(m.sizeT()))},
+                          "item1_sha1": hashlib.sha1(a.tobytes()).hexdigest()}
+        out["DataModel"] = model
         sub = imgutils.fromSpimFolder(os.path.join(root, "spim"), pos=2, count=2)
         out["fromSpimFolder_pos2_count2"] = {"shape": list(sub.shape), "sha1": hashlib.sha1(np.ascontiguousarray(sub).tobytes()).hexdigest()}
     with open(os.path.join(HERE, "frames_ref.json"), "w") as f:

@@ -194,7 +194,17 @@ def test_containers_read_what_the_references_containers_read(tmp_path):
     with open(os.path.join(golden_dir, "frames_ref.json")) as f:
         ref = json.load(f)["containers"]
     specs = frames_inputs.build(str(tmp_path))
-    assert set(specs) | {"fromSpimFolder_pos2_count2"} == set(ref)
+    assert set(specs) | {"fromSpimFolder_pos2_count2", "DataModel"} == set(ref)
+    for key, want in ref["DataModel"].items():
+        m = frames.DataModel.fromPath(os.path.join(str(tmp_path), key), prefetchSize=2)
+        try:
+            assert type(m.dataContainer).__name__ == want["container"] and m.prefetchSize == want["prefetchSize"]
+            assert m.sizeT() == want["sizeT"] and m.pos == want["pos_after_init"]
+            for p, nb in want["neighborhood"].items():
+                assert m.neighborhood(int(p)).tolist() == nb
+            assert hashlib.sha1(np.ascontiguousarray(m[1]).tobytes()).hexdigest() == want["item1_sha1"]
+        finally:
+            m.close()
     for key, (cls, args, kw) in specs.items():
         c = getattr(frames, cls)(*args, **kw)
         want = ref[key]
