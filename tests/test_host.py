@@ -385,3 +385,29 @@ def test_matrix_caches_notice_in_place_changes():
     r.projection = P.astype(np.float64)   # same values, another element type: the inverse is taken in that type
     r.update_matrices()
     expect()
+
+
+def test_bench_arguments(monkeypatch):
+    """bench.py's contract with the driver: defaults that finish within minutes, the workload's own volume size,
+    every host thread for the CPU arms even under torchrun's OMP_NUM_THREADS=1."""
+    import sys
+    sys.path.insert(0, ROOT)
+    try:
+        import bench
+    finally:
+        sys.path.remove(ROOT)
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    a = bench.parse()
+    assert (a.gpus, a.steps, a.warmup, a.impl, a.workload, a.vol, a.img) == (1, 720, 20, "ours", "sweep", 512, 1024)
+    assert a.warmup >= 3
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "iso"])
+    assert bench.parse().vol == 1024                      # BASELINE configs[2]
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "iso", "--vol", "256", "--impl", "reference"])
+    a = bench.parse()
+    assert a.vol == 256 and a.impl == "reference"
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    n = bench.use_all_host_threads()
+    assert n == len(os.sched_getaffinity(0)) >= 1
+    assert bench.SAMPLES_PER_RAY == 208 and bench.MAX_STEPS == 200
+    cams = bench.sweep_cameras(4)
+    assert len(cams) == 4 and np.asarray(cams[0][0]).shape == (4, 4)

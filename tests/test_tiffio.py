@@ -249,3 +249,33 @@ def test_one_file_per_time_point(tmp_path):
         frames.RawMultipleFiles(raws, shape=(40, 5, 6), dtype=np.float32)
     with pytest.raises(ValueError):
         frames.RawMultipleFiles(raws)
+
+
+def test_random_stacks_round_trip(tmp_path):
+    """property test: any 2/3/4-d stack of a supported element type survives write -> read, classic and BigTIFF,
+    whole and in ranges of pages"""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    fn = str(tmp_path / "h.tif")
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.sampled_from(["uint8", "int8", "uint16", "int16", "uint32", "int32", "float32", "float64", "uint64"]),
+           st.lists(st.integers(1, 9), min_size=2, max_size=4), st.booleans(), st.integers(0, 2 ** 31))
+    def check(dtype, shape, big, seed):
+        a = _stack(tuple(shape), dtype, seed=seed) if np.dtype(dtype).itemsize < 8 or np.dtype(dtype).kind == "f" else (
+            np.random.default_rng(seed).integers(0, 2 ** 63, size=tuple(shape)).astype(dtype))
+        tiffio.write3dTiff(a, fn, bigtiff=big)
+        t = tiffio.TiffFile(fn)
+        want = a.reshape((1,) + a.shape) if a.ndim == 2 else a
+        if a.ndim == 4 and a.shape[0] == 1:
+            want = a[0]                                    # frames = 1: a plain stack of slices
+        got = t.asarray()
+        assert got.dtype == a.dtype and got.shape == want.shape and np.array_equal(got, want)
+        n = t.n_images
+        first = seed % n
+        count = 1 + (seed // 7) % (n - first)
+        part = np.empty((count,) + a.shape[-2:], t.dtype)
+        t.read_into(part, first=first, count=count)
+        assert np.array_equal(part, a.reshape((-1,) + a.shape[-2:])[first:first + count])
+
+    check()
