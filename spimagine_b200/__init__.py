@@ -7,5 +7,11 @@ VolumeRenderer), rebuilt as hand-written CUDA for NVIDIA B200 (sm_100a) behind a
 from .volumerender import VolumeRenderer  # noqa: F401
 from ._lib import pinned_empty  # noqa: F401
 from .utils.transform_matrices import *  # noqa: F401,F403
+# the names spimagine/__init__.py:20-27 exports that have a counterpart here (the GUI entry points do not)
+from .frames import (DataModel, SpimData, TiffData, TiffFolderData, NumpyData, RawData, RawMultipleFiles,  # noqa: F401
+                     XwingData, GenericData)
+from .keyframes import TransformData  # noqa: F401
+from .utils.quaternion import Quaternion  # noqa: F401
+from .utils.tiffio import read3dTiff, write3dTiff  # noqa: F401
 
 __version__ = "0.1.0"

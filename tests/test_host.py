@@ -411,3 +411,14 @@ def test_bench_arguments(monkeypatch):
     assert bench.SAMPLES_PER_RAY == 208 and bench.MAX_STEPS == 200
     cams = bench.sweep_cameras(4)
     assert len(cams) == 4 and np.asarray(cams[0][0]).shape == (4, 4)
+
+
+def test_package_exports_what_spimagine_exports():
+    """spimagine/__init__.py:20-27: the data containers, TransformData and the TIFF helpers are importable from the
+    package root (`import spimagine_b200 as spimagine`); importing the package needs neither a GPU nor the library."""
+    import spimagine_b200 as sp
+    for name in ("VolumeRenderer", "DataModel", "SpimData", "TiffData", "TiffFolderData", "NumpyData", "RawData",
+                 "RawMultipleFiles", "XwingData", "GenericData", "TransformData", "read3dTiff", "write3dTiff",
+                 "Quaternion", "mat4_perspective", "mat4_translate", "mat4_rotation", "pinned_empty"):
+        assert hasattr(sp, name), name
+    assert sp.TransformData().zoom == 1 and sp.NumpyData(np.zeros((2, 3, 4))).size() == (1, 2, 3, 4)
