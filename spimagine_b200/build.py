@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Build spimagine_b200/libspimcuda.so (and libspimfft.so) with nvcc for sm_100a (cross-compiles without a GPU).
+"""Build spimagine_b200/libspimcuda.so (and libspimfft.so) with nvcc for sm_100a (cross-compiles without a GPU),
+and libspimtiff.so (host-side strip decoders of the frame reader) with gcc.
 
     python -m spimagine_b200.build [--force] [--verbose]
 
@@ -62,6 +63,23 @@ def build_fft(force=False, verbose=False):
     return FFT_LIB
 
 
+# strip decoders of the frame reader (host code only, gcc)
+TIFF_LIB = os.path.join(HERE, "libspimtiff.so")
+TIFF_SOURCES = ["tiff_codecs.c"]
+
+
+def build_tiff(force=False, verbose=False):
+    deps = [os.path.join(CSRC, f) for f in TIFF_SOURCES] + [os.path.join(INCLUDE, "spimtiff.h"), __file__]
+    if not force and os.path.exists(TIFF_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(TIFF_LIB) for d in deps):
+        return TIFF_LIB
+    cmd = [shutil.which("gcc") or "gcc", "-O2", "-std=c11", "-fPIC", "-fvisibility=hidden", "-shared", "-Wall",
+           "-I", INCLUDE, "-o", TIFF_LIB] + [os.path.join(CSRC, f) for f in TIFF_SOURCES]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return TIFF_LIB
+
+
 def up_to_date():
     if not os.path.exists(LIB):
         return False
@@ -84,3 +102,4 @@ def build(force=False, verbose=False):
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
     print(build_fft(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_tiff(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -12,9 +12,10 @@ at PCIe rate without staging.  The reference reads every time point into fresh p
 GUI thread or a Qt thread and re-uploads it synchronously (gui/glwidget.py:372-374).
 
 Only containers whose bytes are laid out as the renderer wants them (C-order stacks of one element type) are
-rebuilt here: raw files, SpimData folders and uncompressed TIFF stacks (TiffData over utils/tiffio.py).  Compressed
-TIFF and CZI decode through third-party libraries in the reference (tifffile, czifile); their arrays can be wrapped
-in NumpyData or any object with the same protocol.
+rebuilt here: raw files, SpimData folders and TIFF stacks (TiffData over utils/tiffio.py: stored as they are, or
+LZW / deflate / PackBits strips decoded one page per worker thread).  JPEG-compressed or tiled TIFF and CZI decode
+through third-party libraries in the reference (tifffile, czifile); their arrays can be wrapped in NumpyData or any
+object with the same protocol.
 """
 from __future__ import absolute_import, print_function
 
@@ -192,8 +193,8 @@ class RawData(GenericData):
 
 class TiffData(GenericData):
     """2/3/4d tiff data (data_model.py:178-218).  The reference decodes the whole file into memory with tifffile;
-    here only the page directory is parsed (utils/tiffio.py: uncompressed strips, classic / BigTIFF, ImageJ
-    hyperstacks) and a time point is read from the file when it is asked for -- by FrameSource straight into a
+    here only the page directory is parsed (utils/tiffio.py: strips as stored or LZW / deflate / PackBits, classic /
+    BigTIFF, ImageJ hyperstacks) and a time point is read from the file when it is asked for -- by FrameSource straight into a
     page-locked buffer.  Big-endian files are byte-swapped after the read."""
 
     def __init__(self, fName=""):

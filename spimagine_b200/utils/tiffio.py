@@ -6,17 +6,23 @@ are almost always the plainest TIFF there is -- one uncompressed greyscale image
 that subset is what this module implements from the TIFF 6.0 / BigTIFF layout:
 
   * classic TIFF (magic 42, 32-bit offsets) and BigTIFF (magic 43, 64-bit offsets), little and big endian;
-  * pages of one sample per pixel, 8 / 16 / 32 / 64-bit unsigned, signed or IEEE float, Compression = 1;
-  * strips (any RowsPerStrip); contiguous pages are detected and read with ONE readinto per page;
+  * pages of one sample per pixel, 8 / 16 / 32 / 64-bit unsigned, signed or IEEE float;
+  * strips (any RowsPerStrip); contiguous uncompressed pages are detected and read with ONE readinto per page;
+  * compressed strips: LZW (5) and PackBits (32773) through libspimtiff.so (csrc/tiff_codecs.c, include/spimtiff.h),
+    deflate (8 / 32946) through zlib, each with the horizontal-differencing predictor (Predictor = 2) for integers;
+    every decoder runs with the GIL released, so FrameSource's reader thread overlaps it with rendering;
   * ImageJ hyperstacks: `ImageDescription = "ImageJ=...\nimages=N\nslices=Z\nframes=T"` gives the (T, Z, Y, X)
     shape, and ImageJ's "> 4 GB" layout (a single IFD followed by all N images back to back) is understood.
 
-Anything else (tiles, LZW / deflate / JPEG, RGB, planar) raises TiffError naming the tag, so a caller can fall back
+Anything else (tiles, JPEG / ZSTD / LZMA, the floating-point predictor, RGB, planar) raises TiffError naming the tag, so a caller can fall back
 to a full decoder and wrap the result in frames.NumpyData.  `TiffFile.read_into` fills caller memory -- page-locked
 buffers of frames.FrameSource -- straight from the file, which the tifffile path of the reference cannot do.
 """
+import ctypes
 import os
 import struct
+import zlib
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -30,18 +36,47 @@ class TiffError(ValueError):
 # tag ids (TIFF 6.0 section 8)
 _WIDTH, _LENGTH, _BITS, _COMPRESSION, _PHOTOMETRIC, _DESCRIPTION = 256, 257, 258, 259, 262, 270
 _STRIP_OFFSETS, _SAMPLES, _ROWS_PER_STRIP, _STRIP_COUNTS = 273, 277, 278, 279
-_PLANAR, _TILE_WIDTH, _SAMPLE_FORMAT = 284, 322, 339
+_PLANAR, _PREDICTOR, _TILE_WIDTH, _SAMPLE_FORMAT = 284, 317, 322, 339
+_NONE, _LZW, _DEFLATE, _DEFLATE_OLD, _PACKBITS = 1, 5, 8, 32946, 32773
 # field type -> (struct code, bytes)
 _TYPES = {1: ("B", 1), 2: ("c", 1), 3: ("H", 2), 4: ("I", 4), 5: ("II", 8), 6: ("b", 1), 7: ("B", 1), 8: ("h", 2),
           9: ("i", 4), 10: ("ii", 8), 11: ("f", 4), 12: ("d", 8), 13: ("I", 4), 16: ("Q", 8), 17: ("q", 8), 18: ("Q", 8)}
 _KIND = {1: "u", 2: "i", 3: "f"}
 
 
+_CODEC_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libspimtiff.so")
+_codecs = None
+
+
+def load_codecs():
+    """ctypes binding of include/spimtiff.h (built by spimagine_b200.build.build_tiff)"""
+    global _codecs
+    if _codecs is None:
+        if not os.path.exists(_CODEC_PATH):
+            raise TiffError("%s is missing: build it with python -m spimagine_b200.build" % _CODEC_PATH)
+        lib = ctypes.CDLL(_CODEC_PATH)
+        decode = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+        lib.spt_version.restype = ctypes.c_int
+        lib.spt_version.argtypes = []
+        for name in ("spt_lzw_decode", "spt_packbits_decode"):
+            getattr(lib, name).restype = ctypes.c_int
+            getattr(lib, name).argtypes = decode
+        lib.spt_undo_differencing.restype = ctypes.c_int
+        lib.spt_undo_differencing.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
+                                              ctypes.c_int]
+        _codecs = lib
+    return _codecs
+
+
 class _Page(object):
-    __slots__ = ("width", "length", "dtype", "offsets", "counts", "rows_per_strip", "description")
+    __slots__ = ("width", "length", "dtype", "offsets", "counts", "rows_per_strip", "description", "compression",
+                 "predictor")
 
     def contiguous(self):
-        """-> file offset of the image if its strips follow one another without gaps, else None"""
+        """-> file offset of the image if it is stored as it is and its strips follow one another without gaps,
+        else None"""
+        if self.compression != _NONE:
+            return None
         pos = self.offsets[0]
         for o, c in zip(self.offsets, self.counts):
             if o != pos:
@@ -57,6 +92,8 @@ class _Page(object):
 class TiffFile(object):
     """Page directory of a TIFF stack.  `shape` is (pages, Y, X), or (T, Z, Y, X) for an ImageJ hyperstack with
     frames > 1; `dtype` carries the file's byte order."""
+
+    decode_threads = 0  # workers for compressed pages; 0: one per core, at most 16
 
     def __init__(self, fName):
         self.fName = fName
@@ -138,7 +175,7 @@ class TiffFile(object):
             nbytes = size * count
             value = e[4 + inline:]
             if nbytes > inline:
-                if tag not in (_BITS, _DESCRIPTION, _STRIP_OFFSETS, _STRIP_COUNTS, _SAMPLE_FORMAT):
+                if tag not in (_BITS, _DESCRIPTION, _STRIP_OFFSETS, _STRIP_COUNTS, _SAMPLE_FORMAT):  # all others fit inline
                     continue  # a big value of a tag this reader does not use (colour maps, ImageJ metadata, ...)
                 where = struct.unpack(bo + off_fmt, value[:inline])[0]
                 here = f.tell()
@@ -168,15 +205,25 @@ class TiffFile(object):
 
         if _TILE_WIDTH in t:
             raise TiffError("%s: tiled images are not supported (tag 322)" % self.fName)
-        if one(_COMPRESSION, 1) != 1:
-            raise TiffError("%s: compressed images are not supported (tag 259 = %d)" % (self.fName, one(_COMPRESSION)))
+        compression, predictor = one(_COMPRESSION, 1), one(_PREDICTOR, 1)
+        if compression not in (_NONE, _LZW, _DEFLATE, _DEFLATE_OLD, _PACKBITS):
+            raise TiffError("%s: this compression is not supported (tag 259 = %d)" % (self.fName, compression))
+        if predictor not in (1, 2):
+            raise TiffError("%s: this predictor is not supported (tag 317 = %d)" % (self.fName, predictor))
+        if predictor == 2 and compression not in (_LZW, _DEFLATE, _DEFLATE_OLD):
+            # TIFF 6.0 defines the predictor for LZW (deflate inherited it); libtiff writes the tag with other
+            # schemes but does not difference the samples, other writers do: ambiguous, so refuse
+            raise TiffError("%s: predictor with compression %d is ambiguous (tag 317 = 2)" % (self.fName, compression))
         if one(_SAMPLES, 1) != 1:
             raise TiffError("%s: %d samples per pixel are not supported (tag 277)" % (self.fName, one(_SAMPLES)))
         bits = one(_BITS, 1)
         kind = _KIND.get(one(_SAMPLE_FORMAT, 1), "u")
         if bits not in (8, 16, 32, 64) or (kind == "f" and bits < 32):
             raise TiffError("%s: %d-bit samples are not supported (tag 258)" % (self.fName, bits))
+        if predictor == 2 and kind == "f":
+            raise TiffError("%s: horizontal differencing of floating-point samples (tag 317 = 2)" % self.fName)
         p = _Page()
+        p.compression, p.predictor = compression, predictor
         p.width, p.length = int(one(_WIDTH)), int(one(_LENGTH))
         p.dtype = np.dtype(self._bo + kind + str(bits // 8))
         if p.dtype.itemsize == 1:
@@ -188,10 +235,16 @@ class TiffFile(object):
         row = p.width * p.dtype.itemsize
         counts = t.get(_STRIP_COUNTS)
         if counts is None or len(counts) != len(p.offsets):  # old writers leave the counts out
+            if compression != _NONE:
+                raise TiffError("%s: compressed strips without byte counts (tag 279)" % self.fName)
             n = len(p.offsets)
             counts = [row * p.rows_per_strip] * (n - 1) + [p.nbytes - row * p.rows_per_strip * (n - 1)]
         p.counts = [int(c) for c in counts]
-        if sum(p.counts) < p.nbytes:
+        if compression != _NONE:
+            if len(p.offsets) != -(-p.length // p.rows_per_strip):
+                raise TiffError("%s: %d strips for %d rows of %d per strip" % (self.fName, len(p.offsets), p.length,
+                                                                              p.rows_per_strip))
+        elif sum(p.counts) < p.nbytes:
             raise TiffError("%s: strips hold %d bytes, the image needs %d" % (self.fName, sum(p.counts), p.nbytes))
         p.description = t.get(_DESCRIPTION, "")
         return p
@@ -235,9 +288,12 @@ class TiffFile(object):
                 f.seek(self._flat + first * p0.nbytes)
                 self._fill(f, buf)
                 return out
+            packed = [i for i in range(count) if self.pages[first + i].compression != _NONE]
             for i in range(count):
                 p = self.pages[first + i]
                 dst = buf[i * p0.nbytes:(i + 1) * p0.nbytes]
+                if p.compression != _NONE:
+                    continue
                 start = p.contiguous()
                 if start is not None:
                     f.seek(start)
@@ -249,7 +305,58 @@ class TiffFile(object):
                     f.seek(o)
                     self._fill(f, dst[at:at + c])
                     at += c
+            if packed:
+                # pages are independent and every decoder releases the GIL: one page per worker
+                def work(i):
+                    self._decode_page(f.fileno(), self.pages[first + i], buf[i * p0.nbytes:(i + 1) * p0.nbytes])
+
+                workers = min(len(packed), self.decode_threads or min(16, os.cpu_count() or 1))
+                if workers <= 1:
+                    for i in packed:
+                        work(i)
+                else:
+                    with ThreadPoolExecutor(workers) as pool:
+                        list(pool.map(work, packed))
         return out
+
+    def _decode_page(self, fd, p, dst):
+        """compressed strips of one page -> dst (a writable byte view of the page), read with pread so that several
+        pages can be in flight on one descriptor; a strip decodes to rows_per_strip rows (the last one to what is
+        left), writers may pad it: the surplus is dropped"""
+        row = p.width * p.dtype.itemsize
+        at = 0
+        for o, c in zip(p.offsets, p.counts):
+            want = min(row * p.rows_per_strip, p.nbytes - at)
+            raw = os.pread(fd, c, o)
+            if len(raw) < c:
+                raise TiffError("%s: the strip at %d leaves the file" % (self.fName, o))
+            part = dst[at:at + want]
+            if p.compression in (_DEFLATE, _DEFLATE_OLD):
+                try:
+                    got = zlib.decompressobj().decompress(raw, want)
+                except zlib.error as e:
+                    raise TiffError("%s: damaged deflate strip at %d (%s)" % (self.fName, o, e))
+                n = len(got)
+                part[:n] = got
+            else:
+                lib = load_codecs()
+                fn = lib.spt_lzw_decode if p.compression == _LZW else lib.spt_packbits_decode
+                n = ctypes.c_size_t(0)
+                rc = fn(raw, c, ctypes.addressof((ctypes.c_char * want).from_buffer(part)), want,
+                        ctypes.byref(n))
+                if rc not in (0, -3):
+                    raise TiffError("%s: damaged %s strip at %d" % (self.fName, "LZW" if p.compression == _LZW
+                                                                    else "PackBits", o))
+                n = n.value
+            if n < want:
+                raise TiffError("%s: the strip at %d holds %d bytes, %d are needed" % (self.fName, o, n, want))
+            at += want
+        if p.predictor == 2:
+            page = (ctypes.c_char * p.nbytes).from_buffer(dst)
+            rc = load_codecs().spt_undo_differencing(ctypes.addressof(page), p.length, p.width, p.dtype.itemsize,
+                                                     0 if p.dtype.isnative else 1)
+            if rc:
+                raise TiffError("%s: predictor of %d-byte samples" % (self.fName, p.dtype.itemsize))
 
     def asarray(self, native=True):
         """The whole stack, shaped `self.shape`; native=True returns the machine's byte order (what the renderer's

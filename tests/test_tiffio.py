@@ -161,8 +161,11 @@ def test_big_endian_multi_strip(tmp_path):
 
 def test_unsupported_files_say_why(tmp_path):
     fn = str(tmp_path / "c.tif")
-    PIL_Image.fromarray(_stack((8, 8), np.uint8)).save(fn, compression="tiff_lzw")
+    PIL_Image.fromarray(_stack((8, 8), np.uint8)).save(fn, compression="jpeg")
     with pytest.raises(tiffio.TiffError, match="259"):
+        tiffio.TiffFile(fn)
+    PIL_Image.fromarray(_stack((8, 8), np.uint8)).save(fn, compression="packbits", tiffinfo={317: 2})
+    with pytest.raises(tiffio.TiffError, match="317"):
         tiffio.TiffFile(fn)
     PIL_Image.fromarray(np.zeros((8, 8, 3), np.uint8)).save(fn)
     with pytest.raises(tiffio.TiffError, match="277"):
