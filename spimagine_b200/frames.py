@@ -13,7 +13,7 @@ GUI thread or a Qt thread and re-uploads it synchronously (gui/glwidget.py:372-3
 
 Only containers whose bytes are laid out as the renderer wants them (C-order stacks of one element type) are
 rebuilt here: raw files, SpimData folders and TIFF stacks (TiffData over utils/tiffio.py: stored as they are, or
-LZW / deflate / PackBits strips decoded one page per worker thread).  JPEG-compressed or tiled TIFF and CZI decode
+LZW / deflate / PackBits strips or tiles decoded one page per worker thread).  JPEG-compressed TIFF and CZI decode
 through third-party libraries in the reference (tifffile, czifile); their arrays can be wrapped in NumpyData or any
 object with the same protocol.
 """

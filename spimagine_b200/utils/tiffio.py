@@ -8,13 +8,14 @@ that subset is what this module implements from the TIFF 6.0 / BigTIFF layout:
   * classic TIFF (magic 42, 32-bit offsets) and BigTIFF (magic 43, 64-bit offsets), little and big endian;
   * pages of one sample per pixel, 8 / 16 / 32 / 64-bit unsigned, signed or IEEE float;
   * strips (any RowsPerStrip); contiguous uncompressed pages are detected and read with ONE readinto per page;
+  * tiles (TIFF 6.0 section 15: OME-TIFF writers), stored or compressed, edge tiles clipped;
   * compressed strips: LZW (5) and PackBits (32773) through libspimtiff.so (csrc/tiff_codecs.c, include/spimtiff.h),
     deflate (8 / 32946) through zlib, each with the horizontal-differencing predictor (Predictor = 2) for integers;
     every decoder runs with the GIL released, so FrameSource's reader thread overlaps it with rendering;
   * ImageJ hyperstacks: `ImageDescription = "ImageJ=...\nimages=N\nslices=Z\nframes=T"` gives the (T, Z, Y, X)
     shape, and ImageJ's "> 4 GB" layout (a single IFD followed by all N images back to back) is understood.
 
-Anything else (tiles, JPEG / ZSTD / LZMA, the floating-point predictor, RGB, planar) raises TiffError naming the tag, so a caller can fall back
+Anything else (JPEG / ZSTD / LZMA, the floating-point predictor, RGB, planar) raises TiffError naming the tag, so a caller can fall back
 to a full decoder and wrap the result in frames.NumpyData.  `TiffFile.read_into` fills caller memory -- page-locked
 buffers of frames.FrameSource -- straight from the file, which the tifffile path of the reference cannot do.
 """
@@ -36,7 +37,7 @@ class TiffError(ValueError):
 # tag ids (TIFF 6.0 section 8)
 _WIDTH, _LENGTH, _BITS, _COMPRESSION, _PHOTOMETRIC, _DESCRIPTION = 256, 257, 258, 259, 262, 270
 _STRIP_OFFSETS, _SAMPLES, _ROWS_PER_STRIP, _STRIP_COUNTS = 273, 277, 278, 279
-_PLANAR, _PREDICTOR, _TILE_WIDTH, _SAMPLE_FORMAT = 284, 317, 322, 339
+_PLANAR, _PREDICTOR, _TILE_WIDTH, _TILE_LENGTH, _TILE_OFFSETS, _TILE_COUNTS, _SAMPLE_FORMAT = 284, 317, 322, 323, 324, 325, 339
 _NONE, _LZW, _DEFLATE, _DEFLATE_OLD, _PACKBITS = 1, 5, 8, 32946, 32773
 # field type -> (struct code, bytes)
 _TYPES = {1: ("B", 1), 2: ("c", 1), 3: ("H", 2), 4: ("I", 4), 5: ("II", 8), 6: ("b", 1), 7: ("B", 1), 8: ("h", 2),
@@ -70,12 +71,12 @@ def load_codecs():
 
 class _Page(object):
     __slots__ = ("width", "length", "dtype", "offsets", "counts", "rows_per_strip", "description", "compression",
-                 "predictor")
+                 "predictor", "tile")
 
     def contiguous(self):
         """-> file offset of the image if it is stored as it is and its strips follow one another without gaps,
         else None"""
-        if self.compression != _NONE:
+        if self.compression != _NONE or self.tile:
             return None
         pos = self.offsets[0]
         for o, c in zip(self.offsets, self.counts):
@@ -175,7 +176,8 @@ class TiffFile(object):
             nbytes = size * count
             value = e[4 + inline:]
             if nbytes > inline:
-                if tag not in (_BITS, _DESCRIPTION, _STRIP_OFFSETS, _STRIP_COUNTS, _SAMPLE_FORMAT):  # all others fit inline
+                if tag not in (_BITS, _DESCRIPTION, _STRIP_OFFSETS, _STRIP_COUNTS, _SAMPLE_FORMAT, _TILE_OFFSETS,
+                               _TILE_COUNTS):  # all others fit inline
                     continue  # a big value of a tag this reader does not use (colour maps, ImageJ metadata, ...)
                 where = struct.unpack(bo + off_fmt, value[:inline])[0]
                 here = f.tell()
@@ -203,8 +205,6 @@ class TiffFile(object):
                 return default
             return v[0] if isinstance(v, list) else v
 
-        if _TILE_WIDTH in t:
-            raise TiffError("%s: tiled images are not supported (tag 322)" % self.fName)
         compression, predictor = one(_COMPRESSION, 1), one(_PREDICTOR, 1)
         if compression not in (_NONE, _LZW, _DEFLATE, _DEFLATE_OLD, _PACKBITS):
             raise TiffError("%s: this compression is not supported (tag 259 = %d)" % (self.fName, compression))
@@ -228,6 +228,23 @@ class TiffFile(object):
         p.dtype = np.dtype(self._bo + kind + str(bits // 8))
         if p.dtype.itemsize == 1:
             p.dtype = np.dtype(kind + "1")
+        p.tile = None
+        if _TILE_WIDTH in t:
+            # TIFF 6.0 section 15: tiles of TileWidth x TileLength, left to right, top to bottom, the ones at the right
+            # and bottom edges padded to full size
+            tw, tl = int(one(_TILE_WIDTH)), int(one(_TILE_LENGTH))
+            if tw <= 0 or tl <= 0:
+                raise TiffError("%s: tiles of %d x %d (tags 322, 323)" % (self.fName, tw, tl))
+            p.tile = (tw, tl)
+            p.offsets = [int(o) for o in t.get(_TILE_OFFSETS, [])]
+            p.counts = [int(c) for c in t.get(_TILE_COUNTS, [])]
+            n = (-(-p.width // tw)) * (-(-p.length // tl))
+            if len(p.offsets) != n or len(p.counts) != n:
+                raise TiffError("%s: %d tile offsets and %d byte counts for %d tiles (tags 324, 325)"
+                                % (self.fName, len(p.offsets), len(p.counts), n))
+            p.rows_per_strip = tl
+            p.description = t.get(_DESCRIPTION, "")
+            return p
         p.offsets = [int(o) for o in t.get(_STRIP_OFFSETS, [])]
         if not p.offsets:
             raise TiffError("%s: no strips (tag 273)" % self.fName)
@@ -288,11 +305,12 @@ class TiffFile(object):
                 f.seek(self._flat + first * p0.nbytes)
                 self._fill(f, buf)
                 return out
-            packed = [i for i in range(count) if self.pages[first + i].compression != _NONE]
+            packed = [i for i in range(count) if self.pages[first + i].contiguous() is None
+                      and (self.pages[first + i].compression != _NONE or self.pages[first + i].tile)]
             for i in range(count):
                 p = self.pages[first + i]
                 dst = buf[i * p0.nbytes:(i + 1) * p0.nbytes]
-                if p.compression != _NONE:
+                if p.compression != _NONE or p.tile:
                     continue
                 start = p.contiguous()
                 if start is not None:
@@ -323,40 +341,61 @@ class TiffFile(object):
         """compressed strips of one page -> dst (a writable byte view of the page), read with pread so that several
         pages can be in flight on one descriptor; a strip decodes to rows_per_strip rows (the last one to what is
         left), writers may pad it: the surplus is dropped"""
-        row = p.width * p.dtype.itemsize
+        size = p.dtype.itemsize
+        swap = 0 if p.dtype.isnative else 1
+        if p.tile:
+            tw, tl = p.tile
+            across = -(-p.width // tw)
+            image = np.frombuffer(dst, np.uint8).reshape(p.length, p.width * size)
+            tile = np.empty((tl, tw * size), np.uint8)
+            view = memoryview(tile.reshape(-1))
+            for k, (o, c) in enumerate(zip(p.offsets, p.counts)):
+                self._decode_block(fd, p, o, c, view)
+                if p.predictor == 2:
+                    load_codecs().spt_undo_differencing(tile.ctypes.data, tl, tw, size, swap)
+                y, x = (k // across) * tl, (k % across) * tw
+                h, w = min(tl, p.length - y), min(tw, p.width - x)
+                image[y:y + h, x * size:(x + w) * size] = tile[:h, :w * size]
+            return
+        row = p.width * size
         at = 0
         for o, c in zip(p.offsets, p.counts):
             want = min(row * p.rows_per_strip, p.nbytes - at)
-            raw = os.pread(fd, c, o)
-            if len(raw) < c:
-                raise TiffError("%s: the strip at %d leaves the file" % (self.fName, o))
-            part = dst[at:at + want]
-            if p.compression in (_DEFLATE, _DEFLATE_OLD):
-                try:
-                    got = zlib.decompressobj().decompress(raw, want)
-                except zlib.error as e:
-                    raise TiffError("%s: damaged deflate strip at %d (%s)" % (self.fName, o, e))
-                n = len(got)
-                part[:n] = got
-            else:
-                lib = load_codecs()
-                fn = lib.spt_lzw_decode if p.compression == _LZW else lib.spt_packbits_decode
-                n = ctypes.c_size_t(0)
-                rc = fn(raw, c, ctypes.addressof((ctypes.c_char * want).from_buffer(part)), want,
-                        ctypes.byref(n))
-                if rc not in (0, -3):
-                    raise TiffError("%s: damaged %s strip at %d" % (self.fName, "LZW" if p.compression == _LZW
-                                                                    else "PackBits", o))
-                n = n.value
-            if n < want:
-                raise TiffError("%s: the strip at %d holds %d bytes, %d are needed" % (self.fName, o, n, want))
+            self._decode_block(fd, p, o, c, dst[at:at + want])
             at += want
         if p.predictor == 2:
             page = (ctypes.c_char * p.nbytes).from_buffer(dst)
-            rc = load_codecs().spt_undo_differencing(ctypes.addressof(page), p.length, p.width, p.dtype.itemsize,
-                                                     0 if p.dtype.isnative else 1)
+            rc = load_codecs().spt_undo_differencing(ctypes.addressof(page), p.length, p.width, size, swap)
             if rc:
-                raise TiffError("%s: predictor of %d-byte samples" % (self.fName, p.dtype.itemsize))
+                raise TiffError("%s: predictor of %d-byte samples" % (self.fName, size))
+
+    def _decode_block(self, fd, p, o, c, part):
+        """one strip or tile: c bytes at file offset o -> exactly len(part) bytes"""
+        want = len(part)
+        raw = os.pread(fd, c, o)
+        if len(raw) < c:
+            raise TiffError("%s: the block at %d leaves the file" % (self.fName, o))
+        if p.compression == _NONE:
+            n = min(c, want)
+            part[:n] = raw[:n]
+        elif p.compression in (_DEFLATE, _DEFLATE_OLD):
+            try:
+                got = zlib.decompressobj().decompress(raw, want)
+            except zlib.error as e:
+                raise TiffError("%s: damaged deflate block at %d (%s)" % (self.fName, o, e))
+            n = len(got)
+            part[:n] = got
+        else:
+            lib = load_codecs()
+            fn = lib.spt_lzw_decode if p.compression == _LZW else lib.spt_packbits_decode
+            n = ctypes.c_size_t(0)
+            rc = fn(raw, c, ctypes.addressof((ctypes.c_char * want).from_buffer(part)), want, ctypes.byref(n))
+            if rc not in (0, -3):
+                raise TiffError("%s: damaged %s block at %d" % (self.fName, "LZW" if p.compression == _LZW
+                                                                else "PackBits", o))
+            n = n.value
+        if n < want:
+            raise TiffError("%s: the block at %d holds %d bytes, %d are needed" % (self.fName, o, n, want))
 
     def asarray(self, native=True):
         """The whole stack, shaped `self.shape`; native=True returns the machine's byte order (what the renderer's

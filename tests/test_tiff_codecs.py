@@ -279,3 +279,96 @@ def test_truncated_strip_says_so(tmp_path):
     open(fn, "wb").write(raw)
     with pytest.raises(tiffio.TiffError, match="holds"):
         tiffio.TiffFile(fn).asarray()
+
+
+def _tiff_with_tiles(fn, pages, tile, compression=1, predictor=1, bo="<"):
+    """classic TIFF, one directory per page, TileWidth x TileLength tiles (edge tiles zero-padded, TIFF 6.0 s. 15)"""
+    tw, tl = tile
+    ny, nx = pages[0].shape
+    dt = pages[0].dtype
+    blobs = []
+    for a in pages:
+        native = a.astype(dt.newbyteorder("="))
+        tiles = []
+        for y in range(0, ny, tl):
+            for x in range(0, nx, tw):
+                t = np.zeros((tl, tw), native.dtype)
+                part = native[y:y + tl, x:x + tw]
+                t[:part.shape[0], :part.shape[1]] = part
+                if predictor == 2:
+                    d = t.copy()
+                    d[:, 1:] = t[:, 1:] - t[:, :-1]
+                    t = d
+                raw = t.astype(dt.newbyteorder(bo)).tobytes()
+                tiles.append({1: raw, 8: zlib.compress(raw), 5: _lzw_encode(raw)}[compression])
+        blobs.append(tiles)
+    with open(fn, "wb") as f:
+        f.write((b"MM" if bo == ">" else b"II") + struct.pack(bo + "HI", 42, 0))
+        ifds = []
+        for tiles in blobs:
+            n = len(tiles)
+            offsets = []
+            for t in tiles:
+                offsets.append(f.tell())
+                f.write(t)
+            f.write(b"\0" * (f.tell() % 2))
+            offs_at = f.tell()
+            f.write(struct.pack(bo + "%dI" % n, *offsets))
+            cnts_at = f.tell()
+            f.write(struct.pack(bo + "%dI" % n, *[len(t) for t in tiles]))
+            ifds.append(f.tell())
+            entries = [(256, 4, 1, nx), (257, 4, 1, ny), (258, 3, 1, dt.itemsize * 8), (259, 3, 1, compression),
+                       (262, 3, 1, 1), (277, 3, 1, 1), (317, 3, 1, predictor), (322, 4, 1, tw), (323, 4, 1, tl),
+                       (324, 4, n, offs_at if n > 1 else offsets[0]), (325, 4, n, cnts_at if n > 1 else len(tiles[0])),
+                       (339, 3, 1, {"u": 1, "i": 2, "f": 3}[dt.kind])]
+            f.write(struct.pack(bo + "H", len(entries)))
+            for tag, typ, count, value in entries:
+                f.write(struct.pack(bo + "HHI", tag, typ, count))
+                f.write(struct.pack(bo + "HH", value, 0) if typ == 3 else struct.pack(bo + "I", value))
+            f.write(struct.pack(bo + "I", 0))
+        for i, at in enumerate(ifds):
+            f.seek(at + 2 + 12 * 12)
+            f.write(struct.pack(bo + "I", ifds[i + 1] if i + 1 < len(ifds) else 0))
+        f.seek(4)
+        f.write(struct.pack(bo + "I", ifds[0]))
+
+
+@pytest.mark.parametrize("compression,predictor", [(1, 1), (8, 1), (8, 2), (5, 1), (5, 2)])
+@pytest.mark.parametrize("bo", ["<", ">"])
+@pytest.mark.parametrize("tile", [(16, 16), (32, 16), (64, 48)])
+def test_tiled_pages(tmp_path, compression, predictor, bo, tile):
+    """tiles smaller than, ragged against and larger than the 37 x 23 image"""
+    a = _smooth((3, 23, 37), np.uint16, seed=6)
+    fn = str(tmp_path / "tiles.tif")
+    _tiff_with_tiles(fn, list(a), tile, compression, predictor, bo)
+    t = tiffio.TiffFile(fn)
+    assert t.shape == a.shape and t.pages[0].tile == tile and t._flat is None
+    got = t.asarray()
+    assert got.dtype.isnative and np.array_equal(got, a)
+    one = np.empty((1, 23, 37), t.dtype)
+    t.read_into(one, first=2, count=1)
+    assert np.array_equal(one[0].astype(np.uint16), a[2])
+    if bo == "<":
+        assert np.array_equal(_pil_page(fn, 1), a[1])     # libtiff reads the same pixels
+
+
+def _pil_page(fn, i):
+    im = PIL_Image.open(fn)
+    im.seek(i)
+    return np.array(im)
+
+
+def test_tiled_float_pages_and_bad_directories(tmp_path):
+    a = _smooth((2, 20, 20), np.float32, seed=8)
+    fn = str(tmp_path / "f.tif")
+    _tiff_with_tiles(fn, list(a), (16, 16), 8, 1, "<")
+    assert np.array_equal(tiffio.read3dTiff(fn), a)
+    # a directory that lists fewer tiles than the image needs
+    raw = bytearray(open(fn, "rb").read())
+    ifd = struct.unpack("<I", raw[4:8])[0]
+    at = ifd + 2 + 12 * 7 + 8          # value of tag 322 (TileWidth)
+    assert struct.unpack("<H", raw[at - 8:at - 6])[0] == 322
+    raw[at:at + 4] = struct.pack("<I", 8)
+    open(fn, "wb").write(raw)
+    with pytest.raises(tiffio.TiffError, match="324"):
+        tiffio.TiffFile(fn)
