@@ -8,8 +8,8 @@ from .volumerender import VolumeRenderer  # noqa: F401
 from ._lib import pinned_empty  # noqa: F401
 from .utils.transform_matrices import *  # noqa: F401,F403
 # the names spimagine/__init__.py:20-27 exports that have a counterpart here (the GUI entry points do not)
-from .frames import (DataModel, SpimData, TiffData, TiffFolderData, NumpyData, RawData, RawMultipleFiles,  # noqa: F401
-                     XwingData, GenericData)
+from .frames import (DataModel, DemoData, SpimData, TiffData, TiffFolderData, NumpyData, RawData,  # noqa: F401
+                     RawMultipleFiles, XwingData, GenericData)
 from .keyframes import TransformData  # noqa: F401
 from .utils.quaternion import Quaternion  # noqa: F401
 from .utils.tiffio import read3dTiff, write3dTiff  # noqa: F401

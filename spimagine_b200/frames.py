@@ -431,6 +431,88 @@ class NumpyData(GenericData):
         return self.data[pos]
 
 
+def fromSpimFolder(fName, dataFileName="data/data.bin", indexFileName="data/index.txt", pos=0, count=1):
+    """`count` time points of a SpimData folder from `pos` on as one (t, z, y, x) array (imgutils.py:132-148): pos is
+    clamped to the folder, count to what is left behind pos, count <= 0 means everything from pos on."""
+    stackSize = parseIndexFile(os.path.join(fName, indexFileName))
+    if not stackSize:
+        return None
+    stackSize = list(stackSize)
+    pos = max(min(pos, stackSize[0] - 1), 0)
+    stackSize[0] = min(count, stackSize[0] - pos) if count > 0 else max(0, stackSize[0] - pos)
+    voxels = int(np.prod(stackSize[1:], dtype=np.int64))
+    with open(os.path.join(fName, dataFileName), "rb") as f:
+        f.seek(2 * pos * voxels)
+        return np.fromfile(f, dtype="<u2", count=stackSize[0] * voxels).reshape(stackSize)
+
+
+class DemoData(GenericData):
+    """The synthetic demo volume (data_model.py:434-472): a shell with ten meridian stripes plus an off-centre blob,
+    float32, fading by exp(-0.3 t) over the time points.  DemoData(N) is N^3 with sizeT() == N, as in the reference;
+    DemoData() there reads a logo stack shipped with the package (10 time points of 80^3) -- that asset is not part
+    of this package, so the 80^3 synthetic volume stands in for it with the same size() and sizeT()."""
+
+    def __init__(self, N=None):
+        GenericData.__init__(self, "DemoData")
+        self.load(N)
+
+    def load(self, N=None):
+        self.fName = ""
+        self.stackUnits = (1, 1, 1)
+        if N is None:
+            N = 80
+            self.stackSize = (10, N, N, N)
+            self.nT = 10
+        else:
+            self.stackSize = (1, N, N, N)
+            self.nT = N
+        x = np.linspace(-1, 1, N)
+        Z, Y, X = np.meshgrid(x, x, x, indexing="ij")
+        R = np.sqrt(X ** 2 + Y ** 2 + Z ** 2)
+        R2 = np.sqrt((X - .4) ** 2 + (Y + .2) ** 2 + Z ** 2)
+        phi = np.arctan2(Z, Y)
+        theta = np.arctan2(X, np.sqrt(Y ** 2 + Z ** 2))
+        bend = np.exp(-np.sin(2 * (phi + np.pi / 2.)))
+        # python's sum over the stripes, starting from the integer 0, in the reference's order
+        stripes = sum(np.exp(-150 * (-theta - t + .1 * (t - np.pi / 2.) * bend) ** 2)
+                      for t in np.linspace(-np.pi / 2., np.pi / 2., 10))
+        u = np.exp(-500 * (R - 1.) ** 2) * stripes * (1 + Z)
+        u2 = np.exp(-7 * R2 ** 2)
+        self.data = (10000 * (u + 2 * u2)).astype(np.float32)
+
+    @property
+    def dtype(self):
+        return np.dtype(np.float32)
+
+    def sizeT(self):
+        return self.nT
+
+    def __getitem__(self, pos):
+        return (self.data * np.exp(-.3 * pos)).astype(np.float32)
+
+
+class EmptyData(GenericData):
+    """one uint16 voxel of zeros: what the GUI shows before anything is loaded (data_model.py:518-531)"""
+
+    def __init__(self):
+        GenericData.__init__(self, "EmptyData")
+        self.stackSize = (1, 1, 1, 1)
+        self.fName = ""
+        self.nT = 1
+        self.stackUnits = (1, 1, 1)
+        self.data = np.zeros((1, 1, 1)).astype(np.uint16)
+
+    @property
+    def dtype(self):
+        return self.data.dtype
+
+    def sizeT(self):
+        return self.nT
+
+    def __getitem__(self, pos):
+        return self.data
+
+
 def createSpimFolder(fName, data=None, stackSize=[10, 10, 32, 32], stackUnits=(.162, .162, .162)):
     """Write a SpimData folder (imgutils.py:162-191; the reference opens data.bin with the invalid mode "wa")."""
     os.makedirs(os.path.join(fName, "data"), exist_ok=True)

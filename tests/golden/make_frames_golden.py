@@ -88,6 +88,24 @@ def main():
         out["DataModel"] = model
         sub = imgutils.fromSpimFolder(os.path.join(root, "spim"), pos=2, count=2)
         out["fromSpimFolder_pos2_count2"] = {"shape": list(sub.shape), "sha1": hashlib.sha1(np.ascontiguousarray(sub).tobytes()).hexdigest()}
+        for key, pos, count in (("fromSpimFolder_pos9_count5", 9, 5), ("fromSpimFolder_pos1_count0", 1, 0),
+                                ("fromSpimFolder_neg_count1", -3, 1)):
+            sub = imgutils.fromSpimFolder(os.path.join(root, "spim"), pos=pos, count=count)
+            out[key] = {"shape": list(sub.shape), "pos": pos, "count": count,
+                        "sha1": hashlib.sha1(np.ascontiguousarray(sub).tobytes()).hexdigest()}
+    # the synthetic demo volume and the placeholder container (data_model.py:434-472, 518-531)
+    demo = dm.DemoData(24)
+    pts = {}
+    for t in (0, 1, 23):
+        a = np.ascontiguousarray(demo[t])
+        pts[str(t)] = {"sha1": hashlib.sha1(a.tobytes()).hexdigest(), "dtype": a.dtype.name, "max": float(a.max()),
+                       "sum": float(a.astype(np.float64).sum())}
+    out["DemoData_24"] = {"size": [int(s) for s in demo.size()], "sizeT": int(demo.sizeT()),
+                          "stackUnits": [float(u) for u in demo.stackUnits], "points": pts}
+    e = dm.EmptyData()
+    out["EmptyData"] = {"size": [int(s) for s in e.size()], "sizeT": int(e.sizeT()),
+                        "stackUnits": [float(u) for u in e.stackUnits], "dtype": e[0].dtype.name,
+                        "shape": list(e[0].shape), "sum": int(e[0].sum())}
     with open(os.path.join(HERE, "frames_ref.json"), "w") as f:
         json.dump({"generator": "tests/golden/make_frames_golden.py (reference data_model / imgutils)", "containers": out}, f, indent=1)
     for k, v in out.items():

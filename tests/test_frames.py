@@ -194,7 +194,8 @@ def test_containers_read_what_the_references_containers_read(tmp_path):
     with open(os.path.join(golden_dir, "frames_ref.json")) as f:
         ref = json.load(f)["containers"]
     specs = frames_inputs.build(str(tmp_path))
-    assert set(specs) | {"fromSpimFolder_pos2_count2", "DataModel"} == set(ref)
+    extra = {k for k in ref if k.startswith(("fromSpimFolder", "DemoData", "EmptyData"))}
+    assert set(specs) | extra | {"DataModel"} == set(ref)
     for key, want in ref["DataModel"].items():
         m = frames.DataModel.fromPath(os.path.join(str(tmp_path), key), prefetchSize=2)
         try:
@@ -221,6 +222,43 @@ def test_containers_read_what_the_references_containers_read(tmp_path):
     sub = np.stack([d[2], d[3]])                       # fromSpimFolder(pos=2, count=2), imgutils.py:129-146
     want = ref["fromSpimFolder_pos2_count2"]
     assert list(sub.shape) == want["shape"] and hashlib.sha1(sub.tobytes()).hexdigest() == want["sha1"]
+    # fromSpimFolder itself: a window, a window that leaves the folder, "everything behind pos", a negative pos
+    got = frames.fromSpimFolder(specs["SpimData"][1][0], pos=2, count=2)
+    assert got.dtype == np.dtype("<u2") and np.array_equal(got, sub)
+    for key in sorted(extra):
+        if key.startswith("fromSpimFolder") and "pos" in ref[key]:
+            got = frames.fromSpimFolder(specs["SpimData"][1][0], pos=ref[key]["pos"], count=ref[key]["count"])
+            assert list(got.shape) == ref[key]["shape"], key
+            assert hashlib.sha1(np.ascontiguousarray(got).tobytes()).hexdigest() == ref[key]["sha1"], key
+
+
+def test_demo_and_empty_containers_equal_the_references():
+    """DemoData(24) and EmptyData of the reference (data_model.py:434-472, 518-531) recorded by make_frames_golden.py:
+    same sizes, same float32 voxels bit for bit at three time points."""
+    import hashlib
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frames_ref.json")) as f:
+        ref = json.load(f)["containers"]
+    want = ref["DemoData_24"]
+    d = frames.DemoData(24)
+    assert list(d.size()) == want["size"] and d.sizeT() == want["sizeT"] == len(d) and d.dtype == np.float32
+    assert [float(u) for u in d.stackUnits] == want["stackUnits"]
+    for t, p in want["points"].items():
+        a = d[int(t)]
+        assert a.dtype.name == p["dtype"] and a.flags.c_contiguous
+        assert abs(float(a.max()) - p["max"]) <= 1e-6 * p["max"], t
+        assert hashlib.sha1(a.tobytes()).hexdigest() == p["sha1"], t
+    out = np.empty(d.size()[1:], np.float32)
+    d.read_into(3, out)
+    assert np.array_equal(out, d[3])
+    big = frames.DemoData()                 # the reference ships a logo stack of this size instead
+    assert big.size() == (10, 80, 80, 80) and big.sizeT() == 10 and big[9].dtype == np.float32
+    e = frames.EmptyData()
+    want = ref["EmptyData"]
+    assert list(e.size()) == want["size"] and e.sizeT() == want["sizeT"] and [float(u) for u in e.stackUnits] == want["stackUnits"]
+    assert e[0].dtype.name == want["dtype"] and list(e[0].shape) == want["shape"] and int(e[0].sum()) == want["sum"]
+    import spimagine_b200
+    assert spimagine_b200.DemoData is frames.DemoData
 
 
 class _Counting(frames.NumpyData):
