@@ -446,6 +446,45 @@ def fromSpimFolder(fName, dataFileName="data/data.bin", indexFileName="data/inde
         return np.fromfile(f, dtype="<u2", count=stackSize[0] * voxels).reshape(stackSize)
 
 
+class Img2dData(GenericData):
+    """one 2-d image as a (1, 1, Y, X) stack (data_model.py:150-175).  The reference decodes through
+    `imgutils.openImageFile`, which its imgutils does not define, so there every file ends in "couldnt open ... as
+    Img2dData"; here png / jpg / bmp are decoded by PIL where it is installed (colour images as their luminance,
+    8-bit -> uint8, 16-bit -> uint16, anything else -> float32), with the same exception otherwise."""
+
+    def __init__(self, fName=""):
+        GenericData.__init__(self, fName)
+        self.load(fName)
+
+    def load(self, fName, stackUnits=[1., 1., 1.]):
+        if fName:
+            try:
+                from PIL import Image
+                with Image.open(fName) as im:
+                    if im.mode in ("1", "P", "RGB", "RGBA", "LA", "CMYK", "YCbCr"):
+                        im = im.convert("L")
+                    a = np.asarray(im)
+                if a.dtype not in (np.uint8, np.uint16):
+                    a = a.astype(np.uint16 if a.dtype.kind in "ui" and a.min() >= 0 and a.max() < 65536 else np.float32)
+                self.img = np.ascontiguousarray(a)[None]
+                self.stackSize = (1,) + self.img.shape
+            except Exception as e:
+                print(e)
+                self.fName = ""
+                raise Exception("couldnt open %s as Img2dData" % fName)
+            self.stackUnits = stackUnits
+            self.fName = fName
+
+    @property
+    def dtype(self):
+        return self.img.dtype
+
+    def __getitem__(self, pos):
+        if self.stackSize and self.fName:
+            return self.img
+        return None
+
+
 class DemoData(GenericData):
     """The synthetic demo volume (data_model.py:434-472): a shell with ten meridian stripes plus an off-centre blob,
     float32, fading by exp(-0.3 t) over the time points.  DemoData(N) is N^3 with sizeT() == N, as in the reference;
@@ -762,8 +801,8 @@ class DataModel(object):
 
     def loadFromPath(self, fName, prefetchSize=0):
         """data_model.py:733-757: lists of tif / raw files, a tif / raw file, a SpimData / xwing / tiff folder.
-        (png / jpg / bmp images and czi files need decoders this package does not have; raw files need a shape: give
-        RawData / RawMultipleFiles to setContainer instead.)"""
+        png / jpg / bmp images (decoded by PIL).  (czi files need a decoder this package does not have; raw files
+        need a shape: give RawData / RawMultipleFiles to setContainer instead.)"""
         if isinstance(fName, (tuple, list)):
             if re.match(r".*\.(tif|tiff)", fName[0]):
                 self.setContainer(TiffMultipleFiles(fName), prefetchSize)
@@ -771,6 +810,8 @@ class DataModel(object):
                 raise ValueError("a list of %s: only lists of tif files can be opened from their paths alone" % fName[0])
         elif re.match(r".*\.(tif|tiff)", fName):
             self.setContainer(TiffData(fName), prefetchSize=0)
+        elif re.match(r".*\.(png|jpg|bmp)", fName):
+            self.setContainer(Img2dData(fName), prefetchSize=0)
         elif os.path.isdir(fName):
             if os.path.exists(os.path.join(fName, "metadata.txt")):
                 self.setContainer(SpimData(fName), prefetchSize)
@@ -779,4 +820,4 @@ class DataModel(object):
             else:
                 self.setContainer(TiffFolderData(fName), prefetchSize=prefetchSize)
         else:
-            raise ValueError("%s: no container for this path (tif file, SpimData / xwing / tiff folder)" % fName)
+            raise ValueError("%s: no container for this path (tif / png / jpg / bmp file, SpimData / xwing / tiff folder)" % fName)

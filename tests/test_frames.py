@@ -344,3 +344,30 @@ def test_data_model_chooses_the_container_from_the_path(tmp_path):
     for bad in (str(tmp_path / "x.czi"), [str(tmp_path / "a.raw")]):
         with pytest.raises(ValueError):
             frames.DataModel.fromPath(bad)
+
+
+def test_img2d_container(tmp_path):
+    """data_model.py:150-175, :770-771: a 2-d image is a (1, 1, Y, X) stack; loadFromPath picks it by extension"""
+    PIL_Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(11)
+    g8 = rng.integers(0, 256, (13, 17), dtype=np.uint8)
+    g16 = rng.integers(0, 65536, (13, 17), dtype=np.uint16)
+    rgb = rng.integers(0, 256, (13, 17, 3), dtype=np.uint8)
+    PIL_Image.fromarray(g8).save(str(tmp_path / "a.png"))
+    PIL_Image.fromarray(g16).save(str(tmp_path / "b.png"))
+    PIL_Image.fromarray(rgb).save(str(tmp_path / "c.bmp"))
+    d = frames.Img2dData(str(tmp_path / "a.png"))
+    assert d.size() == (1, 1, 13, 17) and d.sizeT() == 1 and d.dtype == np.uint8 and np.array_equal(d[0][0], g8)
+    d = frames.Img2dData(str(tmp_path / "b.png"))
+    assert d.dtype == np.uint16 and np.array_equal(d[0][0], g16)
+    d = frames.Img2dData(str(tmp_path / "c.bmp"))
+    lum = np.asarray(PIL_Image.fromarray(rgb).convert("L"))
+    assert d.dtype == np.uint8 and d[0].shape == (1, 13, 17) and np.array_equal(d[0][0], lum)
+    m = frames.DataModel.fromPath(str(tmp_path / "a.png"))
+    try:
+        assert type(m.dataContainer).__name__ == "Img2dData" and m.sizeT() == 1 and np.array_equal(m[0][0], g8)
+    finally:
+        m.close()
+    (tmp_path / "bad.png").write_bytes(b"not an image")
+    with pytest.raises(Exception, match="couldnt open .* as Img2dData"):
+        frames.Img2dData(str(tmp_path / "bad.png"))
