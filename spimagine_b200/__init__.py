@@ -11,6 +11,7 @@ from .utils.transform_matrices import *  # noqa: F401,F403
 from .frames import (DataModel, DemoData, SpimData, TiffData, TiffFolderData, NumpyData, RawData,  # noqa: F401
                      RawMultipleFiles, XwingData, GenericData)
 from .keyframes import TransformData  # noqa: F401
+from .transform_model import TransformModel  # noqa: F401
 from .utils.quaternion import Quaternion  # noqa: F401
 from .utils.tiffio import read3dTiff, write3dTiff  # noqa: F401
 
