@@ -33,7 +33,7 @@ import numpy as np
 from scipy.linalg import inv
 from scipy.linalg.lapack import get_lapack_funcs
 
-from . import _lib
+from . import _lib, config
 from .utils.transform_matrices import *  # noqa: F401,F403  (the reference module re-exports these too)
 from .utils.transform_matrices import mat4_identity, mat4_perspective, mat4_scale
 
@@ -81,11 +81,10 @@ class VolumeRenderer(object):
         self._lib = _lib.load()
         self._ctx = _lib._CTX()
         if device is None:
-            device = int(os.environ.get("SPIMAGINE_CUDA_DEVICE", "0"))
+            device = config.default_device()  # $SPIMAGINE_CUDA_DEVICE, else id_device of ~/.spimagine
         self.device = device
         self.isGPU = True
-        self.max_steps = int(max_steps) if max_steps is not None else int(
-            os.environ.get("SPIMAGINE_MAX_STEPS", DEFAULT_MAX_STEPS))
+        self.max_steps = int(max_steps) if max_steps is not None else config.default_max_steps()
         self.pinned_outputs = bool(pinned_outputs)
         w, h = size if size else (200, 200)
         rc = self._lib.spv_create(int(device), int(w), int(h), C.byref(self._ctx))
