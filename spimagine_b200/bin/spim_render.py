@@ -65,6 +65,10 @@ def build_parser():
     parser.add_argument("--keyframes", type=str, default=None, help="keyframe file saved by the spimagine GUI")
     parser.add_argument("--frames", type=int, default=100, help="number of frames of the keyframe path")
     parser.add_argument("--device", type=int, default=None, help="CUDA device")
+    parser.add_argument("--colormap", type=str, default="grays",
+                        help="colour map of the keyframe frames: grays, hot, jet, or cmap_<name>.png in --colormap-folder")
+    parser.add_argument("--colormap-folder", dest="colormap_folder", type=str, default=None,
+                        help="folder of cmap_<name>.png strips (default: $SPIMAGINE_COLORMAPS)")
     return parser
 
 
@@ -140,7 +144,8 @@ def main(argv=None):
             keyList = keyframes.KeyFrameList.load_from_JSON(args.keyframes)
             outdir = args.output if os.path.isdir(args.output) or not os.path.splitext(args.output)[1] \
                 else (os.path.dirname(args.output) or ".")
-            lut = np.repeat(np.linspace(0, 1, 256)[:, None], 3, 1)
+            from spimagine_b200 import colormaps
+            lut = colormaps.get(args.colormap, args.colormap_folder)
             # under torchrun (one process per GPU) every rank records its share of the frames
             names = keyframes.record_keyframes(rend, keyList, args.frames, outdir, lut=lut,
                                                source=container if len(container) > 1 else None,
