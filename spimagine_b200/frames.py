@@ -446,6 +446,42 @@ def fromSpimFolder(fName, dataFileName="data/data.bin", indexFileName="data/inde
         return np.fromfile(f, dtype="<u2", count=stackSize[0] * voxels).reshape(stackSize)
 
 
+class OverlayData(GenericData):
+    """Two volumes of one shape wiped over each other along `axis` (models/overlay_volumes.py:9-53): time point i shows
+    y in front of position i and x from i on, so data[0] is x and data[n] is y (n = the length of that axis,
+    n + 1 time points).  The reference keeps one output array and repaints only the slab between the last position
+    and the new one; so does this class (a step of the slider costs one slab, not one volume), and like there the
+    array that is returned is reused by the next call."""
+
+    def __init__(self, x, y, axis=-1):
+        super(OverlayData, self).__init__()
+        if x.shape != y.shape:
+            raise ValueError("shapes of the two arrays have to be equal!")
+        self.x, self.y, self.axis = x, y, axis
+        self.out = x.copy()
+        self._last_index = 0
+
+    @property
+    def dtype(self):
+        return self.out.dtype
+
+    def _slab(self, lo, hi):
+        index = [slice(None)] * self.out.ndim
+        index[self.axis] = slice(lo, hi)
+        return tuple(index)
+
+    def __getitem__(self, i):
+        if i != self._last_index:
+            lo, hi = min(i, self._last_index), max(i, self._last_index)
+            source = self.y if i > self._last_index else self.x   # moving on uncovers y, moving back restores x
+            self.out[self._slab(lo, hi)] = source[self._slab(lo, hi)]
+            self._last_index = i
+        return self.out
+
+    def size(self):
+        return (self.out.shape[self.axis] + 1,) + tuple(self.out.shape)
+
+
 class Img2dData(GenericData):
     """one 2-d image as a (1, 1, Y, X) stack (data_model.py:150-175).  The reference decodes through
     `imgutils.openImageFile`, which its imgutils does not define, so there every file ends in "couldnt open ... as

@@ -102,6 +102,17 @@ def main():
                        "sum": float(a.astype(np.float64).sum())}
     out["DemoData_24"] = {"size": [int(s) for s in demo.size()], "sizeT": int(demo.sizeT()),
                           "stackUnits": [float(u) for u in demo.stackUnits], "points": pts}
+    # OverlayData (models/overlay_volumes.py): a walk back and forth along each axis
+    import spimagine.models.overlay_volumes as ov
+    rng = np.random.default_rng(21)
+    ox, oy = rng.integers(0, 60000, (5, 6, 7)).astype(np.uint16), rng.integers(0, 60000, (5, 6, 7)).astype(np.uint16)
+    walks = {}
+    for axis in (-1, 0, 1):
+        o = ov.OverlayData(ox, oy, axis=axis)
+        walk = [0, 3, 3, 1, o.size()[0] - 1, 2, 0]
+        walks[str(axis)] = {"size": [int(s) for s in o.size()], "sizeT": int(o.sizeT()), "walk": walk,
+                            "sha1": [hashlib.sha1(np.ascontiguousarray(o[i]).tobytes()).hexdigest() for i in walk]}
+    out["OverlayData_seed21_5x6x7"] = walks
     e = dm.EmptyData()
     out["EmptyData"] = {"size": [int(s) for s in e.size()], "sizeT": int(e.sizeT()),
                         "stackUnits": [float(u) for u in e.stackUnits], "dtype": e[0].dtype.name,

@@ -194,7 +194,7 @@ def test_containers_read_what_the_references_containers_read(tmp_path):
     with open(os.path.join(golden_dir, "frames_ref.json")) as f:
         ref = json.load(f)["containers"]
     specs = frames_inputs.build(str(tmp_path))
-    extra = {k for k in ref if k.startswith(("fromSpimFolder", "DemoData", "EmptyData"))}
+    extra = {k for k in ref if k.startswith(("fromSpimFolder", "DemoData", "EmptyData", "OverlayData"))}
     assert set(specs) | extra | {"DataModel"} == set(ref)
     for key, want in ref["DataModel"].items():
         m = frames.DataModel.fromPath(os.path.join(str(tmp_path), key), prefetchSize=2)
@@ -371,3 +371,30 @@ def test_img2d_container(tmp_path):
     (tmp_path / "bad.png").write_bytes(b"not an image")
     with pytest.raises(Exception, match="couldnt open .* as Img2dData"):
         frames.Img2dData(str(tmp_path / "bad.png"))
+
+
+def test_overlay_container_equals_the_references():
+    """models/overlay_volumes.py driven through a walk along each axis by make_frames_golden.py: same sizes, same
+    bytes at every stop; data[0] is x, data[n] is y, the returned array is reused"""
+    import hashlib
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frames_ref.json")) as f:
+        ref = json.load(f)["containers"]["OverlayData_seed21_5x6x7"]
+    rng = np.random.default_rng(21)
+    x, y = rng.integers(0, 60000, (5, 6, 7)).astype(np.uint16), rng.integers(0, 60000, (5, 6, 7)).astype(np.uint16)
+    for axis, want in ref.items():
+        o = frames.OverlayData(x, y, axis=int(axis))
+        assert list(o.size()) == want["size"] and o.sizeT() == want["sizeT"] == len(o) and o.dtype == np.uint16
+        for i, sha in zip(want["walk"], want["sha1"]):
+            assert hashlib.sha1(np.ascontiguousarray(o[i]).tobytes()).hexdigest() == sha, (axis, i)
+        n = o.size()[0] - 1
+        assert np.array_equal(o[0], x) and np.array_equal(o[n], y) and o[1] is o[2]
+        out = np.empty(x.shape, np.uint16)
+        o.read_into(2, out)
+        idx = [slice(None)] * 3
+        idx[int(axis)] = slice(0, 2)
+        assert np.array_equal(out[tuple(idx)], y[tuple(idx)])
+    with pytest.raises(ValueError):
+        frames.OverlayData(x, y[:4])
+    import spimagine_b200
+    assert spimagine_b200.OverlayData is frames.OverlayData
