@@ -10,7 +10,7 @@ from .utils.transform_matrices import *  # noqa: F401,F403
 # the names spimagine/__init__.py:20-27 exports that have a counterpart here (the GUI entry points do not)
 from .frames import (DataModel, DemoData, SpimData, TiffData, TiffFolderData, NumpyData, RawData,  # noqa: F401
                      RawMultipleFiles, XwingData, GenericData)
-from .frames import OverlayData  # noqa: F401  (spimagine/__init__.py:21)
+from .frames import OverlayData, CZIData  # noqa: F401  (spimagine/__init__.py:20-21)
 from .keyframes import TransformData  # noqa: F401
 from .transform_model import TransformModel  # noqa: F401
 from .utils.quaternion import Quaternion  # noqa: F401

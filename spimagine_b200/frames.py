@@ -13,8 +13,8 @@ GUI thread or a Qt thread and re-uploads it synchronously (gui/glwidget.py:372-3
 
 Only containers whose bytes are laid out as the renderer wants them (C-order stacks of one element type) are
 rebuilt here: raw files, SpimData folders and TIFF stacks (TiffData over utils/tiffio.py: stored as they are, or
-LZW / deflate / PackBits strips or tiles decoded one page per worker thread).  JPEG-compressed TIFF and CZI decode
-through third-party libraries in the reference (tifffile, czifile); their arrays can be wrapped in NumpyData or any
+LZW / deflate / PackBits strips or tiles decoded one page per worker thread).  CZI files of uncompressed greyscale sub-blocks are read by utils/cziio.py (CZIData).
+JPEG-compressed TIFF and compressed CZI decode through third-party libraries in the reference (tifffile, czifile); their arrays can be wrapped in NumpyData or any
 object with the same protocol.
 """
 from __future__ import absolute_import, print_function
@@ -446,6 +446,49 @@ def fromSpimFolder(fName, dataFileName="data/data.bin", indexFileName="data/inde
         return np.fromfile(f, dtype="<u2", count=stackSize[0] * voxels).reshape(stackSize)
 
 
+class CZIData(GenericData):
+    """czi files (data_model.py:557-584): the squeezed array of the file must be 3-d (one stack) or 4-d (t, z, y, x).
+    The reference decodes the whole file in the constructor; here only the directory is parsed (utils/cziio.py:
+    uncompressed greyscale sub-blocks) and a time point is read when it is asked for.  A file that cannot be opened
+    raises (the reference prints the error and leaves a container without a size)."""
+
+    def __init__(self, fName=None):
+        GenericData.__init__(self, fName)
+        self.load(fName)
+
+    def load(self, fName, stackUnits=[1., 1., 1.]):
+        if fName:
+            from .utils.cziio import CziFile
+            try:
+                self._czi = CziFile(fName)
+                squeezed = tuple(n for n in self._czi.shape if n != 1)
+                if len(squeezed) not in (3, 4):
+                    raise ValueError("in file %s: data.ndim = %s (not 3 or 4)" % (fName, len(squeezed)))
+            except Exception as e:
+                print(e)
+                self.fName = ""
+                raise Exception("couldnt open %s as CZIData" % fName)
+            self._squeezed = squeezed
+            # a 4-d file whose leading axis is T is read one time point at a time
+            axes = [a for a, n in zip(self._czi.axes, self._czi.shape) if n != 1]
+            self._by_time = len(squeezed) == 4 and axes[0] == "T"
+            self._all = None
+            self.stackSize = squeezed if len(squeezed) == 4 else (1,) + squeezed
+            self.stackUnits = stackUnits
+            self.fName = fName
+
+    @property
+    def dtype(self):
+        return self._czi.dtype.newbyteorder("=")
+
+    def __getitem__(self, pos):
+        if self._by_time:
+            return self._czi.time_point(pos).reshape(self._squeezed[1:])
+        if self._all is None:
+            self._all = self._czi.asarray().reshape(self._squeezed)
+        return self._all if len(self._squeezed) == 3 else self._all[pos]
+
+
 class OverlayData(GenericData):
     """Two volumes of one shape wiped over each other along `axis` (models/overlay_volumes.py:9-53): time point i shows
     y in front of position i and x from i on, so data[0] is x and data[n] is y (n = the length of that axis,
@@ -837,8 +880,8 @@ class DataModel(object):
 
     def loadFromPath(self, fName, prefetchSize=0):
         """data_model.py:733-757: lists of tif / raw files, a tif / raw file, a SpimData / xwing / tiff folder.
-        png / jpg / bmp images (decoded by PIL).  (czi files need a decoder this package does not have; raw files
-        need a shape: give RawData / RawMultipleFiles to setContainer instead.)"""
+        png / jpg / bmp images (decoded by PIL), czi files.  (raw files need a shape: give RawData /
+        RawMultipleFiles to setContainer instead.)"""
         if isinstance(fName, (tuple, list)):
             if re.match(r".*\.(tif|tiff)", fName[0]):
                 self.setContainer(TiffMultipleFiles(fName), prefetchSize)
@@ -848,6 +891,8 @@ class DataModel(object):
             self.setContainer(TiffData(fName), prefetchSize=0)
         elif re.match(r".*\.(png|jpg|bmp)", fName):
             self.setContainer(Img2dData(fName), prefetchSize=0)
+        elif re.match(r".*\.czi", fName):
+            self.setContainer(CZIData(fName), prefetchSize=0)
         elif os.path.isdir(fName):
             if os.path.exists(os.path.join(fName, "metadata.txt")):
                 self.setContainer(SpimData(fName), prefetchSize)
@@ -856,4 +901,4 @@ class DataModel(object):
             else:
                 self.setContainer(TiffFolderData(fName), prefetchSize=prefetchSize)
         else:
-            raise ValueError("%s: no container for this path (tif / png / jpg / bmp file, SpimData / xwing / tiff folder)" % fName)
+            raise ValueError("%s: no container for this path (tif / png / jpg / bmp / czi file, SpimData / xwing / tiff folder)" % fName)

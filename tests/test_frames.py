@@ -341,9 +341,11 @@ def test_data_model_chooses_the_container_from_the_path(tmp_path):
             assert m.sizeT() == 3 and np.array_equal(m[2], data[2]), path
         finally:
             m.close()
-    for bad in (str(tmp_path / "x.czi"), [str(tmp_path / "a.raw")]):
+    for bad in (str(tmp_path / "x.h5"), [str(tmp_path / "a.raw")]):
         with pytest.raises(ValueError):
             frames.DataModel.fromPath(bad)
+    with pytest.raises(Exception, match="couldnt open .* as CZIData"):      # chosen by extension, file missing
+        frames.DataModel.fromPath(str(tmp_path / "x.czi"))
 
 
 def test_img2d_container(tmp_path):
