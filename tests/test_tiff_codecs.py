@@ -372,3 +372,28 @@ def test_tiled_float_pages_and_bad_directories(tmp_path):
     open(fn, "wb").write(raw)
     with pytest.raises(tiffio.TiffError, match="324"):
         tiffio.TiffFile(fn)
+
+
+def test_files_read_like_the_references_tifffile_reads_them(tmp_path):
+    """tests/golden/tiff_ref.json: the reference's vendored tifffile.imread (what read3dTiff / TiffData call there) on
+    the files of tests/golden/tiff_inputs.py -- stacks written by this package's writer (2-d, 3-d, ImageJ 4-d,
+    BigTIFF) and strip / tile files with LZW, deflate and the predictor in both byte orders"""
+    import hashlib
+    import json
+    import sys
+    golden = os.path.join(ROOT, "tests", "golden")
+    sys.path.insert(0, golden)
+    try:
+        import tiff_inputs
+    finally:
+        sys.path.remove(golden)
+    with open(os.path.join(golden, "tiff_ref.json")) as f:
+        ref = json.load(f)["files"]
+    files = tiff_inputs.build(str(tmp_path))
+    assert sorted(files) == sorted(ref) and len(ref) >= 20
+    for name, fn in files.items():
+        got = np.ascontiguousarray(tiffio.read3dTiff(fn))
+        want = ref[name]
+        assert got.dtype.name == want["dtype"] and got.dtype.isnative, name
+        assert list(np.squeeze(got).shape) == list(np.squeeze(np.empty(want["shape"])).shape), name
+        assert hashlib.sha1(got.tobytes()).hexdigest() == want["sha1"], name
