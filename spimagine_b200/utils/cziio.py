@@ -1,5 +1,5 @@
 """Carl Zeiss CZI (ZISRAW) stacks without third-party decoders: the plain case light-sheet and confocal acquisitions
-produce -- uncompressed greyscale sub-blocks listed in a sub-block directory.
+produce -- uncompressed (or LZW) greyscale sub-blocks listed in a sub-block directory.
 
 The reference reads CZI through a vendored `czifile` (spimagine/lib/czifile.py; imgutils.py:44-47 readCziFile,
 data_model.py:557-584 CZIData).  From the ZISRAW layout this module implements:
@@ -13,7 +13,8 @@ The array is assembled as czifile does: its shape spans `min(start) .. max(start
 the mosaic index M, each sub-block is pasted at `start - min(start)`.  `read_into` pastes straight into caller memory
 (a page-locked buffer of frames.FrameSource); `time_point(t)` reads only the sub-blocks of one T index.
 
-Refused with CziError naming the field: compressed sub-blocks (JPEG / LZW / JPEG-XR), colour and complex pixel
+LZW sub-blocks (compression 2) are decoded by libspimtiff.so, as czifile decodes them with tifffile's LZW.
+Refused with CziError naming the field: JPEG / JPEG-XR sub-blocks, colour and complex pixel
 types, pyramid levels (stored size != size), files without a directory.
 """
 import struct
@@ -34,7 +35,7 @@ class CziError(ValueError):
 
 
 class _Block(object):
-    __slots__ = ("dtype", "position", "dims", "start", "shape", "mosaic")
+    __slots__ = ("dtype", "position", "dims", "start", "shape", "mosaic", "compression")
 
 
 class CziFile(object):
@@ -90,10 +91,11 @@ class CziFile(object):
             raise CziError("%s: directory entry of schema %r" % (self.fName, schema))
         if pixel not in _PIXEL:
             raise CziError("%s: pixel type %s is not supported" % (self.fName, _PIXEL_NAMES.get(pixel, pixel)))
-        if compression:
-            raise CziError("%s: compressed sub-blocks are not supported (compression = %d)" % (self.fName, compression))
+        if compression not in (0, 2):
+            raise CziError("%s: this sub-block compression is not supported (compression = %d: %s)"
+                           % (self.fName, compression, {1: "JPEG", 4: "JPEG XR"}.get(compression, "camera specific")))
         b = _Block()
-        b.dtype, b.position, b.mosaic = np.dtype(_PIXEL[pixel]), position, None
+        b.dtype, b.position, b.mosaic, b.compression = np.dtype(_PIXEL[pixel]), position, None, compression
         dims = []
         for _ in range(ndim):
             name, start, size, _, stored = _DIM.unpack(f.read(_DIM.size))
@@ -119,6 +121,17 @@ class CziFile(object):
         # the entry copy is padded so that sizes + entry take 256 bytes (16 + 240), then the XML, then the pixels
         f.seek(ndim * _DIM.size + max(240 - (_ENTRY.size + ndim * _DIM.size), 0) + metadata_size, 1)
         want = int(np.prod(b.shape)) * b.dtype.itemsize
+        if b.compression == 2:
+            # LZW as in TIFF (czifile decodes it with tifffile's decoder): libspimtiff.so, include/spimtiff.h
+            import ctypes
+            from .tiffio import load_codecs
+            raw = f.read(data_size)
+            a = np.empty(want // b.dtype.itemsize, b.dtype)
+            n = ctypes.c_size_t(0)
+            rc = load_codecs().spt_lzw_decode(raw, len(raw), a.ctypes.data, want, ctypes.byref(n))
+            if rc not in (0, -3) or n.value < want:
+                raise CziError("%s: damaged LZW sub-block at %d" % (self.fName, b.position))
+            return a.reshape(b.shape)
         if data_size < want:
             raise CziError("%s: the sub-block at %d holds %d bytes, %d are needed" % (self.fName, b.position, data_size, want))
         a = np.fromfile(f, b.dtype, want // b.dtype.itemsize)

@@ -22,7 +22,7 @@ def _entry(pixel, file_position, dims, compression=0, pyramid=0):
     return e
 
 
-def write_czi(fName, data, axes, block_axes, starts=None, metadata=b"<METADATA/>", with_mosaic=False):
+def write_czi(fName, data, axes, block_axes, starts=None, metadata=b"<METADATA/>", with_mosaic=False, lzw=None):
     """data: array whose axes are named by `axes` (e.g. "TZYX"); one sub-block per index of the axes NOT in
     block_axes (e.g. block_axes "YX": one plane per (T, Z)).  starts: {axis: offset} added to every start index
     (acquisitions that do not begin at 0)."""
@@ -50,15 +50,17 @@ def write_czi(fName, data, axes, block_axes, starts=None, metadata=b"<METADATA/>
     for dims, part in blocks:
         pos = header_size + len(body)
         positions.append(pos)
-        entry = _entry(pixel, pos, dims)
+        entry = _entry(pixel, pos, dims, compression=2 if lzw else 0)
         raw = part.astype(part.dtype.newbyteorder("<")).tobytes()
+        if lzw:
+            raw = lzw(raw)
         payload = struct.pack("<iiq", len(metadata), 0, len(raw)) + entry
         payload += b"\0" * max(256 - len(payload), 0) + metadata + raw
         body += _segment(b"ZISRAWSUBBLOCK", payload)
     directory_position = header_size + len(body)
     payload = struct.pack("<i", len(blocks)) + b"\0" * 124
     for (dims, part), pos in zip(blocks, positions):
-        payload += _entry(pixel, pos, dims)
+        payload += _entry(pixel, pos, dims, compression=2 if lzw else 0)
     body += _segment(b"ZISRAWDIRECTORY", payload)
     guid = bytes(range(16))
     head = struct.pack("<iiii16s16siqqiq", 1, 0, 0, 0, guid, guid, 0, directory_position, 0, 0, 0)
@@ -75,4 +77,26 @@ def cases():
         "tzyx_planes_u8": (rng.integers(0, 256, (3, 4, 5, 6)).astype(np.uint8), "TZYX", "YX", {"T": 2, "Z": 10}, False),
         "tzyx_stacks_f32": (rng.normal(size=(2, 3, 4, 5)).astype(np.float32), "TZYX", "ZYX", None, False),
         "czyx_mosaic_u16": (rng.integers(0, 60000, (1, 4, 5, 6)).astype(np.uint16), "CZYX", "YX", {"C": 1}, True),
+        # written with LZW sub-blocks (write_czi(..., lzw=encoder)): smooth, so that strings grow
+        "zyx_planes_u16_lzw": ((1000 * np.exp(-np.linspace(-2, 2, 6 * 40 * 50).reshape(6, 40, 50) ** 2)).astype(np.uint16),
+                               "ZYX", "YX", None, False),
     }
+
+
+def lzw_encoder():
+    """the TIFF 6.0 encoder of tests/test_tiff_codecs.py"""
+    import os
+    import sys
+    tests = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, tests)
+    try:
+        import test_tiff_codecs
+    finally:
+        sys.path.remove(tests)
+    return test_tiff_codecs._lzw_encode
+
+
+def write_case(fName, key):
+    data, axes, block_axes, starts, mosaic = cases()[key]
+    write_czi(fName, data, axes, block_axes, starts, with_mosaic=mosaic, lzw=lzw_encoder() if key.endswith("_lzw") else None)
+    return data

@@ -19,6 +19,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 REF = "/root/reference"
 
 
@@ -29,12 +30,15 @@ def main():
         m.__path__ = [os.path.join(REF, *name.split("."))]
         sys.modules[name] = m
     warnings.simplefilter("ignore")
+    old = np.fromstring      # binary mode removed from numpy; czifile's LZW path uses it
+    np.fromstring = lambda s, dtype=float, count=-1, sep="": (np.frombuffer(s, dtype, count).copy() if sep == ""
+                                                               else old(s, dtype, count, sep=sep))
     import spimagine.lib.czifile as cz
     out = {}
     with tempfile.TemporaryDirectory() as root:
         for key, (data, axes, block_axes, starts, mosaic) in czi_inputs.cases().items():
             fn = os.path.join(root, key + ".czi")
-            czi_inputs.write_czi(fn, data, axes, block_axes, starts, with_mosaic=mosaic)
+            czi_inputs.write_case(fn, key)
             with cz.CziFile(fn) as f:
                 image = np.zeros(f.shape, f.dtype)
                 blocks = []

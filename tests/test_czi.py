@@ -31,7 +31,7 @@ def test_files_read_like_the_references_reader_reads_them(tmp_path, key):
         want = json.load(f)["files"][key]
     data, axes, block_axes, starts, mosaic = czi_inputs.cases()[key]
     fn = str(tmp_path / (key + ".czi"))
-    czi_inputs.write_czi(fn, data, axes, block_axes, starts, with_mosaic=mosaic)
+    czi_inputs.write_case(fn, key)
     c = cziio.CziFile(fn)
     # czifile appends a samples axis "0" of length 1 to greyscale files
     assert c.axes + "0" == want["axes"] and list(c.shape) + [1] == want["shape"] and list(c.start) + [0] == want["start"]
