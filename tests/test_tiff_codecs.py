@@ -397,3 +397,38 @@ def test_files_read_like_the_references_tifffile_reads_them(tmp_path):
         assert got.dtype.name == want["dtype"] and got.dtype.isnative, name
         assert list(np.squeeze(got).shape) == list(np.squeeze(np.empty(want["shape"])).shape), name
         assert hashlib.sha1(got.tobytes()).hexdigest() == want["sha1"], name
+
+
+def test_frame_source_prefetches_compressed_time_points(tmp_path):
+    """a folder of LZW-compressed stacks (one file per time point, as Fiji's "save as image sequence" with compression
+    writes them) and a CZI timelapse go through FrameSource's reader thread like plain files"""
+    data = _smooth((4, 5, 30, 41), np.uint16, seed=9)
+    folder = tmp_path / "series"
+    folder.mkdir()
+    for t in range(4):
+        pages = [PIL_Image.fromarray(x) for x in data[t]]
+        pages[0].save(str(folder / ("t%03d.tif" % t)), compression="tiff_lzw", save_all=True, append_images=pages[1:],
+                      tiffinfo={317: 2})
+    d = frames.TiffFolderData(str(folder))
+    assert tuple(d.size()) == data.shape
+    src = frames.FrameSource(d, frames=[0, 1, 2, 3], depth=2, pinned=False)
+    try:
+        for t in range(4):
+            assert np.array_equal(src[t], data[t])
+    finally:
+        src.close()
+    import sys
+    golden = os.path.join(ROOT, "tests", "golden")
+    sys.path.insert(0, golden)
+    try:
+        import czi_inputs
+    finally:
+        sys.path.remove(golden)
+    fn = str(tmp_path / "t.czi")
+    czi_inputs.write_czi(fn, data, "TZYX", "YX", lzw=_lzw_encode)
+    c = frames.CZIData(fn)
+    src = frames.FrameSource(c, frames=[3, 1], depth=2, pinned=False)
+    try:
+        assert np.array_equal(src[3], data[3]) and np.array_equal(src[1], data[1])
+    finally:
+        src.close()
