@@ -488,6 +488,13 @@ class CZIData(GenericData):
             self._all = self._czi.asarray().reshape(self._squeezed)
         return self._all if len(self._squeezed) == 3 else self._all[pos]
 
+    def read_into(self, pos, out):
+        """sub-blocks of time point `pos` pasted straight into `out` (FrameSource's page-locked buffers)"""
+        if self._by_time and out.flags.c_contiguous and out.dtype == self.dtype:
+            self._czi.time_point(pos, out=out)
+        else:
+            GenericData.read_into(self, pos, out)
+
 
 class OverlayData(GenericData):
     """Two volumes of one shape wiped over each other along `axis` (models/overlay_volumes.py:9-53): time point i shows
