@@ -24,19 +24,15 @@ int spt_version(void) { return 100; }
 
 int spt_lzw_decode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *written) {
     if (!src || !dst || !written) return -1;
-    /* a string is its prefix code plus one byte; its length and first byte are kept so that it can be written
-     * back to front in one pass */
-    uint16_t prefix[LZW_MAX];
-    uint8_t suffix[LZW_MAX], first[LZW_MAX];
+    /* Every table string is the previous code's string plus one byte, and that is exactly what lies in the output
+     * from where the previous string was written: an entry is (position in the output, length), and a code is
+     * decoded by copying forwards inside dst -- no prefix chains, no per-byte table walk. */
+    size_t where[LZW_MAX];
     uint32_t length[LZW_MAX];
-    for (int i = 0; i < 256; i++) {
-        prefix[i] = 0;
-        suffix[i] = first[i] = (uint8_t)i;
-        length[i] = 1;
-    }
-    size_t out = 0, at = 0;
+    size_t out = 0, at = 0, prev_at = 0;
+    uint32_t prev_len = 0;
     uint64_t acc = 0;
-    int have = 0, width = 9, next = LZW_FIRST, prev = -1, overflow = 0;
+    int have = 0, width = 9, next = LZW_FIRST, prev = -1;
     *written = 0;
     for (;;) {
         while (have < width && at < n) {
@@ -53,43 +49,49 @@ int spt_lzw_decode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_
             prev = -1;
             continue;
         }
+        size_t from;
         uint32_t len;
-        if (prev < 0) {
-            if (code >= 256) return -2;
+        if (code < 256) {
+            from = 0;
             len = 1;
+        } else if (prev < 0) {
+            return -2; /* a table code right behind a clear code */
         } else if (code < next) {
+            from = where[code];
             len = length[code];
         } else if (code == next && next < LZW_MAX) {
-            len = length[prev] + 1;
+            from = prev_at; /* the string being defined: previous string + its own first byte */
+            len = prev_len + 1;
         } else {
             return -2;
         }
         if (prev >= 0 && next < LZW_MAX) {
-            prefix[next] = (uint16_t)prev;
-            first[next] = first[prev];
-            suffix[next] = code < next ? first[code] : first[prev];
-            length[next] = length[prev] + 1;
+            where[next] = prev_at;
+            length[next] = prev_len + 1;
             next++;
             if (next + 1 >= (1 << width) && width < 12) width++;
         }
-        /* write the string of `code` back to front, dropping what lies beyond cap */
-        size_t end = out + len;
-        int c = code;
-        for (uint32_t k = len; k > 0; k--) {
-            size_t p = out + k - 1;
-            if (p < cap) dst[p] = suffix[c];
-            c = prefix[c];
+        uint32_t take = len;
+        int overflow = out + len > cap;
+        if (overflow) take = (uint32_t)(cap - out);
+        if (code < 256) {
+            if (take) dst[out] = (uint8_t)code;
+        } else if (take > 32 && from + take <= out) {
+            memcpy(dst + out, dst + from, take);
+        } else {
+            for (uint32_t k = 0; k < take; k++) dst[out + k] = dst[from + k]; /* overlaps its own output */
         }
-        if (end > cap) {
-            overflow = 1;
-            out = cap;
-            break;
+        if (overflow) {
+            *written = cap;
+            return -3;
         }
-        out = end;
+        prev_at = out;
+        prev_len = len;
+        out += len;
         prev = code;
     }
     *written = out;
-    return overflow ? -3 : 0;
+    return 0;
 }
 
 int spt_packbits_decode(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *written) {
