@@ -432,3 +432,23 @@ def test_frame_source_prefetches_compressed_time_points(tmp_path):
         assert np.array_equal(src[3], data[3]) and np.array_equal(src[1], data[1])
     finally:
         src.close()
+
+
+def test_decoders_survive_arbitrary_bytes():
+    """files are untrusted input: random and mutated streams never write outside [dst, dst + cap) and never crash"""
+    from hypothesis import given, settings, strategies as st
+
+    good = _lzw_encode(np.random.default_rng(1).integers(0, 7, 5000, dtype=np.uint8).tobytes())
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.binary(max_size=600), st.integers(0, 700), st.integers(0, len(good) - 1), st.integers(0, 255))
+    def run(raw, cap, where, value):
+        for fn in ("spt_lzw_decode", "spt_packbits_decode"):
+            rc, got = _decode(fn, raw, cap)
+            assert rc in (0, -2, -3) and len(got) <= cap
+        mutated = bytearray(good)
+        mutated[where] = value
+        rc, got = _decode("spt_lzw_decode", bytes(mutated), 5000)
+        assert rc in (0, -2, -3) and len(got) <= 5000
+
+    run()
