@@ -372,6 +372,8 @@ class TiffFile(object):
     def _decode_block(self, fd, p, o, c, part):
         """one strip or tile: c bytes at file offset o -> exactly len(part) bytes"""
         want = len(part)
+        if c < 0 or o < 0 or o + c > self._size:      # checked before allocating c bytes
+            raise TiffError("%s: the block at %d (%d bytes) leaves the file" % (self.fName, o, c))
         raw = os.pread(fd, c, o)
         if len(raw) < c:
             raise TiffError("%s: the block at %d leaves the file" % (self.fName, o))

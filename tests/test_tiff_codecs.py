@@ -452,3 +452,16 @@ def test_decoders_survive_arbitrary_bytes():
         assert rc in (0, -2, -3) and len(got) <= 5000
 
     run()
+
+
+def test_block_sizes_are_checked_against_the_file(tmp_path):
+    a = _smooth((16, 16), np.uint8, seed=2)
+    fn = str(tmp_path / "t.tif")
+    _tiff_with_strips(fn, a, 8, 1, rows_per_strip=16)
+    raw = bytearray(open(fn, "rb").read())
+    at = 8 + 2 + 12 * 8 + 8            # value of tag 279 (the single strip's byte count)
+    assert struct.unpack(">H", raw[at - 8:at - 6])[0] == 279
+    raw[at:at + 4] = struct.pack(">I", 0x7FFFFFFF)
+    open(fn, "wb").write(raw)
+    with pytest.raises(tiffio.TiffError, match="leaves the file"):
+        tiffio.TiffFile(fn).asarray()
