@@ -279,6 +279,21 @@ class TransformModel(object):
     def toTransformData(self):
         return TransformData(quatRot=self.quatRot, **{k: getattr(self, k) for k in self._TD_FIELDS})
 
+    # -- the "spin current view" button (gui/mainwidget.py:750-765) -----------------------------------------------
+    def spin(self, n_frames, angle=-.02, axis=None):
+        """Generator over n_frames ticks of the GUI's rotate timer: each tick is addRotation(-.02, axis) -- a turn by
+        0.04 rad, the angle being a half angle -- about the axis `spin_axis` of ~/.spimagine names (0 / 1 / 2 = x / y /
+        z, default y), and yields the modelView the renderer gets.  157 ticks are one revolution.
+        `renderer.render_sequence(list(model.spin(n)))` renders the sweep with frames in flight."""
+        if axis is None:
+            from . import config
+            axis = config.get_param("spin_axis")
+        direction = [0, 0, 0]
+        direction[int(axis)] = 1
+        for _ in range(int(n_frames)):
+            self.addRotation(angle, *direction)
+            yield self.getUnscaledModelView()
+
     # -- the renderer (addition) ------------------------------------------------------------------------------------
     def apply(self, renderer):
         """The setter calls GLWidget makes on its renderer before render() (gui/glwidget.py:362-366, 610-636, 322-326):

@@ -100,3 +100,27 @@ def test_apply_makes_the_widgets_setter_calls():
     assert d["set_box_boundaries"] == ([-1., 1., -.5, .5, -1., 1.],)
     assert d["set_occ_strength"] == (.15,) and d["set_occ_radius"] == (21,) and d["set_occ_n_points"] == (31,)
     assert np.array_equal(d["set_projection"][0], m.getProjection())
+
+
+def test_spin_is_the_rotate_timer(tmp_path, monkeypatch):
+    """gui/mainwidget.py:760-765: every tick adds a rotation of half angle -0.02 about the configured spin axis"""
+    monkeypatch.setenv("SPIMAGINE_CONFIG", str(tmp_path / "none"))
+    m, ref = TransformModel(), TransformModel()
+    ticks = []
+    m._rotationChanged.connect(lambda: ticks.append(1))
+    views = list(m.spin(5))
+    for v in views:
+        ref.addRotation(-.02, 0, 1, 0)                 # spin_axis defaults to y
+        assert np.array_equal(v, ref.getUnscaledModelView())
+    assert len(ticks) == 5 and np.array_equal(m.quatRot.data, ref.quatRot.data)
+    # five ticks turn the view by 5 * 0.04 rad about y
+    rot = m.quatRot.toRotation4()[:3, :3]
+    assert np.allclose(np.arccos(rot[0, 0]), .2, atol=1e-12) and np.allclose(rot[1], [0, 1, 0])
+    (tmp_path / "cfg").write_text("spin_axis = 2\n")
+    monkeypatch.setenv("SPIMAGINE_CONFIG", str(tmp_path / "cfg"))
+    m = TransformModel()
+    list(m.spin(3))
+    assert np.allclose(m.quatRot.toRotation4()[2, :3], [0, 0, 1])           # about z now
+    m = TransformModel()
+    list(m.spin(2, angle=.1, axis=0))
+    assert np.allclose(m.quatRot.toRotation4()[0, :3], [1, 0, 0])
