@@ -150,6 +150,7 @@ def main(argv=None):
             names = keyframes.record_keyframes(rend, keyList, args.frames, outdir, lut=lut,
                                                source=container if len(container) > 1 else None,
                                                isPerspective=not args.ortho,
+                                               use_source_units=False,  # -u wins, as for a single time point
                                                rank=int(os.environ.get("RANK", "0")),
                                                world=int(os.environ.get("WORLD_SIZE", "1")))
             print("%d frames written to %s" % (len(names), outdir))

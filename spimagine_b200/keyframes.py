@@ -291,7 +291,7 @@ def keyframe_times(nFrames):
 
 
 def render_keyframes(renderer, keyList, nFrames, source=None, isPerspective=True, pinned=False, pipelined=True,
-                     iso_planes=7, rank=0, world=1):
+                     iso_planes=7, rank=0, world=1, use_source_units=True):
     """Generator over (recordPos, transformData, renderer) for the nFrames frames of the record loop;
     renderer.output / output_alpha (+ the iso planes) hold that frame when it is yielded.
 
@@ -303,6 +303,8 @@ def render_keyframes(renderer, keyList, nFrames, source=None, isPerspective=True
     pipelined   runs of frames with the same render method go through render_sequence
     iso_planes  7: every result plane of an iso-surface frame is read back; 2: only output and output_alpha (what a
                 recorded frame shows), the other planes stay on the device and read as None
+    use_source_units   take the voxel size from source.stackUnits when the source has one (as the GUI does when a
+                data model is loaded); False keeps what the caller set with renderer.set_units (spim_render -u)
     rank, world this process renders frames rank + 1, rank + 1 + world, ... of the loop (one process per GPU, every one
                 with the whole volume or time series; no data-path collective: frames are independent)"""
     if not (0 <= rank < world):
@@ -322,9 +324,10 @@ def render_keyframes(renderer, keyList, nFrames, source=None, isPerspective=True
                     renderer.set_data(vol)
                 else:
                     renderer.update_data(vol, pinned=pinned)
-                if hasattr(source, "stackUnits"):
+                if use_source_units and hasattr(source, "stackUnits"):
                     units = source.stackUnits() if callable(source.stackUnits) else source.stackUnits
-                    renderer.set_units(units)
+                    if units is not None:  # OverlayData / a bare GenericData carry none
+                        renderer.set_units(units)
                 state["pos"] = pos
         return apply_transform(renderer, td, isPerspective)
 

@@ -252,6 +252,35 @@ class SlabMaxProjector(VolumeRenderer):
         self._connected = False  # the staging moved: connect() again
 
 
+    # The pipelined / device-only entry points of VolumeRenderer call the single-context kernels directly; on a slab
+    # context they would return this rank's windowed partial alone.  Every frame of a slab renderer goes through the
+    # composite instead (the peers must make the same calls, as with render()).
+    def render_sequence(self, modelViews, method="max_project", depth=2, iso_planes=7):
+        if not hasattr(self, 'dataImg'):
+            print("no data provided, set_data(data) before")
+            return
+        if method not in ("max_project", "iso_surface"):
+            raise KeyError("method = '%s' not defined, valid: ['max_project', 'iso_surface']" % method)
+        for M in modelViews:
+            self.set_modelView(M)
+            self.render(method=method)
+            yield self
+
+    def render_device_only(self, numParts=1, currentPart=0):
+        """Enqueue one composited max projection without reading anything back (the peers must do the same)."""
+        if numParts != 1 or self.alphaPow != 0:
+            raise NotImplementedError("sort-last compositing needs alpha_pow == 0 and numParts == 1")
+        if self.composite == "peer":
+            self.enqueue_composite()
+            return
+        p = _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma), 0.,
+                           1, 0, int(self.max_steps), _lib.MIP_RAW_ONLY)
+        self._check(self._lib.spv_render_mip(self._ctx, C.byref(p)))
+        if self.world > 1 and self._dist.is_initialized():
+            with self._torch.cuda.stream(self._stream):
+                composite_max(self._raw_tensor(), self.group)
+        self._check(self._lib.spv_mip_finish(self._ctx, C.byref(p)))
+
     def _raw_tensor(self):
         p = C.c_void_p()
         self._check(self._lib.spv_device_ptr(self._ctx, _lib.BUF_RAW, C.byref(p)))

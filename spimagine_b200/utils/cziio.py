@@ -17,6 +17,7 @@ LZW sub-blocks (compression 2) are decoded by libspimtiff.so, as czifile decodes
 Refused with CziError naming the field: JPEG / JPEG-XR sub-blocks, colour and complex pixel
 types, pyramid levels (stored size != size), files without a directory.
 """
+import os
 import struct
 
 import numpy as np
@@ -121,6 +122,10 @@ class CziFile(object):
         # the entry copy is padded so that sizes + entry take 256 bytes (16 + 240), then the XML, then the pixels
         f.seek(ndim * _DIM.size + max(240 - (_ENTRY.size + ndim * _DIM.size), 0) + metadata_size, 1)
         want = int(np.prod(b.shape)) * b.dtype.itemsize
+        fsize = os.fstat(f.fileno()).st_size
+        if data_size < 0 or data_size > fsize or want > (1 << 40):  # file-controlled sizes must not size reads / arrays
+            raise CziError("%s: the sub-block at %d declares %d bytes for %d pixels bytes" % (
+                self.fName, b.position, data_size, want))
         if b.compression == 2:
             # LZW as in TIFF (czifile decodes it with tifffile's decoder): libspimtiff.so, include/spimtiff.h
             import ctypes
@@ -162,7 +167,11 @@ class CziFile(object):
         want = self.start[k] + t
         mine = [b for b in self.blocks if b.start[k] <= want < b.start[k] + b.shape[k]]
         if any(b.shape[k] != 1 for b in mine):
-            return self.asarray().take(t, axis=k)         # sub-blocks that span several time points: read them all
+            arr = self.asarray().take(t, axis=k)          # sub-blocks that span several time points: read them all
+            if out is None:
+                return arr
+            np.copyto(out.reshape(arr.shape), arr)        # the caller's buffer is what FrameSource uploads
+            return out.reshape(arr.shape)
         shape = self.shape[:k] + (1,) + self.shape[k + 1:]
         full = np.zeros(shape, self.dtype.newbyteorder("=")) if out is None else out.reshape(shape)
         if out is not None:

@@ -161,7 +161,13 @@ class TiffFile(object):
         bo = self._bo
         cnt_fmt, ent, off_fmt, inline = ("Q", 20, "Q", 8) if self._big else ("H", 12, "I", 4)
         f.seek(at)
-        n = struct.unpack(bo + cnt_fmt, f.read(struct.calcsize(cnt_fmt)))[0]
+        head = f.read(struct.calcsize(cnt_fmt))
+        if len(head) < struct.calcsize(cnt_fmt):
+            raise TiffError("%s: truncated image directory" % self.fName)
+        n = struct.unpack(bo + cnt_fmt, head)[0]
+        fsize = os.fstat(f.fileno()).st_size
+        if n * ent > fsize:  # a file-controlled count must not size a read
+            raise TiffError("%s: image directory with %d entries does not fit the file" % (self.fName, n))
         raw = f.read(n * ent + struct.calcsize(off_fmt))
         if len(raw) < n * ent + struct.calcsize(off_fmt):
             raise TiffError("%s: truncated image directory" % self.fName)
@@ -180,6 +186,8 @@ class TiffFile(object):
                                _TILE_COUNTS):  # all others fit inline
                     continue  # a big value of a tag this reader does not use (colour maps, ImageJ metadata, ...)
                 where = struct.unpack(bo + off_fmt, value[:inline])[0]
+                if nbytes > fsize or where > fsize - nbytes:
+                    raise TiffError("%s: tag %d points beyond the file" % (self.fName, tag))
                 here = f.tell()
                 f.seek(where)
                 value = f.read(nbytes)
@@ -275,7 +283,8 @@ class TiffFile(object):
             k, _, v = line.partition("=")
             if k in ("images", "slices", "frames", "channels"):
                 try:
-                    out[k] = int(v)
+                    if int(v) > 0:  # a negative or zero count is a damaged description: ignore the key
+                        out[k] = int(v)
                 except ValueError:
                     pass
         return out

@@ -519,7 +519,8 @@ class VolumeRenderer(object):
         the reference, blocks on the read-back of every frame (volumerender.py:388-390) -- frame i+1 is rendered
         while frame i is still being copied to pinned host memory (two output slots, spv_select_slot /
         spv_read_pinned_async / spv_wait_slot).  With pinned_outputs=True the yielded arrays are views of the
-        slot's staging memory and stay valid until the frame after next has been yielded; otherwise copies.
+        slot's staging memory and are valid only until the NEXT frame is requested from the generator: resuming it
+        issues frame i+2 into the slot of frame i (copy a frame that must outlive that); otherwise copies.
         iso_planes=2 reads back only what a display needs of an iso-surface frame (output, output_alpha: 8 of the
         28 bytes per pixel); output_depth / output_normals / output_occlusion are None for such frames."""
         if not hasattr(self, 'dataImg'):
