@@ -57,6 +57,14 @@ def parse():
                     help="edge of the synthetic volume (default: %d; 1024 for the iso workload = configs[2])" % VOL_N)
     ap.add_argument("--img", type=int, default=IMG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true",
+                    help="sweep workload: leave out the `c4` record (BASELINE configs[3], the 2048^3 sort-last composite; "
+                         "at --gpus 1 its single-GPU baselines)")
+    ap.add_argument("--c4-vol", type=int, default=2048)
+    ap.add_argument("--c4-img", type=int, default=2048)
+    ap.add_argument("--c4-steps", type=int, default=24)
+    ap.add_argument("--mip-path", default=None, choices=[None, "tmu", "smem"],
+                    help="max-projection kernel family (default: the library's choice)")
     ap.add_argument("--workload", default="sweep", choices=["sweep", "slab", "timelapse", "iso", "blur", "keyframes"],
                     help="sweep: BASELINE configs[1], frames sharded over the GPUs (default). slab: configs[3], one "
                          "--vol^3 uint16 volume split into z-slabs over the GPUs, sort-last max composite. timelapse: "
@@ -87,6 +95,25 @@ def parse():
 def sweep_cameras(n=SWEEP):
     import scenes
     return [scenes.gui_camera(2 * math.pi * f / n, 4.0) for f in range(n)]
+
+
+def sweep_thetas(steps, rank, world):
+    """View angles (radians) of the K = steps timed frames of rank r of N: 2 pi (j / K + r / (K N)), j < K.  Every
+    rank's frames cover the 360-degree sweep with the same spacing, whatever K and N are, so `value` measures the sweep
+    the metric names and the work per GPU does not change with N (the frame time depends on the angle:
+    profiles/r01_exp_mip_time_vs_angle.txt)."""
+    return [2 * math.pi * (j / float(steps) + rank / float(steps * world)) for j in range(steps)]
+
+
+def sweep_config(args):
+    """`config` of the headline workload -- the same dict in both arms (--impl ours / reference)."""
+    return {
+        "workload": "Vol-G(%d, uint16, seed 0) max_project -> %dx%d, max_steps=200 (208 samples per hit ray); step j "
+                    "of rank r of N renders the sweep angle 360 (j / K + r / (K N)) degrees, K = steps: every rank's "
+                    "frames cover the 360-degree sweep evenly" % (args.vol, args.img, args.img),
+        "camera": "perspective(60,1,.1,10), translate(0,0,-4) . rotation(theta + 1e-3, y)",
+        "window": "minVal 0, maxVal 60000, gamma 1, alpha_pow 0, box +-1, units 1",
+    }
 
 
 def measured_peaks():
@@ -161,7 +188,7 @@ def use_all_host_threads():
     return n
 
 
-def cpu_reference(vol, cams, img, steps, warmup, budget_s, report_all):
+def cpu_reference(vol, cams, img, steps, warmup, budget_s):
     """Time the reference kernels on the host cores.  -> dict(fps, gsamples, kind, cores, sample, ms_per_step)"""
     from oracle import oracle
     use_all_host_threads()
@@ -205,18 +232,19 @@ def cpu_reference(vol, cams, img, steps, warmup, budget_s, report_all):
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's own kernel text compiled for the host (oracle/_ref; the C restatement where
+    that build is missing) on all host cores, same config / steps / warm-up as the GPU arm, frames of rank 0."""
     if rank != 0:
         return
     import scenes
     vol = scenes.vol_g(args.vol, np.uint16, seed=0)
-    cams = sweep_cameras()
-    res = cpu_reference(vol, cams, args.img, args.steps, min(args.warmup, 3), 100.0, True)
+    cams = [scenes.gui_camera(th, 4.0) for th in sweep_thetas(args.steps, 0, max(1, args.gpus))]
+    res = cpu_reference(vol, cams, args.img, args.steps, args.warmup, 100.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["fps"], "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 3), "ms_per_step": res["ms_per_step"],
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16->f32", "data": "synthetic",
-        "config": {"workload": "Vol-G(%d, uint16, seed 0) max_project -> %dx%d, max_steps=200" % (
-            args.vol, args.img, args.img), "camera": "perspective(60), translate(0,0,-4) . rotation(theta, y)"},
+        "config": sweep_config(args),
         "gsamples_per_s": res["gsamples"],
         "cpu_baseline": {"value": res["fps"], "unit": "frames/s", "cores": res["cores"], "kind": res["kind"],
                          "sample": res["sample"]},
@@ -738,7 +766,7 @@ def run_keyframes(args, rank, local_rank, world):
                                 "fresh pageable memory (the reference's SpimData path)"}}))
 
 
-def run_bricks(args):
+def run_bricks(args, local_rank=0):
     """The single-GPU-brick baseline of BASELINE configs[3]: the same slab kernels on ONE GPU, the volume cut into
     --bricks z-slabs, each rendered by its own launch one after the other (what a single GPU does when the volume
     has to be processed brick by brick), the raw partials max-merged (torch.maximum: plumbing), then windowed."""
@@ -748,15 +776,15 @@ def run_bricks(args):
     from spimagine_b200 import _lib
     from spimagine_b200.multigpu import SlabMaxProjector, partition_slabs, slab_with_halo
 
-    torch.cuda.set_device(0)
+    torch.cuda.set_device(local_rank)
     N, W, B = args.vol, args.img, args.bricks
-    stream = torch.cuda.Stream(device=0)
+    stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
     parts = []
     for i, (z0, z1) in enumerate(partition_slabs(N, B)):
         lo, hi = slab_with_halo(z0, z1, N)
-        slab = vol_g_slab_device(N, lo, hi, 2, torch.device("cuda", 0))
-        r = SlabMaxProjector((W, W), rank=i, world=B, device=0, max_steps=MAX_STEPS, pinned_outputs=True)
+        slab = vol_g_slab_device(N, lo, hi, 2, torch.device("cuda", local_rank))
+        r = SlabMaxProjector((W, W), rank=i, world=B, device=local_rank, max_steps=MAX_STEPS, pinned_outputs=True)
         r.use_stream(stream.cuda_stream)
         r.set_slab((np.uint16, N, N), N, z0, z1, device_ptr=slab.data_ptr())
         r.sync()
@@ -802,19 +830,22 @@ def run_bricks(args):
         out = np.empty((W, W), np.float32)
         _lib.check(lib.spv_read(last._ctx, _lib.BUF_OUT, _lib.fp(out), out.size), last._ctx)
         digest.update(out.tobytes())
-    print(json.dumps({
+    line = {
         "metric": "MIP frames/s, %d^3 uint16 -> %d^2, single-GPU-brick baseline" % (N, W),
         "value": args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u16->f32", "data": "synthetic",
         "config": {"workload": "Vol-G(%d, uint16, seed 2) generated on device, max_project -> %dx%d, max_steps=200, "
                                "%d z-slabs rendered one after the other on one GPU, max-merged, windowed" % (N, W, W, B)},
-        "gpu_launches": args.steps * (B + 1), "image_sha1_first8": digest.hexdigest()}))
+        "gpu_launches": args.steps * (B + 1), "image_sha1_first8": digest.hexdigest()}
     for r in parts:
         r.close()
+    del parts, raws
+    torch.cuda.empty_cache()
+    return line
 
 
-def run_slab(args, rank, local_rank, world):
+def run_slab(args, rank, local_rank, world, own_pg=True):
     """BASELINE configs[3]: --vol^3 uint16 split into `world` z-slabs, every frame = raw slab render on each GPU,
     all-reduce(MAX) over NCCL, window.  Strong scaling: the total work per frame is fixed."""
     import hashlib
@@ -826,7 +857,7 @@ def run_slab(args, rank, local_rank, world):
     from spimagine_b200.multigpu import SlabMaxProjector, partition_slabs_multi, slab_with_halo
 
     torch.cuda.set_device(local_rank)
-    if world > 1:
+    if world > 1 and own_pg:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     N, W = args.vol, args.img
     K = max(1, args.slabs_per_rank)
@@ -944,6 +975,7 @@ def run_slab(args, rank, local_rank, world):
         issued_total = float(cnt[0])
     else:
         issued_total = float(issued0)
+    line = None
     if rank == 0:
         fps = args.steps / (ms * 1e-3)
         peaks, peak_src = measured_peaks()
@@ -978,10 +1010,12 @@ def run_slab(args, rank, local_rank, world):
                          "algorithmic_bytes_per_frame_all_gpus": alg_bytes},
             "gen_s": t_gen, "upload_s": t_upload,
         }
-        print(json.dumps(line))
     rend.close()
-    if world > 1:
+    del rend, raw
+    torch.cuda.empty_cache()
+    if world > 1 and own_pg:
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 def main():
@@ -1005,12 +1039,130 @@ def main():
     if args.workload == "slab" and args.bricks > 0:
         if world != 1:
             raise SystemExit("--bricks is the single-GPU baseline: run it with --gpus 1")
-        run_bricks(args)
+        print(json.dumps(run_bricks(args)))
         return
     if args.workload == "slab":
-        run_slab(args, rank, local_rank, world)
+        line = run_slab(args, rank, local_rank, world)
+        if rank == 0:
+            print(json.dumps(line))
         return
 
+    line = run_sweep(args, rank, local_rank, world)
+    if rank == 0:
+        print(json.dumps(line))
+
+
+C4_BASELINE_TMP = "/tmp/spv_c4_baseline_%d_%d.json"
+
+
+def c4_record(args, rank, local_rank, world):
+    """BASELINE configs[3] under the same clock as the headline: a --c4-vol^3 uint16 volume -> --c4-img^2, sort-last.
+      --gpus 1 : the two single-GPU denominators -- the volume as ONE resident array rendered by one launch
+                 ("monolithic"), and cut into 8 z-slabs rendered one after the other and max-merged (the
+                 single-GPU-brick baseline north_star names).  Written to /tmp as well, for a later N > 1 run on this box.
+      --gpus N : z-slabs over the ranks, 4 per rank in serpentine order, partials pushed into the band owners' memory
+                 over NVLink inside the render kernel (peer composite), and the same with an NCCL all-reduce(MAX);
+                 speed-up against the brick baseline of this box (/tmp) or else of profiles/r02_c4_baseline_n1.json.
+    The process group of the sweep is reused."""
+    import copy
+    a = copy.copy(args)
+    a.vol, a.img = args.c4_vol, args.c4_img
+    a.steps, a.warmup = max(4, args.c4_steps), max(3, min(args.warmup, 5))
+    keep = ("value", "ms_per_step", "steps", "warmup", "image_sha1_first8", "gsamples_per_s", "hit_rays_per_frame",
+            "issued_samples_per_frame_all_ranks", "gpu_launches", "gen_s", "upload_s")
+
+    def brief(line):
+        d = dict((k, line[k]) for k in keep if k in line)
+        d["workload"] = line["config"]["workload"]
+        if "e2e" in line:
+            d["e2e"] = {"value": line["e2e"]["value"], "d2h_bytes_per_step": line["e2e"]["d2h_bytes_per_step"]}
+        if "roofline" in line:
+            d["roofline"] = line["roofline"]
+        return d
+
+    rec = {"metric": "MIP frames/s, %d^3 uint16 -> %d^2, sort-last (BASELINE configs[3])" % (a.vol, a.img),
+           "n_gpus": world, "scaling": "strong", "unit": "frames/s"}
+    tmp = C4_BASELINE_TMP % (a.vol, a.img)
+    if world == 1:
+        a.composite, a.slabs_per_rank, a.bricks = "nccl", 1, 0
+        mono = run_slab(a, 0, local_rank, 1, own_pg=False)
+        a.bricks = 8
+        bricks = run_bricks(a, local_rank)
+        rec["monolithic"] = brief(mono)
+        rec["single_gpu_brick"] = brief(bricks)
+        rec["value"] = mono["value"]
+        rec["ms_per_step"] = mono["ms_per_step"]
+        rec["same_image"] = mono["image_sha1_first8"] == bricks["image_sha1_first8"]
+        try:
+            with open(tmp, "w") as f:
+                json.dump({"monolithic_ms": mono["ms_per_step"], "single_gpu_brick_ms": bricks["ms_per_step"],
+                           "image_sha1_first8": bricks["image_sha1_first8"], "source_sha1": source_sha1()}, f)
+        except OSError:
+            pass
+        return rec
+    a.bricks = 0
+    a.composite, a.slabs_per_rank = "peer", 4
+    peer = run_slab(a, rank, local_rank, world, own_pg=False)
+    a.composite = "nccl"
+    nccl = run_slab(a, rank, local_rank, world, own_pg=False)
+    if rank != 0:
+        return None
+    rec["peer_composite"] = brief(peer)
+    rec["nccl_composite"] = brief(nccl)
+    rec["value"] = peer["value"]
+    rec["ms_per_step"] = peer["ms_per_step"]
+    rec["image_sha1_first8"] = peer["image_sha1_first8"]
+    rec["same_image_peer_nccl"] = peer["image_sha1_first8"] == nccl["image_sha1_first8"]
+    W = a.img
+    # per rank and frame: partials of the bands it does not own go to their owners; its own finished band goes to everyone
+    rec["nvlink_bytes_per_frame_per_rank"] = {"partials_pushed": W * W * 4 * (world - 1) // world,
+                                              "finished_band_stored_to_peers": W * W * 4 * (world - 1) // world}
+    base, src = None, None
+    if os.path.exists(tmp):
+        with open(tmp) as f:
+            base, src = json.load(f), "this box, the --gpus 1 run before this one (%s)" % tmp
+    else:
+        path = os.path.join(ROOT, "profiles", "r02_c4_baseline_n1.json")
+        if os.path.exists(path) and (a.vol, a.img) == (2048, 2048):
+            with open(path) as f:
+                base, src = json.load(f), "profiles/r02_c4_baseline_n1.json (another B200 of this pool, `bench.py --gpus 1`)"
+    if base is not None:
+        rec["baseline"] = dict(base, source=src)
+        rec["speedup_vs_single_gpu_brick"] = base["single_gpu_brick_ms"] / peer["ms_per_step"]
+        rec["speedup_vs_monolithic"] = base["monolithic_ms"] / peer["ms_per_step"]
+        rec["same_image_as_baseline"] = base.get("image_sha1_first8") == peer["image_sha1_first8"]
+    return rec
+
+
+def source_sha1():
+    """SHA-1 over the sources of the max-projection kernel: ties a committed ncu traffic figure to the code it was
+    measured on (profiles/r02_mip_traffic.json is written by scripts/ncu_traffic.py)."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in ("spv_mip.cu", "spv_common.cuh", "spv_kernels.h"):
+        with open(os.path.join(ROOT, "spimagine_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def ncu_traffic(workload_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu capture of
+    this workload, or (None, why) when there is none for the current kernel sources."""
+    path = os.path.join(ROOT, "profiles", "r02_mip_traffic.json")
+    if not os.path.exists(path):
+        return None, "no ncu capture committed for this round (scripts/ncu_traffic.py writes %s)" % os.path.basename(path)
+    with open(path) as f:
+        rec = json.load(f).get(workload_key)
+    if rec is None:
+        return None, "no ncu capture of this workload in profiles/r02_mip_traffic.json"
+    if rec.get("source_sha1") != source_sha1():
+        return None, "the committed ncu capture (profiles/r02_mip_traffic.json) predates the current kernel sources"
+    return int(rec["dram_bytes_read"] + rec["dram_bytes_write"]), \
+        "profiles/r02_mip_traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over %d launches of %s" % (
+            rec.get("launches", 0), rec.get("kernel", "?"))
+
+
+def run_sweep(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     import scenes
@@ -1024,7 +1176,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     vol = scenes.vol_g(args.vol, np.uint16, seed=0)
-    cams = sweep_cameras()
+    K = args.steps
+    thetas = sweep_thetas(K, rank, world)
+    cams = [scenes.gui_camera(th, 4.0) for th in thetas]
     W = H = args.img
     rend = VolumeRenderer((W, H), device=local_rank, max_steps=MAX_STEPS, pinned_outputs=True)
     # a dedicated (non-default) stream shared by torch and the renderer, so torch's events bracket the kernels
@@ -1038,8 +1192,10 @@ def main():
     rend.set_max_val(PEAK_VALUE)
     rend.set_skipping(args.skip)
     rend.set_projection(cams[0][1])
+    if args.mip_path is not None:
+        rend.set_mip_path(args.mip_path)  # raises where the library has no such path
 
-    # camera matrices of the whole sweep as the kernels take them (volumerender.py:310-316)
+    # camera matrices of this rank's frames as the kernels take them (volumerender.py:310-316)
     mats = []
     for M, P in cams:
         rend.set_modelView(M)
@@ -1047,20 +1203,17 @@ def main():
     lib, ctx = rend._lib, rend._ctx
     params = _lib.MipParams(rend._box(), 0., PEAK_VALUE, 1., 0., 1, 0, MAX_STEPS, 0)
 
-    def frame_of(i):
-        return (i * world + rank) % SWEEP
-
     def device_step(i):
-        invP, invM = mats[frame_of(i)]
+        invP, invM = mats[i % K]
         lib.spv_set_matrices(ctx, _lib.fp(invP), _lib.fp(invM))
         rc = lib.spv_render_mip(ctx, C.byref(params))
         if rc:
             _lib.check(rc, ctx)
 
-    # algorithmic samples: hit rays x 208, counted on the device in an untimed pass
+    # algorithmic samples: hit rays x 208, counted on the device in an untimed pass over exactly the timed frames
     rend.enable_stats(True)
     hits, issued = [], []
-    for i in range(min(args.steps, SWEEP)):
+    for i in range(K):
         device_step(i)
         h, s = rend.last_stats()
         hits.append(h)
@@ -1085,17 +1238,32 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(K):
         device_step(i)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = rend.launch_count() - launches0 - args.warmup
-    assert launches == args.steps, (launches, args.steps)
+    kernels_per_frame = launches / float(K)
 
-    # ---- end to end through the public API ----
+    # ---- end to end through the public API: render_sequence() over the same frames.  Every frame's output and alpha
+    # reach pinned host memory inside the timed region; frame i+1 renders while frame i is in flight
+    for r in rend.render_sequence(cams[i % K][0] for i in range(min(args.warmup, 5))):
+        pass
+    barrier()
+    checksum_seq = 0.0
+    b0 = rend.d2h_bytes()
+    t0 = time.perf_counter()
+    for r in rend.render_sequence(cams[i][0] for i in range(K)):
+        checksum_seq += float(r.output[H // 2, W // 2])
+    torch.cuda.synchronize()
+    t_seq = time.perf_counter() - t0
+    d2h_seq = (rend.d2h_bytes() - b0) / float(K)
+    barrier()
+
+    # ---- end to end, one blocking call per frame (the reference's frame loop as it stands) ----
     def api_step(i):
-        rend.set_modelView(cams[frame_of(i)][0])
+        rend.set_modelView(cams[i % K][0])
         rend.render()
         return rend.output
 
@@ -1103,25 +1271,14 @@ def main():
         api_step(i)
     barrier()
     checksum = 0.0
+    b0 = rend.d2h_bytes()
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(K):
         out = api_step(i)
         checksum += float(out[H // 2, W // 2])
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
-    barrier()
-
-    # ---- end to end, pipelined: render_sequence() over the same frames (frame i+1 renders while frame i is
-    # copied to pinned host memory); every frame's output and alpha still reach the host inside the timed region
-    for r in rend.render_sequence(cams[frame_of(i)][0] for i in range(min(args.warmup, 5))):
-        pass
-    barrier()
-    checksum_seq = 0.0
-    t0 = time.perf_counter()
-    for r in rend.render_sequence(cams[frame_of(i)][0] for i in range(args.steps)):
-        checksum_seq += float(r.output[H // 2, W // 2])
-    torch.cuda.synchronize()
-    t_seq = time.perf_counter() - t0
+    d2h_sync = (rend.d2h_bytes() - b0) / float(K)
     barrier()
 
     clocks = sampler.stop() if rank == 0 else None
@@ -1130,65 +1287,73 @@ def main():
         t = torch.tensor([ms, t_e2e * 1e3, t_seq * 1e3], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, t_e2e, t_seq = float(t[0]), float(t[1]) / 1e3, float(t[2]) / 1e3
-        cnt = torch.tensor([mean_hits, mean_issued], device="cuda", dtype=torch.float64)
+        cnt = torch.tensor([mean_hits, mean_issued, d2h_seq, d2h_sync], device="cuda", dtype=torch.float64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        mean_hits, mean_issued = float(cnt[0]) / world, float(cnt[1]) / world
+        mean_hits, mean_issued, d2h_seq, d2h_sync = (float(x) / world for x in cnt)
 
+    line = None
     if rank == 0:
-        total_frames = args.steps * world
+        total_frames = K * world
         fps = total_frames / (ms * 1e-3)
-        fps_e2e = total_frames / t_e2e
         peaks, peak_src = measured_peaks()
-        launch_s = ms * 1e-3 / args.steps
+        launch_s = ms * 1e-3 / K
         alg_bytes = vol.nbytes + 2 * W * H * 4
         achieved = alg_bytes / launch_s / 1e9
         tex_peak = rend.texrate_probe(4000)
         # the same probe with the benchmark camera's footprint: neighbouring rays one pixel apart at the volume's
         # centre (2 d tan(fovy/2) / W box units, d = 4), samples L/192 apart along the view direction (mean in-box
-        # path L = 1.23 box units), at 12 angles of the sweep; every fetch hits L1
+        # path L = 1.23 box units), at (up to 24 of) the angles that were timed, each weighted by the
+        # samples its frame issues; every fetch hits L1
         tpu = args.vol / 2.                       # texels per box unit
         pitch = 2. * 4. * np.tan(np.radians(30.)) / W * tpu
         step = 1.23 / (MAX_STEPS // 16 * 16) * tpu
+        pick = sorted(set(int(round(x)) for x in np.linspace(0, K - 1, min(K, 24))))
         foot = []
-        for f in range(0, 360, 30):
-            th = 2 * np.pi * f / 360. + 1e-3
+        for j in pick:
+            th = thetas[j] + 1e-3
             c, s_ = np.cos(th), np.sin(th)
             foot.append(rend.texrate_probe(2000, footprint=[[pitch * c, 0., -pitch * s_], [0., pitch, 0.],
                                                             [-step * s_, 0., -step * c]]))
-        tex_foot = len(foot) / sum(1. / r for r in foot)   # equal samples per angle: harmonic mean
+        wts = np.array([issued[j] for j in pick], float)
+        tex_foot = wts.sum() / sum(w / r for w, r in zip(wts, foot))  # time-weighted: samples / sum(samples / rate)
+        traffic, traffic_src = ncu_traffic("sweep_%d_%d" % (args.vol, W))
+        kernel_name = rend.mip_kernel_name() if hasattr(rend, "mip_kernel_name") else "spv::mip_fast_kernel<u16, linear>"
         line = {
-            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
+            "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u16->f32", "data": "synthetic",
-            "config": {
-                "workload": "Vol-G(%d, uint16, seed 0) max_project -> %dx%d, max_steps=200 (208 samples per hit "
-                            "ray), frames of a 360-degree sweep%s" % (
-                                args.vol, W, H, "" if world == 1 else ", frame f on rank f mod %d" % world),
-                "camera": "perspective(60,1,.1,10), translate(0,0,-4) . rotation(theta + 1e-3, y)",
+            "config": sweep_config(args),
+            "notes": {
                 "l2": "the %d MB volume exceeds the 126 MB L2 and the view changes every step" % (vol.nbytes >> 20),
                 "skipping": bool(args.skip), "parallelism": "frames sharded over %d GPU(s), volume replicated" % world,
-            },
+                "angles_deg_rank0": [round(math.degrees(t), 3) for t in thetas[:4]] + ["..."] if K > 4 else
+                                    [round(math.degrees(t), 3) for t in thetas]},
             "gsamples_per_s": fps * mean_hits * SAMPLES_PER_RAY / 1e9,
             "hit_rays_per_frame": mean_hits,
             "issued_samples_per_frame": mean_issued,
-            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 2 * W * H * 4,
-                    "note": "the drop-in call of the reference's frame loop, synchronous per frame: "
-                            "VolumeRenderer.set_modelView + render() = host 4x4 inversion, one launch whose tile rows "
-                            "are dealt from the image edges inwards, output + alpha copied in 12 bands into pinned host "
-                            "memory by two copy streams that wait on per-band completion counters "
-                            "(cuStreamWaitValue32), wait; the volume stays resident as in the reference's frame loop",
-                    "checksum": checksum},
-            "e2e_pipelined": {"value": total_frames / t_seq, "unit": "frames/s", "h2d_bytes_per_step": 128,
-                              "d2h_bytes_per_step": 2 * W * H * 4,
-                              "note": "VolumeRenderer.render_sequence(modelViews): same frames, every output + alpha "
-                                      "reaches pinned host memory, but frame i+1 renders while frame i is in flight",
-                              "checksum": checksum_seq},
+            "e2e": {"value": total_frames / t_seq, "unit": "frames/s", "h2d_bytes_per_step": 128,
+                    "d2h_bytes_per_step": int(round(d2h_seq)),
+                    "d2h_gbytes_per_s_per_rank": d2h_seq * K / t_seq / 1e9,
+                    "note": "VolumeRenderer.render_sequence(modelViews): per frame the host inverts the 4x4 modelView, "
+                            "launches, and output + alpha are copied to pinned host memory (only the rows the projected "
+                            "box can touch travel: %.0f%% of 2*W*H*4 bytes; the others already hold the miss values); "
+                            "frame i+1 renders while frame i is in flight; a pixel of every frame is read on the host" % (
+                                100. * d2h_seq / (2 * W * H * 4)),
+                    "checksum": checksum_seq},
+            "e2e_synchronous": {"value": total_frames / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128,
+                                "d2h_bytes_per_step": int(round(d2h_sync)),
+                                "note": "the drop-in call of the reference's frame loop, blocking per frame: "
+                                        "VolumeRenderer.set_modelView + render() = host 4x4 inversion, one launch, output "
+                                        "+ alpha copied in 12 bands into pinned host memory by two copy streams that wait "
+                                        "on per-band completion counters (cuStreamWaitValue32), wait",
+                                "checksum": checksum},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": launch_s * 1e6,
-                         "kernel": "spv::mip_fast_kernel<u16, linear>"},
+                         "kernels_per_frame": kernels_per_frame, "kernel": kernel_name},
             "roofline_tex": {"bound": "texture samples", "issued_gsamples_per_s": mean_issued / launch_s / 1e9,
                              "algorithmic_gsamples_per_s": mean_hits * SAMPLES_PER_RAY / launch_s / 1e9,
                              "peak_gsamples_per_s": tex_peak / 1e9,
@@ -1199,8 +1364,9 @@ def main():
                              "frac_issued_at_render_footprint": mean_issued / launch_s / tex_foot,
                              "render_footprint": {"ray_spacing_texels": pitch, "sample_spacing_texels": step,
                                                   "gsamples_per_s_by_angle_deg": dict(
-                                                      (str(f), r / 1e9) for f, r in zip(range(0, 360, 30), foot)),
-                                                  "note": "spv_texrate_probe_footprint: the same independent fetches "
+                                                      ("%.1f" % math.degrees(thetas[j]), r / 1e9) for j, r in zip(pick, foot)),
+                                                  "note": "spv_texrate_probe_footprint at the timed angles (builder-defined "
+                                                          "denominator, not SURVEY 8d's): the same independent fetches "
                                                           "laid out like this camera's rays (a warp's 8x4 tile one "
                                                           "pixel apart, 16 samples in flight along the view "
                                                           "direction), all warps on one L1-resident region: what the "
@@ -1208,14 +1374,21 @@ def main():
             "upload_s": t_upload,
         }
         if world == 1 and not args.no_cpu_baseline:
-            res = cpu_reference(vol, cams, args.img, 24, 1, 20.0, False)
+            sub = cams[::max(1, K // 24)][:24]
+            res = cpu_reference(vol, sub, args.img, len(sub), 1, 20.0)
             line["cpu_baseline"] = {"value": res["fps"], "unit": "frames/s", "cores": res["cores"],
                                     "kind": res["kind"], "sample": res["sample"],
                                     "gsamples_per_s": res["gsamples"]}
-        print(json.dumps(line))
     rend.close()
+    del rend
+    torch.cuda.empty_cache()
+    if not args.no_c4:
+        rec = c4_record(args, rank, local_rank, world)
+        if rank == 0:
+            line["c4"] = rec
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":

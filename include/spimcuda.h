@@ -303,6 +303,10 @@ SPV_API int spv_texrate_probe(spv_ctx *ctx, int iters, double *samples_per_s);
  * the rate the texture unit can deliver for the ray and sample spacing of a given camera */
 SPV_API int spv_texrate_probe_footprint(spv_ctx *ctx, int iters, const float *vec9, double *samples_per_s);
 SPV_API int spv_launch_count(spv_ctx *ctx, unsigned long long *n);  /* kernels launched by this context so far */
+/* Result bytes this context has enqueued for device -> host copies so far (what `.get()` of the result buffers moves in
+ * the reference, volumerender.py:388-390, 499-506): rows that cannot hold a hit are not copied, so a frame
+ * moves fewer than 2 * W * H * 4 bytes. */
+SPV_API int spv_d2h_bytes(spv_ctx *ctx, unsigned long long *n);
 
 #ifdef __cplusplus
 }

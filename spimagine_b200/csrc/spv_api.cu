@@ -100,6 +100,7 @@ struct spv_ctx {
   unsigned long long *d_stats = nullptr;
   unsigned long long h_stats[40] = {0};  // hit rays, samples fetched, longest warp / sum over warps (cycles; iso search)
   unsigned long long launches = 0;
+  unsigned long long d2h_bytes = 0;  // result bytes enqueued for device -> host copies so far (spv_d2h_bytes)
   std::string err;
 
   size_t n() const { return (size_t)width * height; }
@@ -1002,6 +1003,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
       if (wr != CUDA_SUCCESS) return fail(ctx, (int)wr, "cuStreamWaitValue32 failed");
       CU(cudaMemcpy2DAsync(ctx->hpin_s[s] + off, n * sizeof(float), ctx->dbuf_s[s] + off, n * sizeof(float),
                            cnt * sizeof(float), 2, cudaMemcpyDeviceToHost, cs));
+      ctx->d2h_bytes += 2 * cnt * sizeof(float);
     }
     ctx->last_method = 0;
     rc = end_render(ctx);
@@ -1042,6 +1044,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
       // the band's rows of the value plane and of the alpha plane in ONE 2-D copy (2 "rows" one plane apart)
       CU(cudaMemcpy2DAsync(ctx->hpin_s[s] + off, n * sizeof(float), ctx->dbuf_s[s] + off, n * sizeof(float),
                            cnt * sizeof(float), 2, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      ctx->d2h_bytes += 2 * cnt * sizeof(float);
     }
   }
   ctx->last_method = 0;
@@ -1286,6 +1289,7 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
     CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
     CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
     CU(cudaMemcpyAsync(ctx->hpin_s[s] + n, ctx->dbuf_s[s] + n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    ctx->d2h_bytes += n * sizeof(float);
   }
   if (post) {
     // volumerender.py:470-497
@@ -1307,6 +1311,7 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
     CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
     CU(cudaMemcpyAsync(ctx->hpin_s[s], ctx->dbuf_s[s], (post ? 1 : 2) * n * sizeof(float), cudaMemcpyDeviceToHost,
                        ctx->copy_stream));
+    ctx->d2h_bytes += (post ? 1 : 2) * n * sizeof(float);
     CU(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));
     ctx->copy_pending[s] = true;
   }
@@ -1524,6 +1529,7 @@ SPV_API int spv_read(spv_ctx *ctx, int which, float *host_dst, size_t n) {
   if (!src || !host_dst) return fail(ctx, SPV_EINVAL, "spv_read: bad buffer id or null destination");
   if (n != count) return fail(ctx, SPV_EINVAL, "spv_read: element count does not match the buffer");
   CU(cudaMemcpyAsync(host_dst, src, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->d2h_bytes += n * sizeof(float);
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -1535,6 +1541,7 @@ SPV_API int spv_read_many(spv_ctx *ctx, float *out, float *alpha, float *depth, 
   const size_t planes = (depth || normals || occ) ? 7 : 2;
   staging_dirty(ctx, ctx->slot);
   CU(cudaMemcpyAsync(ctx->hpin, ctx->dbuf, planes * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->d2h_bytes += planes * n * sizeof(float);
   CU(cudaStreamSynchronize(ctx->stream));
   if (out) memcpy(out, ctx->hpin, n * sizeof(float));
   if (alpha) memcpy(alpha, ctx->hpin + n, n * sizeof(float));
@@ -1550,6 +1557,7 @@ SPV_API int spv_read_pinned(spv_ctx *ctx, int planes, float **host) {
   if (ctx->copy_pending[ctx->slot]) CU(cudaEventSynchronize(ctx->ev_copied[ctx->slot]));  // same staging memory
   staging_dirty(ctx, ctx->slot);
   CU(cudaMemcpyAsync(ctx->hpin, ctx->dbuf, (size_t)planes * ctx->n() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->d2h_bytes += (size_t)planes * ctx->n() * sizeof(float);
   CU(cudaStreamSynchronize(ctx->stream));
   *host = ctx->hpin;
   return 0;
@@ -1579,6 +1587,7 @@ SPV_API int spv_read_pinned_async(spv_ctx *ctx, int planes) {
   CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
   CU(cudaMemcpyAsync(ctx->hpin_s[s], ctx->dbuf_s[s], (size_t)planes * ctx->n() * sizeof(float), cudaMemcpyDeviceToHost,
                      ctx->copy_stream));
+  ctx->d2h_bytes += (size_t)planes * ctx->n() * sizeof(float);
   CU(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));
   ctx->copy_pending[s] = true;
   return 0;
@@ -1621,6 +1630,7 @@ SPV_API int spv_read_rgba8(spv_ctx *ctx, int mode_black, unsigned char *host_dst
   CU(launch_display(ctx->out(), ctx->alpha(), ctx->d_lut, ctx->n_lut, mode_black != 0, ctx->d_rgba, n, ctx->stream));
   ctx->launches += 1;
   CU(cudaMemcpyAsync(ctx->h_rgba, ctx->d_rgba, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->d2h_bytes += 4 * n;
   CU(cudaStreamSynchronize(ctx->stream));
   memcpy(host_dst, ctx->h_rgba, 4 * n);
   return 0;
@@ -1711,6 +1721,12 @@ SPV_API int spv_texrate_probe_footprint(spv_ctx *ctx, int iters, const float *ve
 SPV_API int spv_launch_count(spv_ctx *ctx, unsigned long long *n) {
   if (!ctx || !n) return SPV_EINVAL;
   *n = ctx->launches;
+  return 0;
+}
+
+SPV_API int spv_d2h_bytes(spv_ctx *ctx, unsigned long long *n) {
+  if (!ctx || !n) return SPV_EINVAL;
+  *n = ctx->d2h_bytes;
   return 0;
 }
 

@@ -655,3 +655,9 @@ class VolumeRenderer(object):
         n = C.c_ulonglong()
         self._check(self._lib.spv_launch_count(self._ctx, C.byref(n)))
         return int(n.value)
+
+    def d2h_bytes(self):
+        """result bytes copied device -> host by this renderer so far (rows that cannot hold a hit are not copied)"""
+        n = C.c_ulonglong()
+        self._check(self._lib.spv_d2h_bytes(self._ctx, C.byref(n)))
+        return int(n.value)
