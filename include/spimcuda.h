@@ -290,6 +290,18 @@ SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
  * misses, and the pinned staging rows already hold the miss values (out 0, alpha 0 / -1), which the library keeps
  * track of per output slot (1, default; 0 = copy every row).  The staging memory must be treated as read-only. */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
+/* Which kernel family renders plain (alpha_pow == 0, num_parts == 1) max projections of uint16 volumes
+ * (max_project_short, volume_kernel.cl:270-345):
+ *   SPV_MIP_PATH_TMU   one hardware-filtered texture fetch per sample (default)
+ *   SPV_MIP_PATH_SMEM  ray-segment slabs of a linear uint16 copy of the volume staged in shared memory by TMA box loads,
+ *                      fp32 software trilinear sampling with exact weights (spv_mip_smem.cu); samples outside the staged
+ *                      boxes, other element types, slab contexts, multi-pass and raw renders use the TMU path.  Costs three
+ *                      permuted linear copies of the volume (6 bytes per voxel), built on first use after an upload.
+ * Both are within north_star's 1e-3 of the OpenCL sampler; they differ from each other by the texture unit's 8-bit weight
+ * quantisation.  spv_mip_path_used reports what the last max projection ran on. */
+enum { SPV_MIP_PATH_TMU = 0, SPV_MIP_PATH_SMEM = 1 };
+SPV_API int spv_set_mip_path(spv_ctx *ctx, int path);
+SPV_API int spv_mip_path_used(spv_ctx *ctx, int *path);
 SPV_API const char *spv_last_error(spv_ctx *ctx);                   /* ctx may be NULL: last create error */
 SPV_API int spv_version(void);
 /* out[i] = the current sampler's value at normalised position pos[3i..3i+2] (what read_imagef(volume, sampler,

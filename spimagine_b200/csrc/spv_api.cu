@@ -100,7 +100,15 @@ struct spv_ctx {
   unsigned long long *d_stats = nullptr;
   unsigned long long h_stats[40] = {0};  // hit rays, samples fetched, longest warp / sum over warps (cycles; iso search)
   unsigned long long launches = 0;
-  unsigned long long d2h_bytes = 0;  // result bytes enqueued for device -> host copies so far (spv_d2h_bytes)
+  unsigned long long d2h_bytes = 0;
+  // software-sampled max projection (spv_set_mip_path, spv_mip_smem.cu): permuted linear uint16 copies of the resident
+  // volume (slowest axis x, y, z) and the tensor maps the kernel's TMA box loads go through
+  int mip_path = 0, last_mip_path = 0;
+  int smem_tex_of8 = 0;  // tuning knob 10: tiles (of every 8) the software-sampled kernel hands to the texture unit
+  void *d_lin[3] = {nullptr, nullptr, nullptr};
+  bool lin_valid = false;
+  CUtensorMap tmaps[8][3];  // per box geometry (tuning knob 11)
+  int smem_cfg = 0;  // result bytes enqueued for device -> host copies so far (spv_d2h_bytes)
   std::string err;
 
   size_t n() const { return (size_t)width * height; }
@@ -195,6 +203,11 @@ static void free_volume(spv_ctx *c) {
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->d_stage) cudaFree(c->d_stage);
   if (c->d_conv) cudaFree(c->d_conv);
+  for (int d = 0; d < 3; ++d) {
+    if (c->d_lin[d]) cudaFree(c->d_lin[d]);
+    c->d_lin[d] = nullptr;
+  }
+  c->lin_valid = false;
   if (c->h_ring) cudaFreeHost(c->h_ring);
   c->d_stage = nullptr;
   c->d_conv = nullptr;
@@ -448,6 +461,7 @@ static int upload(spv_ctx *ctx, const void *src, bool on_device, bool no_wait = 
   }
   ctx->bricks_valid = false;  // rebuilt by ensure_bricks() when something needs them
   ctx->minmax_valid = false;
+  ctx->lin_valid = false;     // rebuilt by ensure_linear() when the software-sampled path renders
 
   // slices per chunk
   const size_t budget = kind == SRC_DEVICE ? ((size_t)128 << 20) : ((size_t)32 << 20);
@@ -591,6 +605,61 @@ static int ensure_bricks(spv_ctx *ctx) {
   ctx->launches += 4;
   ctx->bricks_valid = true;
   ctx->minmax_valid = false;
+  return 0;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+typedef CUresult (*encode_tiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_t encode_tiled_fn() {
+  static encode_tiled_t fn = nullptr;
+  static bool looked = false;
+  if (!looked) {
+    looked = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (encode_tiled_t)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// can the software-sampled path render this context's volume at all?
+static bool smem_path_possible(const spv_ctx *c) {
+  const int m = c->nx < c->ny ? (c->nx < c->gnz ? c->nx : c->gnz) : (c->ny < c->gnz ? c->ny : c->gnz);
+  return c->dtype == SPV_U16 && !c->slab && m >= 48 && encode_tiled_fn() != nullptr;
+}
+
+// The three permuted linear copies (slowest axis x, y, z; contiguous axis z, x, x) of the resident uint16 volume and
+// their tensor maps.  Built from the array on the render stream on first use after an upload.
+static int ensure_linear(spv_ctx *ctx) {
+  if (ctx->lin_valid) return 0;
+  const Volume V = volume_of(ctx);
+  for (int D = 0; D < 3; ++D) {
+    const int NA = D == 0 ? ctx->gnz : ctx->nx, NB = D == 1 ? ctx->gnz : ctx->ny,
+              ND = D == 0 ? ctx->nx : (D == 1 ? ctx->ny : ctx->gnz);
+    const size_t pitchA = ((size_t)NA + 7) / 8 * 8;  // rows start on 16-byte boundaries (tensor map stride rule)
+    if (!ctx->d_lin[D]) CU(cudaMalloc(&ctx->d_lin[D], pitchA * NB * ND * sizeof(unsigned short)));
+    CU(launch_permute(V, fmt_of(ctx), D, NA, NB, ND, pitchA, ctx->d_lin[D], ctx->stream));
+    ctx->launches += 1;
+    const cuuint64_t dims[3] = {(cuuint64_t)NA, (cuuint64_t)NB, (cuuint64_t)ND};
+    const cuuint64_t strides[2] = {pitchA * 2, pitchA * 2 * (cuuint64_t)NB};
+    const cuuint32_t es[3] = {1, 1, 1};
+    for (int cfg = 0; cfg < mip_smem_configs(); ++cfg) {
+      int box[3];
+      mip_smem_box(cfg, box);
+      const cuuint32_t bx[3] = {(cuuint32_t)box[0], (cuuint32_t)box[1], (cuuint32_t)box[2]};
+      CUresult r = encode_tiled_fn()(&ctx->tmaps[cfg][D], CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, ctx->d_lin[D], dims, strides, bx,
+                                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(ctx, (int)r, "cuTensorMapEncodeTiled failed");
+    }
+  }
+  ctx->lin_valid = true;
   return 0;
 }
 
@@ -759,6 +828,19 @@ SPV_API int spv_set_skipping(spv_ctx *ctx, int on) {
   ctx->skipping = on < 0 ? -1 : (on != 0);
   return 0;
 }
+SPV_API int spv_set_mip_path(spv_ctx *ctx, int path) {
+  if (!ctx) return SPV_EINVAL;
+  if (path != SPV_MIP_PATH_TMU && path != SPV_MIP_PATH_SMEM) return fail(ctx, SPV_EINVAL, "spv_set_mip_path: unknown path");
+  if (path == SPV_MIP_PATH_SMEM && !encode_tiled_fn())
+    return fail(ctx, SPV_EINVAL, "spv_set_mip_path: this driver has no cuTensorMapEncodeTiled");
+  ctx->mip_path = path;
+  return 0;
+}
+SPV_API int spv_mip_path_used(spv_ctx *ctx, int *path) {
+  if (!ctx || !path) return SPV_EINVAL;
+  *path = ctx->last_mip_path;
+  return 0;
+}
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   if (!ctx) return SPV_EINVAL;
   if (knob == 0) ctx->tile_variant = value;
@@ -770,6 +852,8 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   else if (knob == 7) ctx->copy_streams = value > 1 ? 2 : 1;
   else if (knob == 8) ctx->row_mode = value == 1 ? 1 : 0;
   else if (knob == 9) ctx->clip_copies = value != 0;
+  else if (knob == 10) ctx->smem_tex_of8 = value < 0 ? 0 : (value > 8 ? 8 : value);
+  else if (knob == 11) ctx->smem_cfg = value < 0 || value >= mip_smem_configs() ? 0 : value;
   else if (knob == 6) occ_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : value);  // process-wide
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
   return 0;
@@ -929,6 +1013,15 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
   int rc = (fast && ctx->skipping > 0) ? ensure_bricks(ctx) : 0;
   if (rc) return rc;
+  // software-sampled path (spv_set_mip_path): whole-frame launches of plain uint16 max projections
+  const bool smem = ctx->mip_path == SPV_MIP_PATH_SMEM && fast && linear && !raw_only && !push && !(ctx->skipping > 0) &&
+                    p->num_parts == 1 && p->current_part == 0 && !ctx->persistent && smem_path_possible(ctx);
+  ctx->last_mip_path = smem ? SPV_MIP_PATH_SMEM : SPV_MIP_PATH_TMU;
+  if (smem) {
+    rc = ensure_linear(ctx);
+    if (rc) return rc;
+    bands = 1;
+  }
   rc = begin_render(ctx);
   if (rc) return rc;
   const int s = ctx->slot;
@@ -1034,7 +1127,11 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     const int y1 = y0 + rows < H ? y0 + rows : H;
     a.y_begin = y0;
     a.y_end = y1;
-    CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, ctx->skipping > 0, ctx->slab, ctx->stats_on != 0, ctx->stream));
+    if (smem) {
+      a.tile_counter = ctx->d_tile_counter;
+      CU(launch_mip_smem(a, fmt_of(ctx), ctx->smem_cfg, ctx->tmaps[ctx->smem_cfg], ctx->smem_tex_of8, ctx->stream));
+    } else
+      CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, ctx->skipping > 0, ctx->slab, ctx->stats_on != 0, ctx->stream));
     ctx->launches += 1;
     const int c0 = y0 > clip_a ? y0 : clip_a, c1 = y1 < clip_b ? y1 : clip_b;
     if (to_host && !direct && c0 < c1) {

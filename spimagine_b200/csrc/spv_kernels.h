@@ -69,6 +69,16 @@ cudaError_t launch_mip(const MipArgs &a, int dtype, bool linear, bool fast, bool
 cudaError_t launch_mip_finish(const float *raw, float *out, int n, float minVal, float maxVal, float gamma,
                               cudaStream_t st);
 
+// software-sampled max projection (spv_mip_smem.cu): TMA-staged shared-memory slabs of permuted linear uint16 copies
+int mip_smem_configs();               // box / ring geometries compiled in (tuning knob 11)
+void mip_smem_box(int cfg, int *abp);  // box extents (contiguous axis, second axis, planes) the tensor maps of cfg need
+// tex_of8: of every 8 tiles (fixed pattern) this many are rendered through the texture unit instead (hybrid mode)
+cudaError_t launch_mip_smem(const MipArgs &a, int fmt, int cfg, const void *maps /* CUtensorMap[3] of cfg */, int tex_of8,
+                            cudaStream_t st);
+// dst[(d * NB + b) * pitchA + a] = the volume with slowest axis D (x, y or z) and contiguous axis z, x, x
+cudaError_t launch_permute(const Volume &V, int fmt, int D, int NA, int NB, int ND, size_t pitchA, void *dst,
+                           cudaStream_t st);
+
 // peer composite (spv_comp.cu)
 struct CompFinishArgs {
   const float *part;          // my band's staging of this parity: [world][band_pixels]

@@ -170,6 +170,24 @@ class VolumeRenderer(object):
         self._check(self._lib.spv_set_layout(self._ctx, codes[layout]))
         self._need_alloc = True
 
+    def set_mip_path(self, path="tmu"):
+        """Kernel family of plain uint16 max projections: "tmu" (one hardware-filtered fetch per sample, default) or
+        "smem" (TMA-staged shared-memory slabs, software trilinear sampling with fp32 weights; spv_set_mip_path)."""
+        codes = {"tmu": 0, "smem": 1}
+        if path not in codes:
+            raise KeyError("mip path = '%s' not defined, valid: %s" % (path, list(codes.keys())))
+        self._check(self._lib.spv_set_mip_path(self._ctx, codes[path]))
+        self.mip_path = path
+
+    def mip_path_used(self):
+        """the kernel family the last max projection ran on: 'tmu' or 'smem'"""
+        v = C.c_int()
+        self._check(self._lib.spv_mip_path_used(self._ctx, C.byref(v)))
+        return ("tmu", "smem")[v.value]
+
+    def mip_kernel_name(self):
+        return "spv::mip_smem_kernel<u16>" if self.mip_path_used() == "smem" else "spv::mip_fast_kernel<u16, linear>"
+
     def set_skipping(self, on=True):
         """Empty-space skipping on the min/max brick grids: True / False, or None for the default (on for
         iso surfaces, off for max projection).  Never changes the image."""

@@ -256,3 +256,91 @@ def test_sort_last_iso_surface_against_oracle(oracle_mod, world):
     finally:
         for s in rs:
             s.close()
+
+
+# ----------------------------------------------------------------------------- software-sampled max projection
+@pytest.mark.parametrize("shape,size", [((96, 112, 128), (200, 168)), ((256, 256, 256), (512, 512))])
+def test_smem_path_against_oracle_and_texture_unit(oracle_mod, shape, size):
+    """VolumeRenderer.set_mip_path("smem") -- TMA-staged shared-memory slabs, software trilinear sampling with fp32 weights
+    (spv_mip_smem.cu) -- against the oracle (1e-3 of the range, north_star) and against the texture-unit kernel (the
+    two differ by the unit's 8-bit weight quantisation only), for views along every axis, oblique ones, a reduced box
+    (samples beyond tfar are real data then), gamma and a window; every geometry the library compiles; the hybrid mode
+    is deterministic."""
+    data = scenes.vol_g(0, np.uint16, seed=4, shape=shape)
+    g = _renderer(size, max_steps=200)
+    g.set_data(data)
+    o = oracle_mod.OracleRenderer(size, kind="port")
+    o.set_data(data)
+    cams = [scenes.gui_camera(th, 3.4) for th in (0.0, 0.6, 1.57, 2.4, 3.9)]
+    from spimagine_b200.utils.transform_matrices import mat4_rotation, mat4_translate
+    cams.append((np.dot(mat4_translate(0, 0, -3.6), mat4_rotation(1.2, 1, 0.2, 0.1)), cams[0][1]))  # looks along y
+    try:
+        for i, (M, P) in enumerate(cams):
+            box = [-1, 1, -1, 1, -1, 1] if i != 2 else [-.6, .7, -1, .8, -.5, 1]
+            gamma, lo = (1., 0.) if i != 3 else (.7, 2000.)
+            for r in (g, o):
+                r.set_modelView(M)
+                r.set_projection(P)
+                r.set_box_boundaries(box)
+                r.set_gamma(gamma)
+                r.set_min_val(lo)
+                r.set_max_val(60000.)
+            o.render()
+            g.set_mip_path("tmu")
+            g.render()
+            tmu = g.output.copy()
+            g.set_mip_path("smem")
+            for cfg in range(5):
+                g._check(g._lib.spv_set_tuning(g._ctx, 11, cfg))
+                g.render()
+                assert g.mip_path_used() == "smem"
+                assert np.array_equal(g.output_alpha, o.output_alpha), (i, cfg)
+                assert np.abs(g.output - o.output).max() < 1e-3, (i, cfg, float(np.abs(g.output - o.output).max()))
+                assert np.abs(g.output - tmu).max() < 1e-3, (i, cfg)
+            g._check(g._lib.spv_set_tuning(g._ctx, 11, 0))
+            # hybrid: a fixed share of the tiles through the texture unit -- the same image every time
+            g._check(g._lib.spv_set_tuning(g._ctx, 10, 3))
+            g.render()
+            first = g.output.copy()
+            g.render()
+            assert np.array_equal(first, g.output)
+            assert np.abs(first - o.output).max() < 1e-3
+            g._check(g._lib.spv_set_tuning(g._ctx, 10, 0))
+        # what the path does not cover falls back to the texture-unit kernels, with the same results as before
+        g.set_alpha_pow(.5)
+        g.render()
+        assert g.mip_path_used() == "tmu"
+        g.set_alpha_pow(0.)
+        g.render(numParts=2, currentPart=1)
+        assert g.mip_path_used() == "tmu"
+    finally:
+        g.close()
+
+
+def test_smem_path_sees_a_new_volume():
+    """update_data invalidates the linear copies the box loads read."""
+    a = scenes.vol_g(0, np.uint16, seed=1, shape=(64, 80, 96))
+    b = np.ascontiguousarray(a[::-1, :, ::-1])
+    g = _renderer((160, 128))
+    M, P = scenes.gui_camera(0.8, 3.2)
+    g.set_projection(P)
+    g.set_modelView(M)
+    g.set_max_val(60000.)
+    g.set_mip_path("smem")
+    try:
+        g.set_data(a)
+        g.render()
+        ia = g.output.copy()
+        g.update_data(b)
+        g.render()
+        ib = g.output.copy()
+        assert not np.array_equal(ia, ib)
+        g.set_mip_path("tmu")
+        g.render()
+        assert np.abs(g.output - ib).max() < 1e-3
+        g.set_mip_path("smem")
+        g.update_data(a)
+        g.render()
+        assert np.array_equal(g.output, ia)
+    finally:
+        g.close()
