@@ -63,6 +63,9 @@ def parse():
     ap.add_argument("--c4-vol", type=int, default=2048)
     ap.add_argument("--c4-img", type=int, default=2048)
     ap.add_argument("--c4-steps", type=int, default=24)
+    ap.add_argument("--alpha-pow", type=float, default=0.,
+                    help="sweep workload with front-to-back attenuation (set_alpha_pow; volume_kernel.cl:300-318): "
+                         "mip_alpha_kernel instead of mip_fast_kernel; no c4 record, no texture-sample roofline")
     ap.add_argument("--mip-path", default=None, choices=[None, "tmu", "smem"],
                     help="max-projection kernel family (default: the library's choice)")
     ap.add_argument("--workload", default="sweep", choices=["sweep", "slab", "timelapse", "iso", "blur", "keyframes"],
@@ -188,7 +191,7 @@ def use_all_host_threads():
     return n
 
 
-def cpu_reference(vol, cams, img, steps, warmup, budget_s):
+def cpu_reference(vol, cams, img, steps, warmup, budget_s, alpha_pow=0.):
     """Time the reference kernels on the host cores.  -> dict(fps, gsamples, kind, cores, sample, ms_per_step)"""
     from oracle import oracle
     use_all_host_threads()
@@ -197,6 +200,7 @@ def cpu_reference(vol, cams, img, steps, warmup, budget_s):
     r.set_data(vol)
     r.set_projection(cams[0][1])
     r.set_max_val(PEAK_VALUE)
+    r.set_alpha_pow(alpha_pow)
     lib = r.lib
     cores = int(lib.so_num_threads())
     # one full frame to size the sample
@@ -1201,7 +1205,8 @@ def run_sweep(args, rank, local_rank, world):
         rend.set_modelView(M)
         mats.append((rend._invP.copy(), rend._invM.copy()))
     lib, ctx = rend._lib, rend._ctx
-    params = _lib.MipParams(rend._box(), 0., PEAK_VALUE, 1., 0., 1, 0, MAX_STEPS, 0)
+    rend.set_alpha_pow(args.alpha_pow)
+    params = _lib.MipParams(rend._box(), 0., PEAK_VALUE, 1., float(args.alpha_pow), 1, 0, MAX_STEPS, 0)
 
     def device_step(i):
         invP, invM = mats[i % K]
@@ -1315,11 +1320,16 @@ def run_sweep(args, rank, local_rank, world):
             foot.append(rend.texrate_probe(2000, footprint=[[pitch * c, 0., -pitch * s_], [0., pitch, 0.],
                                                             [-step * s_, 0., -step * c]]))
         wts = np.array([issued[j] for j in pick], float)
+        if wts.sum() == 0:  # attenuated renders do not count samples
+            wts[:] = 1.
         tex_foot = wts.sum() / sum(w / r for w, r in zip(wts, foot))  # time-weighted: samples / sum(samples / rate)
         traffic, traffic_src = ncu_traffic("sweep_%d_%d" % (args.vol, W))
         kernel_name = rend.mip_kernel_name() if hasattr(rend, "mip_kernel_name") else "spv::mip_fast_kernel<u16, linear>"
+        metric = METRIC if not args.alpha_pow else METRIC + ", alpha_pow = %g" % args.alpha_pow
+        if args.alpha_pow:
+            kernel_name = "spv::mip_alpha_kernel<u16, linear>"
         line = {
-            "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
+            "metric": metric, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u16->f32", "data": "synthetic",
             "config": sweep_config(args),
@@ -1373,16 +1383,22 @@ def run_sweep(args, rank, local_rank, world):
                                                           "texture unit delivers for this footprint without misses"}},
             "upload_s": t_upload,
         }
+        if args.alpha_pow:
+            line["config"] = dict(line["config"], window=line["config"]["window"].replace("alpha_pow 0", "alpha_pow %g" % args.alpha_pow))
+            del line["roofline_tex"]   # executed samples depend on where a ray goes dark: not counted
+            line["gsamples_per_s"] = None
+            line["issued_samples_per_frame"] = None
+            line["hit_rays_per_frame"] = None
         if world == 1 and not args.no_cpu_baseline:
             sub = cams[::max(1, K // 24)][:24]
-            res = cpu_reference(vol, sub, args.img, len(sub), 1, 20.0)
+            res = cpu_reference(vol, sub, args.img, len(sub), 1, 20.0, alpha_pow=args.alpha_pow)
             line["cpu_baseline"] = {"value": res["fps"], "unit": "frames/s", "cores": res["cores"],
                                     "kind": res["kind"], "sample": res["sample"],
                                     "gsamples_per_s": res["gsamples"]}
     rend.close()
     del rend
     torch.cuda.empty_cache()
-    if not args.no_c4:
+    if not args.no_c4 and not args.alpha_pow:
         rec = c4_record(args, rank, local_rank, world)
         if rank == 0:
             line["c4"] = rec

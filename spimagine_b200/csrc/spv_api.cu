@@ -971,8 +971,9 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
   if (bad_float(p->alpha_pow) || bad_float(p->gamma)) return fail(ctx, SPV_EINVAL, "spv_render_mip: NaN parameter");
   const bool raw_only = (p->flags & SPV_MIP_RAW_ONLY) != 0;
   const bool exact = ctx->sampler == SPV_SAMPLER_EXACT;
-  const bool fast = !exact && p->alpha_pow == 0.f;
-  if ((raw_only || ctx->slab) && !fast)
+  const bool fast = !exact;                // texture-unit kernels: mip_fast_kernel, or mip_alpha_kernel when attenuated
+  const bool plain = fast && p->alpha_pow == 0.f;
+  if ((raw_only || ctx->slab) && !plain)
     return fail(ctx, SPV_EINVAL, "spv_render_mip: slab / raw renders need the TMU sampler and alpha_pow == 0");
   if (raw_only && p->num_parts != 1) return fail(ctx, SPV_EINVAL, "spv_render_mip: raw renders need num_parts == 1");
   MipArgs a;
@@ -1011,10 +1012,10 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     a.flags &= ~SPV_MIP_PUSH;
   }
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
-  int rc = (fast && ctx->skipping > 0) ? ensure_bricks(ctx) : 0;
+  int rc = (plain && ctx->skipping > 0) ? ensure_bricks(ctx) : 0;
   if (rc) return rc;
   // software-sampled path (spv_set_mip_path): whole-frame launches of plain uint16 max projections
-  const bool smem = ctx->mip_path == SPV_MIP_PATH_SMEM && fast && linear && !raw_only && !push && !(ctx->skipping > 0) &&
+  const bool smem = ctx->mip_path == SPV_MIP_PATH_SMEM && plain && linear && !raw_only && !push && !(ctx->skipping > 0) &&
                     p->num_parts == 1 && p->current_part == 0 && !ctx->persistent && smem_path_possible(ctx);
   ctx->last_mip_path = smem ? SPV_MIP_PATH_SMEM : SPV_MIP_PATH_TMU;
   if (smem) {
@@ -1027,14 +1028,14 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
   const int s = ctx->slot;
   if (to_host && ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // staging about to be rewritten
   const int H = ctx->height;
-  const bool direct = to_host && ctx->direct_host && fast && p->num_parts == 1 && !raw_only;
+  const bool direct = to_host && ctx->direct_host && plain && p->num_parts == 1 && !raw_only;
   if (direct) {  // zero-copy: the result planes are written over PCIe by the kernel's own 128-bit stores
     staging_dirty(ctx, s);
     a.out = ctx->hpin_s[s];
     a.alpha = ctx->hpin_s[s] + ctx->n();
     bands = 1;
   }
-  if (!fast || bands < 1) bands = 1;
+  if (!plain || bands < 1) bands = 1;
   if (bands > 64) bands = 64;
   int rows = ((H + bands - 1) / bands + 15) / 16 * 16;  // band height: a multiple of every CTA tile height
   if (rows < 16) rows = 16;
@@ -1182,6 +1183,12 @@ SPV_API int spv_comp_init(spv_ctx *ctx, int rank, int world) {
   CU(cudaStreamSynchronize(ctx->stream));
   free_comp(ctx);
   if (ctx->slot != 0) return fail(ctx, SPV_EINVAL, "spv_comp_init: select output slot 0 first");
+  // CUDA loads a kernel at its first launch, and that load can wait for the kernels already running.  The composite's
+  // kernels wait for each other: with several ranks in ONE process a first-time load behind a spinning comp_sync would
+  // block the host thread that still has to enqueue the kernels the spin waits for.  Load them all now.
+  CU(preload_mip_kernels());
+  CU(preload_comp_kernels());
+  CU(preload_iso_kernels());
   const int rows = ((ctx->height + world - 1) / world + 3) / 4 * 4;
   const size_t band = (size_t)rows * ctx->width;
   CU(cudaMalloc(&ctx->comp_part, 6 * (size_t)world * band * sizeof(float)));

@@ -112,4 +112,12 @@ cudaError_t launch_comp_finish(const CompFinishArgs &a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+cudaError_t preload_comp_kernels() {
+  cudaFuncAttributes fa;
+  cudaError_t e;
+  if ((e = cudaFuncGetAttributes(&fa, comp_sync_kernel)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&fa, comp_finish_kernel)) != cudaSuccess) return e;
+  return cudaFuncGetAttributes(&fa, k_reduce_kernel);
+}
+
 }  // namespace spv

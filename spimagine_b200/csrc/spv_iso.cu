@@ -1093,4 +1093,41 @@ cudaError_t launch_shading(float *out, int width, int height, const Camera &cam,
   return cudaGetLastError();
 }
 
+// every kernel a sort-last iso surface launches (see preload_mip_kernels)
+#define SPV_PRELOAD(k)                                         \
+  do {                                                         \
+    cudaFuncAttributes fa_;                                    \
+    cudaError_t e_ = cudaFuncGetAttributes(&fa_, k);           \
+    if (e_ != cudaSuccess) return e_;                          \
+  } while (0)
+template <int FMT>
+static cudaError_t preload_iso_fmt() {
+  SPV_PRELOAD((iso_slab_search_kernel<FMT, true, true>));
+  SPV_PRELOAD((iso_slab_search_kernel<FMT, false, true>));
+  SPV_PRELOAD((iso_slab_search_kernel<FMT, true, false>));
+  SPV_PRELOAD((iso_slab_search_kernel<FMT, false, false>));
+  SPV_PRELOAD((iso_slab_resolve_kernel<FMT, true>));
+  SPV_PRELOAD((iso_slab_resolve_kernel<FMT, false>));
+  return cudaSuccess;
+}
+cudaError_t preload_iso_kernels() {
+  cudaError_t e;
+  if ((e = preload_iso_fmt<0>()) != cudaSuccess) return e;
+  if ((e = preload_iso_fmt<1>()) != cudaSuccess) return e;
+  if ((e = preload_iso_fmt<2>()) != cudaSuccess) return e;
+  if ((e = preload_iso_fmt<4>()) != cudaSuccess) return e;
+  if ((e = preload_iso_fmt<5>()) != cudaSuccess) return e;
+  SPV_PRELOAD(iso_slab_fix_kernel);
+  SPV_PRELOAD((conv_xy_kernel<3, 7>));
+  SPV_PRELOAD((conv_xy_kernel<1, 5>));
+  SPV_PRELOAD((conv_xy_kernel<1, 0>));
+  SPV_PRELOAD((conv_xy_kernel<3, 0>));
+  SPV_PRELOAD(occ_taps_kernel);
+  SPV_PRELOAD(occ_list_kernel);
+  SPV_PRELOAD(occ_queue_kernel);
+  SPV_PRELOAD(occlusion_kernel);
+  SPV_PRELOAD(shading_kernel);
+  return cudaSuccess;
+}
+
 }  // namespace spv

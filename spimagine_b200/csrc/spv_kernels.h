@@ -93,6 +93,10 @@ cudaError_t launch_comp_sync(unsigned *const *peer_flags, const unsigned *flags,
                              unsigned value, unsigned *err, cudaStream_t st);
 cudaError_t launch_comp_finish(const CompFinishArgs &a, cudaStream_t st);
 struct PeerFlagPtrs { unsigned *p[MAX_WORLD]; };
+// load every kernel a sort-last frame launches before any of them can be spinning on a peer (lazy module loading)
+cudaError_t preload_mip_kernels();
+cudaError_t preload_comp_kernels();
+cudaError_t preload_iso_kernels();
 
 cudaError_t launch_sample_points(const Volume &V, int dtype, bool linear, bool exact, const float *pos, int n,
                                  float *out, cudaStream_t st);

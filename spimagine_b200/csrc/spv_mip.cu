@@ -113,6 +113,37 @@ __device__ __forceinline__ int brick_coord(float c, int g, int shift) {
   return min(max(i, 0), g - 1);
 }
 
+// Results of one warp tile: staged through shared memory and written as 128-bit stores (8 per plane per warp); tiles cut
+// by the image edge and later parts of a multi-pass render (fmax merge, volume_kernel.cl:172-182) store per pixel.
+__device__ __forceinline__ void store_tile(const MipArgs &a, float *dst_rows, float outVal, float alphaVal, int warp, int lane,
+                                           int lx, int ly, unsigned x, unsigned tx0, unsigned ty0, bool inb,
+                                           float (*s_out)[32], float (*s_alpha)[32]) {
+  const unsigned Nx = a.width, Ny = a.height;
+  float *alpha_rows = a.alpha + (size_t)ty0 * Nx;
+  const bool vec_ok = (Nx % 4 == 0) && (tx0 + 8 <= Nx) && (ty0 + 4 <= Ny) && a.current_part == 0;
+  if (vec_ok) {
+    s_out[warp][ly * 8 + lx] = outVal;
+    s_alpha[warp][ly * 8 + lx] = alphaVal;
+    __syncwarp();
+    // 8 float4 per plane: lanes 0-7 store the value plane, lanes 8-15 the alpha plane
+    if (lane < 16) {
+      const int q = lane & 7, row = q >> 1, half = q & 1;
+      const float *src = (lane < 8 ? s_out[warp] : s_alpha[warp]) + row * 8 + half * 4;
+      float *base = lane < 8 ? dst_rows : alpha_rows;
+      *reinterpret_cast<float4 *>(base + (size_t)row * Nx + tx0 + half * 4) = *reinterpret_cast<const float4 *>(src);
+    }
+  } else if (inb) {
+    const size_t p = x + (size_t)Nx * ly;
+    if (a.current_part == 0) {
+      dst_rows[p] = outVal;
+      alpha_rows[p] = alphaVal;
+    } else {  // multi-pass rendering: merge into what earlier parts left (volume_kernel.cl:172-182)
+      dst_rows[p] = fmaxf(outVal, dst_rows[p]);
+      alpha_rows[p] = fmaxf(alphaVal, alpha_rows[p]);
+    }
+  }
+}
+
 // One CTA tile: TX x TY warps cover (8*TX) x (4*TY) pixels starting at CTA tile (bx, by).
 template <int FMT, bool LINEAR, bool SKIP, bool SLAB, int TX, int TY>
 __device__ __forceinline__ void mip_fast_tile(const MipArgs &a, unsigned bx, unsigned by, float (*s_out)[32],
@@ -282,29 +313,7 @@ __device__ __forceinline__ void mip_fast_tile(const MipArgs &a, unsigned bx, uns
     outVal = hit ? window_value(cur, a.min_val, a.max_val, a.gamma) : 0.f;
     dst_rows = a.out + (size_t)ty0 * Nx;
   }
-  float *alpha_rows = a.alpha + (size_t)ty0 * Nx;
-  const bool vec_ok = (Nx % 4 == 0) && (tx0 + 8 <= Nx) && (ty0 + 4 <= Ny) && a.current_part == 0;
-  if (vec_ok) {
-    s_out[warp][ly * 8 + lx] = outVal;
-    s_alpha[warp][ly * 8 + lx] = alphaVal;
-    __syncwarp();
-    // 8 float4 per plane: lanes 0-7 store the value plane, lanes 8-15 the alpha plane
-    if (lane < 16) {
-      const int q = lane & 7, row = q >> 1, half = q & 1;
-      const float *src = (lane < 8 ? s_out[warp] : s_alpha[warp]) + row * 8 + half * 4;
-      float *base = lane < 8 ? dst_rows : alpha_rows;
-      *reinterpret_cast<float4 *>(base + (size_t)row * Nx + tx0 + half * 4) = *reinterpret_cast<const float4 *>(src);
-    }
-  } else if (inb) {
-    const size_t p = x + (size_t)Nx * ly;
-    if (a.current_part == 0) {
-      dst_rows[p] = outVal;
-      alpha_rows[p] = alphaVal;
-    } else {  // multi-pass rendering: merge into what earlier parts left (volume_kernel.cl:172-182)
-      dst_rows[p] = fmaxf(outVal, dst_rows[p]);
-      alpha_rows[p] = fmaxf(alphaVal, alpha_rows[p]);
-    }
-  }
+  store_tile(a, dst_rows, outVal, alphaVal, warp, lane, lx, ly, x, tx0, ty0, inb, s_out, s_alpha);
 }
 
 // Static grid: one CTA per tile.
@@ -355,6 +364,83 @@ __global__ void __launch_bounds__(32 * TX * TY, MINB) mip_fast_persistent_kernel
     if (t >= ntiles) break;
     mip_fast_tile<FMT, LINEAR, SKIP, SLAB, TX, TY>(a, t % tiles_x, ty0 + t / tiles_x, s_out, s_alpha);
   }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// alpha_pow != 0 (volume_kernel.cl:134-158 float, :300-318 short): front-to-back attenuation.
+//   v = (s - min) / (max - min);  col = max(col, cum * v);  cum *= 1 - a^2 clamp(v, 0, 1)  |  1 - 0.1 a^2 v  (short)
+// in blocks of 16 samples; `if (cum <= .01) break` leaves the INNER loop only, so a ray that has gone dark still takes
+// one sample at the start of each remaining block -- and every executed sample advances the position by one step, so the
+// n-th executed sample sits at pos0 + n * delta whatever the block structure did.
+// The recurrence is serial, the fetches are not: a block's 16 samples are fetched together (positions by fma, like
+// mip_fast_kernel) and the recurrence runs over the register batch.  A ray that enters a block dark fetches one sample
+// first and the other 15 only if that sample brought it back above the threshold (cum can grow again for short volumes:
+// v < 0 below minVal).
+template <int FMT, bool LINEAR>
+__global__ void __launch_bounds__(128) mip_alpha_kernel(const MipArgs a) {
+  __shared__ __align__(16) float s_out[4][32];
+  __shared__ __align__(16) float s_alpha[4][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lx = (lane & 1) | ((lane >> 1) & 2) | ((lane >> 2) & 4);
+  const int ly = ((lane >> 1) & 1) | ((lane >> 2) & 2);
+  const unsigned tx0 = blockIdx.x * 16 + (warp & 1) * 8, ty0 = blockIdx.y * 8 + (warp >> 1) * 4;
+  const unsigned x = tx0 + lx, y = ty0 + ly;
+  const unsigned Nx = a.width, Ny = a.height;
+  const bool inb = x < Nx && y < Ny;
+  const bool isShort = (FMT % 3) != 0;
+  const Volume &V = a.vol;
+  Ray r = make_ray(x, y, Nx, Ny, a.cam, a.box);
+  const bool hit = inb && r.hit;
+  float tnear = r.tnear;
+  if (tnear < 0.0f) tnear = 0.0f;
+  float col = 0.f;
+  if (hit) {
+    const int reducedSteps = a.max_steps / a.num_parts;
+    const int nblocks = reducedSteps / 16 + 1;
+    const float dt = fabsf(r.tfar - tnear) / (float)((reducedSteps / 16) * 16);
+    const v4 orig = add4(r.orig, scl4((float)a.current_part * dt, r.direc));
+    const v4 delta_pos = scl4(.5f * dt, r.direc);
+    const v4 pos0 = scl4(0.5f, add4(sadd4(1.f, orig), scl4(tnear, r.direc)));
+    Marcher m;
+    m.u0 = pos0.x * V.fnx; m.v0 = pos0.y * V.fny; m.w0 = pos0.z * V.fnz;
+    m.du = delta_pos.x * V.fnx; m.dv = delta_pos.y * V.fny; m.dw = delta_pos.z * V.fnz;
+    const float minVal = a.min_val, maxVal = a.max_val;
+    const float att = isShort ? .1f * a.alpha_pow * a.alpha_pow : a.alpha_pow * a.alpha_pow;  // :312 / :146
+    float cum = 1.f;
+    int n = 0;  // samples executed so far
+    for (int b = 0; b < nblocks; ++b) {
+      float v[16];
+      int j0 = 0;
+      bool done = false;
+      if (cum <= 0.01f) {  // dark on entry: one sample decides whether the block goes on
+        float s = fetch_k<FMT, LINEAR, false>(V, m, (float)n);
+        s = (maxVal == 0.f) ? s : (s - minVal) / (maxVal - minVal);
+        col = fmaxf(col, cum * s);
+        cum *= isShort ? (1.f - att * s) : (1.f - att * clampf_cl(s, 0.f, 1.f));
+        ++n;
+        j0 = 1;
+        done = cum <= 0.01f;
+      }
+      if (!done) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (j >= j0) ? fetch_k<FMT, LINEAR, false>(V, m, (float)(n + j - j0)) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (j >= j0 && !done) {
+            const float s = (maxVal == 0.f) ? v[j] : (v[j] - minVal) / (maxVal - minVal);
+            col = fmaxf(col, cum * s);
+            cum *= isShort ? (1.f - att * s) : (1.f - att * clampf_cl(s, 0.f, 1.f));
+            ++n;
+            done = cum <= 0.01f;
+          }
+        }
+      }
+    }
+    if (a.gamma != 1.f) col = powf(col, a.gamma);
+    col = clampf_cl(col, 0.f, 1.f);
+  }
+  const float alphaVal = hit ? (isShort ? tnear : 1.f) : (isShort ? 0.f : -1.f);
+  store_tile(a, a.out + (size_t)ty0 * Nx, hit ? col : 0.f, alphaVal, warp, lane, lx, ly, x, tx0, ty0, inb, s_out, s_alpha);
 }
 
 // window + gamma of the composited raw maximum (sort-last renders)
@@ -422,6 +508,12 @@ static cudaError_t launch_ref(const MipArgs &a, bool exact, cudaStream_t st) {
 template <int FMT>
 static cudaError_t launch_dt(const MipArgs &a, bool linear, bool fast, bool exact, bool skip, bool slab, bool stats,
                              cudaStream_t st) {
+  if (fast && a.alpha_pow != 0.f) {  // attenuated: batched fetches, serial recurrence
+    dim3 grid((a.width + 15) / 16, (a.height + 7) / 8), block(128);
+    if (linear) mip_alpha_kernel<FMT, true><<<grid, block, 0, st>>>(a);
+    else mip_alpha_kernel<FMT, false><<<grid, block, 0, st>>>(a);
+    return cudaGetLastError();
+  }
   if (fast) return linear ? launch_fast<FMT, true>(a, skip, slab, st) : launch_fast<FMT, false>(a, skip, slab, st);
   return linear ? launch_ref<FMT, true>(a, exact, st) : launch_ref<FMT, false>(a, exact, st);
 }
@@ -530,6 +622,36 @@ cudaError_t launch_texrate_probe(const Volume &V, int dtype, bool linear, int bl
   }
 #undef SPV_PROBE
   return cudaGetLastError();
+}
+
+// Load (CUDA loads kernels lazily, at their first launch, and that load can wait for running kernels) every kernel a
+// sort-last max projection launches.  A composite's kernels wait for each other across contexts: none of them may be
+// loaded for the first time while another one is already spinning (spv_comp_init calls this).
+#define SPV_PRELOAD(k)                                         \
+  do {                                                         \
+    cudaFuncAttributes fa_;                                    \
+    cudaError_t e_ = cudaFuncGetAttributes(&fa_, k);           \
+    if (e_ != cudaSuccess) return e_;                          \
+  } while (0)
+template <int FMT>
+static cudaError_t preload_mip_fmt() {
+  SPV_PRELOAD((mip_fast_kernel<FMT, true, false, true, 2, 2, 1>));
+  SPV_PRELOAD((mip_fast_kernel<FMT, false, false, true, 2, 2, 1>));
+  SPV_PRELOAD((mip_fast_kernel<FMT, true, true, true, 2, 2, 1>));
+  SPV_PRELOAD((mip_fast_kernel<FMT, false, true, true, 2, 2, 1>));
+  SPV_PRELOAD((mip_fast_kernel<FMT, true, false, false, 2, 2, 1>));
+  SPV_PRELOAD((mip_fast_kernel<FMT, false, false, false, 2, 2, 1>));
+  return cudaSuccess;
+}
+cudaError_t preload_mip_kernels() {
+  cudaError_t e;
+  if ((e = preload_mip_fmt<0>()) != cudaSuccess) return e;
+  if ((e = preload_mip_fmt<1>()) != cudaSuccess) return e;
+  if ((e = preload_mip_fmt<2>()) != cudaSuccess) return e;
+  if ((e = preload_mip_fmt<4>()) != cudaSuccess) return e;
+  if ((e = preload_mip_fmt<5>()) != cudaSuccess) return e;
+  SPV_PRELOAD(mip_finish_kernel);
+  return cudaSuccess;
 }
 
 cudaError_t launch_mip_finish(const float *raw, float *out, int n, float minVal, float maxVal, float gamma,
