@@ -178,6 +178,27 @@ class ClockSampler(object):
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU on a two-socket host: run on the cores next to this rank's GPU, so that the page-locked
+    staging the results are copied into (first touched by this process) lies in that socket's memory.  Multi-rank runs
+    only -- a single rank keeps every core for its cpu_baseline leg.  Plumbing; failures are ignored."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms are meant to use every host core (the other
     ranks of the reference arm exit at once, and the GPU arm's host work is negligible).  libgomp is process-global:
@@ -1177,6 +1198,7 @@ def run_sweep(args, rank, local_rank, world):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path in spimagine_b200)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     vol = scenes.vol_g(args.vol, np.uint16, seed=0)
@@ -1286,9 +1308,28 @@ def run_sweep(args, rank, local_rank, world):
     d2h_sync = (rend.d2h_bytes() - b0) / float(K)
     barrier()
 
+    # what the host link gives this rank while every rank copies at once: the same bytes per frame as render_sequence
+    # moves, as plain device -> pinned-host copies back to back (torch: plumbing) -- the ceiling of `e2e` on this box
+    nprobe = max(1, int(d2h_seq) // 4)
+    dev_buf = torch.empty(nprobe, dtype=torch.float32, device="cuda")
+    host_buf = torch.empty(nprobe, dtype=torch.float32, pin_memory=True)
+    for _ in range(3):
+        host_buf.copy_(dev_buf, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        host_buf.copy_(dev_buf, non_blocking=True)
+    torch.cuda.synchronize()
+    d2h_probe = 50 * nprobe * 4 / (time.perf_counter() - t0) / 1e9
+    barrier()
+    del dev_buf, host_buf
+
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
+        pr = torch.tensor([d2h_probe], device="cuda", dtype=torch.float64)
+        dist.all_reduce(pr, op=dist.ReduceOp.MIN)
+        d2h_probe = float(pr[0])
         t = torch.tensor([ms, t_e2e * 1e3, t_seq * 1e3], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, t_e2e, t_seq = float(t[0]), float(t[1]) / 1e3, float(t[2]) / 1e3
@@ -1344,6 +1385,10 @@ def run_sweep(args, rank, local_rank, world):
             "e2e": {"value": total_frames / t_seq, "unit": "frames/s", "h2d_bytes_per_step": 128,
                     "d2h_bytes_per_step": int(round(d2h_seq)),
                     "d2h_gbytes_per_s_per_rank": d2h_seq * K / t_seq / 1e9,
+                    "d2h_ceiling_gbytes_per_s_per_rank": d2h_probe,
+                    "d2h_ceiling_frames_per_s": world * d2h_probe * 1e9 / max(1., d2h_seq),
+                    "d2h_ceiling_note": "plain device -> pinned host copies of the same size, all ranks at once, slowest "
+                                        "rank: what the host link of this box leaves for `e2e`",
                     "note": "VolumeRenderer.render_sequence(modelViews): per frame the host inverts the 4x4 modelView, "
                             "launches, and output + alpha are copied to pinned host memory (only the rows the projected "
                             "box can touch travel: %.0f%% of 2*W*H*4 bytes; the others already hold the miss values); "
