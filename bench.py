@@ -536,12 +536,69 @@ def run_iso(args, rank, local_rank, world):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
+    # where the time of a sort-last frame goes (peer composite): device time per phase, statistics on, untimed
+    phases = None
+    if world > 1 and args.composite == "peer":
+        rend.enable_stats(True)
+        acc = {}
+        for i in range(12):
+            device_step(i)
+            for k_, v_ in rend.last_phases_us().items():
+                acc.setdefault(k_, []).append(v_)
+        rend.enable_stats(False)
+        names = list(rend.PHASES)
+        pv = torch.tensor([float(np.mean(acc.get(k_, [0.])[2:])) for k_ in names], device="cuda", dtype=torch.float64)
+        pmax = pv.clone()
+        dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pv, op=dist.ReduceOp.SUM)
+        phases = dict((k_, {"mean_over_ranks_us": float(pv[j]) / world, "max_over_ranks_us": float(pmax[j])})
+                      for j, k_ in enumerate(names))
+    barrier()
     if world > 1:
         t = torch.tensor([ms, t_e2e * 1e3], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, t_e2e = float(t[0]), float(t[1]) / 1e3
     if rank == 0:
-        print(json.dumps({
+        peaks, peak_src = measured_peaks()
+        alg = float(N) ** 3 * 2 + 6 * W * W * 4   # every voxel once + (3 + 3) result planes
+        achieved = alg / (ms * 1e-3 / args.steps) / 1e9 / world
+        traffic, traffic_src = ncu_traffic("iso_%d_%d" % (N, W), "iso") if world == 1 else (None, "single-GPU captures only")
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            # the oracle's whole pipeline (search, blur, occlusion, blur, shading) on all host cores, a few frames of the sweep
+            from oracle import oracle
+            use_all_host_threads()
+            kind = "reference" if oracle.available("reference") else "port"
+            host_vol = vol_g_slab_device(N, 0, N, 1, dev).cpu().numpy()
+            o = oracle.OracleRenderer((W, W), kind=kind, max_steps=MAX_STEPS)
+            o.set_data(host_vol)
+            o.set_projection(cams[0][1])
+            o.set_max_val(iso_max)
+            o.set_modelView(cams[0][0])
+            o.render(method="iso_surface")
+            nf = 6
+            t0 = time.perf_counter()
+            for i in range(nf):
+                o.set_modelView(cams[(i * 6) % NF][0])
+                o.render(method="iso_surface")
+            t_cpu = (time.perf_counter() - t0) / nf
+            cpu = {"value": 1. / t_cpu, "unit": "frames/s", "cores": int(o.lib.so_num_threads()), "kind": kind,
+                   "sample": "%d whole frames of the sweep (every 6th), iso_surface + blur + occlusion + blur + shading" % nf}
+            del host_vol, o
+        line_extra = {
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s (per GPU)",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "algorithmic_bytes_per_frame": alg,
+                         "kernel": "spv::iso_fast_kernel<u16, linear, skip>" if world == 1 else "spv::iso_slab_search_kernel<u16, linear, skip>",
+                         "note": "SURVEY 8d's algorithmic bytes count every voxel once; the search leaves cells that cannot hold "
+                                 "a crossing in one step (exact hierarchical traversal), so the DRAM traffic is a few per cent of "
+                                 "that and the fraction can exceed 1: this kernel is bound by the latency of its longest warps "
+                                 "(DESIGN 4.3), not by HBM"}}
+        if cpu:
+            line_extra["cpu_baseline"] = cpu
+        if phases:
+            line_extra["phases_us"] = phases
+        print(json.dumps(dict({
             "metric": "iso_surface frames/s, %d^3 uint16 -> %d^2, AO + shading, 36-frame sweep" % (N, W),
             "value": args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -556,7 +613,7 @@ def run_iso(args, rank, local_rank, world):
             "surface_pixels_last": hit_px, "image_sha1_first8": digest.hexdigest(),
             # iso_fast, blur, occlusion list + queue, blur, shading; sort-last: search, resolve, fix-up, 2+2 blur
             # launches, occlusion list + queue, shading (the two NCCL reductions are not counted)
-            "gpu_launches": args.steps * (6 if world == 1 else (11 if args.composite == "peer" else 10))}))
+            "gpu_launches": args.steps * (6 if world == 1 else (13 if args.composite == "peer" else 10))}, **line_extra)))
     rend.close()
     if world > 1:
         dist.destroy_process_group()
@@ -1159,18 +1216,21 @@ def c4_record(args, rank, local_rank, world):
     return rec
 
 
-def source_sha1():
-    """SHA-1 over the sources of the max-projection kernel: ties a committed ncu traffic figure to the code it was
-    measured on (profiles/r02_mip_traffic.json is written by scripts/ncu_traffic.py)."""
+KERNEL_SOURCES = {"mip": ("spv_mip.cu", "spv_common.cuh", "spv_kernels.h"), "iso": ("spv_iso.cu", "spv_common.cuh", "spv_kernels.h")}
+
+
+def source_sha1(family="mip"):
+    """SHA-1 over the sources of a kernel family: ties a committed ncu traffic figure to the code it was measured on
+    (profiles/r02_mip_traffic.json is written by scripts/ncu_traffic.py)."""
     import hashlib
     h = hashlib.sha1()
-    for f in ("spv_mip.cu", "spv_common.cuh", "spv_kernels.h"):
+    for f in KERNEL_SOURCES[family]:
         with open(os.path.join(ROOT, "spimagine_b200", "csrc", f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()
 
 
-def ncu_traffic(workload_key):
+def ncu_traffic(workload_key, family="mip"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu capture of
     this workload, or (None, why) when there is none for the current kernel sources."""
     path = os.path.join(ROOT, "profiles", "r02_mip_traffic.json")
@@ -1180,7 +1240,7 @@ def ncu_traffic(workload_key):
         rec = json.load(f).get(workload_key)
     if rec is None:
         return None, "no ncu capture of this workload in profiles/r02_mip_traffic.json"
-    if rec.get("source_sha1") != source_sha1():
+    if rec.get("source_sha1") != source_sha1(family):
         return None, "the committed ncu capture (profiles/r02_mip_traffic.json) predates the current kernel sources"
     return int(rec["dram_bytes_read"] + rec["dram_bytes_write"]), \
         "profiles/r02_mip_traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over %d launches of %s" % (

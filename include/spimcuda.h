@@ -288,7 +288,11 @@ SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
  * the projected box cannot touch first, then the box's rows top to bottom (default), knob 9 = with knob 8 = 1, rows
  * outside the hull of the projected box corners (+ 9 pixels) are not copied by spv_render_mip_to_host: every ray there
  * misses, and the pinned staging rows already hold the miss values (out 0, alpha 0 / -1), which the library keeps
- * track of per output slot (1, default; 0 = copy every row).  The staging memory must be treated as read-only. */
+ * track of per output slot (1, default; 0 = copy every row).  The staging memory must be treated as read-only.
+ * knob 10 = tiles of every 8 (fixed pattern) that the software-sampled max projection (spv_set_mip_path) hands to the
+ * texture unit (hybrid; changes which sampler a pixel gets, deterministically), knob 11 = its box / ring geometry (0..4),
+ * knob 12 = sort-last iso frames run the screen-space passes on the rank's own band of rows and exchange the finished
+ * bands (1, default) or on the whole image on every rank (0). */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 /* Which kernel family renders plain (alpha_pow == 0, num_parts == 1) max projections of uint16 volumes
  * (max_project_short, volume_kernel.cl:270-345):
@@ -314,6 +318,10 @@ SPV_API int spv_texrate_probe(spv_ctx *ctx, int iters, double *samples_per_s);
  * j = 0..15, with vec9 = {a, b, m} in texels (x, y, z).  All warps walk the same small region (every fetch hits L1):
  * the rate the texture unit can deliver for the ray and sample spacing of a given camera */
 SPV_API int spv_texrate_probe_footprint(spv_ctx *ctx, int iters, const float *vec9, double *samples_per_s);
+/* Device time of each phase of the last spv_render_iso_composite that ran with spv_enable_stats on, in order: search,
+ * wait for the peers' candidates, MIN + redistribution, wait, resolve, wait, screen-space passes, band gather + wait
+ * (the last one only with more than one rank).  *count = phases written. */
+SPV_API int spv_last_phases_ms(spv_ctx *ctx, float *ms, int n, int *count);
 SPV_API int spv_launch_count(spv_ctx *ctx, unsigned long long *n);  /* kernels launched by this context so far */
 /* Result bytes this context has enqueued for device -> host copies so far (what `.get()` of the result buffers moves in
  * the reference, volumerender.py:388-390, 499-506): rows that cannot hold a hit are not copied, so a frame

@@ -23,6 +23,7 @@ UNIT = {"byte": 1., "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 
 
 def main():
     path, key = sys.argv[1], sys.argv[2]
+    family = sys.argv[3] if len(sys.argv) > 3 else "mip"
     rows = []
     with open(path) as f:
         lines = [ln for ln in f if ln.startswith('"')]
@@ -40,7 +41,7 @@ def main():
            "dram_bytes_read": sum(m["dram__bytes_read.sum"] for m in ms) / len(ms),
            "dram_bytes_write": sum(m["dram__bytes_write.sum"] for m in ms) / len(ms),
            "time_us_under_ncu": sum(m["gpu__time_duration.sum"] for m in ms) / len(ms),
-           "source_sha1": bench.source_sha1(), "from": os.path.basename(path)}
+           "source_sha1": bench.source_sha1(family), "from": os.path.basename(path)}
     out = os.path.join(ROOT, "profiles", "r02_mip_traffic.json")
     allrec = {}
     if os.path.exists(out):

@@ -104,6 +104,9 @@ struct spv_ctx {
   // software-sampled max projection (spv_set_mip_path, spv_mip_smem.cu): permuted linear uint16 copies of the resident
   // volume (slowest axis x, y, z) and the tensor maps the kernel's TMA box loads go through
   int mip_path = 0, last_mip_path = 0;
+  cudaEvent_t ev_ph[9] = {nullptr};  // phase boundaries of the last sort-last iso frame (recorded while statistics are on)
+  int n_ph = 0;
+  int iso_post_sharded = 1;  // tuning knob 12: sort-last iso frames run the screen-space passes on the rank's own band
   int smem_tex_of8 = 0;  // tuning knob 10: tiles (of every 8) the software-sampled kernel hands to the texture unit
   void *d_lin[3] = {nullptr, nullptr, nullptr};
   bool lin_valid = false;
@@ -123,7 +126,7 @@ struct spv_ctx {
 };
 
 // arrival-counter phases of the peer composites: 0, 1 max projection; 2, 3, 4 iso surface
-constexpr int COMP_PHASES = 5;
+constexpr int COMP_PHASES = 6;  // + 5: the finished bands of a sort-last iso frame have reached every rank
 
 static thread_local std::string g_create_err;
 
@@ -342,6 +345,8 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
   if (ctx->d_minmax) cudaFree(ctx->d_minmax);
   if (ctx->d_stats) cudaFree(ctx->d_stats);
   if (ctx->d_tile_counter) cudaFree(ctx->d_tile_counter);
+  for (int i = 0; i < 9; ++i)
+    if (ctx->ev_ph[i]) cudaEventDestroy(ctx->ev_ph[i]);
   if (ctx->d_band_done) cudaFree(ctx->d_band_done);
   if (ctx->d_iso_err) cudaFree(ctx->d_iso_err);
   if (ctx->d_taps) cudaFree(ctx->d_taps);
@@ -853,6 +858,7 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   else if (knob == 8) ctx->row_mode = value == 1 ? 1 : 0;
   else if (knob == 9) ctx->clip_copies = value != 0;
   else if (knob == 10) ctx->smem_tex_of8 = value < 0 ? 0 : (value > 8 ? 8 : value);
+  else if (knob == 12) ctx->iso_post_sharded = value != 0;
   else if (knob == 11) ctx->smem_cfg = value < 0 || value >= mip_smem_configs() ? 0 : value;
   else if (knob == 6) occ_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : value);  // process-wide
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
@@ -1575,10 +1581,21 @@ SPV_API int spv_render_iso_composite(spv_ctx *ctx, const spv_iso_params *p) {
   peer.normals_plane = post ? 9 : 4;
   rc = begin_render(ctx);
   if (rc) return rc;
+  ctx->n_ph = 0;
+#define SPV_PHASE()                                                                  \
+  do {                                                                               \
+    if (ctx->stats_on && ctx->n_ph < 9) {                                            \
+      if (!ctx->ev_ph[ctx->n_ph]) CU(cudaEventCreate(&ctx->ev_ph[ctx->n_ph]));       \
+      CU(cudaEventRecord(ctx->ev_ph[ctx->n_ph++], ctx->stream));                     \
+    }                                                                                \
+  } while (0)
+  SPV_PHASE();
   int *k = (int *)ctx->raw();  // the two candidate planes live in [raw | tmp]
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
   CU(launch_iso_slab(a, fmt_of(ctx), linear, 0, k, k + n, ctx->occ(), ctx->d_iso_err, ctx->stream, &peer));
+  SPV_PHASE();
   CU(launch_comp_sync(ctx->peer_flags, ctx->comp_flags, W, R, 2, f, ctx->comp_err, ctx->stream));
+  SPV_PHASE();
   KReduceArgs ka;
   memset(&ka, 0, sizeof ka);
   ka.part = peer.kpart[R];
@@ -1589,26 +1606,62 @@ SPV_API int spv_render_iso_composite(spv_ctx *ctx, const spv_iso_params *p) {
   ka.n_pixels = ka.first_pixel >= n ? 0u : (unsigned)((n - ka.first_pixel) < band ? (n - ka.first_pixel) : band);
   ka.n_image = n;
   CU(launch_k_reduce(ka, ctx->stream));
+  SPV_PHASE();
   CU(launch_comp_sync(ctx->peer_flags, ctx->comp_flags, W, R, 3, f, ctx->comp_err, ctx->stream));
+  SPV_PHASE();
   a.stats = nullptr;
   CU(launch_iso_slab(a, fmt_of(ctx), linear, 1, k, k + n, ctx->occ(), ctx->d_iso_err, ctx->stream, &peer));
+  SPV_PHASE();
   CU(launch_comp_sync(ctx->peer_flags, ctx->comp_flags, W, R, 4, f, ctx->comp_err, ctx->stream));
+  SPV_PHASE();
   ctx->launches += 6;
   if (post) {
+    // The screen-space passes (volumerender.py:470-497) on this rank's band of rows only -- every rank holds the
+    // complete raw planes, and a pass reads whatever rows around the band its taps reach -- then the band's finished
+    // planes go to every peer.  Per rank the passes cost 1 / world of what they cost on one GPU.
+    const int ya = R * ctx->comp_band_rows < ctx->height ? R * ctx->comp_band_rows : ctx->height;
+    const int yb = ya + ctx->comp_band_rows < ctx->height ? ya + ctx->comp_band_rows : ctx->height;
+    const bool shard = W > 1 && ctx->iso_post_sharded;
+    const int y0 = shard ? ya : 0, y1 = shard ? yb : ctx->height;
+    // the occlusion blur of row y reads the raw occlusion of rows y - 2 .. y + 2
+    const int oy0 = shard ? (y0 - 4 > 0 ? y0 - 4 : 0) : 0, oy1 = shard ? (y1 + 4 < ctx->height ? y1 + 4 : ctx->height) : ctx->height;
     CU(launch_conv_xy(ctx->tmp_vec(), ctx->normals(), ctx->width, ctx->height, 3, conv_weights(7, -5.f), a.tile_hit, 0,
-                      ctx->stream));
+                      ctx->stream, y0, y1));
     CU(launch_occlusion(ctx->tmp(), ctx->width, ctx->height, p->occ_radius, p->occ_n_points, ctx->depth(), a.tile_hit,
-                        ctx->d_taps, ctx->d_occ_queue, ctx->occ_frame++, ctx->sms, ctx->stream));
+                        ctx->d_taps, ctx->d_occ_queue, ctx->occ_frame++, ctx->sms, ctx->stream, oy0, oy1));
     CU(launch_conv_xy(ctx->tmp(), ctx->occ(), ctx->width, ctx->height, 1, conv_weights(5, -10.f), a.tile_hit,
-                      p->occ_radius, ctx->stream));
+                      p->occ_radius, ctx->stream, y0, y1));
     CU(launch_shading(ctx->out(), ctx->width, ctx->height, ctx->cam, p->occ_strength, ctx->normals(), ctx->depth(),
-                      ctx->occ(), ctx->stream));
+                      ctx->occ(), ctx->stream, y0, y1));
     ctx->launches += 5;
+    SPV_PHASE();
+    if (shard) {
+      BandGatherArgs g;
+      memset(&g, 0, sizeof g);
+      for (int r = 0; r < W; ++r) g.planes[r] = ctx->peer_out[r];
+      g.world = W; g.rank = R; g.width = ctx->width; g.height = ctx->height; g.y_first = y0; g.y_end = y1;
+      CU(launch_band_gather(g, ctx->stream));
+      CU(launch_comp_sync(ctx->peer_flags, ctx->comp_flags, W, R, 5, f, ctx->comp_err, ctx->stream));
+      ctx->launches += 2;
+      SPV_PHASE();
+    }
   } else {
     CU(cudaMemsetAsync(ctx->occ(), 0, n * sizeof(float), ctx->stream));  // what the NCCL path's resolve leaves there
   }
   ctx->last_method = 1;
   return end_render(ctx);
+#undef SPV_PHASE
+}
+
+// durations between the phase boundaries of the last spv_render_iso_composite that ran with statistics on:
+// search | wait for the candidates | MIN + redistribution | wait | resolve | wait | screen-space passes | band gather + wait
+SPV_API int spv_last_phases_ms(spv_ctx *ctx, float *ms, int n, int *count) {
+  BIND();
+  if (!ms || !count) return fail(ctx, SPV_EINVAL, "spv_last_phases_ms: null argument");
+  CU(cudaStreamSynchronize(ctx->stream));
+  *count = ctx->n_ph > 1 ? ctx->n_ph - 1 : 0;
+  for (int i = 0; i + 1 < ctx->n_ph && i < n; ++i) CU(cudaEventElapsedTime(&ms[i], ctx->ev_ph[i], ctx->ev_ph[i + 1]));
+  return 0;
 }
 
 static float *buf_of(spv_ctx *c, int which, size_t *count) {

@@ -112,12 +112,36 @@ cudaError_t launch_comp_finish(const CompFinishArgs &a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// Sort-last iso surface, last exchange: every rank ran the screen-space passes on its own band of rows only; the band's
+// finished planes go to every peer.  One float4 per thread and plane segment; W * H is a multiple of 4 (spv_comp_init).
+__global__ void __launch_bounds__(256) band_gather_kernel(const BandGatherArgs a) {
+  const size_t n = (size_t)a.width * a.height;
+  const size_t first = (size_t)a.y_first * a.width, count = (size_t)(a.y_end - a.y_first) * a.width;
+  // segments: out [0, n), occ [3n, 4n) -> band pixels each; normals [4n, 7n) -> 3 floats per pixel
+  const size_t q1 = count / 4, q3 = 3 * count / 4, total = 2 * q1 + q3;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    size_t off;  // float offset into the planes
+    if (t < q1) off = first + 4 * t;
+    else if (t < 2 * q1) off = 3 * n + first + 4 * (t - q1);
+    else off = 4 * n + 3 * first + 4 * (t - 2 * q1);
+    const float4 v = *reinterpret_cast<const float4 *>(a.planes[a.rank] + off);
+    for (int r = 0; r < a.world; ++r)
+      if (r != a.rank) *reinterpret_cast<float4 *>(a.planes[r] + off) = v;
+  }
+}
+cudaError_t launch_band_gather(const BandGatherArgs &a, cudaStream_t st) {
+  if (a.world < 2 || a.y_first >= a.y_end) return cudaSuccess;
+  band_gather_kernel<<<592, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t preload_comp_kernels() {
   cudaFuncAttributes fa;
   cudaError_t e;
   if ((e = cudaFuncGetAttributes(&fa, comp_sync_kernel)) != cudaSuccess) return e;
   if ((e = cudaFuncGetAttributes(&fa, comp_finish_kernel)) != cudaSuccess) return e;
-  return cudaFuncGetAttributes(&fa, k_reduce_kernel);
+  if ((e = cudaFuncGetAttributes(&fa, k_reduce_kernel)) != cudaSuccess) return e;
+  return cudaFuncGetAttributes(&fa, band_gather_kernel);
 }
 
 }  // namespace spv

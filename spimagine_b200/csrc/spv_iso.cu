@@ -807,20 +807,22 @@ constexpr int CONV_TH = 16;
 template <int NCOMP, int NH>
 __global__ void __launch_bounds__(256) conv_xy_kernel(const float *__restrict__ input, float *__restrict__ output, int Nx,
                                                       int Ny, const ConvWeights cw,
-                                                      const unsigned char *__restrict__ tile_hit, int tiles_x, int reach) {
+                                                      const unsigned char *__restrict__ tile_hit, int tiles_x, int reach,
+                                                      int y_first, int y_end) {
+  // rows [y_first, y_end) are written (the whole image, or one rank's band of a sort-last frame); taps read any row
   extern __shared__ float s_row[];  // [CONV_TH + Nh - 1][32]
   const int Nh = NH > 0 ? NH : cw.nh, R = Nh / 2;
   const int c = blockIdx.x * 32 + threadIdx.x;  // column of the interleaved image (NCOMP * Nx floats per row)
-  const int i = c / NCOMP, y0 = blockIdx.y * CONV_TH;
+  const int i = c / NCOMP, y0 = y_first + blockIdx.y * CONV_TH;
   const int rows = CONV_TH + Nh - 1;
   const int pitch = NCOMP * Nx;
   if (tile_hit) {
     const int px0 = (int)(blockIdx.x * 32) / NCOMP, px1 = min((int)(blockIdx.x * 32 + 31) / NCOMP, Nx - 1);
-    const int live = __syncthreads_or(tiles_in_reach(tile_hit, tiles_x, Nx, Ny, px0, px1, y0, min(y0 + CONV_TH, Ny) - 1,
+    const int live = __syncthreads_or(tiles_in_reach(tile_hit, tiles_x, Nx, Ny, px0, px1, y0, min(y0 + CONV_TH, y_end) - 1,
                                                      reach + Nh, threadIdx.y * 32 + threadIdx.x, 256));
     if (!live) {
       if (c < pitch)
-        for (int r = threadIdx.y; r < CONV_TH && y0 + r < Ny; r += blockDim.y) output[(size_t)(y0 + r) * pitch + c] = 0.f;
+        for (int r = threadIdx.y; r < CONV_TH && y0 + r < y_end; r += blockDim.y) output[(size_t)(y0 + r) * pitch + c] = 0.f;
       return;
     }
   }
@@ -860,7 +862,7 @@ __global__ void __launch_bounds__(256) conv_xy_kernel(const float *__restrict__ 
   if (c >= pitch) return;
   for (int r = threadIdx.y; r < CONV_TH; r += blockDim.y) {
     const int j = y0 + r;
-    if (j >= Ny) break;
+    if (j >= y_end) break;
     const int h_start = ((j - R) < 0) ? R - j : 0;
     const int h_end = ((j + R) >= Ny) ? Nh - (j + R - Ny + 1) : Nh;
     const float *col = s_row + r * 32 + threadIdx.x;  // tap ht at col[32 * ht]
@@ -881,16 +883,21 @@ __global__ void __launch_bounds__(256) conv_xy_kernel(const float *__restrict__ 
 }
 
 cudaError_t launch_conv_xy(const float *in, float *out, int width, int height, int ncomp, const ConvWeights &w,
-                           const unsigned char *tile_hit, int reach, cudaStream_t st) {
+                           const unsigned char *tile_hit, int reach, cudaStream_t st, int y_first, int y_end) {
   if (in == out || w.nh < 1 || w.nh > 32 || (ncomp != 1 && ncomp != 3)) return cudaErrorInvalidValue;
-  dim3 block(32, 8), grid((ncomp * width + 31) / 32, (height + CONV_TH - 1) / CONV_TH);
+  if (y_end < 0 || y_end > height) y_end = height;
+  if (y_first < 0) y_first = 0;
+  if (y_first >= y_end) return cudaSuccess;
+  dim3 block(32, 8), grid((ncomp * width + 31) / 32, (y_end - y_first + CONV_TH - 1) / CONV_TH);
   if (grid.y > 65535u) return cudaErrorInvalidValue;
   const size_t smem = (size_t)(CONV_TH + w.nh - 1) * 32 * sizeof(float);
   const int tx = (width + 7) / 8;
-  if (ncomp == 3 && w.nh == 7) conv_xy_kernel<3, 7><<<grid, block, smem, st>>>(in, out, width, height, w, tile_hit, tx, reach);
-  else if (ncomp == 1 && w.nh == 5) conv_xy_kernel<1, 5><<<grid, block, smem, st>>>(in, out, width, height, w, tile_hit, tx, reach);
-  else if (ncomp == 1) conv_xy_kernel<1, 0><<<grid, block, smem, st>>>(in, out, width, height, w, tile_hit, tx, reach);
-  else conv_xy_kernel<3, 0><<<grid, block, smem, st>>>(in, out, width, height, w, tile_hit, tx, reach);
+#define SPV_CONV(C, N) conv_xy_kernel<C, N><<<grid, block, smem, st>>>(in, out, width, height, w, tile_hit, tx, reach, y_first, y_end)
+  if (ncomp == 3 && w.nh == 7) SPV_CONV(3, 7);
+  else if (ncomp == 1 && w.nh == 5) SPV_CONV(1, 5);
+  else if (ncomp == 1) SPV_CONV(1, 0);
+  else SPV_CONV(3, 0);
+#undef SPV_CONV
   return cudaGetLastError();
 }
 
@@ -967,7 +974,7 @@ constexpr int OCC_BW = 32, OCC_BH = 2, OCC_GROUP = 4;  // the list kernel classi
 __global__ void __launch_bounds__(256) occ_list_kernel(float *__restrict__ d_output, int Nx, int Ny, int radius,
                                                        const unsigned char *__restrict__ tile_hit, int tiles_x, int obx,
                                                        int oby, unsigned *__restrict__ cnt, unsigned *__restrict__ cnt_next,
-                                                       unsigned *__restrict__ list) {
+                                                       unsigned *__restrict__ list, int y_first, int y_end) {
   // one warp per group of OCC_GROUP vertically adjacent blocks (32 x 8 pixels): their reach rectangles differ by a
   // few rows only, so one scan of the tile flags over the union decides all of them (conservatively: a block that
   // is computed although nothing is in reach still gets the right answer, 0)
@@ -977,6 +984,7 @@ __global__ void __launch_bounds__(256) occ_list_kernel(float *__restrict__ d_out
   if (g >= obx * gy) return;
   const int bx = g % obx, by0 = (g / obx) * OCC_GROUP, nb = min(OCC_GROUP, oby - by0);
   const int px = bx * OCC_BW, py = by0 * OCC_BH;
+  if (py + nb * OCC_BH <= y_first || py >= y_end) return;  // not this rank's rows (sort-last frames): left untouched
   const int mine = tiles_in_reach(tile_hit, tiles_x, Nx, Ny, px, px + OCC_BW - 1, py, py + nb * OCC_BH - 1, radius, lane, 32);
   if (__any_sync(0xffffffffu, mine != 0)) {
     if (lane < nb) list[atomicAdd(cnt, 1u)] = (unsigned)((by0 + lane) * obx + bx);
@@ -1037,13 +1045,15 @@ size_t occ_queue_bytes(int width, int height) {
 int occ_ctas_per_sm = 10;  // resident CTAs (4 warps each) per SM of the occlusion queue kernel (tuning knob 6)
 cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int n_points, const float *depth,
                              const unsigned char *tile_hit, const float4 *taps, unsigned *queue, unsigned frame, int sms,
-                             cudaStream_t st) {
+                             cudaStream_t st, int y_first, int y_end) {
+  if (y_end < 0 || y_end > height) y_end = height;
+  if (y_first < 0) y_first = 0;
   if (tile_hit && queue) {
     const int obx = (width + OCC_BW - 1) / OCC_BW, oby = (height + OCC_BH - 1) / OCC_BH;
     const int groups = obx * ((oby + OCC_GROUP - 1) / OCC_GROUP);
     unsigned *cnt = queue + 2 * (frame & 1u), *cnt_next = queue + 2 * ((frame + 1u) & 1u), *list = queue + 4;
     occ_list_kernel<<<(groups + 7) / 8, 256, 0, st>>>(occ, width, height, radius, tile_hit, (width + 7) / 8, obx, oby, cnt,
-                                                     cnt_next, list);
+                                                     cnt_next, list, y_first, y_end);
     occ_queue_kernel<<<(sms > 0 ? sms : 148) * occ_ctas_per_sm, 128, 0, st>>>(occ, width, height, radius, n_points, depth, taps, obx, cnt,
                                                                  list);
     return cudaGetLastError();
@@ -1057,9 +1067,9 @@ cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int 
 // -------------------------------------------------------------------------------------------------------------
 __global__ void shading_kernel(float *__restrict__ d_output, int Nx, int Ny, const Camera cam, float occ_strength,
                                const float *__restrict__ input_normals, const float *__restrict__ input_depth,
-                               const float *__restrict__ input_occlusion) {
-  const unsigned x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= (unsigned)Nx || y >= (unsigned)Ny) return;
+                               const float *__restrict__ input_occlusion, int y_first, int y_end) {
+  const unsigned x = blockIdx.x * blockDim.x + threadIdx.x, y = (unsigned)y_first + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= (unsigned)Nx || y >= (unsigned)y_end) return;
   if (!(input_depth[x + (size_t)Nx * y] < __int_as_float(0x7f800000))) {  // colVal * 0 below: nothing to compute
     d_output[x + (size_t)Nx * y] = 0.f;
     return;
@@ -1087,9 +1097,13 @@ __global__ void shading_kernel(float *__restrict__ d_output, int Nx, int Ny, con
 }
 
 cudaError_t launch_shading(float *out, int width, int height, const Camera &cam, float occ_strength,
-                           const float *normals, const float *depth, const float *occ, cudaStream_t st) {
-  dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
-  shading_kernel<<<grid, block, 0, st>>>(out, width, height, cam, occ_strength, normals, depth, occ);
+                           const float *normals, const float *depth, const float *occ, cudaStream_t st, int y_first,
+                           int y_end) {
+  if (y_end < 0 || y_end > height) y_end = height;
+  if (y_first < 0) y_first = 0;
+  if (y_first >= y_end) return cudaSuccess;
+  dim3 block(32, 8), grid((width + 31) / 32, (y_end - y_first + 7) / 8);
+  shading_kernel<<<grid, block, 0, st>>>(out, width, height, cam, occ_strength, normals, depth, occ, y_first, y_end);
   return cudaGetLastError();
 }
 

@@ -92,6 +92,13 @@ struct CompFinishArgs {
 cudaError_t launch_comp_sync(unsigned *const *peer_flags, const unsigned *flags, int world, int rank, int phase,
                              unsigned value, unsigned *err, cudaStream_t st);
 cudaError_t launch_comp_finish(const CompFinishArgs &a, cudaStream_t st);
+// rows [y_first, y_end) of the finished planes (out, occlusion, blurred normals) of a sort-last iso frame go from the rank
+// that computed them into every other rank's planes (128-bit peer stores)
+struct BandGatherArgs {
+  float *planes[MAX_WORLD];  // rank r's [out | alpha | depth | occ | normals(3) | ...]
+  int world, rank, width, height, y_first, y_end;
+};
+cudaError_t launch_band_gather(const BandGatherArgs &a, cudaStream_t st);
 struct PeerFlagPtrs { unsigned *p[MAX_WORLD]; };
 // load every kernel a sort-last frame launches before any of them can be spinning on a peer (lazy module loading)
 cudaError_t preload_mip_kernels();
@@ -135,8 +142,9 @@ cudaError_t launch_conv(float *buf, float *tmp, int width, int height, int ncomp
                         cudaStream_t st);
 // both passes in one launch (in != out), bit-identical to launch_conv.  tile_hit (may be null): `in` is +0 on every
 // pixel further than `reach` pixels from a flagged 8x4 tile; such regions are filled with zeros without the arithmetic
+// y_first / y_end: only these rows are written (default: all) -- one rank's band of a sort-last frame
 cudaError_t launch_conv_xy(const float *in, float *out, int width, int height, int ncomp, const ConvWeights &w,
-                           const unsigned char *tile_hit, int reach, cudaStream_t st);
+                           const unsigned char *tile_hit, int reach, cudaStream_t st, int y_first = 0, int y_end = -1);
 // taps[i] = the four rand_int() values of occlusion tap i (they depend on i only)
 cudaError_t launch_occ_taps(float4 *taps, int n, cudaStream_t st);
 // queue (occ_queue_bytes, zero-initialised) + tile flags: only the pixel blocks in reach of a surface are computed, handed
@@ -145,9 +153,10 @@ size_t occ_queue_bytes(int width, int height);
 extern int occ_ctas_per_sm;
 cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int n_points, const float *depth,
                              const unsigned char *tile_hit, const float4 *taps, unsigned *queue, unsigned frame, int sms,
-                             cudaStream_t st);
+                             cudaStream_t st, int y_first = 0, int y_end = -1);
 cudaError_t launch_shading(float *out, int width, int height, const Camera &cam, float occ_strength,
-                           const float *normals, const float *depth, const float *occ, cudaStream_t st);
+                           const float *normals, const float *depth, const float *occ, cudaStream_t st, int y_first = 0,
+                           int y_end = -1);
 
 // min/max brick grids of the resident volume (built from the point texture)
 cudaError_t launch_build_bricks(const Volume &vol, int dtype, int local_nz, float2 *bricks, float2 *coarse, int cgx,

@@ -357,6 +357,16 @@ class SlabMaxProjector(VolumeRenderer):
             raise NotImplementedError("sort-last iso_surface renders one slab per rank")
         self._check(self._lib.spv_render_iso_composite(self._ctx, C.byref(self._iso_params(raw_only))))
 
+    PHASES = ("search", "wait_candidates", "min_redistribute", "wait_min", "resolve", "wait_resolve", "screen_passes",
+              "band_gather_wait")
+
+    def last_phases_us(self):
+        """{phase: microseconds} of the last enqueue_iso_composite that ran with enable_stats(True)."""
+        ms = (C.c_float * 8)()
+        n = C.c_int()
+        self._check(self._lib.spv_last_phases_ms(self._ctx, ms, 8, C.byref(n)))
+        return dict((self.PHASES[i], 1e3 * ms[i]) for i in range(n.value))
+
     def collect_iso(self):
         """Wait for the enqueued iso composite and read all planes back."""
         self._check(self._lib.spv_comp_check(self._ctx))
