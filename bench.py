@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--c4-vol", type=int, default=2048)
     ap.add_argument("--c4-img", type=int, default=2048)
     ap.add_argument("--c4-steps", type=int, default=24)
+    ap.add_argument("--dtype", default="u16", choices=["u16", "f32"],
+                    help="sweep workload: element type of the volume (f32 with --vol 128 --img 512 is BASELINE configs[0])")
     ap.add_argument("--alpha-pow", type=float, default=0.,
                     help="sweep workload with front-to-back attenuation (set_alpha_pow; volume_kernel.cl:300-318): "
                          "mip_alpha_kernel instead of mip_fast_kernel; no c4 record, no texture-sample roofline")
@@ -108,14 +110,27 @@ def sweep_thetas(steps, rank, world):
     return [2 * math.pi * (j / float(steps) + rank / float(steps * world)) for j in range(steps)]
 
 
+def sweep_metric(args):
+    """`metric` of the sweep workload -- the same string in both arms."""
+    f32 = getattr(args, "dtype", "u16") == "f32"
+    m = METRIC
+    if (args.vol, args.img, f32) != (VOL_N, IMG, False):
+        m = "MIP frames/s, %d^3 %s -> %d^2, 360-degree modelView sweep" % (args.vol, "float32" if f32 else "uint16", args.img)
+    if getattr(args, "alpha_pow", 0.):
+        m += ", alpha_pow = %g" % args.alpha_pow
+    return m
+
+
 def sweep_config(args):
     """`config` of the headline workload -- the same dict in both arms (--impl ours / reference)."""
     return {
-        "workload": "Vol-G(%d, uint16, seed 0) max_project -> %dx%d, max_steps=200 (208 samples per hit ray); step j "
+        "workload": "Vol-G(%d, %s, seed 0) max_project -> %dx%d, max_steps=200 (208 samples per hit ray); step j "
                     "of rank r of N renders the sweep angle 360 (j / K + r / (K N)) degrees, K = steps: every rank's "
-                    "frames cover the 360-degree sweep evenly" % (args.vol, args.img, args.img),
+                    "frames cover the 360-degree sweep evenly" % (
+                        args.vol, "float32" if getattr(args, "dtype", "u16") == "f32" else "uint16", args.img, args.img),
         "camera": "perspective(60,1,.1,10), translate(0,0,-4) . rotation(theta + 1e-3, y)",
-        "window": "minVal 0, maxVal 60000, gamma 1, alpha_pow 0, box +-1, units 1",
+        "window": "minVal 0, maxVal %s, gamma 1, alpha_pow 0, box +-1, units 1" % (
+            "1" if getattr(args, "dtype", "u16") == "f32" else "60000"),
     }
 
 
@@ -212,7 +227,7 @@ def use_all_host_threads():
     return n
 
 
-def cpu_reference(vol, cams, img, steps, warmup, budget_s, alpha_pow=0.):
+def cpu_reference(vol, cams, img, steps, warmup, budget_s, alpha_pow=0., peak=PEAK_VALUE):
     """Time the reference kernels on the host cores.  -> dict(fps, gsamples, kind, cores, sample, ms_per_step)"""
     from oracle import oracle
     use_all_host_threads()
@@ -220,7 +235,7 @@ def cpu_reference(vol, cams, img, steps, warmup, budget_s, alpha_pow=0.):
     r = oracle.OracleRenderer((img, img), kind=kind, max_steps=MAX_STEPS)
     r.set_data(vol)
     r.set_projection(cams[0][1])
-    r.set_max_val(PEAK_VALUE)
+    r.set_max_val(peak)
     r.set_alpha_pow(alpha_pow)
     lib = r.lib
     cores = int(lib.so_num_threads())
@@ -262,14 +277,18 @@ def run_reference(args, rank):
     if rank != 0:
         return
     import scenes
-    vol = scenes.vol_g(args.vol, np.uint16, seed=0)
+    f32 = args.dtype == "f32"
+    vol = scenes.vol_g(args.vol, np.float32 if f32 else np.uint16, seed=0)
     cams = [scenes.gui_camera(th, 4.0) for th in sweep_thetas(args.steps, 0, max(1, args.gpus))]
-    res = cpu_reference(vol, cams, args.img, args.steps, args.warmup, 100.0)
+    res = cpu_reference(vol, cams, args.img, args.steps, args.warmup, 100.0, alpha_pow=args.alpha_pow,
+                        peak=1. if f32 else PEAK_VALUE)
     line = {
-        "impl": "reference", "metric": METRIC, "value": res["fps"], "unit": "frames/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": sweep_metric(args), "value": res["fps"], "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16->f32", "data": "synthetic",
-        "config": sweep_config(args),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if f32 else "u16->f32",
+        "data": "synthetic",
+        "config": dict(sweep_config(args), window=sweep_config(args)["window"].replace(
+            "alpha_pow 0", "alpha_pow %g" % args.alpha_pow)) if args.alpha_pow else sweep_config(args),
         "gsamples_per_s": res["gsamples"],
         "cpu_baseline": {"value": res["fps"], "unit": "frames/s", "cores": res["cores"], "kind": res["kind"],
                          "sample": res["sample"]},
@@ -539,15 +558,15 @@ def run_iso(args, rank, local_rank, world):
     # where the time of a sort-last frame goes (peer composite): device time per phase, statistics on, untimed
     phases = None
     if world > 1 and args.composite == "peer":
-        rend.enable_stats(True)
+        rend.time_phases(True)
         acc = {}
         for i in range(12):
             device_step(i)
             for k_, v_ in rend.last_phases_us().items():
                 acc.setdefault(k_, []).append(v_)
-        rend.enable_stats(False)
-        names = list(rend.PHASES)
-        pv = torch.tensor([float(np.mean(acc.get(k_, [0.])[2:])) for k_ in names], device="cuda", dtype=torch.float64)
+        rend.time_phases(False)
+        names = [k_ for k_ in rend.PHASES if len(acc.get(k_, [])) > 2]
+        pv = torch.tensor([float(np.mean(acc[k_][2:])) for k_ in names], device="cuda", dtype=torch.float64)
         pmax = pv.clone()
         dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(pv, op=dist.ReduceOp.SUM)
@@ -1261,7 +1280,9 @@ def run_sweep(args, rank, local_rank, world):
         bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    vol = scenes.vol_g(args.vol, np.uint16, seed=0)
+    f32 = args.dtype == "f32"
+    peak = 1. if f32 else PEAK_VALUE
+    vol = scenes.vol_g(args.vol, np.float32 if f32 else np.uint16, seed=0)
     K = args.steps
     thetas = sweep_thetas(K, rank, world)
     cams = [scenes.gui_camera(th, 4.0) for th in thetas]
@@ -1275,7 +1296,7 @@ def run_sweep(args, rank, local_rank, world):
     rend.set_data(vol)
     torch.cuda.synchronize()
     t_upload = time.perf_counter() - t0
-    rend.set_max_val(PEAK_VALUE)
+    rend.set_max_val(peak)
     rend.set_skipping(args.skip)
     rend.set_projection(cams[0][1])
     if args.mip_path is not None:
@@ -1288,7 +1309,7 @@ def run_sweep(args, rank, local_rank, world):
         mats.append((rend._invP.copy(), rend._invM.copy()))
     lib, ctx = rend._lib, rend._ctx
     rend.set_alpha_pow(args.alpha_pow)
-    params = _lib.MipParams(rend._box(), 0., PEAK_VALUE, 1., float(args.alpha_pow), 1, 0, MAX_STEPS, 0)
+    params = _lib.MipParams(rend._box(), 0., peak, 1., float(args.alpha_pow), 1, 0, MAX_STEPS, 0)
 
     def device_step(i):
         invP, invM = mats[i % K]
@@ -1426,13 +1447,15 @@ def run_sweep(args, rank, local_rank, world):
         tex_foot = wts.sum() / sum(w / r for w, r in zip(wts, foot))  # time-weighted: samples / sum(samples / rate)
         traffic, traffic_src = ncu_traffic("sweep_%d_%d" % (args.vol, W))
         kernel_name = rend.mip_kernel_name() if hasattr(rend, "mip_kernel_name") else "spv::mip_fast_kernel<u16, linear>"
-        metric = METRIC if not args.alpha_pow else METRIC + ", alpha_pow = %g" % args.alpha_pow
+        metric = sweep_metric(args)
+        if f32:
+            kernel_name = "spv::mip_fast_kernel<f32, linear>"
         if args.alpha_pow:
-            kernel_name = "spv::mip_alpha_kernel<u16, linear>"
+            kernel_name = "spv::mip_alpha_kernel<%s, linear>" % args.dtype
         line = {
             "metric": metric, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u16->f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32" if f32 else "u16->f32", "data": "synthetic",
             "config": sweep_config(args),
             "notes": {
                 "l2": "the %d MB volume exceeds the 126 MB L2 and the view changes every step" % (vol.nbytes >> 20),
@@ -1496,14 +1519,14 @@ def run_sweep(args, rank, local_rank, world):
             line["hit_rays_per_frame"] = None
         if world == 1 and not args.no_cpu_baseline:
             sub = cams[::max(1, K // 24)][:24]
-            res = cpu_reference(vol, sub, args.img, len(sub), 1, 20.0, alpha_pow=args.alpha_pow)
+            res = cpu_reference(vol, sub, args.img, len(sub), 1, 20.0, alpha_pow=args.alpha_pow, peak=peak)
             line["cpu_baseline"] = {"value": res["fps"], "unit": "frames/s", "cores": res["cores"],
                                     "kind": res["kind"], "sample": res["sample"],
                                     "gsamples_per_s": res["gsamples"]}
     rend.close()
     del rend
     torch.cuda.empty_cache()
-    if not args.no_c4 and not args.alpha_pow:
+    if not args.no_c4 and not args.alpha_pow and (args.vol, args.img, args.dtype) == (VOL_N, IMG, "u16"):
         rec = c4_record(args, rank, local_rank, world)
         if rank == 0:
             line["c4"] = rec

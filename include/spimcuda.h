@@ -292,7 +292,8 @@ SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
  * knob 10 = tiles of every 8 (fixed pattern) that the software-sampled max projection (spv_set_mip_path) hands to the
  * texture unit (hybrid; changes which sampler a pixel gets, deterministically), knob 11 = its box / ring geometry (0..4),
  * knob 12 = sort-last iso frames run the screen-space passes on the rank's own band of rows and exchange the finished
- * bands (1, default) or on the whole image on every rank (0). */
+ * bands (1) or on the whole image on every rank (0, default: the exchange costs more than the passes save), knob 13 = record CUDA events at the phase boundaries of
+ * sort-last iso frames (spv_last_phases_ms; off by default). */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 /* Which kernel family renders plain (alpha_pow == 0, num_parts == 1) max projections of uint16 volumes
  * (max_project_short, volume_kernel.cl:270-345):
@@ -318,7 +319,7 @@ SPV_API int spv_texrate_probe(spv_ctx *ctx, int iters, double *samples_per_s);
  * j = 0..15, with vec9 = {a, b, m} in texels (x, y, z).  All warps walk the same small region (every fetch hits L1):
  * the rate the texture unit can deliver for the ray and sample spacing of a given camera */
 SPV_API int spv_texrate_probe_footprint(spv_ctx *ctx, int iters, const float *vec9, double *samples_per_s);
-/* Device time of each phase of the last spv_render_iso_composite that ran with spv_enable_stats on, in order: search,
+/* Device time of each phase of the last spv_render_iso_composite that ran with spv_set_tuning(ctx, 13, 1), in order: search,
  * wait for the peers' candidates, MIN + redistribution, wait, resolve, wait, screen-space passes, band gather + wait
  * (the last one only with more than one rank).  *count = phases written. */
 SPV_API int spv_last_phases_ms(spv_ctx *ctx, float *ms, int n, int *count);

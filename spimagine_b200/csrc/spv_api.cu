@@ -106,7 +106,9 @@ struct spv_ctx {
   int mip_path = 0, last_mip_path = 0;
   cudaEvent_t ev_ph[9] = {nullptr};  // phase boundaries of the last sort-last iso frame (recorded while statistics are on)
   int n_ph = 0;
-  int iso_post_sharded = 1;  // tuning knob 12: sort-last iso frames run the screen-space passes on the rank's own band
+  int time_phases = 0;       // tuning knob 13: record the phase boundaries of sort-last iso frames (spv_last_phases_ms)
+  int iso_post_sharded = 0;  // tuning knob 12: sort-last iso frames run the screen-space passes on the rank's own band
+                             // (measured slower than every rank doing the whole image: profiles/r02_exp_iso_sortlast.txt)
   int smem_tex_of8 = 0;  // tuning knob 10: tiles (of every 8) the software-sampled kernel hands to the texture unit
   void *d_lin[3] = {nullptr, nullptr, nullptr};
   bool lin_valid = false;
@@ -859,6 +861,7 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   else if (knob == 9) ctx->clip_copies = value != 0;
   else if (knob == 10) ctx->smem_tex_of8 = value < 0 ? 0 : (value > 8 ? 8 : value);
   else if (knob == 12) ctx->iso_post_sharded = value != 0;
+  else if (knob == 13) ctx->time_phases = value != 0;
   else if (knob == 11) ctx->smem_cfg = value < 0 || value >= mip_smem_configs() ? 0 : value;
   else if (knob == 6) occ_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : value);  // process-wide
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
@@ -1584,7 +1587,7 @@ SPV_API int spv_render_iso_composite(spv_ctx *ctx, const spv_iso_params *p) {
   ctx->n_ph = 0;
 #define SPV_PHASE()                                                                  \
   do {                                                                               \
-    if (ctx->stats_on && ctx->n_ph < 9) {                                            \
+    if (ctx->time_phases && ctx->n_ph < 9) {                                            \
       if (!ctx->ev_ph[ctx->n_ph]) CU(cudaEventCreate(&ctx->ev_ph[ctx->n_ph]));       \
       CU(cudaEventRecord(ctx->ev_ph[ctx->n_ph++], ctx->stream));                     \
     }                                                                                \
@@ -1653,7 +1656,7 @@ SPV_API int spv_render_iso_composite(spv_ctx *ctx, const spv_iso_params *p) {
 #undef SPV_PHASE
 }
 
-// durations between the phase boundaries of the last spv_render_iso_composite that ran with statistics on:
+// durations between the phase boundaries of the last spv_render_iso_composite that ran with tuning knob 13 on:
 // search | wait for the candidates | MIN + redistribution | wait | resolve | wait | screen-space passes | band gather + wait
 SPV_API int spv_last_phases_ms(spv_ctx *ctx, float *ms, int n, int *count) {
   BIND();

@@ -360,8 +360,11 @@ class SlabMaxProjector(VolumeRenderer):
     PHASES = ("search", "wait_candidates", "min_redistribute", "wait_min", "resolve", "wait_resolve", "screen_passes",
               "band_gather_wait")
 
+    def time_phases(self, on=True):
+        self._check(self._lib.spv_set_tuning(self._ctx, 13, int(bool(on))))
+
     def last_phases_us(self):
-        """{phase: microseconds} of the last enqueue_iso_composite that ran with enable_stats(True)."""
+        """{phase: microseconds} of the last enqueue_iso_composite that ran with time_phases(True)."""
         ms = (C.c_float * 8)()
         n = C.c_int()
         self._check(self._lib.spv_last_phases_ms(self._ctx, ms, 8, C.byref(n)))

@@ -176,9 +176,10 @@ def test_sort_last_iso_surface_reports_a_halo_that_is_too_small():
         r.close()
 
 
+@pytest.mark.parametrize("sharded", [0, 1])
 @pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
 @pytest.mark.parametrize("dtype,maxval", [(np.uint16, 24000.), (np.float32, .5)])
-def test_peer_iso_composite_is_bit_exact_on_every_rank(world, dtype, maxval):
+def test_peer_iso_composite_is_bit_exact_on_every_rank(world, dtype, maxval, sharded):
     """spv_render_iso_composite: candidates pushed to the band owners, MIN + redistribution by the owners, finished
     pixels stored into every rank by the rank that owns the crossing -- no reduction on the host side.  Every rank
     ends up with the single-GPU render, frame after frame (the staging alternates by frame parity), also when
@@ -189,6 +190,8 @@ def test_peer_iso_composite_is_bit_exact_on_every_rank(world, dtype, maxval):
     size = (136, 104)
     rs = _iso_ranks(data, size, world, iso_halo(64), composite="peer")
     SlabMaxProjector.connect_local(rs)
+    for s in rs:  # knob 12: the screen-space passes on the rank's own band of rows + band gather, or on the whole image
+        s._check(s._lib.spv_set_tuning(s._ctx, 12, sharded))
     mono = VolumeRenderer(size)
     mono.set_data(data)
     for theta, skip, gamma in [(0.4, None, 1.), (1.9, False, 1.), (3.0, None, .8), (4.4, None, 1.)]:
