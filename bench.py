@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--c4-vol", type=int, default=2048)
     ap.add_argument("--c4-img", type=int, default=2048)
     ap.add_argument("--c4-steps", type=int, default=24)
+    ap.add_argument("--no-iso-overlap", action="store_true",
+                    help="iso workload, one GPU: every frame's screen-space passes on the render stream (as round 1)")
     ap.add_argument("--dtype", default="u16", choices=["u16", "f32"],
                     help="sweep workload: element type of the volume (f32 with --vol 128 --img 512 is BASELINE configs[0])")
     ap.add_argument("--alpha-pow", type=float, default=0.,
@@ -515,7 +517,13 @@ def run_iso(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if world == 1 and not args.no_iso_overlap:
+        # frames alternate between the two output slots; a frame's screen-space passes run beside the next frame's search
+        _lib.check(rend._lib.spv_set_tuning(rend._ctx, 14, 1), rend._ctx)
+
     def device_step(i):
+        if world == 1:
+            _lib.check(rend._lib.spv_select_slot(rend._ctx, i & 1), rend._ctx)
         rend.set_modelView(cams[i % NF][0])
         if world == 1:
             p = _lib.IsoParams(rend._box(), iso_max / 2, 1., MAX_STEPS, .1, 21, 30, 0)
@@ -536,9 +544,14 @@ def run_iso(args, rank, local_rank, world):
     e0.record()
     for i in range(args.steps):
         device_step(i)
+    if world == 1:
+        _lib.check(rend._lib.spv_stream_join(rend._ctx), rend._ctx)  # the last frames' passes, before the closing event
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    if world == 1:
+        _lib.check(rend._lib.spv_set_tuning(rend._ctx, 14, 0), rend._ctx)
+        _lib.check(rend._lib.spv_select_slot(rend._ctx, 0), rend._ctx)
     digest = hashlib.sha1()
     hit_px = 0
     for i in range(8):  # untimed: hash of everything the first frames produce (compared across GPU counts)
@@ -555,6 +568,18 @@ def run_iso(args, rank, local_rank, world):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
+    # one GPU: the same frames through render_sequence (output + alpha of every frame reach pinned host memory; frame
+    # i+1's search runs beside frame i's screen-space passes and read-back)
+    t_seq = None
+    if world == 1:
+        for r_ in rend.render_sequence((cams[i % NF][0] for i in range(6)), method="iso_surface", iso_planes=2):
+            pass
+        chk = 0.
+        t0 = time.perf_counter()
+        for r_ in rend.render_sequence((cams[i % NF][0] for i in range(args.steps)), method="iso_surface", iso_planes=2):
+            chk += float(r_.output[W // 2, W // 2])
+        torch.cuda.synchronize()
+        t_seq = time.perf_counter() - t0
     # where the time of a sort-last frame goes (peer composite): device time per phase, statistics on, untimed
     phases = None
     if world > 1 and args.composite == "peer":
@@ -609,6 +634,8 @@ def run_iso(args, rank, local_rank, world):
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_frame": alg,
                          "kernel": "spv::iso_fast_kernel<u16, linear, skip>" if world == 1 else "spv::iso_slab_search_kernel<u16, linear, skip>",
+                         "overlap": ("frames alternate between two output slots; a frame's screen-space passes run on a second "
+                                     "stream beside the next frame's search (tuning knob 14)") if world == 1 and not args.no_iso_overlap else None,
                          "note": "SURVEY 8d's algorithmic bytes count every voxel once; the search leaves cells that cannot hold "
                                  "a crossing in one step (exact hierarchical traversal), so the DRAM traffic is a few per cent of "
                                  "that and the fraction can exceed 1: this kernel is bound by the latency of its longest warps "
@@ -627,8 +654,18 @@ def run_iso(args, rank, local_rank, world):
                     "peer memory (candidates pushed to the band owners, MIN + redistribution by the owners, finished "
                     "pixels stored into every rank by the crossing's owner; arrival counters, no NCCL on the data path)"
                     if args.composite == "peer" else "NCCL (MIN int32 2 planes, SUM float32 7 planes)")))},
-            "e2e": {"value": args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 2 * W * W * 4,
-                    "note": "set_modelView + render(method='iso_surface'): output + alpha read back per frame (8 MiB); depth, normals and occlusion stay on the device until they are looked at (lazy attributes)"},
+            "e2e": ({"value": args.steps / t_seq, "unit": "frames/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 2 * W * W * 4,
+                     "note": "VolumeRenderer.render_sequence(modelViews, method='iso_surface', iso_planes=2): output + alpha of "
+                             "every frame reach pinned host memory (8 MiB per frame); two frames in flight"}
+                    if t_seq else
+                    {"value": args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 2 * W * W * 4,
+                     "note": "SlabMaxProjector.set_modelView + render(method='iso_surface') on every rank: output + alpha read "
+                             "back per frame (8 MiB)"}),
+            "e2e_synchronous": {"value": args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128,
+                                "d2h_bytes_per_step": 2 * W * W * 4,
+                                "note": "set_modelView + render(method='iso_surface'), blocking per frame: output + alpha read "
+                                        "back (8 MiB); depth, normals and occlusion stay on the device until they are looked "
+                                        "at (lazy attributes)"},
             "surface_pixels_last": hit_px, "image_sha1_first8": digest.hexdigest(),
             # iso_fast, blur, occlusion list + queue, blur, shading; sort-last: search, resolve, fix-up, 2+2 blur
             # launches, occlusion list + queue, shading (the two NCCL reductions are not counted)

@@ -293,7 +293,10 @@ SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
  * texture unit (hybrid; changes which sampler a pixel gets, deterministically), knob 11 = its box / ring geometry (0..4),
  * knob 12 = sort-last iso frames run the screen-space passes on the rank's own band of rows and exchange the finished
  * bands (1) or on the whole image on every rank (0, default: the exchange costs more than the passes save), knob 13 = record CUDA events at the phase boundaries of
- * sort-last iso frames (spv_last_phases_ms; off by default). */
+ * sort-last iso frames (spv_last_phases_ms; off by default), knob 14 = device-only iso-surface renders (spv_render_iso) put
+ * their screen-space passes on a second stream, so that the search of the next frame -- rendered into the other output
+ * slot, spv_select_slot -- runs beside them; reads through this library wait for the passes by themselves, a caller that
+ * takes spv_device_ptr must call spv_stream_join or spv_sync first (off by default; render_sequence switches it on). */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 /* Which kernel family renders plain (alpha_pow == 0, num_parts == 1) max projections of uint16 volumes
  * (max_project_short, volume_kernel.cl:270-345):
@@ -305,6 +308,8 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
  * Both are within north_star's 1e-3 of the OpenCL sampler; they differ from each other by the texture unit's 8-bit weight
  * quantisation.  spv_mip_path_used reports what the last max projection ran on. */
 enum { SPV_MIP_PATH_TMU = 0, SPV_MIP_PATH_SMEM = 1 };
+/* the render stream waits for screen-space passes running beside it (tuning knob 14); asynchronous */
+SPV_API int spv_stream_join(spv_ctx *ctx);
 SPV_API int spv_set_mip_path(spv_ctx *ctx, int path);
 SPV_API int spv_mip_path_used(spv_ctx *ctx, int *path);
 SPV_API const char *spv_last_error(spv_ctx *ctx);                   /* ctx may be NULL: last create error */

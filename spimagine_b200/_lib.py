@@ -104,6 +104,7 @@ SIGNATURES = {
     "spv_launch_count": (C.c_int, [_CTX, C.POINTER(C.c_ulonglong)]),
     "spv_d2h_bytes": (C.c_int, [_CTX, C.POINTER(C.c_ulonglong)]),
     "spv_last_phases_ms": (C.c_int, [_CTX, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
+    "spv_stream_join": (C.c_int, [_CTX]),
     "spv_set_mip_path": (C.c_int, [_CTX, C.c_int]),
     "spv_mip_path_used": (C.c_int, [_CTX, C.POINTER(C.c_int)]),
     "spv_update_volume_device_from": (C.c_int, [_CTX, C.c_void_p, C.c_int]),

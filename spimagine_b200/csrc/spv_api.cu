@@ -106,6 +106,13 @@ struct spv_ctx {
   int mip_path = 0, last_mip_path = 0;
   cudaEvent_t ev_ph[9] = {nullptr};  // phase boundaries of the last sort-last iso frame (recorded while statistics are on)
   int n_ph = 0;
+  // iso surface: the screen-space passes of the frame in one output slot may run on post_stream while the search of
+  // the next frame (other slot) runs on `stream` (tuning knob 14); tile flags per slot
+  int iso_overlap = 0;
+  cudaStream_t post_stream = nullptr;
+  cudaEvent_t ev_searched[2] = {nullptr, nullptr}, ev_posted[2] = {nullptr, nullptr};
+  bool post_pending[2] = {false, false};
+  unsigned char *d_tile_hit_s[2] = {nullptr, nullptr};
   int time_phases = 0;       // tuning knob 13: record the phase boundaries of sort-last iso frames (spv_last_phases_ms)
   int iso_post_sharded = 0;  // tuning knob 12: sort-last iso frames run the screen-space passes on the rank's own band
                              // (measured slower than every rank doing the whole image: profiles/r02_exp_iso_sortlast.txt)
@@ -186,8 +193,12 @@ static void free_buffers(spv_ctx *c) {
     c->hpin_s[s] = nullptr;
     c->copy_pending[s] = false;
   }
+  if (c->post_stream) cudaStreamSynchronize(c->post_stream);
+  c->post_pending[0] = c->post_pending[1] = false;
   if (c->d_tile_hit) cudaFree(c->d_tile_hit);
   c->d_tile_hit = nullptr;
+  if (c->d_tile_hit_s[1]) cudaFree(c->d_tile_hit_s[1]);
+  c->d_tile_hit_s[0] = c->d_tile_hit_s[1] = nullptr;
   if (c->d_occ_queue) cudaFree(c->d_occ_queue);
   c->d_occ_queue = nullptr;
   if (c->d_rgba) cudaFree(c->d_rgba);
@@ -274,6 +285,8 @@ static int alloc_buffers(spv_ctx *ctx, int w, int h) {
   ctx->dbuf = ctx->dbuf_s[0];
   ctx->hpin = ctx->hpin_s[0];
   CU(cudaMalloc(&ctx->d_tile_hit, (size_t)((w + 7) / 8) * ((h + 3) / 4)));  // one flag per 8x4 warp tile
+  CU(cudaMalloc(&ctx->d_tile_hit_s[1], (size_t)((w + 7) / 8) * ((h + 3) / 4)));  // slot 1's flags (iso overlap)
+  ctx->d_tile_hit_s[0] = ctx->d_tile_hit;
   CU(cudaMalloc(&ctx->d_occ_queue, occ_queue_bytes(w, h)));
   CU(cudaMemsetAsync(ctx->d_occ_queue, 0, occ_queue_bytes(w, h), ctx->stream));
   return 0;
@@ -312,6 +325,7 @@ SPV_API int spv_create(int device, int width, int height, spv_ctx **out) {
   CC(cudaEventCreate(&ctx->ev1));
   CC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   CC(cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
+  CC(cudaStreamCreateWithFlags(&ctx->post_stream, cudaStreamNonBlocking));
   CC(cudaEventCreateWithFlags(&ctx->ev_copy2, cudaEventDisableTiming));
   CC(cudaEventCreateWithFlags(&ctx->ev_up_begin, cudaEventDisableTiming));
   for (int s = 0; s < 2; ++s) {
@@ -319,6 +333,8 @@ SPV_API int spv_create(int device, int width, int height, spv_ctx **out) {
     CC(cudaEventCreateWithFlags(&ctx->ev_copied[s], cudaEventDisableTiming));
     CC(cudaEventCreateWithFlags(&ctx->ev_h2d_done[s], cudaEventDisableTiming));
     CC(cudaEventCreateWithFlags(&ctx->ev_consumed[s], cudaEventDisableTiming));
+    CC(cudaEventCreateWithFlags(&ctx->ev_searched[s], cudaEventDisableTiming));
+    CC(cudaEventCreateWithFlags(&ctx->ev_posted[s], cudaEventDisableTiming));
   }
   CC(cudaMalloc(&ctx->d_minmax, 2 * sizeof(float)));
   CC(cudaMalloc(&ctx->d_stats, 40 * sizeof(unsigned long long)));
@@ -342,6 +358,7 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->post_stream) cudaStreamSynchronize(ctx->post_stream);
   free_volume(ctx);
   free_buffers(ctx);
   if (ctx->d_minmax) cudaFree(ctx->d_minmax);
@@ -361,7 +378,10 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
     if (ctx->ev_copied[s]) cudaEventDestroy(ctx->ev_copied[s]);
     if (ctx->ev_h2d_done[s]) cudaEventDestroy(ctx->ev_h2d_done[s]);
     if (ctx->ev_consumed[s]) cudaEventDestroy(ctx->ev_consumed[s]);
+    if (ctx->ev_searched[s]) cudaEventDestroy(ctx->ev_searched[s]);
+    if (ctx->ev_posted[s]) cudaEventDestroy(ctx->ev_posted[s]);
   }
+  if (ctx->post_stream) cudaStreamDestroy(ctx->post_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
   if (ctx->ev_copy2) cudaEventDestroy(ctx->ev_copy2);
@@ -394,8 +414,27 @@ SPV_API int spv_share_stream(spv_ctx *ctx, spv_ctx *other) {
 SPV_API int spv_sync(spv_ctx *ctx) {
   BIND();
   CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->post_stream));
   CU(cudaStreamSynchronize(ctx->copy_stream));
+  ctx->post_pending[0] = ctx->post_pending[1] = false;
   return 0;
+}
+
+// the render stream waits for the screen-space passes that run beside it (iso overlap): whatever is enqueued on the
+// render stream next sees finished planes in slot s (s < 0: both slots)
+static int join_post(spv_ctx *ctx, int s) {
+  for (int k = 0; k < 2; ++k)
+    if ((s < 0 || s == k) && ctx->post_pending[k]) {
+      CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_posted[k], 0));
+      ctx->post_pending[k] = false;
+    }
+  return 0;
+}
+
+
+SPV_API int spv_stream_join(spv_ctx *ctx) {
+  BIND();
+  return join_post(ctx, -1);
 }
 
 static size_t elem_size(int dtype) { return dtype == SPV_F32 ? 4 : (dtype == SPV_U16 ? 2 : 1); }
@@ -862,6 +901,13 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   else if (knob == 10) ctx->smem_tex_of8 = value < 0 ? 0 : (value > 8 ? 8 : value);
   else if (knob == 12) ctx->iso_post_sharded = value != 0;
   else if (knob == 13) ctx->time_phases = value != 0;
+  else if (knob == 14) {
+    if (!value && ctx->iso_overlap) {  // switching off joins what is in flight
+      cudaSetDevice(ctx->device);
+      join_post(ctx, -1);
+    }
+    ctx->iso_overlap = value != 0;
+  }
   else if (knob == 11) ctx->smem_cfg = value < 0 || value >= mip_smem_configs() ? 0 : value;
   else if (knob == 6) occ_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : value);  // process-wide
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
@@ -1035,6 +1081,8 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
   rc = begin_render(ctx);
   if (rc) return rc;
   const int s = ctx->slot;
+  rc = join_post(ctx, s);  // an iso frame's screen-space passes may still be writing this slot beside the render stream
+  if (rc) return rc;
   if (to_host && ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // staging about to be rewritten
   const int H = ctx->height;
   const bool direct = to_host && ctx->direct_host && plain && p->num_parts == 1 && !raw_only;
@@ -1337,6 +1385,7 @@ static int ensure_taps(spv_ctx *ctx, int n) {
   int cap = 64;
   while (cap < n) cap *= 2;
   CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->post_stream));
   if (ctx->d_taps) cudaFree(ctx->d_taps);
   ctx->d_taps = nullptr;
   ctx->taps_n = 0;
@@ -1376,7 +1425,7 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   a.segments = ctx->iso_segments;
   a.centre_out = ctx->iso_centre_out;
   const bool exact_iso = ctx->sampler == SPV_SAMPLER_EXACT;
-  a.tile_hit = exact_iso ? nullptr : ctx->d_tile_hit;
+  a.tile_hit = exact_iso ? nullptr : ctx->d_tile_hit_s[ctx->slot];
   a.skip = ctx->skipping != 0;  // auto (-1) = on: for iso surfaces the brick test is nearly free and exact
   if (a.skip && ctx->sampler != SPV_SAMPLER_EXACT) {
     int rcb = ensure_bricks(ctx);
@@ -1394,10 +1443,25 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   if (rc) return rc;
   const int s = ctx->slot;
   const size_t n = ctx->n();
+  // overlap (tuning knob 14): this frame's screen-space passes go to post_stream, so that the NEXT frame's search (other
+  // slot, render stream) runs beside them -- the search leaves a third of the SM time idle in its tail, the passes are
+  // five small launches.  Only for device-only renders; whoever reads the planes joins (spv_read*, spv_stream_join,
+  // spv_sync).  (Putting every other frame's search on a stream of its own as well was measured: no further gain.)
+  const bool overlap = ctx->iso_overlap && post && !to_host && !ctx->stats_on;
+  rc = join_post(ctx, s);  // the passes of the frame that used this slot last may still be running
+  if (rc) return rc;
   if (to_host && ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // staging about to be rewritten
   if (to_host) staging_dirty(ctx, s);
   CU(launch_iso(a, fmt_of(ctx), linear, ctx->sampler == SPV_SAMPLER_EXACT, ctx->stats_on != 0, ctx->stream));
   ctx->launches += 1;
+  cudaStream_t pst = ctx->stream;
+  if (overlap) {
+    // one set of scratch (occlusion queue; tmp planes are per slot, taps constant): the passes of successive frames
+    // run in order on post_stream; they start when this frame's search is done
+    CU(cudaEventRecord(ctx->ev_searched[s], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->post_stream, ctx->ev_searched[s], 0));
+    pst = ctx->post_stream;
+  }
   if (to_host && post) {
     CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
     CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
@@ -1406,15 +1470,18 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   }
   if (post) {
     // volumerender.py:470-497
-    CU(launch_conv_xy(ctx->tmp_vec(), ctx->normals(), ctx->width, ctx->height, 3, conv_weights(7, -5.f), a.tile_hit, 0,
-                      ctx->stream));
+    CU(launch_conv_xy(ctx->tmp_vec(), ctx->normals(), ctx->width, ctx->height, 3, conv_weights(7, -5.f), a.tile_hit, 0, pst));
     CU(launch_occlusion(ctx->tmp(), ctx->width, ctx->height, p->occ_radius, p->occ_n_points, ctx->depth(), a.tile_hit,
-                        ctx->d_taps, ctx->d_occ_queue, ctx->occ_frame++, ctx->sms, ctx->stream));
+                        ctx->d_taps, ctx->d_occ_queue, ctx->occ_frame++, ctx->sms, pst));
     CU(launch_conv_xy(ctx->tmp(), ctx->occ(), ctx->width, ctx->height, 1, conv_weights(5, -10.f), a.tile_hit,
-                      p->occ_radius, ctx->stream));
+                      p->occ_radius, pst));
     CU(launch_shading(ctx->out(), ctx->width, ctx->height, ctx->cam, p->occ_strength, ctx->normals(), ctx->depth(),
-                      ctx->occ(), ctx->stream));
+                      ctx->occ(), pst));
     ctx->launches += a.tile_hit ? 5 : 4;
+    if (overlap) {
+      CU(cudaEventRecord(ctx->ev_posted[s], ctx->post_stream));
+      ctx->post_pending[s] = true;
+    }
   }
   ctx->last_method = 1;
   rc = end_render(ctx);
@@ -1688,6 +1755,8 @@ SPV_API int spv_read(spv_ctx *ctx, int which, float *host_dst, size_t n) {
   float *src = buf_of(ctx, which, &count);
   if (!src || !host_dst) return fail(ctx, SPV_EINVAL, "spv_read: bad buffer id or null destination");
   if (n != count) return fail(ctx, SPV_EINVAL, "spv_read: element count does not match the buffer");
+  int rcj = join_post(ctx, ctx->slot);
+  if (rcj) return rcj;
   CU(cudaMemcpyAsync(host_dst, src, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   ctx->d2h_bytes += n * sizeof(float);
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1700,6 +1769,8 @@ SPV_API int spv_read_many(spv_ctx *ctx, float *out, float *alpha, float *depth, 
   // [out | alpha | depth | occ | normals]: MIP wrote the first two planes, iso all seven
   const size_t planes = (depth || normals || occ) ? 7 : 2;
   staging_dirty(ctx, ctx->slot);
+  int rcj = join_post(ctx, ctx->slot);
+  if (rcj) return rcj;
   CU(cudaMemcpyAsync(ctx->hpin, ctx->dbuf, planes * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   ctx->d2h_bytes += planes * n * sizeof(float);
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1716,6 +1787,8 @@ SPV_API int spv_read_pinned(spv_ctx *ctx, int planes, float **host) {
   if (planes < 1 || planes > 7 || !host) return fail(ctx, SPV_EINVAL, "spv_read_pinned: planes must be 1..7");
   if (ctx->copy_pending[ctx->slot]) CU(cudaEventSynchronize(ctx->ev_copied[ctx->slot]));  // same staging memory
   staging_dirty(ctx, ctx->slot);
+  int rcj = join_post(ctx, ctx->slot);
+  if (rcj) return rcj;
   CU(cudaMemcpyAsync(ctx->hpin, ctx->dbuf, (size_t)planes * ctx->n() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   ctx->d2h_bytes += (size_t)planes * ctx->n() * sizeof(float);
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1745,6 +1818,9 @@ SPV_API int spv_read_pinned_async(spv_ctx *ctx, int planes) {
   staging_dirty(ctx, s);
   CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
   CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
+  // iso overlap: the slot's screen-space passes run beside the render stream; the copy waits for them, the render
+  // stream (and with it the next frame's search) does not
+  if (ctx->post_pending[s]) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_posted[s], 0));
   CU(cudaMemcpyAsync(ctx->hpin_s[s], ctx->dbuf_s[s], (size_t)planes * ctx->n() * sizeof(float), cudaMemcpyDeviceToHost,
                      ctx->copy_stream));
   ctx->d2h_bytes += (size_t)planes * ctx->n() * sizeof(float);
@@ -1787,6 +1863,8 @@ SPV_API int spv_read_rgba8(spv_ctx *ctx, int mode_black, unsigned char *host_dst
     CU(cudaMalloc(&ctx->d_rgba, 4 * n));
     CU(cudaMallocHost(&ctx->h_rgba, 4 * n));
   }
+  int rcj = join_post(ctx, ctx->slot);
+  if (rcj) return rcj;
   CU(launch_display(ctx->out(), ctx->alpha(), ctx->d_lut, ctx->n_lut, mode_black != 0, ctx->d_rgba, n, ctx->stream));
   ctx->launches += 1;
   CU(cudaMemcpyAsync(ctx->h_rgba, ctx->d_rgba, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));

@@ -553,6 +553,9 @@ class VolumeRenderer(object):
         self._fetch_iso_extras()  # a deferred read-back of an earlier render() happens before the slots are reused
         pending = []  # slots in flight, oldest first
         i = 0
+        if method == "iso_surface":
+            # frame i's screen-space passes run on a second stream beside frame i+1's search (tuning knob 14)
+            self._check(self._lib.spv_set_tuning(self._ctx, 14, 1))
         try:
             for M in modelViews:
                 slot = i & 1
@@ -576,6 +579,7 @@ class VolumeRenderer(object):
                 self._adopt_slot(pending.pop(0), planes, clear)
                 yield self
         finally:
+            self._lib.spv_set_tuning(self._ctx, 14, 0)
             self._lib.spv_sync(self._ctx)
             self._lib.spv_select_slot(self._ctx, 0)
 

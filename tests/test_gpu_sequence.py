@@ -473,3 +473,48 @@ def test_rows_that_cannot_hold_hits_are_not_copied_but_read_the_same(dtype):
     finally:
         a.close()
         b.close()
+
+
+def test_iso_sequence_with_a_new_volume_between_frames():
+    """render_sequence(method="iso_surface") runs a frame's screen-space passes and every other frame's search on
+    streams of their own (tuning knob 14); an update_data issued from the generator between two frames must not reach
+    the array while a search on the second stream is still reading it, and a max projection right after the sequence
+    must see finished slots.  Every frame equals the frame-by-frame render."""
+    vols = [scenes.vol_g(0, np.uint16, seed=s, shape=(72, 80, 88)) for s in (1, 2, 3)]
+    cams = [scenes.gui_camera(0.25 * f, 3.2) for f in range(9)]
+    rend = _renderer((192, 160))
+    rend.set_data(vols[0])
+    rend.set_projection(cams[0][1])
+    rend.set_max_val(24000.)
+    want = []
+    for f, (M, _) in enumerate(cams):
+        if f % 2 == 0:
+            rend.update_data(vols[(f // 2) % 3])
+        rend.set_modelView(M)
+        rend.render(method="iso_surface")
+        want.append([x.copy() for x in (rend.output, rend.output_alpha, rend.output_depth, rend.output_normals,
+                                        rend.output_occlusion)])
+
+    def views():
+        for f, (M, _) in enumerate(cams):
+            if f % 2 == 0:
+                rend.update_data(vols[(f // 2) % 3])
+            yield M
+
+    for rep in range(2):
+        k = 0
+        for r in rend.render_sequence(views(), method="iso_surface"):
+            got = (r.output, r.output_alpha, r.output_depth, r.output_normals, r.output_occlusion)
+            for g, w in zip(got, want[k]):
+                assert np.array_equal(g, w), (rep, k)
+            k += 1
+        assert k == len(cams)
+        rend.update_data(vols[0])
+        rend.set_modelView(cams[0][0])
+        rend.render()                       # a max projection into slot 0 right behind the sequence
+        mip = rend.output.copy()
+        rend.render(method="iso_surface")
+        assert np.array_equal(rend.output, want[0][0]) and np.array_equal(rend.output_depth, want[0][2])
+        rend.render()
+        assert np.array_equal(rend.output, mip)
+    rend.close()
