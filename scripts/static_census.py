@@ -56,8 +56,8 @@ def resources(tag):
 def census(tag):
     txt = subprocess.run(["cuobjdump", "-sass", b.LIB], capture_output=True, text=True, check=True).stdout
     funcs = re.split(r"\n\s*Function : ", txt)[1:]
-    cols = ["TEX", "TLD", "LDG.E.128", "STG.E.128", "STG.E.64", "LDS", "STS", "SHFL", "VOTE", "ATOM", "RED", "BAR", "FFMA",
-            "FMNMX", "MUFU"]
+    cols = ["TEX", "TLD", "UTMALDG", "SYNCS", "LDG.E.128", "STG.E.128", "STG.E.64", "LDS", "STS", "SHFL", "VOTE", "ATOM", "RED",
+            "BAR", "FFMA", "FMNMX", "MUFU"]
     stats, count = collections.defaultdict(collections.Counter), collections.Counter()
     for f, n in zip(funcs, demangle([f.split("\n", 1)[0].strip() for f in funcs])):
         k = base(n)
@@ -70,7 +70,8 @@ def census(tag):
                     break
     out = ["SASS mnemonic census of spimagine_b200/libspimcuda.so (cuobjdump -sass, sm_100a), summed over the instantiations of",
            "each kernel template: what the kernels are made of.  TEX = filtered texture fetches (the hardware trilinear /",
-           "bilinear sampler), TLD = unfiltered texel loads, STG.E.128 = 128-bit stores, SHFL / VOTE = warp-level exchange.",
+           "bilinear sampler), TLD = unfiltered texel loads, UTMALDG = TMA tensor loads (cp.async.bulk.tensor), SYNCS = mbarrier",
+           "operations (init / arrive / expect_tx / try_wait), STG.E.128 = 128-bit stores, SHFL / VOTE = warp-level exchange.",
            "scripts/static_census.py", "",
            "%-28s %5s %8s " % ("kernel", "inst.", "SASS") + " ".join("%9s" % c for c in cols)]
     for k in sorted(stats):
