@@ -451,3 +451,100 @@ def test_attenuated_c2_against_oracle_rows(c2_volume, oracle_mod):
     finally:
         o.lib.so_set_row_sampling(0, 1)
         g.close()
+
+
+# ----------------------------------------------------------------------------- configs[3] and configs[4] at their own sizes
+def test_c4_full_size_sort_last_against_oracle_rows(oracle_mod):
+    """configs[3] itself: Vol-G(2048, uint16, seed 2) as `bench.py` generates it (16 GiB), 2048^2 image, four z-slabs in one
+    process composited over peer memory -- against the oracle on every 128th row (the oracle reads the volume from host
+    memory: 16 GiB) and against the image hash the bench lines carry for 1, 2 and 8 GPUs."""
+    import hashlib
+    import torch
+    import bench
+    from spimagine_b200.multigpu import SlabMaxProjector, partition_slabs, slab_with_halo
+    N, W, world = 2048, 2048, 4
+    dev = torch.device("cuda", 0)
+    import psutil
+    if torch.cuda.mem_get_info(0)[0] < 90e9 or psutil.virtual_memory().available < 40e9:
+        pytest.skip("needs ~80 GB of device memory and 16 GiB of host memory for the oracle's copy of the volume")
+    host = np.empty((N, N, N), np.uint16)
+    rs = []
+    for rank, (z0, z1) in enumerate(partition_slabs(N, world)):
+        lo, hi = slab_with_halo(z0, z1, N)
+        d = bench.vol_g_slab_device(N, lo, hi, 2, dev)
+        host[lo:hi] = d.cpu().numpy()
+        s = SlabMaxProjector((W, W), rank=rank, world=world, composite="peer", max_steps=200)
+        s.set_slab((np.uint16, N, N), N, z0, z1, device_ptr=d.data_ptr())
+        s.sync()
+        del d
+        torch.cuda.empty_cache()
+        rs.append(s)
+    SlabMaxProjector.connect_local(rs)
+    o = oracle_mod.OracleRenderer((W, W), kind="port")
+    o.set_data(host)
+    rows = slice(0, W, 128)
+    digest = hashlib.sha1()
+    try:
+        for i in range(8):   # the frames bench.py hashes: sweep angles (i * 7) mod 360 degrees
+            M, P = scenes.gui_camera(2 * math.pi * ((i * 7) % 360) / 360, 4.0)
+            for s in rs:
+                s.set_projection(P)
+                s.set_modelView(M)
+                s.set_max_val(60000.)
+                s.enqueue_composite()
+            for s in rs:
+                s.collect()
+            digest.update(rs[0].output.tobytes())
+            if i in (0, 5):
+                o.set_modelView(M)
+                o.set_projection(P)
+                o.lib.so_set_row_sampling(0, 128)
+                o.render(maxVal=60000.)
+                err = float(np.abs(rs[0].output[rows] - o.output[rows]).max())
+                print("C4 frame %d: max |gpu - oracle| on every 128th row = %.3g" % (i, err))
+                assert err < 1e-3
+                assert np.array_equal(rs[0].output_alpha[rows], o.output_alpha[rows])
+                assert (rs[0].output_alpha[rows] > 0).mean() > 0.2
+        # the hash `bench.py --workload slab` / the `c4` record print for this volume on 1, 2 and 8 GPUs
+        assert digest.hexdigest() == "172c0890e4a3fd69f3bf6672e57932efd830dd62"
+    finally:
+        o.lib.so_set_row_sampling(0, 1)
+        for s in rs:
+            s.close()
+
+
+def test_c5_time_point_against_oracle_rows(oracle_mod):
+    """configs[4]: one 512 x 1024 x 1024 uint16 time point as `bench.py --workload timelapse` generates it, voxel size
+    (1, 1, 2), -> 1024^2; every 32nd row against the oracle at two views of the slow spin."""
+    import torch
+    import bench
+    shape = (512, 1024, 1024)
+    d = bench.vol_g_device(shape, 100, 7, torch.device("cuda", 0))
+    vol = d.cpu().numpy()
+    g = _renderer((1024, 1024), max_steps=200)
+    g.set_data_device(d.data_ptr(), shape, np.uint16)
+    g.sync()
+    del d
+    torch.cuda.empty_cache()
+    o = oracle_mod.OracleRenderer((1024, 1024), kind="port")
+    o.set_data(vol)
+    rows = slice(0, 1024, 32)
+    try:
+        for f in (3, 200):
+            M, P = scenes.gui_camera(2 * math.pi * f / 720, 4.0)
+            for r in (g, o):
+                r.set_units([1., 1., 2.])
+                r.set_projection(P)
+                r.set_modelView(M)
+                r.set_max_val(60000.)
+            o.lib.so_set_row_sampling(0, 32)
+            o.render()
+            g.render()
+            err = float(np.abs(g.output[rows] - o.output[rows]).max())
+            print("C5 frame %d: max |gpu - oracle| = %.3g" % (f, err))
+            assert err < 1e-3
+            assert np.array_equal(g.output_alpha[rows], o.output_alpha[rows])
+            assert (g.output_alpha[rows] > 0).mean() > 0.2
+    finally:
+        o.lib.so_set_row_sampling(0, 1)
+        g.close()
