@@ -234,7 +234,10 @@ def cpu_reference(vol, cams, img, steps, warmup, budget_s, alpha_pow=0., peak=PE
     from oracle import oracle
     use_all_host_threads()
     kind = "reference" if oracle.available("reference") else "port"
-    r = oracle.OracleRenderer((img, img), kind=kind, max_steps=MAX_STEPS)
+    # timing: the reference's text with the host equivalents of its OpenCL build options (-cl-fast-relaxed-math,
+    # -cl-mad-enable: -O3 -ffast-math -mavx2 -mfma) where that build exists and the CPU can run it
+    build = "reference_fast" if kind == "reference" and oracle.available("reference_fast") and oracle.cpu_has_avx2() else kind
+    r = oracle.OracleRenderer((img, img), kind=build, max_steps=MAX_STEPS)
     r.set_data(vol)
     r.set_projection(cams[0][1])
     r.set_max_val(peak)
@@ -267,8 +270,9 @@ def cpu_reference(vol, cams, img, steps, warmup, budget_s, alpha_pow=0., peak=PE
     fps = frames / dt
     sample = "%d steps, each every %d-th row of one %dx%d frame of the sweep (1/%d of its rays); %s on %d threads" % (
         steps, rowstep, img, img, rowstep,
-        "reference kernel text built for the host (oracle/_ref)" if kind == "reference" else
-        "C restatement of the reference kernels (oracle/)", cores)
+        ("reference kernel text built for the host with the reference's fast-math options (oracle/_ref, -O3 -ffast-math "
+         "-mavx2 -mfma)" if build == "reference_fast" else "reference kernel text built for the host (oracle/_ref, -O2)")
+        if kind == "reference" else "C restatement of the reference kernels (oracle/)", cores)
     return {"fps": fps, "gsamples": fps * mean_hits * SAMPLES_PER_RAY / 1e9, "kind": kind, "cores": cores,
             "sample": sample, "ms_per_step": 1e3 * dt / steps, "seconds": dt}
 
@@ -613,8 +617,9 @@ def run_iso(args, rank, local_rank, world):
             from oracle import oracle
             use_all_host_threads()
             kind = "reference" if oracle.available("reference") else "port"
+            build = "reference_fast" if kind == "reference" and oracle.available("reference_fast") and oracle.cpu_has_avx2() else kind
             host_vol = vol_g_slab_device(N, 0, N, 1, dev).cpu().numpy()
-            o = oracle.OracleRenderer((W, W), kind=kind, max_steps=MAX_STEPS)
+            o = oracle.OracleRenderer((W, W), kind=build, max_steps=MAX_STEPS)
             o.set_data(host_vol)
             o.set_projection(cams[0][1])
             o.set_max_val(iso_max)
@@ -627,7 +632,9 @@ def run_iso(args, rank, local_rank, world):
                 o.render(method="iso_surface")
             t_cpu = (time.perf_counter() - t0) / nf
             cpu = {"value": 1. / t_cpu, "unit": "frames/s", "cores": int(o.lib.so_num_threads()), "kind": kind,
-                   "sample": "%d whole frames of the sweep (every 6th), iso_surface + blur + occlusion + blur + shading" % nf}
+                   "sample": "%d whole frames of the sweep (every 6th), iso_surface + blur + occlusion + blur + shading; %s" % (
+                       nf, "reference kernel text, -O3 -ffast-math -mavx2 -mfma (the reference's fast-math options)"
+                       if build == "reference_fast" else "-O2")}
             del host_vol, o
         line_extra = {
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s (per GPU)",

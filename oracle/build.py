@@ -5,6 +5,12 @@
   oracle/_ref/libspim_ref.so    the REFERENCE's own kernel text compiled for the host,
                                 built only where /root/reference exists (the dev
                                 container); git-ignored, but it travels to the GPU box
+  oracle/_ref/libspim_ref_fast.so   the same text with the host equivalents of the
+                                reference's OpenCL build options (volumerender.py:
+                                154-160: -cl-fast-relaxed-math, -cl-mad-enable, ...:
+                                -O3 -ffast-math -mavx2 -mfma).  TIMING ONLY (bench.py's
+                                reference arm and cpu_baseline): its pixels are not
+                                used for parity, fast-math changes them
 
 The reference build never copies reference sources into the repo: the .cl files are
 read where they lie, passed through one syntax rewrite that OpenCL C needs to be valid
@@ -55,11 +61,15 @@ def reference_translation_unit():
     return "".join(parts)
 
 
-def build_ref(force=False):
-    """Returns the path of libspim_ref.so, or None when the reference tree is absent
+FAST_CFLAGS = ["-O3", "-fopenmp", "-ffast-math", "-mavx2", "-mfma", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall",
+               "-Wno-unknown-pragmas", "-Wno-unused"]
+
+
+def build_ref(force=False, fast=False):
+    """Returns the path of libspim_ref.so (fast=True: libspim_ref_fast.so), or None when the reference tree is absent
     (then a previously built copy, if any, is used as is)."""
     outdir = os.path.join(HERE, "_ref")
-    out = os.path.join(outdir, "libspim_ref.so")
+    out = os.path.join(outdir, "libspim_ref_fast.so" if fast else "libspim_ref.so")
     if not os.path.isdir(REF_KERNELS):
         return out if os.path.exists(out) else None
     deps = [os.path.join(HERE, "ocl_shim.hpp"), os.path.join(HERE, "ref_driver.inc")] + \
@@ -68,7 +78,8 @@ def build_ref(force=False):
         return out
     os.makedirs(outdir, exist_ok=True)
     tu = reference_translation_unit()
-    cmd = ["g++", "-std=gnu++17", "-x", "c++", "-"] + CFLAGS + ["-Wno-narrowing", "-I", HERE, "-o", out, "-lm"]
+    cmd = ["g++", "-std=gnu++17", "-x", "c++", "-"] + (FAST_CFLAGS if fast else CFLAGS) + \
+          ["-Wno-narrowing", "-I", HERE, "-o", out, "-lm"]
     subprocess.run(cmd, input=tu.encode(), check=True)
     return out
 
@@ -77,3 +88,4 @@ if __name__ == "__main__":
     force = "--force" in sys.argv
     print(build_oracle(force))
     print(build_ref(force))
+    print(build_ref(force, fast=True))

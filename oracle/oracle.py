@@ -39,7 +39,17 @@ def lib_path(kind):
         return os.path.join(HERE, "libspim_oracle.so")
     if kind == "reference":
         return os.path.join(HERE, "_ref", "libspim_ref.so")
+    if kind == "reference_fast":  # timing only: the reference's fast-math build options (oracle/build.py)
+        return os.path.join(HERE, "_ref", "libspim_ref_fast.so")
     raise ValueError(kind)
+
+
+def cpu_has_avx2():
+    try:
+        with open("/proc/cpuinfo") as f:
+            return " avx2 " in f.read().replace("\n", " ")
+    except OSError:
+        return False
 
 
 def available(kind):
@@ -55,7 +65,10 @@ def load(kind="port"):
     path = lib_path(kind)
     if not os.path.exists(path):
         from . import build
-        (build.build_oracle if kind == "port" else build.build_ref)()
+        if kind == "port":
+            build.build_oracle()
+        else:
+            build.build_ref(fast=kind == "reference_fast")
     lib = C.CDLL(path)
     VP = C.POINTER(SoVolume)
     lib.so_max_project.argtypes = [VP, C.c_int, C.c_int, _FP, _FP, _FP, C.c_float, C.c_float, C.c_float, C.c_float,
