@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--c4-vol", type=int, default=2048)
     ap.add_argument("--c4-img", type=int, default=2048)
     ap.add_argument("--c4-steps", type=int, default=24)
+    ap.add_argument("--no-mip-overlap", action="store_true",
+                    help="sweep workload: every frame's kernel on the render stream, one after the other (as round 1)")
     ap.add_argument("--no-iso-overlap", action="store_true",
                     help="iso workload, one GPU: every frame's screen-space passes on the render stream (as round 1)")
     ap.add_argument("--dtype", default="u16", choices=["u16", "f32"],
@@ -1355,7 +1357,11 @@ def run_sweep(args, rank, local_rank, world):
     rend.set_alpha_pow(args.alpha_pow)
     params = _lib.MipParams(rend._box(), 0., peak, 1., float(args.alpha_pow), 1, 0, MAX_STEPS, 0)
 
+    overlap = [False]
+
     def device_step(i):
+        if overlap[0]:  # frames alternate between the two output slots; slot 1's kernel runs on a second stream
+            lib.spv_select_slot(ctx, i & 1)
         invP, invM = mats[i % K]
         lib.spv_set_matrices(ctx, _lib.fp(invP), _lib.fp(invM))
         rc = lib.spv_render_mip(ctx, C.byref(params))
@@ -1384,6 +1390,9 @@ def run_sweep(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ----
+    if not args.no_mip_overlap and not args.alpha_pow and args.mip_path != "smem":
+        _lib.check(lib.spv_set_tuning(ctx, 15, 1), ctx)
+        overlap[0] = True
     launches0 = rend.launch_count()
     for i in range(args.warmup):
         device_step(i)
@@ -1392,9 +1401,15 @@ def run_sweep(args, rank, local_rank, world):
     e0.record()
     for i in range(K):
         device_step(i)
+    if overlap[0]:
+        _lib.check(lib.spv_stream_join(ctx), ctx)  # the last slot-1 frame, before the closing event
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    if overlap[0]:
+        _lib.check(lib.spv_set_tuning(ctx, 15, 0), ctx)
+        _lib.check(lib.spv_select_slot(ctx, 0), ctx)
+        overlap[0] = False
     launches = rend.launch_count() - launches0 - args.warmup
     kernels_per_frame = launches / float(K)
 
@@ -1535,7 +1550,10 @@ def run_sweep(args, rank, local_rank, world):
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": launch_s * 1e6,
-                         "kernels_per_frame": kernels_per_frame, "kernel": kernel_name},
+                         "kernels_per_frame": kernels_per_frame, "kernel": kernel_name,
+                         "overlap": None if (args.no_mip_overlap or args.alpha_pow or args.mip_path == "smem") else
+                         "frames alternate between two output slots and two streams: a frame's kernel starts in the tail of "
+                         "the one before (tuning knob 15); avg_launch_us is the timed region / frames"},
             "roofline_tex": {"bound": "texture samples", "issued_gsamples_per_s": mean_issued / launch_s / 1e9,
                              "algorithmic_gsamples_per_s": mean_hits * SAMPLES_PER_RAY / launch_s / 1e9,
                              "peak_gsamples_per_s": tex_peak / 1e9,

@@ -109,6 +109,9 @@ struct spv_ctx {
   // iso surface: the screen-space passes of the frame in one output slot may run on post_stream while the search of
   // the next frame (other slot) runs on `stream` (tuning knob 14); tile flags per slot
   int iso_overlap = 0;
+  int mip_overlap = 0;   // tuning knob 15: plain max projections into output slot 1 run on post_stream, beside slot 0's
+  cudaEvent_t ev_uploaded = nullptr;  // fork point: what the render stream had enqueued when post_stream last caught up
+  unsigned long long upload_seq = 1, side_seq = 0;  // uploads on the render stream / the last one post_stream waited for
   cudaStream_t post_stream = nullptr;
   cudaEvent_t ev_searched[2] = {nullptr, nullptr}, ev_posted[2] = {nullptr, nullptr};
   bool post_pending[2] = {false, false};
@@ -326,6 +329,7 @@ SPV_API int spv_create(int device, int width, int height, spv_ctx **out) {
   CC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   CC(cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking));
   CC(cudaStreamCreateWithFlags(&ctx->post_stream, cudaStreamNonBlocking));
+  CC(cudaEventCreateWithFlags(&ctx->ev_uploaded, cudaEventDisableTiming));
   CC(cudaEventCreateWithFlags(&ctx->ev_copy2, cudaEventDisableTiming));
   CC(cudaEventCreateWithFlags(&ctx->ev_up_begin, cudaEventDisableTiming));
   for (int s = 0; s < 2; ++s) {
@@ -382,6 +386,7 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
     if (ctx->ev_posted[s]) cudaEventDestroy(ctx->ev_posted[s]);
   }
   if (ctx->post_stream) cudaStreamDestroy(ctx->post_stream);
+  if (ctx->ev_uploaded) cudaEventDestroy(ctx->ev_uploaded);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->copy_stream2) cudaStreamDestroy(ctx->copy_stream2);
   if (ctx->ev_copy2) cudaEventDestroy(ctx->ev_copy2);
@@ -490,6 +495,12 @@ enum { SRC_DEVICE = 0, SRC_PINNED = 1, SRC_PAGEABLE = 2 };
 //   src_type >= 0    : the host array has another element type (SPV_SRC_*): its bytes travel as they are, convert_kernel
 //                      turns each chunk into texels on the device (instead of a host-side astype), then as above
 static int upload(spv_ctx *ctx, const void *src, bool on_device, bool no_wait = false, int src_type = -1) {
+  // a max projection running beside the render stream (tuning knob 15) may still be reading the array
+  {
+    int rcj = join_post(ctx, -1);
+    if (rcj) return rcj;
+  }
+  ctx->upload_seq++;
   const size_t es = elem_size(ctx->dtype);
   const size_t slice = (size_t)ctx->nx * ctx->ny;
   const size_t slice_bytes = slice * es;
@@ -901,6 +912,13 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   else if (knob == 10) ctx->smem_tex_of8 = value < 0 ? 0 : (value > 8 ? 8 : value);
   else if (knob == 12) ctx->iso_post_sharded = value != 0;
   else if (knob == 13) ctx->time_phases = value != 0;
+  else if (knob == 15) {
+    if (!value && ctx->mip_overlap) {
+      cudaSetDevice(ctx->device);
+      join_post(ctx, -1);
+    }
+    ctx->mip_overlap = value != 0;
+  }
   else if (knob == 14) {
     if (!value && ctx->iso_overlap) {  // switching off joins what is in flight
       cudaSetDevice(ctx->device);
@@ -1083,6 +1101,21 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
   const int s = ctx->slot;
   rc = join_post(ctx, s);  // an iso frame's screen-space passes may still be writing this slot beside the render stream
   if (rc) return rc;
+  // overlap (tuning knob 15): frames that alternate between the two output slots -- render_sequence, bench.py -- put slot
+  // 1's kernel on post_stream, so that it starts while slot 0's kernel is in its tail (SMs are busy 88-93 % of a launch)
+  // and the other way round.  Readers of slot 1 wait for ev_posted[1] exactly as for an iso frame's passes.
+  const bool side = ctx->mip_overlap && s == 1 && plain && !smem && !ctx->slab && !raw_only && !push && p->num_parts == 1 &&
+                    !(ctx->skipping > 0) && !ctx->persistent && !ctx->stats_on && !ctx->direct_host;
+  cudaStream_t kst = ctx->stream;  // the stream the kernel(s) of this frame run on
+  if (side) {
+    kst = ctx->post_stream;
+    if (ctx->side_seq != ctx->upload_seq) {  // an upload on the render stream that post_stream has not waited for yet
+      CU(cudaEventRecord(ctx->ev_uploaded, ctx->stream));
+      CU(cudaStreamWaitEvent(kst, ctx->ev_uploaded, 0));
+      ctx->side_seq = ctx->upload_seq;
+    }
+    if (ctx->copy_pending[s]) CU(cudaStreamWaitEvent(kst, ctx->ev_copied[s], 0));  // an asynchronous read of this slot
+  }
   if (to_host && ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // staging about to be rewritten
   const int H = ctx->height;
   const bool direct = to_host && ctx->direct_host && plain && p->num_parts == 1 && !raw_only;
@@ -1137,8 +1170,12 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
       for (int i = 0; i < nb; ++i) order[i] = (i & 1) ? nb - 1 - (i >> 1) : (i >> 1);
       staging_dirty(ctx, s);
     }
-    CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, false, false, ctx->stats_on != 0, ctx->stream));
+    CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, false, false, ctx->stats_on != 0, kst));
     ctx->launches += 1;
+    if (side) {
+      CU(cudaEventRecord(ctx->ev_posted[s], kst));
+      ctx->post_pending[s] = true;
+    }
     const unsigned ctas_x = (unsigned)(ctx->width + 15) / 16;
     for (int i = 0; i < nb; ++i) {
       // enqueue the copies in the order the bands complete, alternating between the copy streams
@@ -1189,12 +1226,16 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
       a.tile_counter = ctx->d_tile_counter;
       CU(launch_mip_smem(a, fmt_of(ctx), ctx->smem_cfg, ctx->tmaps[ctx->smem_cfg], ctx->smem_tex_of8, ctx->stream));
     } else
-      CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, ctx->skipping > 0, ctx->slab, ctx->stats_on != 0, ctx->stream));
+      CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, ctx->skipping > 0, ctx->slab, ctx->stats_on != 0, kst));
     ctx->launches += 1;
+    if (side) {
+      CU(cudaEventRecord(ctx->ev_posted[s], kst));
+      ctx->post_pending[s] = true;
+    }
     const int c0 = y0 > clip_a ? y0 : clip_a, c1 = y1 < clip_b ? y1 : clip_b;
     if (to_host && !direct && c0 < c1) {
       const size_t off = (size_t)c0 * ctx->width, cnt = (size_t)(c1 - c0) * ctx->width, n = ctx->n();
-      CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
+      CU(cudaEventRecord(ctx->ev_rendered[s], kst));
       CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
       // the band's rows of the value plane and of the alpha plane in ONE 2-D copy (2 "rows" one plane apart)
       CU(cudaMemcpy2DAsync(ctx->hpin_s[s] + off, n * sizeof(float), ctx->dbuf_s[s] + off, n * sizeof(float),

@@ -556,6 +556,9 @@ class VolumeRenderer(object):
         if method == "iso_surface":
             # frame i's screen-space passes run on a second stream beside frame i+1's search (tuning knob 14)
             self._check(self._lib.spv_set_tuning(self._ctx, 14, 1))
+        else:
+            # the frames of slot 1 run on a second stream: a frame starts in the tail of the one before (tuning knob 15)
+            self._check(self._lib.spv_set_tuning(self._ctx, 15, 1))
         try:
             for M in modelViews:
                 slot = i & 1
@@ -580,6 +583,7 @@ class VolumeRenderer(object):
                 yield self
         finally:
             self._lib.spv_set_tuning(self._ctx, 14, 0)
+            self._lib.spv_set_tuning(self._ctx, 15, 0)
             self._lib.spv_sync(self._ctx)
             self._lib.spv_select_slot(self._ctx, 0)
 

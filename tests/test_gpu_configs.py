@@ -259,7 +259,8 @@ def test_sort_last_iso_surface_against_oracle(oracle_mod, world):
 
 
 # ----------------------------------------------------------------------------- software-sampled max projection
-@pytest.mark.parametrize("shape,size", [((96, 112, 128), (200, 168)), ((256, 256, 256), (512, 512))])
+@pytest.mark.parametrize("shape,size", [((96, 112, 128), (200, 168)), ((256, 256, 256), (512, 512)),
+                                        ((67, 75, 91), (150, 118))])   # ragged: rows of the linear copies are padded
 def test_smem_path_against_oracle_and_texture_unit(oracle_mod, shape, size):
     """VolumeRenderer.set_mip_path("smem") -- TMA-staged shared-memory slabs, software trilinear sampling with fp32 weights
     (spv_mip_smem.cu) -- against the oracle (1e-3 of the range, north_star) and against the texture-unit kernel (the
