@@ -146,6 +146,25 @@ SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p);
  * copy streams wait on (cuStreamWaitValue32); otherwise one launch per band.  wait != 0: returns when the frame is in host memory; wait == 0:
  * returns at once, collect with spv_wait_slot.  *host (may be NULL) = the slot's staging. */
 SPV_API int spv_render_mip_to_host(spv_ctx *ctx, const spv_mip_params *p, int bands, int wait, float **host);
+/* ---- several frames per launch (new; the record loop of a keyframe / rotation sequence:
+ *      spimagine/gui/mainwidget.py renders frame after frame through _render_max_project, volumerender.py:327-390).
+ *      n <= SPV_MAX_BATCH plain projections (alpha_pow 0, one part) of the resident integer volume that share the
+ *      projection, box, window and step count and differ in their model view: invM = n row-major float[16], the invP
+ *      of spv_set_matrices.  ONE launch; its CTAs are dealt (tile row, frame, tile column), so the frames' CTAs of a
+ *      tile row run together and share the volume in L2; every frame picks the layered copy of the volume (pairs along
+ *      x, y or z; built on the device when first wanted, 4 bytes per voxel each) and the lane-to-pixel map under which
+ *      a texture request stays inside one layer.  Results go to one of two sets of planes, [n][out | alpha], that
+ *      alternate from call to call (*set = the one used); to_host != 0: the rows the projected box can touch also
+ *      travel to the set's pinned planes behind the launch.  Enqueue-only: spv_batch_wait waits for a set and returns
+ *      its planes (frame f: + f * 2 * width * height floats).  Pixel values equal spv_render_mip's with the same copy. */
+#define SPV_MAX_BATCH 16
+SPV_API int spv_render_mip_batch(spv_ctx *ctx, const spv_mip_params *p, const float *invM, int n, int to_host, int *set);
+SPV_API int spv_batch_wait(spv_ctx *ctx, int set, float **host, float **dev, int *n_frames);
+/* 1 if spv_render_mip_batch accepts these parameters on the resident volume and the context's settings, else 0 */
+SPV_API int spv_mip_batch_possible(spv_ctx *ctx, const spv_mip_params *p);
+/* layer axis (0 x, 1 y, 2 z) and lane map (0: 2x2-pixel quads, 1: 4x1 row quads, 2: 1x4 column quads) the last plain
+ * projection used; -1 / -1 when it ran mip_fast_kernel (tuning knob 16 = 0, or a path the layered copies do not cover) */
+SPV_API int spv_mip_axis_used(spv_ctx *ctx, int *axis, int *quad);
 /* window + gamma of SPV_BUF_RAW into SPV_BUF_OUT after the cross-GPU max composite */
 SPV_API int spv_mip_finish(spv_ctx *ctx, const spv_mip_params *p);
 

@@ -16,6 +16,7 @@ SPV_F32, SPV_U16, SPV_U8 = 0, 1, 2
 BUF_OUT, BUF_ALPHA, BUF_DEPTH, BUF_NORMALS, BUF_OCC, BUF_RAW, BUF_KPLANES = range(7)
 SAMPLER_TMU, SAMPLER_EXACT = 0, 1
 MIP_RAW_ONLY = 1
+MAX_BATCH = 16
 ISO_RAW_ONLY = 1
 
 DTYPE_CODES = {np.dtype(np.float32): SPV_F32, np.dtype(np.uint16): SPV_U16, np.dtype(np.uint8): SPV_U8}
@@ -107,6 +108,10 @@ SIGNATURES = {
     "spv_stream_join": (C.c_int, [_CTX]),
     "spv_set_mip_path": (C.c_int, [_CTX, C.c_int]),
     "spv_mip_path_used": (C.c_int, [_CTX, C.POINTER(C.c_int)]),
+    "spv_render_mip_batch": (C.c_int, [_CTX, C.POINTER(MipParams), _FP, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "spv_mip_batch_possible": (C.c_int, [_CTX, C.POINTER(MipParams)]),
+    "spv_batch_wait": (C.c_int, [_CTX, C.c_int, C.POINTER(_FP), C.POINTER(_FP), C.POINTER(C.c_int)]),
+    "spv_mip_axis_used": (C.c_int, [_CTX, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "spv_update_volume_device_from": (C.c_int, [_CTX, C.c_void_p, C.c_int]),
     "spv_filter_create": (C.c_int, [C.c_int, C.POINTER(_CTX)]),
     "spv_filter_destroy": (C.c_int, [_CTX]),

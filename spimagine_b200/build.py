@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["spv_api.cu", "spv_mip.cu", "spv_mip_smem.cu", "spv_iso.cu", "spv_bricks.cu", "spv_comp.cu", "spv_display.cu", "spv_filter.cu"]
+SOURCES = ["spv_api.cu", "spv_mip.cu", "spv_mip_axis.cu", "spv_mip_smem.cu", "spv_iso.cu", "spv_bricks.cu", "spv_comp.cu", "spv_display.cu", "spv_filter.cu"]
 HEADERS = ["spv_common.cuh", "spv_kernels.h"]
 LIB = os.path.join(HERE, "libspimcuda.so")
 

@@ -124,6 +124,22 @@ struct spv_ctx {
   bool lin_valid = false;
   CUtensorMap tmaps[8][3];  // per box geometry (tuning knob 11)
   int smem_cfg = 0;  // result bytes enqueued for device -> host copies so far (spv_d2h_bytes)
+  // view-aligned layered copies (spv_mip_axis.cu): pairs along x (0) and y (1); the z copy is `arr` itself.  Built on the
+  // render stream when a frame first wants them, rebuilt after an upload (axis_seq is the upload they were built from).
+  cudaArray_t axis_arr[2] = {nullptr, nullptr};
+  cudaTextureObject_t axis_tex[2] = {0, 0};
+  cudaSurfaceObject_t axis_surf[2] = {0, 0};
+  unsigned long long axis_seq[2] = {0, 0};
+  bool axis_failed[2] = {false, false};  // the copy could not be allocated: not tried again for this volume
+  int axis_mode = 1;       // tuning knob 16: 0 = off (mip_fast_kernel), 1 = per-frame choice, 10 + 3 * axis + quad = forced
+  int last_axis = -1, last_quad = -1;  // what the last plain projection used (-1: mip_fast_kernel)
+  unsigned long long renders_since_upload = 0;
+  // multi-frame launches (spv_render_mip_batch): two sets of [cap][out | alpha] planes, device and pinned
+  float *d_batch[2] = {nullptr, nullptr}, *h_batch[2] = {nullptr, nullptr};
+  int batch_cap = 0, batch_set = 1, batch_n[2] = {0, 0};
+  cudaEvent_t ev_batch_rendered[2] = {nullptr, nullptr}, ev_batch_copied[2] = {nullptr, nullptr};
+  bool batch_copy_pending[2] = {false, false}, batch_render_pending[2] = {false, false};
+  int batch_dirty_lo[2][MAX_BATCH], batch_dirty_hi[2][MAX_BATCH];  // rows of the pinned planes that may hold hits
   std::string err;
 
   size_t n() const { return (size_t)width * height; }
@@ -186,9 +202,33 @@ static void free_comp(spv_ctx *c) {
   c->comp_frame = 0;
 }
 
+static void free_axis(spv_ctx *c) {
+  for (int d = 0; d < 2; ++d) {
+    if (c->axis_tex[d]) cudaDestroyTextureObject(c->axis_tex[d]);
+    if (c->axis_surf[d]) cudaDestroySurfaceObject(c->axis_surf[d]);
+    if (c->axis_arr[d]) cudaFreeArray(c->axis_arr[d]);
+    c->axis_tex[d] = 0;
+    c->axis_surf[d] = 0;
+    c->axis_arr[d] = nullptr;
+    c->axis_seq[d] = 0;
+    c->axis_failed[d] = false;
+  }
+}
+static void free_batch(spv_ctx *c) {
+  for (int s = 0; s < 2; ++s) {
+    if (c->d_batch[s]) cudaFree(c->d_batch[s]);
+    if (c->h_batch[s]) cudaFreeHost(c->h_batch[s]);
+    c->d_batch[s] = c->h_batch[s] = nullptr;
+    c->batch_copy_pending[s] = c->batch_render_pending[s] = false;
+    c->batch_n[s] = 0;
+  }
+  c->batch_cap = 0;
+}
 static void free_buffers(spv_ctx *c) {
   free_comp(c);  // the peers' pointers into these buffers die with them: re-run spv_comp_init + exchange after a resize
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->copy_stream2) cudaStreamSynchronize(c->copy_stream2);
+  free_batch(c);
   for (int s = 0; s < 2; ++s) {
     if (c->dbuf_s[s]) cudaFree(c->dbuf_s[s]);
     if (c->hpin_s[s]) cudaFreeHost(c->hpin_s[s]);
@@ -212,6 +252,7 @@ static void free_buffers(spv_ctx *c) {
   c->slot = 0;
 }
 static void free_volume(spv_ctx *c) {
+  free_axis(c);
   if (c->tex_lin) cudaDestroyTextureObject(c->tex_lin);
   if (c->tex_near) cudaDestroyTextureObject(c->tex_near);
   if (c->tex_pt) cudaDestroyTextureObject(c->tex_pt);
@@ -339,6 +380,8 @@ SPV_API int spv_create(int device, int width, int height, spv_ctx **out) {
     CC(cudaEventCreateWithFlags(&ctx->ev_consumed[s], cudaEventDisableTiming));
     CC(cudaEventCreateWithFlags(&ctx->ev_searched[s], cudaEventDisableTiming));
     CC(cudaEventCreateWithFlags(&ctx->ev_posted[s], cudaEventDisableTiming));
+    CC(cudaEventCreateWithFlags(&ctx->ev_batch_rendered[s], cudaEventDisableTiming));
+    CC(cudaEventCreateWithFlags(&ctx->ev_batch_copied[s], cudaEventDisableTiming));
   }
   CC(cudaMalloc(&ctx->d_minmax, 2 * sizeof(float)));
   CC(cudaMalloc(&ctx->d_stats, 40 * sizeof(unsigned long long)));
@@ -384,6 +427,8 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
     if (ctx->ev_consumed[s]) cudaEventDestroy(ctx->ev_consumed[s]);
     if (ctx->ev_searched[s]) cudaEventDestroy(ctx->ev_searched[s]);
     if (ctx->ev_posted[s]) cudaEventDestroy(ctx->ev_posted[s]);
+    if (ctx->ev_batch_rendered[s]) cudaEventDestroy(ctx->ev_batch_rendered[s]);
+    if (ctx->ev_batch_copied[s]) cudaEventDestroy(ctx->ev_batch_copied[s]);
   }
   if (ctx->post_stream) cudaStreamDestroy(ctx->post_stream);
   if (ctx->ev_uploaded) cudaEventDestroy(ctx->ev_uploaded);
@@ -421,6 +466,7 @@ SPV_API int spv_sync(spv_ctx *ctx) {
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaStreamSynchronize(ctx->post_stream));
   CU(cudaStreamSynchronize(ctx->copy_stream));
+  CU(cudaStreamSynchronize(ctx->copy_stream2));
   ctx->post_pending[0] = ctx->post_pending[1] = false;
   return 0;
 }
@@ -501,6 +547,7 @@ static int upload(spv_ctx *ctx, const void *src, bool on_device, bool no_wait = 
     if (rcj) return rcj;
   }
   ctx->upload_seq++;
+  ctx->renders_since_upload = 0;  // the layered copies along x / y are rebuilt when a frame next wants them
   const size_t es = elem_size(ctx->dtype);
   const size_t slice = (size_t)ctx->nx * ctx->ny;
   const size_t slice_bytes = slice * es;
@@ -926,6 +973,7 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
     }
     ctx->iso_overlap = value != 0;
   }
+  else if (knob == 16) ctx->axis_mode = value;
   else if (knob == 11) ctx->smem_cfg = value < 0 || value >= mip_smem_configs() ? 0 : value;
   else if (knob == 6) occ_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : value);  // process-wide
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
@@ -1034,6 +1082,124 @@ static void hit_tile_rows(const Camera &cam, const float *box, int H, unsigned t
   if (tb < ta) tb = ta;
 }
 
+// ---- view-aligned layered copies (spv_mip_axis.cu) ------------------------------------------------------------------
+// The copy of the resident integer volume with pairs along axis lax (0 x, 1 y), built from the primary z copy on the
+// render stream; post_stream is made to wait for it (frames in output slot 1 may render there).
+static int ensure_axis(spv_ctx *ctx, int lax) {
+  if (lax == 2) return 0;
+  if (ctx->axis_arr[lax] && ctx->axis_seq[lax] == ctx->upload_seq) return 0;
+  if (!ctx->axis_arr[lax]) {
+    const int bits = ctx->dtype == SPV_U16 ? 16 : 8;
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(bits, bits, 0, 0, cudaChannelFormatKindUnsigned);
+    const cudaExtent ext = lax == 0 ? make_cudaExtent(ctx->gnz, ctx->ny, ctx->nx) : make_cudaExtent(ctx->nx, ctx->gnz, ctx->ny);
+    cudaError_t e = cudaMalloc3DArray(&ctx->axis_arr[lax], &cd, ext, cudaArrayLayered | cudaArraySurfaceLoadStore);
+    if (e != cudaSuccess) {  // no room for another copy: this volume renders from the primary one
+      cudaGetLastError();
+      ctx->axis_arr[lax] = nullptr;
+      ctx->axis_failed[lax] = true;
+      return 1;
+    }
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof rd);
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = ctx->axis_arr[lax];
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof td);
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.normalizedCoords = 0;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.filterMode = cudaFilterModeLinear;
+    CU(cudaCreateTextureObject(&ctx->axis_tex[lax], &rd, &td, nullptr));
+    CU(cudaCreateSurfaceObject(&ctx->axis_surf[lax], &rd));
+  }
+  CU(launch_axis_pair(volume_of(ctx), ctx->dtype, lax, ctx->axis_surf[lax], ctx->stream));
+  ctx->launches += 1;
+  ctx->axis_seq[lax] = ctx->upload_seq;
+  CU(cudaEventRecord(ctx->ev_uploaded, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->post_stream, ctx->ev_uploaded, 0));
+  return 0;
+}
+
+// can plain projections of the resident volume go through mip_axis_kernel at all?
+static bool axis_path_possible(const spv_ctx *c) {
+  return c->axis_mode != 0 && c->arr && c->layout == LAYOUT_ZPAIR && !c->slab && c->sampler == SPV_SAMPLER_TMU && c->linear &&
+         c->int_filter && !(c->skipping > 0) && !c->persistent && !c->stats_on && c->tile_variant == 0 &&
+         c->mip_path != SPV_MIP_PATH_SMEM && c->gnz == c->local_nz;
+}
+
+// Layer axis and lane-to-pixel map of one frame.  At the middle of the central ray's path through the box: gx / gy =
+// texels between horizontally / vertically adjacent pixels' samples, gk = texels between a ray's consecutive samples.
+// A quad request is cheapest when its four lanes share a layer and the ray stays in it; the weights are a fit to
+// profiles/r02_exp_multiframe_v3.txt (per-frame time ~ 1 + 0.36 * layers spanned by a quad + 0.09 * layers per step,
+// + 0.10 for column quads).  other_copies: the x / y copies may be used (built if they are not there yet).
+static void choose_axis(spv_ctx *ctx, const float *invP, const float *invM, const float *box, int max_steps,
+                        bool other_copies, int &lax_out, int &quad_out) {
+  lax_out = 2;
+  quad_out = 0;
+  if (ctx->axis_mode >= 10) {  // forced (tests, experiments)
+    const int v = ctx->axis_mode - 10;
+    lax_out = (v / 3) % 3;
+    quad_out = v % 3;
+    if (lax_out != 2 && ctx->axis_failed[lax_out]) lax_out = 2;
+    return;
+  }
+  const int W = ctx->width, H = ctx->height;
+  auto ray = [&](double px, double py, double *o, double *d) {
+    const double u = px / W * 2. - 1., v = py / H * 2. - 1.;
+    const double front[4] = {u, v, -1., 1.}, back[4] = {u, v, 1., 1.};
+    double a[4], b[4], t[4];
+    for (int r = 0; r < 4; ++r) {
+      a[r] = b[r] = 0.;
+      for (int c = 0; c < 4; ++c) { a[r] += invP[4 * r + c] * front[c]; b[r] += invP[4 * r + c] * back[c]; }
+    }
+    for (int r = 0; r < 4; ++r) { a[r] /= a[3] != 0. ? a[3] : 1.; }
+    const double bw = b[3] != 0. ? b[3] : 1.;
+    double len = 0.;
+    for (int r = 0; r < 4; ++r) { t[r] = b[r] / bw - a[r]; len += t[r] * t[r]; }
+    len = len > 0. ? sqrt(len) : 1.;
+    double ow = 0.;
+    for (int c = 0; c < 4; ++c) ow += invM[12 + c] * a[c];
+    if (ow == 0.) ow = 1.;
+    for (int r = 0; r < 3; ++r) {
+      o[r] = d[r] = 0.;
+      for (int c = 0; c < 4; ++c) { o[r] += invM[4 * r + c] * a[c]; d[r] += invM[4 * r + c] * t[c] / len; }
+      o[r] /= ow;
+    }
+  };
+  double o[3], d[3], ox[3], dx[3], oy[3], dy[3];
+  ray(W * .5, H * .5, o, d);
+  ray(W * .5 + 1., H * .5, ox, dx);
+  ray(W * .5, H * .5 + 1., oy, dy);
+  double tn = -1e300, tf = 1e300, dd = 0., od = 0.;
+  for (int r = 0; r < 3; ++r) {
+    dd += d[r] * d[r];
+    od += o[r] * d[r];
+    if (d[r] != 0.) {
+      const double t0 = (box[2 * r] - o[r]) / d[r], t1 = (box[2 * r + 1] - o[r]) / d[r];
+      tn = fmax(tn, fmin(t0, t1));
+      tf = fmin(tf, fmax(t0, t1));
+    }
+  }
+  if (!(dd > 0.)) return;
+  const bool hit = tf > tn && tf > 0.;
+  if (tn < 0.) tn = 0.;
+  const double tm = hit ? .5 * (tn + tf) : -od / dd;  // else: closest approach to the box centre
+  const double dt = hit ? (tf - tn) / (double)((max_steps / 16) * 16) : 2. / max_steps;
+  const double n[3] = {(double)ctx->nx, (double)ctx->ny, (double)ctx->gnz};
+  double best = 1e300;
+  for (int lax = 2; lax >= 0; --lax) {
+    if (lax != 2 && (!other_copies || ctx->axis_failed[lax])) continue;
+    if ((lax == 0 ? ctx->nx : (lax == 1 ? ctx->ny : ctx->gnz)) > 2048) continue;  // layer count of a layered array
+    const double gx = fabs((ox[lax] + tm * dx[lax]) - (o[lax] + tm * d[lax])) * .5 * n[lax];
+    const double gy = fabs((oy[lax] + tm * dy[lax]) - (o[lax] + tm * d[lax])) * .5 * n[lax];
+    const double gk = fabs(.5 * dt * d[lax]) * n[lax];
+    const double own = lax == 2 ? 0. : .02;  // a copy that may have to be built must earn it
+    const double cost[3] = {.36 * (gx + gy) + .09 * gk + own, .36 * 3. * gx + .09 * gk + own, .36 * 3. * gy + .09 * gk + .10 + own};
+    for (int q = 0; q < 3; ++q)
+      if (cost[q] < best) { best = cost[q]; lax_out = lax; quad_out = q; }
+  }
+}
+
 // One max projection.  bands > 1 (fast kernel only): the frame is rendered as `bands` horizontal bands launched back to
 // back, and the rows of a finished band travel to the pinned staging on the copy stream while the next band renders.
 static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, bool to_host, const PushArgs *push = nullptr) {
@@ -1096,6 +1262,44 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     if (rc) return rc;
     bands = 1;
   }
+  // view-aligned layered copy + lane map of this frame (spv_mip_axis.cu); the x / y copies are built from the second
+  // frame after an upload on (a time point that is rendered once does not pay for them)
+  const bool axis = plain && linear && !raw_only && !push && !smem && p->num_parts == 1 && p->current_part == 0 &&
+                    axis_path_possible(ctx);
+  int lax = 2, quad = 0;
+  if (axis) {
+    choose_axis(ctx, ctx->cam.invP, ctx->cam.invM, p->box, p->max_steps, ctx->renders_since_upload >= 1, lax, quad);
+    if (lax != 2) {
+      rc = ensure_axis(ctx, lax);
+      if (rc && !ctx->axis_failed[lax]) return rc;
+      if (ctx->axis_failed[lax]) choose_axis(ctx, ctx->cam.invP, ctx->cam.invM, p->box, p->max_steps, false, lax, quad);
+    }
+  }
+  ctx->last_axis = axis ? lax : -1;
+  ctx->last_quad = axis ? quad : -1;
+  ctx->renders_since_upload++;
+  MipAxisArgs ax;
+  if (axis) {
+    memset(&ax, 0, sizeof ax);
+    memcpy(ax.invP, ctx->cam.invP, sizeof ax.invP);
+    memcpy(ax.invM[0], ctx->cam.invM, sizeof ax.invM[0]);
+    ax.tex[0] = ctx->axis_tex[0]; ax.tex[1] = ctx->axis_tex[1]; ax.tex[2] = ctx->tex_lin;
+    ax.lax[0] = (unsigned char)lax; ax.quad[0] = (unsigned char)quad;
+    ax.nx = ctx->nx; ax.ny = ctx->ny; ax.nz = ctx->gnz;
+    ax.scale = a.vol.scale;
+    memcpy(ax.box, p->box, sizeof ax.box);
+    ax.min_val = p->min_val; ax.max_val = p->max_val; ax.gamma = p->gamma; ax.max_steps = p->max_steps;
+    ax.width = ctx->width; ax.height = ctx->height; ax.n_frames = 1;
+  }
+  // the kernel of this frame (or band of it): a carries what varies between the launches below
+  auto launch_frame = [&](const MipArgs &m, cudaStream_t st) -> cudaError_t {
+    if (!axis) return launch_mip(m, fmt_of(ctx), linear, fast, exact, ctx->skipping > 0, ctx->slab, ctx->stats_on != 0, st);
+    ax.out[0] = m.out; ax.alpha[0] = m.alpha;
+    ax.y_begin = m.y_begin; ax.y_end = m.y_end;
+    ax.band_done = m.band_done; ax.band_rows = m.band_rows; ax.row_mode = m.row_mode;
+    ax.hit_tile_a = m.hit_tile_a; ax.hit_tile_b = m.hit_tile_b;
+    return launch_mip_axis(ax, ctx->dtype, st);
+  };
   rc = begin_render(ctx);
   if (rc) return rc;
   const int s = ctx->slot;
@@ -1170,7 +1374,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
       for (int i = 0; i < nb; ++i) order[i] = (i & 1) ? nb - 1 - (i >> 1) : (i >> 1);
       staging_dirty(ctx, s);
     }
-    CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, false, false, ctx->stats_on != 0, kst));
+    CU(launch_frame(a, kst));
     ctx->launches += 1;
     if (side) {
       CU(cudaEventRecord(ctx->ev_posted[s], kst));
@@ -1226,7 +1430,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
       a.tile_counter = ctx->d_tile_counter;
       CU(launch_mip_smem(a, fmt_of(ctx), ctx->smem_cfg, ctx->tmaps[ctx->smem_cfg], ctx->smem_tex_of8, ctx->stream));
     } else
-      CU(launch_mip(a, fmt_of(ctx), linear, fast, exact, ctx->skipping > 0, ctx->slab, ctx->stats_on != 0, kst));
+      CU(launch_frame(a, kst));
     ctx->launches += 1;
     if (side) {
       CU(cudaEventRecord(ctx->ev_posted[s], kst));
@@ -1269,6 +1473,163 @@ SPV_API int spv_render_mip_to_host(spv_ctx *ctx, const spv_mip_params *p, int ba
     CU(cudaStreamSynchronize(ctx->stream));  // statistics / timing events of this frame
   }
   if (host) *host = ctx->hpin_s[ctx->slot];
+  return 0;
+}
+
+// ---- several frames per launch --------------------------------------------------------------------------------------
+static int ensure_batch(spv_ctx *ctx, int n) {
+  if (n <= ctx->batch_cap) return 0;
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->copy_stream));
+  CU(cudaStreamSynchronize(ctx->copy_stream2));
+  free_batch(ctx);
+  const size_t bytes = (size_t)n * 2 * ctx->n() * sizeof(float);
+  for (int s = 0; s < 2; ++s) {
+    CU(cudaMalloc(&ctx->d_batch[s], bytes));
+    CU(cudaMallocHost(&ctx->h_batch[s], bytes));
+    memset(ctx->h_batch[s], 0, bytes);  // every row holds the miss values (out 0, alpha 0: integer volumes only)
+    for (int f = 0; f < MAX_BATCH; ++f) ctx->batch_dirty_lo[s][f] = ctx->batch_dirty_hi[s][f] = 0;
+  }
+  ctx->batch_cap = n;
+  return 0;
+}
+
+// n (<= SPV_MAX_BATCH) plain max projections of the resident integer volume that differ in their model view only, in ONE
+// launch (mip_axis_kernel): the frames' CTAs of one tile row run together, so the frames share the volume in L2.  Results
+// go to one of two sets of planes, [n][out | alpha] floats, alternating from call to call; with to_host the rows the
+// projected box can touch travel to the set's pinned planes behind the launch (the other rows hold the miss values), and
+// the next call's launch overlaps that copy.  Enqueue-only; spv_batch_wait gives the pointers of a set.
+SPV_API int spv_render_mip_batch(spv_ctx *ctx, const spv_mip_params *p, const float *invM, int n, int to_host, int *set_out) {
+  BIND();
+  if (!p || !invM || !set_out) return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: null argument");
+  if (n < 1 || n > MAX_BATCH) return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: 1 <= n <= SPV_MAX_BATCH frames per launch");
+  if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_render_mip_batch: no volume set");
+  if (p->num_parts != 1 || p->current_part != 0 || p->max_steps < 16 || p->alpha_pow != 0.f || p->flags != 0)
+    return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: plain projections only (alpha_pow 0, one part, no flags, max_steps >= 16)");
+  if (bad_float(p->gamma)) return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: NaN parameter");
+  if (!axis_path_possible(ctx))
+    return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: needs a resident integer volume in the paired layout, the TMU sampler "
+                                 "with linear filtering, and no skipping / statistics / slab / software-sampled path");
+  int rc = ensure_batch(ctx, n);
+  if (rc) return rc;
+  const int set = ctx->batch_set ^ 1;
+  MipAxisArgs ax;
+  memset(&ax, 0, sizeof ax);
+  memcpy(ax.invP, ctx->cam.invP, sizeof ax.invP);
+  memcpy(ax.invM, invM, (size_t)n * 16 * sizeof(float));
+  for (int f = 0; f < n; ++f) {
+    int lax, quad;
+    choose_axis(ctx, ctx->cam.invP, invM + 16 * f, p->box, p->max_steps, true, lax, quad);
+    if (lax != 2) {
+      rc = ensure_axis(ctx, lax);
+      if (rc && !ctx->axis_failed[lax]) return rc;
+      if (ctx->axis_failed[lax]) choose_axis(ctx, ctx->cam.invP, invM + 16 * f, p->box, p->max_steps, false, lax, quad);
+    }
+    ax.lax[f] = (unsigned char)lax;
+    ax.quad[f] = (unsigned char)quad;
+    ax.out[f] = ctx->d_batch[set] + (size_t)f * 2 * ctx->n();
+    ax.alpha[f] = ax.out[f] + ctx->n();
+  }
+  ctx->last_axis = ax.lax[0];
+  ctx->last_quad = ax.quad[0];
+  ctx->renders_since_upload += (unsigned long long)n;
+  ax.tex[0] = ctx->axis_tex[0]; ax.tex[1] = ctx->axis_tex[1]; ax.tex[2] = ctx->tex_lin;
+  ax.nx = ctx->nx; ax.ny = ctx->ny; ax.nz = ctx->gnz;
+  ax.scale = ctx->dtype == SPV_U16 ? 65535.f : 255.f;
+  memcpy(ax.box, p->box, sizeof ax.box);
+  ax.min_val = p->min_val; ax.max_val = p->max_val; ax.gamma = p->gamma; ax.max_steps = p->max_steps;
+  ax.width = ctx->width; ax.height = ctx->height; ax.n_frames = n;
+  ax.y_begin = 0; ax.y_end = ctx->height;
+  rc = join_post(ctx, -1);  // single frames beside the render stream may still read a copy that is about to be rebuilt
+  if (rc) return rc;
+  if (ctx->batch_copy_pending[set]) {  // the copies out of this set's planes, two calls ago
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_batch_copied[set], 0));
+    if (to_host) CU(cudaEventSynchronize(ctx->ev_batch_copied[set]));  // the pinned rows are about to be cleaned by the host
+    ctx->batch_copy_pending[set] = false;
+  }
+  rc = begin_render(ctx);
+  if (rc) return rc;
+  CU(launch_mip_axis(ax, ctx->dtype, ctx->stream));
+  ctx->launches += 1;
+  ctx->last_method = 0;
+  rc = end_render(ctx);
+  if (rc) return rc;
+  CU(cudaEventRecord(ctx->ev_batch_rendered[set], ctx->stream));
+  ctx->batch_render_pending[set] = true;
+  ctx->batch_n[set] = n;
+  ctx->batch_set = set;
+  *set_out = set;
+  if (!to_host) return 0;
+  const int H = ctx->height;
+  const size_t W = (size_t)ctx->width, np = ctx->n();
+  CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_batch_rendered[set], 0));
+  if (ctx->copy_streams > 1) CU(cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_batch_rendered[set], 0));
+  for (int f = 0; f < n; ++f) {
+    int ca = 0, cb = H;
+    if (ctx->clip_copies) {  // rows the box cannot project to are misses: not copied (as spv_render_mip_to_host)
+      Camera cam;
+      memcpy(cam.invP, ctx->cam.invP, sizeof cam.invP);
+      memcpy(cam.invM, invM + 16 * f, sizeof cam.invM);
+      unsigned ta, tb;
+      hit_tile_rows(cam, p->box, H, (unsigned)((H + 7) / 8), ta, tb);
+      ca = (int)ta * 8 - 8 > 0 ? (int)ta * 8 - 8 : 0;
+      cb = (int)tb * 8 + 8 < H ? (int)tb * 8 + 8 : H;
+      if (ca >= cb) ca = cb = 0;
+    }
+    float *hf = ctx->h_batch[set] + (size_t)f * 2 * np;
+    // rows of the pinned planes outside [ca, cb) that an earlier frame left hits in go back to the miss values
+    int &lo = ctx->batch_dirty_lo[set][f], &hi = ctx->batch_dirty_hi[set][f];
+    const int parts[2][2] = {{lo, hi < ca ? hi : ca}, {lo > cb ? lo : cb, hi}};
+    for (int k = 0; k < 2; ++k)
+      if (parts[k][0] < parts[k][1]) {
+        const size_t o0 = (size_t)parts[k][0] * W, cnt = (size_t)(parts[k][1] - parts[k][0]) * W;
+        memset(hf + o0, 0, cnt * sizeof(float));
+        memset(hf + np + o0, 0, cnt * sizeof(float));
+      }
+    lo = ca;
+    hi = cb;
+    if (ca >= cb) continue;
+    const size_t off = (size_t)ca * W, cnt = (size_t)(cb - ca) * W;
+    cudaStream_t cs = (ctx->copy_streams > 1 && (f & 1)) ? ctx->copy_stream2 : ctx->copy_stream;
+    CU(cudaMemcpy2DAsync(hf + off, np * sizeof(float), ax.out[f] + off, np * sizeof(float), cnt * sizeof(float), 2,
+                         cudaMemcpyDeviceToHost, cs));
+    ctx->d2h_bytes += 2 * cnt * sizeof(float);
+  }
+  if (ctx->copy_streams > 1) {
+    CU(cudaEventRecord(ctx->ev_copy2, ctx->copy_stream2));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy2, 0));
+  }
+  CU(cudaEventRecord(ctx->ev_batch_copied[set], ctx->copy_stream));
+  ctx->batch_copy_pending[set] = true;
+  return 0;
+}
+
+SPV_API int spv_mip_batch_possible(spv_ctx *ctx, const spv_mip_params *p) {
+  if (!ctx || !p || !ctx->arr) return 0;
+  if (p->num_parts != 1 || p->current_part != 0 || p->max_steps < 16 || p->alpha_pow != 0.f || p->flags != 0) return 0;
+  return axis_path_possible(ctx) ? 1 : 0;
+}
+
+// Waits for set `set` of spv_render_mip_batch (its copies when it was rendered to the host, else its launch) and
+// returns its planes: frame f's value plane at + f * 2 * width * height floats, its alpha plane one plane further.
+SPV_API int spv_batch_wait(spv_ctx *ctx, int set, float **host, float **dev, int *n_frames) {
+  BIND();
+  if (set < 0 || set > 1 || !ctx->d_batch[set]) return fail(ctx, SPV_EINVAL, "spv_batch_wait: no such set");
+  if (ctx->batch_copy_pending[set]) CU(cudaEventSynchronize(ctx->ev_batch_copied[set]));
+  else if (ctx->batch_render_pending[set]) CU(cudaEventSynchronize(ctx->ev_batch_rendered[set]));
+  ctx->batch_render_pending[set] = false;
+  if (host) *host = ctx->h_batch[set];
+  if (dev) *dev = ctx->d_batch[set];
+  if (n_frames) *n_frames = ctx->batch_n[set];
+  return 0;
+}
+
+// layer axis (0 x, 1 y, 2 z) and lane map (0: 2x2 quads, 1: row quads, 2: column quads) of the last plain projection;
+// -1, -1 when it went through mip_fast_kernel
+SPV_API int spv_mip_axis_used(spv_ctx *ctx, int *axis, int *quad) {
+  if (!ctx) return SPV_EINVAL;
+  if (axis) *axis = ctx->last_axis;
+  if (quad) *quad = ctx->last_quad;
   return 0;
 }
 

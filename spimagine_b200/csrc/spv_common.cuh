@@ -64,22 +64,26 @@ struct Ray {
 };
 
 // volume_kernel.cl:45-76 / iso_kernel.cl:39-71 / iso_kernel.cl:517-542: pixel-corner eye ray
-__device__ __forceinline__ void eye_ray(unsigned x, unsigned y, unsigned Nx, unsigned Ny, const Camera &cam, v4 &orig,
-                                        v4 &direc) {
+__device__ __forceinline__ void eye_ray(unsigned x, unsigned y, unsigned Nx, unsigned Ny, const float *invP,
+                                        const float *invM, v4 &orig, v4 &direc) {
   float u = ((float)x / (float)Nx) * 2.0f - 1.0f;
   float v = ((float)y / (float)Ny) * 2.0f - 1.0f;
   v4 front = mk4(u, v, -1.f, 1.f);
   v4 back = mk4(u, v, 1.f, 1.f);
-  v4 orig0 = mult(cam.invP, front);
+  v4 orig0 = mult(invP, front);
   orig0 = scl4(1.f / orig0.w, orig0);
-  v4 o = mult(cam.invM, orig0);
+  v4 o = mult(invM, orig0);
   o = scl4(1.f / o.w, o);
-  v4 temp = mult(cam.invP, back);
+  v4 temp = mult(invP, back);
   temp = scl4(1.f / temp.w, temp);
-  v4 d = mult(cam.invM, normalize4(sub4(temp, orig0)));
+  v4 d = mult(invM, normalize4(sub4(temp, orig0)));
   d.w = 0.0f;
   orig = o;
   direc = d;
+}
+__device__ __forceinline__ void eye_ray(unsigned x, unsigned y, unsigned Nx, unsigned Ny, const Camera &cam, v4 &orig,
+                                        v4 &direc) {
+  eye_ray(x, y, Nx, Ny, cam.invP, cam.invM, orig, direc);
 }
 
 // utils.cl:41-60 slab test (w lanes carried along like the float4 code does; they never matter)
@@ -102,6 +106,20 @@ __device__ __forceinline__ Ray make_ray(unsigned x, unsigned y, unsigned Nx, uns
   eye_ray(x, y, Nx, Ny, cam, r.orig, r.direc);
   r.hit = intersect_box(r.orig, r.direc, box, r.tnear, r.tfar);
   return r;
+}
+__device__ __forceinline__ Ray make_ray(unsigned x, unsigned y, unsigned Nx, unsigned Ny, const float *invP,
+                                        const float *invM, const float *box) {
+  Ray r;
+  eye_ray(x, y, Nx, Ny, invP, invM, r.orig, r.direc);
+  r.hit = intersect_box(r.orig, r.direc, box, r.tnear, r.tfar);
+  return r;
+}
+
+// window and gamma of a projected maximum (volume_kernel.cl:160-170 / :320-330)
+__device__ __forceinline__ float window_value(float col, float minVal, float maxVal, float gamma) {
+  col = (maxVal == 0.f) ? col : (col - minVal) / (maxVal - minVal);
+  if (gamma != 1.f) col = powf(col, gamma);
+  return clampf_cl(col, 0.f, 1.f);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -79,6 +79,42 @@ cudaError_t launch_mip_smem(const MipArgs &a, int fmt, int cfg, const void *maps
 cudaError_t launch_permute(const Volume &V, int fmt, int D, int NA, int NB, int ND, size_t pitchA, void *dst,
                            cudaStream_t st);
 
+
+// View-aligned layered copies and multi-frame launches (spv_mip_axis.cu).
+// The integer volume is resident as 2-D layered arrays of pairs {v[l], v[l+1]} along a LAYER AXIS (0 x, 1 y, 2 z; the
+// z copy is the primary array).  A frame picks the axis and the way a warp's lanes map to pixels so that the four lanes
+// of a hardware quad (one texture request) and the consecutive samples of a ray stay inside one layer:
+//   quad 0: 2x2-pixel quads, 8x4 warp tiles, 2x2 warps      (layer axis along the view direction)
+//   quad 1: 4x1 row quads,  16x2 warp tiles, 1x4 warps      (layer axis along the camera's up direction)
+//   quad 2: 1x4 column quads, 4x8 warp tiles, 4x1 warps     (layer axis along the camera's right direction)
+// A CTA is 16x8 pixels in every mode.  One launch renders up to MAX_BATCH frames that share everything but the model
+// view; CTAs are dealt (tile row, frame, tile x), so the frames' CTAs of one tile row run together and what one of them
+// pulls into L2 the others find there.
+constexpr int MAX_BATCH = 16;
+struct MipAxisArgs {
+  float invP[16];
+  float invM[MAX_BATCH][16];
+  float *out[MAX_BATCH], *alpha[MAX_BATCH];
+  cudaTextureObject_t tex[3];  // filtered pair textures by layer axis (0: not built)
+  unsigned char lax[MAX_BATCH], quad[MAX_BATCH];
+  int nx, ny, nz;              // volume extent
+  float scale;                 // 65535 or 255
+  float box[6];
+  float min_val, max_val, gamma;
+  int max_steps;
+  int width, height;
+  int n_frames;
+  int y_begin, y_end;          // pixel rows this launch renders (single-frame band launches; multiples of 16)
+  unsigned *band_done;         // as MipArgs (single frames only)
+  int band_rows, row_mode;
+  unsigned hit_tile_a, hit_tile_b;
+};
+cudaError_t launch_mip_axis(const MipAxisArgs &a, int dtype, cudaStream_t st);
+cudaError_t preload_mip_axis();
+// dst (surface of a layered pair array) = the volume re-layered along axis lax (0: width nz, height ny, nx layers;
+// 1: width nx, height nz, ny layers), read from the primary z-pair array through its point texture
+cudaError_t launch_axis_pair(const Volume &V, int dtype, int lax, cudaSurfaceObject_t dst, cudaStream_t st);
+
 // peer composite (spv_comp.cu)
 struct CompFinishArgs {
   const float *part;          // my band's staging of this parity: [world][band_pixels]

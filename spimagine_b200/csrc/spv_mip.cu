@@ -13,12 +13,6 @@
 
 namespace spv {
 
-__device__ __forceinline__ float window_value(float col, float minVal, float maxVal, float gamma) {
-  col = (maxVal == 0.f) ? col : (col - minVal) / (maxVal - minVal);
-  if (gamma != 1.f) col = powf(col, gamma);
-  return clampf_cl(col, 0.f, 1.f);
-}
-
 // -------------------------------------------------------------------------------------------------------------
 template <int FMT, bool LINEAR, bool EXACT>
 __global__ void __launch_bounds__(128) mip_ref_kernel(const MipArgs a) {

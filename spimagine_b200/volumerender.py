@@ -530,7 +530,7 @@ class VolumeRenderer(object):
             self._render_isosurface(raw_only=True)
 
     # ------------------------------------------------------------------ pipelined sequences (addition)
-    def render_sequence(self, modelViews, method="max_project", depth=2, iso_planes=7):
+    def render_sequence(self, modelViews, method="max_project", depth=2, iso_planes=7, batch=None):
         """Generator over the frames of a camera path (a spin, a keyframe sequence): for every modelView of the
         iterable it yields `self` with output / output_alpha (and, for "iso_surface", output_depth /
         output_occlusion / output_normals) holding that frame.  Unlike calling render() per frame -- which, like
@@ -540,7 +540,12 @@ class VolumeRenderer(object):
         slot's staging memory and are valid only until the NEXT frame is requested from the generator: resuming it
         issues frame i+2 into the slot of frame i (copy a frame that must outlive that); otherwise copies.
         iso_planes=2 reads back only what a display needs of an iso-surface frame (output, output_alpha: 8 of the
-        28 bytes per pixel); output_depth / output_normals / output_occlusion are None for such frames."""
+        28 bytes per pixel); output_depth / output_normals / output_occlusion are None for such frames.
+        Plain max projections (alphaPow 0) of integer volumes are rendered `batch` frames per launch (default
+        self.batch_frames = 10, at most 16; batch=1: one launch per frame as above): the frames of a launch share the
+        volume in L2 (spv_render_mip_batch), and a launch's frames are copied to pinned memory while the next launch
+        renders.  With pinned_outputs=True a yielded frame is then valid until the first frame of the launch after
+        the next one is requested."""
         if not hasattr(self, 'dataImg'):
             print("no data provided, set_data(data) before")
             return
@@ -551,6 +556,12 @@ class VolumeRenderer(object):
         planes = 2 if method == "max_project" else iso_planes
         clear = method == "iso_surface" and planes == 2
         self._fetch_iso_extras()  # a deferred read-back of an earlier render() happens before the slots are reused
+        if method == "max_project" and batch != 1:
+            p = self._mip_params()
+            if self._lib.spv_mip_batch_possible(self._ctx, C.byref(p)) == 1:
+                for _ in self._render_sequence_batched(modelViews, p, batch or self.batch_frames):
+                    yield self
+                return
         pending = []  # slots in flight, oldest first
         i = 0
         if method == "iso_surface":
@@ -586,6 +597,85 @@ class VolumeRenderer(object):
             self._lib.spv_set_tuning(self._ctx, 15, 0)
             self._lib.spv_sync(self._ctx)
             self._lib.spv_select_slot(self._ctx, 0)
+
+    def _mip_params(self, numParts=1, currentPart=0):
+        return _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma),
+                              float(self.alphaPow), int(numParts), int(currentPart), int(self.max_steps), 0)
+
+    batch_frames = 10
+
+    def _invM_of(self, modelView):
+        """float32 row-major inverse of modelView . stack scale: what update_matrices hands to the kernels"""
+        return _inv4(np.dot(modelView, self._stack_scale_mat())).astype(np.float32).ravel()
+
+    def render_batch(self, modelViews, to_host=True):
+        """Enqueue ONE launch that renders a max projection for each of up to 16 modelViews (current projection, box,
+        window, gamma, max_steps; alphaPow must be 0) and return the id of the set of planes it went to; collect with
+        batch_frames_of(set).  Raises where spv_render_mip_batch does not apply (float volumes, exact sampler, ...)."""
+        Ms = [np.asarray(M, dtype=np.float64) for M in modelViews]
+        scale = self._stack_scale_mat()
+        inv = np.ascontiguousarray(np.stack([_inv4(np.dot(M, scale)).ravel() for M in Ms]), dtype=np.float32)
+        p = self._mip_params()
+        used = C.c_int()
+        self._check(self._lib.spv_render_mip_batch(self._ctx, C.byref(p), _lib.fp(inv), len(Ms), int(bool(to_host)),
+                                                   C.byref(used)))
+        return used.value
+
+    def batch_frames_of(self, which, copy=None):
+        """[(output, output_alpha), ...] of a set render_batch(to_host=True) returned: waits for its copies; views of
+        the set's pinned planes (valid until the set is rendered into again, two render_batch calls later) or copies"""
+        host, n_frames = _lib._FP(), C.c_int()
+        self._check(self._lib.spv_batch_wait(self._ctx, int(which), C.byref(host), None, C.byref(n_frames)))
+        n = self.width * self.height
+        flat = self._pinned_view(host, n_frames.value * 2 * n)
+        if copy is None:
+            copy = not self.pinned_outputs
+        if copy:
+            flat = flat.copy()
+        shape = (self.height, self.width)
+        return [(flat[2 * f * n:(2 * f + 1) * n].reshape(shape), flat[(2 * f + 1) * n:(2 * f + 2) * n].reshape(shape))
+                for f in range(n_frames.value)]
+
+    def _render_sequence_batched(self, modelViews, p, batch):
+        import itertools
+        batch = max(1, min(int(batch), _lib.MAX_BATCH))
+        it = iter(modelViews)
+        pending = []  # (set, modelViews) in flight, oldest first
+        shape = (self.height, self.width)
+        last = None
+
+        def frames_of(entry):
+            which, Ms = entry
+            for M, (o, a) in zip(Ms, self.batch_frames_of(which)):
+                self.modelView = 1. * M
+                self.output, self.output_alpha = o, a
+                if self.output_depth is None or self.output_depth.shape != shape:
+                    self.output_depth = np.zeros(shape, np.float32)
+                yield self
+        try:
+            while True:
+                Ms = [np.asarray(M, dtype=np.float64) for M in itertools.islice(it, batch)]
+                if not Ms:
+                    break
+                last = Ms[-1]
+                pending.append((self.render_batch(Ms, True), Ms))
+                if len(pending) == 2:
+                    for _ in frames_of(pending.pop(0)):
+                        yield self
+            while pending:
+                for _ in frames_of(pending.pop(0)):
+                    yield self
+        finally:
+            self._lib.spv_sync(self._ctx)
+            if last is not None:
+                self.set_modelView(last)  # the context's own matrices follow the sequence, as with one launch per frame
+
+    def mip_axis_used(self):
+        """(layer axis, lane map) of the last plain max projection: axis 0 x / 1 y / 2 z, lane map 0 = 2x2-pixel quads /
+        1 = row quads / 2 = column quads; (-1, -1): mip_fast_kernel"""
+        a, q = C.c_int(), C.c_int()
+        self._check(self._lib.spv_mip_axis_used(self._ctx, C.byref(a), C.byref(q)))
+        return a.value, q.value
 
     def _adopt_slot(self, slot, planes, clear_extras=False):
         host = _lib._FP()
