@@ -65,6 +65,13 @@ def parse():
     ap.add_argument("--c4-steps", type=int, default=24)
     ap.add_argument("--no-mip-overlap", action="store_true",
                     help="sweep workload: every frame's kernel on the render stream, one after the other (as round 1)")
+    ap.add_argument("--batch", type=int, default=10,
+                    help="sweep workload: frames per launch of the device-resident loop and of render_sequence "
+                         "(spv_render_mip_batch: the frames of a launch share the volume in L2; at most 16; 1 = one launch "
+                         "per frame through spv_render_mip, as before)")
+    ap.add_argument("--no-axis", action="store_true",
+                    help="sweep workload: mip_fast_kernel on the z-paired array for every frame (tuning knob 16 = 0, as "
+                         "round 1) instead of the view-aligned layered copies of spv_mip_axis.cu; implies --batch 1")
     ap.add_argument("--no-iso-overlap", action="store_true",
                     help="iso workload, one GPU: every frame's screen-space passes on the render stream (as round 1)")
     ap.add_argument("--dtype", default="u16", choices=["u16", "f32"],
@@ -1281,7 +1288,7 @@ def c4_record(args, rank, local_rank, world):
     return rec
 
 
-KERNEL_SOURCES = {"mip": ("spv_mip.cu", "spv_common.cuh", "spv_kernels.h"), "iso": ("spv_iso.cu", "spv_common.cuh", "spv_kernels.h")}
+KERNEL_SOURCES = {"mip": ("spv_mip.cu", "spv_mip_axis.cu", "spv_common.cuh", "spv_kernels.h"), "iso": ("spv_iso.cu", "spv_common.cuh", "spv_kernels.h")}
 
 
 def source_sha1(family="mip"):
@@ -1358,6 +1365,23 @@ def run_sweep(args, rank, local_rank, world):
     params = _lib.MipParams(rend._box(), 0., peak, 1., float(args.alpha_pow), 1, 0, MAX_STEPS, 0)
 
     overlap = [False]
+    if args.no_axis:
+        _lib.check(lib.spv_set_tuning(ctx, 16, 0), ctx)
+        args.batch = 1
+    B = max(1, min(int(args.batch), _lib.MAX_BATCH))
+    if B > 1 and lib.spv_mip_batch_possible(ctx, C.byref(params)) != 1:
+        B = 1  # float volumes, attenuated renders, skipping, the software-sampled path: one launch per frame
+    invM_all = np.ascontiguousarray(np.stack([m[1] for m in mats]), dtype=np.float32)  # [K][16]
+
+    def device_batch(i0, n):
+        """frames i0 .. i0 + n - 1 (mod K) in ONE launch; results stay on the device"""
+        idx = [(i0 + j) % K for j in range(n)]
+        inv = invM_all[idx] if idx != list(range(idx[0], idx[0] + n)) else invM_all[idx[0]:idx[0] + n]
+        inv = np.ascontiguousarray(inv)
+        used = C.c_int()
+        rc = lib.spv_render_mip_batch(ctx, C.byref(params), _lib.fp(inv), n, 0, C.byref(used))
+        if rc:
+            _lib.check(rc, ctx)
 
     def device_step(i):
         if overlap[0]:  # frames alternate between the two output slots; slot 1's kernel runs on a second stream
@@ -1390,38 +1414,53 @@ def run_sweep(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ----
-    if not args.no_mip_overlap and not args.alpha_pow and args.mip_path != "smem":
-        _lib.check(lib.spv_set_tuning(ctx, 15, 1), ctx)
-        overlap[0] = True
-    launches0 = rend.launch_count()
-    for i in range(args.warmup):
-        device_step(i)
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        device_step(i)
-    if overlap[0]:
-        _lib.check(lib.spv_stream_join(ctx), ctx)  # the last slot-1 frame, before the closing event
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    if overlap[0]:
-        _lib.check(lib.spv_set_tuning(ctx, 15, 0), ctx)
-        _lib.check(lib.spv_select_slot(ctx, 0), ctx)
-        overlap[0] = False
-    launches = rend.launch_count() - launches0 - args.warmup
+    if B > 1:
+        # K frames in ceil(K / B) launches of (up to) B frames each; the warm-up steps the same way
+        for i in range(0, args.warmup, B):
+            device_batch(i, min(B, args.warmup - i))
+        barrier()
+        launches0 = rend.launch_count()
+        e0.record()
+        for i in range(0, K, B):
+            device_batch(i, min(B, K - i))
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = rend.launch_count() - launches0
+    else:
+        if not args.no_mip_overlap and not args.alpha_pow and args.mip_path != "smem":
+            _lib.check(lib.spv_set_tuning(ctx, 15, 1), ctx)
+            overlap[0] = True
+        launches0 = rend.launch_count()
+        for i in range(args.warmup):
+            device_step(i)
+        barrier()
+        e0.record()
+        for i in range(K):
+            device_step(i)
+        if overlap[0]:
+            _lib.check(lib.spv_stream_join(ctx), ctx)  # the last slot-1 frame, before the closing event
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if overlap[0]:
+            _lib.check(lib.spv_set_tuning(ctx, 15, 0), ctx)
+            _lib.check(lib.spv_select_slot(ctx, 0), ctx)
+            overlap[0] = False
+        launches = rend.launch_count() - launches0 - args.warmup
     kernels_per_frame = launches / float(K)
+    axis_used = rend.mip_axis_used()
 
     # ---- end to end through the public API: render_sequence() over the same frames.  Every frame's output and alpha
     # reach pinned host memory inside the timed region; frame i+1 renders while frame i is in flight
-    for r in rend.render_sequence(cams[i % K][0] for i in range(min(args.warmup, 5))):
+    for r in rend.render_sequence((cams[i % K][0] for i in range(min(args.warmup, 5))), batch=B):
         pass
     barrier()
     checksum_seq = 0.0
     b0 = rend.d2h_bytes()
     t0 = time.perf_counter()
-    for r in rend.render_sequence(cams[i][0] for i in range(K)):
+    for r in rend.render_sequence((cams[i][0] for i in range(K)), batch=B):
         checksum_seq += float(r.output[H // 2, W // 2])
     torch.cuda.synchronize()
     t_seq = time.perf_counter() - t0
@@ -1482,9 +1521,11 @@ def run_sweep(args, rank, local_rank, world):
         total_frames = K * world
         fps = total_frames / (ms * 1e-3)
         peaks, peak_src = measured_peaks()
-        launch_s = ms * 1e-3 / K
-        alg_bytes = vol.nbytes + 2 * W * H * 4
+        launch_s = ms * 1e-3 / K           # per frame (the timed region / frames)
+        alg_bytes = vol.nbytes + 2 * W * H * 4  # per frame: every voxel once + both result planes
         achieved = alg_bytes / launch_s / 1e9
+        frames_per_launch = K / float(launches) if launches else 1.
+        axis_path = axis_used[0] >= 0
         tex_peak = rend.texrate_probe(4000)
         # the same probe with the benchmark camera's footprint: neighbouring rays one pixel apart at the volume's
         # centre (2 d tan(fovy/2) / W box units, d = 4), samples L/192 apart along the view direction (mean in-box
@@ -1494,6 +1535,8 @@ def run_sweep(args, rank, local_rank, world):
         pitch = 2. * 4. * np.tan(np.radians(30.)) / W * tpu
         step = 1.23 / (MAX_STEPS // 16 * 16) * tpu
         pick = sorted(set(int(round(x)) for x in np.linspace(0, K - 1, min(K, 24))))
+        if axis_path:
+            pick = []  # the probe lays lanes out as 2x2-pixel quads on the z-paired array: not this path's footprint
         foot = []
         for j in pick:
             th = thetas[j] + 1e-3
@@ -1503,9 +1546,12 @@ def run_sweep(args, rank, local_rank, world):
         wts = np.array([issued[j] for j in pick], float)
         if wts.sum() == 0:  # attenuated renders do not count samples
             wts[:] = 1.
-        tex_foot = wts.sum() / sum(w / r for w, r in zip(wts, foot))  # time-weighted: samples / sum(samples / rate)
-        traffic, traffic_src = ncu_traffic("sweep_%d_%d" % (args.vol, W))
+        tex_foot = wts.sum() / sum(w / r for w, r in zip(wts, foot)) if pick else None  # samples / sum(samples / rate)
+        traffic, traffic_src = ncu_traffic("sweep_%d_%d%s" % (args.vol, W, "_b%d" % B if axis_path else ""))
         kernel_name = rend.mip_kernel_name() if hasattr(rend, "mip_kernel_name") else "spv::mip_fast_kernel<u16, linear>"
+        if axis_path:
+            kernel_name = "spv::mip_axis_kernel<u16> (layer axis %s, %s)" % (
+                "xyz"[axis_used[0]], ("2x2-pixel quads", "4x1 row quads", "1x4 column quads")[axis_used[1]])
         metric = sweep_metric(args)
         if f32:
             kernel_name = "spv::mip_fast_kernel<f32, linear>"
@@ -1517,7 +1563,12 @@ def run_sweep(args, rank, local_rank, world):
             "vs_baseline": None, "dtype": "f32" if f32 else "u16->f32", "data": "synthetic",
             "config": sweep_config(args),
             "notes": {
-                "l2": "the %d MB volume exceeds the 126 MB L2 and the view changes every step" % (vol.nbytes >> 20),
+                "l2": ("the %d MB volume (%d MB as the paired layered copy the kernel samples) exceeds the 126 MB L2 and the "
+                       "view changes every step%s" % (vol.nbytes >> 20, vol.nbytes >> 19, (
+                           "; the %d frames of one launch (distinct views, each computed in full) are scheduled tile row by "
+                           "tile row so that they share the slab of the volume that row crosses while it is in L2 -- that "
+                           "schedule is the kernel's design, nothing is reused between launches or steps" % B) if B > 1 else "")),
+                "frames_per_launch": B,
                 "skipping": bool(args.skip), "parallelism": "frames sharded over %d GPU(s), volume replicated" % world,
                 "angles_deg_rank0": [round(math.degrees(t), 3) for t in thetas[:4]] + ["..."] if K > 4 else
                                     [round(math.degrees(t), 3) for t in thetas]},
@@ -1531,11 +1582,16 @@ def run_sweep(args, rank, local_rank, world):
                     "d2h_ceiling_frames_per_s": world * d2h_probe * 1e9 / max(1., d2h_seq),
                     "d2h_ceiling_note": "plain device -> pinned host copies of the same size, all ranks at once, slowest "
                                         "rank: what the host link of this box leaves for `e2e`",
-                    "note": "VolumeRenderer.render_sequence(modelViews): per frame the host inverts the 4x4 modelView, "
-                            "launches, and output + alpha are copied to pinned host memory (only the rows the projected "
-                            "box can touch travel: %.0f%% of 2*W*H*4 bytes; the others already hold the miss values); "
-                            "frame i+1 renders while frame i is in flight; a pixel of every frame is read on the host" % (
-                                100. * d2h_seq / (2 * W * H * 4)),
+                    "note": ("VolumeRenderer.render_sequence(modelViews): per frame the host inverts the 4x4 modelView; %d "
+                             "frames go into one launch (spv_render_mip_batch) and the launch's output + alpha planes are "
+                             "copied to pinned host memory while the next launch renders (only the rectangle the projected "
+                             "box can touch travels: %.0f%% of 2*W*H*4 bytes; the rest already holds the miss values); a pixel "
+                             "of every frame is read on the host" % (B, 100. * d2h_seq / (2 * W * H * 4))) if B > 1 else
+                            ("VolumeRenderer.render_sequence(modelViews): per frame the host inverts the 4x4 modelView, "
+                             "launches, and output + alpha are copied to pinned host memory (only the rows the projected "
+                             "box can touch travel: %.0f%% of 2*W*H*4 bytes; the others already hold the miss values); "
+                             "frame i+1 renders while frame i is in flight; a pixel of every frame is read on the host" % (
+                                 100. * d2h_seq / (2 * W * H * 4))),
                     "checksum": checksum_seq},
             "e2e_synchronous": {"value": total_frames / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128,
                                 "d2h_bytes_per_step": int(round(d2h_sync)),
@@ -1549,9 +1605,16 @@ def run_sweep(args, rank, local_rank, world):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": launch_s * 1e6,
+                         "algorithmic_bytes_per_launch": alg_bytes * frames_per_launch,
+                         "avg_launch_us": launch_s * 1e6 * frames_per_launch,
+                         "frames_per_launch": frames_per_launch,
+                         "algorithmic_bytes_per_frame": alg_bytes, "us_per_frame": launch_s * 1e6,
                          "kernels_per_frame": kernels_per_frame, "kernel": kernel_name,
-                         "overlap": None if (args.no_mip_overlap or args.alpha_pow or args.mip_path == "smem") else
+                         "note": ("one launch renders %d frames whose CTAs run tile row by tile row, so the frames share the "
+                                  "volume in L2: `traffic` (DRAM bytes per launch) is BELOW the algorithmic bytes (every voxel "
+                                  "once PER FRAME + the result planes); the path is bound by the texture unit, see "
+                                  "roofline_tex" % B) if B > 1 else None,
+                         "overlap": None if (B > 1 or args.no_mip_overlap or args.alpha_pow or args.mip_path == "smem") else
                          "frames alternate between two output slots and two streams: a frame's kernel starts in the tail of "
                          "the one before (tuning knob 15); avg_launch_us is the timed region / frames"},
             "roofline_tex": {"bound": "texture samples", "issued_gsamples_per_s": mean_issued / launch_s / 1e9,
@@ -1560,9 +1623,9 @@ def run_sweep(args, rank, local_rank, world):
                              "frac_issued": mean_issued / launch_s / tex_peak,
                              "frac_algorithmic": mean_hits * SAMPLES_PER_RAY / launch_s / tex_peak,
                              "peak_source": "spv_texrate_probe on this GPU: cache-resident trilinear uint16 fetches",
-                             "peak_at_render_footprint_gsamples_per_s": tex_foot / 1e9,
-                             "frac_issued_at_render_footprint": mean_issued / launch_s / tex_foot,
-                             "render_footprint": {"ray_spacing_texels": pitch, "sample_spacing_texels": step,
+                             "peak_at_render_footprint_gsamples_per_s": tex_foot / 1e9 if tex_foot else None,
+                             "frac_issued_at_render_footprint": mean_issued / launch_s / tex_foot if tex_foot else None,
+                             "render_footprint": None if not tex_foot else {"ray_spacing_texels": pitch, "sample_spacing_texels": step,
                                                   "gsamples_per_s_by_angle_deg": dict(
                                                       ("%.1f" % math.degrees(thetas[j]), r / 1e9) for j, r in zip(pick, foot)),
                                                   "note": "spv_texrate_probe_footprint at the timed angles (builder-defined "

@@ -50,7 +50,6 @@ for deg in (0, 40, 90, 200):
     line = "angle %3d: max |axis - oracle| on every 64th row (mip_fast_kernel %.1e):" % (deg, float(np.abs(ref[rows] - o.output[rows]).max()))
     for forced in (None, (2, 0), (1, 1), (0, 2), (1, 0), (2, 1), (2, 2), (0, 0), (0, 1), (1, 2)):
         knob(16, 1 if forced is None else 10 + 3 * forced[0] + forced[1])
-        rend.render()   # first frame after set_data renders from the primary copy; from the second on the choice is free
         rend.render()
         used = rend.mip_axis_used()
         d = float(np.abs(rend.output[rows] - o.output[rows]).max())

@@ -86,6 +86,43 @@ __global__ void __launch_bounds__(NT) march(cudaTextureObject_t tex, const __gri
   out[((size_t)f * H + y) * W + x] = cur * 65535.f;
 }
 
+
+// Quads of 2 pixels x 2 sample PHASES: lanes (4i, 4i+1) are two neighbouring pixels of a row taking the even samples,
+// lanes (4i+2, 4i+3) the same two pixels taking the odd samples; the two halves of a ray's maximum meet in a shuffle.
+// A warp covers 16 x 1 pixels, a CTA (4 warps) 16 x 4.  The request's footprint is 2.2 x 2.6 texels instead of 4.5 x 2.
+template <int LAX>
+__global__ void __launch_bounds__(128) march_phase(cudaTextureObject_t tex, const __grid_constant__ Cams cams, int W, int H, int N,
+                                                   int S, float *out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = lane >> 2, ph = (lane >> 1) & 1;
+  const int f = blockIdx.y;
+  const int x = blockIdx.x * 16 + q * 2 + (lane & 1);
+  const int y = blockIdx.z * 4 + warp;
+  float u0, v0, w0, du, dv, dw, cur = 0.f;
+  if (setup(x, y, W, H, cams.c[f], (float)N, u0, v0, w0, du, dv, dw, S)) {
+    float a0, b0, c0, da, db, dc;
+    if (LAX == 2) { a0 = u0; da = du; b0 = v0; db = dv; c0 = w0; dc = dw; }
+    else { a0 = u0; da = du; b0 = w0; db = dw; c0 = v0; dc = dv; }
+    for (int k = 0; k < S; k += 32) {
+      float2 v[16]; float fr[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        int kj = k + 2 * j + ph;
+        float kk = (float)(kj < S ? kj : S - 1);
+        float wb = fmaf(kk, dc, c0) - 0.5f;
+        float fl = floorf(wb);
+        fr[j] = wb - fl;
+        int layer = min(max((int)fl, 0), N - 1);
+        v[j] = tex2DLayered<float2>(tex, fmaf(kk, da, a0), fmaf(kk, db, b0), layer);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) cur = fmaxf(cur, fmaf(fr[j], v[j].y - v[j].x, v[j].x));
+    }
+  }
+  cur = fmaxf(cur, __shfl_xor_sync(0xffffffffu, cur, 2));
+  if (!ph) out[((size_t)f * H + y) * W + x] = cur * 65535.f;
+}
+
 __global__ void count_hits(Cam c, int W, int H, int N, int S, unsigned long long *n) {
   int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   float a, b, d, e, f, g;
@@ -189,6 +226,13 @@ int main(int argc, char **argv) {
     }
     return ms * 1000.f / reps;
   };
+  if (argc > 3) {  // one variant, one launch size, for a profiler: exp_multiframe.bin 512 <variant> <F>
+    const int vi = atoi(argv[2]), F = atoi(argv[3]);
+    Cams cs;
+    for (int f = 0; f < F; ++f) cs.c[f] = cam_at(18.f * f);
+    printf("%s F=%d: %.1f us per launch\n", vars[vi].name, F, run(vars[vi], cs, F, 3));
+    return 0;
+  }
   // the bench's own frame set: 20 frames 18 degrees apart, in launches of F
   printf("20 frames 18 degrees apart (the 20-step bench sweep), us per frame | Gsamples/s, by frames per launch\n%-54s", "");
   const int Fs[] = {1, 2, 4, 5, 10, 16};
@@ -204,6 +248,33 @@ int main(int argc, char **argv) {
         total += run(vars[vi], cs, n, 3);
       }
       printf("  %6.1f | %4.0f", total / 20, samples / total * 1e-3);
+    }
+    printf("\n");
+  }
+  // ---- quads of 2 pixels x 2 sample phases ----
+  for (int lax : {1, 2}) {
+    printf("%s-layered, quads of 2 pixels x 2 sample phases, 16x1 warps:", lax == 1 ? "y" : "z");
+    for (int F : {1, 2, 4, 5, 10, 16}) {
+      double samples = 0, total = 0;
+      for (int g = 0; g * F < 20; ++g) {
+        Cams cs; int n = 0;
+        for (int f = 0; f < F && g * F + f < 20; ++f, ++n) { cs.c[f] = cam_at(18.f * (g * F + f)); samples += hits(cs.c[f]) * S; }
+        const dim3 grid(W / 16, n, H / 4);
+        float ms = 0;
+        for (int it = 0; it < 2; ++it) {
+          CK(cudaEventRecord(e0));
+          for (int r = 0; r < 3; ++r) {
+            if (lax == 1) march_phase<1><<<grid, 128>>>(tex, cs, W, H, N, S, out);
+            else march_phase<2><<<grid, 128>>>(tex, cs, W, H, N, S, out);
+          }
+          CK(cudaEventRecord(e1));
+          CK(cudaEventSynchronize(e1));
+          CK(cudaGetLastError());
+          CK(cudaEventElapsedTime(&ms, e0, e1));
+        }
+        total += ms * 1000.f / 3;
+      }
+      printf("  F=%d %6.1f | %4.0f", F, total / 20, samples / total * 1e-3);
     }
     printf("\n");
   }

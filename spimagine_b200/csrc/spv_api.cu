@@ -131,15 +131,18 @@ struct spv_ctx {
   cudaSurfaceObject_t axis_surf[2] = {0, 0};
   unsigned long long axis_seq[2] = {0, 0};
   bool axis_failed[2] = {false, false};  // the copy could not be allocated: not tried again for this volume
-  int axis_mode = 1;       // tuning knob 16: 0 = off (mip_fast_kernel), 1 = per-frame choice, 10 + 3 * axis + quad = forced
+  int axis_mode = 1;       // tuning knob 16: 0 = off (mip_fast_kernel), 1 = per-frame choice among the three copies (the x / y
+                           // copies are built when a frame first wants them), 2 = per-frame choice of the lane map on the
+                           // primary z copy only (no second copy: streamed time points), 10 + 3 * axis + quad = forced
   int last_axis = -1, last_quad = -1;  // what the last plain projection used (-1: mip_fast_kernel)
-  unsigned long long renders_since_upload = 0;
   // multi-frame launches (spv_render_mip_batch): two sets of [cap][out | alpha] planes, device and pinned
   float *d_batch[2] = {nullptr, nullptr}, *h_batch[2] = {nullptr, nullptr};
   int batch_cap = 0, batch_set = 1, batch_n[2] = {0, 0};
   cudaEvent_t ev_batch_rendered[2] = {nullptr, nullptr}, ev_batch_copied[2] = {nullptr, nullptr};
   bool batch_copy_pending[2] = {false, false}, batch_render_pending[2] = {false, false};
-  int batch_dirty_lo[2][MAX_BATCH], batch_dirty_hi[2][MAX_BATCH];  // rows of the pinned planes that may hold hits
+  // pixel rectangle [x0, x1) x [y0, y1) of a frame's planes that may hold hits, per set and frame: pinned (h) and device (d)
+  struct Rect { int x0, x1, y0, y1; };
+  Rect batch_h_dirty[2][MAX_BATCH], batch_d_dirty[2][MAX_BATCH];
   std::string err;
 
   size_t n() const { return (size_t)width * height; }
@@ -547,7 +550,6 @@ static int upload(spv_ctx *ctx, const void *src, bool on_device, bool no_wait = 
     if (rcj) return rcj;
   }
   ctx->upload_seq++;
-  ctx->renders_since_upload = 0;  // the layered copies along x / y are rebuilt when a frame next wants them
   const size_t es = elem_size(ctx->dtype);
   const size_t slice = (size_t)ctx->nx * ctx->ny;
   const size_t slice_bytes = slice * es;
@@ -1055,31 +1057,64 @@ static bool invert4(const float *m, double *inv) {
   return true;
 }
 
-// Tile rows [ta, tb) (8 pixels each) of an image of H rows that the box can project to: the hull of its eight corners
+// Pixel rectangle [x0, x1) x [y0, y1) of a W x H image that the box can project to: the hull of its eight corners
 // through projection . modelView, one pixel of slack.  The whole image when a corner lies behind the eye (or anything
-// is degenerate).  Scheduling only: pixels are correct for any answer.
-static void hit_tile_rows(const Camera &cam, const float *box, int H, unsigned tiles_y, unsigned &ta, unsigned &tb) {
-  ta = 0;
-  tb = tiles_y;
+// is degenerate); empty (all zeros) when the box is off screen.  Scheduling only where pixels are rendered anyway; where
+// pixels outside it are NOT rendered or copied the callers add one more tile on every side (the kernel's fp32 slab test
+// can differ from the exact geometry by ~1e-4 pixel at most).
+static void hit_rect(const Camera &cam, const float *box, int W, int H, double &x0, double &x1, double &y0, double &y1) {
+  x0 = 0.; x1 = W; y0 = 0.; y1 = H;
   double P[16], M[16];
   if (!invert4(cam.invP, P) || !invert4(cam.invM, M)) return;
-  double ymin = 1e300, ymax = -1e300;
+  double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
   for (int i = 0; i < 8; ++i) {
     const double c[4] = {box[i & 1], box[2 + ((i >> 1) & 1)], box[4 + ((i >> 2) & 1)], 1.};
     double e[4], q[4];
     for (int r = 0; r < 4; ++r) e[r] = M[4 * r] * c[0] + M[4 * r + 1] * c[1] + M[4 * r + 2] * c[2] + M[4 * r + 3] * c[3];
     for (int r = 0; r < 4; ++r) q[r] = P[4 * r] * e[0] + P[4 * r + 1] * e[1] + P[4 * r + 2] * e[2] + P[4 * r + 3] * e[3];
     if (!(q[3] > 1e-9)) return;
+    const double x = (q[0] / q[3] + 1.) * 0.5 * W;  // u = (x / Nx) * 2 - 1
     const double y = (q[1] / q[3] + 1.) * 0.5 * H;  // v = (y / Ny) * 2 - 1
-    if (!(y == y)) return;
+    if (!(x == x) || !(y == y)) return;
+    xmin = x < xmin ? x : xmin;
+    xmax = x > xmax ? x : xmax;
     ymin = y < ymin ? y : ymin;
     ymax = y > ymax ? y : ymax;
   }
-  const double lo = floor((ymin - 1.) / 8.), hi = ceil((ymax + 1.) / 8.) + 1.;
-  if (lo >= (double)tiles_y || hi <= 0.) { ta = tb = 0; return; }  // the box is off screen: nothing to order
+  xmin -= 1.; ymin -= 1.; xmax += 1.; ymax += 1.;
+  if (xmin >= (double)W || xmax <= 0. || ymin >= (double)H || ymax <= 0.) { x0 = x1 = y0 = y1 = 0.; return; }
+  x0 = xmin > 0. ? xmin : 0.;
+  x1 = xmax < (double)W ? xmax : (double)W;
+  y0 = ymin > 0. ? ymin : 0.;
+  y1 = ymax < (double)H ? ymax : (double)H;
+}
+
+// Tile rows [ta, tb) (8 pixels each) of an image of H rows that the box can project to (conservative; any answer is
+// correct for scheduling).
+static void hit_tile_rows(const Camera &cam, const float *box, int H, unsigned tiles_y, unsigned &ta, unsigned &tb) {
+  double x0, x1, y0, y1;
+  hit_rect(cam, box, 16, H, x0, x1, y0, y1);
+  if (!(y1 > y0)) { ta = tb = 0; return; }
+  const double lo = floor(y0 / 8.), hi = ceil(y1 / 8.) + 1.;
   ta = lo > 0. ? (unsigned)lo : 0u;
   tb = hi < (double)tiles_y ? (unsigned)hi : tiles_y;
   if (tb < ta) tb = ta;
+}
+
+// Pixel rectangle, in whole CTA tiles (16 x 8 pixels) with one tile of slack on every side, outside of which every ray
+// of the frame misses the box; empty when the box is off screen.
+static void miss_free_rect(const Camera &cam, const float *box, int W, int H, int &xa, int &xb, int &ya, int &yb) {
+  double x0, x1, y0, y1;
+  hit_rect(cam, box, W, H, x0, x1, y0, y1);
+  if (!(x1 > x0) || !(y1 > y0)) { xa = xb = ya = yb = 0; return; }
+  xa = ((int)floor(x0 / 16.) - 1) * 16;
+  xb = ((int)ceil(x1 / 16.) + 1) * 16;
+  ya = ((int)floor(y0 / 8.) - 1) * 8;
+  yb = ((int)ceil(y1 / 8.) + 1) * 8;
+  xa = xa > 0 ? xa : 0;
+  ya = ya > 0 ? ya : 0;
+  xb = xb < W ? xb : W;
+  yb = yb < H ? yb : H;
 }
 
 // ---- view-aligned layered copies (spv_mip_axis.cu) ------------------------------------------------------------------
@@ -1262,13 +1297,13 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     if (rc) return rc;
     bands = 1;
   }
-  // view-aligned layered copy + lane map of this frame (spv_mip_axis.cu); the x / y copies are built from the second
-  // frame after an upload on (a time point that is rendered once does not pay for them)
+  // view-aligned layered copy + lane map of this frame (spv_mip_axis.cu): a function of the camera alone, so a view
+  // renders to the same bits whatever was rendered before it
   const bool axis = plain && linear && !raw_only && !push && !smem && p->num_parts == 1 && p->current_part == 0 &&
                     axis_path_possible(ctx);
   int lax = 2, quad = 0;
   if (axis) {
-    choose_axis(ctx, ctx->cam.invP, ctx->cam.invM, p->box, p->max_steps, ctx->renders_since_upload >= 1, lax, quad);
+    choose_axis(ctx, ctx->cam.invP, ctx->cam.invM, p->box, p->max_steps, ctx->axis_mode != 2, lax, quad);
     if (lax != 2) {
       rc = ensure_axis(ctx, lax);
       if (rc && !ctx->axis_failed[lax]) return rc;
@@ -1277,7 +1312,6 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
   }
   ctx->last_axis = axis ? lax : -1;
   ctx->last_quad = axis ? quad : -1;
-  ctx->renders_since_upload++;
   MipAxisArgs ax;
   if (axis) {
     memset(&ax, 0, sizeof ax);
@@ -1298,6 +1332,11 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     ax.y_begin = m.y_begin; ax.y_end = m.y_end;
     ax.band_done = m.band_done; ax.band_rows = m.band_rows; ax.row_mode = m.row_mode;
     ax.hit_tile_a = m.hit_tile_a; ax.hit_tile_b = m.hit_tile_b;
+    ax.tile_x0[0] = ax.tile_y0[0] = 0;  // every tile of the band: callers of single frames own the planes' contents
+    ax.tile_nx[0] = (unsigned short)((ctx->width + 15) / 16);
+    ax.tile_ny[0] = (unsigned short)((m.y_end - m.y_begin + 7) / 8);
+    ax.rend_x0[0] = ax.rend_y0[0] = 0;
+    ax.rend_x1[0] = ax.rend_y1[0] = 0xffff;
     return launch_mip_axis(ax, ctx->dtype, st);
   };
   rc = begin_render(ctx);
@@ -1479,6 +1518,9 @@ SPV_API int spv_render_mip_to_host(spv_ctx *ctx, const spv_mip_params *p, int ba
 // ---- several frames per launch --------------------------------------------------------------------------------------
 static int ensure_batch(spv_ctx *ctx, int n) {
   if (n <= ctx->batch_cap) return 0;
+  // room for the largest launch at once (a sequence's first launch may be a short one: no reallocation -- which waits
+  // for everything in flight -- in the middle of it), unless the planes are huge
+  if ((size_t)MAX_BATCH * 2 * ctx->n() * sizeof(float) <= ((size_t)256 << 20)) n = MAX_BATCH;
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaStreamSynchronize(ctx->copy_stream));
   CU(cudaStreamSynchronize(ctx->copy_stream2));
@@ -1487,8 +1529,9 @@ static int ensure_batch(spv_ctx *ctx, int n) {
   for (int s = 0; s < 2; ++s) {
     CU(cudaMalloc(&ctx->d_batch[s], bytes));
     CU(cudaMallocHost(&ctx->h_batch[s], bytes));
-    memset(ctx->h_batch[s], 0, bytes);  // every row holds the miss values (out 0, alpha 0: integer volumes only)
-    for (int f = 0; f < MAX_BATCH; ++f) ctx->batch_dirty_lo[s][f] = ctx->batch_dirty_hi[s][f] = 0;
+    memset(ctx->h_batch[s], 0, bytes);  // every pixel holds the miss values (out 0, alpha 0: integer volumes only)
+    CU(cudaMemsetAsync(ctx->d_batch[s], 0, bytes, ctx->stream));
+    for (int f = 0; f < MAX_BATCH; ++f) ctx->batch_h_dirty[s][f] = ctx->batch_d_dirty[s][f] = spv_ctx::Rect{0, 0, 0, 0};
   }
   ctx->batch_cap = n;
   return 0;
@@ -1519,7 +1562,7 @@ SPV_API int spv_render_mip_batch(spv_ctx *ctx, const spv_mip_params *p, const fl
   memcpy(ax.invM, invM, (size_t)n * 16 * sizeof(float));
   for (int f = 0; f < n; ++f) {
     int lax, quad;
-    choose_axis(ctx, ctx->cam.invP, invM + 16 * f, p->box, p->max_steps, true, lax, quad);
+    choose_axis(ctx, ctx->cam.invP, invM + 16 * f, p->box, p->max_steps, ctx->axis_mode != 2, lax, quad);
     if (lax != 2) {
       rc = ensure_axis(ctx, lax);
       if (rc && !ctx->axis_failed[lax]) return rc;
@@ -1532,7 +1575,6 @@ SPV_API int spv_render_mip_batch(spv_ctx *ctx, const spv_mip_params *p, const fl
   }
   ctx->last_axis = ax.lax[0];
   ctx->last_quad = ax.quad[0];
-  ctx->renders_since_upload += (unsigned long long)n;
   ax.tex[0] = ctx->axis_tex[0]; ax.tex[1] = ctx->axis_tex[1]; ax.tex[2] = ctx->tex_lin;
   ax.nx = ctx->nx; ax.ny = ctx->ny; ax.nz = ctx->gnz;
   ax.scale = ctx->dtype == SPV_U16 ? 65535.f : 255.f;
@@ -1544,11 +1586,83 @@ SPV_API int spv_render_mip_batch(spv_ctx *ctx, const spv_mip_params *p, const fl
   if (rc) return rc;
   if (ctx->batch_copy_pending[set]) {  // the copies out of this set's planes, two calls ago
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_batch_copied[set], 0));
-    if (to_host) CU(cudaEventSynchronize(ctx->ev_batch_copied[set]));  // the pinned rows are about to be cleaned by the host
+    if (to_host) CU(cudaEventSynchronize(ctx->ev_batch_copied[set]));  // the pinned planes are about to be cleaned by the host
     ctx->batch_copy_pending[set] = false;
   }
   rc = begin_render(ctx);
   if (rc) return rc;
+  // Only the CTA tiles the projected box can touch are launched (a third of the image on configs[1]; the ray setup of a
+  // tile that misses costs as much as that of one that hits).  Every pixel outside a frame's rectangle is a miss: the
+  // device planes hold the miss values there -- what an earlier frame of this slot left outside is cleared first.
+  const int W = ctx->width, H = ctx->height;
+  const size_t np = ctx->n();
+  spv_ctx::Rect rect[MAX_BATCH];
+  for (int f = 0; f < n; ++f) {
+    Camera cam;
+    memcpy(cam.invP, ctx->cam.invP, sizeof cam.invP);
+    memcpy(cam.invM, invM + 16 * f, sizeof cam.invM);
+    spv_ctx::Rect &r = rect[f];
+    if (ctx->clip_copies) miss_free_rect(cam, p->box, W, H, r.x0, r.x1, r.y0, r.y1);
+    else r = spv_ctx::Rect{0, W, 0, H};
+    // launched: the tiles of the new rectangle and of the old one (whatever lies outside the new one is cleared by the
+    // kernel: a tile of zeros costs a few stores, a separate memset per frame costs a launch)
+    spv_ctx::Rect &d = ctx->batch_d_dirty[set][f];
+    spv_ctx::Rect u = r;
+    if (d.x1 > d.x0 && d.y1 > d.y0) {
+      if (u.x1 > u.x0 && u.y1 > u.y0) {
+        u.x0 = d.x0 < u.x0 ? d.x0 : u.x0; u.x1 = d.x1 > u.x1 ? d.x1 : u.x1;
+        u.y0 = d.y0 < u.y0 ? d.y0 : u.y0; u.y1 = d.y1 > u.y1 ? d.y1 : u.y1;
+      } else {
+        u = d;
+      }
+    }
+    ax.tile_x0[f] = (unsigned short)(u.x0 / 16);
+    ax.tile_y0[f] = (unsigned short)(u.y0 / 8);
+    ax.tile_nx[f] = (unsigned short)((u.x1 + 15) / 16 - u.x0 / 16);
+    ax.tile_ny[f] = (unsigned short)((u.y1 + 7) / 8 - u.y0 / 8);
+    ax.rend_x0[f] = (unsigned short)(r.x0 / 16);
+    ax.rend_x1[f] = (unsigned short)((r.x1 + 15) / 16);
+    ax.rend_y0[f] = (unsigned short)(r.y0 / 8);
+    ax.rend_y1[f] = (unsigned short)((r.y1 + 7) / 8);
+    d = r;
+  }
+  {  // the same tile rows for every frame: the frames' CTAs that run together cross the same slab of the volume
+    unsigned y0 = 0xffff, y1 = 0;
+    for (int f = 0; f < n; ++f)
+      if (ax.tile_ny[f] && ax.tile_nx[f]) {
+        y0 = ax.tile_y0[f] < y0 ? ax.tile_y0[f] : y0;
+        y1 = (unsigned)ax.tile_y0[f] + ax.tile_ny[f] > y1 ? (unsigned)ax.tile_y0[f] + ax.tile_ny[f] : y1;
+      }
+    for (int f = 0; f < n; ++f)
+      if (ax.tile_ny[f] && ax.tile_nx[f]) {  // rows added to a frame lie outside its rectangle: filled with the miss values
+        ax.tile_y0[f] = (unsigned short)y0;
+        ax.tile_ny[f] = (unsigned short)(y1 - y0);
+      }
+  }
+  // Read-back behind the launch, in bands of tile rows where the driver offers stream memory operations: the CTAs count
+  // themselves into their band's counter (all frames' CTAs of a tile row run together, so a band of every frame completes
+  // at about the same time) and the copy streams wait for a counter before they move that band of every frame -- the
+  // launch's own copies overlap its rendering, not only the next launch's.
+  int nb = 1, band_rows = H;
+  unsigned launch_y0 = 0, launch_ny = 0;
+  for (int f = 0; f < n; ++f)
+    if (ax.tile_ny[f] && ax.tile_nx[f]) { launch_y0 = ax.tile_y0[f]; launch_ny = ax.tile_ny[f]; }
+  const bool banded = to_host && launch_ny > 0 && wait_value_fn() != nullptr && ctx->bands != 1;
+  if (banded) {
+    nb = ctx->bands > 0 ? ctx->bands : 4;
+    if (nb > 16) nb = 16;
+    band_rows = (((int)launch_ny * 8 + nb - 1) / nb + 15) / 16 * 16;
+    nb = ((int)launch_ny * 8 + band_rows - 1) / band_rows;
+    ax.band_done = ctx->d_band_done;
+    ax.band_rows = band_rows;
+    ax.row_mode = 2;  // tile rows in their natural order
+    for (int b = 0; b < nb; ++b) {
+      const unsigned t0 = (unsigned)(b * band_rows / 8), t1 = (unsigned)((b + 1) * band_rows / 8);
+      const unsigned rows = (t1 < launch_ny ? t1 : launch_ny) - t0;
+      for (int f = 0; f < n; ++f)
+        if (ax.tile_ny[f] && ax.tile_nx[f]) ctx->band_expect[b] += (unsigned)ax.tile_nx[f] * rows;
+    }
+  }
   CU(launch_mip_axis(ax, ctx->dtype, ctx->stream));
   ctx->launches += 1;
   ctx->last_method = 0;
@@ -1560,40 +1674,52 @@ SPV_API int spv_render_mip_batch(spv_ctx *ctx, const spv_mip_params *p, const fl
   ctx->batch_set = set;
   *set_out = set;
   if (!to_host) return 0;
-  const int H = ctx->height;
-  const size_t W = (size_t)ctx->width, np = ctx->n();
-  CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_batch_rendered[set], 0));
-  if (ctx->copy_streams > 1) CU(cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_batch_rendered[set], 0));
-  for (int f = 0; f < n; ++f) {
-    int ca = 0, cb = H;
-    if (ctx->clip_copies) {  // rows the box cannot project to are misses: not copied (as spv_render_mip_to_host)
-      Camera cam;
-      memcpy(cam.invP, ctx->cam.invP, sizeof cam.invP);
-      memcpy(cam.invM, invM + 16 * f, sizeof cam.invM);
-      unsigned ta, tb;
-      hit_tile_rows(cam, p->box, H, (unsigned)((H + 7) / 8), ta, tb);
-      ca = (int)ta * 8 - 8 > 0 ? (int)ta * 8 - 8 : 0;
-      cb = (int)tb * 8 + 8 < H ? (int)tb * 8 + 8 : H;
-      if (ca >= cb) ca = cb = 0;
-    }
+  if (!banded) {
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_batch_rendered[set], 0));
+    if (ctx->copy_streams > 1) CU(cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_batch_rendered[set], 0));
+  }
+  for (int f = 0; f < n; ++f) {  // the pinned planes: what an earlier frame left outside this frame's rectangle is cleared
+    const spv_ctx::Rect &r = rect[f];
     float *hf = ctx->h_batch[set] + (size_t)f * 2 * np;
-    // rows of the pinned planes outside [ca, cb) that an earlier frame left hits in go back to the miss values
-    int &lo = ctx->batch_dirty_lo[set][f], &hi = ctx->batch_dirty_hi[set][f];
-    const int parts[2][2] = {{lo, hi < ca ? hi : ca}, {lo > cb ? lo : cb, hi}};
-    for (int k = 0; k < 2; ++k)
-      if (parts[k][0] < parts[k][1]) {
-        const size_t o0 = (size_t)parts[k][0] * W, cnt = (size_t)(parts[k][1] - parts[k][0]) * W;
-        memset(hf + o0, 0, cnt * sizeof(float));
-        memset(hf + np + o0, 0, cnt * sizeof(float));
+    spv_ctx::Rect &d = ctx->batch_h_dirty[set][f];
+    if (!(d.x0 >= r.x0 && d.x1 <= r.x1 && d.y0 >= r.y0 && d.y1 <= r.y1))
+      for (int y = d.y0; y < d.y1; ++y) {
+        const bool row_in = y >= r.y0 && y < r.y1;
+        const int segs[2][2] = {{d.x0, row_in ? (d.x1 < r.x0 ? d.x1 : r.x0) : d.x1}, {row_in ? (d.x0 > r.x1 ? d.x0 : r.x1) : d.x1, d.x1}};
+        for (int k = 0; k < 2; ++k)
+          if (segs[k][0] < segs[k][1]) {
+            memset(hf + (size_t)y * W + segs[k][0], 0, (size_t)(segs[k][1] - segs[k][0]) * sizeof(float));
+            memset(hf + np + (size_t)y * W + segs[k][0], 0, (size_t)(segs[k][1] - segs[k][0]) * sizeof(float));
+          }
       }
-    lo = ca;
-    hi = cb;
-    if (ca >= cb) continue;
-    const size_t off = (size_t)ca * W, cnt = (size_t)(cb - ca) * W;
-    cudaStream_t cs = (ctx->copy_streams > 1 && (f & 1)) ? ctx->copy_stream2 : ctx->copy_stream;
-    CU(cudaMemcpy2DAsync(hf + off, np * sizeof(float), ax.out[f] + off, np * sizeof(float), cnt * sizeof(float), 2,
-                         cudaMemcpyDeviceToHost, cs));
-    ctx->d2h_bytes += 2 * cnt * sizeof(float);
+    d = r;
+  }
+  for (int b = 0; b < nb; ++b) {
+    const int by0 = banded ? (int)launch_y0 * 8 + b * band_rows : 0, by1 = banded ? by0 + band_rows : H;
+    if (banded)
+      for (int k = 0; k < (ctx->copy_streams > 1 ? 2 : 1); ++k) {
+        CUresult wr = wait_value_fn()(k ? ctx->copy_stream2 : ctx->copy_stream, (CUdeviceptr)(uintptr_t)(ctx->d_band_done + b),
+                                      ctx->band_expect[b], CU_STREAM_WAIT_VALUE_GEQ);
+        if (wr != CUDA_SUCCESS) return fail(ctx, (int)wr, "cuStreamWaitValue32 failed");
+      }
+    for (int f = 0; f < n; ++f) {
+      const spv_ctx::Rect &r = rect[f];
+      const int y0 = r.y0 > by0 ? r.y0 : by0, y1 = r.y1 < by1 ? r.y1 : by1;
+      if (r.x1 <= r.x0 || y1 <= y0) continue;
+      float *hf = ctx->h_batch[set] + (size_t)f * 2 * np;
+      // both planes' rectangles in one 3-D copy (depth 2 = the two planes)
+      cudaMemcpy3DParms cp;
+      memset(&cp, 0, sizeof cp);
+      cp.srcPtr = make_cudaPitchedPtr(ax.out[f], (size_t)W * sizeof(float), (size_t)W, (size_t)H);
+      cp.dstPtr = make_cudaPitchedPtr(hf, (size_t)W * sizeof(float), (size_t)W, (size_t)H);
+      cp.srcPos = make_cudaPos((size_t)r.x0 * sizeof(float), (size_t)y0, 0);
+      cp.dstPos = cp.srcPos;
+      cp.extent = make_cudaExtent((size_t)(r.x1 - r.x0) * sizeof(float), (size_t)(y1 - y0), 2);
+      cp.kind = cudaMemcpyDeviceToHost;
+      cudaStream_t cs = (ctx->copy_streams > 1 && (f & 1)) ? ctx->copy_stream2 : ctx->copy_stream;
+      CU(cudaMemcpy3DAsync(&cp, cs));
+      ctx->d2h_bytes += 2 * (size_t)(r.x1 - r.x0) * (size_t)(y1 - y0) * sizeof(float);
+    }
   }
   if (ctx->copy_streams > 1) {
     CU(cudaEventRecord(ctx->ev_copy2, ctx->copy_stream2));

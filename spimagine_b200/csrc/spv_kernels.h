@@ -97,6 +97,11 @@ struct MipAxisArgs {
   float *out[MAX_BATCH], *alpha[MAX_BATCH];
   cudaTextureObject_t tex[3];  // filtered pair textures by layer axis (0: not built)
   unsigned char lax[MAX_BATCH], quad[MAX_BATCH];
+  // CTA tiles (16x8 pixels) [tile_x0, tile_x0 + tile_nx) x [tile_y0, tile_y0 + tile_ny) of frame f are launched.  Of
+  // those, the tiles [rend_x0, rend_x1) x [rend_y0, rend_y1) -- the ones the projected box can touch -- are rendered,
+  // the others are filled with the miss values (what an earlier frame left in these planes outside the new rectangle).
+  unsigned short tile_x0[MAX_BATCH], tile_y0[MAX_BATCH], tile_nx[MAX_BATCH], tile_ny[MAX_BATCH];
+  unsigned short rend_x0[MAX_BATCH], rend_x1[MAX_BATCH], rend_y0[MAX_BATCH], rend_y1[MAX_BATCH];
   int nx, ny, nz;              // volume extent
   float scale;                 // 65535 or 255
   float box[6];

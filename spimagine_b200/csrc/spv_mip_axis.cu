@@ -52,21 +52,28 @@ cudaError_t launch_axis_pair(const Volume &V, int dtype, int lax, cudaSurfaceObj
 }
 
 // ---- the render kernel --------------------------------------------------------------------------------------------
-template <int DT>
-__global__ void __launch_bounds__(128) mip_axis_kernel(const __grid_constant__ MipAxisArgs a) {
-  __shared__ __align__(16) float s_out[4][32];
-  __shared__ __align__(16) float s_alpha[4][32];
+// one CTA tile (bx, by) of frame f
+__device__ __forceinline__ void mip_axis_tile(const MipAxisArgs &a, int f, unsigned bx, unsigned by, float (*s_out)[32],
+                                              float (*s_alpha)[32]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = blockIdx.y;
-  const unsigned bx = blockIdx.x;
-  unsigned by = blockIdx.z + a.y_begin / 8;
-  if (a.band_done) {  // read-back overlap of a single frame: the order mip_fast_kernel deals its tile rows in
-    if (a.row_mode == 1) {
-      const unsigned ta = a.hit_tile_a, tb = a.hit_tile_b, nout = gridDim.z - (tb - ta);
-      by = blockIdx.z < nout ? (blockIdx.z < ta ? blockIdx.z : tb + (blockIdx.z - ta)) : ta + (blockIdx.z - nout);
+  const unsigned Nx = a.width, Ny = a.height;
+  if (bx < a.rend_x0[f] || bx >= a.rend_x1[f] || by < a.rend_y0[f] || by >= a.rend_y1[f]) {
+    // outside the rectangle the box can project to: every ray misses (out 0, alpha 0), no ray is set up
+    const unsigned px0 = bx * 16, py0 = by * 8;
+    if (Nx % 4 == 0 && px0 + 16 <= Nx && py0 + 8 <= Ny) {
+      if (threadIdx.x < 64) {  // 32 float4 per plane
+        float *plane = threadIdx.x < 32 ? a.out[f] : a.alpha[f];
+        const unsigned v = threadIdx.x & 31;
+        *reinterpret_cast<float4 *>(plane + (size_t)(py0 + (v >> 2)) * Nx + px0 + (v & 3) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     } else {
-      by = (blockIdx.z & 1u) ? gridDim.z - 1u - (blockIdx.z >> 1) : (blockIdx.z >> 1);
+      const unsigned x = px0 + (threadIdx.x & 15), y = py0 + (threadIdx.x >> 4);
+      if (x < Nx && y < Ny) {
+        a.out[f][(size_t)y * Nx + x] = 0.f;
+        a.alpha[f][(size_t)y * Nx + x] = 0.f;
+      }
     }
+    return;
   }
   // lanes -> pixels.  tw x th: the warp's tile; (lx, ly): this lane's pixel in it; quads are lanes 4i..4i+3.
   const int quad = a.quad[f], q = lane >> 2, i = lane & 3;
@@ -84,7 +91,6 @@ __global__ void __launch_bounds__(128) mip_axis_kernel(const __grid_constant__ M
   }
   const int th = 32 / tw;
   const unsigned x = tx0 + lx, y = ty0 + ly;
-  const unsigned Nx = a.width, Ny = a.height;
   const bool inb = x < Nx && y < Ny;
 
   Ray r = make_ray(x, y, Nx, Ny, a.invP, a.invM[f], a.box);
@@ -146,17 +152,42 @@ __global__ void __launch_bounds__(128) mip_axis_kernel(const __grid_constant__ M
     out_rows[p] = outVal;
     alpha_rows[p] = alphaVal;
   }
-  if (a.band_done) {  // this CTA's rows are stored: tell the copy stream
+}
+
+template <int DT>
+__global__ void __launch_bounds__(128) mip_axis_kernel(const __grid_constant__ MipAxisArgs a) {
+  __shared__ __align__(16) float s_out[4][32];
+  __shared__ __align__(16) float s_alpha[4][32];
+  const int f = blockIdx.y;
+  if (blockIdx.x >= a.tile_nx[f] || blockIdx.z >= a.tile_ny[f]) return;  // the grid covers the largest frame's tiles
+  const unsigned bx = blockIdx.x + a.tile_x0[f];
+  unsigned by = blockIdx.z + a.tile_y0[f] + a.y_begin / 8;
+  if (a.band_done && a.row_mode < 2) {  // read-back overlap of a single frame: mip_fast_kernel's order of tile rows
+    if (a.row_mode == 1) {
+      const unsigned ta = a.hit_tile_a, tb = a.hit_tile_b, nout = gridDim.z - (tb - ta);
+      by = blockIdx.z < nout ? (blockIdx.z < ta ? blockIdx.z : tb + (blockIdx.z - ta)) : ta + (blockIdx.z - nout);
+    } else {
+      by = (blockIdx.z & 1u) ? gridDim.z - 1u - (blockIdx.z >> 1) : (blockIdx.z >> 1);
+    }
+  }
+  mip_axis_tile(a, f, bx, by, s_out, s_alpha);
+  if (a.band_done) {  // this CTA's rows are stored: tell the copy streams (bands count from the first launched tile row)
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
-      atomicAdd(a.band_done + (by * 8) / (unsigned)a.band_rows, 1u);
+      atomicAdd(a.band_done + ((by - a.tile_y0[f]) * 8) / (unsigned)a.band_rows, 1u);
     }
   }
 }
 
 cudaError_t launch_mip_axis(const MipAxisArgs &a, int dtype, cudaStream_t st) {
-  const dim3 grid((a.width + 15) / 16, a.n_frames, (a.y_end - a.y_begin + 7) / 8);
+  unsigned gx = 0, gz = 0;
+  for (int f = 0; f < a.n_frames; ++f) {
+    gx = a.tile_nx[f] > gx ? a.tile_nx[f] : gx;
+    gz = a.tile_ny[f] > gz ? a.tile_ny[f] : gz;
+  }
+  if (gx == 0 || gz == 0) return cudaSuccess;  // no frame's box is on screen
+  const dim3 grid(gx, a.n_frames, gz);
   if (dtype == 1) mip_axis_kernel<1><<<grid, 128, 0, st>>>(a);
   else if (dtype == 2) mip_axis_kernel<2><<<grid, 128, 0, st>>>(a);
   else return cudaErrorInvalidValue;

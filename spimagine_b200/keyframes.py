@@ -285,6 +285,13 @@ def apply_transform(renderer, transformData, isPerspective=True):
     return modelView, ("iso_surface" if td.isIso else "max_project")
 
 
+def _static_key(td, source, isPerspective):
+    """everything apply_transform / the time-point upload set from a TransformData except the modelView"""
+    pos = None if source is None else int(np.clip(td.dataPos, 0, len(source) - 1))
+    return (pos, float(td.minVal), float(td.maxVal), float(td.gamma), float(td.alphaPow),
+            tuple(float(b) for b in td.bounds), np.asarray(camera_of(td, isPerspective)[1], np.float64).tobytes())
+
+
 def keyframe_times(nFrames):
     """Key times of the record loop (keyframe_view.py:644-653): recordPos = 1 .. nFrames at recordPos / nFrames."""
     return [(k, 1. * k / nFrames) for k in range(1, nFrames + 1)]
@@ -343,6 +350,20 @@ def render_keyframes(renderer, keyList, nFrames, source=None, isPerspective=True
                 prepare(tds[k])
                 renderer.render(method=method)
                 yield times[k][0], tds[k], renderer
+        elif method == "max_project":
+            # stretches in which only the camera moves (same time point, window, box, projection) go to render_sequence
+            # as a list of modelViews: several frames per launch (VolumeRenderer.render_sequence, spv_render_mip_batch)
+            k0 = i
+            while k0 < j:
+                key0 = _static_key(tds[k0], source, isPerspective)
+                k1 = k0 + 1
+                while k1 < j and _static_key(tds[k1], source, isPerspective) == key0:
+                    k1 += 1
+                prepare(tds[k0])
+                views = [camera_of(tds[k], isPerspective)[0] for k in range(k0, k1)]
+                for k, r in zip(range(k0, k1), renderer.render_sequence(views, method=method)):
+                    yield times[k][0], tds[k], r
+                k0 = k1
         else:
             views = (prepare(tds[k])[0] for k in range(i, j))
             for k, r in zip(range(i, j), renderer.render_sequence(views, method=method, iso_planes=iso_planes)):

@@ -419,6 +419,9 @@ class TimelapsePlayer(object):
         self.size = size
         self._kw = dict(kw)
         self.rend = VolumeRenderer(size, **kw)
+        # time points are rendered through the primary (z) copy, streamed or resident: a streamed one is rendered once
+        # (no second layered copy per upload), and a time point looks the same whichever way it is played
+        self.rend.set_view_copies("primary")
         self.resident = {}  # t -> VolumeRenderer holding frame t
 
     def my_frames(self, n_frames):
@@ -437,6 +440,7 @@ class TimelapsePlayer(object):
         frames = self.my_frames(len(source)) if frames is None else frames
         for t in frames:
             r = VolumeRenderer(self.size, **self._kw)
+            r.set_view_copies("primary")
             if device_ptrs:
                 ptr, shape, dtype = source[t]
                 r.set_data_device(ptr, shape, dtype)

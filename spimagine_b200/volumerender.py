@@ -541,11 +541,14 @@ class VolumeRenderer(object):
         issues frame i+2 into the slot of frame i (copy a frame that must outlive that); otherwise copies.
         iso_planes=2 reads back only what a display needs of an iso-surface frame (output, output_alpha: 8 of the
         28 bytes per pixel); output_depth / output_normals / output_occlusion are None for such frames.
-        Plain max projections (alphaPow 0) of integer volumes are rendered `batch` frames per launch (default
-        self.batch_frames = 10, at most 16; batch=1: one launch per frame as above): the frames of a launch share the
-        volume in L2 (spv_render_mip_batch), and a launch's frames are copied to pinned memory while the next launch
-        renders.  With pinned_outputs=True a yielded frame is then valid until the first frame of the launch after
-        the next one is requested."""
+        Plain max projections (alphaPow 0) of integer volumes are rendered `batch` frames per launch (at most 16;
+        batch=1: one launch per frame as above): the frames of a launch share the volume in L2 (spv_render_mip_batch),
+        and a launch's frames are copied to pinned memory band by band while it renders.  All frames of a launch use the
+        renderer's settings (projection, window, box, data) as they are when the launch is issued, so this is the
+        default (self.batch_frames = 10 per launch) only when modelViews is a list / tuple / array; an iterator that
+        changes the renderer as it is pulled (keyframes.render_keyframes) gets one launch per frame unless batch is
+        given.  With pinned_outputs=True a yielded frame is then valid until the first frame of the launch after the
+        next one is requested."""
         if not hasattr(self, 'dataImg'):
             print("no data provided, set_data(data) before")
             return
@@ -556,7 +559,10 @@ class VolumeRenderer(object):
         planes = 2 if method == "max_project" else iso_planes
         clear = method == "iso_surface" and planes == 2
         self._fetch_iso_extras()  # a deferred read-back of an earlier render() happens before the slots are reused
-        if method == "max_project" and batch != 1:
+        # several frames per launch: only when pulling a view cannot change the renderer's state behind the frames
+        # already collected for the launch -- a list / tuple / array of matrices, or a caller that asks for it (batch=k)
+        materialized = isinstance(modelViews, (list, tuple, np.ndarray))
+        if method == "max_project" and batch != 1 and (batch is not None or materialized):
             p = self._mip_params()
             if self._lib.spv_mip_batch_possible(self._ctx, C.byref(p)) == 1:
                 for _ in self._render_sequence_batched(modelViews, p, batch or self.batch_frames):
@@ -666,9 +672,21 @@ class VolumeRenderer(object):
                 for _ in frames_of(pending.pop(0)):
                     yield self
         finally:
-            self._lib.spv_sync(self._ctx)
-            if last is not None:
-                self.set_modelView(last)  # the context's own matrices follow the sequence, as with one launch per frame
+            if getattr(self, "_ctx", None) is not None and self._ctx.value:  # (not closed under an abandoned generator)
+                self._lib.spv_sync(self._ctx)
+                if last is not None:
+                    self.set_modelView(last)  # the context's own matrices follow the sequence, as with one launch per frame
+
+    def set_view_copies(self, mode="auto"):
+        """Which layered copies of an integer volume plain max projections sample (csrc/spv_mip_axis.cu): "auto" (default)
+        = per frame the copy with pairs along x, y or z under which a texture request stays inside one layer -- the x / y
+        copies cost 4 bytes per voxel each and are built on the device when a frame first wants them after an upload;
+        "primary" = the z copy only (time points that are uploaded, rendered once and replaced); "off" = mip_fast_kernel,
+        as round 1."""
+        codes = {"off": 0, "auto": 1, "primary": 2}
+        if mode not in codes:
+            raise KeyError("view copies = '%s' not defined, valid: %s" % (mode, sorted(codes)))
+        self._check(self._lib.spv_set_tuning(self._ctx, 16, codes[mode]))
 
     def mip_axis_used(self):
         """(layer axis, lane map) of the last plain max projection: axis 0 x / 1 y / 2 z, lane map 0 = 2x2-pixel quads /

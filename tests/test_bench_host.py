@@ -35,7 +35,7 @@ def test_traffic_is_only_reported_for_the_sources_it_was_measured_on(tmp_path, m
     monkeypatch.setattr(bench, "ROOT", str(tmp_path))
     os.makedirs(tmp_path / "profiles")
     os.makedirs(tmp_path / "spimagine_b200" / "csrc")
-    for f in ("spv_mip.cu", "spv_common.cuh", "spv_kernels.h"):
+    for f in bench.KERNEL_SOURCES["mip"]:
         (tmp_path / "spimagine_b200" / "csrc" / f).write_text("// " + f)
     t, why = bench.ncu_traffic("sweep_512_1024")
     assert t is None and "no ncu capture" in why

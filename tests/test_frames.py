@@ -133,6 +133,7 @@ def test_timelapse_player_streams_from_a_spim_folder(tmp_path):
     frames.createSpimFolder(folder, vols)
     M, P = scenes.gui_camera(0.4, 3.3)
     ref = VolumeRenderer((96, 80))
+    ref.set_view_copies("primary")  # as the player's renderers: time points are rendered through the z copy
     ref.set_projection(P)
     ref.set_modelView(M)
     want = {}

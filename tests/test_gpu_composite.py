@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 def _mono(data, size, M, P, peak, gamma=1.):
     from spimagine_b200 import VolumeRenderer
     r = VolumeRenderer(size)
+    r.set_view_copies("primary")  # the slabs hold pairs along z: "bit for bit" is against the single-GPU render through the same (z) copy
     r.set_data(data)
     r.set_modelView(M)
     r.set_projection(P)
@@ -139,6 +140,7 @@ def test_sort_last_iso_surface_is_bit_exact(world, dtype, maxval):
     size = (136, 104)
     rs = _iso_ranks(data, size, world, iso_halo(64))
     mono = VolumeRenderer(size)
+    mono.set_view_copies("primary")  # (the max projections composited in between: same z copy as the slabs)
     mono.set_data(data)
     for theta, skip, gamma in [(0.4, None, 1.), (1.9, False, 1.), (3.0, None, .8)]:
         M, P = scenes.gui_camera(theta, 3.2)
@@ -193,6 +195,7 @@ def test_peer_iso_composite_is_bit_exact_on_every_rank(world, dtype, maxval, sha
     for s in rs:  # knob 12: the screen-space passes on the rank's own band of rows + band gather, or on the whole image
         s._check(s._lib.spv_set_tuning(s._ctx, 12, sharded))
     mono = VolumeRenderer(size)
+    mono.set_view_copies("primary")  # (the max projections composited in between: same z copy as the slabs)
     mono.set_data(data)
     for theta, skip, gamma in [(0.4, None, 1.), (1.9, False, 1.), (3.0, None, .8), (4.4, None, 1.)]:
         M, P = scenes.gui_camera(theta, 3.2)

@@ -506,6 +506,7 @@ def test_slab_decomposition_is_bit_exact(world, dtype, peak, layout):
     M, P = scenes.gui_camera(0.9, 2.7)
     mono = _renderer((136, 104))
     mono.set_layout(layout)
+    mono.set_view_copies("primary")  # the slabs hold pairs along z: "bit for bit" is against the single-GPU render through the same (z) copy
     mono.set_data(data)
     mono.set_modelView(M)
     mono.set_projection(P)

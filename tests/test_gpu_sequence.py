@@ -109,7 +109,15 @@ def test_full_size_properties(full_c2):
     vol, rend, M, P = full_c2
     assert rend.data_min_max == (float(vol.min()), float(vol.max()))
     rend.render()
+    auto = rend.output.copy()
+    assert rend.mip_axis_used() == (1, 1)
+    # multi-pass renders and empty-space skipping run mip_fast_kernel on the z copy: bit-level identities are stated
+    # against the plain render through that copy; the default render (pairs along y for this camera) is the same image
+    # up to the texture unit's weight rounding
+    rend.set_view_copies("primary")
+    rend.render()
     img, alpha = rend.output.copy(), rend.output_alpha.copy()
+    assert np.abs(img - auto).max() < 2e-4
     hit = alpha > 0  # uint16 path: alpha = tnear on hit, 0 on miss (camera outside the box)
     assert 0.25 < hit.mean() < 0.45
     assert np.all(img[~hit] == 0) and img.min() >= 0 and img.max() <= 1
@@ -130,6 +138,7 @@ def test_full_size_properties(full_c2):
     rend.render()
     assert np.array_equal(rend.output, img)
     rend.set_skipping(None)
+    rend.set_view_copies("auto")
 
 
 def test_full_size_slabs_are_bit_exact(full_c2):
@@ -139,7 +148,9 @@ def test_full_size_slabs_are_bit_exact(full_c2):
     from spimagine_b200 import _lib
     from spimagine_b200.multigpu import SlabMaxProjector, partition_slabs, slab_with_halo
     vol, rend, M, P = full_c2
+    rend.set_view_copies("primary")  # the slabs hold pairs along z: bit for bit against the render through the z copy
     rend.render()
+    rend.set_view_copies("auto")
     want = rend.output.copy()
     acc = None
     for rank, (z0, z1) in enumerate(partition_slabs(512, 4)):
@@ -292,6 +303,7 @@ def test_timelapse_player_resident_and_streamed():
     P = cams[0][1]
     want = []
     ref = _renderer((96, 80))
+    ref.set_view_copies("primary")  # as the player's renderers: time points are rendered through the z copy
     for t in range(T):
         ref.set_data(source[t])
         ref.set_projection(P)
