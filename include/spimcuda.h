@@ -315,7 +315,13 @@ SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
  * sort-last iso frames (spv_last_phases_ms; off by default), knob 14 = device-only iso-surface renders (spv_render_iso) put
  * their screen-space passes on a second stream, so that the search of the next frame -- rendered into the other output
  * slot, spv_select_slot -- runs beside them; reads through this library wait for the passes by themselves, a caller that
- * takes spv_device_ptr must call spv_stream_join or spv_sync first (off by default; render_sequence switches it on). */
+ * takes spv_device_ptr must call spv_stream_join or spv_sync first (off by default; render_sequence switches it on),
+ * knob 15 = the same for plain max projections into output slot 1 (a frame starts in the tail of the one before),
+ * knob 16 = layered copies plain max projections of integer volumes sample (never changes a result by more than the
+ * texture unit's weight rounding; the hit mask and alpha plane never change): 1 (default) = per frame the copy with pairs
+ * along x, y or z and the lane-to-pixel map under which a texture request stays inside one layer, chosen from the camera
+ * alone (the x / y copies are built on the device when first wanted, 4 bytes per voxel each), 2 = the primary z copy only,
+ * 0 = mip_fast_kernel on the z copy (round 1's path), 10 + 3 * axis + map = forced (tests). */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 /* Which kernel family renders plain (alpha_pow == 0, num_parts == 1) max projections of uint16 volumes
  * (max_project_short, volume_kernel.cl:270-345):

@@ -6,7 +6,9 @@
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
         -k regex:mip_ --csv --log-file gpurun_out/traffic.csv python bench.py --steps 12 --warmup 3 --no-c4 --no-cpu-baseline
   here:
-    python scripts/ncu_traffic.py gpurun_out/traffic.csv sweep_512_1024
+    python scripts/ncu_traffic.py gpurun_out/traffic.csv sweep_512_1024 [family [frames per launch]]
+With frames per launch (multi-frame launches of mip_axis_kernel: the grid's y extent) only those launches are averaged and
+the key gets the suffix _b<frames>.
 """
 import csv
 import json
@@ -24,12 +26,15 @@ UNIT = {"byte": 1., "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 
 def main():
     path, key = sys.argv[1], sys.argv[2]
     family = sys.argv[3] if len(sys.argv) > 3 else "mip"
+    frames = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     rows = []
     with open(path) as f:
         lines = [ln for ln in f if ln.startswith('"')]
     rd = csv.DictReader(lines)
     per = {}
     for r in rd:
+        if frames and (("mip_axis" not in r["Kernel Name"]) or int(r["Grid Size"].strip("()").split(",")[1]) != frames):
+            continue
         k = (r["ID"], r["Kernel Name"])
         per.setdefault(k, {})[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * UNIT.get(r["Metric Unit"], 1.)
     by_kernel = {}
@@ -42,6 +47,9 @@ def main():
            "dram_bytes_write": sum(m["dram__bytes_write.sum"] for m in ms) / len(ms),
            "time_us_under_ncu": sum(m["gpu__time_duration.sum"] for m in ms) / len(ms),
            "source_sha1": bench.source_sha1(family), "from": os.path.basename(path)}
+    if frames:
+        rec["frames_per_launch"] = frames
+        key += "_b%d" % frames
     out = os.path.join(ROOT, "profiles", "r02_mip_traffic.json")
     allrec = {}
     if os.path.exists(out):
