@@ -1556,7 +1556,8 @@ def run_sweep(args, rank, local_rank, world):
         if f32:
             kernel_name = "spv::mip_fast_kernel<f32, linear>"
         if args.alpha_pow:
-            kernel_name = "spv::mip_alpha_kernel<%s, linear>" % args.dtype
+            kernel_name = ("spv::mip_axis_kernel<u16, attenuated> (layer axis %s)" % "xyz"[axis_used[0]]) if axis_path else \
+                "spv::mip_alpha_kernel<%s, linear>" % args.dtype
         line = {
             "metric": metric, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",

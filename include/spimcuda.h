@@ -148,7 +148,7 @@ SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p);
 SPV_API int spv_render_mip_to_host(spv_ctx *ctx, const spv_mip_params *p, int bands, int wait, float **host);
 /* ---- several frames per launch (new; the record loop of a keyframe / rotation sequence:
  *      spimagine/gui/mainwidget.py renders frame after frame through _render_max_project, volumerender.py:327-390).
- *      n <= SPV_MAX_BATCH plain projections (alpha_pow 0, one part) of the resident integer volume that share the
+ *      n <= SPV_MAX_BATCH projections (plain or attenuated, one part) of the resident integer volume that share the
  *      projection, box, window and step count and differ in their model view: invM = n row-major float[16], the invP
  *      of spv_set_matrices.  ONE launch; its CTAs are dealt (tile row, frame, tile column), so the frames' CTAs of a
  *      tile row run together and share the volume in L2; every frame picks the layered copy of the volume (pairs along

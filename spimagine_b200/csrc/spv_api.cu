@@ -1299,8 +1299,8 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
   }
   // view-aligned layered copy + lane map of this frame (spv_mip_axis.cu): a function of the camera alone, so a view
   // renders to the same bits whatever was rendered before it
-  const bool axis = plain && linear && !raw_only && !push && !smem && p->num_parts == 1 && p->current_part == 0 &&
-                    axis_path_possible(ctx);
+  const bool axis = fast && linear && !raw_only && !push && !smem && p->num_parts == 1 && p->current_part == 0 &&
+                    axis_path_possible(ctx);  // plain and attenuated projections alike
   int lax = 2, quad = 0;
   if (axis) {
     choose_axis(ctx, ctx->cam.invP, ctx->cam.invM, p->box, p->max_steps, ctx->axis_mode != 2, lax, quad);
@@ -1323,6 +1323,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     ax.scale = a.vol.scale;
     memcpy(ax.box, p->box, sizeof ax.box);
     ax.min_val = p->min_val; ax.max_val = p->max_val; ax.gamma = p->gamma; ax.max_steps = p->max_steps;
+    ax.alpha_pow = p->alpha_pow;
     ax.width = ctx->width; ax.height = ctx->height; ax.n_frames = 1;
   }
   // the kernel of this frame (or band of it): a carries what varies between the launches below
@@ -1537,7 +1538,7 @@ static int ensure_batch(spv_ctx *ctx, int n) {
   return 0;
 }
 
-// n (<= SPV_MAX_BATCH) plain max projections of the resident integer volume that differ in their model view only, in ONE
+// n (<= SPV_MAX_BATCH) max projections (plain or attenuated) of the resident integer volume that differ in their model view only, in ONE
 // launch (mip_axis_kernel): the frames' CTAs of one tile row run together, so the frames share the volume in L2.  Results
 // go to one of two sets of planes, [n][out | alpha] floats, alternating from call to call; with to_host the rows the
 // projected box can touch travel to the set's pinned planes behind the launch (the other rows hold the miss values), and
@@ -1547,9 +1548,9 @@ SPV_API int spv_render_mip_batch(spv_ctx *ctx, const spv_mip_params *p, const fl
   if (!p || !invM || !set_out) return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: null argument");
   if (n < 1 || n > MAX_BATCH) return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: 1 <= n <= SPV_MAX_BATCH frames per launch");
   if (!ctx->arr) return fail(ctx, SPV_ENODATA, "spv_render_mip_batch: no volume set");
-  if (p->num_parts != 1 || p->current_part != 0 || p->max_steps < 16 || p->alpha_pow != 0.f || p->flags != 0)
-    return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: plain projections only (alpha_pow 0, one part, no flags, max_steps >= 16)");
-  if (bad_float(p->gamma)) return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: NaN parameter");
+  if (p->num_parts != 1 || p->current_part != 0 || p->max_steps < 16 || p->flags != 0)
+    return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: one part, no flags, max_steps >= 16");
+  if (bad_float(p->gamma) || bad_float(p->alpha_pow)) return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: NaN parameter");
   if (!axis_path_possible(ctx))
     return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: needs a resident integer volume in the paired layout, the TMU sampler "
                                  "with linear filtering, and no skipping / statistics / slab / software-sampled path");
@@ -1580,6 +1581,7 @@ SPV_API int spv_render_mip_batch(spv_ctx *ctx, const spv_mip_params *p, const fl
   ax.scale = ctx->dtype == SPV_U16 ? 65535.f : 255.f;
   memcpy(ax.box, p->box, sizeof ax.box);
   ax.min_val = p->min_val; ax.max_val = p->max_val; ax.gamma = p->gamma; ax.max_steps = p->max_steps;
+  ax.alpha_pow = p->alpha_pow;
   ax.width = ctx->width; ax.height = ctx->height; ax.n_frames = n;
   ax.y_begin = 0; ax.y_end = ctx->height;
   rc = join_post(ctx, -1);  // single frames beside the render stream may still read a copy that is about to be rebuilt
@@ -1732,7 +1734,7 @@ SPV_API int spv_render_mip_batch(spv_ctx *ctx, const spv_mip_params *p, const fl
 
 SPV_API int spv_mip_batch_possible(spv_ctx *ctx, const spv_mip_params *p) {
   if (!ctx || !p || !ctx->arr) return 0;
-  if (p->num_parts != 1 || p->current_part != 0 || p->max_steps < 16 || p->alpha_pow != 0.f || p->flags != 0) return 0;
+  if (p->num_parts != 1 || p->current_part != 0 || p->max_steps < 16 || p->flags != 0) return 0;
   return axis_path_possible(ctx) ? 1 : 0;
 }
 

@@ -106,6 +106,7 @@ struct MipAxisArgs {
   float scale;                 // 65535 or 255
   float box[6];
   float min_val, max_val, gamma;
+  float alpha_pow;             // != 0: front-to-back attenuation (the ALPHA instantiation)
   int max_steps;
   int width, height;
   int n_frames;

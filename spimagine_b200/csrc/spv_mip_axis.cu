@@ -52,7 +52,9 @@ cudaError_t launch_axis_pair(const Volume &V, int dtype, int lax, cudaSurfaceObj
 }
 
 // ---- the render kernel --------------------------------------------------------------------------------------------
-// one CTA tile (bx, by) of frame f
+// one CTA tile (bx, by) of frame f.  ALPHA: front-to-back attenuation (alpha_pow != 0, volume_kernel.cl:300-318) with the
+// block structure of mip_alpha_kernel (spv_mip.cu): a block's 16 fetches in flight, the serial recurrence over the batch.
+template <bool ALPHA>
 __device__ __forceinline__ void mip_axis_tile(const MipAxisArgs &a, int f, unsigned bx, unsigned by, float (*s_out)[32],
                                               float (*s_alpha)[32]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -113,28 +115,72 @@ __device__ __forceinline__ void mip_axis_tile(const MipAxisArgs &a, int f, unsig
     const float c0 = lax == 0 ? u0 : (lax == 1 ? v0 : w0), dc = lax == 0 ? du : (lax == 1 ? dv : dw);
     const float top = (float)((lax == 0 ? a.nx : (lax == 1 ? a.ny : a.nz)) - 1);
     const cudaTextureObject_t tex = a.tex[lax];
-    for (int k = 0; k < S; k += 16) {
-      float2 t[16];
-      float fr[16];
+    // layer l = {v[l], v[l+1]} (the last layer repeats itself): bilinear in the texture unit, lerp along c here
+    auto fetch = [&](float kk, float2 &t, float &fr) {
+      const float cb = fmaf(kk, dc, c0) - 0.5f;
+      const float fl = floorf(cb);
+      fr = fl < 0.f ? 0.f : cb - fl;  // below the first slice centre: clamp-to-edge
+      const int layer = (int)fminf(fmaxf(fl, 0.f), top);
+      t = tex2DLayered<float2>(tex, fmaf(kk, da, a0), fmaf(kk, db, b0), layer);
+    };
+    if (!ALPHA) {
+      for (int k = 0; k < S; k += 16) {
+        float2 t[16];
+        float fr[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float kk = (float)(k + j);
-        // layer l = {v[l], v[l+1]} (the last layer repeats itself): bilinear in the texture unit, lerp along c here
-        const float cb = fmaf(kk, dc, c0) - 0.5f;
-        const float fl = floorf(cb);
-        fr[j] = fl < 0.f ? 0.f : cb - fl;  // below the first slice centre: clamp-to-edge
-        const int layer = (int)fminf(fmaxf(fl, 0.f), top);
-        t[j] = tex2DLayered<float2>(tex, fmaf(kk, da, a0), fmaf(kk, db, b0), layer);
+        for (int j = 0; j < 16; ++j) fetch((float)(k + j), t[j], fr[j]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) cur = fmaxf(cur, fmaf(fr[j], t[j].y - t[j].x, t[j].x));
       }
+      cur *= a.scale;  // rounding is monotone: max(s * t_k) == s * max(t_k), the value mip_fast_kernel computes
+    } else {
+      // v = (s - min) / (max - min);  col = max(col, cum * v);  cum *= 1 - 0.1 a^2 v   (integer volumes)
+      // `if (cum <= .01) break` leaves the inner loop only: a ray that has gone dark still takes one sample at the start
+      // of every remaining block, and the n-th executed sample sits at pos0 + n * delta.
+      const float minVal = a.min_val, maxVal = a.max_val, att = .1f * a.alpha_pow * a.alpha_pow;
+      const int nblocks = a.max_steps / 16 + 1;
+      float cum = 1.f, col = 0.f;
+      int n = 0;  // samples executed so far
+      for (int b = 0; b < nblocks; ++b) {
+        float2 t[16];
+        float fr[16];
+        int j0 = 0;
+        bool done = false;
+        if (cum <= 0.01f) {  // dark on entry: one sample decides whether the block goes on
+          fetch((float)n, t[0], fr[0]);
+          float v = fmaf(fr[0], t[0].y - t[0].x, t[0].x) * a.scale;
+          v = (maxVal == 0.f) ? v : (v - minVal) / (maxVal - minVal);
+          col = fmaxf(col, cum * v);
+          cum *= 1.f - att * v;
+          ++n;
+          j0 = 1;
+          done = cum <= 0.01f;
+        }
+        if (!done) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) cur = fmaxf(cur, fmaf(fr[j], t[j].y - t[j].x, t[j].x));
+          for (int j = 0; j < 16; ++j)
+            if (j >= j0) fetch((float)(n + j - j0), t[j], fr[j]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (j >= j0 && !done) {
+              float v = fmaf(fr[j], t[j].y - t[j].x, t[j].x) * a.scale;
+              v = (maxVal == 0.f) ? v : (v - minVal) / (maxVal - minVal);
+              col = fmaxf(col, cum * v);
+              cum *= 1.f - att * v;
+              ++n;
+              done = cum <= 0.01f;
+            }
+          }
+        }
+      }
+      if (a.gamma != 1.f) col = powf(col, a.gamma);
+      cur = clampf_cl(col, 0.f, 1.f);
     }
-    cur *= a.scale;  // rounding is monotone: max(s * t_k) == s * max(t_k), the value mip_fast_kernel computes
   }
 
   // ---- epilogue: window, gamma; the tile goes through shared memory and leaves as 128-bit stores ----
   const float alphaVal = hit ? tnear : 0.f;
-  const float outVal = hit ? window_value(cur, a.min_val, a.max_val, a.gamma) : 0.f;
+  const float outVal = hit ? (ALPHA ? cur : window_value(cur, a.min_val, a.max_val, a.gamma)) : 0.f;
   float *out_rows = a.out[f] + (size_t)ty0 * Nx, *alpha_rows = a.alpha[f] + (size_t)ty0 * Nx;
   const bool vec_ok = (Nx % 4 == 0) && (tx0 + tw <= Nx) && (ty0 + th <= Ny);
   if (vec_ok) {
@@ -154,7 +200,7 @@ __device__ __forceinline__ void mip_axis_tile(const MipAxisArgs &a, int f, unsig
   }
 }
 
-template <int DT>
+template <int DT, bool ALPHA>
 __global__ void __launch_bounds__(128) mip_axis_kernel(const __grid_constant__ MipAxisArgs a) {
   __shared__ __align__(16) float s_out[4][32];
   __shared__ __align__(16) float s_alpha[4][32];
@@ -170,7 +216,7 @@ __global__ void __launch_bounds__(128) mip_axis_kernel(const __grid_constant__ M
       by = (blockIdx.z & 1u) ? gridDim.z - 1u - (blockIdx.z >> 1) : (blockIdx.z >> 1);
     }
   }
-  mip_axis_tile(a, f, bx, by, s_out, s_alpha);
+  mip_axis_tile<ALPHA>(a, f, bx, by, s_out, s_alpha);
   if (a.band_done) {  // this CTA's rows are stored: tell the copy streams (bands count from the first launched tile row)
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -188,17 +234,20 @@ cudaError_t launch_mip_axis(const MipAxisArgs &a, int dtype, cudaStream_t st) {
   }
   if (gx == 0 || gz == 0) return cudaSuccess;  // no frame's box is on screen
   const dim3 grid(gx, a.n_frames, gz);
-  if (dtype == 1) mip_axis_kernel<1><<<grid, 128, 0, st>>>(a);
-  else if (dtype == 2) mip_axis_kernel<2><<<grid, 128, 0, st>>>(a);
+  const bool att = a.alpha_pow != 0.f;
+  if (dtype == 1) { if (att) mip_axis_kernel<1, true><<<grid, 128, 0, st>>>(a); else mip_axis_kernel<1, false><<<grid, 128, 0, st>>>(a); }
+  else if (dtype == 2) { if (att) mip_axis_kernel<2, true><<<grid, 128, 0, st>>>(a); else mip_axis_kernel<2, false><<<grid, 128, 0, st>>>(a); }
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 
 cudaError_t preload_mip_axis() {
   cudaFuncAttributes fa;
-  cudaError_t e = cudaFuncGetAttributes(&fa, mip_axis_kernel<1>);
-  if (e != cudaSuccess) return e;
-  return cudaFuncGetAttributes(&fa, mip_axis_kernel<2>);
+  cudaError_t e = cudaFuncGetAttributes(&fa, mip_axis_kernel<1, false>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, mip_axis_kernel<1, true>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, mip_axis_kernel<2, false>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, mip_axis_kernel<2, true>);
+  return e;
 }
 
 }  // namespace spv

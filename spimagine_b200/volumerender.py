@@ -541,7 +541,7 @@ class VolumeRenderer(object):
         issues frame i+2 into the slot of frame i (copy a frame that must outlive that); otherwise copies.
         iso_planes=2 reads back only what a display needs of an iso-surface frame (output, output_alpha: 8 of the
         28 bytes per pixel); output_depth / output_normals / output_occlusion are None for such frames.
-        Plain max projections (alphaPow 0) of integer volumes are rendered `batch` frames per launch (at most 16;
+        Max projections of integer volumes are rendered `batch` frames per launch (at most 16;
         batch=1: one launch per frame as above): the frames of a launch share the volume in L2 (spv_render_mip_batch),
         and a launch's frames are copied to pinned memory band by band while it renders.  All frames of a launch use the
         renderer's settings (projection, window, box, data) as they are when the launch is issued, so this is the
@@ -616,7 +616,7 @@ class VolumeRenderer(object):
 
     def render_batch(self, modelViews, to_host=True):
         """Enqueue ONE launch that renders a max projection for each of up to 16 modelViews (current projection, box,
-        window, gamma, max_steps; alphaPow must be 0) and return the id of the set of planes it went to; collect with
+        window, gamma, alphaPow, max_steps) and return the id of the set of planes it went to; collect with
         batch_frames_of(set).  Raises where spv_render_mip_batch does not apply (float volumes, exact sampler, ...)."""
         Ms = [np.asarray(M, dtype=np.float64) for M in modelViews]
         scale = self._stack_scale_mat()

@@ -104,6 +104,41 @@ def test_window_gamma_box_and_ragged_image_sizes(oracle_mod):
             rend.close()
 
 
+@pytest.mark.parametrize("dtype", [np.uint16, np.uint8])
+def test_attenuated_projection_through_every_copy(oracle_mod, dtype):
+    """alpha_pow != 0 (volume_kernel.cl:300-318) through the layered copies: sub-critical attenuation against the oracle,
+    the z copy against mip_alpha_kernel bit for bit"""
+    vol = scenes.vol_g(96, dtype, seed=8)
+    peak = float(vol.max())
+    size = (176, 144)
+    M, P = scenes.gui_camera(0.7, 3.3)
+    rend = _renderer(size)
+    rend.set_data(vol)
+    rend.set_projection(P)
+    rend.set_modelView(M)
+    try:
+        for alpha_pow, gamma in [(0.3, 1.), (1.0, 0.7)]:
+            ref, ref_a = _oracle_image(oracle_mod, vol, size, M, P, max_val=peak, alpha_pow=alpha_pow, gamma=gamma)
+            rend.set_alpha_pow(alpha_pow)
+            rend.set_gamma(gamma)
+            _knob(rend, 16, 0)
+            rend.render(maxVal=peak)
+            fast = rend.output.copy()
+            assert rend.mip_axis_used() == (-1, -1) and np.abs(fast - ref).max() < 1e-3
+            for axis in range(3):
+                for quad in range(3):
+                    _knob(rend, 16, 10 + 3 * axis + quad)
+                    rend.render()
+                    assert rend.mip_axis_used() == (axis, quad)
+                    assert np.abs(rend.output - ref).max() < 1e-3, (alpha_pow, axis, quad)
+                    assert np.array_equal(rend.output_alpha, ref_a)
+                    if axis == 2:
+                        assert np.array_equal(rend.output, fast), (alpha_pow, quad)
+            assert ref.max() > 0.05
+    finally:
+        rend.close()
+
+
 def test_choice_follows_the_camera():
     """the GUI camera spins about y: pairs along y, row quads, at every angle, from the first frame after an upload on
     (the choice is a function of the camera: a view renders to the same bits whatever came before); seen along y (from
@@ -256,16 +291,28 @@ def test_render_sequence_in_launches_of_several_frames():
                 if per_launch > 1:  # (one launch per frame: the next frame has been issued -- its modelView set -- already)
                     assert np.allclose(M, cams[i][0])
             assert np.allclose(rend.modelView, cams[-1][0])
+        # attenuated projections take the same launches
         rend.set_alpha_pow(0.5)
-        att = [r.output.copy() for r in rend.render_sequence(M for M, _ in cams[:5])]
-        rend.render(modelView=cams[4][0])
-        assert np.array_equal(att[4], rend.output)
-        assert rend.mip_axis_used() == (-1, -1)
-        with pytest.raises(Exception):
-            rend.render_batch([M for M, _ in cams[:3]])
+        want_att = []
+        for M, _ in cams[:12]:
+            rend.render(modelView=M)
+            want_att.append(rend.output.copy())
+        assert rend.mip_axis_used() == (1, 1)
+        assert not np.array_equal(want_att[3], want[3][0])
+        for views in ([M for M, _ in cams[:12]], (M for M, _ in cams[:12])):
+            att = [r.output.copy() for r in rend.render_sequence(views)]
+            assert len(att) == 12 and all(np.array_equal(x, y) for x, y in zip(att, want_att))
         rend.set_alpha_pow(0.)
         with pytest.raises(Exception):
             rend.render_batch([M for M, _ in cams[:17]])
+        # settings the launches of several frames do not cover fall back to one launch per frame
+        rend.set_skipping(True)
+        sk = [r.output.copy() for r in rend.render_sequence([M for M, _ in cams[:5]])]
+        assert rend.mip_axis_used() == (-1, -1)
+        assert all(np.abs(x - w[0]).max() < 4e-3 for x, w in zip(sk, want))
+        with pytest.raises(Exception):
+            rend.render_batch([M for M, _ in cams[:3]])
+        rend.set_skipping(None)
     finally:
         rend.close()
 
