@@ -351,16 +351,30 @@ def render_keyframes(renderer, keyList, nFrames, source=None, isPerspective=True
                 renderer.render(method=method)
                 yield times[k][0], tds[k], renderer
         elif method == "max_project":
-            # stretches in which only the camera moves (same time point, window, box, projection) go to render_sequence
-            # as a list of modelViews: several frames per launch (VolumeRenderer.render_sequence, spv_render_mip_batch)
+            # stretches of at least 4 frames in which only the camera moves (same time point, window, box, projection) go
+            # to render_sequence as a LIST of modelViews: several frames per launch (spv_render_mip_batch).  Frames
+            # between such stretches keep the two-frames-in-flight pipeline fed by a generator that applies each frame's
+            # settings as it is pulled.
+            keys_ = [_static_key(tds[k], source, isPerspective) for k in range(i, j)]
+            run_end = {}
+            k = i
+            while k < j:
+                e = k + 1
+                while e < j and keys_[e - i] == keys_[k - i]:
+                    e += 1
+                run_end[k] = e
+                k = e
             k0 = i
             while k0 < j:
-                key0 = _static_key(tds[k0], source, isPerspective)
-                k1 = k0 + 1
-                while k1 < j and _static_key(tds[k1], source, isPerspective) == key0:
-                    k1 += 1
-                prepare(tds[k0])
-                views = [camera_of(tds[k], isPerspective)[0] for k in range(k0, k1)]
+                if run_end[k0] - k0 >= 4:
+                    k1 = run_end[k0]
+                    prepare(tds[k0])
+                    views = [camera_of(tds[k], isPerspective)[0] for k in range(k0, k1)]
+                else:
+                    k1 = k0
+                    while k1 < j and run_end[k1] - k1 < 4:
+                        k1 = run_end[k1]
+                    views = (prepare(tds[k])[0] for k in range(k0, k1))
                 for k, r in zip(range(k0, k1), renderer.render_sequence(views, method=method)):
                     yield times[k][0], tds[k], r
                 k0 = k1

@@ -323,6 +323,46 @@ def test_record_loop_sharded_over_ranks_covers_every_frame_once():
         next(kf.render_keyframes(_FakeRenderer(), keys, 5, rank=2, world=2))
 
 
+def test_pipelined_loop_hands_static_stretches_over_as_lists():
+    """render_keyframes(pipelined=True): stretches of >= 4 frames in which only the camera moves reach render_sequence as
+    a list of modelViews (several frames per launch), everything else as a generator that applies each frame's settings
+    when it is pulled; every frame is rendered once, in order, with its own settings in force"""
+    class Seq(_FakeRenderer):
+        def __init__(self):
+            _FakeRenderer.__init__(self)
+            self.handed = []
+
+        def render_sequence(self, views, method="max_project", iso_planes=7):
+            rec = [isinstance(views, list), 0, method]
+            self.handed.append(rec)
+            for M in views:          # pulling a generator applies that frame's settings
+                self.calls.append(("frame", method))
+                rec[1] += 1
+                yield self
+
+    q0, q1 = kf.Quaternion(1, 0, 0, 0), kf.Quaternion(0.7, 0, 0.7, 0)
+    keys = kf.KeyFrameList()
+    keys.addItem(kf.KeyFrame(0., kf.TransformData(quatRot=q0, maxVal=200., gamma=1.)))
+    keys.addItem(kf.KeyFrame(.5, kf.TransformData(quatRot=q1, maxVal=200., gamma=1.)))   # only the camera moves
+    keys.addItem(kf.KeyFrame(1., kf.TransformData(quatRot=q0, maxVal=100., gamma=.5)))   # the window moves as well
+    r = Seq()
+    frames = [(pos, td.maxVal) for pos, td, _ in kf.render_keyframes(r, keys, 40)]
+    assert [f[0] for f in frames] == list(range(1, 41))
+    assert sum(n for _, n, _ in r.handed) == 40 and all(m == "max_project" for _, _, m in r.handed)
+    lists = [n for is_list, n, _ in r.handed if is_list]
+    assert lists and max(lists) >= 15          # the first half of the path is one static stretch
+    gens = [n for is_list, n, _ in r.handed if not is_list]
+    assert gens and sum(gens) >= 15            # the second half changes its window every frame
+    # settings in force when a frame is rendered: the last set_max_val before the k-th "frame" is frame k's maxVal
+    seen, cur = [], None
+    for name, v in r.calls:
+        if name == "set_max_val":
+            cur = v
+        elif name == "frame":
+            seen.append(cur)
+    assert np.allclose(seen, [f[1] for f in frames])
+
+
 def _kf_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
