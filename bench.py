@@ -1554,7 +1554,9 @@ def run_sweep(args, rank, local_rank, world):
                 "xyz"[axis_used[0]], ("2x2-pixel quads", "4x1 row quads", "1x4 column quads")[axis_used[1]])
         metric = sweep_metric(args)
         if f32:
-            kernel_name = "spv::mip_fast_kernel<f32, linear>"
+            kernel_name = ("spv::mip_axis_kernel<f32> (layer axis %s, %s)" % (
+                "xyz"[axis_used[0]], ("2x2-pixel quads", "4x1 row quads", "1x4 column quads")[axis_used[1]])) if axis_path else \
+                "spv::mip_fast_kernel<f32, linear>"
         if args.alpha_pow:
             kernel_name = ("spv::mip_axis_kernel<u16, attenuated> (layer axis %s)" % "xyz"[axis_used[0]]) if axis_path else \
                 "spv::mip_alpha_kernel<%s, linear>" % args.dtype

@@ -51,8 +51,8 @@ __device__ __forceinline__ bool setup(int x, int y, int W, int H, const Cam &c, 
 // The array itself is the same noise cube for every variant -- only the coordinates are permuted, which is what a
 // permuted copy of the volume would look like to the texture unit.
 struct Shape { int qw, qh, wx, wy, cx, cy; };  // cx x cy warps per CTA
-template <int LAX, int TR, int UN, int NT>
-__global__ void __launch_bounds__(NT) march(cudaTextureObject_t tex, const __grid_constant__ Cams cams, int W, int H, int N,
+template <int LAX, int TR, int UN, int NT, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB) march(cudaTextureObject_t tex, const __grid_constant__ Cams cams, int W, int H, int N,
                                              int S, int row0, Shape sh, float *out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = lane >> 2, i = lane & 3, nqx = sh.wx / sh.qw;
@@ -82,6 +82,13 @@ __global__ void __launch_bounds__(NT) march(cudaTextureObject_t tex, const __gri
 #pragma unroll
       for (int j = 0; j < UN; ++j) cur = fmaxf(cur, fmaf(fr[j], v[j].y - v[j].x, v[j].x));
     }
+  }
+  if (MINB == 11) {  // the library kernel's 1 KB of static shared memory (tile staging): does the L1 carve-out matter?
+    __shared__ float stage[4][64];
+    stage[warp][lane] = cur;
+    stage[warp][32 + lane] = cur + 1.f;
+    __syncwarp();
+    cur = stage[warp][lane ^ 1] + stage[warp][32 + (lane ^ 1)] * 0.f;
   }
   out[((size_t)f * H + y) * W + x] = cur * 65535.f;
 }
@@ -226,6 +233,40 @@ int main(int argc, char **argv) {
     }
     return ms * 1000.f / reps;
   };
+  if (argc > 2 && !strcmp(argv[2], "occ")) {  // resident CTAs per SM (register budget) of the y-layered row-quad kernel
+    const Shape sh = {4, 1, 16, 2, 1, 4};
+    for (int minb : {10, 11, 10, 11, 12}) {
+      double samples = 0, total = 0;
+      for (int g = 0; g < 2; ++g) {
+        Cams cs;
+        for (int f = 0; f < 10; ++f) { cs.c[f] = cam_at(18.f * (g * 10 + f)); samples += hits(cs.c[f]) * S; }
+        const dim3 grid(W / 16, 10, H / 8);
+        float ms = 0;
+        for (int it = 0; it < 2; ++it) {
+          CK(cudaEventRecord(e0));
+          for (int r = 0; r < 3; ++r) {
+            switch (minb) {
+              case 2: march<1, 0, 16, 128, 2><<<grid, 128, 40 * 1024>>>(tex, cs, W, H, N, S, 0, sh, out); break;   // + shared memory: 2 / 4 CTAs really
+              case 4: march<1, 0, 16, 128, 4><<<grid, 128, 40 * 1024>>>(tex, cs, W, H, N, S, 0, sh, out); break;
+              case 6: march<1, 0, 16, 128, 6><<<grid, 128, 32 * 1024>>>(tex, cs, W, H, N, S, 0, sh, out); break;
+              case 8: march<1, 0, 16, 128, 8><<<grid, 128, 24 * 1024>>>(tex, cs, W, H, N, S, 0, sh, out); break;
+              case 10: march<1, 0, 16, 128, 10><<<grid, 128>>>(tex, cs, W, H, N, S, 0, sh, out); break;
+              case 11: march<1, 0, 16, 128, 11><<<grid, 128>>>(tex, cs, W, H, N, S, 0, sh, out); break;
+              case 12: march<1, 0, 16, 128, 12><<<grid, 128>>>(tex, cs, W, H, N, S, 0, sh, out); break;
+              default: march<1, 0, 16, 128, 16><<<grid, 128>>>(tex, cs, W, H, N, S, 0, sh, out); break;
+            }
+          }
+          CK(cudaEventRecord(e1));
+          CK(cudaEventSynchronize(e1));
+          CK(cudaGetLastError());
+          CK(cudaEventElapsedTime(&ms, e0, e1));
+        }
+        total += ms * 1000.f / 3;
+      }
+      printf("launch bounds (128, %2d): %.1f us per frame, %.0f Gs/s\n", minb, total / 20, samples / total * 1e-3);
+    }
+    return 0;
+  }
   if (argc > 3) {  // one variant, one launch size, for a profiler: exp_multiframe.bin 512 <variant> <F>
     const int vi = atoi(argv[2]), F = atoi(argv[3]);
     Cams cs;

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <thread>
 
@@ -126,11 +127,13 @@ struct spv_ctx {
   int smem_cfg = 0;  // result bytes enqueued for device -> host copies so far (spv_d2h_bytes)
   // view-aligned layered copies (spv_mip_axis.cu): pairs along x (0) and y (1); the z copy is `arr` itself.  Built on the
   // render stream when a frame first wants them, rebuilt after an upload (axis_seq is the upload they were built from).
-  cudaArray_t axis_arr[2] = {nullptr, nullptr};
-  cudaTextureObject_t axis_tex[2] = {0, 0};
-  cudaSurfaceObject_t axis_surf[2] = {0, 0};
-  unsigned long long axis_seq[2] = {0, 0};
-  bool axis_failed[2] = {false, false};  // the copy could not be allocated: not tried again for this volume
+  // (float32 volumes live in a 3-D array: for them the z copy [2] is a layered pair copy of its own as well)
+  cudaArray_t axis_arr[3] = {nullptr, nullptr, nullptr};
+  cudaTextureObject_t axis_tex[3] = {0, 0, 0};
+  cudaSurfaceObject_t axis_surf[3] = {0, 0, 0};
+  unsigned long long axis_seq[3] = {0, 0, 0};
+  bool axis_failed[3] = {false, false, false};  // the copy could not be allocated: not tried again for this volume
+  float batch_miss_alpha = 0.f;  // what the alpha planes of the batch sets hold outside the tracked rectangles
   int axis_mode = 1;       // tuning knob 16: 0 = off (mip_fast_kernel), 1 = per-frame choice among the three copies (the x / y
                            // copies are built when a frame first wants them), 2 = per-frame choice of the lane map on the
                            // primary z copy only (no second copy: streamed time points), 10 + 3 * axis + quad = forced
@@ -206,7 +209,7 @@ static void free_comp(spv_ctx *c) {
 }
 
 static void free_axis(spv_ctx *c) {
-  for (int d = 0; d < 2; ++d) {
+  for (int d = 0; d < 3; ++d) {
     if (c->axis_tex[d]) cudaDestroyTextureObject(c->axis_tex[d]);
     if (c->axis_surf[d]) cudaDestroySurfaceObject(c->axis_surf[d]);
     if (c->axis_arr[d]) cudaFreeArray(c->axis_arr[d]);
@@ -1121,14 +1124,16 @@ static void miss_free_rect(const Camera &cam, const float *box, int W, int H, in
 // The copy of the resident integer volume with pairs along axis lax (0 x, 1 y), built from the primary z copy on the
 // render stream; post_stream is made to wait for it (frames in output slot 1 may render there).
 static int ensure_axis(spv_ctx *ctx, int lax) {
-  if (lax == 2) return 0;
+  const bool f32 = ctx->dtype == SPV_F32;
+  if (lax == 2 && !f32) return 0;  // integer volumes: the primary array is the z copy
   if (ctx->axis_arr[lax] && ctx->axis_seq[lax] == ctx->upload_seq) return 0;
   if (!ctx->axis_arr[lax]) {
-    const int bits = ctx->dtype == SPV_U16 ? 16 : 8;
-    cudaChannelFormatDesc cd = cudaCreateChannelDesc(bits, bits, 0, 0, cudaChannelFormatKindUnsigned);
-    const cudaExtent ext = lax == 0 ? make_cudaExtent(ctx->gnz, ctx->ny, ctx->nx) : make_cudaExtent(ctx->nx, ctx->gnz, ctx->ny);
+    const int bits = f32 ? 32 : (ctx->dtype == SPV_U16 ? 16 : 8);
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(bits, bits, 0, 0, f32 ? cudaChannelFormatKindFloat : cudaChannelFormatKindUnsigned);
+    const cudaExtent ext = lax == 0 ? make_cudaExtent(ctx->gnz, ctx->ny, ctx->nx)
+                                    : (lax == 1 ? make_cudaExtent(ctx->nx, ctx->gnz, ctx->ny) : make_cudaExtent(ctx->nx, ctx->ny, ctx->gnz));
     cudaError_t e = cudaMalloc3DArray(&ctx->axis_arr[lax], &cd, ext, cudaArrayLayered | cudaArraySurfaceLoadStore);
-    if (e != cudaSuccess) {  // no room for another copy: this volume renders from the primary one
+    if (e != cudaSuccess) {  // no room for another copy: this volume renders from what it has
       cudaGetLastError();
       ctx->axis_arr[lax] = nullptr;
       ctx->axis_failed[lax] = true;
@@ -1142,7 +1147,7 @@ static int ensure_axis(spv_ctx *ctx, int lax) {
     memset(&td, 0, sizeof td);
     td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
     td.normalizedCoords = 0;
-    td.readMode = cudaReadModeNormalizedFloat;
+    td.readMode = f32 ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
     td.filterMode = cudaFilterModeLinear;
     CU(cudaCreateTextureObject(&ctx->axis_tex[lax], &rd, &td, nullptr));
     CU(cudaCreateSurfaceObject(&ctx->axis_surf[lax], &rd));
@@ -1157,8 +1162,12 @@ static int ensure_axis(spv_ctx *ctx, int lax) {
 
 // can plain projections of the resident volume go through mip_axis_kernel at all?
 static bool axis_path_possible(const spv_ctx *c) {
-  return c->axis_mode != 0 && c->arr && c->layout == LAYOUT_ZPAIR && !c->slab && c->sampler == SPV_SAMPLER_TMU && c->linear &&
-         c->int_filter && !(c->skipping > 0) && !c->persistent && !c->stats_on && c->tile_variant == 0 &&
+  // integer volumes in the z-paired layout (the z copy exists already), or float32 volumes (3-D array: every copy is extra)
+  const bool ints = c->dtype != SPV_F32 && c->layout == LAYOUT_ZPAIR && c->int_filter;
+  const bool f32 = c->dtype == SPV_F32 && c->layout == LAYOUT_3D && c->axis_mode != 2 &&
+                   !(c->axis_failed[0] && c->axis_failed[1] && c->axis_failed[2]);
+  return c->axis_mode != 0 && c->arr && (ints || f32) && !c->slab && c->sampler == SPV_SAMPLER_TMU && c->linear &&
+         !(c->skipping > 0) && !c->persistent && !c->stats_on && c->tile_variant == 0 &&
          c->mip_path != SPV_MIP_PATH_SMEM && c->gnz == c->local_nz;
 }
 
@@ -1175,7 +1184,10 @@ static void choose_axis(spv_ctx *ctx, const float *invP, const float *invM, cons
     const int v = ctx->axis_mode - 10;
     lax_out = (v / 3) % 3;
     quad_out = v % 3;
-    if (lax_out != 2 && ctx->axis_failed[lax_out]) lax_out = 2;
+    if (ctx->axis_failed[lax_out]) {  // fall back to a copy that exists or can exist
+      lax_out = 2;
+      if (ctx->dtype == SPV_F32 && ctx->axis_failed[2]) lax_out = ctx->axis_failed[1] ? 0 : 1;
+    }
     return;
   }
   const int W = ctx->width, H = ctx->height;
@@ -1222,13 +1234,15 @@ static void choose_axis(spv_ctx *ctx, const float *invP, const float *invM, cons
   const double dt = hit ? (tf - tn) / (double)((max_steps / 16) * 16) : 2. / max_steps;
   const double n[3] = {(double)ctx->nx, (double)ctx->ny, (double)ctx->gnz};
   double best = 1e300;
+  const bool f32 = ctx->dtype == SPV_F32;
+  if (f32) lax_out = ctx->axis_failed[2] ? (ctx->axis_failed[1] ? 0 : 1) : 2;
   for (int lax = 2; lax >= 0; --lax) {
-    if (lax != 2 && (!other_copies || ctx->axis_failed[lax])) continue;
+    if (ctx->axis_failed[lax] || (lax != 2 && !other_copies && !f32)) continue;
     if ((lax == 0 ? ctx->nx : (lax == 1 ? ctx->ny : ctx->gnz)) > 2048) continue;  // layer count of a layered array
     const double gx = fabs((ox[lax] + tm * dx[lax]) - (o[lax] + tm * d[lax])) * .5 * n[lax];
     const double gy = fabs((oy[lax] + tm * dy[lax]) - (o[lax] + tm * d[lax])) * .5 * n[lax];
     const double gk = fabs(.5 * dt * d[lax]) * n[lax];
-    const double own = lax == 2 ? 0. : .02;  // a copy that may have to be built must earn it
+    const double own = (lax == 2 && !f32) ? 0. : .02;  // a copy that may have to be built must earn it
     const double cost[3] = {.36 * (gx + gy) + .09 * gk + own, .36 * 3. * gx + .09 * gk + own, .36 * 3. * gy + .09 * gk + .10 + own};
     for (int q = 0; q < 3; ++q)
       if (cost[q] < best) { best = cost[q]; lax_out = lax; quad_out = q; }
@@ -1303,21 +1317,23 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
                     axis_path_possible(ctx);  // plain and attenuated projections alike
   int lax = 2, quad = 0;
   if (axis) {
-    choose_axis(ctx, ctx->cam.invP, ctx->cam.invM, p->box, p->max_steps, ctx->axis_mode != 2, lax, quad);
-    if (lax != 2) {
+    for (int tries = 0; tries < 3; ++tries) {  // a copy that cannot be allocated drops out of the choice
+      choose_axis(ctx, ctx->cam.invP, ctx->cam.invM, p->box, p->max_steps, ctx->axis_mode != 2, lax, quad);
       rc = ensure_axis(ctx, lax);
       if (rc && !ctx->axis_failed[lax]) return rc;
-      if (ctx->axis_failed[lax]) choose_axis(ctx, ctx->cam.invP, ctx->cam.invM, p->box, p->max_steps, false, lax, quad);
+      if (!ctx->axis_failed[lax]) break;
     }
   }
-  ctx->last_axis = axis ? lax : -1;
-  ctx->last_quad = axis ? quad : -1;
+  const bool axis_ok = axis && !ctx->axis_failed[lax];  // (float32 volumes: all three copies may have failed)
+  ctx->last_axis = axis_ok ? lax : -1;
+  ctx->last_quad = axis_ok ? quad : -1;
   MipAxisArgs ax;
-  if (axis) {
+  if (axis_ok) {
     memset(&ax, 0, sizeof ax);
     memcpy(ax.invP, ctx->cam.invP, sizeof ax.invP);
     memcpy(ax.invM[0], ctx->cam.invM, sizeof ax.invM[0]);
-    ax.tex[0] = ctx->axis_tex[0]; ax.tex[1] = ctx->axis_tex[1]; ax.tex[2] = ctx->tex_lin;
+    ax.tex[0] = ctx->axis_tex[0]; ax.tex[1] = ctx->axis_tex[1];
+    ax.tex[2] = ctx->dtype == SPV_F32 ? ctx->axis_tex[2] : ctx->tex_lin;
     ax.lax[0] = (unsigned char)lax; ax.quad[0] = (unsigned char)quad;
     ax.nx = ctx->nx; ax.ny = ctx->ny; ax.nz = ctx->gnz;
     ax.scale = a.vol.scale;
@@ -1328,7 +1344,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
   }
   // the kernel of this frame (or band of it): a carries what varies between the launches below
   auto launch_frame = [&](const MipArgs &m, cudaStream_t st) -> cudaError_t {
-    if (!axis) return launch_mip(m, fmt_of(ctx), linear, fast, exact, ctx->skipping > 0, ctx->slab, ctx->stats_on != 0, st);
+    if (!axis_ok) return launch_mip(m, fmt_of(ctx), linear, fast, exact, ctx->skipping > 0, ctx->slab, ctx->stats_on != 0, st);
     ax.out[0] = m.out; ax.alpha[0] = m.alpha;
     ax.y_begin = m.y_begin; ax.y_end = m.y_end;
     ax.band_done = m.band_done; ax.band_rows = m.band_rows; ax.row_mode = m.row_mode;
@@ -1530,12 +1546,31 @@ static int ensure_batch(spv_ctx *ctx, int n) {
   for (int s = 0; s < 2; ++s) {
     CU(cudaMalloc(&ctx->d_batch[s], bytes));
     CU(cudaMallocHost(&ctx->h_batch[s], bytes));
-    memset(ctx->h_batch[s], 0, bytes);  // every pixel holds the miss values (out 0, alpha 0: integer volumes only)
+    memset(ctx->h_batch[s], 0, bytes);  // every pixel holds the miss values of integer volumes (out 0, alpha 0)
     CU(cudaMemsetAsync(ctx->d_batch[s], 0, bytes, ctx->stream));
     for (int f = 0; f < MAX_BATCH; ++f) ctx->batch_h_dirty[s][f] = ctx->batch_d_dirty[s][f] = spv_ctx::Rect{0, 0, 0, 0};
   }
+  ctx->batch_miss_alpha = 0.f;
   ctx->batch_cap = n;
   return 0;
+}
+
+// the alpha planes of the batch sets hold `miss` outside the tracked rectangles: when the element type of the volume
+// changes the miss value (0 for integer volumes, -1 for float32), everything counts as dirty once
+static void batch_miss_value(spv_ctx *ctx, float miss) {
+  if (ctx->batch_miss_alpha == miss) return;
+  const size_t np = ctx->n();
+  for (int s = 0; s < 2; ++s)
+    for (int f = 0; f < ctx->batch_cap && f < MAX_BATCH; ++f) {
+      // pinned planes: refilled here, once (the copies out of them are quiescent: the caller has synchronised);
+      // device planes: everything counts as dirty, the next launch into a slot covers the whole image
+      float *hf = ctx->h_batch[s] + (size_t)f * 2 * np;
+      memset(hf, 0, np * sizeof(float));
+      std::fill_n(hf + np, np, miss);
+      ctx->batch_h_dirty[s][f] = spv_ctx::Rect{0, 0, 0, 0};
+      ctx->batch_d_dirty[s][f] = spv_ctx::Rect{0, ctx->width, 0, ctx->height};
+    }
+  ctx->batch_miss_alpha = miss;
 }
 
 // n (<= SPV_MAX_BATCH) max projections (plain or attenuated) of the resident integer volume that differ in their model view only, in ONE
@@ -1553,22 +1588,24 @@ SPV_API int spv_render_mip_batch(spv_ctx *ctx, const spv_mip_params *p, const fl
   if (bad_float(p->gamma) || bad_float(p->alpha_pow)) return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: NaN parameter");
   if (!axis_path_possible(ctx))
     return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: needs a resident integer volume in the paired layout, the TMU sampler "
-                                 "with linear filtering, and no skipping / statistics / slab / software-sampled path");
+                                 "(or a float32 volume) with linear filtering, and no skipping / statistics / slab / software-sampled path");
   int rc = ensure_batch(ctx, n);
   if (rc) return rc;
+  const float miss_alpha = ctx->dtype == SPV_F32 ? -1.f : 0.f;
   const int set = ctx->batch_set ^ 1;
   MipAxisArgs ax;
   memset(&ax, 0, sizeof ax);
   memcpy(ax.invP, ctx->cam.invP, sizeof ax.invP);
   memcpy(ax.invM, invM, (size_t)n * 16 * sizeof(float));
   for (int f = 0; f < n; ++f) {
-    int lax, quad;
-    choose_axis(ctx, ctx->cam.invP, invM + 16 * f, p->box, p->max_steps, ctx->axis_mode != 2, lax, quad);
-    if (lax != 2) {
+    int lax = 2, quad = 0;
+    for (int tries = 0; tries < 3; ++tries) {  // a copy that cannot be allocated drops out of the choice
+      choose_axis(ctx, ctx->cam.invP, invM + 16 * f, p->box, p->max_steps, ctx->axis_mode != 2, lax, quad);
       rc = ensure_axis(ctx, lax);
       if (rc && !ctx->axis_failed[lax]) return rc;
-      if (ctx->axis_failed[lax]) choose_axis(ctx, ctx->cam.invP, invM + 16 * f, p->box, p->max_steps, false, lax, quad);
+      if (!ctx->axis_failed[lax]) break;
     }
+    if (ctx->axis_failed[lax]) return fail(ctx, SPV_EINVAL, "spv_render_mip_batch: no room for a layered copy of this float32 volume");
     ax.lax[f] = (unsigned char)lax;
     ax.quad[f] = (unsigned char)quad;
     ax.out[f] = ctx->d_batch[set] + (size_t)f * 2 * ctx->n();
@@ -1576,9 +1613,10 @@ SPV_API int spv_render_mip_batch(spv_ctx *ctx, const spv_mip_params *p, const fl
   }
   ctx->last_axis = ax.lax[0];
   ctx->last_quad = ax.quad[0];
-  ax.tex[0] = ctx->axis_tex[0]; ax.tex[1] = ctx->axis_tex[1]; ax.tex[2] = ctx->tex_lin;
+  ax.tex[0] = ctx->axis_tex[0]; ax.tex[1] = ctx->axis_tex[1];
+  ax.tex[2] = ctx->dtype == SPV_F32 ? ctx->axis_tex[2] : ctx->tex_lin;
   ax.nx = ctx->nx; ax.ny = ctx->ny; ax.nz = ctx->gnz;
-  ax.scale = ctx->dtype == SPV_U16 ? 65535.f : 255.f;
+  ax.scale = ctx->dtype == SPV_F32 ? 1.f : (ctx->dtype == SPV_U16 ? 65535.f : 255.f);
   memcpy(ax.box, p->box, sizeof ax.box);
   ax.min_val = p->min_val; ax.max_val = p->max_val; ax.gamma = p->gamma; ax.max_steps = p->max_steps;
   ax.alpha_pow = p->alpha_pow;
@@ -1590,6 +1628,11 @@ SPV_API int spv_render_mip_batch(spv_ctx *ctx, const spv_mip_params *p, const fl
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_batch_copied[set], 0));
     if (to_host) CU(cudaEventSynchronize(ctx->ev_batch_copied[set]));  // the pinned planes are about to be cleaned by the host
     ctx->batch_copy_pending[set] = false;
+  }
+  if (ctx->batch_miss_alpha != miss_alpha) {  // the other set's copies may still be running: they read planes we re-clean
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    CU(cudaStreamSynchronize(ctx->copy_stream2));
+    batch_miss_value(ctx, miss_alpha);
   }
   rc = begin_render(ctx);
   if (rc) return rc;
@@ -1691,7 +1734,9 @@ SPV_API int spv_render_mip_batch(spv_ctx *ctx, const spv_mip_params *p, const fl
         for (int k = 0; k < 2; ++k)
           if (segs[k][0] < segs[k][1]) {
             memset(hf + (size_t)y * W + segs[k][0], 0, (size_t)(segs[k][1] - segs[k][0]) * sizeof(float));
-            memset(hf + np + (size_t)y * W + segs[k][0], 0, (size_t)(segs[k][1] - segs[k][0]) * sizeof(float));
+            float *al = hf + np + (size_t)y * W;
+            if (miss_alpha == 0.f) memset(al + segs[k][0], 0, (size_t)(segs[k][1] - segs[k][0]) * sizeof(float));
+            else std::fill(al + segs[k][0], al + segs[k][1], miss_alpha);
           }
       }
     d = r;
@@ -2463,9 +2508,20 @@ static int texrate_probe_impl(spv_ctx *ctx, int iters, const float *vec9, double
   const int blocks = sms * 8;
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
   Volume V = volume_of(ctx);
-  CU(launch_texrate_probe(V, fmt_of(ctx), linear, blocks, 8, vec9, ctx->tmp(), ctx->stream));  // warm-up
+  int fmt = fmt_of(ctx);
+  // float32 volumes that render through the layered pair copies (spv_mip_axis.cu): the rate of THAT fetch -- bilinear on
+  // two-channel float texels + the lerp -- not of the 3-D array's trilinear fetch
+  if (ctx->dtype == SPV_F32 && linear && axis_path_possible(ctx)) {
+    int rca = ensure_axis(ctx, 2);
+    if (rca && !ctx->axis_failed[2]) return rca;
+    if (!ctx->axis_failed[2]) {
+      V.filt = ctx->axis_tex[2];
+      fmt = SPV_F32 + 3 * LAYOUT_ZPAIR;
+    }
+  }
+  CU(launch_texrate_probe(V, fmt, linear, blocks, 8, vec9, ctx->tmp(), ctx->stream));  // warm-up
   CU(cudaEventRecord(ctx->ev0, ctx->stream));
-  CU(launch_texrate_probe(V, fmt_of(ctx), linear, blocks, iters, vec9, ctx->tmp(), ctx->stream));
+  CU(launch_texrate_probe(V, fmt, linear, blocks, iters, vec9, ctx->tmp(), ctx->stream));
   CU(cudaEventRecord(ctx->ev1, ctx->stream));
   CU(cudaEventSynchronize(ctx->ev1));
   float ms = 0.f;

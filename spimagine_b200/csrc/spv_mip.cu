@@ -610,6 +610,7 @@ cudaError_t launch_texrate_probe(const Volume &V, int dtype, bool linear, int bl
     case 0: SPV_PROBE(0); break;
     case 1: SPV_PROBE(1); break;
     case 2: SPV_PROBE(2); break;
+    case 3: SPV_PROBE(3); break;  // float32 pairs (the layered copies of spv_mip_axis.cu; V.filt is that copy's texture)
     case 4: SPV_PROBE(4); break;
     case 5: SPV_PROBE(5); break;
     default: return cudaErrorInvalidValue;

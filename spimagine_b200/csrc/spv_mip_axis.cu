@@ -31,21 +31,28 @@ __global__ void __launch_bounds__(256) axis_pair_kernel(const Volume V, int lax,
   const int dx = blockIdx.x * 32 + (threadIdx.x & 31);      // destination column
   const int dy = blockIdx.y;                                // destination row
   const int dl = blockIdx.z * 8 + (threadIdx.x >> 5);       // destination layer
-  // lax 0: (column, row, layer) = (z, y, x), partner x + 1;   lax 1: (x, z, y), partner y + 1
-  const int W = lax == 0 ? V.nz : V.nx, L = lax == 0 ? V.nx : V.ny;
+  // lax 0: (column, row, layer) = (z, y, x), partner x + 1;   lax 1: (x, z, y), partner y + 1;   lax 2: (x, y, z), z + 1
+  const int W = lax == 0 ? V.nz : V.nx, L = lax == 0 ? V.nx : (lax == 1 ? V.ny : V.nz);
   if (dx >= W || dl >= L) return;
-  const int x = lax == 0 ? dl : dx, y = lax == 0 ? dy : dl, z = lax == 0 ? dx : dy;
-  const int x1 = lax == 0 ? min(x + 1, V.nx - 1) : x, y1 = lax == 1 ? min(y + 1, V.ny - 1) : y;
+  const int x = lax == 0 ? dl : dx, y = lax == 0 ? dy : (lax == 1 ? dl : dy), z = lax == 0 ? dx : (lax == 1 ? dy : dl);
+  const int x1 = lax == 0 ? min(x + 1, V.nx - 1) : x, y1 = lax == 1 ? min(y + 1, V.ny - 1) : y,
+            z1 = lax == 2 ? min(z + 1, V.nz - 1) : z;
   pair_t p;
-  p.x = tex2DLayered<pair_t>(V.pt, (float)x + 0.5f, (float)y + 0.5f, z).x;
-  p.y = tex2DLayered<pair_t>(V.pt, (float)x1 + 0.5f, (float)y1 + 0.5f, z).x;
+  if (DT == 0) {  // float32 volumes live in a 3-D single-channel array
+    p.x = tex3D<typename TexelType<DT>::type>(V.pt, (float)x + 0.5f, (float)y + 0.5f, (float)z + 0.5f);
+    p.y = tex3D<typename TexelType<DT>::type>(V.pt, (float)x1 + 0.5f, (float)y1 + 0.5f, (float)z1 + 0.5f);
+  } else {        // integer volumes in the z-paired layered array (lax 2 is that array itself: never built)
+    p.x = tex2DLayered<pair_t>(V.pt, (float)x + 0.5f, (float)y + 0.5f, z).x;
+    p.y = tex2DLayered<pair_t>(V.pt, (float)x1 + 0.5f, (float)y1 + 0.5f, z1).x;
+  }
   surf2DLayeredwrite(p, dst, dx * (int)sizeof(pair_t), dy, dl);
 }
 
 cudaError_t launch_axis_pair(const Volume &V, int dtype, int lax, cudaSurfaceObject_t dst, cudaStream_t st) {
-  const int W = lax == 0 ? V.nz : V.nx, H = lax == 0 ? V.ny : V.nz, L = lax == 0 ? V.nx : V.ny;
+  const int W = lax == 0 ? V.nz : V.nx, H = lax == 0 ? V.ny : (lax == 1 ? V.nz : V.ny), L = lax == 0 ? V.nx : (lax == 1 ? V.ny : V.nz);
   const dim3 grid((W + 31) / 32, H, (L + 7) / 8);
-  if (dtype == 1) axis_pair_kernel<1><<<grid, 256, 0, st>>>(V, lax, dst);
+  if (dtype == 0) axis_pair_kernel<0><<<grid, 256, 0, st>>>(V, lax, dst);
+  else if (dtype == 1) axis_pair_kernel<1><<<grid, 256, 0, st>>>(V, lax, dst);
   else if (dtype == 2) axis_pair_kernel<2><<<grid, 256, 0, st>>>(V, lax, dst);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
@@ -54,25 +61,27 @@ cudaError_t launch_axis_pair(const Volume &V, int dtype, int lax, cudaSurfaceObj
 // ---- the render kernel --------------------------------------------------------------------------------------------
 // one CTA tile (bx, by) of frame f.  ALPHA: front-to-back attenuation (alpha_pow != 0, volume_kernel.cl:300-318) with the
 // block structure of mip_alpha_kernel (spv_mip.cu): a block's 16 fetches in flight, the serial recurrence over the batch.
-template <bool ALPHA>
+template <int DT, bool ALPHA>
 __device__ __forceinline__ void mip_axis_tile(const MipAxisArgs &a, int f, unsigned bx, unsigned by, float (*s_out)[32],
                                               float (*s_alpha)[32]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned Nx = a.width, Ny = a.height;
   if (bx < a.rend_x0[f] || bx >= a.rend_x1[f] || by < a.rend_y0[f] || by >= a.rend_y1[f]) {
-    // outside the rectangle the box can project to: every ray misses (out 0, alpha 0), no ray is set up
+    // outside the rectangle the box can project to: every ray misses (out 0, alpha 0 / -1 for float32), no ray is set up
     const unsigned px0 = bx * 16, py0 = by * 8;
+    const float miss_alpha = DT == 0 ? -1.f : 0.f;
     if (Nx % 4 == 0 && px0 + 16 <= Nx && py0 + 8 <= Ny) {
       if (threadIdx.x < 64) {  // 32 float4 per plane
         float *plane = threadIdx.x < 32 ? a.out[f] : a.alpha[f];
+        const float m = threadIdx.x < 32 ? 0.f : miss_alpha;
         const unsigned v = threadIdx.x & 31;
-        *reinterpret_cast<float4 *>(plane + (size_t)(py0 + (v >> 2)) * Nx + px0 + (v & 3) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4 *>(plane + (size_t)(py0 + (v >> 2)) * Nx + px0 + (v & 3) * 4) = make_float4(m, m, m, m);
       }
     } else {
       const unsigned x = px0 + (threadIdx.x & 15), y = py0 + (threadIdx.x >> 4);
       if (x < Nx && y < Ny) {
         a.out[f][(size_t)y * Nx + x] = 0.f;
-        a.alpha[f][(size_t)y * Nx + x] = 0.f;
+        a.alpha[f][(size_t)y * Nx + x] = miss_alpha;
       }
     }
     return;
@@ -137,7 +146,9 @@ __device__ __forceinline__ void mip_axis_tile(const MipAxisArgs &a, int f, unsig
       // v = (s - min) / (max - min);  col = max(col, cum * v);  cum *= 1 - 0.1 a^2 v   (integer volumes)
       // `if (cum <= .01) break` leaves the inner loop only: a ray that has gone dark still takes one sample at the start
       // of every remaining block, and the n-th executed sample sits at pos0 + n * delta.
-      const float minVal = a.min_val, maxVal = a.max_val, att = .1f * a.alpha_pow * a.alpha_pow;
+      // (float32 volumes: cum *= 1 - a^2 clamp(v, 0, 1), volume_kernel.cl:146)
+      const float minVal = a.min_val, maxVal = a.max_val;
+      const float att = DT == 0 ? a.alpha_pow * a.alpha_pow : .1f * a.alpha_pow * a.alpha_pow;
       const int nblocks = a.max_steps / 16 + 1;
       float cum = 1.f, col = 0.f;
       int n = 0;  // samples executed so far
@@ -151,7 +162,7 @@ __device__ __forceinline__ void mip_axis_tile(const MipAxisArgs &a, int f, unsig
           float v = fmaf(fr[0], t[0].y - t[0].x, t[0].x) * a.scale;
           v = (maxVal == 0.f) ? v : (v - minVal) / (maxVal - minVal);
           col = fmaxf(col, cum * v);
-          cum *= 1.f - att * v;
+          cum *= DT == 0 ? 1.f - att * clampf_cl(v, 0.f, 1.f) : 1.f - att * v;
           ++n;
           j0 = 1;
           done = cum <= 0.01f;
@@ -166,7 +177,7 @@ __device__ __forceinline__ void mip_axis_tile(const MipAxisArgs &a, int f, unsig
               float v = fmaf(fr[j], t[j].y - t[j].x, t[j].x) * a.scale;
               v = (maxVal == 0.f) ? v : (v - minVal) / (maxVal - minVal);
               col = fmaxf(col, cum * v);
-              cum *= 1.f - att * v;
+              cum *= DT == 0 ? 1.f - att * clampf_cl(v, 0.f, 1.f) : 1.f - att * v;
               ++n;
               done = cum <= 0.01f;
             }
@@ -179,7 +190,7 @@ __device__ __forceinline__ void mip_axis_tile(const MipAxisArgs &a, int f, unsig
   }
 
   // ---- epilogue: window, gamma; the tile goes through shared memory and leaves as 128-bit stores ----
-  const float alphaVal = hit ? tnear : 0.f;
+  const float alphaVal = DT == 0 ? (hit ? 1.f : -1.f) : (hit ? tnear : 0.f);  // volume_kernel.cl:176-177 / :333-334
   const float outVal = hit ? (ALPHA ? cur : window_value(cur, a.min_val, a.max_val, a.gamma)) : 0.f;
   float *out_rows = a.out[f] + (size_t)ty0 * Nx, *alpha_rows = a.alpha[f] + (size_t)ty0 * Nx;
   const bool vec_ok = (Nx % 4 == 0) && (tx0 + tw <= Nx) && (ty0 + th <= Ny);
@@ -216,7 +227,7 @@ __global__ void __launch_bounds__(128) mip_axis_kernel(const __grid_constant__ M
       by = (blockIdx.z & 1u) ? gridDim.z - 1u - (blockIdx.z >> 1) : (blockIdx.z >> 1);
     }
   }
-  mip_axis_tile<ALPHA>(a, f, bx, by, s_out, s_alpha);
+  mip_axis_tile<DT, ALPHA>(a, f, bx, by, s_out, s_alpha);
   if (a.band_done) {  // this CTA's rows are stored: tell the copy streams (bands count from the first launched tile row)
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -235,15 +246,21 @@ cudaError_t launch_mip_axis(const MipAxisArgs &a, int dtype, cudaStream_t st) {
   if (gx == 0 || gz == 0) return cudaSuccess;  // no frame's box is on screen
   const dim3 grid(gx, a.n_frames, gz);
   const bool att = a.alpha_pow != 0.f;
-  if (dtype == 1) { if (att) mip_axis_kernel<1, true><<<grid, 128, 0, st>>>(a); else mip_axis_kernel<1, false><<<grid, 128, 0, st>>>(a); }
-  else if (dtype == 2) { if (att) mip_axis_kernel<2, true><<<grid, 128, 0, st>>>(a); else mip_axis_kernel<2, false><<<grid, 128, 0, st>>>(a); }
+#define SPV_AXIS(DT) \
+  do { if (att) mip_axis_kernel<DT, true><<<grid, 128, 0, st>>>(a); else mip_axis_kernel<DT, false><<<grid, 128, 0, st>>>(a); } while (0)
+  if (dtype == 0) SPV_AXIS(0);
+  else if (dtype == 1) SPV_AXIS(1);
+  else if (dtype == 2) SPV_AXIS(2);
   else return cudaErrorInvalidValue;
+#undef SPV_AXIS
   return cudaGetLastError();
 }
 
 cudaError_t preload_mip_axis() {
   cudaFuncAttributes fa;
-  cudaError_t e = cudaFuncGetAttributes(&fa, mip_axis_kernel<1, false>);
+  cudaError_t e = cudaFuncGetAttributes(&fa, mip_axis_kernel<0, false>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, mip_axis_kernel<0, true>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, mip_axis_kernel<1, false>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, mip_axis_kernel<1, true>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, mip_axis_kernel<2, false>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, mip_axis_kernel<2, true>);
