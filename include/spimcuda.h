@@ -148,7 +148,7 @@ SPV_API int spv_render_mip(spv_ctx *ctx, const spv_mip_params *p);
 SPV_API int spv_render_mip_to_host(spv_ctx *ctx, const spv_mip_params *p, int bands, int wait, float **host);
 /* ---- several frames per launch (new; the record loop of a keyframe / rotation sequence:
  *      spimagine/gui/mainwidget.py renders frame after frame through _render_max_project, volumerender.py:327-390).
- *      n <= SPV_MAX_BATCH projections (plain or attenuated, one part) of the resident integer volume that share the
+ *      n <= SPV_MAX_BATCH projections (plain or attenuated, one part) of the resident volume (integer in the paired layout, or float32) that share the
  *      projection, box, window and step count and differ in their model view: invM = n row-major float[16], the invP
  *      of spv_set_matrices.  ONE launch; its CTAs are dealt (tile row, frame, tile column), so the frames' CTAs of a
  *      tile row run together and share the volume in L2; every frame picks the layered copy of the volume (pairs along
@@ -317,10 +317,11 @@ SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
  * slot, spv_select_slot -- runs beside them; reads through this library wait for the passes by themselves, a caller that
  * takes spv_device_ptr must call spv_stream_join or spv_sync first (off by default; render_sequence switches it on),
  * knob 15 = the same for plain max projections into output slot 1 (a frame starts in the tail of the one before),
- * knob 16 = layered copies plain max projections of integer volumes sample (never changes a result by more than the
+ * knob 16 = layered copies max projections sample (never changes a result by more than the
  * texture unit's weight rounding; the hit mask and alpha plane never change): 1 (default) = per frame the copy with pairs
  * along x, y or z and the lane-to-pixel map under which a texture request stays inside one layer, chosen from the camera
- * alone (the x / y copies are built on the device when first wanted, 4 bytes per voxel each), 2 = the primary z copy only,
+ * alone (the x / y copies -- for float32 volumes, whose array is 3-D, the z copy as well -- are built on the device when
+ * first wanted, 4 bytes per voxel each, 8 for float32), 2 = the primary z copy only (float32: mip_fast_kernel),
  * 0 = mip_fast_kernel on the z copy (round 1's path), 10 + 3 * axis + map = forced (tests). */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 /* Which kernel family renders plain (alpha_pow == 0, num_parts == 1) max projections of uint16 volumes

@@ -541,7 +541,7 @@ class VolumeRenderer(object):
         issues frame i+2 into the slot of frame i (copy a frame that must outlive that); otherwise copies.
         iso_planes=2 reads back only what a display needs of an iso-surface frame (output, output_alpha: 8 of the
         28 bytes per pixel); output_depth / output_normals / output_occlusion are None for such frames.
-        Max projections of integer volumes are rendered `batch` frames per launch (at most 16;
+        Max projections are rendered `batch` frames per launch (at most 16;
         batch=1: one launch per frame as above): the frames of a launch share the volume in L2 (spv_render_mip_batch),
         and a launch's frames are copied to pinned memory band by band while it renders.  All frames of a launch use the
         renderer's settings (projection, window, box, data) as they are when the launch is issued, so this is the
@@ -678,11 +678,12 @@ class VolumeRenderer(object):
                     self.set_modelView(last)  # the context's own matrices follow the sequence, as with one launch per frame
 
     def set_view_copies(self, mode="auto"):
-        """Which layered copies of an integer volume plain max projections sample (csrc/spv_mip_axis.cu): "auto" (default)
+        """Which layered copies of the volume max projections sample (csrc/spv_mip_axis.cu): "auto" (default)
         = per frame the copy with pairs along x, y or z under which a texture request stays inside one layer -- the x / y
         copies cost 4 bytes per voxel each and are built on the device when a frame first wants them after an upload;
-        "primary" = the z copy only (time points that are uploaded, rendered once and replaced); "off" = mip_fast_kernel,
-        as round 1."""
+        (8 for float32 volumes, for which the z copy is an extra one as well);
+        "primary" = the z copy only (time points that are uploaded, rendered once and replaced; float32: mip_fast_kernel
+        on the 3-D array); "off" = mip_fast_kernel, as round 1."""
         codes = {"off": 0, "auto": 1, "primary": 2}
         if mode not in codes:
             raise KeyError("view copies = '%s' not defined, valid: %s" % (mode, sorted(codes)))
