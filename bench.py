@@ -588,11 +588,13 @@ def run_iso(args, rank, local_rank, world):
         for r_ in rend.render_sequence((cams[i % NF][0] for i in range(6)), method="iso_surface", iso_planes=2):
             pass
         chk = 0.
+        b0 = rend.d2h_bytes()
         t0 = time.perf_counter()
         for r_ in rend.render_sequence((cams[i % NF][0] for i in range(args.steps)), method="iso_surface", iso_planes=2):
             chk += float(r_.output[W // 2, W // 2])
         torch.cuda.synchronize()
         t_seq = time.perf_counter() - t0
+        d2h_seq = (rend.d2h_bytes() - b0) / float(args.steps)
     # where the time of a sort-last frame goes (peer composite): device time per phase, statistics on, untimed
     phases = None
     if world > 1 and args.composite == "peer":
@@ -670,9 +672,10 @@ def run_iso(args, rank, local_rank, world):
                     "peer memory (candidates pushed to the band owners, MIN + redistribution by the owners, finished "
                     "pixels stored into every rank by the crossing's owner; arrival counters, no NCCL on the data path)"
                     if args.composite == "peer" else "NCCL (MIN int32 2 planes, SUM float32 7 planes)")))},
-            "e2e": ({"value": args.steps / t_seq, "unit": "frames/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 2 * W * W * 4,
+            "e2e": ({"value": args.steps / t_seq, "unit": "frames/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": int(round(d2h_seq)),
                      "note": "VolumeRenderer.render_sequence(modelViews, method='iso_surface', iso_planes=2): output + alpha of "
-                             "every frame reach pinned host memory (8 MiB per frame); two frames in flight"}
+                             "every frame reach pinned host memory (the rectangle the projected box can touch: the rest holds "
+                             "no surface and reads out 0 / alpha 0 already); two frames in flight"}
                     if t_seq else
                     {"value": args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 2 * W * W * 4,
                      "note": "SlabMaxProjector.set_modelView + render(method='iso_surface') on every rank: output + alpha read "

@@ -55,6 +55,7 @@ struct spv_ctx {
   // per output slot: rows [dirty_lo, dirty_hi) of the pinned out / alpha staging may differ from the miss values
   // (out 0, alpha clean_alpha); every other row holds them
   int dirty_lo[2] = {0, 0}, dirty_hi[2] = {0, 0};
+  int dirty_x0[2] = {0, 0}, dirty_x1[2] = {0, 0};  // ... and, of those rows, the columns [dirty_x0, dirty_x1)
   float clean_alpha[2] = {0.f, 0.f};
   int direct_host = 0;  // spv_render_mip_to_host: the kernel stores straight into the pinned staging (tuning knob 3)
   unsigned *d_tile_counter = nullptr;
@@ -98,6 +99,11 @@ struct spv_ctx {
   spv_ctx *extra[MAX_EXTRA_SLABS] = {nullptr};  // spv_set_extra_slabs: contexts whose slabs my slab renders march too
   int n_extra = 0;
   int last_method = 0;    // 0 = mip, 1 = iso
+  // per output slot: the camera and box of the iso-surface frame that was rendered into it last (valid_iso_s), for the
+  // clipped read-back of spv_read_pinned_async
+  Camera iso_cam_s[2];
+  float iso_box_s[2][6];
+  bool valid_iso_s[2] = {false, false};
   unsigned long long *d_stats = nullptr;
   unsigned long long h_stats[40] = {0};  // hit rays, samples fetched, longest warp / sum over warps (cycles; iso search)
   unsigned long long launches = 0;
@@ -295,6 +301,7 @@ static int alloc_slot(spv_ctx *ctx, int s) {
   CU(cudaMallocHost(&ctx->hpin_s[s], 7 * n * sizeof(float)));
   memset(ctx->hpin_s[s], 0, 7 * n * sizeof(float));
   ctx->dirty_lo[s] = ctx->dirty_hi[s] = 0;
+  ctx->dirty_x0[s] = ctx->dirty_x1[s] = 0;
   ctx->clean_alpha[s] = 0.f;
   return 0;
 }
@@ -303,26 +310,40 @@ static int alloc_slot(spv_ctx *ctx, int s) {
 static void staging_dirty(spv_ctx *ctx, int s) {
   ctx->dirty_lo[s] = 0;
   ctx->dirty_hi[s] = ctx->height;
+  ctx->dirty_x0[s] = 0;
+  ctx->dirty_x1[s] = ctx->width;
 }
-// make rows outside [ya, yb) of slot s's out / alpha staging hold the miss values (the staging is quiescent)
-static void staging_clean_outside(spv_ctx *ctx, int s, int ya, int yb, float miss_alpha) {
-  const int H = ctx->height;
+// make everything outside the rectangle [xa, xb) x [ya, yb) of slot s's out / alpha staging hold the miss values (the
+// staging is quiescent): what the tracked dirty rectangle covers outside the new one is refilled
+static void staging_clean_outside_rect(spv_ctx *ctx, int s, int xa, int xb, int ya, int yb, float miss_alpha) {
+  const int H = ctx->height, Wd = ctx->width;
   const size_t W = (size_t)ctx->width, n = ctx->n();
   if (ctx->clean_alpha[s] != miss_alpha) staging_dirty(ctx, s);
-  const int parts[2][2] = {{ctx->dirty_lo[s], ctx->dirty_hi[s] < ya ? ctx->dirty_hi[s] : ya},
-                           {ctx->dirty_lo[s] > yb ? ctx->dirty_lo[s] : yb, ctx->dirty_hi[s]}};
-  for (int k = 0; k < 2; ++k) {
-    const int r0 = parts[k][0] < 0 ? 0 : parts[k][0], r1 = parts[k][1] > H ? H : parts[k][1];
-    if (r0 >= r1) continue;
-    float *o = ctx->hpin_s[s] + (size_t)r0 * W, *al = ctx->hpin_s[s] + n + (size_t)r0 * W;
-    const size_t cnt = (size_t)(r1 - r0) * W;
-    memset(o, 0, cnt * sizeof(float));
-    if (miss_alpha == 0.f) memset(al, 0, cnt * sizeof(float));
-    else for (size_t i = 0; i < cnt; ++i) al[i] = miss_alpha;
-  }
+  const int dx0 = ctx->dirty_x0[s] < 0 ? 0 : ctx->dirty_x0[s], dx1 = ctx->dirty_x1[s] > Wd ? Wd : ctx->dirty_x1[s];
+  const int dy0 = ctx->dirty_lo[s] < 0 ? 0 : ctx->dirty_lo[s], dy1 = ctx->dirty_hi[s] > H ? H : ctx->dirty_hi[s];
+  const bool keep = xa < xb && ya < yb;
+  auto fill = [&](int y, int x0, int x1) {
+    if (x0 >= x1) return;
+    float *o = ctx->hpin_s[s] + (size_t)y * W, *al = ctx->hpin_s[s] + n + (size_t)y * W;
+    memset(o + x0, 0, (size_t)(x1 - x0) * sizeof(float));
+    if (miss_alpha == 0.f) memset(al + x0, 0, (size_t)(x1 - x0) * sizeof(float));
+    else std::fill(al + x0, al + x1, miss_alpha);
+  };
+  if (dx0 < dx1)
+    for (int y = dy0; y < dy1; ++y) {
+      if (!keep || y < ya || y >= yb) { fill(y, dx0, dx1); continue; }
+      fill(y, dx0, dx1 < xa ? dx1 : xa);
+      fill(y, dx0 > xb ? dx0 : xb, dx1);
+    }
   ctx->clean_alpha[s] = miss_alpha;
-  ctx->dirty_lo[s] = ya < yb ? ya : 0;
-  ctx->dirty_hi[s] = ya < yb ? yb : 0;
+  ctx->dirty_lo[s] = keep ? ya : 0;
+  ctx->dirty_hi[s] = keep ? yb : 0;
+  ctx->dirty_x0[s] = keep ? xa : 0;
+  ctx->dirty_x1[s] = keep ? xb : 0;
+}
+// rows only: the rectangle spans the image's width
+static void staging_clean_outside(spv_ctx *ctx, int s, int ya, int yb, float miss_alpha) {
+  staging_clean_outside_rect(ctx, s, 0, ctx->width, ya, yb, miss_alpha);
 }
 
 static int alloc_buffers(spv_ctx *ctx, int w, int h) {
@@ -1325,6 +1346,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     }
   }
   const bool axis_ok = axis && !ctx->axis_failed[lax];  // (float32 volumes: all three copies may have failed)
+  ctx->valid_iso_s[ctx->slot] = false;
   ctx->last_axis = axis_ok ? lax : -1;
   ctx->last_quad = axis_ok ? quad : -1;
   MipAxisArgs ax;
@@ -2059,6 +2081,9 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
     }
   }
   ctx->last_method = 1;
+  ctx->iso_cam_s[s] = ctx->cam;
+  memcpy(ctx->iso_box_s[s], p->box, sizeof ctx->iso_box_s[s]);
+  ctx->valid_iso_s[s] = true;
   rc = end_render(ctx);
   if (rc) return rc;
   if (to_host) {
@@ -2131,6 +2156,7 @@ SPV_API int spv_iso_slab_search(spv_ctx *ctx, const spv_iso_params *p) {
   CU(launch_iso_slab(a, fmt_of(ctx), linear, 0, k, k + ctx->n(), ctx->occ(), ctx->d_iso_err, ctx->stream));
   ctx->launches += 1;
   ctx->last_method = 1;
+  ctx->valid_iso_s[ctx->slot] = false;  // (sort-last frames: read back whole)
   return end_render(ctx);
 }
 
@@ -2294,6 +2320,7 @@ SPV_API int spv_render_iso_composite(spv_ctx *ctx, const spv_iso_params *p) {
     CU(cudaMemsetAsync(ctx->occ(), 0, n * sizeof(float), ctx->stream));  // what the NCCL path's resolve leaves there
   }
   ctx->last_method = 1;
+  ctx->valid_iso_s[ctx->slot] = false;  // (sort-last frames: read back whole)
   return end_render(ctx);
 #undef SPV_PHASE
 }
@@ -2390,15 +2417,38 @@ SPV_API int spv_read_pinned_async(spv_ctx *ctx, int planes) {
   BIND();
   if (planes < 1 || planes > 7) return fail(ctx, SPV_EINVAL, "spv_read_pinned_async: planes must be 1..7");
   const int s = ctx->slot;
-  staging_dirty(ctx, s);
   CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
   CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
   // iso overlap: the slot's screen-space passes run beside the render stream; the copy waits for them, the render
   // stream (and with it the next frame's search) does not
   if (ctx->post_pending[s]) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_posted[s], 0));
-  CU(cudaMemcpyAsync(ctx->hpin_s[s], ctx->dbuf_s[s], (size_t)planes * ctx->n() * sizeof(float), cudaMemcpyDeviceToHost,
-                     ctx->copy_stream));
-  ctx->d2h_bytes += (size_t)planes * ctx->n() * sizeof(float);
+  // output + alpha of an iso-surface frame (what a display needs): pixels the projected box cannot touch hold no surface --
+  // out 0 (shading_kernel: depth = INFINITY), alpha 0 (iso kernels: no crossing) for every element type -- and are not
+  // copied; the pinned rows hold those values already (as for max projections, tuning knob 9)
+  if (ctx->last_method == 1 && ctx->valid_iso_s[s] && planes <= 2 && ctx->clip_copies) {
+    const int W = ctx->width, H = ctx->height;
+    int xa, xb, ya, yb;
+    miss_free_rect(ctx->iso_cam_s[s], ctx->iso_box_s[s], W, H, xa, xb, ya, yb);
+    if (ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // the staging is about to be cleaned
+    staging_clean_outside_rect(ctx, s, xa, xb, ya, yb, 0.f);
+    if (xa < xb && ya < yb) {
+      cudaMemcpy3DParms cp;  // the rectangle of the leading plane(s) in one 3-D copy
+      memset(&cp, 0, sizeof cp);
+      cp.srcPtr = make_cudaPitchedPtr(ctx->dbuf_s[s], (size_t)W * sizeof(float), (size_t)W, (size_t)H);
+      cp.dstPtr = make_cudaPitchedPtr(ctx->hpin_s[s], (size_t)W * sizeof(float), (size_t)W, (size_t)H);
+      cp.srcPos = make_cudaPos((size_t)xa * sizeof(float), (size_t)ya, 0);
+      cp.dstPos = cp.srcPos;
+      cp.extent = make_cudaExtent((size_t)(xb - xa) * sizeof(float), (size_t)(yb - ya), (size_t)planes);
+      cp.kind = cudaMemcpyDeviceToHost;
+      CU(cudaMemcpy3DAsync(&cp, ctx->copy_stream));
+      ctx->d2h_bytes += (size_t)planes * (size_t)(xb - xa) * (size_t)(yb - ya) * sizeof(float);
+    }
+  } else {
+    staging_dirty(ctx, s);
+    CU(cudaMemcpyAsync(ctx->hpin_s[s], ctx->dbuf_s[s], (size_t)planes * ctx->n() * sizeof(float), cudaMemcpyDeviceToHost,
+                       ctx->copy_stream));
+    ctx->d2h_bytes += (size_t)planes * ctx->n() * sizeof(float);
+  }
   CU(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));
   ctx->copy_pending[s] = true;
   return 0;

@@ -67,6 +67,45 @@ def test_sequence_equals_frame_by_frame_iso():
     rend.close()
 
 
+def test_iso_sequence_reads_back_only_rows_that_can_hold_a_surface():
+    """render_sequence(method="iso_surface", iso_planes=2): output and alpha of rows the projected box cannot touch are
+    not copied (they hold out 0 / alpha 0 for every element type); cameras that move the box across the image, max
+    projections and full read-backs in between, float32 and uint16 volumes -- every frame equals the blocking render"""
+    from spimagine_b200.utils.transform_matrices import mat4_rotation, mat4_translate
+    P = scenes.gui_camera(0., 4.)[1]
+    cams = [np.dot(mat4_translate(0.3 * math.sin(i), 1.4 * math.cos(0.9 * i), -4.5 - 0.5 * (i % 3)), mat4_rotation(0.4 * i, 0., 1., 0.))
+            for i in range(9)]
+    cams.append(np.dot(mat4_translate(0., 9., -4.), mat4_rotation(0.3, 0., 1., 0.)))   # the box is off screen
+    for vol, maxval in ((scenes.iso_sphere(48), 20.), (scenes.vol_g(56, np.uint16, seed=2), 30000.)):
+        rend = _renderer((144, 176), pinned_outputs=True)
+        rend.set_data(vol)
+        rend.set_projection(P)
+        rend.set_max_val(maxval)
+        try:
+            want = []
+            for M in cams:
+                rend.render(modelView=M, method="iso_surface")
+                want.append((rend.output.copy(), rend.output_alpha.copy()))
+            assert any(w[0].max() > 0 for w in want) and want[-1][0].max() == 0
+            b0 = rend.d2h_bytes()
+            got = [(r.output.copy(), r.output_alpha.copy()) for r in
+                   rend.render_sequence(cams, method="iso_surface", iso_planes=2)]
+            moved = rend.d2h_bytes() - b0
+            assert 0 < moved < 0.9 * len(cams) * 2 * 144 * 176 * 4        # rows were left out ...
+            for i, ((o, a), (wo, wa)) in enumerate(zip(got, want)):        # ... and the frames read the same
+                assert np.array_equal(o, wo) and np.array_equal(a, wa), i
+            # a max projection and a full iso read-back dirty the staging in between
+            rend.render(modelView=cams[2], method="max_project")
+            full = [r.output_depth.copy() for r in rend.render_sequence(cams[:3], method="iso_surface")]
+            assert np.isfinite(full[0]).any()
+            got = [(r.output.copy(), r.output_alpha.copy()) for r in
+                   rend.render_sequence(cams[::-1], method="iso_surface", iso_planes=2)]
+            for i, ((o, a), (wo, wa)) in enumerate(zip(got, want[::-1])):
+                assert np.array_equal(o, wo) and np.array_equal(a, wa), i
+        finally:
+            rend.close()
+
+
 def test_sequence_abandoned_midway_leaves_renderer_usable():
     data = scenes.vol_g(32, np.uint16, seed=1)
     cams = [scenes.gui_camera(0.1 * f, 3.5) for f in range(6)]
