@@ -99,11 +99,10 @@ struct spv_ctx {
   spv_ctx *extra[MAX_EXTRA_SLABS] = {nullptr};  // spv_set_extra_slabs: contexts whose slabs my slab renders march too
   int n_extra = 0;
   int last_method = 0;    // 0 = mip, 1 = iso
-  // per output slot: the camera and box of the iso-surface frame that was rendered into it last (valid_iso_s), for the
-  // clipped read-back of spv_read_pinned_async
-  Camera iso_cam_s[2];
-  float iso_box_s[2][6];
-  bool valid_iso_s[2] = {false, false};
+  // per output slot: camera, box and alpha miss value of the finished frame it holds (valid), for the clipped read-back
+  // of out + alpha (spv_read_pinned, spv_read_pinned_async): pixels outside the projected box are misses
+  struct SlotClip { bool valid = false; Camera cam; float box[6]; float miss_alpha = 0.f; };
+  SlotClip clip_s[2];
   unsigned long long *d_stats = nullptr;
   unsigned long long h_stats[40] = {0};  // hit rays, samples fetched, longest warp / sum over warps (cycles; iso search)
   unsigned long long launches = 0;
@@ -344,6 +343,13 @@ static void staging_clean_outside_rect(spv_ctx *ctx, int s, int xa, int xb, int 
 // rows only: the rectangle spans the image's width
 static void staging_clean_outside(spv_ctx *ctx, int s, int ya, int yb, float miss_alpha) {
   staging_clean_outside_rect(ctx, s, 0, ctx->width, ya, yb, miss_alpha);
+}
+
+static void slot_clip_set(spv_ctx *ctx, int s, const Camera &cam, const float *box, float miss_alpha) {
+  ctx->clip_s[s].valid = true;
+  ctx->clip_s[s].cam = cam;
+  memcpy(ctx->clip_s[s].box, box, sizeof ctx->clip_s[s].box);
+  ctx->clip_s[s].miss_alpha = miss_alpha;
 }
 
 static int alloc_buffers(spv_ctx *ctx, int w, int h) {
@@ -1346,7 +1352,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     }
   }
   const bool axis_ok = axis && !ctx->axis_failed[lax];  // (float32 volumes: all three copies may have failed)
-  ctx->valid_iso_s[ctx->slot] = false;
+  ctx->clip_s[ctx->slot].valid = false;
   ctx->last_axis = axis_ok ? lax : -1;
   ctx->last_quad = axis_ok ? quad : -1;
   MipAxisArgs ax;
@@ -1476,6 +1482,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
       ctx->d2h_bytes += 2 * cnt * sizeof(float);
     }
     ctx->last_method = 0;
+    if (!raw_only) slot_clip_set(ctx, s, a.cam, a.box, (ctx->dtype == SPV_F32 ? -1.f : 0.f));
     rc = end_render(ctx);
     if (rc) return rc;
     if (ctx->copy_streams > 1) {
@@ -1526,6 +1533,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     }
   }
   ctx->last_method = 0;
+  if (!raw_only && !push) slot_clip_set(ctx, s, a.cam, a.box, (ctx->dtype == SPV_F32 ? -1.f : 0.f));
   rc = end_render(ctx);
   if (rc) return rc;
   if (to_host) {
@@ -1939,6 +1947,7 @@ SPV_API int spv_render_mip_composite(spv_ctx *ctx, const spv_mip_params *p) {
   CU(launch_comp_sync(ctx->peer_flags, ctx->comp_flags, W, R, 1, f, ctx->comp_err, ctx->stream));
   CU(cudaEventRecord(ctx->ev1, ctx->stream));  // spv_last_timing_ms covers render + composite
   ctx->launches += 3;
+  slot_clip_set(ctx, ctx->slot, ctx->cam, p->box, (ctx->dtype == SPV_F32 ? -1.f : 0.f));  // the composited frame: misses outside the projected box
   return 0;
 }
 
@@ -1973,6 +1982,7 @@ SPV_API int spv_mip_finish(spv_ctx *ctx, const spv_mip_params *p) {
   CU(launch_mip_finish(ctx->raw(), ctx->out(), (int)ctx->n(), p->min_val, p->max_val, p->gamma, ctx->stream));
   ctx->launches += 1;
   ctx->last_method = 0;
+  slot_clip_set(ctx, ctx->slot, ctx->cam, p->box, (ctx->dtype == SPV_F32 ? -1.f : 0.f));  // the composited frame: misses outside the projected box
   return 0;
 }
 
@@ -2081,9 +2091,7 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
     }
   }
   ctx->last_method = 1;
-  ctx->iso_cam_s[s] = ctx->cam;
-  memcpy(ctx->iso_box_s[s], p->box, sizeof ctx->iso_box_s[s]);
-  ctx->valid_iso_s[s] = true;
+  slot_clip_set(ctx, s, ctx->cam, p->box, 0.f);  // no surface: out 0 (shading_kernel), alpha 0 (every element type)
   rc = end_render(ctx);
   if (rc) return rc;
   if (to_host) {
@@ -2156,7 +2164,7 @@ SPV_API int spv_iso_slab_search(spv_ctx *ctx, const spv_iso_params *p) {
   CU(launch_iso_slab(a, fmt_of(ctx), linear, 0, k, k + ctx->n(), ctx->occ(), ctx->d_iso_err, ctx->stream));
   ctx->launches += 1;
   ctx->last_method = 1;
-  ctx->valid_iso_s[ctx->slot] = false;  // (sort-last frames: read back whole)
+  ctx->clip_s[ctx->slot].valid = false;  // (sort-last iso frames: read back whole)
   return end_render(ctx);
 }
 
@@ -2320,7 +2328,7 @@ SPV_API int spv_render_iso_composite(spv_ctx *ctx, const spv_iso_params *p) {
     CU(cudaMemsetAsync(ctx->occ(), 0, n * sizeof(float), ctx->stream));  // what the NCCL path's resolve leaves there
   }
   ctx->last_method = 1;
-  ctx->valid_iso_s[ctx->slot] = false;  // (sort-last frames: read back whole)
+  ctx->clip_s[ctx->slot].valid = false;  // (sort-last iso frames: read back whole)
   return end_render(ctx);
 #undef SPV_PHASE
 }
@@ -2384,15 +2392,45 @@ SPV_API int spv_read_many(spv_ctx *ctx, float *out, float *alpha, float *depth, 
   return 0;
 }
 
+// Enqueue the copy of the leading `planes` result planes of slot s into its pinned staging on stream st (the staging is
+// quiescent).  output + alpha of a finished frame (what a display needs): pixels the projected box cannot touch are misses
+// -- out 0; alpha 0 for integer max projections and for iso surfaces (no crossing), -1 for float32 max projections -- and
+// are not copied; the pinned planes hold those values there already (tuning knob 9, as spv_render_mip_to_host).
+static int copy_slot_planes(spv_ctx *ctx, int s, int planes, cudaStream_t st) {
+  const spv_ctx::SlotClip &c = ctx->clip_s[s];
+  if (c.valid && planes <= 2 && ctx->clip_copies) {
+    const int W = ctx->width, H = ctx->height;
+    int xa, xb, ya, yb;
+    miss_free_rect(c.cam, c.box, W, H, xa, xb, ya, yb);
+    staging_clean_outside_rect(ctx, s, xa, xb, ya, yb, c.miss_alpha);
+    if (xa < xb && ya < yb) {
+      cudaMemcpy3DParms cp;  // the rectangle of the leading plane(s) in one 3-D copy
+      memset(&cp, 0, sizeof cp);
+      cp.srcPtr = make_cudaPitchedPtr(ctx->dbuf_s[s], (size_t)W * sizeof(float), (size_t)W, (size_t)H);
+      cp.dstPtr = make_cudaPitchedPtr(ctx->hpin_s[s], (size_t)W * sizeof(float), (size_t)W, (size_t)H);
+      cp.srcPos = make_cudaPos((size_t)xa * sizeof(float), (size_t)ya, 0);
+      cp.dstPos = cp.srcPos;
+      cp.extent = make_cudaExtent((size_t)(xb - xa) * sizeof(float), (size_t)(yb - ya), (size_t)planes);
+      cp.kind = cudaMemcpyDeviceToHost;
+      CU(cudaMemcpy3DAsync(&cp, st));
+      ctx->d2h_bytes += (size_t)planes * (size_t)(xb - xa) * (size_t)(yb - ya) * sizeof(float);
+    }
+    return 0;
+  }
+  staging_dirty(ctx, s);
+  CU(cudaMemcpyAsync(ctx->hpin_s[s], ctx->dbuf_s[s], (size_t)planes * ctx->n() * sizeof(float), cudaMemcpyDeviceToHost, st));
+  ctx->d2h_bytes += (size_t)planes * ctx->n() * sizeof(float);
+  return 0;
+}
+
 SPV_API int spv_read_pinned(spv_ctx *ctx, int planes, float **host) {
   BIND();
   if (planes < 1 || planes > 7 || !host) return fail(ctx, SPV_EINVAL, "spv_read_pinned: planes must be 1..7");
   if (ctx->copy_pending[ctx->slot]) CU(cudaEventSynchronize(ctx->ev_copied[ctx->slot]));  // same staging memory
-  staging_dirty(ctx, ctx->slot);
   int rcj = join_post(ctx, ctx->slot);
   if (rcj) return rcj;
-  CU(cudaMemcpyAsync(ctx->hpin, ctx->dbuf, (size_t)planes * ctx->n() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  ctx->d2h_bytes += (size_t)planes * ctx->n() * sizeof(float);
+  rcj = copy_slot_planes(ctx, ctx->slot, planes, ctx->stream);
+  if (rcj) return rcj;
   CU(cudaStreamSynchronize(ctx->stream));
   *host = ctx->hpin;
   return 0;
@@ -2422,32 +2460,10 @@ SPV_API int spv_read_pinned_async(spv_ctx *ctx, int planes) {
   // iso overlap: the slot's screen-space passes run beside the render stream; the copy waits for them, the render
   // stream (and with it the next frame's search) does not
   if (ctx->post_pending[s]) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_posted[s], 0));
-  // output + alpha of an iso-surface frame (what a display needs): pixels the projected box cannot touch hold no surface --
-  // out 0 (shading_kernel: depth = INFINITY), alpha 0 (iso kernels: no crossing) for every element type -- and are not
-  // copied; the pinned rows hold those values already (as for max projections, tuning knob 9)
-  if (ctx->last_method == 1 && ctx->valid_iso_s[s] && planes <= 2 && ctx->clip_copies) {
-    const int W = ctx->width, H = ctx->height;
-    int xa, xb, ya, yb;
-    miss_free_rect(ctx->iso_cam_s[s], ctx->iso_box_s[s], W, H, xa, xb, ya, yb);
-    if (ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // the staging is about to be cleaned
-    staging_clean_outside_rect(ctx, s, xa, xb, ya, yb, 0.f);
-    if (xa < xb && ya < yb) {
-      cudaMemcpy3DParms cp;  // the rectangle of the leading plane(s) in one 3-D copy
-      memset(&cp, 0, sizeof cp);
-      cp.srcPtr = make_cudaPitchedPtr(ctx->dbuf_s[s], (size_t)W * sizeof(float), (size_t)W, (size_t)H);
-      cp.dstPtr = make_cudaPitchedPtr(ctx->hpin_s[s], (size_t)W * sizeof(float), (size_t)W, (size_t)H);
-      cp.srcPos = make_cudaPos((size_t)xa * sizeof(float), (size_t)ya, 0);
-      cp.dstPos = cp.srcPos;
-      cp.extent = make_cudaExtent((size_t)(xb - xa) * sizeof(float), (size_t)(yb - ya), (size_t)planes);
-      cp.kind = cudaMemcpyDeviceToHost;
-      CU(cudaMemcpy3DAsync(&cp, ctx->copy_stream));
-      ctx->d2h_bytes += (size_t)planes * (size_t)(xb - xa) * (size_t)(yb - ya) * sizeof(float);
-    }
-  } else {
-    staging_dirty(ctx, s);
-    CU(cudaMemcpyAsync(ctx->hpin_s[s], ctx->dbuf_s[s], (size_t)planes * ctx->n() * sizeof(float), cudaMemcpyDeviceToHost,
-                       ctx->copy_stream));
-    ctx->d2h_bytes += (size_t)planes * ctx->n() * sizeof(float);
+  if (ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // the staging may be cleaned by the host
+  {
+    int rcc = copy_slot_planes(ctx, s, planes, ctx->copy_stream);
+    if (rcc) return rcc;
   }
   CU(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));
   ctx->copy_pending[s] = true;
