@@ -1115,12 +1115,14 @@ def run_slab(args, rank, local_rank, world, own_pg=True):
         if rend.readback_ranks is None or rank in rend.readback_ranks:
             digest.update(rend.output.tobytes())
     barrier()
+    d2h0 = rend.d2h_bytes()
     t0 = time.perf_counter()
     for i in range(args.steps):
         rend.set_modelView(cams[(i * 7) % SWEEP][0])
         rend.render()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    d2h_e2e = (rend.d2h_bytes() - d2h0) / float(args.steps)  # this rank's (rank 0: the display rank's) bytes per frame
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -1155,9 +1157,10 @@ def run_slab(args, rank, local_rank, world, own_pg=True):
             "gsamples_per_s": fps * hits0 * SAMPLES_PER_RAY / 1e9,
             "hit_rays_per_frame": hits0, "issued_samples_per_frame_all_ranks": issued_total,
             "e2e": {"value": args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128,
-                    "d2h_bytes_per_step": 2 * W * W * 4,
+                    "d2h_bytes_per_step": int(round(d2h_e2e)),
                     "note": "SlabMaxProjector.set_modelView + render() on every rank, composited output + alpha read "
-                            "back into pinned host memory%s" % (" on rank 0 (the display rank)" if peer else " on every rank")},
+                            "back into pinned host memory%s (the rectangle the projected box can touch; the rest of the "
+                            "planes holds the miss values already)" % (" on rank 0 (the display rank)" if peer else " on every rank")},
             "image_sha1_first8": digest.hexdigest(),
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3 / args.steps) / 1e9 / world,
