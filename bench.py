@@ -574,12 +574,14 @@ def run_iso(args, rank, local_rank, world):
             digest.update(np.ascontiguousarray(a).tobytes())
         hit_px = int(np.isfinite(rend.output_depth).sum())
     barrier()
+    d2h0 = rend.d2h_bytes()
     t0 = time.perf_counter()
     for i in range(args.steps):
         rend.set_modelView(cams[i % NF][0])
         rend.render(method="iso_surface")
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    d2h_sync = (rend.d2h_bytes() - d2h0) / float(args.steps)
     barrier()
     # one GPU: the same frames through render_sequence (output + alpha of every frame reach pinned host memory; frame
     # i+1's search runs beside frame i's screen-space passes and read-back)
@@ -681,10 +683,10 @@ def run_iso(args, rank, local_rank, world):
                      "note": "SlabMaxProjector.set_modelView + render(method='iso_surface') on every rank: output + alpha read "
                              "back per frame (8 MiB)"}),
             "e2e_synchronous": {"value": args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128,
-                                "d2h_bytes_per_step": 2 * W * W * 4,
+                                "d2h_bytes_per_step": int(round(d2h_sync)),
                                 "note": "set_modelView + render(method='iso_surface'), blocking per frame: output + alpha read "
-                                        "back (8 MiB); depth, normals and occlusion stay on the device until they are looked "
-                                        "at (lazy attributes)"},
+                                        "back (the rectangle the projected box can touch); depth, normals and occlusion stay "
+                                        "on the device until they are looked at (lazy attributes)"},
             "surface_pixels_last": hit_px, "image_sha1_first8": digest.hexdigest(),
             # iso_fast, blur, occlusion list + queue, blur, shading; sort-last: search, resolve, fix-up, 2+2 blur
             # launches, occlusion list + queue, shading (the two NCCL reductions are not counted)

@@ -340,11 +340,6 @@ static void staging_clean_outside_rect(spv_ctx *ctx, int s, int xa, int xb, int 
   ctx->dirty_x0[s] = keep ? xa : 0;
   ctx->dirty_x1[s] = keep ? xb : 0;
 }
-// rows only: the rectangle spans the image's width
-static void staging_clean_outside(spv_ctx *ctx, int s, int ya, int yb, float miss_alpha) {
-  staging_clean_outside_rect(ctx, s, 0, ctx->width, ya, yb, miss_alpha);
-}
-
 static void slot_clip_set(spv_ctx *ctx, int s, const Camera &cam, const float *box, float miss_alpha) {
   ctx->clip_s[s].valid = true;
   ctx->clip_s[s].cam = cam;
@@ -1406,6 +1401,30 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
   }
   if (to_host && ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // staging about to be rewritten
   const int H = ctx->height;
+  // read-back: columns [clip_xa, clip_xb) of the copied rows (the projected box's rectangle where rows are clipped too)
+  int clip_xa = 0, clip_xb = ctx->width;
+  auto clip_columns = [&]() {
+    int xa, xb, ya, yb;
+    miss_free_rect(a.cam, a.box, ctx->width, H, xa, xb, ya, yb);
+    clip_xa = xa;
+    clip_xb = xb;
+  };
+  // rows [c0, c1) x those columns of the value and alpha planes in one 3-D copy (depth 2 = the two planes)
+  auto copy_rows = [&](int c0, int c1, cudaStream_t cs) -> int {
+    if (c0 >= c1 || clip_xa >= clip_xb) return 0;
+    const size_t Wd = (size_t)ctx->width;
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof cp);
+    cp.srcPtr = make_cudaPitchedPtr(ctx->dbuf_s[ctx->slot], Wd * sizeof(float), Wd, (size_t)H);
+    cp.dstPtr = make_cudaPitchedPtr(ctx->hpin_s[ctx->slot], Wd * sizeof(float), Wd, (size_t)H);
+    cp.srcPos = make_cudaPos((size_t)clip_xa * sizeof(float), (size_t)c0, 0);
+    cp.dstPos = cp.srcPos;
+    cp.extent = make_cudaExtent((size_t)(clip_xb - clip_xa) * sizeof(float), (size_t)(c1 - c0), 2);
+    cp.kind = cudaMemcpyDeviceToHost;
+    CU(cudaMemcpy3DAsync(&cp, cs));
+    ctx->d2h_bytes += 2 * (size_t)(clip_xb - clip_xa) * (size_t)(c1 - c0) * sizeof(float);
+    return 0;
+  };
   const bool direct = to_host && ctx->direct_host && plain && p->num_parts == 1 && !raw_only;
   if (direct) {  // zero-copy: the result planes are written over PCIe by the kernel's own 128-bit stores
     staging_dirty(ctx, s);
@@ -1443,7 +1462,8 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
         clip_a = ya - 8 > 0 ? ya - 8 : 0;
         clip_b = yb + 8 < H ? yb + 8 : H;
         if (clip_a >= clip_b) clip_a = clip_b = 0;
-        staging_clean_outside(ctx, s, clip_a, clip_b, ctx->dtype == SPV_F32 ? -1.f : 0.f);
+        clip_columns();
+        staging_clean_outside_rect(ctx, s, clip_xa, clip_xb, clip_a, clip_b, ctx->dtype == SPV_F32 ? -1.f : 0.f);
       } else {
         staging_dirty(ctx, s);
       }
@@ -1472,14 +1492,12 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
       ctx->band_expect[b] += ctas_x * (unsigned)((y1 - y0 + 7) / 8);
       const int c0 = y0 > clip_a ? y0 : clip_a, c1 = y1 < clip_b ? y1 : clip_b;  // the band's rows that can hold hits
       if (c0 >= c1) continue;
-      const size_t off = (size_t)c0 * ctx->width, cnt = (size_t)(c1 - c0) * ctx->width, n = ctx->n();
       cudaStream_t cs = (ctx->copy_streams > 1 && (i & 1)) ? ctx->copy_stream2 : ctx->copy_stream;
       CUresult wr = wait_value_fn()(cs, (CUdeviceptr)(uintptr_t)(ctx->d_band_done + b), ctx->band_expect[b],
                                     CU_STREAM_WAIT_VALUE_GEQ);
       if (wr != CUDA_SUCCESS) return fail(ctx, (int)wr, "cuStreamWaitValue32 failed");
-      CU(cudaMemcpy2DAsync(ctx->hpin_s[s] + off, n * sizeof(float), ctx->dbuf_s[s] + off, n * sizeof(float),
-                           cnt * sizeof(float), 2, cudaMemcpyDeviceToHost, cs));
-      ctx->d2h_bytes += 2 * cnt * sizeof(float);
+      rc = copy_rows(c0, c1, cs);
+      if (rc) return rc;
     }
     ctx->last_method = 0;
     if (!raw_only) slot_clip_set(ctx, s, a.cam, a.box, (ctx->dtype == SPV_F32 ? -1.f : 0.f));
@@ -1502,7 +1520,8 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
       clip_a = (int)ta * 8 - 8 > 0 ? (int)ta * 8 - 8 : 0;
       clip_b = (int)tb * 8 + 8 < H ? (int)tb * 8 + 8 : H;
       if (clip_a >= clip_b) clip_a = clip_b = 0;
-      staging_clean_outside(ctx, s, clip_a, clip_b, ctx->dtype == SPV_F32 ? -1.f : 0.f);
+      clip_columns();
+      staging_clean_outside_rect(ctx, s, clip_xa, clip_xb, clip_a, clip_b, ctx->dtype == SPV_F32 ? -1.f : 0.f);
     } else {
       staging_dirty(ctx, s);
     }
@@ -1523,13 +1542,10 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     }
     const int c0 = y0 > clip_a ? y0 : clip_a, c1 = y1 < clip_b ? y1 : clip_b;
     if (to_host && !direct && c0 < c1) {
-      const size_t off = (size_t)c0 * ctx->width, cnt = (size_t)(c1 - c0) * ctx->width, n = ctx->n();
       CU(cudaEventRecord(ctx->ev_rendered[s], kst));
       CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
-      // the band's rows of the value plane and of the alpha plane in ONE 2-D copy (2 "rows" one plane apart)
-      CU(cudaMemcpy2DAsync(ctx->hpin_s[s] + off, n * sizeof(float), ctx->dbuf_s[s] + off, n * sizeof(float),
-                           cnt * sizeof(float), 2, cudaMemcpyDeviceToHost, ctx->copy_stream));
-      ctx->d2h_bytes += 2 * cnt * sizeof(float);
+      rc = copy_rows(c0, c1, ctx->copy_stream);  // the band's part of the value and alpha planes in one copy
+      if (rc) return rc;
     }
   }
   ctx->last_method = 0;
@@ -2058,7 +2074,33 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   rc = join_post(ctx, s);  // the passes of the frame that used this slot last may still be running
   if (rc) return rc;
   if (to_host && ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // staging about to be rewritten
-  if (to_host) staging_dirty(ctx, s);
+  // read-back: only the rectangle the projected box can touch (outside it there is no surface: out 0, alpha 0, which the
+  // pinned planes hold already)
+  int cxa = 0, cxb = ctx->width, cya = 0, cyb = ctx->height;
+  if (to_host) {
+    if (ctx->clip_copies) {
+      miss_free_rect(ctx->cam, p->box, ctx->width, ctx->height, cxa, cxb, cya, cyb);
+      staging_clean_outside_rect(ctx, s, cxa, cxb, cya, cyb, 0.f);
+    } else {
+      staging_dirty(ctx, s);
+    }
+  }
+  // planes [first, first + count) of the slot, clipped to that rectangle, device -> pinned on the copy stream
+  auto copy_planes = [&](int first, int count) -> int {
+    if (cxa >= cxb || cya >= cyb) return 0;
+    const size_t W = (size_t)ctx->width, H = (size_t)ctx->height;
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof cp);
+    cp.srcPtr = make_cudaPitchedPtr(ctx->dbuf_s[s], W * sizeof(float), W, H);
+    cp.dstPtr = make_cudaPitchedPtr(ctx->hpin_s[s], W * sizeof(float), W, H);
+    cp.srcPos = make_cudaPos((size_t)cxa * sizeof(float), (size_t)cya, (size_t)first);
+    cp.dstPos = cp.srcPos;
+    cp.extent = make_cudaExtent((size_t)(cxb - cxa) * sizeof(float), (size_t)(cyb - cya), (size_t)count);
+    cp.kind = cudaMemcpyDeviceToHost;
+    CU(cudaMemcpy3DAsync(&cp, ctx->copy_stream));
+    ctx->d2h_bytes += (size_t)count * (size_t)(cxb - cxa) * (size_t)(cyb - cya) * sizeof(float);
+    return 0;
+  };
   CU(launch_iso(a, fmt_of(ctx), linear, ctx->sampler == SPV_SAMPLER_EXACT, ctx->stats_on != 0, ctx->stream));
   ctx->launches += 1;
   cudaStream_t pst = ctx->stream;
@@ -2072,8 +2114,8 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   if (to_host && post) {
     CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
     CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
-    CU(cudaMemcpyAsync(ctx->hpin_s[s] + n, ctx->dbuf_s[s] + n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
-    ctx->d2h_bytes += n * sizeof(float);
+    rc = copy_planes(1, 1);  // the alpha plane is final once the march has run
+    if (rc) return rc;
   }
   if (post) {
     // volumerender.py:470-497
@@ -2097,9 +2139,8 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   if (to_host) {
     CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
     CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
-    CU(cudaMemcpyAsync(ctx->hpin_s[s], ctx->dbuf_s[s], (post ? 1 : 2) * n * sizeof(float), cudaMemcpyDeviceToHost,
-                       ctx->copy_stream));
-    ctx->d2h_bytes += (post ? 1 : 2) * n * sizeof(float);
+    rc = copy_planes(0, post ? 1 : 2);
+    if (rc) return rc;
     CU(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));
     ctx->copy_pending[s] = true;
   }
