@@ -2068,9 +2068,9 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   const size_t n = ctx->n();
   // overlap (tuning knob 14): this frame's screen-space passes go to post_stream, so that the NEXT frame's search (other
   // slot, render stream) runs beside them -- the search leaves a third of the SM time idle in its tail, the passes are
-  // five small launches.  Only for device-only renders; whoever reads the planes joins (spv_read*, spv_stream_join,
-  // spv_sync).  (Putting every other frame's search on a stream of its own as well was measured: no further gain.)
-  const bool overlap = ctx->iso_overlap && post && !to_host && !ctx->stats_on;
+  // five small launches.  Whoever reads the planes joins (spv_read*, spv_stream_join, spv_sync); the read-back of
+  // spv_render_iso_to_host waits for the passes on the copy stream only.  (Putting every other frame's search on a stream of its own as well was measured: no further gain.)
+  const bool overlap = ctx->iso_overlap && post && !ctx->stats_on;
   rc = join_post(ctx, s);  // the passes of the frame that used this slot last may still be running
   if (rc) return rc;
   if (to_host && ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // staging about to be rewritten
@@ -2137,8 +2137,12 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   rc = end_render(ctx);
   if (rc) return rc;
   if (to_host) {
-    CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
-    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
+    if (overlap) {  // the passes ran beside the render stream: the value plane is final when they are
+      CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_posted[s], 0));
+    } else {
+      CU(cudaEventRecord(ctx->ev_rendered[s], ctx->stream));
+      CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rendered[s], 0));
+    }
     rc = copy_planes(0, post ? 1 : 2);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));

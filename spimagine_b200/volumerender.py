@@ -588,8 +588,13 @@ class VolumeRenderer(object):
                 else:
                     p = _lib.IsoParams(self._box(), float(self.maxVal / 2), float(self.gamma), int(self.max_steps),
                                        float(self.occ_strength), int(self.occ_radius), int(self.occ_n_points), 0)
-                    self._check(self._lib.spv_render_iso(self._ctx, C.byref(p)))
-                    self._check(self._lib.spv_read_pinned_async(self._ctx, planes))
+                    if planes == 2:
+                        # output + alpha only: the alpha plane travels as soon as the search is done, the value plane
+                        # when the screen-space passes (beside the next frame's search) are
+                        self._check(self._lib.spv_render_iso_to_host(self._ctx, C.byref(p), 0, None))
+                    else:
+                        self._check(self._lib.spv_render_iso(self._ctx, C.byref(p)))
+                        self._check(self._lib.spv_read_pinned_async(self._ctx, planes))
                 pending.append(slot)
                 i += 1
                 if len(pending) == 2:
