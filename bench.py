@@ -677,7 +677,8 @@ def run_iso(args, rank, local_rank, world):
             "e2e": ({"value": args.steps / t_seq, "unit": "frames/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": int(round(d2h_seq)),
                      "note": "VolumeRenderer.render_sequence(modelViews, method='iso_surface', iso_planes=2): output + alpha of "
                              "every frame reach pinned host memory (the rectangle the projected box can touch: the rest holds "
-                             "no surface and reads out 0 / alpha 0 already); two frames in flight"}
+                             "no surface and reads out 0 / alpha 0 already); renders issued three frames ahead of the frame "
+                             "handed out, read-backs two ahead"}
                     if t_seq else
                     {"value": args.steps / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 2 * W * W * 4,
                      "note": "SlabMaxProjector.set_modelView + render(method='iso_surface') on every rank: output + alpha read "

@@ -2074,6 +2074,9 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   rc = join_post(ctx, s);  // the passes of the frame that used this slot last may still be running
   if (rc) return rc;
   if (to_host && ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // staging about to be rewritten
+  // a device-only render into a slot whose planes an asynchronous read-back may still be copying: the search waits for it
+  // on the device (render_sequence issues frames three ahead of the one it hands out)
+  if (!to_host && ctx->copy_pending[s]) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[s], 0));
   // read-back: only the rectangle the projected box can touch (outside it there is no surface: out 0, alpha 0, which the
   // pinned planes hold already)
   int cxa = 0, cxb = ctx->width, cya = 0, cyb = ctx->height;

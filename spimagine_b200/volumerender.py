@@ -568,33 +568,24 @@ class VolumeRenderer(object):
                 for _ in self._render_sequence_batched(modelViews, p, batch or self.batch_frames):
                     yield self
                 return
+        if method == "iso_surface":
+            for _ in self._render_sequence_iso(modelViews, planes, clear):
+                yield self
+            return
+        # one launch per frame (float volumes with the copies switched off, skipping, the exact sampler, iterators that
+        # change the renderer as they are pulled): two frames in flight over the two output slots
         pending = []  # slots in flight, oldest first
         i = 0
-        if method == "iso_surface":
-            # frame i's screen-space passes run on a second stream beside frame i+1's search (tuning knob 14)
-            self._check(self._lib.spv_set_tuning(self._ctx, 14, 1))
-        else:
-            # the frames of slot 1 run on a second stream: a frame starts in the tail of the one before (tuning knob 15)
-            self._check(self._lib.spv_set_tuning(self._ctx, 15, 1))
+        # the frames of slot 1 run on a second stream: a frame starts in the tail of the one before (tuning knob 15)
+        self._check(self._lib.spv_set_tuning(self._ctx, 15, 1))
         try:
             for M in modelViews:
                 slot = i & 1
                 self._check(self._lib.spv_select_slot(self._ctx, slot))
                 self.set_modelView(M)
-                if method == "max_project":
-                    p = _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma),
-                                       float(self.alphaPow), 1, 0, int(self.max_steps), 0)
-                    self._check(self._lib.spv_render_mip_to_host(self._ctx, C.byref(p), 1, 0, None))
-                else:
-                    p = _lib.IsoParams(self._box(), float(self.maxVal / 2), float(self.gamma), int(self.max_steps),
-                                       float(self.occ_strength), int(self.occ_radius), int(self.occ_n_points), 0)
-                    if planes == 2:
-                        # output + alpha only: the alpha plane travels as soon as the search is done, the value plane
-                        # when the screen-space passes (beside the next frame's search) are
-                        self._check(self._lib.spv_render_iso_to_host(self._ctx, C.byref(p), 0, None))
-                    else:
-                        self._check(self._lib.spv_render_iso(self._ctx, C.byref(p)))
-                        self._check(self._lib.spv_read_pinned_async(self._ctx, planes))
+                p = _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma),
+                                   float(self.alphaPow), 1, 0, int(self.max_steps), 0)
+                self._check(self._lib.spv_render_mip_to_host(self._ctx, C.byref(p), 1, 0, None))
                 pending.append(slot)
                 i += 1
                 if len(pending) == 2:
@@ -604,10 +595,61 @@ class VolumeRenderer(object):
                 self._adopt_slot(pending.pop(0), planes, clear)
                 yield self
         finally:
-            self._lib.spv_set_tuning(self._ctx, 14, 0)
-            self._lib.spv_set_tuning(self._ctx, 15, 0)
-            self._lib.spv_sync(self._ctx)
-            self._lib.spv_select_slot(self._ctx, 0)
+            if getattr(self, "_ctx", None) is not None and self._ctx.value:
+                self._lib.spv_set_tuning(self._ctx, 15, 0)
+                self._lib.spv_sync(self._ctx)
+                self._lib.spv_select_slot(self._ctx, 0)
+
+    def _render_sequence_iso(self, modelViews, planes, clear):
+        """Iso-surface frames of a sequence: renders are issued three frames ahead of the frame that is handed out,
+        read-backs two ahead.  A device slot is reused as soon as the copy out of it has been enqueued (the next search
+        into it waits for that copy on the device); a slot's pinned staging is rewritten only after the frame it held
+        has been handed out and the consumer has come back.  The screen-space passes of frame i run beside the search
+        of frame i + 1 (tuning knob 14)."""
+        it = iter(modelViews)
+        rendered, copied = [], []   # frame numbers: rendered but not yet read back / read-back enqueued, oldest first
+        state = {"n": 0}
+        lib, ctx = self._lib, self._ctx
+
+        def render_next():
+            try:
+                M = next(it)
+            except StopIteration:
+                return False
+            k = state["n"]
+            self._check(lib.spv_select_slot(ctx, k & 1))
+            self.set_modelView(M)
+            p = _lib.IsoParams(self._box(), float(self.maxVal / 2), float(self.gamma), int(self.max_steps),
+                               float(self.occ_strength), int(self.occ_radius), int(self.occ_n_points), 0)
+            self._check(lib.spv_render_iso(ctx, C.byref(p)))
+            rendered.append(k)
+            state["n"] = k + 1
+            return True
+
+        def copy_next():
+            k = rendered.pop(0)
+            self._check(lib.spv_select_slot(ctx, k & 1))
+            self._check(lib.spv_read_pinned_async(ctx, planes))
+            copied.append(k)
+
+        self._check(lib.spv_set_tuning(ctx, 14, 1))
+        try:
+            for _ in range(2):
+                if render_next():
+                    copy_next()
+            render_next()
+            while copied:
+                k = copied.pop(0)
+                self._adopt_slot(k & 1, planes, clear)
+                yield self
+                if rendered:
+                    copy_next()
+                render_next()
+        finally:
+            if getattr(self, "_ctx", None) is not None and self._ctx.value:
+                lib.spv_set_tuning(ctx, 14, 0)
+                lib.spv_sync(ctx)
+                lib.spv_select_slot(ctx, 0)
 
     def _mip_params(self, numParts=1, currentPart=0):
         return _lib.MipParams(self._box(), float(self.minVal), float(self.maxVal), float(self.gamma),
