@@ -236,7 +236,10 @@ SPV_API int spv_read(spv_ctx *ctx, int which, float *host_dst, size_t n);
  * scattered to the given host pointers (any may be NULL) */
 SPV_API int spv_read_many(spv_ctx *ctx, float *out, float *alpha, float *depth, float *normals, float *occ);
 /* zero-copy variant: one device->host transfer of the first `planes` planes of [out | alpha | depth | occ |
- * normals(3)] into the context's pinned staging buffer; *host points at it (valid until the next read/resize) */
+ * normals(3)] into the context's pinned staging buffer; *host points at it (valid until the next read/resize).
+ * With planes <= 2 and a finished frame in the slot (max projection, composite, iso surface) only the rectangle the
+ * projected box can touch is transferred (tuning knob 9): every pixel outside it is a miss, and the staging holds the
+ * miss values there already (out 0; alpha 0, or -1 for float32 max projections) -- the staging is read-only for callers. */
 SPV_API int spv_read_pinned(spv_ctx *ctx, int planes, float **host);
 SPV_API int spv_device_ptr(spv_ctx *ctx, int which, void **dev_ptr);
 
@@ -256,7 +259,7 @@ SPV_API int spv_read_rgba8(spv_ctx *ctx, int mode_black, unsigned char *host_dst
  * into a slot waits on the device for an asynchronous read of that slot that is still in flight. */
 SPV_API int spv_select_slot(spv_ctx *ctx, int slot);
 /* enqueue one device->host transfer of the first `planes` planes of the selected slot on the context's copy stream,
- * ordered after everything enqueued so far on the render stream; returns immediately */
+ * ordered after everything enqueued so far on the render stream; returns immediately (clipped like spv_read_pinned) */
 SPV_API int spv_read_pinned_async(spv_ctx *ctx, int planes);
 /* block until the last asynchronous read of `slot` has landed; *host = its pinned staging (valid until the next
  * read of that slot or a resize) */
