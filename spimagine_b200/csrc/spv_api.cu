@@ -1448,6 +1448,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
     const int nb = (H + rows - 1) / rows;
     int order[64];
     int clip_a = 0, clip_b = H;  // rows that are copied; the others are known to be misses and are not
+    bool clean_after_launch = false;
     if (ctx->row_mode == 1) {
       // rows the box cannot project to are dealt first, then its rows top to bottom: bands without any of those rows
       // complete at once, the others in ascending order
@@ -1463,7 +1464,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
         clip_b = yb + 8 < H ? yb + 8 : H;
         if (clip_a >= clip_b) clip_a = clip_b = 0;
         clip_columns();
-        staging_clean_outside_rect(ctx, s, clip_xa, clip_xb, clip_a, clip_b, ctx->dtype == SPV_F32 ? -1.f : 0.f);
+        clean_after_launch = true;  // (outside the rectangle the copies write: the host refills it beside the kernel)
       } else {
         staging_dirty(ctx, s);
       }
@@ -1484,6 +1485,8 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
       CU(cudaEventRecord(ctx->ev_posted[s], kst));
       ctx->post_pending[s] = true;
     }
+    if (clean_after_launch)
+      staging_clean_outside_rect(ctx, s, clip_xa, clip_xb, clip_a, clip_b, ctx->dtype == SPV_F32 ? -1.f : 0.f);
     const unsigned ctas_x = (unsigned)(ctx->width + 15) / 16;
     for (int i = 0; i < nb; ++i) {
       // enqueue the copies in the order the bands complete, alternating between the copy streams
@@ -2081,12 +2084,8 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   // pinned planes hold already)
   int cxa = 0, cxb = ctx->width, cya = 0, cyb = ctx->height;
   if (to_host) {
-    if (ctx->clip_copies) {
-      miss_free_rect(ctx->cam, p->box, ctx->width, ctx->height, cxa, cxb, cya, cyb);
-      staging_clean_outside_rect(ctx, s, cxa, cxb, cya, cyb, 0.f);
-    } else {
-      staging_dirty(ctx, s);
-    }
+    if (ctx->clip_copies) miss_free_rect(ctx->cam, p->box, ctx->width, ctx->height, cxa, cxb, cya, cyb);
+    else staging_dirty(ctx, s);
   }
   // planes [first, first + count) of the slot, clipped to that rectangle, device -> pinned on the copy stream
   auto copy_planes = [&](int first, int count) -> int {
@@ -2106,6 +2105,8 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   };
   CU(launch_iso(a, fmt_of(ctx), linear, ctx->sampler == SPV_SAMPLER_EXACT, ctx->stats_on != 0, ctx->stream));
   ctx->launches += 1;
+  // (the pinned planes outside the rectangle go back to the miss values on the host while the search runs)
+  if (to_host && ctx->clip_copies) staging_clean_outside_rect(ctx, s, cxa, cxb, cya, cyb, 0.f);
   cudaStream_t pst = ctx->stream;
   if (overlap) {
     // one set of scratch (occlusion queue; tmp planes are per slot, taps constant): the passes of successive frames
