@@ -302,6 +302,7 @@ static int alloc_slot(spv_ctx *ctx, int s) {
   ctx->dirty_lo[s] = ctx->dirty_hi[s] = 0;
   ctx->dirty_x0[s] = ctx->dirty_x1[s] = 0;
   ctx->clean_alpha[s] = 0.f;
+  ctx->clip_s[s].valid = false;  // no finished frame in the new planes
   return 0;
 }
 
