@@ -726,15 +726,17 @@ def run_blur(args, rank, local_rank, world):
     by_mode = {}
     for fuse in (1, 0):  # x + y as one kernel (opt-in) / three passes (the default, timed last): same result
         vf.set_tuning(0, fuse)
-        ms = []
+        ms, pass_ms = [], []
         for i in range(warmup + steps):
             vf.load_device(dvol.data_ptr(), vol.shape, np.uint16)  # read in place: 512 MiB result > L2 between steps
             vf.convolve_sep3(*taps)
             vf.sync()
             if i >= warmup:
                 ms.append(vf.last_ms())
+                pass_ms.append(vf.last_pass_ms())
         by_mode[fuse] = float(np.mean(ms))
     dev_ms = by_mode[0]
+    pass_ms = [float(x) for x in np.mean(np.array(pass_ms), axis=0)]  # x, y, z pass of the three-pass mode
     got = vf.result()
     # the spectrum processor (FFTProcessor, libspimfft.so) on the same resident volume, timed beside the blur
     plan = ip.SpectrumPlan(local_rank)
@@ -804,7 +806,17 @@ def run_blur(args, rank, local_rank, world):
                      "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_step": alg, "bytes_moved_by_the_three_passes": moved,
                      "frac_of_moved_bytes": moved / (dev_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                     "kernel": "spv::conv_x_kernel<u16,19> + 2 x spv::conv_axis_kernel<19> (y, z), timed together"},
+                     "kernel": "spv::conv_x2_kernel<u16,19> (x, row pairs, pipelined) + 2 x spv::conv_axisw_kernel<19,16,4> "
+                               "(y, z; four columns per thread), packed fma.rn.f32x2; timed together",
+                     "passes": [{"pass": name, "ms": ms_k, "bytes": nvox * by, "gbytes_per_s": nvox * by / (ms_k * 1e-3) / 1e9,
+                                 "frac_of_peak": nvox * by / (ms_k * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+                                for name, ms_k, by in zip(("x: uint16 -> float32", "y: float32 -> float32", "z: float32 -> float32"),
+                                                          pass_ms, (6, 8, 8))],
+                     "note": "each pass against the bytes it moves itself; the fraction above is against the algorithmic "
+                             "bytes of the whole filter (every voxel read once, the result written once), which three "
+                             "separable passes through memory cannot reach: at the copy rate they take %.3f ms, and the "
+                             "57 fused multiply-adds per voxel alone take %.3f ms of the FMA pipes" % (
+                                 moved / peaks["hbm_gbs"] / 1e6, 57 * nvox / (148 * 128 * 1.965e9) * 1e3)},
         "cpu_baseline": {"value": 1. / t_cpu, "unit": "volumes/s", "cores": use_all_host_threads(), "kind": "port",
                          "sample": "one %d^3 corner block of the volume through oracle/filter_oracle.c (OpenMP, all host "
                                    "cores), time scaled by (%d/%d)^3" % (cb, N, cb)}}))

@@ -287,11 +287,18 @@ SPV_API int spv_filter_sync(spv_filter *f);
 SPV_API int spv_filter_result_device(spv_filter *f, float **dev);
 SPV_API int spv_filter_read(spv_filter *f, float *host_dst, size_t n);
 SPV_API int spv_filter_last_ms(spv_filter *f, float *ms);  /* device time of the last convolution (three passes) */
+/* device time of each kernel of the last convolution: ms[0..2] = x, y, z pass (passes = 3), or fused x + y, z, 0
+ * (passes = 2); `passes` may be NULL */
+SPV_API int spv_filter_last_pass_ms(spv_filter *f, float ms[3], int *passes);
 SPV_API const char *spv_filter_last_error(spv_filter *f);  /* f may be NULL: last create error */
 /* knob 0: 1 = the x and y pass run as one kernel where both tap counts fall into the same size class of at most 31
  * taps (one float32 round trip of the volume less; measured slower than the three passes so far), 0 = three passes
- * (default); knob 1: variant of the y / z passes (process-wide): 1 = automatic,
- * 16 / 32 = outputs per thread, 2 / 4 = columns per thread where the row length allows it; results are identical */
+ * (default); knob 1: variant of the y / z passes (process-wide): 1 = automatic (four columns per thread where rows
+ * are multiples of 16 bytes, two where of 8 bytes, else one), 16 / 32 = one column, that many outputs per thread,
+ * 1602 / 1604 = two / four columns per thread; knob 2 (process-wide): the x pass works on row pairs through a
+ * software-pipelined tile loop (2, default), on row pairs with loads at the top of every tile (1), on single rows (0).
+ * The variants with several columns / row pairs update two outputs per instruction (packed fma.rn.f32x2 of sm_100,
+ * each half an IEEE fused multiply-add); results are identical bit for bit under every knob */
 SPV_API int spv_filter_set_tuning(spv_filter *f, int knob, int value);
 SPV_API int spv_filter_launch_count(spv_filter *f, unsigned long long *n);  /* kernels launched by this filter so far */
 

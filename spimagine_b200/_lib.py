@@ -121,6 +121,7 @@ SIGNATURES = {
     "spv_filter_result_device": (C.c_int, [_CTX, C.POINTER(_FP)]),
     "spv_filter_read": (C.c_int, [_CTX, _FP, C.c_size_t]),
     "spv_filter_last_ms": (C.c_int, [_CTX, _FP]),
+    "spv_filter_last_pass_ms": (C.c_int, [_CTX, _FP, C.POINTER(C.c_int)]),
     "spv_filter_last_error": (C.c_char_p, [_CTX]),
     "spv_filter_set_tuning": (C.c_int, [_CTX, C.c_int, C.c_int]),
     "spv_filter_launch_count": (C.c_int, [_CTX, C.POINTER(C.c_ulonglong)]),

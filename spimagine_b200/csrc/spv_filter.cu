@@ -99,8 +99,11 @@ __global__ void __launch_bounds__(128) conv_axis_kernel(const float *__restrict_
 }
 
 // The same pass W = 2 or 4 columns wide: a thread owns x = W t .. W t + W - 1 (one 64- or 128-bit load / store per
-// position: 1/W of the address arithmetic and memory instructions per output) and R outputs of each column.  Needs
-// nx % W == 0 and volumes aligned to 4 W bytes.  grid = (ceil(nx / (128 W)), ceil(na / R), no).
+// position: 1/W of the address arithmetic and memory instructions per output) and R outputs of each column.  The
+// two columns of a 64-bit pair are updated by ONE packed instruction (FFMA2 of sm_100: fma.rn.f32x2, whose weight
+// operand is a broadcast scalar out of a uniform register) -- each half is the same IEEE fused multiply-add as the
+// scalar kernel's, so the results are bit-identical while the issue slots per output halve.  Needs nx % W == 0 and
+// volumes aligned to 4 W bytes.  grid = (ceil(nx / (128 W)), ceil(na / R), no).
 template <int W> struct VecOf;
 template <> struct VecOf<2> { typedef float2 type; };
 template <> struct VecOf<4> { typedef float4 type; };
@@ -109,6 +112,7 @@ template <int NHMAX, int NHMIN, int R, int W>
 __global__ void __launch_bounds__(128) conv_axisw_kernel(const float *__restrict__ in, float *__restrict__ out, int nx, int na,
                                                          size_t sa, size_t so, int nh, const FilterTaps t) {
   typedef typename VecOf<W>::type vec;
+  constexpr int P = W / 2;  // packed pairs per position
   const int x = (blockIdx.x * 128 + threadIdx.x) * W;
   if (x >= nx) return;
   const int p0 = blockIdx.y * R;
@@ -117,53 +121,54 @@ __global__ void __launch_bounds__(128) conv_axisw_kernel(const float *__restrict
   const int half = nh / 2;
   const int qtop = p0 + R - 1 + half;
   const int nsteps = R + nh - 1;
-  float acc[R][W];
+  float2 acc[R][P];
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int k = 0; k < W; ++k) acc[r][k] = 0.f;
+    for (int k = 0; k < P; ++k) acc[r][k] = make_float2(0.f, 0.f);
   const bool interior = qtop < na && qtop - (nsteps - 1) >= 0;  // uniform per CTA
-  const float *ptr = src + (size_t)qtop * sa;
-#pragma unroll
-  for (int jj = 0; jj < R + NHMAX - 1; ++jj) {
-    const int q = qtop - jj;
-    float v[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) v[k] = 0.f;
-    if ((jj < R + NHMIN - 1 || jj < nsteps) && (interior || (q >= 0 && q < na))) {
-      const vec l = __ldg(reinterpret_cast<const vec *>(ptr));
-      v[0] = l.x;
-      v[1] = l.y;
-      if (W == 4) {
-        v[2] = reinterpret_cast<const float *>(&l)[2];
-        v[3] = reinterpret_cast<const float *>(&l)[3];
-      }
-    }
-    ptr -= sa;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int ht = jj - (R - 1 - r);
-      if (ht >= 0 && ht < NHMAX && (ht < NHMIN || ht < nh)) {
-        const float w = t.w[ht];
-#pragma unroll
-        for (int k = 0; k < W; ++k) acc[r][k] = fmaf(w, v[k], acc[r][k]);
-      }
-    }
+  constexpr int K = R + NHMAX - 2;
+  const unsigned step = (unsigned)(sa * sizeof(float));
+  const char *low = reinterpret_cast<const char *>(src) + ((long long)qtop - K) * (long long)(sa * sizeof(float));
+  // one step of the stream: the position's W columns meet the taps of the R outputs that see it
+#define SPV_AXISW_STEP(LOADED)                                                                                   \
+  {                                                                                                              \
+    float2 v[P];                                                                                                 \
+    _Pragma("unroll") for (int k = 0; k < P; ++k) v[k] = make_float2(0.f, 0.f);                                  \
+    if (LOADED) {                                                                                                \
+      const vec l = __ldg(reinterpret_cast<const vec *>(mad_wide(step, (unsigned)(K - jj), low)));              \
+      v[0] = make_float2(l.x, l.y);                                                                              \
+      if (W == 4) v[P - 1] = make_float2(reinterpret_cast<const float *>(&l)[2], reinterpret_cast<const float *>(&l)[3]); \
+    }                                                                                                            \
+    _Pragma("unroll") for (int r = 0; r < R; ++r) {                                                              \
+      const int ht = jj - (R - 1 - r);                                                                           \
+      if (ht >= 0 && ht < NHMAX && (ht < NHMIN || ht < nh)) {                                                    \
+        const float w = t.w[ht];                                                                                 \
+        _Pragma("unroll") for (int k = 0; k < P; ++k) acc[r][k] = __ffma2_rn(make_float2(w, w), v[k], acc[r][k]); \
+      }                                                                                                          \
+    }                                                                                                            \
   }
-  float *o = dst + (size_t)p0 * sa;
+  if (interior) {
+#pragma unroll
+    for (int jj = 0; jj < R + NHMAX - 1; ++jj) SPV_AXISW_STEP(jj < R + NHMIN - 1 || jj < nsteps)
+  } else {
+#pragma unroll
+    for (int jj = 0; jj < R + NHMAX - 1; ++jj) SPV_AXISW_STEP(jj < nsteps && qtop - jj >= 0 && qtop - jj < na)
+  }
+#undef SPV_AXISW_STEP
+  char *obase = reinterpret_cast<char *>(dst + (size_t)p0 * sa);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     if (p0 + r < na) {
       vec sv;
-      sv.x = acc[r][0];
-      sv.y = acc[r][1];
+      sv.x = acc[r][0].x;
+      sv.y = acc[r][0].y;
       if (W == 4) {
-        reinterpret_cast<float *>(&sv)[2] = acc[r][2];
-        reinterpret_cast<float *>(&sv)[3] = acc[r][3];
+        reinterpret_cast<float *>(&sv)[2] = acc[r][P - 1].x;
+        reinterpret_cast<float *>(&sv)[3] = acc[r][P - 1].y;
       }
-      *reinterpret_cast<vec *>(o) = sv;
+      *reinterpret_cast<vec *>(const_cast<char *>(mad_wide(step, (unsigned)r, obase))) = sv;
     }
-    o += sa;
   }
 }
 
@@ -263,6 +268,141 @@ __global__ void __launch_bounds__(32 * NW) conv_x_kernel(const TIN *__restrict__
         o += (size_t)G * nx;
       }
     }
+  }
+}
+
+// The x pass on row PAIRS, software-pipelined: a CTA of 8 warps takes tiles of 64 consecutive rows x XW = 8 R outputs,
+// a fixed grid of resident CTAs walks the tiles (x tiles fastest: concurrent CTAs read whole rows).
+//   loads    every warp loads 8 rows of the tile as whole 32-bit words (full 128-byte lines per request), all of a
+//            thread's loads in flight at once; with PIPE the NEXT tile's loads are issued before the current tile's
+//            arithmetic and wait in registers, so a CTA has a tile of reads in flight all the time (the separate
+//            load -> barrier -> compute -> barrier -> store phases of conv_x_kernel left the memory system idle for
+//            most of a CTA's life: 3.3 of 6.5 TB/s)
+//   taps     lane p owns rows p and p + 32, whose inputs sit side by side in shared memory (one 64-bit load per
+//            position); both rows are updated by ONE packed FFMA2 per tap (fma.rn.f32x2, each half the scalar
+//            kernel's IEEE fused multiply-add: bit-identical results, half the issue slots and shared-memory loads)
+//   stores   the output tile reuses the input tile's memory and leaves as coalesced rows
+// Needs rows of whole words (nx * sizeof(TIN) % 4 == 0, base aligned to 4 bytes); other volumes run conv_x_kernel.
+template <typename TIN> __device__ __forceinline__ float word_elem(unsigned w, int k) {
+  constexpr unsigned BITS = (8u * sizeof(TIN)) & 31u;
+  return to_float((w >> (BITS * k)) & ((1u << BITS) - 1u));
+}
+template <> __device__ __forceinline__ float word_elem<float>(unsigned w, int) { return __uint_as_float(w); }
+
+template <typename TIN, int NHMAX, int NHMIN, int R, int PIPE>
+__global__ void __launch_bounds__(256, PIPE ? (sizeof(TIN) == 4 ? 2 : 3) : 4) conv_x2_kernel(const TIN *__restrict__ in, float *__restrict__ out, int nx, long long nrows,
+                                                      int nh, const FilterTaps t, unsigned ntiles) {
+  constexpr int NW = 8, E = 4 / (int)sizeof(TIN);  // voxels per 32-bit word
+  constexpr int XW = NW * R, TW = XW + NHMAX - 1, PITCH = (TW + E - 1) | 1, OPITCH = XW | 1;
+  constexpr int NWORDS = (TW + 2 * (E - 1)) / E, NCH = (NWORDS + 31) / 32;  // words per tile row, 32-word chunks
+  constexpr int SMEM_FLOATS = 64 * PITCH > 64 * OPITCH ? 64 * PITCH : 64 * OPITCH;
+  static_assert(SMEM_FLOATS * sizeof(float) <= 48 * 1024, "static shared memory");
+  static_assert(NWORDS * E <= PITCH + E - 1, "tile row");
+  __shared__ __align__(8) float s_mem[SMEM_FLOATS];
+  float2(*s_in)[PITCH] = reinterpret_cast<float2(*)[PITCH]>(s_mem);   // [32][PITCH]: (row p, row p + 32)
+  float(*s_out)[OPITCH] = reinterpret_cast<float(*)[OPITCH]>(s_mem);  // [64][OPITCH], after the taps have been read
+  const unsigned ntx = (unsigned)((nx + XW - 1) / XW);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = nh / 2, nsteps = R + nh - 1;
+  const unsigned pitch8 = 8u * (unsigned)nx * (unsigned)sizeof(TIN);  // bytes between the rows a warp loads
+  unsigned held[8 * NCH];
+
+  // issue the loads of `tile`: warp w takes rows w, w + 8, ..., w + 56
+  auto issue = [&](unsigned tile) {
+    const int x0 = (int)(tile % ntx) * XW;
+    const long long row0 = (long long)(tile / ntx) * 64;
+    const int qbase = x0 + half - (NHMAX - 1);
+    const int qa = qbase - (((qbase % E) + E) % E);  // first word of the tile row (position, multiple of E)
+    const int nr = nrows - row0 < 64 ? (int)(nrows - row0) : 64;
+    const char *base = reinterpret_cast<const char *>(in) + ((row0 + warp) * (long long)nx + qa) * (long long)sizeof(TIN) + lane * 4;
+    if (nr == 64 && qa >= 0 && qa + NWORDS * E <= nx) {  // uniform: the tile lies inside the volume
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+          held[k * NCH + ch] = (ch * 32 + 31 < NWORDS || ch * 32 + lane < NWORDS)
+                                   ? __ldg(reinterpret_cast<const unsigned *>(mad_wide(pitch8, (unsigned)k, base) + ch * 128))
+                                   : 0u;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          const int wi = ch * 32 + lane, q = qa + wi * E;
+          held[k * NCH + ch] = (wi < NWORDS && q >= 0 && q < nx && warp + 8 * k < nr)
+                                   ? __ldg(reinterpret_cast<const unsigned *>(mad_wide(pitch8, (unsigned)k, base) + ch * 128))
+                                   : 0u;
+        }
+    }
+  };
+
+  unsigned tile = blockIdx.x;
+  if (tile >= ntiles) return;
+  issue(tile);
+  for (;;) {
+    const int x0 = (int)(tile % ntx) * XW;
+    const long long row0 = (long long)(tile / ntx) * 64;
+    const int qbase = x0 + half - (NHMAX - 1);
+    const int shift = ((qbase % E) + E) % E;  // tile column 0 holds position qbase - shift
+    const int nr = nrows - row0 < 64 ? (int)(nrows - row0) : 64;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int wi = ch * 32 + lane;
+        if (ch * 32 + 31 < NWORDS || wi < NWORDS) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int c = wi * E + e;
+            if (c < PITCH)
+              s_in[warp + 8 * k][c] = make_float2(word_elem<TIN>(held[k * NCH + ch], e), word_elem<TIN>(held[(k + 4) * NCH + ch], e));
+          }
+        }
+      }
+    __syncthreads();
+    const unsigned next = tile + gridDim.x;
+    if (PIPE && next < ntiles) issue(next);  // in flight during this tile's arithmetic and stores
+    float2 acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
+    const float2 *line = s_in[lane] + shift + warp * R + R - 1 + NHMAX - 1;  // column of the position met first
+#pragma unroll
+    for (int jj = 0; jj < R + NHMAX - 1; ++jj) {
+      float2 v = line[-jj];
+      if (jj >= R + NHMIN - 1 && jj >= nsteps) v = make_float2(0.f, 0.f);  // beyond the real window: only padded taps would meet it
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int ht = jj - (R - 1 - r);
+        if (ht >= 0 && ht < NHMAX && (ht < NHMIN || ht < nh)) {
+          const float w = t.w[ht];
+          acc[r] = __ffma2_rn(make_float2(w, w), v, acc[r]);
+        }
+      }
+    }
+    __syncthreads();  // every warp has read its taps: the tile's memory becomes the output tile
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      s_out[lane][warp * R + r] = acc[r].x;
+      s_out[lane + 32][warp * R + r] = acc[r].y;
+    }
+    __syncthreads();
+    {  // a thread per output column and every G-th row
+      const int c = threadIdx.x % XW, g = threadIdx.x / XW;
+      constexpr int G = 256 / XW;
+      static_assert(64 % G == 0, "rows split evenly");
+      if (x0 + c < nx) {
+        float *o = out + (size_t)(row0 + g) * nx + x0 + c;
+#pragma unroll 8
+        for (int rr = g; rr < 64; rr += G) {
+          if (rr < nr) *o = s_out[rr][c];
+          o += (size_t)G * nx;
+        }
+      }
+    }
+    if (next >= ntiles) break;
+    if (!PIPE) issue(next);
+    __syncthreads();  // the output tile has left: its memory takes the next tile's inputs
+    tile = next;
   }
 }
 
@@ -390,8 +530,8 @@ __global__ void __launch_bounds__(256) conv_generic_kernel(const TIN *__restrict
   out[base + (size_t)p * sa] = res;
 }
 
-int filter_axis_wide = 1;  // columns per thread of the y / z passes where the row length allows it: 1, 2 or 4 (tuning; measured: 1 is
-                            // fastest -- the wider variants hold too few warps to hide the load latency)
+int filter_axis_wide = 1;  // variant of the y / z passes (tuning knob 1): 1 = automatic, 16 / 32 = one column per thread with that many
+                            // outputs, 1602 / 1604 = two / four columns per thread (packed FFMA2)
 
 static const int FILT_SIZES[] = {3, 7, 11, 15, 19, 23, 27, 31, 35, 39, 47, 63};
 
@@ -401,22 +541,27 @@ static int pick_size(int nh) {
   return 0;
 }
 
+template <int NHMAX, int NHMIN, int R, int W>
+static void launch_axisw(const float *in, float *out, int nx, int na, int no, size_t sa, size_t so, int nh,
+                         const FilterTaps &t, cudaStream_t st) {
+  dim3 grid((nx + 128 * W - 1) / (128 * W), (na + R - 1) / R, no);
+  conv_axisw_kernel<NHMAX, NHMIN, R, W><<<grid, 128, 0, st>>>(in, out, nx, na, sa, so, nh, t);
+}
+
 template <int NHMAX, int NHMIN>
 static void launch_axis_n(const float *in, float *out, int nx, int na, int no, size_t sa, size_t so, int nh,
                           const FilterTaps &t, cudaStream_t st) {
-  constexpr int RW = 16;
-  if (filter_axis_wide == 4 && nx % 4 == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
-    dim3 grid((nx + 511) / 512, (na + RW - 1) / RW, no);
-    conv_axisw_kernel<NHMAX, NHMIN, RW, 4><<<grid, 128, 0, st>>>(in, out, nx, na, sa, so, nh, t);
-    return;
-  }
-  if (filter_axis_wide == 2 && nx % 2 == 0 && (((uintptr_t)in | (uintptr_t)out) & 7) == 0) {
-    dim3 grid((nx + 255) / 256, (na + RW - 1) / RW, no);
-    conv_axisw_kernel<NHMAX, NHMIN, RW, 2><<<grid, 128, 0, st>>>(in, out, nx, na, sa, so, nh, t);
-    return;
-  }
-  // 32 outputs per thread from 11 taps up (1.56 instead of 2.1 loads per output: 3-5 % faster), 16 below
-  if (filter_axis_wide == 32 || (filter_axis_wide == 1 && NHMAX >= 11)) {
+  // default (1): four columns per thread with packed FFMA2 where rows are multiples of 16 bytes, two where of 8 bytes
+  // (measured on B200, 512^3, 19 taps: y / z pass 180 / 195 us with one column, 172 / 177 with two, 164 / 171 with four =
+  // 6.3-6.5 TB/s, the copy rate; profiles/r02s3_exp_blur2.txt), else one column
+  const int wide = filter_axis_wide == 1 ? 4 : (filter_axis_wide == 1604 ? 4 : (filter_axis_wide == 1602 ? 2 : 0));
+  const bool only = filter_axis_wide != 1;  // a variant asked for by the tuning knob is not replaced by a narrower one
+  if (wide == 4 && nx % 4 == 0 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0)
+    return launch_axisw<NHMAX, NHMIN, 16, 4>(in, out, nx, na, no, sa, so, nh, t, st);
+  if ((wide == 2 || (wide == 4 && !only)) && nx % 2 == 0 && (((uintptr_t)in | (uintptr_t)out) & 7) == 0)
+    return launch_axisw<NHMAX, NHMIN, 16, 2>(in, out, nx, na, no, sa, so, nh, t, st);
+  // one column: 32 outputs per thread from 11 taps up (1.56 instead of 2.1 loads per output: 3-5 % faster), 16 below
+  if (filter_axis_wide == 32 || (filter_axis_wide != 16 && NHMAX >= 11)) {
     constexpr int R = 32;
     dim3 grid((nx + 127) / 128, (na + R - 1) / R, no);
     conv_axis_kernel<NHMAX, NHMIN, R><<<grid, 128, 0, st>>>(in, out, nx, na, sa, so, nh, t);
@@ -427,12 +572,39 @@ static void launch_axis_n(const float *in, float *out, int nx, int na, int no, s
   conv_axis_kernel<NHMAX, NHMIN, R><<<grid, 128, 0, st>>>(in, out, nx, na, sa, so, nh, t);
 }
 
+int filter_x_pairs = 2;  // x pass on row pairs with packed FFMA2 (conv_x2_kernel): 2 = software-pipelined (default), 1 = loads at the
+                         // top of every tile, 0 = conv_x_kernel (tuning knob 2)
+
+// resident CTAs of a kernel on the current device (cached per instantiation)
+template <typename K> static int resident_ctas(K kernel, int threads) {
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return sms * per_sm;
+}
+
 template <typename TIN, int NHMAX, int NHMIN>
 static void launch_x_n(const TIN *in, float *out, int nx, long long nrows, int nh, const FilterTaps &t, cudaStream_t st) {
   constexpr int R = 16, NW = 8;
+  const int words = ((size_t)nx * sizeof(TIN)) % 4 == 0 && ((uintptr_t)in & 3) == 0;
+  if constexpr (NHMAX <= 47) {
+    const unsigned long long ntiles = (unsigned long long)((nrows + 63) / 64) * ((nx + NW * R - 1) / (NW * R));
+    if (filter_x_pairs && words && ntiles < 0xffffffffull) {
+      if (filter_x_pairs == 2) {
+        static const int resident = resident_ctas(conv_x2_kernel<TIN, NHMAX, NHMIN, R, 1>, 256);
+        const unsigned grid = ntiles < (unsigned long long)resident ? (unsigned)ntiles : (unsigned)resident;
+        conv_x2_kernel<TIN, NHMAX, NHMIN, R, 1><<<grid, 256, 0, st>>>(in, out, nx, nrows, nh, t, (unsigned)ntiles);
+      } else {
+        static const int resident = resident_ctas(conv_x2_kernel<TIN, NHMAX, NHMIN, R, 0>, 256);
+        const unsigned grid = ntiles < (unsigned long long)resident ? (unsigned)ntiles : (unsigned)resident;
+        conv_x2_kernel<TIN, NHMAX, NHMIN, R, 0><<<grid, 256, 0, st>>>(in, out, nx, nrows, nh, t, (unsigned)ntiles);
+      }
+      return;
+    }
+  }
   dim3 grid((unsigned)(((nrows + 31) / 32) * ((nx + NW * R - 1) / (NW * R))));
-  const int words = sizeof(TIN) < 4 && ((size_t)nx * sizeof(TIN)) % 4 == 0 && ((uintptr_t)in & 3) == 0;
-  conv_x_kernel<TIN, NHMAX, NHMIN, R, NW><<<grid, 32 * NW, 0, st>>>(in, out, nx, nrows, nh, t, words);
+  conv_x_kernel<TIN, NHMAX, NHMIN, R, NW><<<grid, 32 * NW, 0, st>>>(in, out, nx, nrows, nh, t, words && sizeof(TIN) < 4);
 }
 
 // CALL(NHMAX, NHMIN): the instantiation for tap counts NHMIN..NHMAX
@@ -586,6 +758,8 @@ struct spv_filter {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_pass[2] = {nullptr, nullptr};  // after the first / second kernel of the last convolution
+  int passes = 0;                               // kernels of the last convolution (3, or 2 with the fused x + y pass)
   void *d_src = nullptr;   // the loaded volume in its own element type (host sources and converted ones)
   size_t src_cap = 0;
   float *buf[2] = {nullptr, nullptr};
@@ -638,6 +812,7 @@ SPV_API int spv_filter_create(int device, spv_filter **out) {
   f->device = device;
   if ((e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreate(&f->ev0)) != cudaSuccess || (e = cudaEventCreate(&f->ev1)) != cudaSuccess ||
+      (e = cudaEventCreate(&f->ev_pass[0])) != cudaSuccess || (e = cudaEventCreate(&f->ev_pass[1])) != cudaSuccess ||
       (e = cudaMalloc(&f->d_taps, 3 * FILT_LONG_TAPS * sizeof(float))) != cudaSuccess) {
     int rc = fcufail(nullptr, e, "spv_filter_create");
     spv_filter_destroy(f);
@@ -660,6 +835,8 @@ SPV_API int spv_filter_destroy(spv_filter *f) {
     if (f->ev_ring[i]) cudaEventDestroy(f->ev_ring[i]);
   if (f->ev0) cudaEventDestroy(f->ev0);
   if (f->ev1) cudaEventDestroy(f->ev1);
+  for (cudaEvent_t e : f->ev_pass)
+    if (e) cudaEventDestroy(e);
   if (f->stream) cudaStreamDestroy(f->stream);
   cudaGetLastError();
   delete f;
@@ -770,6 +947,8 @@ SPV_API int spv_filter_convolve_sep3(spv_filter *f, const float *hx, int nhx, co
   if (fuse && filter_xy_fusable(nhx, nhy)) {  // x + y in one kernel: cur -> buf[i], then z: buf[i] -> buf[1-i]
     const int j = i;  // buf[i] is not the source
     FCU(launch_filter_xy(f->cur, f->cur_dtype, f->buf[j], f->nx, f->ny, f->nz, hx, nhx, hy, nhy, f->stream));
+    FCU(cudaEventRecord(f->ev_pass[0], f->stream));
+    f->passes = 2;
     FCU(launch_filter_axis(f->buf[j], f->buf[1 - j], f->nx, f->ny, f->nz, 2, hz, nhz, f->d_taps + 2 * FILT_LONG_TAPS, f->stream));
     f->launches += 2;
     FCU(cudaEventRecord(f->ev1, f->stream));
@@ -780,7 +959,10 @@ SPV_API int spv_filter_convolve_sep3(spv_filter *f, const float *hx, int nhx, co
     return 0;
   }
   FCU(launch_filter_x(f->cur, f->cur_dtype, f->buf[i], f->nx, f->ny, f->nz, hx, nhx, f->d_taps, f->stream));
+  FCU(cudaEventRecord(f->ev_pass[0], f->stream));
   FCU(launch_filter_axis(f->buf[i], f->buf[1 - i], f->nx, f->ny, f->nz, 1, hy, nhy, f->d_taps + FILT_LONG_TAPS, f->stream));
+  FCU(cudaEventRecord(f->ev_pass[1], f->stream));
+  f->passes = 3;
   FCU(launch_filter_axis(f->buf[1 - i], f->buf[i], f->nx, f->ny, f->nz, 2, hz, nhz, f->d_taps + 2 * FILT_LONG_TAPS, f->stream));
   f->launches += 3;
   FCU(cudaEventRecord(f->ev1, f->stream));
@@ -824,13 +1006,33 @@ SPV_API int spv_filter_last_ms(spv_filter *f, float *ms) {
   return 0;
 }
 
+SPV_API int spv_filter_last_pass_ms(spv_filter *f, float ms[3], int *passes) {
+  FBIND();
+  if (!ms) return ffail(f, SPV_EINVAL, "spv_filter_last_pass_ms: null pointer");
+  if (!f->timed) return ffail(f, SPV_ENODATA, "spv_filter_last_pass_ms: nothing convolved yet");
+  FCU(cudaEventSynchronize(f->ev1));
+  ms[0] = ms[1] = ms[2] = 0.f;
+  FCU(cudaEventElapsedTime(&ms[0], f->ev0, f->ev_pass[0]));
+  if (f->passes == 3) {
+    FCU(cudaEventElapsedTime(&ms[1], f->ev_pass[0], f->ev_pass[1]));
+    FCU(cudaEventElapsedTime(&ms[2], f->ev_pass[1], f->ev1));
+  } else {
+    FCU(cudaEventElapsedTime(&ms[1], f->ev_pass[0], f->ev1));
+  }
+  if (passes) *passes = f->passes;
+  return 0;
+}
+
 /* knob 0: x and y pass in one kernel wherever the tap counts allow it (default 0: three passes);
- * knob 1: the y / z pass variant: 1 = automatic (one column per thread, 16 or 32 outputs), 16 / 32 = outputs per thread,
- * 2 / 4 = columns per thread where the row length allows it */
+ * knob 1: the y / z pass variant: 1 = automatic (4 / 2 / 1 columns per thread as the row length allows), 16 / 32 = one column
+ * with that many outputs per thread, 1602 / 1604 = two / four columns; knob 2: the x pass on row pairs, pipelined (2,
+ * default) or not (1), or on single rows (0) */
 SPV_API int spv_filter_set_tuning(spv_filter *f, int knob, int value) {
   FBIND();
   if (knob == 0) f->fuse_xy = value != 0;
-  else if (knob == 1) filter_axis_wide = (value == 4 || value == 2 || value == 32 || value == 16) ? value : 1;  // process-wide
+  else if (knob == 1)  // process-wide: 1 = automatic, 16 / 32 = one column, R outputs per thread, 1602 / 1604 = 2 / 4 columns
+    filter_axis_wide = (value == 32 || value == 16 || value == 1602 || value == 1604) ? value : 1;
+  else if (knob == 2) filter_x_pairs = value == 1 ? 1 : (value ? 2 : 0);  // process-wide
   else return ffail(f, SPV_EINVAL, "spv_filter_set_tuning: unknown knob");
   return 0;
 }

@@ -91,7 +91,9 @@ class VolumeFilter(object):
 
     def set_tuning(self, knob, value):
         """knob 0: x and y pass as one kernel where the tap counts allow it (default 0: three passes);
-        knob 1: columns per thread of the y / z passes (1, 2 or 4; default 1)"""
+        knob 1: variant of the y / z passes (1 = automatic, 16 / 32 = one column per thread with that many outputs,
+        1602 / 1604 = two / four columns per thread); knob 2: x pass on row pairs, pipelined (2, default) or not (1),
+        or on single rows (0).  Results are bit-identical under every knob (include/spimcuda.h)"""
         self._check(self._lib.spv_filter_set_tuning(self._f, int(knob), int(value)))
 
     def launch_count(self):
@@ -103,6 +105,12 @@ class VolumeFilter(object):
         ms = C.c_float()
         self._check(self._lib.spv_filter_last_ms(self._f, C.byref(ms)))
         return ms.value
+
+    def last_pass_ms(self):
+        """device time of each kernel of the last convolution: [x, y, z] (or [fused x + y, z] with tuning knob 0)"""
+        ms, n = (C.c_float * 3)(), C.c_int()
+        self._check(self._lib.spv_filter_last_pass_ms(self._f, ms, C.byref(n)))
+        return [ms[k] for k in range(n.value)]
 
 
 _shared = {}

@@ -110,6 +110,31 @@ def _gpu_sep3(data, hx, hy, hz, fuse=1):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("x_pairs,axis", [(0, 16), (1, 32), (2, 1602), (2, 1604), (0, 1604)])
+@pytest.mark.parametrize("dtype", [np.float32, np.uint16, np.uint8])
+def test_gpu_kernel_variants_equal_the_oracle_bitwise(forc, dtype, x_pairs, axis):
+    """every x / axis kernel variant (single rows or row pairs, one / two / four columns per thread, packed
+    fma.rn.f32x2) gives the oracle's bits: volumes with several 64-row tiles per CTA, cut tiles on every face, rows of
+    whole words (132, 8) and not (the kernels fall back: 131 as uint8 / uint16)"""
+    from spimagine_b200 import imageprocessor as ip
+    vf = ip._shared_filter(0)
+    try:
+        for shape, taps in (((9, 150, 132), (19, 7, 31)), ((70, 3, 8), (5, 19, 3)), ((6, 40, 131), (11, 19, 19)),
+                            ((2, 700, 260), (47, 3, 1))):
+            rng = np.random.default_rng(sum(shape) + sum(taps))
+            data = scenes.random_vol(shape, dtype, seed=sum(shape))
+            hs = [rng.random(n) - .2 for n in taps]
+            want = forc.convolve_sep3(data, *hs)
+            vf.set_tuning(1, axis)
+            vf.set_tuning(2, x_pairs)
+            got = ip.convolve_sep3(data, *hs)
+            assert np.array_equal(got, want), (shape, taps)
+    finally:
+        vf.set_tuning(1, 1)
+        vf.set_tuning(2, 2)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("fuse", [1, 0])
 @pytest.mark.parametrize("dtype", [np.float32, np.uint16, np.uint8])
 @pytest.mark.parametrize("shape,taps", [((40, 50, 300), (19, 19, 19)),   # several x tiles, interior + face chunks
