@@ -72,6 +72,9 @@ def parse():
     ap.add_argument("--no-axis", action="store_true",
                     help="sweep workload: mip_fast_kernel on the z-paired array for every frame (tuning knob 16 = 0, as "
                          "round 1) instead of the view-aligned layered copies of spv_mip_axis.cu; implies --batch 1")
+    ap.add_argument("--no-occ-table", action="store_true",
+                    help="iso workload: hash every ambient-occlusion tap in every frame (tuning knob 17 = 0) instead of "
+                         "reading its pixel offsets from the per-image table")
     ap.add_argument("--no-iso-overlap", action="store_true",
                     help="iso workload, one GPU: every frame's screen-space passes on the render stream (as round 1)")
     ap.add_argument("--dtype", default="u16", choices=["u16", "f32"],
@@ -521,6 +524,8 @@ def run_iso(args, rank, local_rank, world):
     del vol
     torch.cuda.empty_cache()
     rend.set_max_val(iso_max)
+    if args.no_occ_table:
+        _lib.check(rend._lib.spv_set_tuning(rend._ctx, 17, 0), rend._ctx)
     NF = 36
     cams = [scenes.gui_camera(2 * math.pi * f / NF, 4.0) for f in range(NF)]
     rend.set_projection(cams[0][1])

@@ -332,7 +332,10 @@ SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
  * along x, y or z and the lane-to-pixel map under which a texture request stays inside one layer, chosen from the camera
  * alone (the x / y copies -- for float32 volumes, whose array is 3-D, the z copy as well -- are built on the device when
  * first wanted, 4 bytes per voxel each, 8 for float32), 2 = the primary z copy only (float32: mip_fast_kernel),
- * 0 = mip_fast_kernel on the z copy (round 1's path), 10 + 3 * axis + map = forced (tests). */
+ * 0 = mip_fast_kernel on the z copy (round 1's path), 10 + 3 * axis + map = forced (tests),
+ * knob 17 = the ambient-occlusion pass reads the pixel offsets of its taps from a table built once per (image size,
+ * radius, tap count) -- 64 bytes per pixel and 32 taps -- and gathers depths from a shared-memory tile (1, default)
+ * instead of hashing every tap in every frame (0); same result bit for bit. */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 /* Which kernel family renders plain (alpha_pow == 0, num_parts == 1) max projections of uint16 volumes
  * (max_project_short, volume_kernel.cl:270-345):

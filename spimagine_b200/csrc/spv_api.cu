@@ -70,6 +70,9 @@ struct spv_ctx {
   unsigned char *d_rgba = nullptr, *h_rgba = nullptr;  // packed display image (device, pinned host), per image size
   float4 *d_taps = nullptr;             // occlusion tap table (launch_occ_taps), valid for taps_n taps
   int taps_n = 0;
+  void *d_occ_table = nullptr;          // pixel offsets of every tap of every pixel (launch_occ_table), for occ_key
+  int occ_key[4] = {0, 0, -1, 0};       // width, height, radius, n_points the table was built for
+  int occ_table_on = 1;                 // tuning knob 17
   Camera cam;
   // result buffers: one allocation  [out | alpha | depth | occ | normals(3) | raw | tmp | tmp_vec(3)]
   float *dbuf = nullptr;
@@ -255,6 +258,9 @@ static void free_buffers(spv_ctx *c) {
   c->d_tile_hit_s[0] = c->d_tile_hit_s[1] = nullptr;
   if (c->d_occ_queue) cudaFree(c->d_occ_queue);
   c->d_occ_queue = nullptr;
+  if (c->d_occ_table) cudaFree(c->d_occ_table);
+  c->d_occ_table = nullptr;
+  c->occ_key[2] = -1;
   if (c->d_rgba) cudaFree(c->d_rgba);
   if (c->h_rgba) cudaFreeHost(c->h_rgba);
   c->d_rgba = c->h_rgba = nullptr;
@@ -445,6 +451,7 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
   if (ctx->d_band_done) cudaFree(ctx->d_band_done);
   if (ctx->d_iso_err) cudaFree(ctx->d_iso_err);
   if (ctx->d_taps) cudaFree(ctx->d_taps);
+  if (ctx->d_occ_table) cudaFree(ctx->d_occ_table);
   if (ctx->d_lut) cudaFree(ctx->d_lut);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1004,6 +1011,7 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   else if (knob == 16) ctx->axis_mode = value;
   else if (knob == 11) ctx->smem_cfg = value < 0 || value >= mip_smem_configs() ? 0 : value;
   else if (knob == 6) occ_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : value);  // process-wide
+  else if (knob == 17) ctx->occ_table_on = value != 0;
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
   return 0;
 }
@@ -2023,6 +2031,47 @@ static int ensure_taps(spv_ctx *ctx, int n) {
   return 0;
 }
 
+// The table of tap offsets (launch_occ_table) for the current image size and these occlusion parameters: built when
+// they change (one launch of the per-tap hashing over the whole image), reused by every frame after that.
+// *table = nullptr where the table form does not apply (knob 17 off, radius > 44, table beyond 1 GiB, no memory).
+static int ensure_occ_table(spv_ctx *ctx, int radius, int n_points, const void **table) {
+  *table = nullptr;
+  if (!ctx->occ_table_on || !ctx->d_occ_queue) return 0;
+  const int key[4] = {ctx->width, ctx->height, radius, n_points};
+  if (ctx->d_occ_table && memcmp(key, ctx->occ_key, sizeof(key)) == 0) {
+    *table = ctx->d_occ_table;
+    return 0;
+  }
+  const size_t bytes = occ_table_bytes(ctx->width, ctx->height, radius, n_points);
+  if (!bytes) return 0;
+  CU(cudaStreamSynchronize(ctx->stream));  // frames in flight may still read the old table
+  if (ctx->post_stream) CU(cudaStreamSynchronize(ctx->post_stream));
+  if (ctx->d_occ_table) cudaFree(ctx->d_occ_table);
+  ctx->d_occ_table = nullptr;
+  ctx->occ_key[2] = -1;
+  if (cudaMalloc(&ctx->d_occ_table, bytes) != cudaSuccess) {  // not enough memory: the queue form needs none
+    cudaGetLastError();
+    ctx->d_occ_table = nullptr;
+    return 0;
+  }
+  unsigned *bad = nullptr, h_bad = 0;
+  CU(cudaMalloc(&bad, sizeof(unsigned)));
+  CU(cudaMemsetAsync(bad, 0, sizeof(unsigned), ctx->stream));
+  CU(launch_occ_table(ctx->d_occ_table, ctx->width, ctx->height, radius, n_points, ctx->d_taps, bad, ctx->stream));
+  ctx->launches += 1;
+  CU(cudaMemcpyAsync(&h_bad, bad, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // the passes of later frames read it from other streams as well
+  cudaFree(bad);
+  if (h_bad) {  // an offset beyond the halo: keep hashing per frame
+    cudaFree(ctx->d_occ_table);
+    ctx->d_occ_table = nullptr;
+    return 0;
+  }
+  memcpy(ctx->occ_key, key, sizeof(key));
+  *table = ctx->d_occ_table;
+  return 0;
+}
+
 static ConvWeights conv_weights(int Nh, float coef) {
   ConvWeights w;
   memset(&w, 0, sizeof w);
@@ -2065,6 +2114,8 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   a.stats = ctx->stats_on ? ctx->d_stats : nullptr;
   const bool linear = ctx->linear && (ctx->dtype == SPV_F32 || ctx->int_filter);
   int rc = post ? ensure_taps(ctx, p->occ_n_points) : 0;
+  const void *occ_table = nullptr;
+  if (!rc && post) rc = ensure_occ_table(ctx, p->occ_radius, p->occ_n_points, &occ_table);
   if (rc) return rc;
   rc = begin_render(ctx);
   if (rc) return rc;
@@ -2126,7 +2177,7 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
     // volumerender.py:470-497
     CU(launch_conv_xy(ctx->tmp_vec(), ctx->normals(), ctx->width, ctx->height, 3, conv_weights(7, -5.f), a.tile_hit, 0, pst));
     CU(launch_occlusion(ctx->tmp(), ctx->width, ctx->height, p->occ_radius, p->occ_n_points, ctx->depth(), a.tile_hit,
-                        ctx->d_taps, ctx->d_occ_queue, ctx->occ_frame++, ctx->sms, pst));
+                        ctx->d_taps, ctx->d_occ_queue, ctx->occ_frame++, ctx->sms, pst, 0, -1, occ_table));
     CU(launch_conv_xy(ctx->tmp(), ctx->occ(), ctx->width, ctx->height, 1, conv_weights(5, -10.f), a.tile_hit,
                       p->occ_radius, pst));
     CU(launch_shading(ctx->out(), ctx->width, ctx->height, ctx->cam, p->occ_strength, ctx->normals(), ctx->depth(),
@@ -2289,6 +2340,8 @@ SPV_API int spv_render_iso_composite(spv_ctx *ctx, const spv_iso_params *p) {
     if (rc) return rc;
   }
   const bool post = !(p->flags & SPV_ISO_RAW_ONLY);
+  // (no tap-offset table here: building it allocates and synchronises, which must not happen while a peer's frame --
+  // whose kernels spin on this rank's flags -- is in flight; sort-last frames hash their taps)
   if (post) {
     rc = ensure_taps(ctx, p->occ_n_points);
     if (rc) return rc;

@@ -974,7 +974,7 @@ constexpr int OCC_BW = 32, OCC_BH = 2, OCC_GROUP = 4;  // the list kernel classi
 __global__ void __launch_bounds__(256) occ_list_kernel(float *__restrict__ d_output, int Nx, int Ny, int radius,
                                                        const unsigned char *__restrict__ tile_hit, int tiles_x, int obx,
                                                        int oby, unsigned *__restrict__ cnt, unsigned *__restrict__ cnt_next,
-                                                       unsigned *__restrict__ list, int y_first, int y_end) {
+                                                       unsigned *__restrict__ list, int y_first, int y_end, int by_group) {
   // one warp per group of OCC_GROUP vertically adjacent blocks (32 x 8 pixels): their reach rectangles differ by a
   // few rows only, so one scan of the tile flags over the union decides all of them (conservatively: a block that
   // is computed although nothing is in reach still gets the right answer, 0)
@@ -987,7 +987,9 @@ __global__ void __launch_bounds__(256) occ_list_kernel(float *__restrict__ d_out
   if (py + nb * OCC_BH <= y_first || py >= y_end) return;  // not this rank's rows (sort-last frames): left untouched
   const int mine = tiles_in_reach(tile_hit, tiles_x, Nx, Ny, px, px + OCC_BW - 1, py, py + nb * OCC_BH - 1, radius, lane, 32);
   if (__any_sync(0xffffffffu, mine != 0)) {
-    if (lane < nb) list[atomicAdd(cnt, 1u)] = (unsigned)((by0 + lane) * obx + bx);
+    if (by_group) {  // occ_tile_kernel takes whole groups (32 x 8 pixels)
+      if (lane == 0) list[atomicAdd(cnt, 1u)] = (unsigned)g;
+    } else if (lane < nb) list[atomicAdd(cnt, 1u)] = (unsigned)((by0 + lane) * obx + bx);
   } else {
     const int x = px + lane;
     if (x < Nx)
@@ -1037,6 +1039,111 @@ __global__ void __launch_bounds__(128) occ_queue_kernel(float *__restrict__ d_ou
   }
 }
 
+// Table form.  Where a tap of pixel (x, y) lands -- clamp((int)(x + r cos(phi))), clamp((int)(y + r sin(phi))) with r and
+// phi hashed from (x, y, tap) -- does not depend on the image: the offsets (x2 - x, y2 - y) are evaluated once per
+// (image size, radius, tap count) by the very expressions of occlusion_pixel and kept as signed bytes.  A frame then
+// costs one 16-byte table load per lane (its 8 taps) instead of 2 x 10 LCG rounds, cos and sin per tap (205
+// instructions), and the depth gathers come out of a shared-memory tile of the 32 x 8 pixel group and its halo
+// (random banks: ~3 cycles per request instead of one tag lookup per lane).  Same taps, same comparisons, sums of
+// 0 / 1: the result is bit-identical to the queue form.
+//   layout   table[((chunk * Npix + pixel) * 4 + g) * 8 + j] = offsets of tap 32 chunk + g + 4 j (lane g of a pixel's 4 lanes)
+__global__ void __launch_bounds__(256) occ_table_kernel(char2 *__restrict__ table, int Nx, int Ny, int radius, int number_points,
+                                                        const float4 *__restrict__ taps, int halo, unsigned *__restrict__ bad) {
+  const size_t npix = (size_t)Nx * Ny;
+  const int chunks = (number_points + 31) / 32;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npix * 32 * chunks) return;
+  const int j = (int)(idx & 7), g = (int)((idx >> 3) & 3);
+  const size_t pc = idx >> 5;
+  const int chunk = (int)(pc / npix);
+  const size_t pix = pc % npix;
+  const int x = (int)(pix % Nx), y = (int)(pix / Nx);
+  const unsigned i = 32u * chunk + g + 4u * j;
+  char2 o = make_char2(0, 0);
+  if (i < (unsigned)number_points) {  // occlusion.cl:60-65
+    const float MPI_2 = 6.2831853071795f;
+    const float4 tp = __ldg(taps + i);
+    const float r = (float)(unsigned)radius * random_cl((uint32_t)((float)x + tp.x), (uint32_t)((float)y + tp.y));
+    const float phi = MPI_2 * random_cl((uint32_t)((float)x + tp.z), (uint32_t)((float)y + tp.w));
+    const int dx = clampi((int)((float)x + r * cosf(phi)), 0, Nx - 1) - x;
+    const int dy = clampi((int)((float)y + r * sinf(phi)), 0, Ny - 1) - y;
+    if (dx < -halo || dx > halo || dy < -halo || dy > halo) atomicAdd(bad, 1u);  // (cannot happen: |r| <= radius)
+    o = make_char2((signed char)dx, (signed char)dy);
+  }
+  table[idx] = o;
+}
+
+__global__ void __launch_bounds__(256) occ_tile_kernel(float *__restrict__ d_output, int Nx, int Ny, int number_points,
+                                                       const float *__restrict__ input_depth, const char2 *__restrict__ table,
+                                                       int halo, int obx, const unsigned *__restrict__ cnt,
+                                                       const unsigned *__restrict__ list) {
+  extern __shared__ float s_depth[];  // [8 + 2 halo][32 + 2 halo]
+  const int tw = OCC_BW + 2 * halo, th = OCC_GROUP * OCC_BH + 2 * halo;
+  const unsigned total = cnt[0];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane & 3;
+  const size_t npix = (size_t)Nx * Ny;
+  const int chunks = (number_points + 31) / 32;
+  for (unsigned item = blockIdx.x; item < total; item += gridDim.x) {
+    const int grp = (int)list[item];
+    const int px = (grp % obx) * OCC_BW, py = (grp / obx) * OCC_GROUP * OCC_BH;
+    const int ox = px - halo, oy = py - halo;  // image position of tile element (0, 0)
+    __syncthreads();                           // the previous item's gathers are done
+    for (int e = threadIdx.x; e < tw * th; e += 256) {
+      const int tx = e % tw, ty = e / tw, ix = ox + tx, iy = oy + ty;
+      if (ix >= 0 && ix < Nx && iy >= 0 && iy < Ny) s_depth[e] = input_depth[ix + (size_t)iy * Nx];  // taps are clamped into the image
+    }
+    __syncthreads();
+    const int y = py + warp;
+#pragma unroll
+    for (int step = 0; step < OCC_BW / 8; ++step) {
+      const int x = px + step * 8 + (lane >> 2);
+      const bool inb = x < Nx && y < Ny;
+      float occ = 0.f;
+      if (inb) {
+        const float *centre = s_depth + (warp + halo) * tw + (x - ox);
+        const float depth0 = *centre;
+        const size_t pix = x + (size_t)y * Nx;
+        for (int chunk = 0; chunk < chunks; ++chunk) {
+          const uint4 q = __ldg(reinterpret_cast<const uint4 *>(table + ((chunk * npix + pix) * 4 + g) * 8));
+          const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const unsigned i = 32u * chunk + g + 4u * j;
+            const unsigned pair = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+            const int dx = (int)(signed char)(pair & 0xffu), dy = (int)(signed char)(pair >> 8);
+            if (i < (unsigned)number_points) occ += (centre[dy * tw + dx] < depth0 ? 1.f : 0.f);
+          }
+        }
+      }
+      occ += __shfl_xor_sync(0xffffffffu, occ, 1);
+      occ += __shfl_xor_sync(0xffffffffu, occ, 2);
+      if (inb && g == 0) d_output[x + (size_t)Nx * y] = occ / (float)(unsigned)number_points;
+    }
+  }
+}
+
+// bytes of the tap-offset table of a width x height image (0: the table form does not apply -- radius beyond a signed
+// byte or a shared-memory tile, or a table beyond 1 GiB)
+size_t occ_table_bytes(int width, int height, int radius, int n_points) {
+  if (radius < 0 || radius > 44 || n_points < 1) return 0;  // the group's tile and halo within 48 KB of shared memory
+  const size_t bytes = (size_t)width * height * 64 * (size_t)((n_points + 31) / 32);
+  return bytes <= ((size_t)1 << 30) ? bytes : 0;
+}
+static size_t occ_tile_smem(int radius) {
+  const int halo = radius + 1;
+  return (size_t)(OCC_BW + 2 * halo) * (OCC_GROUP * OCC_BH + 2 * halo) * sizeof(float);
+}
+// fills `table` (occ_table_bytes) for this image size, radius and tap count; *bad (device, zeroed by the caller) counts
+// offsets beyond the halo (none: the caller falls back to the queue form if it is not 0)
+cudaError_t launch_occ_table(void *table, int width, int height, int radius, int n_points, const float4 *taps, unsigned *bad,
+                             cudaStream_t st) {
+  const size_t n = (size_t)width * height * 32 * (size_t)((n_points + 31) / 32);
+  if ((n + 255) / 256 > 0x7fffffffull) return cudaErrorInvalidValue;
+  occ_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<char2 *>(table), width, height, radius, n_points,
+                                                             taps, radius + 1, bad);
+  return cudaGetLastError();
+}
+
 size_t occ_queue_bytes(int width, int height) {
   const size_t n_ob = (size_t)((width + OCC_BW - 1) / OCC_BW) * ((height + OCC_BH - 1) / OCC_BH);
   return (4 + n_ob) * sizeof(unsigned);  // [2 parities][count, head] + the list
@@ -1045,7 +1152,7 @@ size_t occ_queue_bytes(int width, int height) {
 int occ_ctas_per_sm = 10;  // resident CTAs (4 warps each) per SM of the occlusion queue kernel (tuning knob 6)
 cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int n_points, const float *depth,
                              const unsigned char *tile_hit, const float4 *taps, unsigned *queue, unsigned frame, int sms,
-                             cudaStream_t st, int y_first, int y_end) {
+                             cudaStream_t st, int y_first, int y_end, const void *table) {
   if (y_end < 0 || y_end > height) y_end = height;
   if (y_first < 0) y_first = 0;
   if (tile_hit && queue) {
@@ -1053,7 +1160,14 @@ cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int 
     const int groups = obx * ((oby + OCC_GROUP - 1) / OCC_GROUP);
     unsigned *cnt = queue + 2 * (frame & 1u), *cnt_next = queue + 2 * ((frame + 1u) & 1u), *list = queue + 4;
     occ_list_kernel<<<(groups + 7) / 8, 256, 0, st>>>(occ, width, height, radius, tile_hit, (width + 7) / 8, obx, oby, cnt,
-                                                     cnt_next, list, y_first, y_end);
+                                                     cnt_next, list, y_first, y_end, table != nullptr);
+    if (table) {  // groups of 32 x 8 pixels in reach, one CTA each (a fixed grid walks the list)
+      const int per_sm = 8, nsm = sms > 0 ? sms : 148;
+      const unsigned grid = (unsigned)(groups < nsm * per_sm ? groups : nsm * per_sm);
+      occ_tile_kernel<<<grid, 256, occ_tile_smem(radius), st>>>(occ, width, height, n_points, depth,
+                                                                reinterpret_cast<const char2 *>(table), radius + 1, obx, cnt, list);
+      return cudaGetLastError();
+    }
     occ_queue_kernel<<<(sms > 0 ? sms : 148) * occ_ctas_per_sm, 128, 0, st>>>(occ, width, height, radius, n_points, depth, taps, obx, cnt,
                                                                  list);
     return cudaGetLastError();
@@ -1139,6 +1253,8 @@ cudaError_t preload_iso_kernels() {
   SPV_PRELOAD(occ_taps_kernel);
   SPV_PRELOAD(occ_list_kernel);
   SPV_PRELOAD(occ_queue_kernel);
+  SPV_PRELOAD(occ_table_kernel);
+  SPV_PRELOAD(occ_tile_kernel);
   SPV_PRELOAD(occlusion_kernel);
   SPV_PRELOAD(shading_kernel);
   return cudaSuccess;

@@ -193,9 +193,14 @@ cudaError_t launch_occ_taps(float4 *taps, int n, cudaStream_t st);
 // out dynamically; `frame` must change parity from call to call on the same queue.  Without: every block, in place.
 size_t occ_queue_bytes(int width, int height);
 extern int occ_ctas_per_sm;
+// `table` (may be null; launch_occ_table for this image size, radius and tap count): the taps' pixel offsets are read
+// from it instead of being hashed per frame, depth gathers go through a shared-memory tile (same result, bit for bit)
 cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int n_points, const float *depth,
                              const unsigned char *tile_hit, const float4 *taps, unsigned *queue, unsigned frame, int sms,
-                             cudaStream_t st, int y_first = 0, int y_end = -1);
+                             cudaStream_t st, int y_first = 0, int y_end = -1, const void *table = nullptr);
+size_t occ_table_bytes(int width, int height, int radius, int n_points);  // 0: no table for these parameters
+cudaError_t launch_occ_table(void *table, int width, int height, int radius, int n_points, const float4 *taps, unsigned *bad,
+                             cudaStream_t st);
 cudaError_t launch_shading(float *out, int width, int height, const Camera &cam, float occ_strength,
                            const float *normals, const float *depth, const float *occ, cudaStream_t st, int y_first = 0,
                            int y_end = -1);

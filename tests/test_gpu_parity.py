@@ -436,6 +436,37 @@ def test_iso_tuning_knobs_do_not_change_the_image():
     g.close()
 
 
+def test_occlusion_tap_table_does_not_change_the_image():
+    """The ambient-occlusion pass with its taps' pixel offsets read from the per-image table and depths gathered from a
+    shared-memory tile (tuning knob 17, default) against the form that hashes every tap in every frame: all planes bit
+    for bit, across changes of the radius, the tap count (more than one 32-tap chunk, a radius beyond the table's
+    range) and the image size (the table is rebuilt), on images whose extents are not multiples of the 32 x 8 groups."""
+    data = scenes.vol_g(0, np.uint16, seed=3, shape=(90, 120, 100))
+    M, P = scenes.gui_camera(0.9, 3.0)
+    n_hit = 0
+    g = _renderer((203, 149))
+    g.set_data(data)
+    g.set_modelView(M)
+    g.set_projection(P)
+    for size in ((203, 149), (96, 64)):
+        g.resize(size)
+        for radius, n_points in ((21, 31), (21, 30), (7, 5), (44, 70), (60, 12), (1, 1)):
+            g.set_occ_radius(radius)
+            g.set_occ_n_points(n_points)
+            res = []
+            for table in (1, 0, 1):
+                g._check(g._lib.spv_set_tuning(g._ctx, 17, table))
+                g.render(maxVal=26000., method="iso_surface")
+                res.append([a.copy() for a in (g.output, g.output_alpha, g.output_depth, g.output_normals, g.output_occlusion)])
+            for other in res[1:]:
+                for a, b in zip(res[0], other):
+                    assert np.array_equal(a, b), (size, radius, n_points)
+            n_hit += int((res[0][4] > 0).sum())
+    assert n_hit > 5000
+    g._check(g._lib.spv_set_tuning(g._ctx, 17, 1))
+    g.close()
+
+
 def test_iso_post_passes_on_the_tmu_path(oracle_mod):
     """The texture-unit path skips the occlusion hashing where no surface pixel is within reach and shades only
     surface pixels; both shortcuts must be invisible: recompute occlusion -> blur -> shading with the oracle from
