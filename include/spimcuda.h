@@ -335,7 +335,10 @@ SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
  * 0 = mip_fast_kernel on the z copy (round 1's path), 10 + 3 * axis + map = forced (tests),
  * knob 17 = the ambient-occlusion pass reads the pixel offsets of its taps from a table built once per (image size,
  * radius, tap count) -- 64 bytes per pixel and 32 taps -- and gathers depths from a shared-memory tile (1, default)
- * instead of hashing every tap in every frame (0); same result bit for bit. */
+ * instead of hashing every tap in every frame (0); same result bit for bit,
+ * knob 18 = spv_read_pinned_async of a clipped rectangle (output, alpha) first moves it into a device staging buffer
+ * (one small kernel), after which the slot's planes are free for the next render while the rectangle crosses the host
+ * link (1, default), or copies straight out of the slot, which then stays busy for the length of the copy (0). */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 /* Which kernel family renders plain (alpha_pow == 0, num_parts == 1) max projections of uint16 volumes
  * (max_project_short, volume_kernel.cl:270-345):

@@ -73,6 +73,7 @@ struct spv_ctx {
   void *d_occ_table = nullptr;          // pixel offsets of every tap of every pixel (launch_occ_table), for occ_key
   int occ_key[4] = {0, 0, -1, 0};       // width, height, radius, n_points the table was built for
   int occ_table_on = 1;                 // tuning knob 17
+  int stage_reads = 1;                  // tuning knob 18: spv_read_pinned_async frees the slot through a device staging copy
   Camera cam;
   // result buffers: one allocation  [out | alpha | depth | occ | normals(3) | raw | tmp | tmp_vec(3)]
   float *dbuf = nullptr;
@@ -87,6 +88,11 @@ struct spv_ctx {
   int copy_streams = 2;  // tuning knob 7 (measured: 267 us per synchronous C2 frame with 2, 280 with 1)
   cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   bool copy_pending[2] = {false, false};
+  // spv_read_pinned_async of a clipped rectangle first moves it into a device staging buffer (a few us), so that the
+  // slot's planes are free for the next render long before the rectangle has crossed the host link (~65 us)
+  float *dstage_s[2] = {nullptr, nullptr};  // [out | alpha] per slot, allocated when first used
+  cudaEvent_t ev_freed[2] = {nullptr, nullptr};
+  bool freed_by_stage[2] = {false, false};  // the slot's last asynchronous read went through dstage: renders wait for ev_freed
   // sort-last composite over peer memory (spv_comp_*): I own image band comp_rank
   int comp_rank = -1, comp_world = 0, comp_band_rows = 0;
   float *comp_part = nullptr;      // [2 parities][world][band_rows * width] floats (max-projection partials), then
@@ -104,7 +110,9 @@ struct spv_ctx {
   int last_method = 0;    // 0 = mip, 1 = iso
   // per output slot: camera, box and alpha miss value of the finished frame it holds (valid), for the clipped read-back
   // of out + alpha (spv_read_pinned, spv_read_pinned_async): pixels outside the projected box are misses
-  struct SlotClip { bool valid = false; Camera cam; float box[6]; float miss_alpha = 0.f; };
+  // full: every pixel of the slot's device planes outside the rectangle holds the miss values as well (iso frames with
+  // their screen-space passes), so a copy may cover more than the rectangle
+  struct SlotClip { bool valid = false; Camera cam; float box[6]; float miss_alpha = 0.f; bool full = false; };
   SlotClip clip_s[2];
   unsigned long long *d_stats = nullptr;
   unsigned long long h_stats[40] = {0};  // hit rays, samples fetched, longest warp / sum over warps (cycles; iso search)
@@ -249,6 +257,9 @@ static void free_buffers(spv_ctx *c) {
     c->dbuf_s[s] = nullptr;
     c->hpin_s[s] = nullptr;
     c->copy_pending[s] = false;
+    if (c->dstage_s[s]) cudaFree(c->dstage_s[s]);
+    c->dstage_s[s] = nullptr;
+    c->freed_by_stage[s] = false;
   }
   if (c->post_stream) cudaStreamSynchronize(c->post_stream);
   c->post_pending[0] = c->post_pending[1] = false;
@@ -347,8 +358,11 @@ static void staging_clean_outside_rect(spv_ctx *ctx, int s, int xa, int xb, int 
   ctx->dirty_x0[s] = keep ? xa : 0;
   ctx->dirty_x1[s] = keep ? xb : 0;
 }
-static void slot_clip_set(spv_ctx *ctx, int s, const Camera &cam, const float *box, float miss_alpha) {
+// the event after which the device planes of slot s may be rendered into again (its last asynchronous read-back)
+static cudaEvent_t slot_free_event(spv_ctx *ctx, int s) { return ctx->freed_by_stage[s] ? ctx->ev_freed[s] : ctx->ev_copied[s]; }
+static void slot_clip_set(spv_ctx *ctx, int s, const Camera &cam, const float *box, float miss_alpha, bool full = false) {
   ctx->clip_s[s].valid = true;
+  ctx->clip_s[s].full = full;
   ctx->clip_s[s].cam = cam;
   memcpy(ctx->clip_s[s].box, box, sizeof ctx->clip_s[s].box);
   ctx->clip_s[s].miss_alpha = miss_alpha;
@@ -411,6 +425,7 @@ SPV_API int spv_create(int device, int width, int height, spv_ctx **out) {
   for (int s = 0; s < 2; ++s) {
     CC(cudaEventCreateWithFlags(&ctx->ev_rendered[s], cudaEventDisableTiming));
     CC(cudaEventCreateWithFlags(&ctx->ev_copied[s], cudaEventDisableTiming));
+    CC(cudaEventCreateWithFlags(&ctx->ev_freed[s], cudaEventDisableTiming));
     CC(cudaEventCreateWithFlags(&ctx->ev_h2d_done[s], cudaEventDisableTiming));
     CC(cudaEventCreateWithFlags(&ctx->ev_consumed[s], cudaEventDisableTiming));
     CC(cudaEventCreateWithFlags(&ctx->ev_searched[s], cudaEventDisableTiming));
@@ -459,6 +474,7 @@ SPV_API int spv_destroy(spv_ctx *ctx) {
   for (int s = 0; s < 2; ++s) {
     if (ctx->ev_rendered[s]) cudaEventDestroy(ctx->ev_rendered[s]);
     if (ctx->ev_copied[s]) cudaEventDestroy(ctx->ev_copied[s]);
+    if (ctx->ev_freed[s]) cudaEventDestroy(ctx->ev_freed[s]);
     if (ctx->ev_h2d_done[s]) cudaEventDestroy(ctx->ev_h2d_done[s]);
     if (ctx->ev_consumed[s]) cudaEventDestroy(ctx->ev_consumed[s]);
     if (ctx->ev_searched[s]) cudaEventDestroy(ctx->ev_searched[s]);
@@ -1012,6 +1028,7 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   else if (knob == 11) ctx->smem_cfg = value < 0 || value >= mip_smem_configs() ? 0 : value;
   else if (knob == 6) occ_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : value);  // process-wide
   else if (knob == 17) ctx->occ_table_on = value != 0;
+  else if (knob == 18) ctx->stage_reads = value != 0;
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
   return 0;
 }
@@ -1406,7 +1423,7 @@ static int render_mip_impl(spv_ctx *ctx, const spv_mip_params *p, int bands, boo
       CU(cudaStreamWaitEvent(kst, ctx->ev_uploaded, 0));
       ctx->side_seq = ctx->upload_seq;
     }
-    if (ctx->copy_pending[s]) CU(cudaStreamWaitEvent(kst, ctx->ev_copied[s], 0));  // an asynchronous read of this slot
+    if (ctx->copy_pending[s]) CU(cudaStreamWaitEvent(kst, slot_free_event(ctx, s), 0));  // an asynchronous read of this slot
   }
   if (to_host && ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // staging about to be rewritten
   const int H = ctx->height;
@@ -2131,7 +2148,7 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
   if (to_host && ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // staging about to be rewritten
   // a device-only render into a slot whose planes an asynchronous read-back may still be copying: the search waits for it
   // on the device (render_sequence issues frames three ahead of the one it hands out)
-  if (!to_host && ctx->copy_pending[s]) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[s], 0));
+  if (!to_host && ctx->copy_pending[s]) CU(cudaStreamWaitEvent(ctx->stream, slot_free_event(ctx, s), 0));
   // read-back: only the rectangle the projected box can touch (outside it there is no surface: out 0, alpha 0, which the
   // pinned planes hold already)
   int cxa = 0, cxb = ctx->width, cya = 0, cyb = ctx->height;
@@ -2189,7 +2206,7 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
     }
   }
   ctx->last_method = 1;
-  slot_clip_set(ctx, s, ctx->cam, p->box, 0.f);  // no surface: out 0 (shading_kernel), alpha 0 (every element type)
+  slot_clip_set(ctx, s, ctx->cam, p->box, 0.f, post);  // no surface: out 0 (shading_kernel), alpha 0 (every element type)
   rc = end_render(ctx);
   if (rc) return rc;
   if (to_host) {
@@ -2499,13 +2516,41 @@ SPV_API int spv_read_many(spv_ctx *ctx, float *out, float *alpha, float *depth, 
 // quiescent).  output + alpha of a finished frame (what a display needs): pixels the projected box cannot touch are misses
 // -- out 0; alpha 0 for integer max projections and for iso surfaces (no crossing), -1 for float32 max projections -- and
 // are not copied; the pinned planes hold those values there already (tuning knob 9, as spv_render_mip_to_host).
-static int copy_slot_planes(spv_ctx *ctx, int s, int planes, cudaStream_t st) {
+static int copy_slot_planes(spv_ctx *ctx, int s, int planes, cudaStream_t st, bool stage = false) {
   const spv_ctx::SlotClip &c = ctx->clip_s[s];
+  ctx->freed_by_stage[s] = false;
   if (c.valid && planes <= 2 && ctx->clip_copies) {
     const int W = ctx->width, H = ctx->height;
     int xa, xb, ya, yb;
     miss_free_rect(c.cam, c.box, W, H, xa, xb, ya, yb);
+    if (stage && ctx->stage_reads && c.full && xa < xb && ya < yb && ctx->clean_alpha[s] == c.miss_alpha &&
+        ctx->dirty_x0[s] < ctx->dirty_x1[s] && ctx->dirty_lo[s] < ctx->dirty_hi[s]) {
+      // the pinned planes hold an earlier frame inside their dirty rectangle.  Where that sticks out of this frame's
+      // rectangle by little (a camera path: a few pixels per frame), copying the union of the two from the device --
+      // whose planes hold the miss values out there -- is cheaper than having the host clear thousands of row ends
+      const int ux0 = xa < ctx->dirty_x0[s] ? xa : ctx->dirty_x0[s], ux1 = xb > ctx->dirty_x1[s] ? xb : ctx->dirty_x1[s];
+      const int uy0 = ya < ctx->dirty_lo[s] ? ya : ctx->dirty_lo[s], uy1 = yb > ctx->dirty_hi[s] ? yb : ctx->dirty_hi[s];
+      if ((double)(ux1 - ux0) * (uy1 - uy0) <= 1.125 * (double)(xb - xa) * (yb - ya)) {
+        xa = ux0 < 0 ? 0 : ux0; xb = ux1 > W ? W : ux1;
+        ya = uy0 < 0 ? 0 : uy0; yb = uy1 > H ? H : uy1;
+      }
+    }
     staging_clean_outside_rect(ctx, s, xa, xb, ya, yb, c.miss_alpha);
+    if (stage && ctx->stage_reads && xa < xb && ya < yb) {
+      // rectangle -> device staging (same layout), slot free; then staging -> pinned host memory, one 2-D copy per plane
+      if (!ctx->dstage_s[s]) CU(cudaMalloc(&ctx->dstage_s[s], 2 * ctx->n() * sizeof(float)));
+      CU(launch_rect_copy(ctx->dbuf_s[s], ctx->dstage_s[s], W, H, xa, xb, ya, yb, planes, st));
+      ctx->launches += 1;
+      CU(cudaEventRecord(ctx->ev_freed[s], st));
+      ctx->freed_by_stage[s] = true;
+      const size_t off = (size_t)ya * W + xa;
+      for (int pl = 0; pl < planes; ++pl)
+        CU(cudaMemcpy2DAsync(ctx->hpin_s[s] + pl * ctx->n() + off, (size_t)W * sizeof(float), ctx->dstage_s[s] + pl * ctx->n() + off,
+                             (size_t)W * sizeof(float), (size_t)(xb - xa) * sizeof(float), (size_t)(yb - ya),
+                             cudaMemcpyDeviceToHost, st));
+      ctx->d2h_bytes += (size_t)planes * (size_t)(xb - xa) * (size_t)(yb - ya) * sizeof(float);
+      return 0;
+    }
     if (xa < xb && ya < yb) {
       cudaMemcpy3DParms cp;  // the rectangle of the leading plane(s) in one 3-D copy
       memset(&cp, 0, sizeof cp);
@@ -2547,7 +2592,7 @@ SPV_API int spv_select_slot(spv_ctx *ctx, int slot) {
     if (rc) return rc;
   }
   // renders into this slot must not overtake an asynchronous read of it that is still in flight
-  if (ctx->copy_pending[slot]) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[slot], 0));
+  if (ctx->copy_pending[slot]) CU(cudaStreamWaitEvent(ctx->stream, slot_free_event(ctx, slot), 0));
   ctx->slot = slot;
   ctx->dbuf = ctx->dbuf_s[slot];
   ctx->hpin = ctx->hpin_s[slot];
@@ -2565,7 +2610,7 @@ SPV_API int spv_read_pinned_async(spv_ctx *ctx, int planes) {
   if (ctx->post_pending[s]) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_posted[s], 0));
   if (ctx->copy_pending[s]) CU(cudaEventSynchronize(ctx->ev_copied[s]));  // the staging may be cleaned by the host
   {
-    int rcc = copy_slot_planes(ctx, s, planes, ctx->copy_stream);
+    int rcc = copy_slot_planes(ctx, s, planes, ctx->copy_stream, true);
     if (rcc) return rcc;
   }
   CU(cudaEventRecord(ctx->ev_copied[s], ctx->copy_stream));

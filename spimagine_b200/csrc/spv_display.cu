@@ -48,4 +48,21 @@ cudaError_t launch_display(const float *value, const float *alpha, const float *
   return cudaGetLastError();
 }
 
+// columns [xa, xb) of rows [ya, yb) of the first `planes` planes (W x H floats each), same position in dst: the
+// rectangle an asynchronous read-back moves into its device staging, which frees the slot's planes for the next render
+__global__ void __launch_bounds__(256) rect_copy_kernel(const float *__restrict__ src, float *__restrict__ dst, int W, size_t n, int xa,
+                                                        int xb, int ya) {
+  const int x = xa + blockIdx.x * 256 + threadIdx.x;
+  if (x >= xb) return;
+  const size_t p = (size_t)blockIdx.z * n + (size_t)(ya + blockIdx.y) * W + x;
+  dst[p] = src[p];
+}
+cudaError_t launch_rect_copy(const float *src, float *dst, int W, int H, int xa, int xb, int ya, int yb, int planes, cudaStream_t st) {
+  if (xa >= xb || ya >= yb || planes < 1) return cudaSuccess;
+  if (yb - ya > 65535) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)((xb - xa + 255) / 256), (unsigned)(yb - ya), (unsigned)planes);
+  rect_copy_kernel<<<grid, 256, 0, st>>>(src, dst, W, (size_t)W * H, xa, xb, ya);
+  return cudaGetLastError();
+}
+
 }  // namespace spv

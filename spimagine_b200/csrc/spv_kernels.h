@@ -214,6 +214,7 @@ cudaError_t launch_pair(const void *src, void *dst, int dtype, size_t slice, int
                         cudaStream_t st);
 
 // display hand-off (spv_display.cu): value plane + LUT -> packed RGBA8
+cudaError_t launch_rect_copy(const float *src, float *dst, int W, int H, int xa, int xb, int ya, int yb, int planes, cudaStream_t st);
 cudaError_t launch_display(const float *value, const float *alpha, const float *lut, int n_lut, int mode_black,
                            void *rgba, size_t n, cudaStream_t st);
 

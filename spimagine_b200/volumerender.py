@@ -601,11 +601,13 @@ class VolumeRenderer(object):
                 self._lib.spv_select_slot(self._ctx, 0)
 
     def _render_sequence_iso(self, modelViews, planes, clear):
-        """Iso-surface frames of a sequence: renders are issued three frames ahead of the frame that is handed out,
+        """Iso-surface frames of a sequence: renders are issued four frames ahead of the frame that is handed out,
         read-backs two ahead.  A device slot is reused as soon as the copy out of it has been enqueued (the next search
-        into it waits for that copy on the device); a slot's pinned staging is rewritten only after the frame it held
-        has been handed out and the consumer has come back.  The screen-space passes of frame i run beside the search
-        of frame i + 1 (tuning knob 14)."""
+        into it waits on the device until the frame's rectangle has left the slot -- for output + alpha that is a small
+        copy into a device staging buffer, tuning knob 18, not the trip over the host link); a slot's pinned staging is
+        rewritten only after the frame it held has been handed out and the consumer has come back.  The screen-space
+        passes of frame i run beside the search of frame i + 1 (tuning knob 14).  With renders only three ahead the
+        device ran dry for ~12 us per frame: frame i + 3 was enqueued after frame i's read-back had been waited for."""
         it = iter(modelViews)
         rendered, copied = [], []   # frame numbers: rendered but not yet read back / read-back enqueued, oldest first
         state = {"n": 0}
@@ -638,6 +640,8 @@ class VolumeRenderer(object):
                 if render_next():
                     copy_next()
             render_next()
+            if planes == 2:  # (whole frames, 7 planes, are bound by the host link: 519 us per frame three ahead, 623 four ahead)
+                render_next()
             while copied:
                 k = copied.pop(0)
                 self._adopt_slot(k & 1, planes, clear)

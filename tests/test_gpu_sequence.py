@@ -106,6 +106,38 @@ def test_iso_sequence_reads_back_only_rows_that_can_hold_a_surface():
             rend.close()
 
 
+def test_iso_sequence_on_a_camera_path_equals_unclipped_reads():
+    """A slowly turning, drifting camera: render_sequence(iso_planes=2) moves each frame's rectangle through the device
+    staging and, where the previous frame's rectangle sticks out by little, copies the union of the two instead of
+    clearing the pinned planes on the host.  Every frame must equal a blocking render whose planes are read back
+    whole (tuning knob 9 = 0), for both settings of the staging knob (18)."""
+    from spimagine_b200.utils.transform_matrices import mat4_rotation, mat4_translate
+    P = scenes.gui_camera(0., 4.)[1]
+    cams = [np.dot(mat4_translate(0.02 * i - 0.3, 0.25 * math.sin(0.2 * i), -4.2 + 0.01 * i), mat4_rotation(0.05 * i, 0.3, 1., 0.))
+            for i in range(24)]
+    rend = _renderer((208, 176), pinned_outputs=True)
+    try:
+        rend.set_data(scenes.vol_g(56, np.uint16, seed=2))
+        rend.set_projection(P)
+        rend.set_max_val(30000.)
+        rend._check(rend._lib.spv_set_tuning(rend._ctx, 9, 0))
+        want = []
+        for M in cams:
+            rend.render(modelView=M, method="iso_surface")
+            want.append((rend.output.copy(), rend.output_alpha.copy()))
+        rend._check(rend._lib.spv_set_tuning(rend._ctx, 9, 1))
+        assert sum(w[0].max() > 0 for w in want) == len(cams)
+        for stage in (1, 0, 1):
+            rend._check(rend._lib.spv_set_tuning(rend._ctx, 18, stage))
+            b0 = rend.d2h_bytes()
+            got = [(r.output.copy(), r.output_alpha.copy()) for r in rend.render_sequence(cams, method="iso_surface", iso_planes=2)]
+            assert rend.d2h_bytes() - b0 < 0.9 * len(cams) * 2 * 208 * 176 * 4
+            for i, ((o, a), (wo, wa)) in enumerate(zip(got, want)):
+                assert np.array_equal(o, wo) and np.array_equal(a, wa), (stage, i)
+    finally:
+        rend.close()
+
+
 def test_sequence_abandoned_midway_leaves_renderer_usable():
     data = scenes.vol_g(32, np.uint16, seed=1)
     cams = [scenes.gui_camera(0.1 * f, 3.5) for f in range(6)]
