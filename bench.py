@@ -559,6 +559,7 @@ def run_iso(args, rank, local_rank, world):
         device_step(i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = rend.launch_count()
     e0.record()
     for i in range(args.steps):
         device_step(i)
@@ -567,6 +568,7 @@ def run_iso(args, rank, local_rank, world):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    launches_counted = rend.launch_count() - launches0  # as the library counts its own launches
     if world == 1:
         _lib.check(rend._lib.spv_set_tuning(rend._ctx, 14, 0), rend._ctx)
         _lib.check(rend._lib.spv_select_slot(rend._ctx, 0), rend._ctx)
@@ -694,9 +696,11 @@ def run_iso(args, rank, local_rank, world):
                                         "back (the rectangle the projected box can touch); depth, normals and occlusion stay "
                                         "on the device until they are looked at (lazy attributes)"},
             "surface_pixels_last": hit_px, "image_sha1_first8": digest.hexdigest(),
-            # iso_fast, blur, occlusion list + queue, blur, shading; sort-last: search, resolve, fix-up, 2+2 blur
-            # launches, occlusion list + queue, shading (the two NCCL reductions are not counted)
-            "gpu_launches": args.steps * (6 if world == 1 else (13 if args.composite == "peer" else 10))}, **line_extra)))
+            # one GPU (counted by the library): iso_fast, normal blur, occlusion (tap table: one launch), occlusion blur
+            # + shading; sort-last: search, resolve, fix-up, 2+2 blur launches, occlusion list + queue, shading (the two
+            # NCCL reductions are not counted)
+            "gpu_launches": int(launches_counted) if world == 1 else args.steps * (13 if args.composite == "peer" else 10)},
+                          **line_extra)))
     rend.close()
     if world > 1:
         dist.destroy_process_group()

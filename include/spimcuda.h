@@ -338,7 +338,9 @@ SPV_API int spv_enable_stats(spv_ctx *ctx, int on);
  * instead of hashing every tap in every frame (0); same result bit for bit,
  * knob 18 = spv_read_pinned_async of a clipped rectangle (output, alpha) first moves it into a device staging buffer
  * (one small kernel), after which the slot's planes are free for the next render while the rectangle crosses the host
- * link (1, default), or copies straight out of the slot, which then stays busy for the length of the copy (0). */
+ * link (1, default), or copies straight out of the slot, which then stays busy for the length of the copy (0),
+ * knob 20 = iso-surface frames compute the shading in the epilogue of the occlusion blur (1, default: one launch and one
+ * pass over the occlusion plane less) or in a launch of its own (0); same result bit for bit. */
 SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value);
 /* Which kernel family renders plain (alpha_pow == 0, num_parts == 1) max projections of uint16 volumes
  * (max_project_short, volume_kernel.cl:270-345):

@@ -74,6 +74,7 @@ struct spv_ctx {
   int occ_key[4] = {0, 0, -1, 0};       // width, height, radius, n_points the table was built for
   int occ_table_on = 1;                 // tuning knob 17
   int stage_reads = 1;                  // tuning knob 18: spv_read_pinned_async frees the slot through a device staging copy
+  int fuse_shading = 1;                 // tuning knob 20: iso frames shade in the epilogue of the occlusion blur
   Camera cam;
   // result buffers: one allocation  [out | alpha | depth | occ | normals(3) | raw | tmp | tmp_vec(3)]
   float *dbuf = nullptr;
@@ -1029,6 +1030,7 @@ SPV_API int spv_set_tuning(spv_ctx *ctx, int knob, int value) {
   else if (knob == 6) occ_ctas_per_sm = value < 1 ? 1 : (value > 16 ? 16 : value);  // process-wide
   else if (knob == 17) ctx->occ_table_on = value != 0;
   else if (knob == 18) ctx->stage_reads = value != 0;
+  else if (knob == 20) ctx->fuse_shading = value != 0;
   else return fail(ctx, SPV_EINVAL, "spv_set_tuning: unknown knob");
   return 0;
 }
@@ -2194,12 +2196,21 @@ static int render_iso_impl(spv_ctx *ctx, const spv_iso_params *p, bool to_host) 
     // volumerender.py:470-497
     CU(launch_conv_xy(ctx->tmp_vec(), ctx->normals(), ctx->width, ctx->height, 3, conv_weights(7, -5.f), a.tile_hit, 0, pst));
     CU(launch_occlusion(ctx->tmp(), ctx->width, ctx->height, p->occ_radius, p->occ_n_points, ctx->depth(), a.tile_hit,
-                        ctx->d_taps, ctx->d_occ_queue, ctx->occ_frame++, ctx->sms, pst, 0, -1, occ_table));
-    CU(launch_conv_xy(ctx->tmp(), ctx->occ(), ctx->width, ctx->height, 1, conv_weights(5, -10.f), a.tile_hit,
-                      p->occ_radius, pst));
-    CU(launch_shading(ctx->out(), ctx->width, ctx->height, ctx->cam, p->occ_strength, ctx->normals(), ctx->depth(),
-                      ctx->occ(), pst));
-    ctx->launches += a.tile_hit ? 5 : 4;
+                        ctx->d_taps, ctx->d_occ_queue, occ_table ? ctx->occ_frame : ctx->occ_frame++, ctx->sms, pst, 0, -1,
+                        occ_table));  // (the table form leaves the queue's counters alone: the frame parity stays)
+    if (ctx->fuse_shading) {  // knob 20: the shading rides on the epilogue of the occlusion blur
+      ShadeArgs sh;
+      sh.out = ctx->out(); sh.cam = ctx->cam; sh.occ_strength = p->occ_strength;
+      sh.normals = ctx->normals(); sh.depth = ctx->depth();
+      CU(launch_conv_xy(ctx->tmp(), ctx->occ(), ctx->width, ctx->height, 1, conv_weights(5, -10.f), a.tile_hit,
+                        p->occ_radius, pst, 0, -1, &sh));
+    } else {
+      CU(launch_conv_xy(ctx->tmp(), ctx->occ(), ctx->width, ctx->height, 1, conv_weights(5, -10.f), a.tile_hit,
+                        p->occ_radius, pst));
+      CU(launch_shading(ctx->out(), ctx->width, ctx->height, ctx->cam, p->occ_strength, ctx->normals(), ctx->depth(),
+                        ctx->occ(), pst));
+    }
+    ctx->launches += (a.tile_hit && !occ_table ? 5 : 4) - (ctx->fuse_shading ? 1 : 0);  // (the queue form of the occlusion is two launches)
     if (overlap) {
       CU(cudaEventRecord(ctx->ev_posted[s], ctx->post_stream));
       ctx->post_pending[s] = true;

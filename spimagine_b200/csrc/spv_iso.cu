@@ -794,6 +794,32 @@ __device__ __forceinline__ int tiles_in_reach(const unsigned char *__restrict__ 
   return mine;
 }
 
+// iso_kernel.cl:505-588 for one pixel: the shaded value from the blurred normal, the depth and the blurred occlusion
+__device__ __forceinline__ float shade_pixel(unsigned x, unsigned y, int Nx, int Ny, const Camera &cam, float occ_strength,
+                                             const float *__restrict__ input_normals, const float *__restrict__ input_depth,
+                                             float occ) {
+  const size_t p = x + (size_t)Nx * y;
+  const float depth = input_depth[p];
+  if (!(depth < __int_as_float(0x7f800000))) return 0.f;  // colVal * 0 below: nothing to compute
+  v4 orig, direc;
+  eye_ray(x, y, Nx, Ny, cam, orig, direc);
+  v4 light = mk4(2.f, -1.f, -2.f, 0.f);
+  const float c_ambient = .5f, c_diffuse = .3f, c_specular = .2f;
+  light = mult(cam.invM, light);
+  light = normalize4(light);
+  v4 normal = mk4(input_normals[3 * p], input_normals[1 + 3 * p], input_normals[2 + 3 * p], 0.f);
+  normal = normalize4(normal);
+  const v4 reflect = sub4(scl4(2.f * dot4(light, normal), normal), light);
+  const float diffuse = fmaxf(0.f, dot4(light, normal));
+  const float specular = powf(fmaxf(0.f, dot4(normalize4(reflect), normalize4(direc))), 10.f);
+  float colVal = c_ambient + c_diffuse * diffuse + (diffuse > 0.f ? 1.f : 0.f) * c_specular * specular;
+  colVal = (1.f - occ_strength) * colVal + occ_strength * colVal * (1.f - occ);
+  // iso_kernel.cl:580 has a double literal: the sum is formed in double and rounded once
+  colVal = (float)((double)((1.f - occ_strength) * colVal) + 1.0 * (double)occ_strength * (double)colVal);
+  colVal *= ((depth < __int_as_float(0x7f800000)) ? 1.f : 0.f);
+  return colVal;
+}
+
 // Both passes in one launch: the x pass of the rows a 32x16 output tile needs (Nh-1 halo rows) goes to shared memory,
 // the y pass reads it from there.  Every output is the same sequence of fp32 operations as conv_kernel<.,false>
 // followed by conv_kernel<.,true>, so the result is bit-identical to the two-launch form; it needs `in` != `out`.
@@ -803,12 +829,15 @@ __device__ __forceinline__ int tiles_in_reach(const unsigned char *__restrict__ 
 // unrolled loop with the weights in registers; NH == 0: any tap count up to 32.
 // tile_hit != nullptr: the input is known to be +0 on every pixel further than `reach` pixels from a flagged 8x4 tile;
 // a CTA whose taps see only such pixels stores zeros (what the arithmetic would give) and is done.
+// SHADE (NCOMP == 1: the blur of the occlusion plane): the shading pass rides on the epilogue -- the pixel's blurred
+// occlusion goes to its plane and, with the blurred normal and the depth, straight into shade_pixel (one launch and one
+// read of the occlusion plane less; the same expressions on the same values as shading_kernel).
 constexpr int CONV_TH = 16;
-template <int NCOMP, int NH>
+template <int NCOMP, int NH, bool SHADE>
 __global__ void __launch_bounds__(256) conv_xy_kernel(const float *__restrict__ input, float *__restrict__ output, int Nx,
                                                       int Ny, const ConvWeights cw,
                                                       const unsigned char *__restrict__ tile_hit, int tiles_x, int reach,
-                                                      int y_first, int y_end) {
+                                                      int y_first, int y_end, const ShadeArgs sh) {
   // rows [y_first, y_end) are written (the whole image, or one rank's band of a sort-last frame); taps read any row
   extern __shared__ float s_row[];  // [CONV_TH + Nh - 1][32]
   const int Nh = NH > 0 ? NH : cw.nh, R = Nh / 2;
@@ -822,7 +851,10 @@ __global__ void __launch_bounds__(256) conv_xy_kernel(const float *__restrict__ 
                                                      reach + Nh, threadIdx.y * 32 + threadIdx.x, 256));
     if (!live) {
       if (c < pitch)
-        for (int r = threadIdx.y; r < CONV_TH && y0 + r < y_end; r += blockDim.y) output[(size_t)(y0 + r) * pitch + c] = 0.f;
+        for (int r = threadIdx.y; r < CONV_TH && y0 + r < y_end; r += blockDim.y) {
+          output[(size_t)(y0 + r) * pitch + c] = 0.f;
+          if (SHADE) sh.out[(size_t)(y0 + r) * pitch + c] = 0.f;  // no surface tile in reach: no surface pixel here
+        }
       return;
     }
   }
@@ -878,12 +910,15 @@ __global__ void __launch_bounds__(256) conv_xy_kernel(const float *__restrict__ 
         res += val * col[32 * ht];
       }
     }
-    output[(size_t)j * pitch + c] = res / sum_val;
+    const float v = res / sum_val;
+    output[(size_t)j * pitch + c] = v;
+    if (SHADE) sh.out[(size_t)j * pitch + c] = shade_pixel((unsigned)c, (unsigned)j, Nx, Ny, sh.cam, sh.occ_strength, sh.normals, sh.depth, v);
   }
 }
 
 cudaError_t launch_conv_xy(const float *in, float *out, int width, int height, int ncomp, const ConvWeights &w,
-                           const unsigned char *tile_hit, int reach, cudaStream_t st, int y_first, int y_end) {
+                           const unsigned char *tile_hit, int reach, cudaStream_t st, int y_first, int y_end,
+                           const ShadeArgs *shade) {
   if (in == out || w.nh < 1 || w.nh > 32 || (ncomp != 1 && ncomp != 3)) return cudaErrorInvalidValue;
   if (y_end < 0 || y_end > height) y_end = height;
   if (y_first < 0) y_first = 0;
@@ -892,11 +927,19 @@ cudaError_t launch_conv_xy(const float *in, float *out, int width, int height, i
   if (grid.y > 65535u) return cudaErrorInvalidValue;
   const size_t smem = (size_t)(CONV_TH + w.nh - 1) * 32 * sizeof(float);
   const int tx = (width + 7) / 8;
-#define SPV_CONV(C, N) conv_xy_kernel<C, N><<<grid, block, smem, st>>>(in, out, width, height, w, tile_hit, tx, reach, y_first, y_end)
-  if (ncomp == 3 && w.nh == 7) SPV_CONV(3, 7);
-  else if (ncomp == 1 && w.nh == 5) SPV_CONV(1, 5);
-  else if (ncomp == 1) SPV_CONV(1, 0);
-  else SPV_CONV(3, 0);
+  ShadeArgs sh;
+  memset(&sh, 0, sizeof sh);
+  if (shade) {
+    if (ncomp != 1 || !shade->out || shade->out == out || shade->out == in) return cudaErrorInvalidValue;
+    sh = *shade;
+  }
+#define SPV_CONV(C, N, S) conv_xy_kernel<C, N, S><<<grid, block, smem, st>>>(in, out, width, height, w, tile_hit, tx, reach, y_first, y_end, sh)
+  if (ncomp == 3 && w.nh == 7) SPV_CONV(3, 7, false);
+  else if (ncomp == 1 && w.nh == 5 && shade) SPV_CONV(1, 5, true);
+  else if (ncomp == 1 && w.nh == 5) SPV_CONV(1, 5, false);
+  else if (ncomp == 1 && shade) SPV_CONV(1, 0, true);
+  else if (ncomp == 1) SPV_CONV(1, 0, false);
+  else SPV_CONV(3, 0, false);
 #undef SPV_CONV
   return cudaGetLastError();
 }
@@ -974,7 +1017,7 @@ constexpr int OCC_BW = 32, OCC_BH = 2, OCC_GROUP = 4;  // the list kernel classi
 __global__ void __launch_bounds__(256) occ_list_kernel(float *__restrict__ d_output, int Nx, int Ny, int radius,
                                                        const unsigned char *__restrict__ tile_hit, int tiles_x, int obx,
                                                        int oby, unsigned *__restrict__ cnt, unsigned *__restrict__ cnt_next,
-                                                       unsigned *__restrict__ list, int y_first, int y_end, int by_group) {
+                                                       unsigned *__restrict__ list, int y_first, int y_end) {
   // one warp per group of OCC_GROUP vertically adjacent blocks (32 x 8 pixels): their reach rectangles differ by a
   // few rows only, so one scan of the tile flags over the union decides all of them (conservatively: a block that
   // is computed although nothing is in reach still gets the right answer, 0)
@@ -987,9 +1030,7 @@ __global__ void __launch_bounds__(256) occ_list_kernel(float *__restrict__ d_out
   if (py + nb * OCC_BH <= y_first || py >= y_end) return;  // not this rank's rows (sort-last frames): left untouched
   const int mine = tiles_in_reach(tile_hit, tiles_x, Nx, Ny, px, px + OCC_BW - 1, py, py + nb * OCC_BH - 1, radius, lane, 32);
   if (__any_sync(0xffffffffu, mine != 0)) {
-    if (by_group) {  // occ_tile_kernel takes whole groups (32 x 8 pixels)
-      if (lane == 0) list[atomicAdd(cnt, 1u)] = (unsigned)g;
-    } else if (lane < nb) list[atomicAdd(cnt, 1u)] = (unsigned)((by0 + lane) * obx + bx);
+    if (lane < nb) list[atomicAdd(cnt, 1u)] = (unsigned)((by0 + lane) * obx + bx);
   } else {
     const int x = px + lane;
     if (x < Nx)
@@ -1073,52 +1114,56 @@ __global__ void __launch_bounds__(256) occ_table_kernel(char2 *__restrict__ tabl
   table[idx] = o;
 }
 
-__global__ void __launch_bounds__(256) occ_tile_kernel(float *__restrict__ d_output, int Nx, int Ny, int number_points,
+__global__ void __launch_bounds__(256) occ_tile_kernel(float *__restrict__ d_output, int Nx, int Ny, int radius, int number_points,
                                                        const float *__restrict__ input_depth, const char2 *__restrict__ table,
-                                                       int halo, int obx, const unsigned *__restrict__ cnt,
-                                                       const unsigned *__restrict__ list) {
+                                                       const unsigned char *__restrict__ tile_hit, int tiles_x, int obx) {
+  // one CTA per group of 32 x 8 pixels; a group without a surface tile in reach stores its zeros and is done (as
+  // occ_list_kernel decides for the queue form: no list, no counters here -- a CTA costs a few us at most)
   extern __shared__ float s_depth[];  // [8 + 2 halo][32 + 2 halo]
+  const int halo = radius + 1;
   const int tw = OCC_BW + 2 * halo, th = OCC_GROUP * OCC_BH + 2 * halo;
-  const unsigned total = cnt[0];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane & 3;
+  const int px = (blockIdx.x % obx) * OCC_BW, py = (blockIdx.x / obx) * OCC_GROUP * OCC_BH;
+  const int reach = __syncthreads_or(tiles_in_reach(tile_hit, tiles_x, Nx, Ny, px, px + OCC_BW - 1, py,
+                                                    py + OCC_GROUP * OCC_BH - 1, radius, threadIdx.x, 256));
+  if (!reach) {
+    const int x = px + lane, y = py + warp;
+    if (x < Nx && y < Ny) d_output[x + (size_t)Nx * y] = 0.f;
+    return;
+  }
+  const int ox = px - halo, oy = py - halo;  // image position of tile element (0, 0)
+  for (int e = threadIdx.x; e < tw * th; e += 256) {
+    const int tx = e % tw, ty = e / tw, ix = ox + tx, iy = oy + ty;
+    if (ix >= 0 && ix < Nx && iy >= 0 && iy < Ny) s_depth[e] = input_depth[ix + (size_t)iy * Nx];  // taps are clamped into the image
+  }
+  __syncthreads();
   const size_t npix = (size_t)Nx * Ny;
   const int chunks = (number_points + 31) / 32;
-  for (unsigned item = blockIdx.x; item < total; item += gridDim.x) {
-    const int grp = (int)list[item];
-    const int px = (grp % obx) * OCC_BW, py = (grp / obx) * OCC_GROUP * OCC_BH;
-    const int ox = px - halo, oy = py - halo;  // image position of tile element (0, 0)
-    __syncthreads();                           // the previous item's gathers are done
-    for (int e = threadIdx.x; e < tw * th; e += 256) {
-      const int tx = e % tw, ty = e / tw, ix = ox + tx, iy = oy + ty;
-      if (ix >= 0 && ix < Nx && iy >= 0 && iy < Ny) s_depth[e] = input_depth[ix + (size_t)iy * Nx];  // taps are clamped into the image
-    }
-    __syncthreads();
-    const int y = py + warp;
+  const int y = py + warp;
 #pragma unroll
-    for (int step = 0; step < OCC_BW / 8; ++step) {
-      const int x = px + step * 8 + (lane >> 2);
-      const bool inb = x < Nx && y < Ny;
-      float occ = 0.f;
-      if (inb) {
-        const float *centre = s_depth + (warp + halo) * tw + (x - ox);
-        const float depth0 = *centre;
-        const size_t pix = x + (size_t)y * Nx;
-        for (int chunk = 0; chunk < chunks; ++chunk) {
-          const uint4 q = __ldg(reinterpret_cast<const uint4 *>(table + ((chunk * npix + pix) * 4 + g) * 8));
-          const unsigned w[4] = {q.x, q.y, q.z, q.w};
+  for (int step = 0; step < OCC_BW / 8; ++step) {
+    const int x = px + step * 8 + (lane >> 2);
+    const bool inb = x < Nx && y < Ny;
+    float occ = 0.f;
+    if (inb) {
+      const float *centre = s_depth + (warp + halo) * tw + (x - ox);
+      const float depth0 = *centre;
+      const size_t pix = x + (size_t)y * Nx;
+      for (int chunk = 0; chunk < chunks; ++chunk) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(table + ((chunk * npix + pix) * 4 + g) * 8));
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const unsigned i = 32u * chunk + g + 4u * j;
-            const unsigned pair = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
-            const int dx = (int)(signed char)(pair & 0xffu), dy = (int)(signed char)(pair >> 8);
-            if (i < (unsigned)number_points) occ += (centre[dy * tw + dx] < depth0 ? 1.f : 0.f);
-          }
+        for (int j = 0; j < 8; ++j) {
+          const unsigned i = 32u * chunk + g + 4u * j;
+          const unsigned pair = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+          const int dx = (int)(signed char)(pair & 0xffu), dy = (int)(signed char)(pair >> 8);
+          if (i < (unsigned)number_points) occ += (centre[dy * tw + dx] < depth0 ? 1.f : 0.f);
         }
       }
-      occ += __shfl_xor_sync(0xffffffffu, occ, 1);
-      occ += __shfl_xor_sync(0xffffffffu, occ, 2);
-      if (inb && g == 0) d_output[x + (size_t)Nx * y] = occ / (float)(unsigned)number_points;
     }
+    occ += __shfl_xor_sync(0xffffffffu, occ, 1);
+    occ += __shfl_xor_sync(0xffffffffu, occ, 2);
+    if (inb && g == 0) d_output[x + (size_t)Nx * y] = occ / (float)(unsigned)number_points;
   }
 }
 
@@ -1159,15 +1204,13 @@ cudaError_t launch_occlusion(float *occ, int width, int height, int radius, int 
     const int obx = (width + OCC_BW - 1) / OCC_BW, oby = (height + OCC_BH - 1) / OCC_BH;
     const int groups = obx * ((oby + OCC_GROUP - 1) / OCC_GROUP);
     unsigned *cnt = queue + 2 * (frame & 1u), *cnt_next = queue + 2 * ((frame + 1u) & 1u), *list = queue + 4;
-    occ_list_kernel<<<(groups + 7) / 8, 256, 0, st>>>(occ, width, height, radius, tile_hit, (width + 7) / 8, obx, oby, cnt,
-                                                     cnt_next, list, y_first, y_end, table != nullptr);
-    if (table) {  // groups of 32 x 8 pixels in reach, one CTA each (a fixed grid walks the list)
-      const int per_sm = 8, nsm = sms > 0 ? sms : 148;
-      const unsigned grid = (unsigned)(groups < nsm * per_sm ? groups : nsm * per_sm);
-      occ_tile_kernel<<<grid, 256, occ_tile_smem(radius), st>>>(occ, width, height, n_points, depth,
-                                                                reinterpret_cast<const char2 *>(table), radius + 1, obx, cnt, list);
+    if (table && y_first == 0 && y_end == height) {  // one CTA per group of 32 x 8 pixels
+      occ_tile_kernel<<<groups, 256, occ_tile_smem(radius), st>>>(occ, width, height, radius, n_points, depth,
+                                                                  reinterpret_cast<const char2 *>(table), tile_hit, (width + 7) / 8, obx);
       return cudaGetLastError();
     }
+    occ_list_kernel<<<(groups + 7) / 8, 256, 0, st>>>(occ, width, height, radius, tile_hit, (width + 7) / 8, obx, oby, cnt,
+                                                     cnt_next, list, y_first, y_end);
     occ_queue_kernel<<<(sms > 0 ? sms : 148) * occ_ctas_per_sm, 128, 0, st>>>(occ, width, height, radius, n_points, depth, taps, obx, cnt,
                                                                  list);
     return cudaGetLastError();
@@ -1184,30 +1227,12 @@ __global__ void shading_kernel(float *__restrict__ d_output, int Nx, int Ny, con
                                const float *__restrict__ input_occlusion, int y_first, int y_end) {
   const unsigned x = blockIdx.x * blockDim.x + threadIdx.x, y = (unsigned)y_first + blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= (unsigned)Nx || y >= (unsigned)y_end) return;
-  if (!(input_depth[x + (size_t)Nx * y] < __int_as_float(0x7f800000))) {  // colVal * 0 below: nothing to compute
-    d_output[x + (size_t)Nx * y] = 0.f;
+  const size_t p = x + (size_t)Nx * y;
+  if (!(input_depth[p] < __int_as_float(0x7f800000))) {  // (the occlusion plane is not read where there is no surface)
+    d_output[p] = 0.f;
     return;
   }
-  v4 orig, direc;
-  eye_ray(x, y, Nx, Ny, cam, orig, direc);
-  v4 light = mk4(2.f, -1.f, -2.f, 0.f);
-  const float c_ambient = .5f, c_diffuse = .3f, c_specular = .2f;
-  light = mult(cam.invM, light);
-  light = normalize4(light);
-  const size_t p = x + (size_t)Nx * y;
-  v4 normal = mk4(input_normals[3 * p], input_normals[1 + 3 * p], input_normals[2 + 3 * p], 0.f);
-  const float occ = input_occlusion[p];
-  const float depth = input_depth[p];
-  normal = normalize4(normal);
-  const v4 reflect = sub4(scl4(2.f * dot4(light, normal), normal), light);
-  const float diffuse = fmaxf(0.f, dot4(light, normal));
-  const float specular = powf(fmaxf(0.f, dot4(normalize4(reflect), normalize4(direc))), 10.f);
-  float colVal = c_ambient + c_diffuse * diffuse + (diffuse > 0.f ? 1.f : 0.f) * c_specular * specular;
-  colVal = (1.f - occ_strength) * colVal + occ_strength * colVal * (1.f - occ);
-  // iso_kernel.cl:580 has a double literal: the sum is formed in double and rounded once
-  colVal = (float)((double)((1.f - occ_strength) * colVal) + 1.0 * (double)occ_strength * (double)colVal);
-  colVal *= ((depth < __int_as_float(0x7f800000)) ? 1.f : 0.f);
-  d_output[p] = colVal;
+  d_output[p] = shade_pixel(x, y, Nx, Ny, cam, occ_strength, input_normals, input_depth, input_occlusion[p]);
 }
 
 cudaError_t launch_shading(float *out, int width, int height, const Camera &cam, float occ_strength,
@@ -1246,10 +1271,12 @@ cudaError_t preload_iso_kernels() {
   if ((e = preload_iso_fmt<4>()) != cudaSuccess) return e;
   if ((e = preload_iso_fmt<5>()) != cudaSuccess) return e;
   SPV_PRELOAD(iso_slab_fix_kernel);
-  SPV_PRELOAD((conv_xy_kernel<3, 7>));
-  SPV_PRELOAD((conv_xy_kernel<1, 5>));
-  SPV_PRELOAD((conv_xy_kernel<1, 0>));
-  SPV_PRELOAD((conv_xy_kernel<3, 0>));
+  SPV_PRELOAD((conv_xy_kernel<3, 7, false>));
+  SPV_PRELOAD((conv_xy_kernel<1, 5, false>));
+  SPV_PRELOAD((conv_xy_kernel<1, 0, false>));
+  SPV_PRELOAD((conv_xy_kernel<3, 0, false>));
+  SPV_PRELOAD((conv_xy_kernel<1, 5, true>));
+  SPV_PRELOAD((conv_xy_kernel<1, 0, true>));
   SPV_PRELOAD(occ_taps_kernel);
   SPV_PRELOAD(occ_list_kernel);
   SPV_PRELOAD(occ_queue_kernel);

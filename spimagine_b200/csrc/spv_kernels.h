@@ -185,8 +185,17 @@ cudaError_t launch_conv(float *buf, float *tmp, int width, int height, int ncomp
 // both passes in one launch (in != out), bit-identical to launch_conv.  tile_hit (may be null): `in` is +0 on every
 // pixel further than `reach` pixels from a flagged 8x4 tile; such regions are filled with zeros without the arithmetic
 // y_first / y_end: only these rows are written (default: all) -- one rank's band of a sort-last frame
+// shade (ncomp == 1 only, may be null): the shading pass in the blur's epilogue -- out[p] = launch_shading's value for
+// the pixel, computed from the blurred occlusion just stored, normals and depth (same result as the separate launch)
+struct ShadeArgs {
+  float *out;
+  Camera cam;
+  float occ_strength;
+  const float *normals, *depth;
+};
 cudaError_t launch_conv_xy(const float *in, float *out, int width, int height, int ncomp, const ConvWeights &w,
-                           const unsigned char *tile_hit, int reach, cudaStream_t st, int y_first = 0, int y_end = -1);
+                           const unsigned char *tile_hit, int reach, cudaStream_t st, int y_first = 0, int y_end = -1,
+                           const ShadeArgs *shade = nullptr);
 // taps[i] = the four rand_int() values of occlusion tap i (they depend on i only)
 cudaError_t launch_occ_taps(float4 *taps, int n, cudaStream_t st);
 // queue (occ_queue_bytes, zero-initialised) + tile flags: only the pixel blocks in reach of a surface are computed, handed

@@ -414,7 +414,8 @@ def test_iso_cell_traversal_is_exact_on_large_and_anisotropic_volumes(shape):
 
 
 def test_iso_tuning_knobs_do_not_change_the_image():
-    """Ray segments (1 / 2 / 4 warps share a ray), CTA order, occlusion queue width: scheduling only."""
+    """Ray segments (1 / 2 / 4 warps share a ray), CTA order, occlusion queue width, the occlusion's tap table, shading in
+    the epilogue of the occlusion blur or in its own launch: scheduling only."""
     data = scenes.vol_g(0, np.uint16, seed=3, shape=(90, 120, 100))
     g = _renderer((200, 152))
     g.set_data(data)
@@ -422,8 +423,8 @@ def test_iso_tuning_knobs_do_not_change_the_image():
     g.set_modelView(M)
     g.set_projection(P)
     ref = None
-    for segments, centre, occ_ctas in ((1, 1, 10), (2, 1, 10), (4, 0, 3), (1, 0, 16)):
-        for knob, value in ((4, segments), (5, centre), (6, occ_ctas)):
+    for segments, centre, occ_ctas, table, fused_shading in ((1, 1, 10, 1, 0), (2, 1, 10, 0, 1), (4, 0, 3, 0, 0), (1, 0, 16, 1, 1)):
+        for knob, value in ((4, segments), (5, centre), (6, occ_ctas), (17, table), (20, fused_shading)):
             g._check(g._lib.spv_set_tuning(g._ctx, knob, value))
         g.render(maxVal=26000., method="iso_surface")
         planes = [a.copy() for a in (g.output, g.output_alpha, g.output_depth, g.output_normals, g.output_occlusion)]
@@ -431,7 +432,7 @@ def test_iso_tuning_knobs_do_not_change_the_image():
             ref = planes
             assert np.isfinite(planes[2]).sum() > 1000
         for a, b in zip(planes, ref):
-            assert np.array_equal(a, b), (segments, centre, occ_ctas)
+            assert np.array_equal(a, b), (segments, centre, occ_ctas, table, fused_shading)
     g._check(g._lib.spv_set_tuning(g._ctx, 6, 10))
     g.close()
 
