@@ -57,7 +57,7 @@ def census(tag):
     txt = subprocess.run(["cuobjdump", "-sass", b.LIB], capture_output=True, text=True, check=True).stdout
     funcs = re.split(r"\n\s*Function : ", txt)[1:]
     cols = ["TEX", "TLD", "UTMALDG", "SYNCS", "LDG.E.128", "STG.E.128", "STG.E.64", "LDS", "STS", "SHFL", "VOTE", "ATOM", "RED",
-            "BAR", "FFMA", "FMNMX", "MUFU"]
+            "BAR", "FFMA2", "FFMA", "FMNMX", "MUFU"]
     stats, count = collections.defaultdict(collections.Counter), collections.Counter()
     for f, n in zip(funcs, demangle([f.split("\n", 1)[0].strip() for f in funcs])):
         k = base(n)
@@ -71,7 +71,8 @@ def census(tag):
     out = ["SASS mnemonic census of spimagine_b200/libspimcuda.so (cuobjdump -sass, sm_100a), summed over the instantiations of",
            "each kernel template: what the kernels are made of.  TEX = filtered texture fetches (the hardware trilinear /",
            "bilinear sampler), TLD = unfiltered texel loads, UTMALDG = TMA tensor loads (cp.async.bulk.tensor), SYNCS = mbarrier",
-           "operations (init / arrive / expect_tx / try_wait), STG.E.128 = 128-bit stores, SHFL / VOTE = warp-level exchange.",
+           "operations (init / arrive / expect_tx / try_wait), STG.E.128 = 128-bit stores, SHFL / VOTE = warp-level exchange,",
+           "FFMA2 = packed two-wide float32 fused multiply-add (fma.rn.f32x2 of sm_100).",
            "scripts/static_census.py", "",
            "%-28s %5s %8s " % ("kernel", "inst.", "SASS") + " ".join("%9s" % c for c in cols)]
     for k in sorted(stats):
