@@ -2547,9 +2547,14 @@ static int copy_slot_planes(spv_ctx *ctx, int s, int planes, cudaStream_t st, bo
       }
     }
     staging_clean_outside_rect(ctx, s, xa, xb, ya, yb, c.miss_alpha);
+    if (stage && ctx->stage_reads && xa < xb && ya < yb && !ctx->dstage_s[s] &&
+        cudaMalloc(&ctx->dstage_s[s], 2 * ctx->n() * sizeof(float)) != cudaSuccess) {
+      cudaGetLastError();  // no memory for the staging planes: copy straight out of the slot
+      ctx->dstage_s[s] = nullptr;
+      stage = false;
+    }
     if (stage && ctx->stage_reads && xa < xb && ya < yb) {
       // rectangle -> device staging (same layout), slot free; then staging -> pinned host memory, one 2-D copy per plane
-      if (!ctx->dstage_s[s]) CU(cudaMalloc(&ctx->dstage_s[s], 2 * ctx->n() * sizeof(float)));
       CU(launch_rect_copy(ctx->dbuf_s[s], ctx->dstage_s[s], W, H, xa, xb, ya, yb, planes, st));
       ctx->launches += 1;
       CU(cudaEventRecord(ctx->ev_freed[s], st));
