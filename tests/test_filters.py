@@ -110,6 +110,28 @@ def _gpu_sep3(data, hx, hy, hz, fuse=1):
 
 
 @pytest.mark.gpu
+def test_gpu_per_pass_times_add_up():
+    """spv_filter_last_pass_ms: three kernels (x, y, z) or two with the fused x + y pass; their times add up to the
+    time of the whole convolution (events on one stream, back to back)"""
+    from spimagine_b200 import imageprocessor as ip
+    vf = ip.VolumeFilter(0)
+    try:
+        data = scenes.random_vol((40, 64, 128), np.uint16, seed=5)
+        taps = [np.full(n, 1. / n) for n in (19, 19, 19)]
+        for fuse, n in ((0, 3), (1, 2)):
+            vf.set_tuning(0, fuse)
+            vf.load(data)
+            vf.convolve_sep3(*taps)
+            vf.sync()
+            ms = vf.last_pass_ms()
+            assert len(ms) == n and all(m > 0 for m in ms)
+            assert abs(sum(ms) - vf.last_ms()) < 0.02 * vf.last_ms() + 1e-3
+    finally:
+        vf.set_tuning(0, 0)
+        vf.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("x_pairs,axis", [(0, 16), (1, 32), (2, 1602), (2, 1604), (0, 1604)])
 @pytest.mark.parametrize("dtype", [np.float32, np.uint16, np.uint8])
 def test_gpu_kernel_variants_equal_the_oracle_bitwise(forc, dtype, x_pairs, axis):
