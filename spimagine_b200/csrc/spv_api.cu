@@ -2534,7 +2534,9 @@ static int copy_slot_planes(spv_ctx *ctx, int s, int planes, cudaStream_t st, bo
     const int W = ctx->width, H = ctx->height;
     int xa, xb, ya, yb;
     miss_free_rect(c.cam, c.box, W, H, xa, xb, ya, yb);
-    if (stage && ctx->stage_reads && c.full && xa < xb && ya < yb && ctx->clean_alpha[s] == c.miss_alpha &&
+    const int fxa = xa, fxb = xb, fya = ya, fyb = yb;  // this frame's own rectangle
+    bool widened = false;
+    if (stage && ctx->stage_reads && c.full && planes == 2 && xa < xb && ya < yb && ctx->clean_alpha[s] == c.miss_alpha &&
         ctx->dirty_x0[s] < ctx->dirty_x1[s] && ctx->dirty_lo[s] < ctx->dirty_hi[s]) {
       // the pinned planes hold an earlier frame inside their dirty rectangle.  Where that sticks out of this frame's
       // rectangle by little (a camera path: a few pixels per frame), copying the union of the two from the device --
@@ -2544,9 +2546,14 @@ static int copy_slot_planes(spv_ctx *ctx, int s, int planes, cudaStream_t st, bo
       if ((double)(ux1 - ux0) * (uy1 - uy0) <= 1.125 * (double)(xb - xa) * (yb - ya)) {
         xa = ux0 < 0 ? 0 : ux0; xb = ux1 > W ? W : ux1;
         ya = uy0 < 0 ? 0 : uy0; yb = uy1 > H ? H : uy1;
+        widened = true;
       }
     }
     staging_clean_outside_rect(ctx, s, xa, xb, ya, yb, c.miss_alpha);
+    if (widened) {  // what is copied outside the frame's own rectangle are miss values: the planes are dirty inside it only
+      ctx->dirty_x0[s] = fxa; ctx->dirty_x1[s] = fxb;
+      ctx->dirty_lo[s] = fya; ctx->dirty_hi[s] = fyb;
+    }
     if (stage && ctx->stage_reads && xa < xb && ya < yb && !ctx->dstage_s[s] &&
         cudaMalloc(&ctx->dstage_s[s], 2 * ctx->n() * sizeof(float)) != cudaSuccess) {
       cudaGetLastError();  // no memory for the staging planes: copy straight out of the slot
