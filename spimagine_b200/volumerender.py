@@ -693,9 +693,17 @@ class VolumeRenderer(object):
         return [(flat[2 * f * n:(2 * f + 1) * n].reshape(shape), flat[(2 * f + 1) * n:(2 * f + 2) * n].reshape(shape))
                 for f in range(n_frames.value)]
 
+    # the first launch of a sequence takes half a batch: the device starts after half the host preparation (a batch's
+    # matrices are inverted one by one, ~10 us each), and a sequence whose length is a multiple of the batch ends on a
+    # half launch, whose last read-back band is half as long -- fill and drain of short sequences (configs[1], 20 frames:
+    # 8282 -> 8606 frames/s end to end, three runs each); 5 frames per launch cost 103 instead of 98 us per frame
+    # (profiles/r02_exp_axis_v4.txt), long sequences are unchanged
+    first_batch_half = True
+
     def _render_sequence_batched(self, modelViews, p, batch):
         import itertools
         batch = max(1, min(int(batch), _lib.MAX_BATCH))
+        first = max(2, (batch + 1) // 2) if (self.first_batch_half and batch >= 4) else batch
         it = iter(modelViews)
         pending = []  # (set, modelViews) in flight, oldest first
         shape = (self.height, self.width)
@@ -711,7 +719,8 @@ class VolumeRenderer(object):
                 yield self
         try:
             while True:
-                Ms = [np.asarray(M, dtype=np.float64) for M in itertools.islice(it, batch)]
+                Ms = [np.asarray(M, dtype=np.float64) for M in itertools.islice(it, first)]
+                first = batch
                 if not Ms:
                     break
                 last = Ms[-1]
