@@ -422,3 +422,65 @@ def test_package_exports_what_spimagine_exports():
                  "Quaternion", "mat4_perspective", "mat4_translate", "mat4_rotation", "pinned_empty"):
         assert hasattr(sp, name), name
     assert sp.TransformData().zoom == 1 and sp.NumpyData(np.zeros((2, 3, 4))).size() == (1, 2, 3, 4)
+
+
+def test_batched_sequence_launch_schedule():
+    """render_sequence over a list of views, several frames per launch (volumerender._render_sequence_batched) with the
+    device calls stubbed out: the first launch takes half a batch (from 4 frames per launch up), every later one a whole
+    batch; two launches are in flight before the first frame is handed out; frames come back in order with the modelView
+    they were rendered with; a generator is consumed lazily (never more than two launches ahead)."""
+    from spimagine_b200 import VolumeRenderer
+
+    class _Ctx(object):
+        value = 1
+
+    def run(n, batch, half=True):
+        r = _host_only_renderer()
+        r._ctx = _Ctx()
+        r.width, r.height = 4, 3
+        r.output_depth = None
+        r.first_batch_half = half
+
+        class _Lib(object):
+            def spv_sync(self, ctx):
+                return 0
+
+            def spv_set_matrices(self, ctx, invP, invM):
+                return 0
+        r._lib = _Lib()
+        launches, pulled, events = [], [0], []
+
+        def render_batch(Ms, to_host=True):
+            launches.append([float(M[0, 3]) for M in Ms])
+            events.append(("launch", len(launches) - 1, pulled[0]))
+            return len(launches) - 1
+
+        def batch_frames_of(which, copy=None):
+            return [(np.full((3, 4), v, np.float32), np.full((3, 4), -v, np.float32)) for v in launches[which]]
+        r.render_batch, r.batch_frames_of = render_batch, batch_frames_of
+
+        def views():
+            for i in range(n):
+                pulled[0] += 1
+                M = tm.mat4_identity()
+                M[0, 3] = float(i)
+                yield M
+        got = []
+        for f in VolumeRenderer._render_sequence_batched(r, views(), None, batch):
+            got.append((float(f.output[0, 0]), float(f.output_alpha[0, 0]), float(f.modelView[0, 3])))
+            events.append(("frame", len(got) - 1, pulled[0]))
+        return [len(l) for l in launches], got, events
+
+    for n, batch, sizes in ((20, 10, [5, 10, 5]), (23, 7, [4, 7, 7, 5]), (23, 16, [8, 15]), (5, 2, [2, 2, 1]), (3, 10, [3]),
+                            (720, 10, [5] + [10] * 71 + [5]), (0, 10, [])):
+        got_sizes, got, events = run(n, batch)
+        assert got_sizes == sizes, (n, batch, got_sizes)
+        assert got == [(float(i), -float(i), float(i)) for i in range(n)]
+        if len(sizes) >= 2:  # two launches are issued before the first frame is handed out, never more than two ahead
+            first_frame = next(k for k, e in enumerate(events) if e[0] == "frame")
+            assert [e[0] for e in events[:first_frame]] == ["launch", "launch"]
+            for kind, idx, pulled in events:
+                if kind == "frame":
+                    done = sum(sizes[:1 + next(j for j in range(len(sizes)) if sum(sizes[:j + 1]) > idx)])
+                    assert pulled <= done + sizes[min(len(sizes) - 1, 1 + next(j for j in range(len(sizes)) if sum(sizes[:j + 1]) > idx))]
+    assert run(20, 10, half=False)[0] == [10, 10]
