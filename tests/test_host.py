@@ -484,3 +484,73 @@ def test_batched_sequence_launch_schedule():
                     done = sum(sizes[:1 + next(j for j in range(len(sizes)) if sum(sizes[:j + 1]) > idx)])
                     assert pulled <= done + sizes[min(len(sizes) - 1, 1 + next(j for j in range(len(sizes)) if sum(sizes[:j + 1]) > idx))]
     assert run(20, 10, half=False)[0] == [10, 10]
+
+
+def test_iso_sequence_issue_order():
+    """render_sequence(method="iso_surface") with the device calls recorded (volumerender._render_sequence_iso): with
+    output + alpha only, renders run four frames ahead of the frame handed out and read-backs two ahead.  The invariants
+    the device side relies on: a frame is rendered into slot k & 1 only after the read-back of the frame that used the
+    slot before it has been enqueued; a slot's pinned planes are rewritten (read-back of frame k + 2) only after frame k
+    has been handed out and the consumer has come back; frames are handed out in order."""
+    from spimagine_b200 import VolumeRenderer
+
+    class _Ctx(object):
+        value = 1
+
+    def run(n, planes):
+        r = _host_only_renderer()
+        r._ctx = _Ctx()
+        r.width = r.height = 4
+        r.maxVal, r.gamma, r.max_steps = 100., 1., 200
+        r.occ_strength, r.occ_radius, r.occ_n_points = .1, 21, 30
+        r.boxBounds = [-1, 1, -1, 1, -1, 1]
+        r.stackUnits = np.ones(3)
+        r.dataImg = type("D", (), {"shape": (8, 8, 8)})()
+        log, state = [], {"slot": 0, "frame": -1}
+
+        class _Lib(object):
+            def spv_set_matrices(self, ctx, invP, invM):
+                return 0
+
+            def spv_select_slot(self, ctx, slot):
+                state["slot"] = slot
+                return 0
+
+            def spv_render_iso(self, ctx, p):
+                state["frame"] += 1
+                assert state["slot"] == state["frame"] & 1
+                log.append(("render", state["frame"]))
+                return 0
+
+            def spv_read_pinned_async(self, ctx, pl):
+                assert pl == planes
+                k = sum(1 for e in log if e[0] == "copy")
+                assert state["slot"] == k & 1
+                log.append(("copy", k))
+                return 0
+
+            def spv_set_tuning(self, ctx, knob, value):
+                return 0
+
+            def spv_sync(self, ctx):
+                return 0
+        r._lib = _Lib()
+        r._adopt_slot = lambda slot, pl, clear=False: log.append(("adopt", slot))
+        handed = 0
+        for _ in VolumeRenderer._render_sequence_iso(r, (tm.mat4_identity() for _ in range(n)), planes, planes == 2):
+            assert log[-1] == ("adopt", handed & 1)
+            log.append(("frame", handed))
+            handed += 1
+        assert handed == n
+        pos = {e: i for i, e in enumerate(log)}
+        for k in range(n):
+            assert pos[("render", k)] < pos[("copy", k)] < pos[("frame", k)]
+            if k >= 2:
+                assert pos[("copy", k - 2)] < pos[("render", k)]      # the slot's previous frame is on its way out
+                assert pos[("frame", k - 2)] < pos[("copy", k)]       # the pinned planes it sat in have been seen
+        ahead = max(sum(1 for e in log[:pos[("frame", k)]] if e[0] == "render") - k for k in range(n)) if n else 0
+        return ahead
+
+    assert run(12, 2) == 4      # frame k is handed out with frames k .. k + 3 rendered
+    assert run(12, 7) == 3      # whole frames stay three ahead (bound by the host link either way)
+    assert run(1, 2) == 1 and run(3, 2) == 3 and run(0, 2) == 0
