@@ -72,16 +72,22 @@ class TransformData(object):
         """keyframe_model.py:130-170.  Rotation by slerp; zoom, window, gamma, bounds, alphaPow, translate linearly;
         dataPos rounded, slicePos truncated; isBox / isIso / isSlice / sliceDim are taken from the left keyframe."""
         t = f(lam)
-
-        def mix(name):
-            return (1. - t) * getattr(x1, name) + t * getattr(x2, name)
-
-        return cls(quatRot=quaternion_slerp(x1.quatRot, x2.quatRot, t),
-                   zoom=mix("zoom"), dataPos=int(np.round(mix("dataPos"))),
-                   minVal=mix("minVal"), maxVal=mix("maxVal"), gamma=mix("gamma"),
-                   translate=mix("translate"), bounds=mix("bounds"),
-                   isBox=x1.isBox, isIso=x1.isIso, alphaPow=mix("alphaPow"),
-                   isSlice=x1.isSlice, slicePos=int(mix("slicePos")), sliceDim=x1.sliceDim)
+        u = 1. - t
+        # the same expressions as cls(quatRot=..., zoom=(1 - t) * x1.zoom + t * x2.zoom, ...), assigned without the
+        # keyword round trip of the constructor (one TransformData per recorded frame)
+        td = cls.__new__(cls)
+        td.quatRot = quaternion_slerp(x1.quatRot, x2.quatRot, t)
+        td.zoom = u * x1.zoom + t * x2.zoom
+        td.dataPos = int(np.round(u * x1.dataPos + t * x2.dataPos))
+        td.minVal = u * x1.minVal + t * x2.minVal
+        td.maxVal = u * x1.maxVal + t * x2.maxVal
+        td.gamma = u * x1.gamma + t * x2.gamma
+        td.translate = u * x1.translate + t * x2.translate
+        td.bounds = u * x1.bounds + t * x2.bounds
+        td.isBox, td.isIso = x1.isBox, x1.isIso
+        td.alphaPow = u * x1.alphaPow + t * x2.alphaPow
+        td.isSlice, td.slicePos, td.sliceDim = x1.isSlice, int(u * x1.slicePos + t * x2.slicePos), x1.sliceDim
+        return td
 
 
 class KeyFrame(object):
@@ -250,6 +256,11 @@ class KeyFrameDecoder(json.JSONDecoder):
 
 
 # ------------------------------------------------------------------ TransformData -> renderer state
+def _projection_of(isPerspective=True):
+    """the projection TransformModel.setPerspective installs (transform_model.py:303-312): it depends on the mode only"""
+    return mat4_perspective(60., 1., .1, 10) if isPerspective else mat4_ortho(-2., 2., -2., 2., -1.5, 1.5)
+
+
 def camera_of(transformData, isPerspective=True):
     """-> (modelView, projection) exactly as TransformModel hands them to the renderer
     (transform_model.py:262-312: update, setPerspective, getUnscaledModelView; glwidget.py:615-616)."""
@@ -258,11 +269,10 @@ def camera_of(transformData, isPerspective=True):
     if isPerspective:
         cameraZ = 4 * (1 - np.log(zoom) / np.log(2.))
         scaleAll = 1.
-        projection = mat4_perspective(60., 1., .1, 10)
     else:
         cameraZ = 0.
         scaleAll = 2.5 ** (zoom - 1.)
-        projection = mat4_ortho(-2., 2., -2., 2., -1.5, 1.5)
+    projection = _projection_of(isPerspective)
     model = mat4_scale(*[scaleAll] * 3)
     model = np.dot(model, td.quatRot.toRotation4())
     model = np.dot(model, mat4_translate(*td.translate))
@@ -286,10 +296,11 @@ def apply_transform(renderer, transformData, isPerspective=True):
 
 
 def _static_key(td, source, isPerspective):
-    """everything apply_transform / the time-point upload set from a TransformData except the modelView"""
+    """everything apply_transform / the time-point upload set from a TransformData except the modelView (the projection
+    depends on the mode alone, which is the same for every frame of a record loop)"""
     pos = None if source is None else int(np.clip(td.dataPos, 0, len(source) - 1))
     return (pos, float(td.minVal), float(td.maxVal), float(td.gamma), float(td.alphaPow),
-            tuple(float(b) for b in td.bounds), np.asarray(camera_of(td, isPerspective)[1], np.float64).tobytes())
+            tuple(float(b) for b in td.bounds), bool(isPerspective))
 
 
 def keyframe_times(nFrames):

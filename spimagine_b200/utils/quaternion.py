@@ -18,6 +18,14 @@ class Quaternion(object):
         self.data = np.array([w, x, y, z])
 
     @classmethod
+    def _of(cls, data):
+        """The quaternion whose components ARE the 4-vector `data` (a fresh array): what Quaternion(*data) builds,
+        without unpacking the vector and packing it again (the record loop interpolates one per frame)."""
+        q = cls.__new__(cls)
+        q.data = data
+        return q
+
+    @classmethod
     def copy(cls, rhs):
         return cls(*rhs.data)
 
@@ -31,15 +39,15 @@ class Quaternion(object):
         return "Quaternion(%s,%s,%s,%s)" % tuple(self.data)
 
     def __add__(self, q):
-        return Quaternion(*(self.data + q.data))
+        return Quaternion._of(self.data + q.data)
 
     def __sub__(self, q):
-        return Quaternion(*(self.data - q.data))
+        return Quaternion._of(self.data - q.data)
 
     def __mul__(self, q):
         """Hamilton product with a Quaternion, component scaling with a number."""
         if not isinstance(q, Quaternion):
-            return Quaternion(*(q * self.data))
+            return Quaternion._of(np.asarray(q * self.data))
         w1, v1 = self.data[0], self.data[1:]
         w2, v2 = q.data[0], q.data[1:]
         # written out per component so that the rounding matches the reference's expression order
@@ -53,13 +61,15 @@ class Quaternion(object):
         return Quaternion(self.data[0], -self.data[1], -self.data[2], -self.data[3])
 
     def norm(self):
-        return np.linalg.norm(self.data)
+        # np.linalg.norm of a real vector: sqrt(x . x) after a conversion of integer components to float
+        d = self.data if self.data.dtype.kind == "f" else self.data.astype(float)
+        return np.sqrt(d.dot(d))
 
     def dot(self, q):
         return np.inner(self.data, q.data)
 
     def normalize(self):
-        return Quaternion(*(self.data * 1. / self.norm()))
+        return Quaternion._of(self.data * 1. / self.norm())
 
     def toRotation3(self):
         a, b, c, d = self.data
